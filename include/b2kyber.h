@@ -1,0 +1,99 @@
+/* b2kyber.h -- C ABI of the B200 batch group-arithmetic engine (libb2kyber.so).
+ *
+ * This is the drop-in boundary under dedis/kyber's kyber.Group/Point/Scalar and pairing.Suite
+ * (reference: group.go:23-194, pairing/pairing.go:8-20).  The reference has NO batch entry point
+ * and no FFI; every function below names the reference call site(s) whose Go loop / single-op method
+ * it replaces.  A Go adapter (pairing/bls12381/b200, shaped like pairing/bls12381/kilic) binds these
+ * with cgo -- see INTEGRATION.md.
+ *
+ * Conventions
+ *   - all buffers are caller-owned, contiguous, fixed stride; nothing is retained after return
+ *   - scalars: 32 bytes big-endian, canonical (< group order) = mod.Int.MarshalBinary
+ *     (group/mod/int.go:334-349); a scalar >= order yields B2K_ERR_SCALAR_RANGE, like
+ *     mod.Int.UnmarshalBinary (int.go:359-372)
+ *   - operand points: affine coordinates, big-endian canonical field elements, all-zero = infinity
+ *       BLS12-381 G1: x||y            (96 B)     G2: x.c1||x.c0||y.c1||y.c0 (192 B)
+ *       bn254     G1: x||y            (64 B)
+ *   - result points: the reference's MarshalBinary bytes
+ *       BLS12-381 G1: 48 B ZCash compressed (kilic/g1.go:119-124)   G2: 96 B (kilic/g2.go:118-123)
+ *       bn254     G1: 64 B x||y, infinity all-zero (pairing/bn254/point.go:113-132)
+ *   - return value: 0 = ok, negative = B2K_ERR_*; no exceptions, no callbacks
+ *   - a context owns one CUDA stream and its scratch memory; calls on one context are serialised by
+ *     the caller (one context per goroutine/thread), several contexts may be used concurrently
+ *   - there is NO CPU fallback: without a usable sm_100 device b2k_create fails
+ *   - *_dev variants take DEVICE pointers (same layouts) and only enqueue work on the context's
+ *     stream; they exist so a caller that keeps batches resident in HBM pays no PCIe traffic
+ */
+#ifndef B2KYBER_H
+#define B2KYBER_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct b2k_ctx b2k_ctx;
+
+enum {
+  B2K_OK = 0,
+  B2K_ERR_CUDA = -1,          /* a CUDA runtime call failed; see b2k_last_error */
+  B2K_ERR_ARG = -2,           /* null pointer / size out of range */
+  B2K_ERR_SCALAR_RANGE = -3,  /* some scalar >= group order */
+  B2K_ERR_NO_DEVICE = -4,     /* no sm_100 device */
+  B2K_ERR_POINT = -5          /* some operand point is malformed (coordinate >= p or not on curve) */
+};
+
+/* ---- lifetime ------------------------------------------------------------------------------ */
+int b2k_create(int device, b2k_ctx** out);
+void b2k_destroy(b2k_ctx* ctx);
+const char* b2k_last_error(const b2k_ctx* ctx);
+const char* b2k_version(void);
+/* Use an existing CUDA stream (cudaStream_t passed as void*) instead of the context's own. */
+int b2k_set_stream(b2k_ctx* ctx, void* cuda_stream);
+int b2k_synchronize(b2k_ctx* ctx);
+/* Device-side durations (ms, CUDA events on the context's stream) of the stages of the LAST MSM call:
+ * [0] load/convert points  [1] digits+histogram  [2] scan  [3] scatter  [4] bucket accumulate
+ * [5] chunk reduce  [6] window sum  [7] final (Horner + encode)  [8] whole pipeline.
+ * Returns the number of entries written (<= max). Synchronises the stream. */
+int b2k_last_timings(b2k_ctx* ctx, float* ms, int max);
+/* Override the MSM window size (0 = automatic).  Testing / tuning aid. */
+int b2k_set_msm_window(b2k_ctx* ctx, int c);
+/* Number of kernels launched by this context so far. */
+uint64_t b2k_launch_count(const b2k_ctx* ctx);
+
+/* ---- BLS12-381 G1 ------------------------------------------------------------------------------ */
+/* out[i] = scalars[i] * points[i]    -- n independent Point.Mul
+ * replaces: kilic.G1Elt.Mul, pairing/bls12381/kilic/g1.go:110-116 called in loops such as
+ * sign/bdn/mask.go:58-61 and util/test/group.go:118-122 */
+int b2k_bls12381_g1_mul_batch(b2k_ctx* ctx, size_t n, const uint8_t* scalars /*[n][32]*/,
+                              const uint8_t* points /*[n][96]*/, uint8_t* out /*[n][48]*/);
+int b2k_bls12381_g1_mul_batch_dev(b2k_ctx* ctx, size_t n, const void* d_scalars, const void* d_points,
+                                  void* d_out);
+/* Same, but results in OPERAND form (96 B affine x||y, all-zero = infinity): what the adapter keeps
+ * in a G1Elt between operations (MarshalBinary is applied only when bytes are asked for). */
+int b2k_bls12381_g1_mul_batch_affine(b2k_ctx* ctx, size_t n, const uint8_t* scalars, const uint8_t* points,
+                                     uint8_t* out /*[n][96]*/);
+int b2k_bls12381_g1_mul_batch_affine_dev(b2k_ctx* ctx, size_t n, const void* d_scalars, const void* d_points,
+                                         void* d_out);
+/* out = sum_i scalars[i] * points[i]    -- Pippenger MSM
+ * replaces the Mul+Add loops of share.RecoverCommit (share/poly.go:461-473) and
+ * bdn.AggregateSignatures (sign/bdn/bdn.go:126-161) */
+int b2k_bls12381_g1_msm(b2k_ctx* ctx, size_t n, const uint8_t* scalars /*[n][32]*/,
+                        const uint8_t* points /*[n][96]*/, uint8_t* out /*[48]*/);
+int b2k_bls12381_g1_msm_dev(b2k_ctx* ctx, size_t n, const void* d_scalars, const void* d_points,
+                            void* d_out);
+
+/* ---- bn254 G1 (share.RecoverCommit config: t = 1024 over bn254 G1) ------------------------------ */
+/* replaces bn254 curvePoint.Mul, pairing/bn254/curve.go:196-218 */
+int b2k_bn254_g1_mul_batch(b2k_ctx* ctx, size_t n, const uint8_t* scalars /*[n][32]*/,
+                           const uint8_t* points /*[n][64]*/, uint8_t* out /*[n][64]*/);
+int b2k_bn254_g1_msm(b2k_ctx* ctx, size_t n, const uint8_t* scalars /*[n][32]*/,
+                     const uint8_t* points /*[n][64]*/, uint8_t* out /*[64]*/);
+int b2k_bn254_g1_msm_dev(b2k_ctx* ctx, size_t n, const void* d_scalars, const void* d_points, void* d_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2KYBER_H */

@@ -1,0 +1,151 @@
+"""ctypes binding of include/b2kyber.h -- the same C ABI a Go adapter binds with cgo.
+
+There is no CPU fallback: importing this without the built library, or creating an Engine
+without an sm_100 device, raises.
+"""
+from __future__ import annotations
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb2kyber.so")
+
+B2K_OK, ERR_CUDA, ERR_ARG, ERR_SCALAR_RANGE, ERR_NO_DEVICE, ERR_POINT = 0, -1, -2, -3, -4, -5
+
+
+class B2KError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"b2kyber error {code}: {msg}")
+        self.code = code
+
+
+def load_library() -> C.CDLL:
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(f"{LIB_PATH} is missing: build it with `python -m kyber_b200.build` "
+                          "(there is no CPU fallback)")
+    lib = C.CDLL(LIB_PATH)
+    vp, sz, u8p = C.c_void_p, C.c_size_t, C.c_char_p
+    sigs = {
+        "b2k_create": (C.c_int, [C.c_int, C.POINTER(vp)]),
+        "b2k_destroy": (None, [vp]),
+        "b2k_last_error": (C.c_char_p, [vp]),
+        "b2k_version": (C.c_char_p, []),
+        "b2k_set_stream": (C.c_int, [vp, vp]),
+        "b2k_synchronize": (C.c_int, [vp]),
+        "b2k_last_timings": (C.c_int, [vp, C.POINTER(C.c_float), C.c_int]),
+        "b2k_set_msm_window": (C.c_int, [vp, C.c_int]),
+        "b2k_launch_count": (C.c_uint64, [vp]),
+    }
+    host3 = (C.c_int, [vp, sz, vp, vp, vp])
+    for name in HOST_FUNCS + DEV_FUNCS:
+        sigs[name] = host3
+    for name, (res, args) in sigs.items():
+        fn = getattr(lib, name)      # AttributeError here = ABI drift between header and library
+        fn.restype, fn.argtypes = res, args
+    return lib
+
+
+HOST_FUNCS = [
+    "b2k_bls12381_g1_mul_batch", "b2k_bls12381_g1_mul_batch_affine", "b2k_bls12381_g1_msm",
+    "b2k_bn254_g1_mul_batch", "b2k_bn254_g1_msm",
+]
+DEV_FUNCS = [
+    "b2k_bls12381_g1_mul_batch_dev", "b2k_bls12381_g1_mul_batch_affine_dev", "b2k_bls12381_g1_msm_dev",
+    "b2k_bn254_g1_msm_dev",
+]
+
+
+def _buf(b):
+    """bytes-like -> (ctypes pointer, keepalive)."""
+    if isinstance(b, (bytes, bytearray)):
+        arr = (C.c_char * len(b)).from_buffer_copy(b) if isinstance(b, bytes) else (C.c_char * len(b)).from_buffer(b)
+        return C.cast(arr, C.c_void_p), arr
+    if isinstance(b, int):
+        return C.c_void_p(b), None
+    mv = memoryview(b)
+    arr = (C.c_char * mv.nbytes).from_buffer(mv)
+    return C.cast(arr, C.c_void_p), arr
+
+
+class Engine:
+    """One b2k context (one CUDA stream + scratch arena) on one device."""
+
+    def __init__(self, device: int = 0):
+        self.lib = load_library()
+        h = C.c_void_p()
+        rc = self.lib.b2k_create(device, C.byref(h))
+        if rc != 0:
+            raise B2KError(rc, "b2k_create failed (no sm_100 device? there is no CPU fallback)")
+        self.h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.b2k_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int):
+        if rc != 0:
+            raise B2KError(rc, (self.lib.b2k_last_error(self.h) or b"").decode())
+
+    # -- generic calls ---------------------------------------------------------------------------
+    def call_host(self, name: str, n: int, scalars, points, out_len: int) -> bytes:
+        out = bytearray(out_len)
+        ps, k1 = _buf(scalars); pp, k2 = _buf(points); po, k3 = _buf(out)
+        self._check(getattr(self.lib, name)(self.h, n, ps, pp, po))
+        return bytes(out)
+
+    def call_dev(self, name: str, n: int, d_scalars: int, d_points: int, d_out: int):
+        self._check(getattr(self.lib, name)(self.h, n, C.c_void_p(d_scalars), C.c_void_p(d_points), C.c_void_p(d_out)))
+
+    def set_stream(self, cuda_stream: int):
+        self._check(self.lib.b2k_set_stream(self.h, C.c_void_p(cuda_stream)))
+
+    def synchronize(self):
+        self._check(self.lib.b2k_synchronize(self.h))
+
+    def set_msm_window(self, c: int):
+        self._check(self.lib.b2k_set_msm_window(self.h, c))
+
+    def last_timings(self):
+        arr = (C.c_float * 16)()
+        n = self.lib.b2k_last_timings(self.h, arr, 16)
+        if n < 0:
+            self._check(n)
+        return [float(arr[i]) for i in range(n)]
+
+    def launch_count(self) -> int:
+        return int(self.lib.b2k_launch_count(self.h))
+
+    # -- BLS12-381 G1 -----------------------------------------------------------------------------
+    def bls12381_g1_mul_batch(self, scalars: bytes, points: bytes) -> bytes:
+        n = len(scalars) // 32
+        assert len(scalars) == 32 * n and len(points) == 96 * n
+        return self.call_host("b2k_bls12381_g1_mul_batch", n, scalars, points, 48 * n)
+
+    def bls12381_g1_mul_batch_affine(self, scalars: bytes, points: bytes) -> bytes:
+        n = len(scalars) // 32
+        assert len(scalars) == 32 * n and len(points) == 96 * n
+        return self.call_host("b2k_bls12381_g1_mul_batch_affine", n, scalars, points, 96 * n)
+
+    def bls12381_g1_msm(self, scalars: bytes, points: bytes) -> bytes:
+        n = len(scalars) // 32
+        assert len(scalars) == 32 * n and len(points) == 96 * n
+        return self.call_host("b2k_bls12381_g1_msm", n, scalars, points, 48)
+
+    # -- bn254 G1 ---------------------------------------------------------------------------------
+    def bn254_g1_mul_batch(self, scalars: bytes, points: bytes) -> bytes:
+        n = len(scalars) // 32
+        assert len(scalars) == 32 * n and len(points) == 64 * n
+        return self.call_host("b2k_bn254_g1_mul_batch", n, scalars, points, 64 * n)
+
+    def bn254_g1_msm(self, scalars: bytes, points: bytes) -> bytes:
+        n = len(scalars) // 32
+        assert len(scalars) == 32 * n and len(points) == 64 * n
+        return self.call_host("b2k_bn254_g1_msm", n, scalars, points, 64)

@@ -1,0 +1,342 @@
+// b2k_api.cu -- the C ABI of include/b2kyber.h: context, scratch arena, stage timing, launches.
+// Host side is plumbing only; every arithmetic step runs in the sm_100a kernels of kernels.cuh.
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <new>
+
+#include "../../include/b2kyber.h"
+#include "kernels.cuh"
+
+using namespace b2k;
+
+namespace {
+
+constexpr int N_EV = 10;
+
+struct Arena {
+  char* base = nullptr;
+  size_t cap = 0, used = 0;
+};
+
+}  // namespace
+
+struct b2k_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  Arena arena;
+  uint32_t* d_flags = nullptr;
+  uint32_t* h_flags = nullptr;   // pinned
+  cudaEvent_t ev[N_EV];
+  bool timings_valid = false;
+  int force_c = 0;
+  uint64_t launches = 0;
+  std::string err;
+};
+
+namespace {
+
+#define CK(call)                                                                       \
+  do {                                                                                 \
+    cudaError_t e_ = (call);                                                           \
+    if (e_ != cudaSuccess) {                                                           \
+      ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_);                   \
+      return B2K_ERR_CUDA;                                                             \
+    }                                                                                  \
+  } while (0)
+
+int arena_reserve(b2k_ctx* ctx, size_t bytes) {
+  Arena& a = ctx->arena;
+  a.used = 0;
+  if (bytes <= a.cap) return B2K_OK;
+  if (a.base) {
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaFree(a.base));
+    a.base = nullptr;
+    a.cap = 0;
+  }
+  size_t want = bytes + (bytes >> 3);
+  CK(cudaMalloc(&a.base, want));
+  a.cap = want;
+  return B2K_OK;
+}
+
+template <class T>
+T* arena_take(b2k_ctx* ctx, size_t count) {
+  Arena& a = ctx->arena;
+  size_t off = (a.used + 255) & ~size_t(255);
+  size_t bytes = count * sizeof(T);
+  if (off + bytes > a.cap) return nullptr;
+  a.used = off + bytes;
+  return reinterpret_cast<T*>(a.base + off);
+}
+
+inline size_t pad256(size_t b) { return (b + 255) & ~size_t(255); }
+
+int pick_window(size_t n) {
+  // minimise  W * (10 n + 40 * 2^(c-1))  field multiplications (mixed add ~10, bucket reduce ~40/bucket)
+  int best = 4;
+  double bestc = 1e300;
+  for (int c = 4; c <= 16; c++) {
+    int W = (256 + c - 1) / c;
+    double cost = (double)W * (10.0 * (double)n + 40.0 * (double)(1u << (c - 1)));
+    if (cost < bestc) { bestc = cost; best = c; }
+  }
+  return best;
+}
+
+MsmPlan make_plan(size_t n, int force_c) {
+  MsmPlan pl;
+  pl.c = force_c ? force_c : pick_window(n);
+  pl.W = (256 + pl.c - 1) / pl.c;
+  pl.nb = 1 << (pl.c - 1);
+  size_t total = (size_t)pl.W * pl.nb;
+  int m = 1;
+  while (m < 64 && m * 2 <= pl.nb && total / (size_t)(m * 2) >= 16384) m *= 2;
+  pl.m = m;
+  memset(pl.K, 0, sizeof pl.K);
+  for (int w = 0; w < pl.W; w++) {
+    int bit = pl.c * w + pl.c - 1;
+    pl.K[bit >> 5] |= 1u << (bit & 31);
+  }
+  return pl;
+}
+
+int check_flags(b2k_ctx* ctx) {
+  uint32_t f = *ctx->h_flags;
+  if (f & FLAG_SCALAR_RANGE) { ctx->err = "scalar not below the group order"; return B2K_ERR_SCALAR_RANGE; }
+  if (f & FLAG_POINT) { ctx->err = "malformed operand point"; return B2K_ERR_POINT; }
+  return B2K_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+template <class CV>
+size_t msm_scratch_bytes(size_t n, const MsmPlan& pl) {
+  using F = typename CV::F;
+  size_t total = (size_t)pl.W * pl.nb;
+  size_t T = pl.nb / pl.m;
+  size_t b = 0;
+  b += pad256(n * sizeof(Affine<F>));
+  b += pad256((total + 1) * 4) * 3;               // counts, offs, cursor
+  b += pad256(n * (size_t)pl.W * 4);              // entries
+  b += pad256(total * sizeof(Xyzz<F>));           // buckets
+  b += pad256((size_t)pl.W * T * sizeof(Xyzz<F>));  // partials
+  b += pad256((size_t)pl.W * sizeof(Xyzz<F>));    // window sums
+  return b + 4096;
+}
+
+// Enqueue the whole MSM on ctx->stream. d_scalars/d_points/d_out are device pointers; scratch must
+// already be reserved (arena) for msm_scratch_bytes().
+template <class CV>
+int msm_enqueue(b2k_ctx* ctx, size_t n, const MsmPlan& pl, const uint8_t* d_scalars, const uint8_t* d_points,
+                uint8_t* d_out) {
+  using F = typename CV::F;
+  cudaStream_t st = ctx->stream;
+  size_t total = (size_t)pl.W * pl.nb;
+  int T = pl.nb / pl.m;
+  auto* pts = arena_take<Affine<F>>(ctx, n);
+  auto* counts = arena_take<uint32_t>(ctx, total + 1);
+  auto* offs = arena_take<uint32_t>(ctx, total + 1);
+  auto* cursor = arena_take<uint32_t>(ctx, total + 1);
+  auto* entries = arena_take<uint32_t>(ctx, n * (size_t)pl.W);
+  auto* buckets = arena_take<Xyzz<F>>(ctx, total);
+  auto* partials = arena_take<Xyzz<F>>(ctx, (size_t)pl.W * T);
+  auto* wsum = arena_take<Xyzz<F>>(ctx, pl.W);
+  if (!pts || !counts || !offs || !cursor || !entries || !buckets || !partials || !wsum) {
+    ctx->err = "scratch arena too small";
+    return B2K_ERR_ARG;
+  }
+  unsigned gb_n = (unsigned)((n + 255) / 256);
+  CK(cudaEventRecord(ctx->ev[0], st));
+  CK(cudaMemsetAsync(counts, 0, (total + 1) * 4, st));
+  k_load_points<CV><<<gb_n, 256, 0, st>>>(n, d_points, pts);
+  CK(cudaEventRecord(ctx->ev[1], st));
+  k_msm_count<CV><<<gb_n, 256, 0, st>>>(n, d_scalars, pl, counts, ctx->d_flags);
+  CK(cudaEventRecord(ctx->ev[2], st));
+  k_msm_scan<<<1, 1024, 0, st>>>(total, counts, offs, cursor);
+  CK(cudaEventRecord(ctx->ev[3], st));
+  k_msm_scatter<CV><<<gb_n, 256, 0, st>>>(n, d_scalars, pl, cursor, entries);
+  CK(cudaEventRecord(ctx->ev[4], st));
+  k_msm_accumulate<CV><<<(unsigned)((total + 127) / 128), 128, 0, st>>>(total, pts, offs, entries, buckets);
+  CK(cudaEventRecord(ctx->ev[5], st));
+  size_t nchunks = (size_t)pl.W * T;
+  k_msm_reduce_chunks<CV><<<(unsigned)((nchunks + 127) / 128), 128, 0, st>>>(pl, buckets, partials);
+  CK(cudaEventRecord(ctx->ev[6], st));
+  k_msm_window_sum<CV><<<pl.W, 128, 0, st>>>(T, partials, wsum);
+  CK(cudaEventRecord(ctx->ev[7], st));
+  k_msm_final<CV><<<1, 32, 0, st>>>(pl, wsum, d_out);
+  CK(cudaEventRecord(ctx->ev[8], st));
+  CK(cudaGetLastError());
+  ctx->launches += 8;
+  ctx->timings_valid = true;
+  return B2K_OK;
+}
+
+template <class CV>
+int msm_dev(b2k_ctx* ctx, size_t n, const void* d_scalars, const void* d_points, void* d_out) {
+  if (!ctx || !d_scalars || !d_points || !d_out || n == 0 || n >= (size_t(1) << 31)) {
+    if (ctx) ctx->err = "bad argument";
+    return B2K_ERR_ARG;
+  }
+  CK(cudaSetDevice(ctx->device));
+  MsmPlan pl = make_plan(n, ctx->force_c);
+  int rc = arena_reserve(ctx, msm_scratch_bytes<CV>(n, pl));
+  if (rc) return rc;
+  return msm_enqueue<CV>(ctx, n, pl, (const uint8_t*)d_scalars, (const uint8_t*)d_points, (uint8_t*)d_out);
+}
+
+template <class CV>
+int msm_host(b2k_ctx* ctx, size_t n, const uint8_t* scalars, const uint8_t* points, uint8_t* out) {
+  if (!ctx || !scalars || !points || !out || n == 0 || n >= (size_t(1) << 31)) {
+    if (ctx) ctx->err = "bad argument";
+    return B2K_ERR_ARG;
+  }
+  CK(cudaSetDevice(ctx->device));
+  MsmPlan pl = make_plan(n, ctx->force_c);
+  size_t in_bytes = pad256(n * 32) + pad256(n * (size_t)CV::IN_BYTES) + 256;
+  int rc = arena_reserve(ctx, msm_scratch_bytes<CV>(n, pl) + in_bytes);
+  if (rc) return rc;
+  auto* d_s = arena_take<uint8_t>(ctx, n * 32);
+  auto* d_p = arena_take<uint8_t>(ctx, n * (size_t)CV::IN_BYTES);
+  auto* d_o = arena_take<uint8_t>(ctx, 256);
+  CK(cudaMemsetAsync(ctx->d_flags, 0, 4, ctx->stream));
+  CK(cudaMemcpyAsync(d_s, scalars, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(d_p, points, n * (size_t)CV::IN_BYTES, cudaMemcpyHostToDevice, ctx->stream));
+  rc = msm_enqueue<CV>(ctx, n, pl, d_s, d_p, d_o);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(out, d_o, CV::OUT_BYTES, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->h_flags, ctx->d_flags, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return check_flags(ctx);
+}
+
+template <class CV, bool AFF>
+int mul_batch_dev(b2k_ctx* ctx, size_t n, const void* d_scalars, const void* d_points, void* d_out) {
+  if (!ctx || !d_scalars || !d_points || !d_out || n == 0) {
+    if (ctx) ctx->err = "bad argument";
+    return B2K_ERR_ARG;
+  }
+  CK(cudaSetDevice(ctx->device));
+  k_mul_batch<CV, AFF><<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(
+      n, (const uint8_t*)d_scalars, (const uint8_t*)d_points, (uint8_t*)d_out, ctx->d_flags);
+  CK(cudaGetLastError());
+  ctx->launches += 1;
+  return B2K_OK;
+}
+
+template <class CV, bool AFF>
+int mul_batch_host(b2k_ctx* ctx, size_t n, const uint8_t* scalars, const uint8_t* points, uint8_t* out) {
+  if (!ctx || !scalars || !points || !out || n == 0) {
+    if (ctx) ctx->err = "bad argument";
+    return B2K_ERR_ARG;
+  }
+  CK(cudaSetDevice(ctx->device));
+  const size_t ob = AFF ? (size_t)CV::IN_BYTES : (size_t)CV::OUT_BYTES;
+  size_t bytes = pad256(n * 32) + pad256(n * (size_t)CV::IN_BYTES) + pad256(n * ob) + 1024;
+  int rc = arena_reserve(ctx, bytes);
+  if (rc) return rc;
+  auto* d_s = arena_take<uint8_t>(ctx, n * 32);
+  auto* d_p = arena_take<uint8_t>(ctx, n * (size_t)CV::IN_BYTES);
+  auto* d_o = arena_take<uint8_t>(ctx, n * ob);
+  CK(cudaMemsetAsync(ctx->d_flags, 0, 4, ctx->stream));
+  CK(cudaMemcpyAsync(d_s, scalars, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(d_p, points, n * (size_t)CV::IN_BYTES, cudaMemcpyHostToDevice, ctx->stream));
+  rc = mul_batch_dev<CV, AFF>(ctx, n, d_s, d_p, d_o);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(out, d_o, n * ob, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->h_flags, ctx->d_flags, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return check_flags(ctx);
+}
+
+}  // namespace
+
+// ================================================================================================
+extern "C" {
+
+const char* b2k_version(void) { return "b2kyber 0.1 (sm_100a)"; }
+
+int b2k_create(int device, b2k_ctx** out) {
+  if (!out) return B2K_ERR_ARG;
+  *out = nullptr;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0 || device < 0 || device >= count) return B2K_ERR_NO_DEVICE;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return B2K_ERR_NO_DEVICE;
+  if (prop.major != 10) return B2K_ERR_NO_DEVICE;   // sm_100a code only; no fallback
+  b2k_ctx* ctx = new (std::nothrow) b2k_ctx();
+  if (!ctx) return B2K_ERR_ARG;
+  ctx->device = device;
+  bool ok = cudaSetDevice(device) == cudaSuccess &&
+            cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaMalloc(&ctx->d_flags, 256) == cudaSuccess &&
+            cudaMallocHost(&ctx->h_flags, 256) == cudaSuccess &&
+            cudaMemset(ctx->d_flags, 0, 256) == cudaSuccess;
+  for (int i = 0; ok && i < N_EV; i++) ok = cudaEventCreate(&ctx->ev[i]) == cudaSuccess;
+  if (!ok) { delete ctx; return B2K_ERR_CUDA; }
+  ctx->own_stream = true;
+  *ctx->h_flags = 0;
+  *out = ctx;
+  return B2K_OK;
+}
+
+void b2k_destroy(b2k_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  if (ctx->arena.base) cudaFree(ctx->arena.base);
+  if (ctx->d_flags) cudaFree(ctx->d_flags);
+  if (ctx->h_flags) cudaFreeHost(ctx->h_flags);
+  for (int i = 0; i < N_EV; i++) cudaEventDestroy(ctx->ev[i]);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+const char* b2k_last_error(const b2k_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int b2k_set_stream(b2k_ctx* ctx, void* cuda_stream) {
+  if (!ctx) return B2K_ERR_ARG;
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (ctx->own_stream) { cudaStreamDestroy(ctx->stream); ctx->own_stream = false; }
+  ctx->stream = (cudaStream_t)cuda_stream;
+  return B2K_OK;
+}
+
+int b2k_synchronize(b2k_ctx* ctx) {
+  if (!ctx) return B2K_ERR_ARG;
+  CK(cudaStreamSynchronize(ctx->stream));
+  return B2K_OK;
+}
+
+int b2k_last_timings(b2k_ctx* ctx, float* ms, int max) {
+  if (!ctx || !ms || max <= 0) return B2K_ERR_ARG;
+  if (!ctx->timings_valid) return 0;
+  CK(cudaStreamSynchronize(ctx->stream));
+  int n = 0;
+  for (int i = 0; i < 8 && n < max; i++, n++) CK(cudaEventElapsedTime(&ms[i], ctx->ev[i], ctx->ev[i + 1]));
+  if (n < max) { CK(cudaEventElapsedTime(&ms[8], ctx->ev[0], ctx->ev[8])); n++; }
+  return n;
+}
+
+int b2k_set_msm_window(b2k_ctx* ctx, int c) {
+  if (!ctx || (c != 0 && (c < 4 || c > 16))) return B2K_ERR_ARG;
+  ctx->force_c = c;
+  return B2K_OK;
+}
+
+uint64_t b2k_launch_count(const b2k_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int b2k_bls12381_g1_mul_batch(b2k_ctx* c, size_t n, const uint8_t* s, const uint8_t* p, uint8_t* o) { return mul_batch_host<Bls381G1, false>(c, n, s, p, o); }
+int b2k_bls12381_g1_mul_batch_affine(b2k_ctx* c, size_t n, const uint8_t* s, const uint8_t* p, uint8_t* o) { return mul_batch_host<Bls381G1, true>(c, n, s, p, o); }
+int b2k_bls12381_g1_mul_batch_dev(b2k_ctx* c, size_t n, const void* s, const void* p, void* o) { return mul_batch_dev<Bls381G1, false>(c, n, s, p, o); }
+int b2k_bls12381_g1_mul_batch_affine_dev(b2k_ctx* c, size_t n, const void* s, const void* p, void* o) { return mul_batch_dev<Bls381G1, true>(c, n, s, p, o); }
+int b2k_bls12381_g1_msm(b2k_ctx* c, size_t n, const uint8_t* s, const uint8_t* p, uint8_t* o) { return msm_host<Bls381G1>(c, n, s, p, o); }
+int b2k_bls12381_g1_msm_dev(b2k_ctx* c, size_t n, const void* s, const void* p, void* o) { return msm_dev<Bls381G1>(c, n, s, p, o); }
+
+int b2k_bn254_g1_mul_batch(b2k_ctx* c, size_t n, const uint8_t* s, const uint8_t* p, uint8_t* o) { return mul_batch_host<Bn254G1, false>(c, n, s, p, o); }
+int b2k_bn254_g1_msm(b2k_ctx* c, size_t n, const uint8_t* s, const uint8_t* p, uint8_t* o) { return msm_host<Bn254G1>(c, n, s, p, o); }
+int b2k_bn254_g1_msm_dev(b2k_ctx* c, size_t n, const void* s, const void* p, void* o) { return msm_dev<Bn254G1>(c, n, s, p, o); }
+
+}  // extern "C"

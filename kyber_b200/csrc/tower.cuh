@@ -1,0 +1,269 @@
+// tower.cuh -- Fp2 / Fp6 / Fp12 extension towers over fp.cuh, all limbs in registers / local arrays.
+//
+//   Fp2  = Fp[u]/(u^2+1)                      (both BLS12-381 and bn254: i^2 = -1,
+//                                              reference bn254: pairing/bn254/gfp2.go:82-157)
+//   Fp6  = Fp2[v]/(v^3 - xi)                  xi = 1+u (BLS12-381), 9+u (bn254 gfp2.go:104-126)
+//   Fp12 = Fp6[w]/(w^2 - v)                   (bn254: pairing/bn254/gfp6.go, gfp12.go)
+// A tower config T supplies  typename T::Base (the Fp config) and  mul_xi(Fp2&).
+#pragma once
+#include "fp.cuh"
+
+namespace b2k {
+
+template <class C>
+struct Fp2 {
+  Fp<C> c0, c1;  // c0 + c1*u
+};
+
+template <class C> B2K_D void fp2_add(Fp2<C>& r, const Fp2<C>& a, const Fp2<C>& b) { fp_add(r.c0, a.c0, b.c0); fp_add(r.c1, a.c1, b.c1); }
+template <class C> B2K_D void fp2_sub(Fp2<C>& r, const Fp2<C>& a, const Fp2<C>& b) { fp_sub(r.c0, a.c0, b.c0); fp_sub(r.c1, a.c1, b.c1); }
+template <class C> B2K_D void fp2_neg(Fp2<C>& r, const Fp2<C>& a) { fp_neg(r.c0, a.c0); fp_neg(r.c1, a.c1); }
+template <class C> B2K_D void fp2_conj(Fp2<C>& r, const Fp2<C>& a) { r.c0 = a.c0; fp_neg(r.c1, a.c1); }
+template <class C> B2K_D void fp2_dbl(Fp2<C>& r, const Fp2<C>& a) { fp_add(r.c0, a.c0, a.c0); fp_add(r.c1, a.c1, a.c1); }
+template <class C> B2K_D bool fp2_is_zero(const Fp2<C>& a) { return fp_is_zero(a.c0) && fp_is_zero(a.c1); }
+template <class C> B2K_D bool fp2_eq(const Fp2<C>& a, const Fp2<C>& b) { return fp_eq(a.c0, b.c0) && fp_eq(a.c1, b.c1); }
+template <class C> B2K_D void fp2_set_zero(Fp2<C>& r) { fp_set_zero(r.c0); fp_set_zero(r.c1); }
+template <class C> B2K_D void fp2_set_one(Fp2<C>& r) { fp_set_one(r.c0); fp_set_zero(r.c1); }
+
+// Karatsuba: 3 base multiplications
+template <class C>
+B2K_D void fp2_mul(Fp2<C>& r, const Fp2<C>& a, const Fp2<C>& b) {
+  Fp<C> t0, t1, s0, s1;
+  fp_mul_c(t0, a.c0, b.c0);
+  fp_mul_c(t1, a.c1, b.c1);
+  fp_add(s0, a.c0, a.c1);
+  fp_add(s1, b.c0, b.c1);
+  fp_mul_c(s0, s0, s1);
+  fp_sub(s0, s0, t0);
+  fp_sub(r.c1, s0, t1);
+  fp_sub(r.c0, t0, t1);
+}
+
+// complex squaring: 2 base multiplications
+template <class C>
+B2K_D void fp2_sqr(Fp2<C>& r, const Fp2<C>& a) {
+  Fp<C> s, d, m;
+  fp_add(s, a.c0, a.c1);
+  fp_sub(d, a.c0, a.c1);
+  fp_mul_c(m, a.c0, a.c1);
+  fp_mul_c(r.c0, s, d);
+  fp_add(r.c1, m, m);
+}
+
+template <class C>
+B2K_D void fp2_mul_fp(Fp2<C>& r, const Fp2<C>& a, const Fp<C>& k) { fp_mul_c(r.c0, a.c0, k); fp_mul_c(r.c1, a.c1, k); }
+
+template <class C>
+B2K_NI void fp2_inv(Fp2<C>& r, const Fp2<C>& a) {
+  Fp<C> n, t;
+  fp_sqr_c(n, a.c0);
+  fp_sqr_c(t, a.c1);
+  fp_add(n, n, t);
+  fp_inv(n, n);
+  fp_mul_c(r.c0, a.c0, n);
+  fp_mul_c(t, a.c1, n);
+  fp_neg(r.c1, t);
+}
+
+// ---- uniform "field" vocabulary so curve code is written once for Fp and Fp2 -------------------
+template <class C> B2K_D void f_add(Fp<C>& r, const Fp<C>& a, const Fp<C>& b) { fp_add(r, a, b); }
+template <class C> B2K_D void f_sub(Fp<C>& r, const Fp<C>& a, const Fp<C>& b) { fp_sub(r, a, b); }
+template <class C> B2K_D void f_mul(Fp<C>& r, const Fp<C>& a, const Fp<C>& b) { fp_mul(r, a, b); }
+template <class C> B2K_D void f_sqr(Fp<C>& r, const Fp<C>& a) { fp_sqr(r, a); }
+template <class C> B2K_D void f_neg(Fp<C>& r, const Fp<C>& a) { fp_neg(r, a); }
+template <class C> B2K_D void f_dbl(Fp<C>& r, const Fp<C>& a) { fp_add(r, a, a); }
+template <class C> B2K_D void f_inv(Fp<C>& r, const Fp<C>& a) { fp_inv(r, a); }
+template <class C> B2K_D bool f_is_zero(const Fp<C>& a) { return fp_is_zero(a); }
+template <class C> B2K_D bool f_eq(const Fp<C>& a, const Fp<C>& b) { return fp_eq(a, b); }
+template <class C> B2K_D void f_set_zero(Fp<C>& r) { fp_set_zero(r); }
+template <class C> B2K_D void f_set_one(Fp<C>& r) { fp_set_one(r); }
+
+template <class C> B2K_D void f_add(Fp2<C>& r, const Fp2<C>& a, const Fp2<C>& b) { fp2_add(r, a, b); }
+template <class C> B2K_D void f_sub(Fp2<C>& r, const Fp2<C>& a, const Fp2<C>& b) { fp2_sub(r, a, b); }
+template <class C> B2K_D void f_mul(Fp2<C>& r, const Fp2<C>& a, const Fp2<C>& b) { fp2_mul(r, a, b); }
+template <class C> B2K_D void f_sqr(Fp2<C>& r, const Fp2<C>& a) { fp2_sqr(r, a); }
+template <class C> B2K_D void f_neg(Fp2<C>& r, const Fp2<C>& a) { fp2_neg(r, a); }
+template <class C> B2K_D void f_dbl(Fp2<C>& r, const Fp2<C>& a) { fp2_dbl(r, a); }
+template <class C> B2K_D void f_inv(Fp2<C>& r, const Fp2<C>& a) { fp2_inv(r, a); }
+template <class C> B2K_D bool f_is_zero(const Fp2<C>& a) { return fp2_is_zero(a); }
+template <class C> B2K_D bool f_eq(const Fp2<C>& a, const Fp2<C>& b) { return fp2_eq(a, b); }
+template <class C> B2K_D void f_set_zero(Fp2<C>& r) { fp2_set_zero(r); }
+template <class C> B2K_D void f_set_one(Fp2<C>& r) { fp2_set_one(r); }
+
+// ---- tower configs ------------------------------------------------------------------------------
+struct Bls381Tower {
+  using Base = Bls381Fp;
+  // xi = 1 + u:  (a0 + a1 u)(1 + u) = (a0 - a1) + (a0 + a1) u
+  B2K_D static void mul_xi(Fp2<Base>& r, const Fp2<Base>& a) {
+    Fp<Base> t;
+    fp_sub(t, a.c0, a.c1);
+    fp_add(r.c1, a.c0, a.c1);
+    r.c0 = t;
+  }
+};
+
+struct Bn254Tower {
+  using Base = Bn254Fp;
+  // xi = 9 + u (pairing/bn254/gfp2.go:104-126):  (9 a0 - a1) + (9 a1 + a0) u
+  B2K_D static void mul_xi(Fp2<Base>& r, const Fp2<Base>& a) {
+    Fp<Base> t0, t1, n0, n1;
+    fp_add(t0, a.c0, a.c0); fp_add(t0, t0, t0); fp_add(t0, t0, t0); fp_add(t0, t0, a.c0);  // 9 a0
+    fp_add(t1, a.c1, a.c1); fp_add(t1, t1, t1); fp_add(t1, t1, t1); fp_add(t1, t1, a.c1);  // 9 a1
+    fp_sub(n0, t0, a.c1);
+    fp_add(n1, t1, a.c0);
+    r.c0 = n0; r.c1 = n1;
+  }
+};
+
+// ---- Fp6 ----------------------------------------------------------------------------------------
+template <class T>
+struct Fp6 {
+  Fp2<typename T::Base> c0, c1, c2;  // c0 + c1 v + c2 v^2
+};
+
+template <class T> B2K_D void fp6_add(Fp6<T>& r, const Fp6<T>& a, const Fp6<T>& b) { fp2_add(r.c0, a.c0, b.c0); fp2_add(r.c1, a.c1, b.c1); fp2_add(r.c2, a.c2, b.c2); }
+template <class T> B2K_D void fp6_sub(Fp6<T>& r, const Fp6<T>& a, const Fp6<T>& b) { fp2_sub(r.c0, a.c0, b.c0); fp2_sub(r.c1, a.c1, b.c1); fp2_sub(r.c2, a.c2, b.c2); }
+template <class T> B2K_D void fp6_neg(Fp6<T>& r, const Fp6<T>& a) { fp2_neg(r.c0, a.c0); fp2_neg(r.c1, a.c1); fp2_neg(r.c2, a.c2); }
+template <class T> B2K_D void fp6_set_zero(Fp6<T>& r) { fp2_set_zero(r.c0); fp2_set_zero(r.c1); fp2_set_zero(r.c2); }
+template <class T> B2K_D void fp6_set_one(Fp6<T>& r) { fp2_set_one(r.c0); fp2_set_zero(r.c1); fp2_set_zero(r.c2); }
+template <class T> B2K_D bool fp6_eq(const Fp6<T>& a, const Fp6<T>& b) { return fp2_eq(a.c0, b.c0) && fp2_eq(a.c1, b.c1) && fp2_eq(a.c2, b.c2); }
+
+// multiply by v: (c0,c1,c2) -> (xi*c2, c0, c1)
+template <class T>
+B2K_D void fp6_mul_v(Fp6<T>& r, const Fp6<T>& a) {
+  Fp2<typename T::Base> t;
+  T::mul_xi(t, a.c2);
+  r.c2 = a.c1;
+  r.c1 = a.c0;
+  r.c0 = t;
+}
+
+// Karatsuba/Toom-style: 6 Fp2 multiplications
+template <class T>
+B2K_NI void fp6_mul(Fp6<T>& r, const Fp6<T>& a, const Fp6<T>& b) {
+  using F2 = Fp2<typename T::Base>;
+  F2 v0, v1, v2, t0, t1, t2, s;
+  fp2_mul(v0, a.c0, b.c0);
+  fp2_mul(v1, a.c1, b.c1);
+  fp2_mul(v2, a.c2, b.c2);
+  // c0 = v0 + xi((a1+a2)(b1+b2) - v1 - v2)
+  fp2_add(t0, a.c1, a.c2); fp2_add(s, b.c1, b.c2); fp2_mul(t0, t0, s);
+  fp2_sub(t0, t0, v1); fp2_sub(t0, t0, v2); T::mul_xi(t0, t0); fp2_add(t0, t0, v0);
+  // c1 = (a0+a1)(b0+b1) - v0 - v1 + xi v2
+  fp2_add(t1, a.c0, a.c1); fp2_add(s, b.c0, b.c1); fp2_mul(t1, t1, s);
+  fp2_sub(t1, t1, v0); fp2_sub(t1, t1, v1); T::mul_xi(s, v2); fp2_add(t1, t1, s);
+  // c2 = (a0+a2)(b0+b2) - v0 - v2 + v1
+  fp2_add(t2, a.c0, a.c2); fp2_add(s, b.c0, b.c2); fp2_mul(t2, t2, s);
+  fp2_sub(t2, t2, v0); fp2_sub(t2, t2, v2); fp2_add(t2, t2, v1);
+  r.c0 = t0; r.c1 = t1; r.c2 = t2;
+}
+
+template <class T>
+B2K_D void fp6_sqr(Fp6<T>& r, const Fp6<T>& a) { fp6_mul(r, a, a); }
+
+// multiply by a sparse element (b0, b1, 0): 5 Fp2 multiplications
+template <class T>
+B2K_NI void fp6_mul_by_01(Fp6<T>& r, const Fp6<T>& a, const Fp2<typename T::Base>& b0, const Fp2<typename T::Base>& b1) {
+  using F2 = Fp2<typename T::Base>;
+  F2 v0, v1, t0, t1, t2, s;
+  fp2_mul(v0, a.c0, b0);
+  fp2_mul(v1, a.c1, b1);
+  // c0 = v0 + xi((a1+a2) b1 - v1)
+  fp2_add(t0, a.c1, a.c2); fp2_mul(t0, t0, b1); fp2_sub(t0, t0, v1); T::mul_xi(t0, t0); fp2_add(t0, t0, v0);
+  // c1 = (a0+a1)(b0+b1) - v0 - v1
+  fp2_add(t1, a.c0, a.c1); fp2_add(s, b0, b1); fp2_mul(t1, t1, s); fp2_sub(t1, t1, v0); fp2_sub(t1, t1, v1);
+  // c2 = a2 b0 + v1        ( (a0+a2) b0 - v0 + v1 )
+  fp2_mul(t2, a.c2, b0); fp2_add(t2, t2, v1);
+  r.c0 = t0; r.c1 = t1; r.c2 = t2;
+}
+
+// multiply by a sparse element (0, b1, 0): 3 Fp2 multiplications
+template <class T>
+B2K_NI void fp6_mul_by_1(Fp6<T>& r, const Fp6<T>& a, const Fp2<typename T::Base>& b1) {
+  using F2 = Fp2<typename T::Base>;
+  F2 t0, t1, t2;
+  fp2_mul(t0, a.c2, b1); T::mul_xi(t0, t0);
+  fp2_mul(t1, a.c0, b1);
+  fp2_mul(t2, a.c1, b1);
+  r.c0 = t0; r.c1 = t1; r.c2 = t2;
+}
+
+template <class T>
+B2K_D void fp6_mul_fp2(Fp6<T>& r, const Fp6<T>& a, const Fp2<typename T::Base>& k) {
+  fp2_mul(r.c0, a.c0, k); fp2_mul(r.c1, a.c1, k); fp2_mul(r.c2, a.c2, k);
+}
+
+template <class T>
+B2K_NI void fp6_inv(Fp6<T>& r, const Fp6<T>& a) {
+  using F2 = Fp2<typename T::Base>;
+  F2 t0, t1, t2, s, d;
+  // t0 = a0^2 - xi a1 a2 ; t1 = xi a2^2 - a0 a1 ; t2 = a1^2 - a0 a2
+  fp2_sqr(t0, a.c0); fp2_mul(s, a.c1, a.c2); T::mul_xi(s, s); fp2_sub(t0, t0, s);
+  fp2_sqr(t1, a.c2); T::mul_xi(t1, t1); fp2_mul(s, a.c0, a.c1); fp2_sub(t1, t1, s);
+  fp2_sqr(t2, a.c1); fp2_mul(s, a.c0, a.c2); fp2_sub(t2, t2, s);
+  // d = a0 t0 + xi (a2 t1 + a1 t2)
+  fp2_mul(d, a.c2, t1); fp2_mul(s, a.c1, t2); fp2_add(d, d, s); T::mul_xi(d, d);
+  fp2_mul(s, a.c0, t0); fp2_add(d, d, s);
+  fp2_inv(d, d);
+  fp2_mul(r.c0, t0, d); fp2_mul(r.c1, t1, d); fp2_mul(r.c2, t2, d);
+}
+
+// ---- Fp12 ---------------------------------------------------------------------------------------
+template <class T>
+struct Fp12 {
+  Fp6<T> c0, c1;  // c0 + c1 w
+};
+
+template <class T> B2K_D void fp12_set_one(Fp12<T>& r) { fp6_set_one(r.c0); fp6_set_zero(r.c1); }
+template <class T> B2K_D bool fp12_eq(const Fp12<T>& a, const Fp12<T>& b) { return fp6_eq(a.c0, b.c0) && fp6_eq(a.c1, b.c1); }
+template <class T> B2K_D void fp12_conj(Fp12<T>& r, const Fp12<T>& a) { r.c0 = a.c0; fp6_neg(r.c1, a.c1); }
+template <class T>
+B2K_D bool fp12_is_one(const Fp12<T>& a) {
+  Fp12<T> one;
+  fp12_set_one(one);
+  return fp12_eq(a, one);
+}
+
+template <class T>
+B2K_NI void fp12_mul(Fp12<T>& r, const Fp12<T>& a, const Fp12<T>& b) {
+  Fp6<T> t0, t1, s0, s1;
+  fp6_mul(t0, a.c0, b.c0);
+  fp6_mul(t1, a.c1, b.c1);
+  fp6_add(s0, a.c0, a.c1);
+  fp6_add(s1, b.c0, b.c1);
+  fp6_mul(s0, s0, s1);
+  fp6_sub(s0, s0, t0);
+  fp6_sub(r.c1, s0, t1);
+  fp6_mul_v(t1, t1);
+  fp6_add(r.c0, t0, t1);
+}
+
+// complex squaring: 2 Fp6 multiplications
+template <class T>
+B2K_NI void fp12_sqr(Fp12<T>& r, const Fp12<T>& a) {
+  Fp6<T> ab, s, t;
+  fp6_mul(ab, a.c0, a.c1);
+  fp6_add(s, a.c0, a.c1);
+  fp6_mul_v(t, a.c1);
+  fp6_add(t, t, a.c0);
+  fp6_mul(s, s, t);        // (a0+a1)(a0+v a1) = a0^2 + v a1^2 + (1+v) a0 a1
+  fp6_sub(s, s, ab);
+  fp6_mul_v(t, ab);
+  fp6_sub(r.c0, s, t);
+  fp6_add(r.c1, ab, ab);
+}
+
+template <class T>
+B2K_NI void fp12_inv(Fp12<T>& r, const Fp12<T>& a) {
+  Fp6<T> d, t;
+  fp6_sqr(d, a.c0);
+  fp6_sqr(t, a.c1);
+  fp6_mul_v(t, t);
+  fp6_sub(d, d, t);
+  fp6_inv(d, d);
+  fp6_mul(r.c0, a.c0, d);
+  fp6_mul(t, a.c1, d);
+  fp6_neg(r.c1, t);
+}
+
+}  // namespace b2k

@@ -1,0 +1,93 @@
+// Host emulation of the device limb code (test infrastructure only; never loaded by the product).
+#include "../../kyber_b200/csrc/constants.cuh"
+#include "../../kyber_b200/csrc/fp.cuh"
+using namespace b2k;
+extern "C" {
+#define FIELD_API(name, C)                                                                        \
+  void emul_##name##_mul(const uint32_t* a, const uint32_t* b, uint32_t* r) {                      \
+    Fp<C> x, y, z; for (int i = 0; i < C::N; i++) { x.v[i] = a[i]; y.v[i] = b[i]; }                \
+    fp_mul(z, x, y); for (int i = 0; i < C::N; i++) r[i] = z.v[i]; }                               \
+  void emul_##name##_add(const uint32_t* a, const uint32_t* b, uint32_t* r) {                      \
+    Fp<C> x, y, z; for (int i = 0; i < C::N; i++) { x.v[i] = a[i]; y.v[i] = b[i]; }                \
+    fp_add(z, x, y); for (int i = 0; i < C::N; i++) r[i] = z.v[i]; }                               \
+  void emul_##name##_sub(const uint32_t* a, const uint32_t* b, uint32_t* r) {                      \
+    Fp<C> x, y, z; for (int i = 0; i < C::N; i++) { x.v[i] = a[i]; y.v[i] = b[i]; }                \
+    fp_sub(z, x, y); for (int i = 0; i < C::N; i++) r[i] = z.v[i]; }                               \
+  void emul_##name##_neg(const uint32_t* a, uint32_t* r) {                                         \
+    Fp<C> x, z; for (int i = 0; i < C::N; i++) x.v[i] = a[i];                                      \
+    fp_neg(z, x); for (int i = 0; i < C::N; i++) r[i] = z.v[i]; }                                  \
+  void emul_##name##_inv(const uint32_t* a, uint32_t* r) {                                         \
+    Fp<C> x, z; for (int i = 0; i < C::N; i++) x.v[i] = a[i];                                      \
+    fp_inv(z, x); for (int i = 0; i < C::N; i++) r[i] = z.v[i]; }                                  \
+  void emul_##name##_to_mont(const uint32_t* a, uint32_t* r) {                                     \
+    Fp<C> x, z; for (int i = 0; i < C::N; i++) x.v[i] = a[i];                                      \
+    fp_to_mont(z, x); for (int i = 0; i < C::N; i++) r[i] = z.v[i]; }                              \
+  void emul_##name##_from_mont(const uint32_t* a, uint32_t* r) {                                   \
+    Fp<C> x, z; for (int i = 0; i < C::N; i++) x.v[i] = a[i];                                      \
+    fp_from_mont(z, x); for (int i = 0; i < C::N; i++) r[i] = z.v[i]; }
+FIELD_API(fp381, Bls381Fp)
+FIELD_API(fr381, Bls381Fr)
+FIELD_API(fp254, Bn254Fp)
+}
+
+// ------------------------------------------------------------------------------------------------
+// curve-level emulation: run the per-thread kernel bodies in plain loops
+#include "../../kyber_b200/csrc/msm.cuh"
+#include <vector>
+#include <cstring>
+
+template <class CV>
+static void emul_mul_batch(size_t n, const uint8_t* scalars, const uint8_t* pts, uint8_t* out) {
+  for (size_t i = 0; i < n; i++) {
+    Scalar256 k; scalar_load_be(k, scalars + 32 * i);
+    Affine<typename CV::F> p; CV::load(p, pts + CV::IN_BYTES * i);
+    Jac<typename CV::F> r; scalar_mul<CV>(r, k, p);
+    Affine<typename CV::F> a; jac_to_affine(a, r);
+    CV::store(out + CV::OUT_BYTES * i, a);
+  }
+}
+
+template <class CV>
+static int emul_msm(size_t n, const uint8_t* scalars, const uint8_t* pts, int c, int m, uint8_t* out) {
+  using F = typename CV::F;
+  MsmPlan pl; pl.c = c; pl.W = (256 + c - 1) / c; pl.nb = 1 << (c - 1); pl.m = m;
+  // K = sum_w 2^(c-1) 2^(cw)
+  { unsigned __int128 dummy = 0; (void)dummy;
+    uint32_t K[9] = {0};
+    for (int w = 0; w < pl.W; w++) { int bit = c * w + c - 1; if (bit < 288) K[bit >> 5] |= 1u << (bit & 31); }
+    memcpy(pl.K, K, sizeof K); }
+  std::vector<Affine<F>> P(n);
+  for (size_t i = 0; i < n; i++) CV::load(P[i], pts + CV::IN_BYTES * i);
+  size_t total = (size_t)pl.W * pl.nb;
+  std::vector<uint32_t> counts(total + 1, 0), offs(total + 1, 0);
+  for (size_t i = 0; i < n; i++) {
+    Scalar256 s; scalar_load_be(s, scalars + 32 * i);
+    if (!scalar_in_range<typename CV::ScalarField>(s)) return -3;
+    uint32_t sp[9]; msm_recode(sp, s, pl.K);
+    for (int w = 0; w < pl.W; w++) { int d = msm_digit(sp, c, w); if (d) counts[(size_t)w * pl.nb + (d < 0 ? -d : d) - 1]++; }
+  }
+  for (size_t g = 0; g < total; g++) offs[g + 1] = offs[g] + counts[g];
+  std::vector<uint32_t> cursor(offs.begin(), offs.end()), entries(offs[total]);
+  for (size_t i = 0; i < n; i++) {
+    Scalar256 s; scalar_load_be(s, scalars + 32 * i);
+    uint32_t sp[9]; msm_recode(sp, s, pl.K);
+    for (int w = 0; w < pl.W; w++) { int d = msm_digit(sp, c, w); if (d) { size_t g = (size_t)w * pl.nb + (d < 0 ? -d : d) - 1; entries[cursor[g]++] = (uint32_t)i | (d < 0 ? 0x80000000u : 0); } }
+  }
+  std::vector<Xyzz<F>> B(total);
+  for (size_t g = 0; g < total; g++) msm_accumulate_bucket<CV>(B[g], P.data(), entries.data(), offs[g], offs[g + 1]);
+  int T = pl.nb / m;
+  std::vector<Xyzz<F>> part((size_t)pl.W * T), wsum(pl.W);
+  for (int w = 0; w < pl.W; w++) for (int t = 0; t < T; t++) msm_reduce_chunk<CV>(part[(size_t)w * T + t], &B[(size_t)w * pl.nb], t, m);
+  for (int w = 0; w < pl.W; w++) { Xyzz<F> a; xyzz_set_inf(a); for (int t = 0; t < T; t++) xyzz_add(a, a, part[(size_t)w * T + t]); wsum[w] = a; }
+  Xyzz<F> r; msm_horner<CV>(r, wsum.data(), pl.W, c);
+  Affine<F> a; xyzz_to_affine(a, r);
+  CV::store(out, a);
+  return 0;
+}
+
+extern "C" {
+void emul_bls12381_g1_mul_batch(size_t n, const uint8_t* s, const uint8_t* p, uint8_t* o) { emul_mul_batch<Bls381G1>(n, s, p, o); }
+int emul_bls12381_g1_msm(size_t n, const uint8_t* s, const uint8_t* p, int c, int m, uint8_t* o) { return emul_msm<Bls381G1>(n, s, p, c, m, o); }
+void emul_bn254_g1_mul_batch(size_t n, const uint8_t* s, const uint8_t* p, uint8_t* o) { emul_mul_batch<Bn254G1>(n, s, p, o); }
+int emul_bn254_g1_msm(size_t n, const uint8_t* s, const uint8_t* p, int c, int m, uint8_t* o) { return emul_msm<Bn254G1>(n, s, p, c, m, o); }
+}

@@ -1,0 +1,91 @@
+"""GPU parity: BLS12-381 G1 Point.Mul batches and MSM through the C ABI vs the Python oracle.
+
+Reads like the reference's own group tests (pairing/bls12381/bls12381_test.go:196-418 testGroup,
+util/test/test.go:409-424 CompareGroups): same inputs through two implementations, compare
+MarshalBinary bytes.
+"""
+import random
+
+import pytest
+
+from kyber_b200 import B2KError
+from kyber_b200 import workload as wl
+from oracle import bls12381 as o
+
+pytestmark = pytest.mark.gpu
+
+
+def _rand_points(rng, n):
+    return [o.g1_mul(rng.randrange(1, o.R)) for _ in range(n)]
+
+
+def test_mul_batch_matches_oracle(engine):
+    rng = random.Random(11)
+    n = 40
+    ks = [0, 1, 2, o.R - 1, o.R - 2] + [rng.randrange(o.R) for _ in range(n - 5)]
+    pts = _rand_points(rng, n)
+    pts[7] = None                      # infinity operand
+    out = engine.bls12381_g1_mul_batch(wl.scalars_to_bytes(ks), b"".join(o.g1_to_affine_bytes(p) for p in pts))
+    for i in range(n):
+        assert out[48 * i:48 * i + 48] == o.g1_compress(o.g1_mul(ks[i], pts[i])), i
+
+
+def test_mul_batch_affine_output_roundtrip(engine):
+    rng = random.Random(12)
+    ks = [rng.randrange(o.R) for _ in range(9)] + [0]
+    sb = wl.scalars_to_bytes(ks)
+    out = engine.bls12381_g1_mul_batch_affine(sb, wl.G1_BLS12381_AFFINE * len(ks))
+    for i, k in enumerate(ks):
+        assert out[96 * i:96 * i + 96] == o.g1_to_affine_bytes(o.g1_mul(k)), i
+
+
+def test_scalar_out_of_range_is_rejected(engine):
+    bad = o.R.to_bytes(32, "big")     # == r: mod.Int.UnmarshalBinary rejects (group/mod/int.go:359-372)
+    with pytest.raises(B2KError) as e:
+        engine.bls12381_g1_mul_batch(bad, wl.G1_BLS12381_AFFINE)
+    assert e.value.code == -3
+    with pytest.raises(B2KError) as e:
+        engine.bls12381_g1_msm(bad + (5).to_bytes(32, "big"), wl.G1_BLS12381_AFFINE * 2)
+    assert e.value.code == -3
+
+
+@pytest.mark.parametrize("c", [0, 4, 7, 8, 13, 16])
+def test_msm_small_matches_oracle(engine, c):
+    rng = random.Random(100 + c)
+    n = 37
+    ks = [rng.randrange(o.R) for _ in range(n)]
+    pts = _rand_points(rng, n)
+    # exceptional cases inside one bucket: P+P, P+(-P), infinity operand, zero scalar
+    pts[1], ks[1] = pts[0], ks[0]
+    pts[3], ks[3] = o.g1_neg(pts[2]), ks[2]
+    pts[4] = None
+    ks[5] = 0
+    ks[6] = o.R - 1
+    engine.set_msm_window(c)
+    try:
+        got = engine.bls12381_g1_msm(wl.scalars_to_bytes(ks), b"".join(o.g1_to_affine_bytes(p) for p in pts))
+    finally:
+        engine.set_msm_window(0)
+    assert got == o.g1_compress(o.g1_msm(ks, pts))
+
+
+def test_msm_single_and_all_cancel(engine):
+    k = 0x1234567890ABCDEF
+    p = o.g1_mul(77)
+    assert engine.bls12381_g1_msm(wl.scalars_to_bytes([k]), o.g1_to_affine_bytes(p)) == o.g1_compress(o.g1_mul(k, p))
+    # k*P + (r-k)*P = infinity -> c0 00 .. 00
+    got = engine.bls12381_g1_msm(wl.scalars_to_bytes([k, o.R - k]), o.g1_to_affine_bytes(p) * 2)
+    assert got == o.g1_compress(None)
+
+
+@pytest.mark.parametrize("n", [1000, 1 << 14])
+def test_msm_known_discrete_logs(engine, n):
+    """sum s_i*(a_i*G) == ((sum s_i a_i) mod r)*G  (SURVEY 8c trick (i)); points made by the engine itself,
+    a sample of them re-checked against the oracle."""
+    a = wl.prng_scalars("b2k/test-a", n, o.R)
+    s = wl.prng_scalars("b2k/test-s", n, o.R)
+    pts = engine.bls12381_g1_mul_batch_affine(wl.scalars_to_bytes(a), wl.G1_BLS12381_AFFINE * n)
+    for i in (0, 1, n // 2, n - 1):
+        assert pts[96 * i:96 * i + 96] == o.g1_to_affine_bytes(o.g1_mul(a[i]))
+    got = engine.bls12381_g1_msm(wl.scalars_to_bytes(s), pts)
+    assert got == o.g1_compress(o.g1_mul(wl.dot_mod(s, a, o.R)))
