@@ -1,0 +1,339 @@
+#!/usr/bin/env python3
+"""bench.py -- BLS12-381 G1 scalar-muls/sec through the Pippenger MSM hot path (BASELINE.json configs[1]).
+
+  python bench.py --gpus N --steps K --warmup W            # our arm (sm_100a kernels via the C ABI)
+  python bench.py --impl reference --gpus N --steps K ...  # CPU arm: the reference's algorithm (oracle port)
+
+A "step" is one MSM over one resident batch of 2^20 (scalar, point) pairs per GPU (weak scaling: rank r
+owns pairs [r*n, (r+1)*n) of an N*n-pair MSM; partial sums are exchanged with ONE NCCL all-gather of
+96-byte affine points and added on every rank).  `value` = pairs / device time with inputs resident in
+HBM; `e2e` = the same through b2k_bls12381_g1_msm with pinned HOST buffers (H2D of scalars+points and
+D2H of the result inside the timed region).  Results are checked against the oracle every run
+(sum s_i*(a_i*G) == (sum s_i a_i mod r)*G).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "bls12381_g1_scalar_muls_per_sec"
+UNIT = "scalar-muls/s"
+LOG_N = int(os.environ.get("B2K_BENCH_LOGN", "20"))
+
+
+# ------------------------------------------------------------------------------------------------
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index = index
+        self.rows = []
+        self.stop_flag = False
+        self.proc = None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append(line.strip())
+                if self.stop_flag:
+                    break
+        except Exception:
+            pass
+
+    def finish(self):
+        self.stop_flag = True
+        if self.proc:
+            try:
+                self.proc.terminate()
+            except Exception:
+                pass
+        sm, mx, reasons = [], 0.0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx = max(mx, float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        med = sm[len(sm) // 2] if sm else None
+        return {"sm_mhz": med, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_run(n_sample: int, threads: int, seed_start: int = 0):
+    """Time the oracle's restatement of the reference path (N x Point.Mul + Add, share/poly.go:461-473)
+    and, separately, a CPU Pippenger, on a bounded sample of the same workload."""
+    from kyber_b200 import workload as wl
+    from oracle import cpu_ref
+    from oracle import bls12381 as o
+    lib = cpu_ref.load()
+    s = wl.prng_scalars("b2k/c2", n_sample, wl.R_BLS12381, seed_start)
+    a = wl.prng_scalars("b2k/c2-a", n_sample, wl.R_BLS12381, seed_start)
+    sb = wl.scalars_to_bytes(s)
+    # points a_i*G made by the CPU port itself (fixed-base muls), then affine via the Python oracle
+    comp = cpu_ref.g1_mul_batch(lib, wl.scalars_to_bytes(a), wl.G1_BLS12381_AFFINE * n_sample, threads)
+    pts = b"".join(o.g1_to_affine_bytes(o.g1_decompress(comp[48 * i:48 * i + 48], subgroup_check=False))
+                   for i in range(n_sample))
+    t0 = time.perf_counter()
+    out = cpu_ref.g1_msm_muladd(lib, sb, pts, threads)
+    t_muladd = time.perf_counter() - t0
+    expect = o.g1_compress(o.g1_mul(wl.dot_mod(s, a, o.R)))
+    assert out == expect, "CPU reference arm produced a wrong MSM"
+    t0 = time.perf_counter()
+    out2 = cpu_ref.g1_msm_pippenger(lib, sb, pts, threads)
+    t_pip = time.perf_counter() - t0
+    assert out2 == expect
+    return {"value": n_sample / t_muladd, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"{n_sample} pairs of the 2^{LOG_N} workload: Mul+Add loop (the reference's algorithm, "
+                      f"share/poly.go:461-473) on {threads} threads, {t_muladd:.2f} s; oracle/cpu_ref.c "
+                      "(C restatement, NOT the Go reference: no Go toolchain on this image)",
+            "pippenger_value": n_sample / t_pip,
+            "pippenger_note": "same sample through a multi-threaded CPU Pippenger (a stronger baseline than the "
+                              "reference, which has no MSM)"}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    threads = os.cpu_count() or 1
+    n_sample = int(os.environ.get("B2K_REF_SAMPLE", str(max(2048, 192 * threads))))
+    vals = []
+    last = None
+    for i in range(args.warmup + args.steps):
+        last = cpu_reference_run(n_sample, threads, seed_start=i * n_sample)
+        if i >= args.warmup:
+            vals.append(last["value"])
+    v = sum(vals) / len(vals)
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * n_sample / v,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
+            "data": "synthetic",
+            "config": {"workload": f"BLS12-381 G1 MSM, 2^{LOG_N} random (scalar,point) pairs per GPU",
+                       "step": f"bounded sample of {n_sample} pairs"},
+            "cpu_baseline": dict(last, value=v),
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from kyber_b200 import Engine, workload as wl
+    from oracle import bls12381 as o
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run --nproc-per-node N for --gpus N")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    n = 1 << LOG_N
+    eng = Engine(local)
+    stream = torch.cuda.current_stream()
+    eng.set_stream(stream.cuda_stream)
+
+    # ---- synthetic inputs (seed b2k/c2; rank r owns counters [r*n, (r+1)*n)) --------------------
+    a = wl.prng_scalars("b2k/c2-a", n, wl.R_BLS12381, rank * n)
+    s = wl.prng_scalars("b2k/c2", n, wl.R_BLS12381, rank * n)
+    sb = wl.scalars_to_bytes(s)
+    h_scal = torch.frombuffer(bytearray(sb), dtype=torch.uint8).pin_memory()
+    h_a = torch.frombuffer(bytearray(wl.scalars_to_bytes(a)), dtype=torch.uint8)
+    d_a = h_a.to(dev)
+    d_gen = torch.frombuffer(bytearray(wl.G1_BLS12381_AFFINE), dtype=torch.uint8).to(dev).repeat(n)
+    d_pts = torch.empty(n * 96, dtype=torch.uint8, device=dev)
+    eng.call_dev("b2k_bls12381_g1_mul_batch_affine_dev", n, d_a.data_ptr(), d_gen.data_ptr(), d_pts.data_ptr())
+    torch.cuda.synchronize()
+    del d_gen, d_a
+    h_pts = d_pts.cpu().pin_memory()
+    # sample-check the generated points against the oracle
+    for i in (0, n // 3, n - 1):
+        assert bytes(h_pts[96 * i:96 * i + 96].tolist()) == o.g1_to_affine_bytes(o.g1_mul(a[i])), "bad input point"
+    d_scal = h_scal.to(dev)
+    d_out = torch.zeros(96, dtype=torch.uint8, device=dev)
+    d_gather = torch.zeros(world * 96, dtype=torch.uint8, device=dev)
+    d_ones = torch.frombuffer(bytearray(b"".join((1).to_bytes(32, "big") for _ in range(world))),
+                              dtype=torch.uint8).to(dev)
+    d_final = torch.zeros(64, dtype=torch.uint8, device=dev)
+    my_dot = wl.dot_mod(s, a, o.R)
+
+    def step_device():
+        """one pass of the hot path, inputs resident in HBM"""
+        if world == 1:
+            eng.call_dev("b2k_bls12381_g1_msm_dev", n, d_scal.data_ptr(), d_pts.data_ptr(), d_final.data_ptr())
+        else:
+            eng.call_dev("b2k_bls12381_g1_msm_affine_dev", n, d_scal.data_ptr(), d_pts.data_ptr(), d_out.data_ptr())
+            dist.all_gather_into_tensor(d_gather, d_out)            # the ONE exchange: world x 96 B
+            eng.call_dev("b2k_bls12381_g1_msm_dev", world, d_ones.data_ptr(), d_gather.data_ptr(), d_final.data_ptr())
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing --------------------------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    launches0 = eng.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    acc_ms = []
+    barrier()
+    ev0.record(stream)
+    for _ in range(args.steps):
+        step_device()
+    ev1.record(stream)
+    barrier()
+    dev_ms = ev0.elapsed_time(ev1)
+    launches = eng.launch_count() - launches0
+    # stage timings of the last MSM (CUDA events recorded on the same stream inside the library)
+    for _ in range(3):
+        eng.call_dev("b2k_bls12381_g1_msm_dev", n, d_scal.data_ptr(), d_pts.data_ptr(), d_final.data_ptr())
+        acc_ms.append(eng.last_timings())
+    barrier()
+    # ---- end-to-end through the host C ABI (pinned host buffers) -----------------------------------
+    hs_ptr, hp_ptr = h_scal.data_ptr(), h_pts.data_ptr()
+    h_res = torch.zeros(64, dtype=torch.uint8).pin_memory()
+
+    def step_e2e():
+        eng._check(eng.lib.b2k_bls12381_g1_msm(eng.h, n, ctypes.c_void_p(hs_ptr), ctypes.c_void_p(hp_ptr),
+                                               ctypes.c_void_p(h_res.data_ptr())))
+
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        step_e2e()
+    e1.record(stream)
+    barrier()
+    e2e_ms = e0.elapsed_time(e1)
+    clocks = sampler.finish() if rank == 0 else None
+
+    # ---- correctness of what was timed ---------------------------------------------------------------
+    got_e2e = bytes(h_res[:48].tolist())
+    assert got_e2e == o.g1_compress(o.g1_mul(my_dot)), "e2e MSM result differs from the oracle"
+    step_device()
+    barrier()
+    got = bytes(d_final[:48].cpu().tolist())
+    if world > 1:
+        dots = [None] * world
+        dist.all_gather_object(dots, my_dot)
+        total_dot = sum(dots) % o.R
+    else:
+        total_dot = my_dot
+    assert got == o.g1_compress(o.g1_mul(total_dot)), "device MSM result differs from the oracle"
+
+    # ---- max over ranks ---------------------------------------------------------------------------------
+    t = torch.tensor([dev_ms, e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_ms = float(t[0]), float(t[1])
+
+    if rank == 0:
+        ms_step = dev_ms / args.steps
+        value = world * n / (ms_step * 1e-3)
+        e2e_value = world * n / (e2e_ms / args.steps * 1e-3)
+        tm = [sum(x[i] for x in acc_ms) / len(acc_ms) for i in range(len(acc_ms[0]))]
+        c_bits = 16 if LOG_N >= 18 else None
+        peak, peak_src = load_peaks()
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+                "config": {"workload": f"BLS12-381 G1 MSM, 2^{LOG_N} random (scalar,point) pairs per GPU "
+                                       "(BASELINE.json configs[1]); seed b2k/c2",
+                           "pairs_per_gpu": n, "parallelism": f"shard{world}" if world > 1 else "single",
+                           "l2": "no flush: each step streams >400 MB (128 MiB inputs + sort + buckets) > 126 MB L2",
+                           "exchange": "1 x ncclAllGather of 96 B/rank + add" if world > 1 else "none"},
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * 128, "d2h_bytes_per_step": 52,
+                        "ms_per_step": e2e_ms / args.steps,
+                        "note": "b2k_bls12381_g1_msm with pinned host buffers; per-rank local MSM"},
+                "gpu_launches": int(launches),
+                "clocks": clocks,
+                "stages_ms": dict(zip(["load", "digits_hist", "scan", "scatter", "accumulate", "reduce_chunks",
+                                       "window_sum", "final", "pipeline"], [round(x, 4) for x in tm]))}
+        if c_bits:
+            W = 256 // c_bits
+            alg_bytes = n * W * 100 + W * (1 << (c_bits - 1)) * 144
+            acc = tm[4] * 1e-3
+            traffic = None
+            tp = os.path.join(ROOT, "profiles", "accumulate_traffic.json")
+            if os.path.exists(tp):
+                try:
+                    traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+                except Exception:
+                    traffic = None
+            line["roofline"] = {"bound": "hbm", "kernel": "k_msm_accumulate", "achieved": alg_bytes / acc / 1e9,
+                                "peak": peak, "unit": "GB/s", "frac": alg_bytes / acc / 1e9 / peak,
+                                "traffic": traffic, "peak_source": peak_src,
+                                "algorithmic_bytes": alg_bytes, "kernel_ms": tm[4], "window_bits": c_bits,
+                                "note": "integer-ALU bound kernel (SURVEY.md F9): see DESIGN.md for the IMAD roofline"}
+        if world == 1 and not os.environ.get("B2K_SKIP_CPU_BASELINE"):
+            threads = os.cpu_count() or 1
+            line["cpu_baseline"] = cpu_reference_run(max(2048, 192 * threads), threads)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

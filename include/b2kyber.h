@@ -84,6 +84,9 @@ int b2k_bls12381_g1_msm(b2k_ctx* ctx, size_t n, const uint8_t* scalars /*[n][32]
                         const uint8_t* points /*[n][96]*/, uint8_t* out /*[48]*/);
 int b2k_bls12381_g1_msm_dev(b2k_ctx* ctx, size_t n, const void* d_scalars, const void* d_points,
                             void* d_out);
+/* Same with the sum in OPERAND form (96 B): the partial a rank contributes to a multi-GPU MSM. */
+int b2k_bls12381_g1_msm_affine_dev(b2k_ctx* ctx, size_t n, const void* d_scalars, const void* d_points,
+                                   void* d_out /*[96]*/);
 
 /* ---- bn254 G1 (share.RecoverCommit config: t = 1024 over bn254 G1) ------------------------------ */
 /* replaces bn254 curvePoint.Mul, pairing/bn254/curve.go:196-218 */

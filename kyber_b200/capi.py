@@ -51,7 +51,7 @@ HOST_FUNCS = [
 ]
 DEV_FUNCS = [
     "b2k_bls12381_g1_mul_batch_dev", "b2k_bls12381_g1_mul_batch_affine_dev", "b2k_bls12381_g1_msm_dev",
-    "b2k_bn254_g1_msm_dev",
+    "b2k_bls12381_g1_msm_affine_dev", "b2k_bn254_g1_msm_dev",
 ]
 
 

@@ -131,7 +131,7 @@ size_t msm_scratch_bytes(size_t n, const MsmPlan& pl) {
 // already be reserved (arena) for msm_scratch_bytes().
 template <class CV>
 int msm_enqueue(b2k_ctx* ctx, size_t n, const MsmPlan& pl, const uint8_t* d_scalars, const uint8_t* d_points,
-                uint8_t* d_out) {
+                uint8_t* d_out, int affine_out = 0) {
   using F = typename CV::F;
   cudaStream_t st = ctx->stream;
   size_t total = (size_t)pl.W * pl.nb;
@@ -166,7 +166,7 @@ int msm_enqueue(b2k_ctx* ctx, size_t n, const MsmPlan& pl, const uint8_t* d_scal
   CK(cudaEventRecord(ctx->ev[6], st));
   k_msm_window_sum<CV><<<pl.W, 128, 0, st>>>(T, partials, wsum);
   CK(cudaEventRecord(ctx->ev[7], st));
-  k_msm_final<CV><<<1, 32, 0, st>>>(pl, wsum, d_out);
+  k_msm_final<CV><<<1, 32, 0, st>>>(pl, wsum, d_out, affine_out);
   CK(cudaEventRecord(ctx->ev[8], st));
   CK(cudaGetLastError());
   ctx->launches += 8;
@@ -175,7 +175,7 @@ int msm_enqueue(b2k_ctx* ctx, size_t n, const MsmPlan& pl, const uint8_t* d_scal
 }
 
 template <class CV>
-int msm_dev(b2k_ctx* ctx, size_t n, const void* d_scalars, const void* d_points, void* d_out) {
+int msm_dev(b2k_ctx* ctx, size_t n, const void* d_scalars, const void* d_points, void* d_out, int affine_out = 0) {
   if (!ctx || !d_scalars || !d_points || !d_out || n == 0 || n >= (size_t(1) << 31)) {
     if (ctx) ctx->err = "bad argument";
     return B2K_ERR_ARG;
@@ -184,7 +184,7 @@ int msm_dev(b2k_ctx* ctx, size_t n, const void* d_scalars, const void* d_points,
   MsmPlan pl = make_plan(n, ctx->force_c);
   int rc = arena_reserve(ctx, msm_scratch_bytes<CV>(n, pl));
   if (rc) return rc;
-  return msm_enqueue<CV>(ctx, n, pl, (const uint8_t*)d_scalars, (const uint8_t*)d_points, (uint8_t*)d_out);
+  return msm_enqueue<CV>(ctx, n, pl, (const uint8_t*)d_scalars, (const uint8_t*)d_points, (uint8_t*)d_out, affine_out);
 }
 
 template <class CV>
@@ -334,6 +334,7 @@ int b2k_bls12381_g1_mul_batch_dev(b2k_ctx* c, size_t n, const void* s, const voi
 int b2k_bls12381_g1_mul_batch_affine_dev(b2k_ctx* c, size_t n, const void* s, const void* p, void* o) { return mul_batch_dev<Bls381G1, true>(c, n, s, p, o); }
 int b2k_bls12381_g1_msm(b2k_ctx* c, size_t n, const uint8_t* s, const uint8_t* p, uint8_t* o) { return msm_host<Bls381G1>(c, n, s, p, o); }
 int b2k_bls12381_g1_msm_dev(b2k_ctx* c, size_t n, const void* s, const void* p, void* o) { return msm_dev<Bls381G1>(c, n, s, p, o); }
+int b2k_bls12381_g1_msm_affine_dev(b2k_ctx* c, size_t n, const void* s, const void* p, void* o) { return msm_dev<Bls381G1>(c, n, s, p, o, 1); }
 
 int b2k_bn254_g1_mul_batch(b2k_ctx* c, size_t n, const uint8_t* s, const uint8_t* p, uint8_t* o) { return mul_batch_host<Bn254G1, false>(c, n, s, p, o); }
 int b2k_bn254_g1_msm(b2k_ctx* c, size_t n, const uint8_t* s, const uint8_t* p, uint8_t* o) { return msm_host<Bn254G1>(c, n, s, p, o); }

@@ -156,13 +156,15 @@ __global__ void __launch_bounds__(128) k_msm_window_sum(int T, const Xyzz<typena
 
 // ---- MSM stage 7: Horner over windows, affine, wire bytes ------------------------------------------
 template <class CV>
-__global__ void k_msm_final(MsmPlan pl, const Xyzz<typename CV::F>* __restrict__ wsum, uint8_t* __restrict__ out) {
+__global__ void k_msm_final(MsmPlan pl, const Xyzz<typename CV::F>* __restrict__ wsum, uint8_t* __restrict__ out,
+                            int affine_out) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   Xyzz<typename CV::F> r;
   msm_horner<CV>(r, wsum, pl.W, pl.c);
   Affine<typename CV::F> a;
   xyzz_to_affine(a, r);
-  CV::store(out, a);
+  if (affine_out) CV::store_affine(out, a);
+  else CV::store(out, a);
 }
 
 }  // namespace b2k

@@ -1,0 +1,58 @@
+#!/usr/bin/env python3
+"""Extract the reference's own fixtures for this path into tests/golden/*.json.
+
+Run in the build container (needs /root/reference); the JSON files are committed so that tests on the
+GPU box, which has no /root/reference, can use them.  Only DATA (hex strings, accept/reject flags) is
+extracted -- no reference code.
+Sources:
+  pairing/bls12381/deserialization_tests/G1/*.yaml, G2/*.yaml   (ZCash-format accept/reject vectors,
+      driven in the reference by pairing/bls12381/bls12381_test.go:74-186)
+  pairing/bls12381/kilic/suite_test.go:17-72                     (drand signature KATs)
+  pairing/bls12381/bls12381_test.go:877-904                      (TestSignatureEdgeCase)
+"""
+import glob
+import json
+import os
+import re
+
+REF = "/root/reference"
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def yaml_vectors(group, key):
+    out = []
+    for path in sorted(glob.glob(f"{REF}/pairing/bls12381/deserialization_tests/{group}/*.yaml")):
+        txt = open(path).read()
+        m = re.search(key + r":\s*'?\"?([0-9a-fA-Fx]*)'?\"?\s*}", txt)
+        hexstr = m.group(1)
+        valid = re.search(r"output:\s*(\S+)", txt).group(1)
+        out.append({"name": os.path.basename(path)[:-5], "input": hexstr, "valid": valid != "null"})
+    return out
+
+
+def go_bytes(src, var):
+    m = re.search(var + r"\s*:=\s*\[\]byte\{([^}]*)\}", src)
+    return bytes(int(x, 16) for x in re.findall(r"0x([0-9a-fA-F]+)", m.group(1))).hex()
+
+
+def main():
+    json.dump({"G1": yaml_vectors("G1", "pubkey"), "G2": yaml_vectors("G2", "signature")},
+              open(os.path.join(HERE, "bls12381_deserialization.json"), "w"), indent=1)
+    st = open(f"{REF}/pairing/bls12381/kilic/suite_test.go").read()
+    t = open(f"{REF}/pairing/bls12381/bls12381_test.go").read()
+    strs = re.findall(r'(\w+)\s*:=\s*"([0-9a-f]{64,})"', st)
+    kat = {
+        "sig_on_g1_g2domain": {"pk_g2": strs[0][1], "sig_g1": strs[1][1], "round": 1,
+                               "note": "kilic/suite_test.go:17-46: msg = sha256(u64be(round)); verifies ONLY with the G2 DST "
+                                       "used for hashing to G1"},
+        "sig_on_g2": {"pk_g1": strs[2][1], "sig_g2": strs[3][1], "prev_sig": strs[4][1], "round": 1,
+                      "note": "kilic/suite_test.go:48-72: msg = sha256(prev_sig || u64be(round)), default G2 DST"},
+        "edge_case_g1": {"pk_g2": go_bytes(t, "publicBytes"), "msg": go_bytes(t, "message"), "sig_g1": go_bytes(t, "sig"),
+                         "note": "bls12381_test.go:877-904 TestSignatureEdgeCase: sigs on G1, default G1 DST"},
+    }
+    json.dump(kat, open(os.path.join(HERE, "bls12381_signature_kats.json"), "w"), indent=1)
+    print("wrote golden fixtures")
+
+
+if __name__ == "__main__":
+    main()

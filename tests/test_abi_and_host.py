@@ -1,0 +1,113 @@
+"""CPU tests: the C-ABI library loads and exports every symbol include/b2kyber.h declares (no compute
+calls without a GPU); host-side workload generation; device limb code under host emulation."""
+import ctypes
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from kyber_b200 import build, capi
+    build.build()
+    lib = capi.load_library()
+    hdr = open(os.path.join(ROOT, "include", "b2kyber.h")).read()
+    names = set(re.findall(r"\b(b2k_[a-z0-9_]+)\s*\(", hdr))
+    assert len(names) >= 15
+    for n in sorted(names):
+        assert hasattr(lib, n), f"{n} declared in include/b2kyber.h but not exported"
+    assert b"sm_100a" in lib.b2k_version()
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from kyber_b200 import Engine, B2KError
+    with pytest.raises(B2KError):
+        Engine(0)
+
+
+def test_product_never_imports_the_oracle():
+    for root, _, files in os.walk(os.path.join(ROOT, "kyber_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp")):
+                txt = open(os.path.join(root, f), errors="ignore").read()
+                assert "oracle" not in txt.replace("# oracle-free", ""), f"{f} mentions the oracle"
+
+
+def test_prng_workload_is_deterministic_and_in_range():
+    from kyber_b200 import workload as wl
+    a = wl.prng_scalars("b2k/c2", 64, wl.R_BLS12381)
+    b = wl.prng_scalars("b2k/c2", 32, wl.R_BLS12381, start=32)
+    assert a[32:] == b and all(0 <= x < wl.R_BLS12381 for x in a) and len(set(a)) == 64
+    assert wl.dot_mod([2, 3], [5, 7], 11) == (10 + 21) % 11
+
+
+@pytest.fixture(scope="module")
+def emul():
+    src = os.path.join(ROOT, "tests", "host_emul", "emul.cpp")
+    lib = os.path.join(ROOT, "tests", "host_emul", "libb2k_emul.so")
+    if not os.path.exists(lib) or os.path.getmtime(lib) < max(
+            os.path.getmtime(src), *(os.path.getmtime(os.path.join(ROOT, "kyber_b200", "csrc", f))
+                                     for f in os.listdir(os.path.join(ROOT, "kyber_b200", "csrc")) if f.endswith(".cuh"))):
+        subprocess.run(["g++", "-O2", "-shared", "-fPIC", "-std=c++17", "-DB2K_HOST_EMUL", src, "-o", lib], check=True)
+    return ctypes.CDLL(lib)
+
+
+def test_device_field_code_under_host_emulation(emul):
+    import random
+    rng = random.Random(1)
+    fields = (("fp381", 0x1a0111ea397fe69a4b1ba7b6434bacd764774b84f38512bf6730d2a0f6b0f6241eabfffeb153ffffb9feffffffffaaab, 12),
+              ("fr381", 0x73eda753299d7d483339d80809a1d80553bda402fffe5bfeffffffff00000001, 8),
+              ("fp254", 21888242871839275222246405745257275088696311157297823662689037894645226208583, 8))
+    for name, p, n in fields:
+        R = 1 << (32 * n)
+        Ri = pow(R, -1, p)
+
+        def lim(v):
+            return (ctypes.c_uint32 * n)(*[(v >> (32 * i)) & 0xFFFFFFFF for i in range(n)])
+
+        def val(a):
+            return sum(int(x) << (32 * i) for i, x in enumerate(a))
+
+        vals = [0, 1, p - 1, p - 2, (p - 1) // 2, R % p] + [rng.randrange(p) for _ in range(60)]
+        for _ in range(400):
+            a, b = rng.choice(vals), rng.choice(vals)
+            out = (ctypes.c_uint32 * n)()
+            getattr(emul, f"emul_{name}_mul")(lim(a), lim(b), out)
+            assert val(out) == a * b * Ri % p
+            getattr(emul, f"emul_{name}_add")(lim(a), lim(b), out)
+            assert val(out) == (a + b) % p
+            getattr(emul, f"emul_{name}_sub")(lim(a), lim(b), out)
+            assert val(out) == (a - b) % p
+        for a in vals[:12]:
+            out = (ctypes.c_uint32 * n)()
+            getattr(emul, f"emul_{name}_inv")(lim(a * R % p), out)
+            assert val(out) == (pow(a, -1, p) * R % p if a else 0)
+
+
+def test_device_msm_bodies_under_host_emulation(emul):
+    import random
+    from oracle import bls12381 as o
+    rng = random.Random(2)
+    n = 21
+    ks = [0, 1, o.R - 1] + [rng.randrange(o.R) for _ in range(n - 3)]
+    pts = [o.g1_mul(rng.randrange(1, o.R)) for _ in range(n)]
+    pts[4] = None
+    pts[6], ks[6] = pts[5], ks[5]
+    pts[8], ks[8] = o.g1_neg(pts[7]), ks[7]
+    sb = b"".join(o.scalar_to_bytes(k) for k in ks)
+    pb = b"".join(o.g1_to_affine_bytes(p) for p in pts)
+    out = ctypes.create_string_buffer(48 * n)
+    emul.emul_bls12381_g1_mul_batch(ctypes.c_size_t(n), sb, pb, out)
+    for i in range(n):
+        assert out.raw[48 * i:48 * i + 48] == o.g1_compress(o.g1_mul(ks[i], pts[i]))
+    exp = o.g1_compress(o.g1_msm(ks, pts))
+    for c, m in ((4, 2), (8, 8), (13, 32), (16, 32)):
+        o48 = ctypes.create_string_buffer(48)
+        assert emul.emul_bls12381_g1_msm(ctypes.c_size_t(n), sb, pb, c, m, o48) == 0
+        assert o48.raw == exp, (c, m)

@@ -1,0 +1,121 @@
+"""CPU tests: pin the oracle against the reference's own fixtures (tests/golden, extracted by
+tests/golden/make_golden.py from the reference's test data) and check its algebra.
+
+Mirrors TestZKCryptoVectorsG1Compressed / G2Compressed (pairing/bls12381/bls12381_test.go:74-186) and the
+group / pairing property tests (:196-474, :580-631)."""
+import json
+import os
+import random
+
+import pytest
+
+from oracle import bls12381 as o
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+DESER = json.load(open(os.path.join(GOLD, "bls12381_deserialization.json")))
+
+
+@pytest.mark.parametrize("vec", DESER["G1"], ids=lambda v: v["name"])
+def test_zkcrypto_g1_vectors(vec):
+    try:
+        raw = bytes.fromhex(vec["input"])
+    except ValueError:
+        assert not vec["valid"]
+        return
+    try:
+        pt = o.g1_decompress(raw)
+        ok = True
+    except ValueError:
+        ok = False
+    assert ok == vec["valid"]
+    if ok:
+        assert o.g1_compress(pt) == raw           # canonical re-encoding
+
+
+@pytest.mark.parametrize("vec", DESER["G2"], ids=lambda v: v["name"])
+def test_zkcrypto_g2_vectors(vec):
+    try:
+        raw = bytes.fromhex(vec["input"])
+    except ValueError:
+        assert not vec["valid"]
+        return
+    try:
+        pt = o.g2_decompress(raw)
+        ok = True
+    except ValueError:
+        ok = False
+    assert ok == vec["valid"]
+    if ok:
+        assert o.g2_compress(pt) == raw
+
+
+def test_kat_public_keys_decode_into_the_subgroups():
+    kat = json.load(open(os.path.join(GOLD, "bls12381_signature_kats.json")))
+    assert o.g2_decompress(bytes.fromhex(kat["sig_on_g1_g2domain"]["pk_g2"])) is not None
+    assert o.g1_decompress(bytes.fromhex(kat["sig_on_g1_g2domain"]["sig_g1"])) is not None
+    assert o.g1_decompress(bytes.fromhex(kat["sig_on_g2"]["pk_g1"])) is not None
+    assert o.g2_decompress(bytes.fromhex(kat["sig_on_g2"]["sig_g2"])) is not None
+    assert o.g2_decompress(bytes.fromhex(kat["edge_case_g1"]["pk_g2"])) is not None
+    assert o.g1_decompress(bytes.fromhex(kat["edge_case_g1"]["sig_g1"])) is not None
+
+
+def test_scalar_wire_format():
+    # TestScalarEndianess (bls12381_test.go:41-72): big-endian, scalar 1 ends in 0x01
+    assert o.scalar_to_bytes(1)[-1] == 1 and len(o.scalar_to_bytes(1)) == 32
+    with pytest.raises(ValueError):
+        o.scalar_from_bytes(o.R.to_bytes(32, "big"))
+    assert o.scalar_from_bytes((o.R - 1).to_bytes(32, "big")) == o.R - 1
+
+
+def test_group_laws_g1_g2():
+    rng = random.Random(5)
+    a, b = rng.randrange(o.R), rng.randrange(o.R)
+    for mul, add, neg, gen, comp, dec in (
+            (o.g1_mul, o.g1_add, o.g1_neg, o.G1, o.g1_compress, o.g1_decompress),
+            (o.g2_mul, o.g2_add, o.g2_neg, o.G2, o.g2_compress, o.g2_decompress)):
+        pa, pb = mul(a, gen), mul(b, gen)
+        assert mul(a, pb) == mul(b, pa)                                # DH
+        assert add(pa, pb) == mul((a + b) % o.R, gen)                  # homomorphism
+        assert add(pa, neg(pa)) is None
+        assert mul(o.R, pa) is None
+        assert dec(comp(pa)) == pa and dec(comp(None)) is None         # marshal round trip incl. identity
+
+
+def test_pairing_bilinearity_and_product_identity():
+    rng = random.Random(6)
+    a, b = rng.randrange(1, 1 << 64), rng.randrange(1, 1 << 64)
+    e = o.pairing(o.G1, o.G2)
+    assert e != o.F12_ONE and o.f12_pow(e, o.R) == o.F12_ONE
+    assert o.pairing(o.g1_mul(a), o.g2_mul(b)) == o.f12_pow(e, a * b)
+    # e(aG1,bG2) = e(cG1,G2) e(G1,dG2) with ab = c+d  (bls12381_test.go:580-631)
+    c = rng.randrange(1, a * b)
+    d = a * b - c
+    lhs = o.pairing(o.g1_mul(a), o.g2_mul(b))
+    rhs = o.f12_mul(o.pairing(o.g1_mul(c), o.G2), o.pairing(o.G1, o.g2_mul(d)))
+    assert lhs == rhs
+    assert o.validate_pairing(o.g1_mul(a), o.g2_mul(b), o.g1_mul(a * b % o.R), o.G2)
+    assert not o.validate_pairing(o.g1_mul(a), o.g2_mul(b), o.g1_mul(a * b + 1), o.G2)
+    assert o.pairing(None, o.G2) == o.F12_ONE
+    assert o.gt_from_bytes(o.gt_to_bytes(e)) == e and len(o.gt_to_bytes(e)) == 576
+
+
+def test_c_port_matches_python_oracle():
+    from oracle import cpu_ref
+    lib = cpu_ref.load()
+    rng = random.Random(8)
+    n = 24
+    ks = [0, 1, o.R - 1] + [rng.randrange(o.R) for _ in range(n - 3)]
+    pts = [o.g1_mul(rng.randrange(1, o.R)) for _ in range(n)]
+    pts[3] = None
+    pts[6], ks[6] = pts[5], ks[5]
+    pts[8], ks[8] = o.g1_neg(pts[7]), ks[7]
+    sb = b"".join(o.scalar_to_bytes(k) for k in ks)
+    pb = b"".join(o.g1_to_affine_bytes(p) for p in pts)
+    out = cpu_ref.g1_mul_batch(lib, sb, pb, 2)
+    for i in range(n):
+        assert out[48 * i:48 * i + 48] == o.g1_compress(o.g1_mul(ks[i], pts[i]))
+    exp = o.g1_compress(o.g1_msm(ks, pts))
+    assert cpu_ref.g1_msm_muladd(lib, sb, pb, 3) == exp
+    assert cpu_ref.g1_msm_pippenger(lib, sb, pb, 3) == exp
+    with pytest.raises(ValueError):
+        cpu_ref.g1_mul_batch(lib, o.R.to_bytes(32, "big"), o.g1_to_affine_bytes(o.G1))
