@@ -55,11 +55,16 @@ int b2k_set_stream(b2k_ctx* ctx, void* cuda_stream);
 int b2k_synchronize(b2k_ctx* ctx);
 /* Device-side durations (ms, CUDA events on the context's stream) of the stages of the LAST MSM call:
  * [0] load/convert points  [1] digits+histogram  [2] scan  [3] scatter  [4] bucket accumulate
- * [5] chunk reduce  [6] window sum  [7] final (Horner + encode)  [8] whole pipeline.
+ * [5] chunk reduce  [6] window sum  [7] final (Horner + encode)  [8] whole pipeline
+ * [9] fix-up of buckets cut by slice boundaries ([4] is the accumulate kernel alone).
  * Returns the number of entries written (<= max). Synchronises the stream. */
 int b2k_last_timings(b2k_ctx* ctx, float* ms, int max);
 /* Override the MSM window size (0 = automatic).  Testing / tuning aid. */
 int b2k_set_msm_window(b2k_ctx* ctx, int c);
+/* Slice length of the balanced bucket-accumulate (0 = automatic) and the accumulate variant
+ * (0 = balanced slices [default], 1 = one thread per bucket).  Testing / tuning aids. */
+int b2k_set_msm_slice(b2k_ctx* ctx, int slice_len);
+int b2k_set_msm_variant(b2k_ctx* ctx, int one_thread_per_bucket);
 /* Number of kernels launched by this context so far. */
 uint64_t b2k_launch_count(const b2k_ctx* ctx);
 
@@ -87,6 +92,22 @@ int b2k_bls12381_g1_msm_dev(b2k_ctx* ctx, size_t n, const void* d_scalars, const
 /* Same with the sum in OPERAND form (96 B): the partial a rank contributes to a multi-GPU MSM. */
 int b2k_bls12381_g1_msm_affine_dev(b2k_ctx* ctx, size_t n, const void* d_scalars, const void* d_points,
                                    void* d_out /*[96]*/);
+
+/* ---- BLS12-381 pairings ---------------------------------------------------------------------------- */
+/* gt[i] = e(g1[i], g2[i]); g2 operands are 192 B: x.c1||x.c0||y.c1||y.c0.  GT = 576 B, 12 x 48 B
+ * big-endian, highest tower coefficient first (kilic/gt.go:115-117), exponent exactly (p^12-1)/r.
+ * An infinity operand gives the GT identity.   replaces: kilic.Suite.Pair, kilic/suite.go:70-75
+ * NOTE: GT byte parity with the Go back-ends is UNPINNED (the reference has no GT byte fixture). */
+int b2k_bls12381_pair(b2k_ctx* ctx, size_t n, const uint8_t* g1 /*[n][96]*/, const uint8_t* g2 /*[n][192]*/,
+                      uint8_t* gt /*[n][576]*/);
+int b2k_bls12381_pair_dev(b2k_ctx* ctx, size_t n, const void* d_g1, const void* d_g2, void* d_gt);
+/* ok[i] = ( e(a1[i], a2[i]) == e(b1[i], b2[i]) ) as 1/0 -- one 2-pair Miller loop + one final
+ * exponentiation per element.   replaces: kilic.Suite.ValidatePairing(p1,p2,inv1,inv2),
+ * kilic/suite.go:57-68, as called by bls.Verify (sign/bls/bls.go:82-96). */
+int b2k_bls12381_pairing_check(b2k_ctx* ctx, size_t n, const uint8_t* a1 /*[n][96]*/, const uint8_t* a2 /*[n][192]*/,
+                               const uint8_t* b1 /*[n][96]*/, const uint8_t* b2 /*[n][192]*/, uint8_t* ok /*[n]*/);
+int b2k_bls12381_pairing_check_dev(b2k_ctx* ctx, size_t n, const void* d_a1, const void* d_a2, const void* d_b1,
+                                   const void* d_b2, void* d_ok);
 
 /* ---- bn254 G1 (share.RecoverCommit config: t = 1024 over bn254 G1) ------------------------------ */
 /* replaces bn254 curvePoint.Mul, pairing/bn254/curve.go:196-218 */

@@ -35,7 +35,13 @@ def load_library() -> C.CDLL:
         "b2k_last_timings": (C.c_int, [vp, C.POINTER(C.c_float), C.c_int]),
         "b2k_set_msm_window": (C.c_int, [vp, C.c_int]),
         "b2k_launch_count": (C.c_uint64, [vp]),
+        "b2k_set_msm_slice": (C.c_int, [vp, C.c_int]),
+        "b2k_set_msm_variant": (C.c_int, [vp, C.c_int]),
     }
+    sigs["b2k_bls12381_pair"] = (C.c_int, [vp, sz, vp, vp, vp])
+    sigs["b2k_bls12381_pair_dev"] = (C.c_int, [vp, sz, vp, vp, vp])
+    sigs["b2k_bls12381_pairing_check"] = (C.c_int, [vp, sz, vp, vp, vp, vp, vp])
+    sigs["b2k_bls12381_pairing_check_dev"] = (C.c_int, [vp, sz, vp, vp, vp, vp, vp])
     host3 = (C.c_int, [vp, sz, vp, vp, vp])
     for name in HOST_FUNCS + DEV_FUNCS:
         sigs[name] = host3
@@ -113,6 +119,12 @@ class Engine:
     def set_msm_window(self, c: int):
         self._check(self.lib.b2k_set_msm_window(self.h, c))
 
+    def set_msm_slice(self, L: int):
+        self._check(self.lib.b2k_set_msm_slice(self.h, L))
+
+    def set_msm_variant(self, one_thread_per_bucket: bool):
+        self._check(self.lib.b2k_set_msm_variant(self.h, int(one_thread_per_bucket)))
+
     def last_timings(self):
         arr = (C.c_float * 16)()
         n = self.lib.b2k_last_timings(self.h, arr, 16)
@@ -138,6 +150,20 @@ class Engine:
         n = len(scalars) // 32
         assert len(scalars) == 32 * n and len(points) == 96 * n
         return self.call_host("b2k_bls12381_g1_msm", n, scalars, points, 48)
+
+    # -- BLS12-381 pairings ---------------------------------------------------------------------------
+    def bls12381_pair(self, g1: bytes, g2: bytes) -> bytes:
+        n = len(g1) // 96
+        assert len(g1) == 96 * n and len(g2) == 192 * n
+        return self.call_host("b2k_bls12381_pair", n, g1, g2, 576 * n)
+
+    def bls12381_pairing_check(self, a1: bytes, a2: bytes, b1: bytes, b2: bytes) -> bytes:
+        n = len(a1) // 96
+        assert len(a1) == len(b1) == 96 * n and len(a2) == len(b2) == 192 * n
+        out = bytearray(n)
+        bufs = [_buf(x) for x in (a1, a2, b1, b2, out)]
+        self._check(self.lib.b2k_bls12381_pairing_check(self.h, n, *[b[0] for b in bufs]))
+        return bytes(out)
 
     # -- bn254 G1 ---------------------------------------------------------------------------------
     def bn254_g1_mul_batch(self, scalars: bytes, points: bytes) -> bytes:

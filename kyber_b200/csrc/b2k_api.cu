@@ -11,30 +11,10 @@
 
 using namespace b2k;
 
-namespace {
+#include "b2k_ctx.h"
 
-constexpr int N_EV = 10;
-
-struct Arena {
-  char* base = nullptr;
-  size_t cap = 0, used = 0;
-};
-
-}  // namespace
-
-struct b2k_ctx {
-  int device = 0;
-  cudaStream_t stream = nullptr;
-  bool own_stream = false;
-  Arena arena;
-  uint32_t* d_flags = nullptr;
-  uint32_t* h_flags = nullptr;   // pinned
-  cudaEvent_t ev[N_EV];
-  bool timings_valid = false;
-  int force_c = 0;
-  uint64_t launches = 0;
-  std::string err;
-};
+using Arena = b2k_arena;
+constexpr int N_EV = B2K_N_EV;
 
 namespace {
 
@@ -104,6 +84,24 @@ MsmPlan make_plan(size_t n, int force_c) {
   return pl;
 }
 
+// slice length of the balanced accumulate: 64 additions per thread when there is enough work to fill
+// the chip (>= 128k slices), shorter slices for small problems
+uint32_t slice_len(size_t n, const MsmPlan& pl, int force_L) {
+  if (force_L > 0) return (uint32_t)force_L;
+  size_t e = n * (size_t)pl.W;
+  size_t L = e / 131072;
+  if (L > 64) L = 64;
+  if (L < 4) L = 4;
+  return (uint32_t)L;
+}
+
+}  // namespace
+
+int b2k_arena_reserve(b2k_ctx* ctx, size_t bytes) { return arena_reserve(ctx, bytes); }
+void* b2k_arena_take(b2k_ctx* ctx, size_t bytes) { return arena_take<char>(ctx, bytes); }
+
+namespace {
+
 int check_flags(b2k_ctx* ctx) {
   uint32_t f = *ctx->h_flags;
   if (f & FLAG_SCALAR_RANGE) { ctx->err = "scalar not below the group order"; return B2K_ERR_SCALAR_RANGE; }
@@ -113,7 +111,7 @@ int check_flags(b2k_ctx* ctx) {
 
 // ------------------------------------------------------------------------------------------------
 template <class CV>
-size_t msm_scratch_bytes(size_t n, const MsmPlan& pl) {
+size_t msm_scratch_bytes(size_t n, const MsmPlan& pl, int force_L) {
   using F = typename CV::F;
   size_t total = (size_t)pl.W * pl.nb;
   size_t T = pl.nb / pl.m;
@@ -124,7 +122,10 @@ size_t msm_scratch_bytes(size_t n, const MsmPlan& pl) {
   b += pad256(total * sizeof(Xyzz<F>));           // buckets
   b += pad256((size_t)pl.W * T * sizeof(Xyzz<F>));  // partials
   b += pad256((size_t)pl.W * sizeof(Xyzz<F>));    // window sums
-  return b + 4096;
+  size_t smax = (n * (size_t)pl.W) / (size_t)slice_len(n, pl, force_L) + 2;
+  b += pad256(2 * smax * sizeof(Xyzz<F>));        // slice partials (worst case: smallest automatic L)
+  b += pad256((total + 1) * 4) + pad256(4096);    // big-bucket list, block sums
+  return b + 8192;
 }
 
 // Enqueue the whole MSM on ctx->stream. d_scalars/d_points/d_out are device pointers; scratch must
@@ -148,28 +149,53 @@ int msm_enqueue(b2k_ctx* ctx, size_t n, const MsmPlan& pl, const uint8_t* d_scal
     ctx->err = "scratch arena too small";
     return B2K_ERR_ARG;
   }
+  const uint32_t L = slice_len(n, pl, ctx->force_L);
+  const uint32_t smax = (uint32_t)((n * (size_t)pl.W + L - 1) / L) + 1;
+  auto* spart = arena_take<Xyzz<F>>(ctx, 2 * (size_t)smax);
+  auto* big_list = arena_take<uint32_t>(ctx, total + 1);
+  auto* bsum = arena_take<uint32_t>(ctx, 1024);
+  if (!spart || !big_list || !bsum || total > 1024u * 1024u) {
+    ctx->err = "scratch arena too small / too many buckets";
+    return B2K_ERR_ARG;
+  }
+  uint32_t* big_count = bsum + 1023;      // last word of the block-sum page is never a block sum (<= 1023 blocks used)
   unsigned gb_n = (unsigned)((n + 255) / 256);
+  unsigned sblocks = (unsigned)((total + 1023) / 1024);
+  int nl = 0;
   CK(cudaEventRecord(ctx->ev[0], st));
   CK(cudaMemsetAsync(counts, 0, (total + 1) * 4, st));
-  k_load_points<CV><<<gb_n, 256, 0, st>>>(n, d_points, pts);
+  k_load_points<CV><<<gb_n, 256, 0, st>>>(n, d_points, pts); nl++;
   CK(cudaEventRecord(ctx->ev[1], st));
-  k_msm_count<CV><<<gb_n, 256, 0, st>>>(n, d_scalars, pl, counts, ctx->d_flags);
+  k_msm_count<CV><<<gb_n, 256, 0, st>>>(n, d_scalars, pl, counts, ctx->d_flags); nl++;
   CK(cudaEventRecord(ctx->ev[2], st));
-  k_msm_scan<<<1, 1024, 0, st>>>(total, counts, offs, cursor);
+  k_scan_blocks<<<sblocks, 1024, 0, st>>>((uint32_t)total, counts, offs, bsum);
+  k_scan_tops<<<1, 1024, 0, st>>>(sblocks, (uint32_t)total, bsum, offs);
+  k_scan_finish<<<sblocks, 1024, 0, st>>>((uint32_t)total, bsum, offs, cursor); nl += 3;
   CK(cudaEventRecord(ctx->ev[3], st));
-  k_msm_scatter<CV><<<gb_n, 256, 0, st>>>(n, d_scalars, pl, cursor, entries);
-  CK(cudaEventRecord(ctx->ev[4], st));
-  k_msm_accumulate<CV><<<(unsigned)((total + 127) / 128), 128, 0, st>>>(total, pts, offs, entries, buckets);
+  k_msm_scatter<CV><<<gb_n, 256, 0, st>>>(n, d_scalars, pl, cursor, entries); nl++;
+  if (ctx->use_v1) {
+    CK(cudaEventRecord(ctx->ev[4], st));
+    k_msm_accumulate<CV><<<(unsigned)((total + 127) / 128), 128, 0, st>>>(total, pts, offs, entries, buckets); nl++;
+    CK(cudaEventRecord(ctx->ev[9], st));
+  } else {
+    CK(cudaMemsetAsync(buckets, 0, total * sizeof(Xyzz<F>), st));
+    CK(cudaMemsetAsync(big_count, 0, 4, st));
+    CK(cudaEventRecord(ctx->ev[4], st));
+    k_msm_accumulate_slices<CV><<<(smax + 127) / 128, 128, 0, st>>>(smax, L, (uint32_t)total, pts, offs, entries, buckets, spart); nl++;
+    CK(cudaEventRecord(ctx->ev[9], st));
+    k_msm_fixup<CV><<<(unsigned)((total + 127) / 128), 128, 0, st>>>((uint32_t)total, L, offs, buckets, spart, big_count, big_list);
+    k_msm_fixup_big<CV><<<256, 128, 0, st>>>(L, offs, buckets, spart, big_count, big_list); nl += 2;
+  }
   CK(cudaEventRecord(ctx->ev[5], st));
   size_t nchunks = (size_t)pl.W * T;
-  k_msm_reduce_chunks<CV><<<(unsigned)((nchunks + 127) / 128), 128, 0, st>>>(pl, buckets, partials);
+  k_msm_reduce_chunks<CV><<<(unsigned)((nchunks + 127) / 128), 128, 0, st>>>(pl, buckets, partials); nl++;
   CK(cudaEventRecord(ctx->ev[6], st));
-  k_msm_window_sum<CV><<<pl.W, 128, 0, st>>>(T, partials, wsum);
+  k_msm_window_sum<CV><<<pl.W, 128, 0, st>>>(T, partials, wsum); nl++;
   CK(cudaEventRecord(ctx->ev[7], st));
-  k_msm_final<CV><<<1, 32, 0, st>>>(pl, wsum, d_out, affine_out);
+  k_msm_final<CV><<<1, 128, 0, st>>>(pl, wsum, d_out, affine_out); nl++;
   CK(cudaEventRecord(ctx->ev[8], st));
   CK(cudaGetLastError());
-  ctx->launches += 8;
+  ctx->launches += (uint64_t)nl;
   ctx->timings_valid = true;
   return B2K_OK;
 }
@@ -182,7 +208,7 @@ int msm_dev(b2k_ctx* ctx, size_t n, const void* d_scalars, const void* d_points,
   }
   CK(cudaSetDevice(ctx->device));
   MsmPlan pl = make_plan(n, ctx->force_c);
-  int rc = arena_reserve(ctx, msm_scratch_bytes<CV>(n, pl));
+  int rc = arena_reserve(ctx, msm_scratch_bytes<CV>(n, pl, ctx->force_L));
   if (rc) return rc;
   return msm_enqueue<CV>(ctx, n, pl, (const uint8_t*)d_scalars, (const uint8_t*)d_points, (uint8_t*)d_out, affine_out);
 }
@@ -196,7 +222,7 @@ int msm_host(b2k_ctx* ctx, size_t n, const uint8_t* scalars, const uint8_t* poin
   CK(cudaSetDevice(ctx->device));
   MsmPlan pl = make_plan(n, ctx->force_c);
   size_t in_bytes = pad256(n * 32) + pad256(n * (size_t)CV::IN_BYTES) + 256;
-  int rc = arena_reserve(ctx, msm_scratch_bytes<CV>(n, pl) + in_bytes);
+  int rc = arena_reserve(ctx, msm_scratch_bytes<CV>(n, pl, ctx->force_L) + in_bytes);
   if (rc) return rc;
   auto* d_s = arena_take<uint8_t>(ctx, n * 32);
   auto* d_p = arena_take<uint8_t>(ctx, n * (size_t)CV::IN_BYTES);
@@ -315,8 +341,12 @@ int b2k_last_timings(b2k_ctx* ctx, float* ms, int max) {
   if (!ctx->timings_valid) return 0;
   CK(cudaStreamSynchronize(ctx->stream));
   int n = 0;
-  for (int i = 0; i < 8 && n < max; i++, n++) CK(cudaEventElapsedTime(&ms[i], ctx->ev[i], ctx->ev[i + 1]));
+  for (int i = 0; i < 8 && n < max; i++, n++) {
+    if (i == 4) CK(cudaEventElapsedTime(&ms[i], ctx->ev[4], ctx->ev[9]));
+    else CK(cudaEventElapsedTime(&ms[i], ctx->ev[i], ctx->ev[i + 1]));
+  }
   if (n < max) { CK(cudaEventElapsedTime(&ms[8], ctx->ev[0], ctx->ev[8])); n++; }
+  if (n < max) { CK(cudaEventElapsedTime(&ms[9], ctx->ev[9], ctx->ev[5])); n++; }
   return n;
 }
 
@@ -327,6 +357,18 @@ int b2k_set_msm_window(b2k_ctx* ctx, int c) {
 }
 
 uint64_t b2k_launch_count(const b2k_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int b2k_set_msm_slice(b2k_ctx* ctx, int L) {
+  if (!ctx || L < 0 || L > 4096) return B2K_ERR_ARG;
+  ctx->force_L = L;
+  return B2K_OK;
+}
+
+int b2k_set_msm_variant(b2k_ctx* ctx, int v1) {
+  if (!ctx) return B2K_ERR_ARG;
+  ctx->use_v1 = v1 ? 1 : 0;
+  return B2K_OK;
+}
 
 int b2k_bls12381_g1_mul_batch(b2k_ctx* c, size_t n, const uint8_t* s, const uint8_t* p, uint8_t* o) { return mul_batch_host<Bls381G1, false>(c, n, s, p, o); }
 int b2k_bls12381_g1_mul_batch_affine(b2k_ctx* c, size_t n, const uint8_t* s, const uint8_t* p, uint8_t* o) { return mul_batch_host<Bls381G1, true>(c, n, s, p, o); }

@@ -1,0 +1,33 @@
+// b2k_ctx.h -- private definition of the context shared by the translation units of libb2kyber.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+
+constexpr int B2K_N_EV = 12;
+
+struct b2k_arena {
+  char* base = nullptr;
+  size_t cap = 0, used = 0;
+};
+
+struct b2k_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  b2k_arena arena;
+  uint32_t* d_flags = nullptr;
+  uint32_t* h_flags = nullptr;   // pinned
+  cudaEvent_t ev[B2K_N_EV];
+  bool timings_valid = false;
+  int force_c = 0;
+  int force_L = 0;      // slice length override (0 = automatic)
+  int use_v1 = 0;       // 1 = one-thread-per-bucket accumulate (kept for A/B measurements)
+  uint64_t launches = 0;
+  std::string err;
+};
+
+// scratch arena (defined in b2k_api.cu): reserve resets the arena and grows it if needed;
+// take returns 256-byte aligned sub-buffers or nullptr.
+int b2k_arena_reserve(b2k_ctx* ctx, size_t bytes);
+void* b2k_arena_take(b2k_ctx* ctx, size_t bytes);

@@ -1,0 +1,81 @@
+// b2k_pairing.cu -- C ABI entry points for batched BLS12-381 pairings (separate translation unit so the
+// two large kernel families compile in parallel).
+#include <cuda_runtime.h>
+#include <string>
+#include "../../include/b2kyber.h"
+#include "b2k_ctx.h"
+#include "pairing_kernels.cuh"
+
+using namespace b2k;
+
+#define CK(call)                                                                       \
+  do {                                                                                 \
+    cudaError_t e_ = (call);                                                           \
+    if (e_ != cudaSuccess) {                                                           \
+      ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_);                   \
+      return B2K_ERR_CUDA;                                                             \
+    }                                                                                  \
+  } while (0)
+
+extern "C" {
+
+int b2k_bls12381_pair_dev(b2k_ctx* ctx, size_t n, const void* d_g1, const void* d_g2, void* d_gt) {
+  if (!ctx || !d_g1 || !d_g2 || !d_gt || n == 0) return B2K_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  k_bls_pair<<<(unsigned)((n + 63) / 64), 64, 0, ctx->stream>>>(n, (const uint8_t*)d_g1, (const uint8_t*)d_g2, (uint8_t*)d_gt);
+  CK(cudaGetLastError());
+  ctx->launches += 1;
+  return B2K_OK;
+}
+
+int b2k_bls12381_pair(b2k_ctx* ctx, size_t n, const uint8_t* g1, const uint8_t* g2, uint8_t* gt) {
+  if (!ctx || !g1 || !g2 || !gt || n == 0) return B2K_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  int rc = b2k_arena_reserve(ctx, n * (96 + 192 + 576) + 4096);
+  if (rc) return rc;
+  uint8_t* d1 = (uint8_t*)b2k_arena_take(ctx, n * 96);
+  uint8_t* d2 = (uint8_t*)b2k_arena_take(ctx, n * 192);
+  uint8_t* dg = (uint8_t*)b2k_arena_take(ctx, n * 576);
+  CK(cudaMemcpyAsync(d1, g1, n * 96, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(d2, g2, n * 192, cudaMemcpyHostToDevice, ctx->stream));
+  rc = b2k_bls12381_pair_dev(ctx, n, d1, d2, dg);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(gt, dg, n * 576, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return B2K_OK;
+}
+
+int b2k_bls12381_pairing_check_dev(b2k_ctx* ctx, size_t n, const void* a1, const void* a2, const void* b1,
+                                   const void* b2, void* d_ok) {
+  if (!ctx || !a1 || !a2 || !b1 || !b2 || !d_ok || n == 0) return B2K_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  k_bls_pairing_check<<<(unsigned)((n + 63) / 64), 64, 0, ctx->stream>>>(
+      n, (const uint8_t*)a1, (const uint8_t*)a2, (const uint8_t*)b1, (const uint8_t*)b2, (uint8_t*)d_ok);
+  CK(cudaGetLastError());
+  ctx->launches += 1;
+  return B2K_OK;
+}
+
+int b2k_bls12381_pairing_check(b2k_ctx* ctx, size_t n, const uint8_t* a1, const uint8_t* a2, const uint8_t* b1,
+                               const uint8_t* b2, uint8_t* ok) {
+  if (!ctx || !a1 || !a2 || !b1 || !b2 || !ok || n == 0) return B2K_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  int rc = b2k_arena_reserve(ctx, n * (2 * 96 + 2 * 192 + 1) + 8192);
+  if (rc) return rc;
+  uint8_t* da1 = (uint8_t*)b2k_arena_take(ctx, n * 96);
+  uint8_t* da2 = (uint8_t*)b2k_arena_take(ctx, n * 192);
+  uint8_t* db1 = (uint8_t*)b2k_arena_take(ctx, n * 96);
+  uint8_t* db2 = (uint8_t*)b2k_arena_take(ctx, n * 192);
+  uint8_t* dok = (uint8_t*)b2k_arena_take(ctx, n);
+  CK(cudaMemcpyAsync(da1, a1, n * 96, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(da2, a2, n * 192, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(db1, b1, n * 96, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(db2, b2, n * 192, cudaMemcpyHostToDevice, ctx->stream));
+  rc = b2k_bls12381_pairing_check_dev(ctx, n, da1, da2, db1, db2, dok);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(ok, dok, n, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return B2K_OK;
+}
+
+}  // extern "C"

@@ -55,32 +55,60 @@ __global__ void __launch_bounds__(256) k_msm_count(size_t n, const uint8_t* __re
   }
 }
 
-// ---- MSM stage 2: exclusive scan of the histogram (single block) ---------------------------------
-__global__ void __launch_bounds__(1024) k_msm_scan(size_t total, const uint32_t* __restrict__ counts,
-                                                   uint32_t* __restrict__ offs, uint32_t* __restrict__ cursor) {
+// ---- MSM stage 2: exclusive scan of the histogram (3 small kernels, 1024 elements per block) -------
+// pass A: per-block exclusive scan + block totals
+__global__ void __launch_bounds__(1024) k_scan_blocks(uint32_t total, const uint32_t* __restrict__ counts,
+                                                      uint32_t* __restrict__ offs, uint32_t* __restrict__ bsum) {
+  __shared__ uint32_t wsum[32];
+  uint32_t i = blockIdx.x * 1024u + threadIdx.x;
+  uint32_t v = (i < total) ? counts[i] : 0u;
+  uint32_t x = v;
+  int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    uint32_t y = __shfl_up_sync(0xffffffffu, x, d);
+    if (lane >= d) x += y;
+  }
+  if (lane == 31) wsum[warp] = x;
+  __syncthreads();
+  if (warp == 0) {
+    uint32_t w = wsum[lane], z = w;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      uint32_t y = __shfl_up_sync(0xffffffffu, z, d);
+      if (lane >= d) z += y;
+    }
+    wsum[lane] = z - w;                       // exclusive prefix of warp totals
+    if (lane == 31) bsum[blockIdx.x] = z;     // block total
+  }
+  __syncthreads();
+  if (i < total) offs[i] = x - v + wsum[warp];
+}
+// pass B: exclusive scan of the block totals (<= 1024 blocks), grand total to offs[total]
+__global__ void __launch_bounds__(1024) k_scan_tops(uint32_t nblocks, uint32_t total, uint32_t* __restrict__ bsum,
+                                                    uint32_t* __restrict__ offs) {
   __shared__ uint32_t sm[1024];
   int tid = threadIdx.x;
-  size_t per = (total + 1023) / 1024;
-  size_t b = (size_t)tid * per, e = b + per;
-  if (b > total) b = total;
-  if (e > total) e = total;
-  uint32_t s = 0;
-  for (size_t i = b; i < e; i++) s += counts[i];
-  sm[tid] = s;
+  uint32_t v = ((uint32_t)tid < nblocks) ? bsum[tid] : 0u;
+  sm[tid] = v;
   __syncthreads();
-  for (int d = 1; d < 1024; d <<= 1) {   // Hillis-Steele inclusive scan
-    uint32_t v = (tid >= d) ? sm[tid - d] : 0;
+  for (int d = 1; d < 1024; d <<= 1) {
+    uint32_t y = (tid >= d) ? sm[tid - d] : 0u;
     __syncthreads();
-    sm[tid] += v;
+    sm[tid] += y;
     __syncthreads();
   }
-  uint32_t run = sm[tid] - s;            // exclusive prefix of this thread's slice
-  for (size_t i = b; i < e; i++) {
-    offs[i] = run;
-    cursor[i] = run;
-    run += counts[i];
-  }
+  if ((uint32_t)tid < nblocks) bsum[tid] = sm[tid] - v;
   if (tid == 1023) offs[total] = sm[1023];
+}
+// pass C: add block offsets, duplicate into the scatter cursor
+__global__ void __launch_bounds__(1024) k_scan_finish(uint32_t total, const uint32_t* __restrict__ bsum,
+                                                      uint32_t* __restrict__ offs, uint32_t* __restrict__ cursor) {
+  uint32_t i = blockIdx.x * 1024u + threadIdx.x;
+  if (i >= total) return;
+  uint32_t o = offs[i] + bsum[blockIdx.x];
+  offs[i] = o;
+  cursor[i] = o;
 }
 
 // ---- MSM stage 3: counting-sort scatter ----------------------------------------------------------
@@ -113,6 +141,66 @@ __global__ void __launch_bounds__(128) k_msm_accumulate(size_t total, const Affi
   Xyzz<typename CV::F> acc;
   msm_accumulate_bucket<CV>(acc, pts, entries, offs[g], offs[g + 1]);
   buckets[g] = acc;
+}
+
+// ---- MSM stage 4 (v2): fixed-length slices of the sorted entries (balanced, skew-proof) ------------
+template <class CV>
+__global__ void __launch_bounds__(128) k_msm_accumulate_slices(uint32_t nslices, uint32_t L, uint32_t total,
+                                                               const Affine<typename CV::F>* __restrict__ pts,
+                                                               const uint32_t* __restrict__ offs,
+                                                               const uint32_t* __restrict__ entries,
+                                                               Xyzz<typename CV::F>* __restrict__ buckets,
+                                                               Xyzz<typename CV::F>* __restrict__ spart) {
+  uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= nslices) return;
+  msm_accumulate_slice<CV>(j, L, total, pts, offs, entries, buckets, spart);
+}
+
+// buckets cut by slice boundaries: add their partials (<= 64 serially, larger ones go to a work list)
+template <class CV>
+__global__ void __launch_bounds__(128) k_msm_fixup(uint32_t total, uint32_t L, const uint32_t* __restrict__ offs,
+                                                   Xyzz<typename CV::F>* __restrict__ buckets,
+                                                   const Xyzz<typename CV::F>* __restrict__ spart,
+                                                   uint32_t* __restrict__ big_count, uint32_t* __restrict__ big_list) {
+  uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= total) return;
+  if (msm_fixup_bucket<CV, 64>(g, L, offs, buckets, spart)) big_list[atomicAdd(big_count, 1u)] = g;
+}
+
+// heavily populated buckets (skewed scalars): one block per listed bucket, strided sums + smem tree
+template <class CV>
+__global__ void __launch_bounds__(128) k_msm_fixup_big(uint32_t L, const uint32_t* __restrict__ offs,
+                                                       Xyzz<typename CV::F>* __restrict__ buckets,
+                                                       const Xyzz<typename CV::F>* __restrict__ spart,
+                                                       const uint32_t* __restrict__ big_count,
+                                                       const uint32_t* __restrict__ big_list) {
+  using X = Xyzz<typename CV::F>;
+  __shared__ X sm[128];
+  const int tid = threadIdx.x;
+  const uint32_t nbig = *big_count;
+  for (uint32_t k = blockIdx.x; k < nbig; k += gridDim.x) {
+    uint32_t g = big_list[k];
+    uint32_t s = offs[g], t = offs[g + 1];
+    uint32_t j0 = s / L, j1 = (t - 1) / L;
+    X acc;
+    xyzz_set_inf(acc);
+    for (uint32_t j = j0 + tid; j <= j1; j += 128) {
+      X p = spart[2 * (size_t)j + (j == j0 ? 1 : 0)];
+      xyzz_add(acc, acc, p);
+    }
+    sm[tid] = acc;
+    __syncthreads();
+    for (int h = 64; h > 0; h >>= 1) {
+      if (tid < h) {
+        X a = sm[tid], b = sm[tid + h];
+        xyzz_add(a, a, b);
+        sm[tid] = a;
+      }
+      __syncthreads();
+    }
+    if (tid == 0) buckets[g] = sm[0];
+    __syncthreads();
+  }
 }
 
 // ---- MSM stage 5: per-chunk running sums ---------------------------------------------------------
@@ -155,16 +243,64 @@ __global__ void __launch_bounds__(128) k_msm_window_sum(int T, const Xyzz<typena
 }
 
 // ---- MSM stage 7: Horner over windows, affine, wire bytes ------------------------------------------
+// The 240 doublings of the Horner recombination are a serial chain; a lone thread needs ~1.2 us per
+// field multiplication.  Four warps (one active lane each, so that they issue on different SM
+// sub-partitions) split the independent multiplications of every XYZZ doubling into 3 stages.
 template <class CV>
-__global__ void k_msm_final(MsmPlan pl, const Xyzz<typename CV::F>* __restrict__ wsum, uint8_t* __restrict__ out,
-                            int affine_out) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  Xyzz<typename CV::F> r;
-  msm_horner<CV>(r, wsum, pl.W, pl.c);
-  Affine<typename CV::F> a;
-  xyzz_to_affine(a, r);
-  if (affine_out) CV::store_affine(out, a);
-  else CV::store(out, a);
+__global__ void __launch_bounds__(128) k_msm_final(MsmPlan pl, const Xyzz<typename CV::F>* __restrict__ wsum,
+                                                   uint8_t* __restrict__ out, int affine_out) {
+  using F = typename CV::F;
+  __shared__ Xyzz<F> acc;
+  __shared__ F U, V, Wt, S, M, T, MM, Yt;
+  const int warp = threadIdx.x >> 5;
+  const bool lead = (threadIdx.x & 31) == 0;
+  if (threadIdx.x == 0) acc = wsum[pl.W - 1];
+  __syncthreads();
+  for (int w = pl.W - 2; w >= 0; w--) {
+    for (int i = 0; i < pl.c; i++) {
+      const bool inf = xyzz_is_inf(acc);     // same value in every thread
+      if (!inf) {
+        if (lead) {                          // stage 1:  V = (2Y)^2   |  M = 3 X^2
+          if (warp == 0) { f_dbl(U, acc.Y); f_sqr(V, U); }
+          else if (warp == 1) { F t; f_sqr(t, acc.X); f_dbl(M, t); f_add(M, M, t); }
+        }
+        __syncthreads();
+        if (lead) {                          // stage 2:  W = U V | S = X V | ZZ *= V | MM = M^2
+          if (warp == 0) f_mul(Wt, U, V);
+          else if (warp == 1) f_mul(S, acc.X, V);
+          else if (warp == 2) { F t; f_mul(t, V, acc.ZZ); acc.ZZ = t; }
+          else f_sqr(MM, M);
+        }
+        __syncthreads();
+        if (lead) {                          // stage 3:  T = W Y | ZZZ *= W | X3, M (S - X3)
+          if (warp == 0) f_mul(T, Wt, acc.Y);
+          else if (warp == 1) { F t; f_mul(t, Wt, acc.ZZZ); acc.ZZZ = t; }
+          else if (warp == 2) {
+            F x3, t;
+            f_sub(x3, MM, S); f_sub(x3, x3, S);
+            f_sub(t, S, x3); f_mul(t, M, t);
+            acc.X = x3; Yt = t;
+          }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) f_sub(acc.Y, Yt, T);
+        __syncthreads();
+      }
+    }
+    if (threadIdx.x == 0) {
+      Xyzz<F> t = wsum[w], a = acc;
+      xyzz_add(a, a, t);
+      acc = a;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    Xyzz<F> r = acc;
+    Affine<F> a;
+    xyzz_to_affine(a, r);
+    if (affine_out) CV::store_affine(out, a);
+    else CV::store(out, a);
+  }
 }
 
 }  // namespace b2k

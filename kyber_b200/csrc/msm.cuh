@@ -18,6 +18,7 @@
 // The per-thread bodies below are plain functions of explicit indices so that tests/host_emul can run
 // them on the CPU; the __global__ wrappers live in kernels.cu.
 #pragma once
+#include <stddef.h>
 #include "curves.cuh"
 
 namespace b2k {
@@ -110,6 +111,80 @@ B2K_D void scalar_mul(Jac<typename CV::F>& r, const Scalar256& k, const Affine<t
     }
   }
   r = acc;
+}
+
+}  // namespace b2k
+
+// =================================================================================================
+// v2 accumulate: fixed-length slices of the sorted entry list (perfectly balanced, skew-proof)
+// =================================================================================================
+// The sorted entries are cut into slices of L consecutive entries regardless of bucket boundaries;
+// one thread per slice performs exactly L mixed additions.  A bucket that lies entirely inside a
+// slice is written straight to buckets[]; a bucket cut by a slice boundary gets one partial sum per
+// slice it touches (spart[2*j+0] if it started before slice j, spart[2*j+1] if it starts inside slice
+// j and runs past its end) and msm_fixup_bucket() adds the partials.  Work per thread is independent
+// of the scalar distribution (all-equal scalars, 128-bit BDN coefficients, short top windows ...).
+namespace b2k {
+
+// largest g in [0,total) with offs[g] <= pos   (offs non-decreasing, offs[0] = 0, offs[total] > pos)
+B2K_D uint32_t msm_find_bucket(const uint32_t* offs, uint32_t total, uint32_t pos) {
+  uint32_t lo = 0, hi = total;
+  while (hi - lo > 1) {
+    uint32_t mid = lo + ((hi - lo) >> 1);
+    if (offs[mid] <= pos) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+template <class CV>
+B2K_D void msm_slice_flush(const Xyzz<typename CV::F>& acc, uint32_t g, uint32_t s, uint32_t t, uint32_t j,
+                           uint32_t b, uint32_t e, Xyzz<typename CV::F>* buckets, Xyzz<typename CV::F>* spart) {
+  if (s >= b && t <= e) buckets[g] = acc;
+  else spart[2 * (size_t)j + (s < b ? 0 : 1)] = acc;
+}
+
+template <class CV>
+B2K_D void msm_accumulate_slice(uint32_t j, uint32_t L, uint32_t total, const Affine<typename CV::F>* pts,
+                                const uint32_t* offs, const uint32_t* entries,
+                                Xyzz<typename CV::F>* buckets, Xyzz<typename CV::F>* spart) {
+  const uint32_t E = offs[total];
+  const uint32_t b = j * L;
+  if (b >= E) return;
+  const uint32_t e = (E - b < L) ? E : b + L;
+  uint32_t g = msm_find_bucket(offs, total, b);
+  uint32_t gs = offs[g], ge = offs[g + 1];
+  Xyzz<typename CV::F> acc;
+  xyzz_set_inf(acc);
+  for (uint32_t pos = b; pos < e; pos++) {
+    if (pos == ge) {                       // crossed into a later bucket
+      msm_slice_flush<CV>(acc, g, gs, ge, j, b, e, buckets, spart);
+      xyzz_set_inf(acc);
+      do { g++; gs = ge; ge = offs[g + 1]; } while (ge <= pos);
+    }
+    uint32_t v = entries[pos];
+    Affine<typename CV::F> q = pts[v & 0x7fffffffu];
+    xyzz_madd(acc, acc, q, (v >> 31) != 0);
+  }
+  msm_slice_flush<CV>(acc, g, gs, ge, j, b, e, buckets, spart);
+}
+
+// Combine the partials of a bucket that was cut by slice boundaries.  Returns true when the bucket has
+// more than SERIAL_MAX partials (left to the block-parallel path), false when done / nothing to do.
+template <class CV, int SERIAL_MAX>
+B2K_D bool msm_fixup_bucket(uint32_t g, uint32_t L, const uint32_t* offs, Xyzz<typename CV::F>* buckets,
+                            const Xyzz<typename CV::F>* spart) {
+  uint32_t s = offs[g], t = offs[g + 1];
+  if (t == s) return false;
+  uint32_t j0 = s / L, j1 = (t - 1) / L;
+  if (j0 == j1) return false;
+  if (j1 - j0 + 1 > (uint32_t)SERIAL_MAX) return true;
+  Xyzz<typename CV::F> acc = spart[2 * (size_t)j0 + 1];
+  for (uint32_t j = j0 + 1; j <= j1; j++) {
+    Xyzz<typename CV::F> p = spart[2 * (size_t)j];
+    xyzz_add(acc, acc, p);
+  }
+  buckets[g] = acc;
+  return false;
 }
 
 }  // namespace b2k

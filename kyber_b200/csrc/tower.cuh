@@ -6,6 +6,7 @@
 //   Fp12 = Fp6[w]/(w^2 - v)                   (bn254: pairing/bn254/gfp6.go, gfp12.go)
 // A tower config T supplies  typename T::Base (the Fp config) and  mul_xi(Fp2&).
 #pragma once
+#include "constants.cuh"
 #include "fp.cuh"
 
 namespace b2k {

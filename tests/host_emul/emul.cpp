@@ -48,7 +48,7 @@ static void emul_mul_batch(size_t n, const uint8_t* scalars, const uint8_t* pts,
 }
 
 template <class CV>
-static int emul_msm(size_t n, const uint8_t* scalars, const uint8_t* pts, int c, int m, uint8_t* out) {
+static int emul_msm(size_t n, const uint8_t* scalars, const uint8_t* pts, int c, int m, uint8_t* out, int L = 0) {
   using F = typename CV::F;
   MsmPlan pl; pl.c = c; pl.W = (256 + c - 1) / c; pl.nb = 1 << (c - 1); pl.m = m;
   // K = sum_w 2^(c-1) 2^(cw)
@@ -74,7 +74,24 @@ static int emul_msm(size_t n, const uint8_t* scalars, const uint8_t* pts, int c,
     for (int w = 0; w < pl.W; w++) { int d = msm_digit(sp, c, w); if (d) { size_t g = (size_t)w * pl.nb + (d < 0 ? -d : d) - 1; entries[cursor[g]++] = (uint32_t)i | (d < 0 ? 0x80000000u : 0); } }
   }
   std::vector<Xyzz<F>> B(total);
-  for (size_t g = 0; g < total; g++) msm_accumulate_bucket<CV>(B[g], P.data(), entries.data(), offs[g], offs[g + 1]);
+  if (L == 0) {
+    for (size_t g = 0; g < total; g++) msm_accumulate_bucket<CV>(B[g], P.data(), entries.data(), offs[g], offs[g + 1]);
+  } else {   // v2: fixed-length slices + fix-up (buckets start as all-zero = infinity, like cudaMemset)
+    memset((void*)B.data(), 0, total * sizeof(Xyzz<F>));
+    uint32_t E = offs[total];
+    uint32_t S = (E + L - 1) / L;
+    std::vector<Xyzz<F>> spart(2 * (size_t)S + 2);
+    for (uint32_t j = 0; j < S; j++) msm_accumulate_slice<CV>(j, (uint32_t)L, (uint32_t)total, P.data(), offs.data(), entries.data(), B.data(), spart.data());
+    for (size_t g = 0; g < total; g++) {
+      bool big = msm_fixup_bucket<CV, 3>((uint32_t)g, (uint32_t)L, offs.data(), B.data(), spart.data());
+      if (big) {   // emulate the block-parallel path serially
+        uint32_t s0 = offs[g], t0 = offs[g + 1], j0 = s0 / L, j1 = (t0 - 1) / L;
+        Xyzz<F> a = spart[2 * (size_t)j0 + 1];
+        for (uint32_t j = j0 + 1; j <= j1; j++) xyzz_add(a, a, spart[2 * (size_t)j]);
+        B[g] = a;
+      }
+    }
+  }
   int T = pl.nb / m;
   std::vector<Xyzz<F>> part((size_t)pl.W * T), wsum(pl.W);
   for (int w = 0; w < pl.W; w++) for (int t = 0; t < T; t++) msm_reduce_chunk<CV>(part[(size_t)w * T + t], &B[(size_t)w * pl.nb], t, m);
@@ -88,6 +105,31 @@ static int emul_msm(size_t n, const uint8_t* scalars, const uint8_t* pts, int c,
 extern "C" {
 void emul_bls12381_g1_mul_batch(size_t n, const uint8_t* s, const uint8_t* p, uint8_t* o) { emul_mul_batch<Bls381G1>(n, s, p, o); }
 int emul_bls12381_g1_msm(size_t n, const uint8_t* s, const uint8_t* p, int c, int m, uint8_t* o) { return emul_msm<Bls381G1>(n, s, p, c, m, o); }
+int emul_bls12381_g1_msm_v2(size_t n, const uint8_t* s, const uint8_t* p, int c, int m, int L, uint8_t* o) { return emul_msm<Bls381G1>(n, s, p, c, m, o, L); }
 void emul_bn254_g1_mul_batch(size_t n, const uint8_t* s, const uint8_t* p, uint8_t* o) { emul_mul_batch<Bn254G1>(n, s, p, o); }
 int emul_bn254_g1_msm(size_t n, const uint8_t* s, const uint8_t* p, int c, int m, uint8_t* o) { return emul_msm<Bn254G1>(n, s, p, c, m, o); }
+}
+
+// ------------------------------------------------------------------------------------------------
+#include "../../kyber_b200/csrc/pairing.cuh"
+extern "C" {
+void emul_bls12381_pair(const uint8_t* g1, const uint8_t* g2, uint8_t* gt576) {
+  Affine<BFp> P; Affine<BFp2> Q;
+  Bls381G1::load(P, g1); g2_load(Q, g2);
+  BFp12 f, e;
+  miller_loop<1>(f, &P, &Q);
+  final_exponentiation(e, f);
+  gt_store(gt576, e);
+}
+// e(a1,a2) == e(b1,b2)
+int emul_bls12381_pairing_check(const uint8_t* a1, const uint8_t* a2, const uint8_t* b1, const uint8_t* b2) {
+  Affine<BFp> P[2]; Affine<BFp2> Q[2];
+  Bls381G1::load(P[0], a1); g2_load(Q[0], a2);
+  Bls381G1::load(P[1], b1); g2_load(Q[1], b2);
+  fp_neg(P[1].y, P[1].y);
+  BFp12 f, e;
+  miller_loop<2>(f, P, Q);
+  final_exponentiation(e, f);
+  return fp12_is_one(e) ? 1 : 0;
+}
 }

@@ -89,3 +89,45 @@ def test_msm_known_discrete_logs(engine, n):
         assert pts[96 * i:96 * i + 96] == o.g1_to_affine_bytes(o.g1_mul(a[i]))
     got = engine.bls12381_g1_msm(wl.scalars_to_bytes(s), pts)
     assert got == o.g1_compress(o.g1_mul(wl.dot_mod(s, a, o.R)))
+
+
+@pytest.mark.parametrize("dist_name", ["equal", "small", "two_values", "bdn128"])
+def test_msm_skewed_scalar_distributions(engine, dist_name):
+    """Balanced-slice accumulate must not depend on the scalar distribution (buckets with thousands of
+    points, empty upper windows, 128-bit BDN coefficients sign/bdn/bdn.go:29-63)."""
+    n = 3000
+    rng = random.Random(77)
+    a = wl.prng_scalars("b2k/test-a", n, o.R)
+    if dist_name == "equal":
+        s = [0x1D2C3B4A59687] * n
+    elif dist_name == "small":
+        s = [rng.randrange(1 << 20) for _ in range(n)]
+    elif dist_name == "two_values":
+        s = [rng.choice([1, o.R - 1]) for _ in range(n)]
+    else:
+        s = [rng.randrange(1 << 128) + 1 for _ in range(n)]
+    pts = engine.bls12381_g1_mul_batch_affine(wl.scalars_to_bytes(a), wl.G1_BLS12381_AFFINE * n)
+    want = o.g1_compress(o.g1_mul(wl.dot_mod(s, a, o.R)))
+    for c, L in ((0, 0), (16, 0), (8, 3), (11, 1)):
+        engine.set_msm_window(c)
+        engine.set_msm_slice(L)
+        try:
+            got = engine.bls12381_g1_msm(wl.scalars_to_bytes(s), pts)
+        finally:
+            engine.set_msm_window(0)
+            engine.set_msm_slice(0)
+        assert got == want, (dist_name, c, L)
+
+
+def test_msm_variants_agree(engine):
+    n = 2000
+    a = wl.prng_scalars("b2k/test-a", n, o.R)
+    s = wl.prng_scalars("b2k/test-v", n, o.R)
+    pts = engine.bls12381_g1_mul_batch_affine(wl.scalars_to_bytes(a), wl.G1_BLS12381_AFFINE * n)
+    sb = wl.scalars_to_bytes(s)
+    engine.set_msm_variant(True)
+    try:
+        v1 = engine.bls12381_g1_msm(sb, pts)
+    finally:
+        engine.set_msm_variant(False)
+    assert v1 == engine.bls12381_g1_msm(sb, pts) == o.g1_compress(o.g1_mul(wl.dot_mod(s, a, o.R)))
