@@ -125,6 +125,56 @@ def cpu_reference_run(n_sample: int, threads: int, seed_start: int = 0):
                               "reference, which has no MSM)"}
 
 
+def cpu_pairing_run(n_sample: int, threads: int):
+    """CPU baseline for pairings/s: n_sample 2-pair checks (ValidatePairing, kilic/suite.go:57-68) on all threads."""
+    from oracle import cpu_ref
+    from oracle import bls12381 as o
+    lib = cpu_ref.load()
+    x, y = 0x1234567, 0x89abcdef
+    a1 = o.g1_to_affine_bytes(o.g1_mul(x)) * n_sample
+    a2 = o.g2_to_affine_bytes(o.g2_mul(y)) * n_sample
+    b1 = o.g1_to_affine_bytes(o.g1_mul(x * y)) * n_sample
+    b2 = o.g2_to_affine_bytes(o.G2) * n_sample
+    t0 = time.perf_counter()
+    ok = cpu_ref.pairing_check(lib, a1, a2, b1, b2, threads)
+    dt = time.perf_counter() - t0
+    assert set(ok) == {1}
+    return {"value": 2 * n_sample / dt, "unit": "pairings/s", "cores": threads, "kind": "port",
+            "sample": f"{n_sample} ValidatePairing checks (2 pairings each) on {threads} threads, {dt:.2f} s; "
+                      "oracle/cpu_ref.c (C restatement, NOT the Go reference)"}
+
+
+def gpu_pairing_run(eng, torch, dev, n: int, steps: int):
+    """pairings/s on the GPU: n independent ValidatePairing checks per step (BASELINE configs[2] mode A's
+    pairing stage), operands resident in HBM; verified (all ones, one corrupted element zero)."""
+    from oracle import bls12381 as o
+    x, y = 0x1234567, 0x89abcdef
+    a1 = torch.frombuffer(bytearray(o.g1_to_affine_bytes(o.g1_mul(x)) * n), dtype=torch.uint8).to(dev)
+    a2 = torch.frombuffer(bytearray(o.g2_to_affine_bytes(o.g2_mul(y)) * n), dtype=torch.uint8).to(dev)
+    good = o.g1_to_affine_bytes(o.g1_mul(x * y))
+    hb1 = bytearray(good * n)
+    hb1[96 * 7:96 * 8] = o.g1_to_affine_bytes(o.g1_mul(x * y + 1))      # one wrong element
+    b1 = torch.frombuffer(hb1, dtype=torch.uint8).to(dev)
+    b2 = torch.frombuffer(bytearray(o.g2_to_affine_bytes(o.G2) * n), dtype=torch.uint8).to(dev)
+    ok = torch.zeros(n, dtype=torch.uint8, device=dev)
+
+    def step():
+        eng._check(eng.lib.b2k_bls12381_pairing_check_dev(eng.h, n, a1.data_ptr(), a2.data_ptr(), b1.data_ptr(),
+                                                          b2.data_ptr(), ok.data_ptr()))
+    step(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    res = ok.cpu()
+    assert int(res.sum()) == n - 1 and int(res[7]) == 0, "pairing check results wrong"
+    return {"value": 2 * n / (ms * 1e-3), "unit": "pairings/s", "ms_per_step": ms,
+            "workload": f"{n} independent ValidatePairing checks (2-pair Miller loop + final exponentiation each)",
+            "checks_per_sec": n / (ms * 1e-3)}
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -146,6 +196,7 @@ def run_reference_arm(args):
                        "step": f"bounded sample of {n_sample} pairs"},
             "cpu_baseline": dict(last, value=v),
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "pairings": cpu_pairing_run(max(64, 4 * threads), threads),
             "gpu_launches": 0}
     print(json.dumps(line))
     return 0
@@ -297,7 +348,7 @@ def run_ours(args):
                 "gpu_launches": int(launches),
                 "clocks": clocks,
                 "stages_ms": dict(zip(["load", "digits_hist", "scan", "scatter", "accumulate", "reduce_chunks",
-                                       "window_sum", "final", "pipeline"], [round(x, 4) for x in tm]))}
+                                       "window_sum", "final", "pipeline", "fixup"], [round(x, 4) for x in tm]))}
         if c_bits:
             W = 256 // c_bits
             alg_bytes = n * W * 100 + W * (1 << (c_bits - 1)) * 144
@@ -309,14 +360,18 @@ def run_ours(args):
                     traffic = json.load(open(tp)).get("dram_bytes_per_launch")
                 except Exception:
                     traffic = None
-            line["roofline"] = {"bound": "hbm", "kernel": "k_msm_accumulate", "achieved": alg_bytes / acc / 1e9,
+            line["roofline"] = {"bound": "hbm", "kernel": "k_msm_accumulate_slices", "achieved": alg_bytes / acc / 1e9,
                                 "peak": peak, "unit": "GB/s", "frac": alg_bytes / acc / 1e9 / peak,
                                 "traffic": traffic, "peak_source": peak_src,
                                 "algorithmic_bytes": alg_bytes, "kernel_ms": tm[4], "window_bits": c_bits,
                                 "note": "integer-ALU bound kernel (SURVEY.md F9): see DESIGN.md for the IMAD roofline"}
+        if world == 1 and not os.environ.get("B2K_SKIP_PAIRINGS"):
+            line["pairings"] = gpu_pairing_run(eng, torch, dev, 1 << 16, max(2, min(args.steps, 5)))
         if world == 1 and not os.environ.get("B2K_SKIP_CPU_BASELINE"):
             threads = os.cpu_count() or 1
             line["cpu_baseline"] = cpu_reference_run(max(2048, 192 * threads), threads)
+            if "pairings" in line:
+                line["pairings"]["cpu_baseline"] = cpu_pairing_run(max(64, 4 * threads), threads)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

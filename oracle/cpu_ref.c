@@ -408,3 +408,224 @@ int cpu_g1_msm_pippenger(size_t n, const uint8_t* scalars, const uint8_t* points
   jac_to_aff(&a, &s); aff_store_compressed(out48, &a);
   return rc;
 }
+
+/* ==================================================================================================
+ * Pairing (CPU baseline for pairings/s).  Restates the optimal-ate pairing the reference reaches through
+ * kilic.Suite.Pair / ValidatePairing (pairing/bls12381/kilic/suite.go:57-75; arithmetic third-party),
+ * structured like the in-tree bn254 one (pairing/bn254/optate.go:5-271): Jacobian twist point,
+ * inversion-free lines, sparse line multiplication, final exponentiation with exponent (p^12-1)/r.
+ * Checked against oracle/bls12381.py (GT bytes) in tests/test_oracle_bls12381.py.
+ * ================================================================================================== */
+typedef struct { fp c0, c1; } fp2;
+typedef struct { fp2 c0, c1, c2; } fp6;
+typedef struct { fp6 c0, c1; } fp12;
+
+static void fp2_add(fp2* r, const fp2* a, const fp2* b) { fp_add(r->c0, a->c0, b->c0); fp_add(r->c1, a->c1, b->c1); }
+static void fp2_sub(fp2* r, const fp2* a, const fp2* b) { fp_sub(r->c0, a->c0, b->c0); fp_sub(r->c1, a->c1, b->c1); }
+static void fp2_neg(fp2* r, const fp2* a) { fp_neg(r->c0, a->c0); fp_neg(r->c1, a->c1); }
+static void fp2_conj(fp2* r, const fp2* a) { memcpy(r->c0, a->c0, sizeof(fp)); fp_neg(r->c1, a->c1); }
+static void fp2_dbl(fp2* r, const fp2* a) { fp2_add(r, a, a); }
+static void fp2_mul(fp2* r, const fp2* a, const fp2* b) {
+  fp t0, t1, s0, s1;
+  fp_mul(t0, a->c0, b->c0); fp_mul(t1, a->c1, b->c1);
+  fp_add(s0, a->c0, a->c1); fp_add(s1, b->c0, b->c1); fp_mul(s0, s0, s1);
+  fp_sub(s0, s0, t0); fp_sub(r->c1, s0, t1); fp_sub(r->c0, t0, t1);
+}
+static void fp2_sqr(fp2* r, const fp2* a) {
+  fp s, d, m;
+  fp_add(s, a->c0, a->c1); fp_sub(d, a->c0, a->c1); fp_mul(m, a->c0, a->c1);
+  fp_mul(r->c0, s, d); fp_add(r->c1, m, m);
+}
+static void fp2_mul_fp(fp2* r, const fp2* a, const fp k) { fp_mul(r->c0, a->c0, k); fp_mul(r->c1, a->c1, k); }
+static void fp2_mul_xi(fp2* r, const fp2* a) { fp t; fp_sub(t, a->c0, a->c1); fp_add(r->c1, a->c0, a->c1); memcpy(r->c0, t, sizeof(fp)); }
+static void fp2_inv(fp2* r, const fp2* a) {
+  fp n, t;
+  fp_sqr(n, a->c0); fp_sqr(t, a->c1); fp_add(n, n, t); fp_inv(n, n);
+  fp_mul(r->c0, a->c0, n); fp_mul(t, a->c1, n); fp_neg(r->c1, t);
+}
+static void fp6_add(fp6* r, const fp6* a, const fp6* b) { fp2_add(&r->c0, &a->c0, &b->c0); fp2_add(&r->c1, &a->c1, &b->c1); fp2_add(&r->c2, &a->c2, &b->c2); }
+static void fp6_sub(fp6* r, const fp6* a, const fp6* b) { fp2_sub(&r->c0, &a->c0, &b->c0); fp2_sub(&r->c1, &a->c1, &b->c1); fp2_sub(&r->c2, &a->c2, &b->c2); }
+static void fp6_neg(fp6* r, const fp6* a) { fp2_neg(&r->c0, &a->c0); fp2_neg(&r->c1, &a->c1); fp2_neg(&r->c2, &a->c2); }
+static void fp6_mul_v(fp6* r, const fp6* a) { fp2 t; fp2_mul_xi(&t, &a->c2); r->c2 = a->c1; r->c1 = a->c0; r->c0 = t; }
+static void fp6_mul(fp6* r, const fp6* a, const fp6* b) {
+  fp2 v0, v1, v2, t0, t1, t2, s;
+  fp2_mul(&v0, &a->c0, &b->c0); fp2_mul(&v1, &a->c1, &b->c1); fp2_mul(&v2, &a->c2, &b->c2);
+  fp2_add(&t0, &a->c1, &a->c2); fp2_add(&s, &b->c1, &b->c2); fp2_mul(&t0, &t0, &s);
+  fp2_sub(&t0, &t0, &v1); fp2_sub(&t0, &t0, &v2); fp2_mul_xi(&t0, &t0); fp2_add(&t0, &t0, &v0);
+  fp2_add(&t1, &a->c0, &a->c1); fp2_add(&s, &b->c0, &b->c1); fp2_mul(&t1, &t1, &s);
+  fp2_sub(&t1, &t1, &v0); fp2_sub(&t1, &t1, &v1); fp2_mul_xi(&s, &v2); fp2_add(&t1, &t1, &s);
+  fp2_add(&t2, &a->c0, &a->c2); fp2_add(&s, &b->c0, &b->c2); fp2_mul(&t2, &t2, &s);
+  fp2_sub(&t2, &t2, &v0); fp2_sub(&t2, &t2, &v2); fp2_add(&t2, &t2, &v1);
+  r->c0 = t0; r->c1 = t1; r->c2 = t2;
+}
+static void fp6_inv(fp6* r, const fp6* a) {
+  fp2 t0, t1, t2, s, d;
+  fp2_sqr(&t0, &a->c0); fp2_mul(&s, &a->c1, &a->c2); fp2_mul_xi(&s, &s); fp2_sub(&t0, &t0, &s);
+  fp2_sqr(&t1, &a->c2); fp2_mul_xi(&t1, &t1); fp2_mul(&s, &a->c0, &a->c1); fp2_sub(&t1, &t1, &s);
+  fp2_sqr(&t2, &a->c1); fp2_mul(&s, &a->c0, &a->c2); fp2_sub(&t2, &t2, &s);
+  fp2_mul(&d, &a->c2, &t1); fp2_mul(&s, &a->c1, &t2); fp2_add(&d, &d, &s); fp2_mul_xi(&d, &d);
+  fp2_mul(&s, &a->c0, &t0); fp2_add(&d, &d, &s); fp2_inv(&d, &d);
+  fp2_mul(&r->c0, &t0, &d); fp2_mul(&r->c1, &t1, &d); fp2_mul(&r->c2, &t2, &d);
+}
+static void fp12_one(fp12* r) { memset(r, 0, sizeof *r); memcpy(r->c0.c0.c0, R1, sizeof(fp)); }
+static void fp12_mul(fp12* r, const fp12* a, const fp12* b) {
+  fp6 t0, t1, s0, s1;
+  fp6_mul(&t0, &a->c0, &b->c0); fp6_mul(&t1, &a->c1, &b->c1);
+  fp6_add(&s0, &a->c0, &a->c1); fp6_add(&s1, &b->c0, &b->c1); fp6_mul(&s0, &s0, &s1);
+  fp6_sub(&s0, &s0, &t0); fp6_sub(&r->c1, &s0, &t1);
+  fp6_mul_v(&t1, &t1); fp6_add(&r->c0, &t0, &t1);
+}
+static void fp12_sqr(fp12* r, const fp12* a) {
+  fp6 ab, s, t;
+  fp6_mul(&ab, &a->c0, &a->c1);
+  fp6_add(&s, &a->c0, &a->c1); fp6_mul_v(&t, &a->c1); fp6_add(&t, &t, &a->c0);
+  fp6_mul(&s, &s, &t); fp6_sub(&s, &s, &ab); fp6_mul_v(&t, &ab);
+  fp6_sub(&r->c0, &s, &t); fp6_add(&r->c1, &ab, &ab);
+}
+static void fp12_conj(fp12* r, const fp12* a) { r->c0 = a->c0; fp6_neg(&r->c1, &a->c1); }
+static void fp12_inv(fp12* r, const fp12* a) {
+  fp6 d, t;
+  fp6_mul(&d, &a->c0, &a->c0); fp6_mul(&t, &a->c1, &a->c1); fp6_mul_v(&t, &t); fp6_sub(&d, &d, &t);
+  fp6_inv(&d, &d);
+  fp6_mul(&r->c0, &a->c0, &d); fp6_mul(&t, &a->c1, &d); fp6_neg(&r->c1, &t);
+}
+/* sparse line (l0, l2, 0) + (0, l3, 0) w */
+static void fp12_mul_line(fp12* f, const fp2* l0, const fp2* l2, const fp2* l3) {
+  fp12 l;
+  memset(&l, 0, sizeof l);
+  l.c0.c0 = *l0; l.c0.c1 = *l2; l.c1.c1 = *l3;
+  fp12_mul(f, f, &l);      /* dense product: the Go back-ends use sparse formulas; <15% of a pairing */
+}
+static fp2 FROB1[6];
+static int g_pinit = 0;
+static void pairing_init(void) {
+  if (g_pinit) return;
+  init_once();
+  /* (p-1)/6 by long division */
+  uint64_t e[6]; u128 rem = 0;
+  uint64_t pm1[6]; memcpy(pm1, P, sizeof pm1); pm1[0] -= 1;
+  for (int i = 5; i >= 0; i--) { u128 cur = (rem << 64) | pm1[i]; e[i] = (uint64_t)(cur / 6); rem = cur % 6; }
+  fp2 xi, acc, base;
+  memcpy(xi.c0, R1, sizeof(fp)); memcpy(xi.c1, R1, sizeof(fp));
+  memset(&acc, 0, sizeof acc); memcpy(acc.c0, R1, sizeof(fp));
+  base = xi;
+  for (int i = 6 * 64 - 1; i >= 0; i--) { fp2_sqr(&acc, &acc); if ((e[i >> 6] >> (i & 63)) & 1) fp2_mul(&acc, &acc, &base); }
+  memset(&FROB1[0], 0, sizeof(fp2)); memcpy(FROB1[0].c0, R1, sizeof(fp));
+  for (int k = 1; k < 6; k++) fp2_mul(&FROB1[k], &FROB1[k - 1], &acc);
+  g_pinit = 1;
+}
+static void fp12_frob(fp12* r, const fp12* f) {   /* f^p */
+  fp2* dst[6] = {&r->c0.c0, &r->c1.c0, &r->c0.c1, &r->c1.c1, &r->c0.c2, &r->c1.c2};
+  const fp2* src[6] = {&f->c0.c0, &f->c1.c0, &f->c0.c1, &f->c1.c1, &f->c0.c2, &f->c1.c2};
+  for (int k = 0; k < 6; k++) { fp2 a; fp2_conj(&a, src[k]); fp2_mul(dst[k], &a, &FROB1[k]); }
+}
+static void fp12_pow_u64(fp12* r, const fp12* a, uint64_t e) {
+  fp12 acc = *a;
+  int top = 63;
+  while (top > 0 && !((e >> top) & 1)) top--;
+  for (int b = top - 1; b >= 0; b--) { fp12_sqr(&acc, &acc); if ((e >> b) & 1) fp12_mul(&acc, &acc, a); }
+  *r = acc;
+}
+#define X_ABS 0xd201000000010000ULL
+#define E3 0x460055555555aaabULL
+static void final_exp(fp12* r, const fp12* f) {
+  fp12 m, t, y3, y2, y1, y0;
+  fp12_inv(&t, f); fp12_conj(&m, f); fp12_mul(&m, &m, &t);
+  fp12_frob(&t, &m); fp12_frob(&t, &t); fp12_mul(&m, &t, &m);
+  fp12_pow_u64(&t, &m, E3); fp12_pow_u64(&y3, &t, X_ABS); fp12_mul(&y3, &y3, &t);
+  fp12_pow_u64(&y2, &y3, X_ABS); fp12_conj(&y2, &y2);
+  fp12_pow_u64(&y1, &y2, X_ABS); fp12_conj(&y1, &y1); fp12_conj(&t, &y3); fp12_mul(&y1, &y1, &t);
+  fp12_pow_u64(&y0, &y1, X_ABS); fp12_conj(&y0, &y0); fp12_mul(&y0, &y0, &m);
+  fp12_frob(&t, &y1); fp12_mul(&y0, &y0, &t);
+  fp12_frob(&t, &y2); fp12_frob(&t, &t); fp12_mul(&y0, &y0, &t);
+  fp12_frob(&t, &y3); fp12_frob(&t, &t); fp12_frob(&t, &t); fp12_mul(r, &y0, &t);
+}
+typedef struct { fp2 X, Y, Z; } jac2;
+typedef struct { fp2 x, y; int inf; } aff2;
+static void g2_load(aff2* r, const uint8_t* b /*192: x.c1||x.c0||y.c1||y.c0*/) {
+  int z = 1;
+  for (int i = 0; i < 192; i++) if (b[i]) { z = 0; break; }
+  memset(r, 0, sizeof *r);
+  if (z) { r->inf = 1; return; }
+  fp t;
+  fp_from_be(t, b); fp_mul(r->x.c1, t, R2); fp_from_be(t, b + 48); fp_mul(r->x.c0, t, R2);
+  fp_from_be(t, b + 96); fp_mul(r->y.c1, t, R2); fp_from_be(t, b + 144); fp_mul(r->y.c0, t, R2);
+}
+static void miller_dbl(fp2* l0, fp2* l2, fp2* l3, jac2* T, const aff* Pp) {
+  fp2 A, B, C, D, E, ZZ, t;
+  fp2_sqr(&A, &T->X); fp2_sqr(&B, &T->Y); fp2_sqr(&C, &B); fp2_sqr(&ZZ, &T->Z);
+  fp2_add(&D, &T->X, &B); fp2_sqr(&D, &D); fp2_sub(&D, &D, &A); fp2_sub(&D, &D, &C); fp2_dbl(&D, &D);
+  fp2_dbl(&E, &A); fp2_add(&E, &E, &A);
+  fp2_mul(l0, &E, &T->X); fp2_sub(l0, l0, &B); fp2_sub(l0, l0, &B);
+  fp2_mul(&t, &E, &ZZ); fp2_mul_fp(&t, &t, Pp->x); fp2_neg(l2, &t);
+  fp2_mul(&t, &T->Y, &T->Z); fp2_dbl(&T->Z, &t);
+  fp2_mul(&t, &T->Z, &ZZ); fp2_mul_fp(l3, &t, Pp->y);
+  fp2_sqr(&A, &E); fp2_sub(&A, &A, &D); fp2_sub(&A, &A, &D);
+  fp2_dbl(&C, &C); fp2_dbl(&C, &C); fp2_dbl(&C, &C);
+  fp2_sub(&D, &D, &A); fp2_mul(&D, &E, &D); fp2_sub(&T->Y, &D, &C);
+  T->X = A;
+}
+static void miller_add(fp2* l0, fp2* l2, fp2* l3, jac2* T, const aff2* Q, const aff* Pp) {
+  fp2 ZZ, U2, S2, H, R, HH, HHH, V, t;
+  fp2_sqr(&ZZ, &T->Z); fp2_mul(&U2, &Q->x, &ZZ); fp2_mul(&S2, &Q->y, &T->Z); fp2_mul(&S2, &S2, &ZZ);
+  fp2_sub(&H, &U2, &T->X); fp2_sub(&R, &S2, &T->Y);
+  fp2_sqr(&HH, &H); fp2_mul(&HHH, &H, &HH); fp2_mul(&V, &T->X, &HH);
+  fp2_mul(&T->Z, &T->Z, &H);
+  fp2_mul(l0, &R, &Q->x); fp2_mul(&t, &T->Z, &Q->y); fp2_sub(l0, l0, &t);
+  fp2_mul_fp(&t, &R, Pp->x); fp2_neg(l2, &t);
+  fp2_mul_fp(l3, &T->Z, Pp->y);
+  fp2_sqr(&t, &R); fp2_sub(&t, &t, &HHH); fp2_sub(&t, &t, &V); fp2_sub(&t, &t, &V);
+  fp2_sub(&V, &V, &t); fp2_mul(&V, &R, &V); fp2_mul(&HHH, &T->Y, &HHH); fp2_sub(&T->Y, &V, &HHH);
+  T->X = t;
+}
+static void miller_n(fp12* f, int np, const aff* Pp, const aff2* Q) {
+  jac2 T[2]; int live[2];
+  for (int i = 0; i < np; i++) { live[i] = !(Pp[i].inf || Q[i].inf); T[i].X = Q[i].x; T[i].Y = Q[i].y; memset(&T[i].Z, 0, sizeof(fp2)); memcpy(T[i].Z.c0, R1, sizeof(fp)); }
+  fp12_one(f);
+  fp2 l0, l2, l3;
+  for (int b = 62; b >= 0; b--) {
+    fp12_sqr(f, f);
+    for (int i = 0; i < np; i++) if (live[i]) { miller_dbl(&l0, &l2, &l3, &T[i], &Pp[i]); fp12_mul_line(f, &l0, &l2, &l3); }
+    if ((X_ABS >> b) & 1) for (int i = 0; i < np; i++) if (live[i]) { miller_add(&l0, &l2, &l3, &T[i], &Q[i], &Pp[i]); fp12_mul_line(f, &l0, &l2, &l3); }
+  }
+  fp12_conj(f, f);
+}
+static void gt_store(uint8_t* out, const fp12* f) {
+  const fp2* order[6] = {&f->c1.c2, &f->c1.c1, &f->c1.c0, &f->c0.c2, &f->c0.c1, &f->c0.c0};
+  fp one = {1, 0, 0, 0, 0, 0}, t;
+  for (int i = 0; i < 6; i++) { fp_mul(t, order[i]->c1, one); fp_to_be(out + 96 * i, t); fp_mul(t, order[i]->c0, one); fp_to_be(out + 96 * i + 48, t); }
+}
+typedef struct { size_t lo, hi; const uint8_t *a1, *a2, *b1, *b2; uint8_t* out; int mode; } pjob_t;
+static void* pworker(void* arg) {
+  pjob_t* j = (pjob_t*)arg;
+  for (size_t i = j->lo; i < j->hi; i++) {
+    aff Pp[2]; aff2 Q[2]; fp12 f, e;
+    aff_load(&Pp[0], j->a1 + 96 * i); g2_load(&Q[0], j->a2 + 192 * i);
+    if (j->mode == 0) { miller_n(&f, 1, Pp, Q); final_exp(&e, &f); gt_store(j->out + 576 * i, &e); }
+    else {
+      aff_load(&Pp[1], j->b1 + 96 * i); g2_load(&Q[1], j->b2 + 192 * i); fp_neg(Pp[1].y, Pp[1].y);
+      miller_n(&f, 2, Pp, Q); final_exp(&e, &f);
+      fp12 one; fp12_one(&one);
+      j->out[i] = memcmp(&e, &one, sizeof one) == 0;
+    }
+  }
+  return NULL;
+}
+static int prun(int mode, size_t n, const uint8_t* a1, const uint8_t* a2, const uint8_t* b1, const uint8_t* b2, uint8_t* out, int nthreads) {
+  pairing_init();
+  if (nthreads < 1) nthreads = 1;
+  if ((size_t)nthreads > n) nthreads = (int)n;
+  pjob_t* jobs = (pjob_t*)calloc((size_t)nthreads, sizeof(pjob_t));
+  pthread_t* th = (pthread_t*)calloc((size_t)nthreads, sizeof(pthread_t));
+  for (int t = 0; t < nthreads; t++) {
+    jobs[t] = (pjob_t){n * (size_t)t / nthreads, n * (size_t)(t + 1) / nthreads, a1, a2, b1, b2, out, mode};
+    if (nthreads == 1) pworker(&jobs[t]); else pthread_create(&th[t], NULL, pworker, &jobs[t]);
+  }
+  for (int t = 0; t < nthreads; t++) if (nthreads > 1) pthread_join(th[t], NULL);
+  free(jobs); free(th);
+  return 0;
+}
+/* gt[i] = e(g1[i], g2[i]) */
+int cpu_pair(size_t n, const uint8_t* g1, const uint8_t* g2, uint8_t* gt576n, int nthreads) { return prun(0, n, g1, g2, NULL, NULL, gt576n, nthreads); }
+/* ok[i] = e(a1,a2) == e(b1,b2) */
+int cpu_pairing_check(size_t n, const uint8_t* a1, const uint8_t* a2, const uint8_t* b1, const uint8_t* b2, uint8_t* ok, int nthreads) { return prun(1, n, a1, a2, b1, b2, ok, nthreads); }

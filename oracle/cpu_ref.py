@@ -48,3 +48,21 @@ def g1_msm_muladd(lib, scalars: bytes, points: bytes, threads: int = 1) -> bytes
 
 def g1_msm_pippenger(lib, scalars: bytes, points: bytes, threads: int = 1) -> bytes:
     return _call(lib, "cpu_g1_msm_pippenger", scalars, points, 48, threads)
+
+
+def pair(lib, g1: bytes, g2: bytes, threads: int = 1) -> bytes:
+    n = len(g1) // 96
+    out = C.create_string_buffer(576 * n)
+    lib.cpu_pair.restype = C.c_int
+    lib.cpu_pair.argtypes = [C.c_size_t, C.c_char_p, C.c_char_p, C.c_char_p, C.c_int]
+    assert lib.cpu_pair(n, g1, g2, out, threads) == 0
+    return out.raw
+
+
+def pairing_check(lib, a1: bytes, a2: bytes, b1: bytes, b2: bytes, threads: int = 1) -> bytes:
+    n = len(a1) // 96
+    out = C.create_string_buffer(n)
+    lib.cpu_pairing_check.restype = C.c_int
+    lib.cpu_pairing_check.argtypes = [C.c_size_t, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_int]
+    assert lib.cpu_pairing_check(n, a1, a2, b1, b2, out, threads) == 0
+    return out.raw
