@@ -93,6 +93,33 @@ int b2k_bls12381_g1_msm_dev(b2k_ctx* ctx, size_t n, const void* d_scalars, const
 int b2k_bls12381_g1_msm_affine_dev(b2k_ctx* ctx, size_t n, const void* d_scalars, const void* d_points,
                                    void* d_out /*[96]*/);
 
+/* ---- BLS12-381 G2 ------------------------------------------------------------------------------------ */
+/* replaces: kilic.G2Elt.Mul, pairing/bls12381/kilic/g2.go:109-115 (public keys / signatures on G2:
+ * bdn.NewMask terms sign/bdn/mask.go:58-61, bdn.AggregateSignatures on G2).  Operands 192 B
+ * (x.c1||x.c0||y.c1||y.c0), results 96 B ZCash compressed (kilic/g2.go:118-123). */
+int b2k_bls12381_g2_mul_batch(b2k_ctx* ctx, size_t n, const uint8_t* scalars /*[n][32]*/,
+                              const uint8_t* points /*[n][192]*/, uint8_t* out /*[n][96]*/);
+int b2k_bls12381_g2_mul_batch_affine(b2k_ctx* ctx, size_t n, const uint8_t* scalars, const uint8_t* points,
+                                     uint8_t* out /*[n][192]*/);
+int b2k_bls12381_g2_mul_batch_affine_dev(b2k_ctx* ctx, size_t n, const void* d_scalars, const void* d_points,
+                                         void* d_out);
+int b2k_bls12381_g2_msm(b2k_ctx* ctx, size_t n, const uint8_t* scalars /*[n][32]*/,
+                        const uint8_t* points /*[n][192]*/, uint8_t* out /*[96]*/);
+int b2k_bls12381_g2_msm_dev(b2k_ctx* ctx, size_t n, const void* d_scalars, const void* d_points, void* d_out);
+
+/* ---- BLS12-381 UnmarshalBinary (decompress + subgroup check) --------------------------------------------- */
+/* out[i] = operand form of the ZCash-compressed input, ok[i] = 1, or ok[i] = 0 (out[i] zeroed) when the
+ * reference's UnmarshalBinary would return an error: wrong flag bits, x >= p, not on the curve, not in the
+ * r-torsion subgroup.   replaces: kilic.G1Elt.UnmarshalBinary -> FromCompressed (kilic/g1.go:127-131),
+ * kilic.G2Elt.UnmarshalBinary (kilic/g2.go:126-130); behaviour pinned by the 34 ZCash fixtures.
+ * (Wrong LENGTH is the caller's check: the stride is fixed.) */
+int b2k_bls12381_g1_decompress(b2k_ctx* ctx, size_t n, const uint8_t* in /*[n][48]*/, uint8_t* out /*[n][96]*/,
+                               uint8_t* ok /*[n]*/);
+int b2k_bls12381_g1_decompress_dev(b2k_ctx* ctx, size_t n, const void* d_in, void* d_out, void* d_ok);
+int b2k_bls12381_g2_decompress(b2k_ctx* ctx, size_t n, const uint8_t* in /*[n][96]*/, uint8_t* out /*[n][192]*/,
+                               uint8_t* ok /*[n]*/);
+int b2k_bls12381_g2_decompress_dev(b2k_ctx* ctx, size_t n, const void* d_in, void* d_out, void* d_ok);
+
 /* ---- BLS12-381 pairings ---------------------------------------------------------------------------- */
 /* gt[i] = e(g1[i], g2[i]); g2 operands are 192 B: x.c1||x.c0||y.c1||y.c0.  GT = 576 B, 12 x 48 B
  * big-endian, highest tower coefficient first (kilic/gt.go:115-117), exponent exactly (p^12-1)/r.

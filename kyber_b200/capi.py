@@ -52,10 +52,14 @@ def load_library() -> C.CDLL:
 
 
 HOST_FUNCS = [
+    "b2k_bls12381_g2_mul_batch", "b2k_bls12381_g2_mul_batch_affine", "b2k_bls12381_g2_msm",
+    "b2k_bls12381_g1_decompress", "b2k_bls12381_g2_decompress",
     "b2k_bls12381_g1_mul_batch", "b2k_bls12381_g1_mul_batch_affine", "b2k_bls12381_g1_msm",
     "b2k_bn254_g1_mul_batch", "b2k_bn254_g1_msm",
 ]
 DEV_FUNCS = [
+    "b2k_bls12381_g2_mul_batch_affine_dev", "b2k_bls12381_g2_msm_dev",
+    "b2k_bls12381_g1_decompress_dev", "b2k_bls12381_g2_decompress_dev",
     "b2k_bls12381_g1_mul_batch_dev", "b2k_bls12381_g1_mul_batch_affine_dev", "b2k_bls12381_g1_msm_dev",
     "b2k_bls12381_g1_msm_affine_dev", "b2k_bn254_g1_msm_dev",
 ]
@@ -150,6 +154,38 @@ class Engine:
         n = len(scalars) // 32
         assert len(scalars) == 32 * n and len(points) == 96 * n
         return self.call_host("b2k_bls12381_g1_msm", n, scalars, points, 48)
+
+    # -- BLS12-381 G2 -----------------------------------------------------------------------------------
+    def bls12381_g2_mul_batch(self, scalars: bytes, points: bytes) -> bytes:
+        n = len(scalars) // 32
+        assert len(scalars) == 32 * n and len(points) == 192 * n
+        return self.call_host("b2k_bls12381_g2_mul_batch", n, scalars, points, 96 * n)
+
+    def bls12381_g2_mul_batch_affine(self, scalars: bytes, points: bytes) -> bytes:
+        n = len(scalars) // 32
+        assert len(scalars) == 32 * n and len(points) == 192 * n
+        return self.call_host("b2k_bls12381_g2_mul_batch_affine", n, scalars, points, 192 * n)
+
+    def bls12381_g2_msm(self, scalars: bytes, points: bytes) -> bytes:
+        n = len(scalars) // 32
+        assert len(scalars) == 32 * n and len(points) == 192 * n
+        return self.call_host("b2k_bls12381_g2_msm", n, scalars, points, 96)
+
+    # -- UnmarshalBinary batches ------------------------------------------------------------------------
+    def _decompress(self, name: str, data: bytes, in_len: int, out_len: int):
+        n = len(data) // in_len
+        assert len(data) == in_len * n
+        out, ok = bytearray(out_len * n), bytearray(n)
+        bufs = [_buf(x) for x in (data, out, ok)]
+        self._check(getattr(self.lib, name)(self.h, n, *[b[0] for b in bufs]))
+        return bytes(out), bytes(ok)
+
+    def bls12381_g1_decompress(self, data: bytes):
+        """-> (operand bytes [n][96], ok flags [n])"""
+        return self._decompress("b2k_bls12381_g1_decompress", data, 48, 96)
+
+    def bls12381_g2_decompress(self, data: bytes):
+        return self._decompress("b2k_bls12381_g2_decompress", data, 96, 192)
 
     # -- BLS12-381 pairings ---------------------------------------------------------------------------
     def bls12381_pair(self, g1: bytes, g2: bytes) -> bytes:

@@ -7,27 +7,18 @@
 #include <new>
 
 #include "../../include/b2kyber.h"
-#include "kernels.cuh"
+#include "msm_host.cuh"
 
 using namespace b2k;
 
 #include "b2k_ctx.h"
 
 using Arena = b2k_arena;
-constexpr int N_EV = B2K_N_EV;
+
 
 namespace {
 
-#define CK(call)                                                                       \
-  do {                                                                                 \
-    cudaError_t e_ = (call);                                                           \
-    if (e_ != cudaSuccess) {                                                           \
-      ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_);                   \
-      return B2K_ERR_CUDA;                                                             \
-    }                                                                                  \
-  } while (0)
-
-int arena_reserve(b2k_ctx* ctx, size_t bytes) {
+int arena_reserve_impl(b2k_ctx* ctx, size_t bytes) {
   Arena& a = ctx->arena;
   a.used = 0;
   if (bytes <= a.cap) return B2K_OK;
@@ -44,7 +35,7 @@ int arena_reserve(b2k_ctx* ctx, size_t bytes) {
 }
 
 template <class T>
-T* arena_take(b2k_ctx* ctx, size_t count) {
+T* arena_take_impl(b2k_ctx* ctx, size_t count) {
   Arena& a = ctx->arena;
   size_t off = (a.used + 255) & ~size_t(255);
   size_t bytes = count * sizeof(T);
@@ -55,229 +46,12 @@ T* arena_take(b2k_ctx* ctx, size_t count) {
 
 inline size_t pad256(size_t b) { return (b + 255) & ~size_t(255); }
 
-int pick_window(size_t n) {
-  // minimise  W * (10 n + 40 * 2^(c-1))  field multiplications (mixed add ~10, bucket reduce ~40/bucket)
-  int best = 4;
-  double bestc = 1e300;
-  for (int c = 4; c <= 16; c++) {
-    int W = (256 + c - 1) / c;
-    double cost = (double)W * (10.0 * (double)n + 40.0 * (double)(1u << (c - 1)));
-    if (cost < bestc) { bestc = cost; best = c; }
-  }
-  return best;
-}
-
-MsmPlan make_plan(size_t n, int force_c) {
-  MsmPlan pl;
-  pl.c = force_c ? force_c : pick_window(n);
-  pl.W = (256 + pl.c - 1) / pl.c;
-  pl.nb = 1 << (pl.c - 1);
-  size_t total = (size_t)pl.W * pl.nb;
-  int m = 1;
-  while (m < 64 && m * 2 <= pl.nb && total / (size_t)(m * 2) >= 16384) m *= 2;
-  pl.m = m;
-  memset(pl.K, 0, sizeof pl.K);
-  for (int w = 0; w < pl.W; w++) {
-    int bit = pl.c * w + pl.c - 1;
-    pl.K[bit >> 5] |= 1u << (bit & 31);
-  }
-  return pl;
-}
-
-// slice length of the balanced accumulate: 64 additions per thread when there is enough work to fill
-// the chip (>= 128k slices), shorter slices for small problems
-uint32_t slice_len(size_t n, const MsmPlan& pl, int force_L) {
-  if (force_L > 0) return (uint32_t)force_L;
-  size_t e = n * (size_t)pl.W;
-  size_t L = e / 131072;
-  if (L > 64) L = 64;
-  if (L < 4) L = 4;
-  return (uint32_t)L;
-}
-
 }  // namespace
 
-int b2k_arena_reserve(b2k_ctx* ctx, size_t bytes) { return arena_reserve(ctx, bytes); }
-void* b2k_arena_take(b2k_ctx* ctx, size_t bytes) { return arena_take<char>(ctx, bytes); }
+int b2k_arena_reserve(b2k_ctx* ctx, size_t bytes) { return arena_reserve_impl(ctx, bytes); }
+void* b2k_arena_take(b2k_ctx* ctx, size_t bytes) { return arena_take_impl<char>(ctx, bytes); }
 
-namespace {
-
-int check_flags(b2k_ctx* ctx) {
-  uint32_t f = *ctx->h_flags;
-  if (f & FLAG_SCALAR_RANGE) { ctx->err = "scalar not below the group order"; return B2K_ERR_SCALAR_RANGE; }
-  if (f & FLAG_POINT) { ctx->err = "malformed operand point"; return B2K_ERR_POINT; }
-  return B2K_OK;
-}
-
-// ------------------------------------------------------------------------------------------------
-template <class CV>
-size_t msm_scratch_bytes(size_t n, const MsmPlan& pl, int force_L) {
-  using F = typename CV::F;
-  size_t total = (size_t)pl.W * pl.nb;
-  size_t T = pl.nb / pl.m;
-  size_t b = 0;
-  b += pad256(n * sizeof(Affine<F>));
-  b += pad256((total + 1) * 4) * 3;               // counts, offs, cursor
-  b += pad256(n * (size_t)pl.W * 4);              // entries
-  b += pad256(total * sizeof(Xyzz<F>));           // buckets
-  b += pad256((size_t)pl.W * T * sizeof(Xyzz<F>));  // partials
-  b += pad256((size_t)pl.W * sizeof(Xyzz<F>));    // window sums
-  size_t smax = (n * (size_t)pl.W) / (size_t)slice_len(n, pl, force_L) + 2;
-  b += pad256(2 * smax * sizeof(Xyzz<F>));        // slice partials (worst case: smallest automatic L)
-  b += pad256((total + 1) * 4) + pad256(4096);    // big-bucket list, block sums
-  return b + 8192;
-}
-
-// Enqueue the whole MSM on ctx->stream. d_scalars/d_points/d_out are device pointers; scratch must
-// already be reserved (arena) for msm_scratch_bytes().
-template <class CV>
-int msm_enqueue(b2k_ctx* ctx, size_t n, const MsmPlan& pl, const uint8_t* d_scalars, const uint8_t* d_points,
-                uint8_t* d_out, int affine_out = 0) {
-  using F = typename CV::F;
-  cudaStream_t st = ctx->stream;
-  size_t total = (size_t)pl.W * pl.nb;
-  int T = pl.nb / pl.m;
-  auto* pts = arena_take<Affine<F>>(ctx, n);
-  auto* counts = arena_take<uint32_t>(ctx, total + 1);
-  auto* offs = arena_take<uint32_t>(ctx, total + 1);
-  auto* cursor = arena_take<uint32_t>(ctx, total + 1);
-  auto* entries = arena_take<uint32_t>(ctx, n * (size_t)pl.W);
-  auto* buckets = arena_take<Xyzz<F>>(ctx, total);
-  auto* partials = arena_take<Xyzz<F>>(ctx, (size_t)pl.W * T);
-  auto* wsum = arena_take<Xyzz<F>>(ctx, pl.W);
-  if (!pts || !counts || !offs || !cursor || !entries || !buckets || !partials || !wsum) {
-    ctx->err = "scratch arena too small";
-    return B2K_ERR_ARG;
-  }
-  const uint32_t L = slice_len(n, pl, ctx->force_L);
-  const uint32_t smax = (uint32_t)((n * (size_t)pl.W + L - 1) / L) + 1;
-  auto* spart = arena_take<Xyzz<F>>(ctx, 2 * (size_t)smax);
-  auto* big_list = arena_take<uint32_t>(ctx, total + 1);
-  auto* bsum = arena_take<uint32_t>(ctx, 1024);
-  if (!spart || !big_list || !bsum || total > 1024u * 1024u) {
-    ctx->err = "scratch arena too small / too many buckets";
-    return B2K_ERR_ARG;
-  }
-  uint32_t* big_count = bsum + 1023;      // last word of the block-sum page is never a block sum (<= 1023 blocks used)
-  unsigned gb_n = (unsigned)((n + 255) / 256);
-  unsigned sblocks = (unsigned)((total + 1023) / 1024);
-  int nl = 0;
-  CK(cudaEventRecord(ctx->ev[0], st));
-  CK(cudaMemsetAsync(counts, 0, (total + 1) * 4, st));
-  k_load_points<CV><<<gb_n, 256, 0, st>>>(n, d_points, pts); nl++;
-  CK(cudaEventRecord(ctx->ev[1], st));
-  k_msm_count<CV><<<gb_n, 256, 0, st>>>(n, d_scalars, pl, counts, ctx->d_flags); nl++;
-  CK(cudaEventRecord(ctx->ev[2], st));
-  k_scan_blocks<<<sblocks, 1024, 0, st>>>((uint32_t)total, counts, offs, bsum);
-  k_scan_tops<<<1, 1024, 0, st>>>(sblocks, (uint32_t)total, bsum, offs);
-  k_scan_finish<<<sblocks, 1024, 0, st>>>((uint32_t)total, bsum, offs, cursor); nl += 3;
-  CK(cudaEventRecord(ctx->ev[3], st));
-  k_msm_scatter<CV><<<gb_n, 256, 0, st>>>(n, d_scalars, pl, cursor, entries); nl++;
-  if (ctx->use_v1) {
-    CK(cudaEventRecord(ctx->ev[4], st));
-    k_msm_accumulate<CV><<<(unsigned)((total + 127) / 128), 128, 0, st>>>(total, pts, offs, entries, buckets); nl++;
-    CK(cudaEventRecord(ctx->ev[9], st));
-  } else {
-    CK(cudaMemsetAsync(buckets, 0, total * sizeof(Xyzz<F>), st));
-    CK(cudaMemsetAsync(big_count, 0, 4, st));
-    CK(cudaEventRecord(ctx->ev[4], st));
-    k_msm_accumulate_slices<CV><<<(smax + 127) / 128, 128, 0, st>>>(smax, L, (uint32_t)total, pts, offs, entries, buckets, spart); nl++;
-    CK(cudaEventRecord(ctx->ev[9], st));
-    k_msm_fixup<CV><<<(unsigned)((total + 127) / 128), 128, 0, st>>>((uint32_t)total, L, offs, buckets, spart, big_count, big_list);
-    k_msm_fixup_big<CV><<<256, 128, 0, st>>>(L, offs, buckets, spart, big_count, big_list); nl += 2;
-  }
-  CK(cudaEventRecord(ctx->ev[5], st));
-  size_t nchunks = (size_t)pl.W * T;
-  k_msm_reduce_chunks<CV><<<(unsigned)((nchunks + 127) / 128), 128, 0, st>>>(pl, buckets, partials); nl++;
-  CK(cudaEventRecord(ctx->ev[6], st));
-  k_msm_window_sum<CV><<<pl.W, 128, 0, st>>>(T, partials, wsum); nl++;
-  CK(cudaEventRecord(ctx->ev[7], st));
-  k_msm_final<CV><<<1, 128, 0, st>>>(pl, wsum, d_out, affine_out); nl++;
-  CK(cudaEventRecord(ctx->ev[8], st));
-  CK(cudaGetLastError());
-  ctx->launches += (uint64_t)nl;
-  ctx->timings_valid = true;
-  return B2K_OK;
-}
-
-template <class CV>
-int msm_dev(b2k_ctx* ctx, size_t n, const void* d_scalars, const void* d_points, void* d_out, int affine_out = 0) {
-  if (!ctx || !d_scalars || !d_points || !d_out || n == 0 || n >= (size_t(1) << 31)) {
-    if (ctx) ctx->err = "bad argument";
-    return B2K_ERR_ARG;
-  }
-  CK(cudaSetDevice(ctx->device));
-  MsmPlan pl = make_plan(n, ctx->force_c);
-  int rc = arena_reserve(ctx, msm_scratch_bytes<CV>(n, pl, ctx->force_L));
-  if (rc) return rc;
-  return msm_enqueue<CV>(ctx, n, pl, (const uint8_t*)d_scalars, (const uint8_t*)d_points, (uint8_t*)d_out, affine_out);
-}
-
-template <class CV>
-int msm_host(b2k_ctx* ctx, size_t n, const uint8_t* scalars, const uint8_t* points, uint8_t* out) {
-  if (!ctx || !scalars || !points || !out || n == 0 || n >= (size_t(1) << 31)) {
-    if (ctx) ctx->err = "bad argument";
-    return B2K_ERR_ARG;
-  }
-  CK(cudaSetDevice(ctx->device));
-  MsmPlan pl = make_plan(n, ctx->force_c);
-  size_t in_bytes = pad256(n * 32) + pad256(n * (size_t)CV::IN_BYTES) + 256;
-  int rc = arena_reserve(ctx, msm_scratch_bytes<CV>(n, pl, ctx->force_L) + in_bytes);
-  if (rc) return rc;
-  auto* d_s = arena_take<uint8_t>(ctx, n * 32);
-  auto* d_p = arena_take<uint8_t>(ctx, n * (size_t)CV::IN_BYTES);
-  auto* d_o = arena_take<uint8_t>(ctx, 256);
-  CK(cudaMemsetAsync(ctx->d_flags, 0, 4, ctx->stream));
-  CK(cudaMemcpyAsync(d_s, scalars, n * 32, cudaMemcpyHostToDevice, ctx->stream));
-  CK(cudaMemcpyAsync(d_p, points, n * (size_t)CV::IN_BYTES, cudaMemcpyHostToDevice, ctx->stream));
-  rc = msm_enqueue<CV>(ctx, n, pl, d_s, d_p, d_o);
-  if (rc) return rc;
-  CK(cudaMemcpyAsync(out, d_o, CV::OUT_BYTES, cudaMemcpyDeviceToHost, ctx->stream));
-  CK(cudaMemcpyAsync(ctx->h_flags, ctx->d_flags, 4, cudaMemcpyDeviceToHost, ctx->stream));
-  CK(cudaStreamSynchronize(ctx->stream));
-  return check_flags(ctx);
-}
-
-template <class CV, bool AFF>
-int mul_batch_dev(b2k_ctx* ctx, size_t n, const void* d_scalars, const void* d_points, void* d_out) {
-  if (!ctx || !d_scalars || !d_points || !d_out || n == 0) {
-    if (ctx) ctx->err = "bad argument";
-    return B2K_ERR_ARG;
-  }
-  CK(cudaSetDevice(ctx->device));
-  k_mul_batch<CV, AFF><<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(
-      n, (const uint8_t*)d_scalars, (const uint8_t*)d_points, (uint8_t*)d_out, ctx->d_flags);
-  CK(cudaGetLastError());
-  ctx->launches += 1;
-  return B2K_OK;
-}
-
-template <class CV, bool AFF>
-int mul_batch_host(b2k_ctx* ctx, size_t n, const uint8_t* scalars, const uint8_t* points, uint8_t* out) {
-  if (!ctx || !scalars || !points || !out || n == 0) {
-    if (ctx) ctx->err = "bad argument";
-    return B2K_ERR_ARG;
-  }
-  CK(cudaSetDevice(ctx->device));
-  const size_t ob = AFF ? (size_t)CV::IN_BYTES : (size_t)CV::OUT_BYTES;
-  size_t bytes = pad256(n * 32) + pad256(n * (size_t)CV::IN_BYTES) + pad256(n * ob) + 1024;
-  int rc = arena_reserve(ctx, bytes);
-  if (rc) return rc;
-  auto* d_s = arena_take<uint8_t>(ctx, n * 32);
-  auto* d_p = arena_take<uint8_t>(ctx, n * (size_t)CV::IN_BYTES);
-  auto* d_o = arena_take<uint8_t>(ctx, n * ob);
-  CK(cudaMemsetAsync(ctx->d_flags, 0, 4, ctx->stream));
-  CK(cudaMemcpyAsync(d_s, scalars, n * 32, cudaMemcpyHostToDevice, ctx->stream));
-  CK(cudaMemcpyAsync(d_p, points, n * (size_t)CV::IN_BYTES, cudaMemcpyHostToDevice, ctx->stream));
-  rc = mul_batch_dev<CV, AFF>(ctx, n, d_s, d_p, d_o);
-  if (rc) return rc;
-  CK(cudaMemcpyAsync(out, d_o, n * ob, cudaMemcpyDeviceToHost, ctx->stream));
-  CK(cudaMemcpyAsync(ctx->h_flags, ctx->d_flags, 4, cudaMemcpyDeviceToHost, ctx->stream));
-  CK(cudaStreamSynchronize(ctx->stream));
-  return check_flags(ctx);
-}
-
-}  // namespace
+using namespace b2k_host;
 
 // ================================================================================================
 extern "C" {
@@ -378,8 +152,5 @@ int b2k_bls12381_g1_msm(b2k_ctx* c, size_t n, const uint8_t* s, const uint8_t* p
 int b2k_bls12381_g1_msm_dev(b2k_ctx* c, size_t n, const void* s, const void* p, void* o) { return msm_dev<Bls381G1>(c, n, s, p, o); }
 int b2k_bls12381_g1_msm_affine_dev(b2k_ctx* c, size_t n, const void* s, const void* p, void* o) { return msm_dev<Bls381G1>(c, n, s, p, o, 1); }
 
-int b2k_bn254_g1_mul_batch(b2k_ctx* c, size_t n, const uint8_t* s, const uint8_t* p, uint8_t* o) { return mul_batch_host<Bn254G1, false>(c, n, s, p, o); }
-int b2k_bn254_g1_msm(b2k_ctx* c, size_t n, const uint8_t* s, const uint8_t* p, uint8_t* o) { return msm_host<Bn254G1>(c, n, s, p, o); }
-int b2k_bn254_g1_msm_dev(b2k_ctx* c, size_t n, const void* s, const void* p, void* o) { return msm_dev<Bn254G1>(c, n, s, p, o); }
 
 }  // extern "C"

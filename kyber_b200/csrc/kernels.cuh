@@ -57,7 +57,7 @@ __global__ void __launch_bounds__(256) k_msm_count(size_t n, const uint8_t* __re
 
 // ---- MSM stage 2: exclusive scan of the histogram (3 small kernels, 1024 elements per block) -------
 // pass A: per-block exclusive scan + block totals
-__global__ void __launch_bounds__(1024) k_scan_blocks(uint32_t total, const uint32_t* __restrict__ counts,
+static __global__ void __launch_bounds__(1024) k_scan_blocks(uint32_t total, const uint32_t* __restrict__ counts,
                                                       uint32_t* __restrict__ offs, uint32_t* __restrict__ bsum) {
   __shared__ uint32_t wsum[32];
   uint32_t i = blockIdx.x * 1024u + threadIdx.x;
@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(1024) k_scan_blocks(uint32_t total, const uint
   if (i < total) offs[i] = x - v + wsum[warp];
 }
 // pass B: exclusive scan of the block totals (<= 1024 blocks), grand total to offs[total]
-__global__ void __launch_bounds__(1024) k_scan_tops(uint32_t nblocks, uint32_t total, uint32_t* __restrict__ bsum,
+static __global__ void __launch_bounds__(1024) k_scan_tops(uint32_t nblocks, uint32_t total, uint32_t* __restrict__ bsum,
                                                     uint32_t* __restrict__ offs) {
   __shared__ uint32_t sm[1024];
   int tid = threadIdx.x;
@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(1024) k_scan_tops(uint32_t nblocks, uint32_t t
   if (tid == 1023) offs[total] = sm[1023];
 }
 // pass C: add block offsets, duplicate into the scatter cursor
-__global__ void __launch_bounds__(1024) k_scan_finish(uint32_t total, const uint32_t* __restrict__ bsum,
+static __global__ void __launch_bounds__(1024) k_scan_finish(uint32_t total, const uint32_t* __restrict__ bsum,
                                                       uint32_t* __restrict__ offs, uint32_t* __restrict__ cursor) {
   uint32_t i = blockIdx.x * 1024u + threadIdx.x;
   if (i >= total) return;

@@ -11,7 +11,7 @@
 
 #if defined(__CUDACC__)
 #define B2K_D __device__ __forceinline__
-#define B2K_NI __device__ __noinline__
+#define B2K_NI static __device__ __noinline__
 #else
 #define B2K_D inline
 #define B2K_NI inline

@@ -520,3 +520,35 @@ def gt_from_bytes(b: bytes):
     v = [int.from_bytes(b[i * 48:(i + 1) * 48], "big") for i in range(12)]
     f2s = [(v[2 * i + 1], v[2 * i]) for i in range(6)]          # order: c1.c2, c1.c1, c1.c0, c0.c2, c0.c1, c0.c0
     return ((f2s[5], f2s[4], f2s[3]), (f2s[2], f2s[1], f2s[0]))
+
+
+# ----------------------------------------------------------------------------- fast subgroup tests
+# Endomorphism-based membership tests (M. Scott, "A note on group membership tests for G1, G2 and GT on
+# BLS pairing-friendly curves", 2021 [FROM MEMORY]); the engine uses these on the device.  They are
+# validated here against the definition ([r]P = inf) in tests/test_oracle_bls12381.py.
+BETA = pow(2, (P - 1) // 3, P)
+if (BETA * G1_X % P, G1_Y) != g1_mul((-X_ABS * X_ABS) % R, G1):
+    BETA = BETA * BETA % P
+assert (BETA * G1_X % P, G1_Y) == g1_mul((-X_ABS * X_ABS) % R, G1)    # phi(P) = [-x^2]P on G1
+PSI_CX = f2_inv(f2_pow(XI, (P - 1) // 3))
+PSI_CY = f2_inv(f2_pow(XI, (P - 1) // 2))
+
+
+def g1_in_subgroup_fast(pt) -> bool:
+    """[x^2]P + phi(P) == inf,  phi(x,y) = (BETA x, y)."""
+    if pt is None:
+        return True
+    t = g1_mul(X_ABS, g1_mul(X_ABS, pt))
+    return g1_add(t, (BETA * pt[0] % P, pt[1])) is None
+
+
+def g2_psi(pt):
+    """untwist-Frobenius-twist endomorphism; acts as [p] = [x] on G2."""
+    return (f2_mul(f2_conj(pt[0]), PSI_CX), f2_mul(f2_conj(pt[1]), PSI_CY))
+
+
+def g2_in_subgroup_fast(pt) -> bool:
+    """psi(P) == [x]P = -[|x|]P."""
+    if pt is None:
+        return True
+    return g2_psi(pt) == g2_neg(g2_mul(X_ABS, pt))

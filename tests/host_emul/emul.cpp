@@ -133,3 +133,22 @@ int emul_bls12381_pairing_check(const uint8_t* a1, const uint8_t* a2, const uint
   return fp12_is_one(e) ? 1 : 0;
 }
 }
+
+// ------------------------------------------------------------------------------------------------
+#include "../../kyber_b200/csrc/codec.cuh"
+extern "C" {
+int emul_bls12381_g1_decompress(const uint8_t* in48, uint8_t* out96) {
+  Affine<BFp> a;
+  bool ok = g1_decompress(a, in48, true);
+  if (ok) Bls381G1::store_affine(out96, a);
+  return ok ? 1 : 0;
+}
+int emul_bls12381_g2_decompress(const uint8_t* in96, uint8_t* out192) {
+  Affine<BFp2> a;
+  bool ok = g2_decompress(a, in96, true);
+  if (ok) Bls381G2::store_affine(out192, a);
+  return ok ? 1 : 0;
+}
+void emul_bls12381_g2_mul_batch(size_t n, const uint8_t* s, const uint8_t* p, uint8_t* o) { emul_mul_batch<Bls381G2>(n, s, p, o); }
+int emul_bls12381_g2_msm(size_t n, const uint8_t* s, const uint8_t* p, int c, int m, int L, uint8_t* o) { return emul_msm<Bls381G2>(n, s, p, c, m, o, L); }
+}
