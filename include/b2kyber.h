@@ -120,6 +120,26 @@ int b2k_bls12381_g2_decompress(b2k_ctx* ctx, size_t n, const uint8_t* in /*[n][9
                                uint8_t* ok /*[n]*/);
 int b2k_bls12381_g2_decompress_dev(b2k_ctx* ctx, size_t n, const void* d_in, void* d_out, void* d_ok);
 
+/* ---- BLS12-381 hash-to-G1 and signature verification ------------------------------------------------- */
+/* out[i] = hash_to_curve(msgs[offsets[i] .. offsets[i+1]), dst) in operand form (96 B), RFC 9380 suite
+ * BLS12381G1_XMD:SHA-256_SSWU_RO_.   replaces: kilic.G1Elt.Hash, pairing/bls12381/kilic/g1.go:161-170
+ * (default DST "BLS_SIG_BLS12381G1_XMD:SHA-256_SSWU_RO_NUL_", g1.go:17; suite override suite.go:32-46).
+ * offsets are n+1 uint32 byte offsets into msgs; 0 < dst_len <= 255. */
+int b2k_bls12381_hash_to_g1(b2k_ctx* ctx, size_t n, const uint8_t* msgs, const uint32_t* offsets /*[n+1]*/,
+                            const uint8_t* dst, uint32_t dst_len, uint8_t* out /*[n][96]*/);
+int b2k_bls12381_hash_to_g1_dev(b2k_ctx* ctx, size_t n, const void* d_msgs, const void* d_offsets, const void* d_dst,
+                                uint32_t dst_len, void* d_out);
+/* ok[i] = 1 iff bls.Verify(pk_i, msg_i, sig_i) == nil for the scheme with signatures on G1
+ * (bls.NewSchemeOnG1, sign/bls/bls.go:33-44,82-96): UnmarshalBinary of the 96-byte compressed G2 key and
+ * the 48-byte compressed G1 signature (subgroup checks included), H(msg), then
+ * ValidatePairing(H(m), pk, sig, G2 generator) (kilic/suite.go:57-68).  One call = n independent
+ * verifications = the loop of util/test/benchmark.go:62-71 (BLSBenchVerify). */
+int b2k_bls12381_verify_g1sig(b2k_ctx* ctx, size_t n, const uint8_t* pks /*[n][96]*/, const uint8_t* msgs,
+                              const uint32_t* offsets /*[n+1]*/, const uint8_t* dst, uint32_t dst_len,
+                              const uint8_t* sigs /*[n][48]*/, uint8_t* ok /*[n]*/);
+int b2k_bls12381_verify_g1sig_dev(b2k_ctx* ctx, size_t n, const void* d_pks, const void* d_msgs, const void* d_offsets,
+                                  const void* d_dst, uint32_t dst_len, const void* d_sigs, void* d_ok);
+
 /* ---- BLS12-381 pairings ---------------------------------------------------------------------------- */
 /* gt[i] = e(g1[i], g2[i]); g2 operands are 192 B: x.c1||x.c0||y.c1||y.c0.  GT = 576 B, 12 x 48 B
  * big-endian, highest tower coefficient first (kilic/gt.go:115-117), exponent exactly (p^12-1)/r.

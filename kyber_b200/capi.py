@@ -42,6 +42,10 @@ def load_library() -> C.CDLL:
     sigs["b2k_bls12381_pair_dev"] = (C.c_int, [vp, sz, vp, vp, vp])
     sigs["b2k_bls12381_pairing_check"] = (C.c_int, [vp, sz, vp, vp, vp, vp, vp])
     sigs["b2k_bls12381_pairing_check_dev"] = (C.c_int, [vp, sz, vp, vp, vp, vp, vp])
+    sigs["b2k_bls12381_hash_to_g1"] = (C.c_int, [vp, sz, vp, vp, vp, C.c_uint32, vp])
+    sigs["b2k_bls12381_hash_to_g1_dev"] = (C.c_int, [vp, sz, vp, vp, vp, C.c_uint32, vp])
+    sigs["b2k_bls12381_verify_g1sig"] = (C.c_int, [vp, sz, vp, vp, vp, vp, C.c_uint32, vp, vp])
+    sigs["b2k_bls12381_verify_g1sig_dev"] = (C.c_int, [vp, sz, vp, vp, vp, vp, C.c_uint32, vp, vp])
     host3 = (C.c_int, [vp, sz, vp, vp, vp])
     for name in HOST_FUNCS + DEV_FUNCS:
         sigs[name] = host3
@@ -186,6 +190,37 @@ class Engine:
 
     def bls12381_g2_decompress(self, data: bytes):
         return self._decompress("b2k_bls12381_g2_decompress", data, 96, 192)
+
+    # -- hash-to-G1 / BLS verify -------------------------------------------------------------------------
+    @staticmethod
+    def _pack_msgs(msgs):
+        import struct
+        offs, blob, pos = [0], b"", 0
+        for m in msgs:
+            pos += len(m)
+            offs.append(pos)
+        blob = b"".join(msgs) or b"\x00"
+        return blob, struct.pack("<%dI" % len(offs), *offs)
+
+    def bls12381_hash_to_g1(self, msgs, dst: bytes) -> bytes:
+        """msgs: list of bytes -> operand bytes [n][96]"""
+        n = len(msgs)
+        blob, offs = self._pack_msgs(msgs)
+        out = bytearray(96 * n)
+        bufs = [_buf(x) for x in (blob, offs, dst, out)]
+        self._check(self.lib.b2k_bls12381_hash_to_g1(self.h, n, bufs[0][0], bufs[1][0], bufs[2][0], len(dst), bufs[3][0]))
+        return bytes(out)
+
+    def bls12381_verify_g1sig(self, pks: bytes, msgs, dst: bytes, sigs: bytes) -> bytes:
+        """n x bls.Verify (sigs on G1): pks [n][96] compressed G2, sigs [n][48] compressed G1 -> ok flags [n]"""
+        n = len(msgs)
+        assert len(pks) == 96 * n and len(sigs) == 48 * n
+        blob, offs = self._pack_msgs(msgs)
+        ok = bytearray(n)
+        bufs = [_buf(x) for x in (pks, blob, offs, dst, sigs, ok)]
+        self._check(self.lib.b2k_bls12381_verify_g1sig(self.h, n, bufs[0][0], bufs[1][0], bufs[2][0], bufs[3][0], len(dst),
+                                                       bufs[4][0], bufs[5][0]))
+        return bytes(ok)
 
     # -- BLS12-381 pairings ---------------------------------------------------------------------------
     def bls12381_pair(self, g1: bytes, g2: bytes) -> bytes:

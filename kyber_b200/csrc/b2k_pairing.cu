@@ -50,7 +50,7 @@ int b2k_bls12381_pairing_check_dev(b2k_ctx* ctx, size_t n, const void* a1, const
   if (!ctx || !a1 || !a2 || !b1 || !b2 || !d_ok || n == 0) return B2K_ERR_ARG;
   CK(cudaSetDevice(ctx->device));
   k_bls_pairing_check<<<(unsigned)((n + 63) / 64), 64, 0, ctx->stream>>>(
-      n, (const uint8_t*)a1, (const uint8_t*)a2, (const uint8_t*)b1, (const uint8_t*)b2, (uint8_t*)d_ok);
+      n, (const uint8_t*)a1, (const uint8_t*)a2, (const uint8_t*)b1, (const uint8_t*)b2, (uint8_t*)d_ok, 0, nullptr);
   CK(cudaGetLastError());
   ctx->launches += 1;
   return B2K_OK;
