@@ -207,6 +207,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     from kyber_b200 import Engine, workload as wl
+    from kyber_b200.multi import msm_sharded
     from oracle import bls12381 as o
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -243,7 +244,6 @@ def run_ours(args):
         assert bytes(h_pts[96 * i:96 * i + 96].tolist()) == o.g1_to_affine_bytes(o.g1_mul(a[i])), "bad input point"
     d_scal = h_scal.to(dev)
     d_out = torch.zeros(96, dtype=torch.uint8, device=dev)
-    d_gather = torch.zeros(world * 96, dtype=torch.uint8, device=dev)
     d_ones = torch.frombuffer(bytearray(b"".join((1).to_bytes(32, "big") for _ in range(world))),
                               dtype=torch.uint8).to(dev)
     d_final = torch.zeros(64, dtype=torch.uint8, device=dev)
@@ -254,9 +254,14 @@ def run_ours(args):
         if world == 1:
             eng.call_dev("b2k_bls12381_g1_msm_dev", n, d_scal.data_ptr(), d_pts.data_ptr(), d_final.data_ptr())
         else:
-            eng.call_dev("b2k_bls12381_g1_msm_affine_dev", n, d_scal.data_ptr(), d_pts.data_ptr(), d_out.data_ptr())
-            dist.all_gather_into_tensor(d_gather, d_out)            # the ONE exchange: world x 96 B
-            eng.call_dev("b2k_bls12381_g1_msm_dev", world, d_ones.data_ptr(), d_gather.data_ptr(), d_final.data_ptr())
+            def local_partial():
+                eng.call_dev("b2k_bls12381_g1_msm_affine_dev", n, d_scal.data_ptr(), d_pts.data_ptr(), d_out.data_ptr())
+                return d_out
+
+            def combine(gathered, w):                              # add the partials: MSM with unit scalars
+                eng.call_dev("b2k_bls12381_g1_msm_dev", w, d_ones.data_ptr(), gathered.data_ptr(), d_final.data_ptr())
+                return d_final
+            msm_sharded(local_partial, combine)                    # the ONE exchange: ncclAllGather of world x 96 B
 
     def barrier():
         if world > 1:

@@ -163,6 +163,12 @@ int b2k_bn254_g1_mul_batch(b2k_ctx* ctx, size_t n, const uint8_t* scalars /*[n][
 int b2k_bn254_g1_msm(b2k_ctx* ctx, size_t n, const uint8_t* scalars /*[n][32]*/,
                      const uint8_t* points /*[n][64]*/, uint8_t* out /*[64]*/);
 int b2k_bn254_g1_msm_dev(b2k_ctx* ctx, size_t n, const void* d_scalars, const void* d_points, void* d_out);
+/* out = sum_i lambda_i * points[i] with lambda_i = prod_{j!=i} x_j / (x_j - x_i) mod r, x_i = indices[i] + 1:
+ * the whole of share.RecoverCommit (share/poly.go:449-476) after xyCommit's sort/selection (poly.go:418-445):
+ * Lagrange weights (t^2 scalar products + t inversions) and the t-term MSM both run on the device.
+ * Duplicate indices -> B2K_ERR_ARG. */
+int b2k_bn254_recover_commit(b2k_ctx* ctx, size_t t, const uint32_t* indices /*[t]*/, const uint8_t* points /*[t][64]*/,
+                             uint8_t* out /*[64]*/);
 
 #ifdef __cplusplus
 }

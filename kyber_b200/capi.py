@@ -46,6 +46,7 @@ def load_library() -> C.CDLL:
     sigs["b2k_bls12381_hash_to_g1_dev"] = (C.c_int, [vp, sz, vp, vp, vp, C.c_uint32, vp])
     sigs["b2k_bls12381_verify_g1sig"] = (C.c_int, [vp, sz, vp, vp, vp, vp, C.c_uint32, vp, vp])
     sigs["b2k_bls12381_verify_g1sig_dev"] = (C.c_int, [vp, sz, vp, vp, vp, vp, C.c_uint32, vp, vp])
+    sigs["b2k_bn254_recover_commit"] = (C.c_int, [vp, sz, vp, vp, vp])
     host3 = (C.c_int, [vp, sz, vp, vp, vp])
     for name in HOST_FUNCS + DEV_FUNCS:
         sigs[name] = host3
@@ -241,6 +242,13 @@ class Engine:
         n = len(scalars) // 32
         assert len(scalars) == 32 * n and len(points) == 64 * n
         return self.call_host("b2k_bn254_g1_mul_batch", n, scalars, points, 64 * n)
+
+    def bn254_recover_commit(self, indices, points: bytes) -> bytes:
+        """share.RecoverCommit over bn254 G1: indices = share indices I_i (x_i = I_i + 1), points [t][64] -> 64 B"""
+        import struct
+        t = len(indices)
+        assert len(points) == 64 * t
+        return self.call_host("b2k_bn254_recover_commit", t, struct.pack("<%dI" % t, *indices), points, 64)
 
     def bn254_g1_msm(self, scalars: bytes, points: bytes) -> bytes:
         n = len(scalars) // 32

@@ -7,7 +7,7 @@
 // Accept/reject behaviour is pinned by the reference's 16 + 18 ZCash fixtures
 // (pairing/bls12381/deserialization_tests, tests/golden/bls12381_deserialization.json):
 //   flag bits (bit7 compressed, bit6 infinity, bit5 sign), x < p, on curve, in the r-torsion subgroup.
-// Subgroup tests use the curve endomorphisms (validated against [r]P = inf in the oracle tests):
+// Subgroup tests use the curve endomorphisms (validated against [r]P = inf in tests/):
 //   G1:  [x^2]P + phi(P) == inf,   phi(x,y) = (beta x, y)
 //   G2:  psi(P) == [x]P,           psi = twist o Frobenius o untwist
 #pragma once
