@@ -107,6 +107,11 @@ int b2k_bls12381_g2_msm(b2k_ctx* ctx, size_t n, const uint8_t* scalars /*[n][32]
                         const uint8_t* points /*[n][192]*/, uint8_t* out /*[96]*/);
 int b2k_bls12381_g2_msm_dev(b2k_ctx* ctx, size_t n, const void* d_scalars, const void* d_points, void* d_out);
 
+/* MSM with the sum in OPERAND form (G1 96 B / G2 192 B), host buffers: what the adapter's Point.Add / Sub use
+ * (unit scalars) so that results stay in operand form between operations. */
+int b2k_bls12381_g1_msm_affine(b2k_ctx* ctx, size_t n, const uint8_t* scalars, const uint8_t* points, uint8_t* out /*[96]*/);
+int b2k_bls12381_g2_msm_affine(b2k_ctx* ctx, size_t n, const uint8_t* scalars, const uint8_t* points, uint8_t* out /*[192]*/);
+
 /* ---- BLS12-381 UnmarshalBinary (decompress + subgroup check) --------------------------------------------- */
 /* out[i] = operand form of the ZCash-compressed input, ok[i] = 1, or ok[i] = 0 (out[i] zeroed) when the
  * reference's UnmarshalBinary would return an error: wrong flag bits, x >= p, not on the curve, not in the
@@ -169,6 +174,16 @@ int b2k_bn254_g1_msm_dev(b2k_ctx* ctx, size_t n, const void* d_scalars, const vo
  * Duplicate indices -> B2K_ERR_ARG. */
 int b2k_bn254_recover_commit(b2k_ctx* ctx, size_t t, const uint32_t* indices /*[t]*/, const uint8_t* points /*[t][64]*/,
                              uint8_t* out /*[64]*/);
+
+/* ---- edwards25519 ---------------------------------------------------------------------------------------- */
+/* out[i] = scalars[i] * points[i] on edwards25519.  scalars: RAW 256-bit little-endian integers (the reference
+ * does not reduce on UnmarshalBinary, group/edwards25519/scalar.go:226-233); points and results: 32-byte
+ * compressed (ge.go:99-150; non-canonical y accepted).  A point that does not decode -> B2K_ERR_POINT
+ * (its output zeroed).   replaces: point.Mul, group/edwards25519/point.go:235-258 (geScalarMult, ge.go:443-502)
+ * in loops such as util/test/group.go:118-122. */
+int b2k_ed25519_mul_batch(b2k_ctx* ctx, size_t n, const uint8_t* scalars /*[n][32] LE*/,
+                          const uint8_t* points /*[n][32]*/, uint8_t* out /*[n][32]*/);
+int b2k_ed25519_mul_batch_dev(b2k_ctx* ctx, size_t n, const void* d_scalars, const void* d_points, void* d_out);
 
 #ifdef __cplusplus
 }

@@ -57,16 +57,17 @@ def load_library() -> C.CDLL:
 
 
 HOST_FUNCS = [
+    "b2k_bls12381_g1_msm_affine", "b2k_bls12381_g2_msm_affine",
     "b2k_bls12381_g2_mul_batch", "b2k_bls12381_g2_mul_batch_affine", "b2k_bls12381_g2_msm",
     "b2k_bls12381_g1_decompress", "b2k_bls12381_g2_decompress",
     "b2k_bls12381_g1_mul_batch", "b2k_bls12381_g1_mul_batch_affine", "b2k_bls12381_g1_msm",
-    "b2k_bn254_g1_mul_batch", "b2k_bn254_g1_msm",
+    "b2k_bn254_g1_mul_batch", "b2k_bn254_g1_msm", "b2k_ed25519_mul_batch",
 ]
 DEV_FUNCS = [
     "b2k_bls12381_g2_mul_batch_affine_dev", "b2k_bls12381_g2_msm_dev",
     "b2k_bls12381_g1_decompress_dev", "b2k_bls12381_g2_decompress_dev",
     "b2k_bls12381_g1_mul_batch_dev", "b2k_bls12381_g1_mul_batch_affine_dev", "b2k_bls12381_g1_msm_dev",
-    "b2k_bls12381_g1_msm_affine_dev", "b2k_bn254_g1_msm_dev",
+    "b2k_bls12381_g1_msm_affine_dev", "b2k_bn254_g1_msm_dev", "b2k_ed25519_mul_batch_dev",
 ]
 
 
@@ -242,6 +243,12 @@ class Engine:
         n = len(scalars) // 32
         assert len(scalars) == 32 * n and len(points) == 64 * n
         return self.call_host("b2k_bn254_g1_mul_batch", n, scalars, points, 64 * n)
+
+    def ed25519_mul_batch(self, scalars_le: bytes, points: bytes) -> bytes:
+        """n x edwards25519 Point.Mul: raw little-endian 32-byte scalars, 32-byte compressed points -> 32 B each"""
+        n = len(scalars_le) // 32
+        assert len(scalars_le) == 32 * n and len(points) == 32 * n
+        return self.call_host("b2k_ed25519_mul_batch", n, scalars_le, points, 32 * n)
 
     def bn254_recover_commit(self, indices, points: bytes) -> bytes:
         """share.RecoverCommit over bn254 G1: indices = share indices I_i (x_i = I_i + 1), points [t][64] -> 64 B"""

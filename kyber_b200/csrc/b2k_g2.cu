@@ -78,5 +78,6 @@ int b2k_bls12381_g2_mul_batch(b2k_ctx* c, size_t n, const uint8_t* s, const uint
 int b2k_bls12381_g2_mul_batch_affine(b2k_ctx* c, size_t n, const uint8_t* s, const uint8_t* p, uint8_t* o) { return mul_batch_host<Bls381G2, true>(c, n, s, p, o); }
 int b2k_bls12381_g2_mul_batch_affine_dev(b2k_ctx* c, size_t n, const void* s, const void* p, void* o) { return mul_batch_dev<Bls381G2, true>(c, n, s, p, o); }
 int b2k_bls12381_g2_msm(b2k_ctx* c, size_t n, const uint8_t* s, const uint8_t* p, uint8_t* o) { return msm_host<Bls381G2>(c, n, s, p, o); }
+int b2k_bls12381_g2_msm_affine(b2k_ctx* c, size_t n, const uint8_t* s, const uint8_t* p, uint8_t* o) { return msm_host<Bls381G2>(c, n, s, p, o, 1); }
 int b2k_bls12381_g2_msm_dev(b2k_ctx* c, size_t n, const void* s, const void* p, void* o) { return msm_dev<Bls381G2>(c, n, s, p, o); }
 }  // extern "C"

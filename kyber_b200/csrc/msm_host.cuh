@@ -178,7 +178,7 @@ int msm_dev(b2k_ctx* ctx, size_t n, const void* d_scalars, const void* d_points,
 }
 
 template <class CV>
-int msm_host(b2k_ctx* ctx, size_t n, const uint8_t* scalars, const uint8_t* points, uint8_t* out) {
+int msm_host(b2k_ctx* ctx, size_t n, const uint8_t* scalars, const uint8_t* points, uint8_t* out, int affine_out = 0) {
   if (!ctx || !scalars || !points || !out || n == 0 || n >= (size_t(1) << 31)) {
     if (ctx) ctx->err = "bad argument";
     return B2K_ERR_ARG;
@@ -194,9 +194,9 @@ int msm_host(b2k_ctx* ctx, size_t n, const uint8_t* scalars, const uint8_t* poin
   CK(cudaMemsetAsync(ctx->d_flags, 0, 4, ctx->stream));
   CK(cudaMemcpyAsync(d_s, scalars, n * 32, cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyAsync(d_p, points, n * (size_t)CV::IN_BYTES, cudaMemcpyHostToDevice, ctx->stream));
-  rc = msm_enqueue<CV>(ctx, n, pl, d_s, d_p, d_o);
+  rc = msm_enqueue<CV>(ctx, n, pl, d_s, d_p, d_o, affine_out);
   if (rc) return rc;
-  CK(cudaMemcpyAsync(out, d_o, CV::OUT_BYTES, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(out, d_o, affine_out ? CV::IN_BYTES : CV::OUT_BYTES, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaMemcpyAsync(ctx->h_flags, ctx->d_flags, 4, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   return check_flags(ctx);

@@ -1,0 +1,135 @@
+// Conformance test of the C++ host mirror (kyber_b200/host/kyber_b200.hpp) against the engine, written after
+// the reference's own generic tests: testGroup (pairing/bls12381/bls12381_test.go:196-418 = util/test/test.go:
+// 325-401), the pairing property tests (:448-474, :580-631) and sign/bls tests (sign/bls/bls_test.go).
+// Run by tests/test_gpu_cpp_host.py on the GPU box.  Prints "ok <name>" per check; exit code != 0 on failure.
+#include <cstdio>
+#include <cstdlib>
+#include <random>
+#include "../../kyber_b200/host/kyber_b200.hpp"
+
+using namespace b200;
+static int fails = 0;
+#define CHECK(name, cond) do { if (cond) printf("ok %s\n", name); else { printf("FAIL %s (line %d)\n", name, __LINE__); fails++; } } while (0)
+
+static Scalar pick(std::mt19937_64& g) {       // Scalar.Pick stand-in: uniform bytes reduced mod r
+  Bytes b(40);
+  for (auto& x : b) x = (uint8_t)g();
+  Scalar s; s.SetBytes(b); return s;
+}
+
+template <class E, class G>
+static void test_group(const char* tag, const G& grp, std::shared_ptr<Engine> eng, std::mt19937_64& rng) {
+  char nm[128];
+  auto N = [&](const char* s) { snprintf(nm, sizeof nm, "%s.%s", tag, s); return nm; };
+  Scalar s1 = pick(rng), s2 = pick(rng), st;
+  E gen(eng), p1(eng), p2(eng), dh1(eng), dh2(eng), pt(eng), zero(eng);
+  gen.Base(); zero.Null();
+  CHECK(N("generator_not_identity"), !gen.Equal(zero));
+  // Diffie-Hellman: s2*(s1*G) == s1*(s2*G)
+  p1.Mul(s1, nullptr); p2.Mul(s2, nullptr);
+  CHECK(N("pubkeys_differ"), !p1.Equal(p2));
+  dh1.Mul(s2, &p1); dh2.Mul(s1, &p2);
+  CHECK(N("dh"), dh1.Equal(dh2));
+  // additive homomorphism: (s1+s2)G == s1 G + s2 G ; Sub ; Neg
+  st.Add(s1, s2); pt.Mul(st, nullptr);
+  E sum(eng); sum.Add(p1, p2);
+  CHECK(N("add_homomorphism"), pt.Equal(sum));
+  E back(eng); back.Sub(sum, p2);
+  CHECK(N("sub"), back.Equal(p1));
+  E neg(eng); neg.Neg(p1); E z(eng); z.Add(p1, neg);
+  CHECK(N("neg_gives_identity"), z.Equal(zero));
+  // multiplicative: s1*(s2*G) == (s1*s2)*G ; division
+  st.Mul(s1, s2); pt.Mul(st, nullptr);
+  CHECK(N("mul_homomorphism"), pt.Equal(dh1));
+  Scalar inv; inv.Div(st, s2);
+  CHECK(N("scalar_div"), inv.Equal(s1));
+  // aliasing receiver == argument (bls.go:73)
+  E al(eng); al.Set(p1); al.Mul(s2, &al);
+  CHECK(N("aliasing_mul"), al.Equal(dh1));
+  al.Set(p1); al.Add(al, al); E dbl(eng); Scalar two(2); dbl.Mul(two, &p1);
+  CHECK(N("aliasing_add_doubling"), al.Equal(dbl));
+  // marshal round trip, identity included; wrong sizes and garbage are errors
+  Bytes enc = p1.MarshalBinary();
+  CHECK(N("marshal_size"), (int)enc.size() == grp.PointLen());
+  E dec(eng); dec.UnmarshalBinary(enc);
+  CHECK(N("marshal_roundtrip"), dec.Equal(p1));
+  Bytes ze = zero.MarshalBinary();
+  CHECK(N("identity_encoding"), ze[0] == 0xC0);
+  dec.UnmarshalBinary(ze);
+  CHECK(N("identity_roundtrip"), dec.Equal(zero));
+  bool threw = false;
+  try { Bytes bad(enc.begin(), enc.end() - 1); dec.UnmarshalBinary(bad); } catch (const std::runtime_error&) { threw = true; }
+  CHECK(N("unmarshal_wrong_size_is_error"), threw);
+  threw = false;
+  try { Bytes bad = enc; bad[0] &= 0x7f; dec.UnmarshalBinary(bad); } catch (const std::runtime_error&) { threw = true; }
+  CHECK(N("unmarshal_bad_flags_is_error"), threw);
+  CHECK(N("is_in_correct_group"), p1.IsInCorrectGroup());
+  // batch extension == loops
+  std::vector<Scalar> ss; std::vector<E> pp;
+  E acc(eng); acc.Null();
+  for (int i = 0; i < 9; i++) { ss.push_back(pick(rng)); E q(eng); q.Mul(pick(rng), nullptr); pp.push_back(q); }
+  auto mb = grp.MulBatch(ss, pp);
+  bool all = true;
+  for (int i = 0; i < 9; i++) { E t(eng); t.Mul(ss[i], &pp[i]); all = all && t.Equal(mb[i]); acc.Add(acc, t); }
+  CHECK(N("mul_batch_equals_loop"), all);
+  CHECK(N("msm_equals_mul_add_loop"), grp.MSM(ss, pp).Equal(acc));
+}
+
+int main() {
+  std::mt19937_64 rng(20260923);
+  Suite suite(0);
+  auto eng = suite.engine();
+  // scalar wire format (TestScalarEndianess, bls12381_test.go:41-72)
+  Scalar one; one.One();
+  Bytes ob = one.MarshalBinary();
+  CHECK("scalar.big_endian_one", ob.size() == 32 && ob[31] == 1 && ob[0] == 0);
+  Scalar a = pick(rng), ai, prod; ai.Inv(a); prod.Mul(a, ai);
+  CHECK("scalar.inverse", prod.Equal(one));
+  bool threw = false;
+  try { Bytes rb(32); for (int i = 0; i < 4; i++) for (int k = 0; k < 8; k++) rb[(3 - i) * 8 + k] = (uint8_t)(Scalar::R[i] >> (56 - 8 * k)); Scalar t; t.UnmarshalBinary(rb); } catch (const std::runtime_error&) { threw = true; }
+  CHECK("scalar.unmarshal_rejects_modulus", threw);
+  CHECK("group.names", suite.G1().String() == "bls12-381.G1" && suite.G2().String() == "bls12-381.G2" && suite.G1().PointLen() == 48 && suite.G2().PointLen() == 96 && suite.G1().ScalarLen() == 32);
+
+  test_group<G1Elt>("G1", suite.G1(), eng, rng);
+  test_group<G2Elt>("G2", suite.G2(), eng, rng);
+
+  // pairing: bilinearity e(aG1,bG2) == e(abG1,G2) (bls12381_test.go:448-474) and the a*b = c+d identity via
+  // ValidatePairing semantics e(p1,p2) == e(inv1,inv2)
+  Scalar sa = pick(rng), sb = pick(rng), sab; sab.Mul(sa, sb);
+  G1Elt pa(eng), pab(eng), g1(eng); G2Elt qb(eng), g2(eng);
+  g1.Base(); g2.Base(); pa.Mul(sa, nullptr); qb.Mul(sb, nullptr); pab.Mul(sab, nullptr);
+  GTElt e1 = suite.Pair(pa, qb), e2 = suite.Pair(pab, g2);
+  CHECK("pairing.bilinear_gt_equal", e1.Equal(e2));
+  CHECK("pairing.gt_size", e1.MarshalSize() == 576 && !e1.Equal(suite.Pair(g1, g2)));
+  CHECK("pairing.validate_true", suite.ValidatePairing(pa, qb, pab, g2));
+  G1Elt wrong(eng); Scalar sab1; sab1.Add(sab, one); wrong.Mul(sab1, nullptr);
+  CHECK("pairing.validate_false", !suite.ValidatePairing(pa, qb, wrong, g2));
+  auto vb = suite.ValidatePairingBatch({pa, pa}, {qb, qb}, {pab, wrong}, {g2, g2});
+  CHECK("pairing.validate_batch", vb.size() == 2 && vb[0] && !vb[1]);
+  bool panicked = false;
+  try { suite.Pair(qb, pa); } catch (const std::logic_error&) { panicked = true; }
+  CHECK("pairing.wrong_group_panics", panicked);
+
+  // sign/bls on G1 (sign/bls/bls.go:33-96): sign, verify, reject wrong message / key / mangled signature
+  SchemeOnG1 scheme(suite);
+  Scalar sk = pick(rng), sk2 = pick(rng);
+  G2Elt pk(eng), pk2(eng); pk.Mul(sk, nullptr); pk2.Mul(sk2, nullptr);
+  Bytes msg = {'H', 'e', 'l', 'l', 'o', ' ', 'B', 'o', 'n', 'e', 'h', '-', 'L', 'y', 'n', 'n', '-', 'S', 'h', 'a', 'c', 'h', 'a', 'm'};
+  Bytes sig = scheme.Sign(sk, msg);
+  CHECK("bls.sign_size", sig.size() == 48);
+  CHECK("bls.verify", scheme.Verify(pk, msg, sig));
+  Bytes msg2 = msg; msg2[0] ^= 1;
+  CHECK("bls.verify_wrong_msg_fails", !scheme.Verify(pk, msg2, sig));
+  CHECK("bls.verify_wrong_key_fails", !scheme.Verify(pk2, msg, sig));
+  Bytes sig2 = sig; sig2[20] ^= 0x40;
+  CHECK("bls.verify_mangled_sig_fails", !scheme.Verify(pk, msg, sig2));
+  // TestSignatureEdgeCase (bls12381_test.go:877-904), bytes from the reference test
+  static const uint8_t pkb[96] = {0x83, 0xcf, 0xf, 0x28, 0x96, 0xad, 0xee, 0x7e, 0xb8, 0xb5, 0xf0, 0x1f, 0xca, 0xd3, 0x91, 0x22, 0x12, 0xc4, 0x37, 0xe0, 0x7, 0x3e, 0x91, 0x1f, 0xb9, 0x0, 0x22, 0xd3, 0xe7, 0x60, 0x18, 0x3c, 0x8c, 0x4b, 0x45, 0xb, 0x6a, 0xa, 0x6c, 0x3a, 0xc6, 0xa5, 0x77, 0x6a, 0x2d, 0x10, 0x64, 0x51, 0xd, 0x1f, 0xec, 0x75, 0x8c, 0x92, 0x1c, 0xc2, 0x2b, 0xe, 0x17, 0xe6, 0x3a, 0xaf, 0x4b, 0xcb, 0x5e, 0xd6, 0x63, 0x4, 0xde, 0x9c, 0xf8, 0x9, 0xbd, 0x27, 0x4c, 0xa7, 0x3b, 0xab, 0x4a, 0xf5, 0xa6, 0xe9, 0xc7, 0x6a, 0x4b, 0xc0, 0x9e, 0x76, 0xea, 0xe8, 0x99, 0x1e, 0xf5, 0xec, 0xe4, 0x5a};
+  static const uint8_t mb[32] = {0xa1, 0xc6, 0xbe, 0xc3, 0xb9, 0xa6, 0xf0, 0x98, 0x9d, 0x4d, 0x80, 0x2d, 0xbf, 0xe2, 0xb9, 0xb, 0x49, 0x5f, 0xa1, 0x74, 0x2b, 0x58, 0x99, 0x63, 0x45, 0x1e, 0xeb, 0xa9, 0xb1, 0x87, 0xb8, 0x15};
+  static const uint8_t sgb[48] = {0x95, 0x89, 0x0, 0x9b, 0x47, 0xbf, 0xd9, 0xe3, 0x65, 0x10, 0x6b, 0x11, 0xa3, 0x42, 0xfe, 0x50, 0x75, 0xeb, 0x44, 0x5, 0xb0, 0x2b, 0x80, 0xe8, 0x93, 0x42, 0x69, 0x86, 0xcf, 0xb6, 0x0, 0x77, 0x99, 0x8e, 0x3b, 0x47, 0x99, 0x68, 0x86, 0xe0, 0x35, 0xca, 0x1c, 0xde, 0x5f, 0xd9, 0x62, 0x89};
+  G2Elt epk(eng); epk.UnmarshalBinary(Bytes(pkb, pkb + 96));
+  CHECK("bls.TestSignatureEdgeCase", scheme.Verify(epk, Bytes(mb, mb + 32), Bytes(sgb, sgb + 48)));
+
+  printf("%s: %d failure(s)\n", fails ? "FAILED" : "PASSED", fails);
+  return fails ? 1 : 0;
+}
