@@ -37,6 +37,7 @@ def load_library() -> C.CDLL:
         "b2k_launch_count": (C.c_uint64, [vp]),
         "b2k_set_msm_slice": (C.c_int, [vp, C.c_int]),
         "b2k_set_msm_variant": (C.c_int, [vp, C.c_int]),
+        "b2k_set_pairing_variant": (C.c_int, [vp, C.c_int]),
     }
     sigs["b2k_bls12381_pair"] = (C.c_int, [vp, sz, vp, vp, vp])
     sigs["b2k_bls12381_pair_dev"] = (C.c_int, [vp, sz, vp, vp, vp])

@@ -23,6 +23,7 @@ struct b2k_ctx {
   int force_c = 0;
   int force_L = 0;      // slice length override (0 = automatic)
   int use_v1 = 0;       // 1 = one-thread-per-bucket accumulate (kept for A/B measurements)
+  int pair_variant = 0; // launch-bound variant of the pairing kernels (tuning aid)
   uint64_t launches = 0;
   std::string err;
 };

@@ -22,7 +22,7 @@ extern "C" {
 int b2k_bls12381_pair_dev(b2k_ctx* ctx, size_t n, const void* d_g1, const void* d_g2, void* d_gt) {
   if (!ctx || !d_g1 || !d_g2 || !d_gt || n == 0) return B2K_ERR_ARG;
   CK(cudaSetDevice(ctx->device));
-  k_bls_pair<<<(unsigned)((n + 63) / 64), 64, 0, ctx->stream>>>(n, (const uint8_t*)d_g1, (const uint8_t*)d_g2, (uint8_t*)d_gt);
+  launch_pair(ctx, n, (const uint8_t*)d_g1, (const uint8_t*)d_g2, (uint8_t*)d_gt);
   CK(cudaGetLastError());
   ctx->launches += 1;
   return B2K_OK;
@@ -49,8 +49,7 @@ int b2k_bls12381_pairing_check_dev(b2k_ctx* ctx, size_t n, const void* a1, const
                                    const void* b2, void* d_ok) {
   if (!ctx || !a1 || !a2 || !b1 || !b2 || !d_ok || n == 0) return B2K_ERR_ARG;
   CK(cudaSetDevice(ctx->device));
-  k_bls_pairing_check<<<(unsigned)((n + 63) / 64), 64, 0, ctx->stream>>>(
-      n, (const uint8_t*)a1, (const uint8_t*)a2, (const uint8_t*)b1, (const uint8_t*)b2, (uint8_t*)d_ok, 0, nullptr);
+  launch_pairing_check(ctx, n, (const uint8_t*)a1, (const uint8_t*)a2, (const uint8_t*)b1, (const uint8_t*)b2, (uint8_t*)d_ok, 0, nullptr);
   CK(cudaGetLastError());
   ctx->launches += 1;
   return B2K_OK;
@@ -75,6 +74,12 @@ int b2k_bls12381_pairing_check(b2k_ctx* ctx, size_t n, const uint8_t* a1, const 
   if (rc) return rc;
   CK(cudaMemcpyAsync(ok, dok, n, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
+  return B2K_OK;
+}
+
+int b2k_set_pairing_variant(b2k_ctx* ctx, int v) {
+  if (!ctx || v < 0 || v > 5) return B2K_ERR_ARG;
+  ctx->pair_variant = v;
   return B2K_OK;
 }
 

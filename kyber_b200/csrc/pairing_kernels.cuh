@@ -2,11 +2,13 @@
 #pragma once
 #include "pairing.cuh"
 #include "curves.cuh"
+#include "b2k_ctx.h"
 
 namespace b2k {
 
 // gt[i] = e(g1[i], g2[i])           replaces n x Suite.Pair (kilic/suite.go:70-75)
-static __global__ void __launch_bounds__(64) k_bls_pair(size_t n, const uint8_t* __restrict__ g1, const uint8_t* __restrict__ g2,
+template <int BLOCK, int MINB>
+static __global__ void __launch_bounds__(BLOCK, MINB) k_bls_pair(size_t n, const uint8_t* __restrict__ g1, const uint8_t* __restrict__ g2,
                                                   uint8_t* __restrict__ gt) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -22,7 +24,8 @@ static __global__ void __launch_bounds__(64) k_bls_pair(size_t n, const uint8_t*
 
 // ok[i] = ( e(a1[i], a2[i]) == e(b1[i], b2[i]) )     replaces n x Suite.ValidatePairing
 // (kilic/suite.go:57-68): one 2-pair Miller loop (second pair negated) + one final exponentiation.
-static __global__ void __launch_bounds__(64) k_bls_pairing_check(size_t n, const uint8_t* __restrict__ a1,
+template <int BLOCK, int MINB>
+static __global__ void __launch_bounds__(BLOCK, MINB) k_bls_pairing_check(size_t n, const uint8_t* __restrict__ a1,
                                                            const uint8_t* __restrict__ a2,
                                                            const uint8_t* __restrict__ b1,
                                                            const uint8_t* __restrict__ b2, uint8_t* __restrict__ ok,
@@ -41,6 +44,27 @@ static __global__ void __launch_bounds__(64) k_bls_pairing_check(size_t n, const
   miller_loop<2>(f, P, Q);
   final_exponentiation(e, f);
   ok[i] = fp12_is_one(e) ? 1 : 0;
+}
+
+
+// launch-bound variants: (threads per block, min blocks per SM) -> register cap 65536 / (threads * blocks)
+#define B2K_PAIR_VARIANTS(X) X(0, 64, 4) X(1, 64, 8) X(2, 128, 4) X(3, 32, 16) X(4, 64, 6) X(5, 128, 3)
+inline void launch_pair(const b2k_ctx* ctx, size_t n, const uint8_t* g1, const uint8_t* g2, uint8_t* gt) {
+  switch (ctx->pair_variant) {
+#define X(ID, B, M) case ID: k_bls_pair<B, M><<<(unsigned)((n + B - 1) / B), B, 0, ctx->stream>>>(n, g1, g2, gt); break;
+    B2K_PAIR_VARIANTS(X)
+#undef X
+    default: k_bls_pair<64, 4><<<(unsigned)((n + 63) / 64), 64, 0, ctx->stream>>>(n, g1, g2, gt);
+  }
+}
+inline void launch_pairing_check(const b2k_ctx* ctx, size_t n, const uint8_t* a1, const uint8_t* a2, const uint8_t* b1,
+                                 const uint8_t* b2, uint8_t* ok, int b2_broadcast, const uint8_t* pre_ok) {
+  switch (ctx->pair_variant) {
+#define X(ID, B, M) case ID: k_bls_pairing_check<B, M><<<(unsigned)((n + B - 1) / B), B, 0, ctx->stream>>>(n, a1, a2, b1, b2, ok, b2_broadcast, pre_ok); break;
+    B2K_PAIR_VARIANTS(X)
+#undef X
+    default: k_bls_pairing_check<64, 4><<<(unsigned)((n + 63) / 64), 64, 0, ctx->stream>>>(n, a1, a2, b1, b2, ok, b2_broadcast, pre_ok);
+  }
 }
 
 }  // namespace b2k

@@ -26,29 +26,37 @@ template <class C> B2K_D bool fp2_eq(const Fp2<C>& a, const Fp2<C>& b) { return 
 template <class C> B2K_D void fp2_set_zero(Fp2<C>& r) { fp_set_zero(r.c0); fp_set_zero(r.c1); }
 template <class C> B2K_D void fp2_set_one(Fp2<C>& r) { fp_set_one(r.c0); fp_set_zero(r.c1); }
 
-// Karatsuba: 3 base multiplications
+// Karatsuba: 3 base multiplications.  Out of line, but the three products are inlined so that the six
+// input limbs-vectors are loaded once and every intermediate stays in registers (one 24-word store per
+// Fp2 product instead of three round trips through local memory).
 template <class C>
-B2K_D void fp2_mul(Fp2<C>& r, const Fp2<C>& a, const Fp2<C>& b) {
+B2K_NI void fp2_mul(Fp2<C>& r, const Fp2<C>& a, const Fp2<C>& b) {
+  const Fp<C> a0 = a.c0, a1 = a.c1, b0 = b.c0, b1 = b.c1;
   Fp<C> t0, t1, s0, s1;
-  fp_mul_c(t0, a.c0, b.c0);
-  fp_mul_c(t1, a.c1, b.c1);
-  fp_add(s0, a.c0, a.c1);
-  fp_add(s1, b.c0, b.c1);
-  fp_mul_c(s0, s0, s1);
+  fp_mul(t0, a0, b0);
+  fp_mul(t1, a1, b1);
+  fp_add(s0, a0, a1);
+  fp_add(s1, b0, b1);
+  fp_mul(s0, s0, s1);
   fp_sub(s0, s0, t0);
-  fp_sub(r.c1, s0, t1);
-  fp_sub(r.c0, t0, t1);
+  fp_sub(s0, s0, t1);
+  fp_sub(t0, t0, t1);
+  r.c1 = s0;
+  r.c0 = t0;
 }
 
-// complex squaring: 2 base multiplications
+// complex squaring: 2 base multiplications (same register-resident structure)
 template <class C>
-B2K_D void fp2_sqr(Fp2<C>& r, const Fp2<C>& a) {
+B2K_NI void fp2_sqr(Fp2<C>& r, const Fp2<C>& a) {
+  const Fp<C> a0 = a.c0, a1 = a.c1;
   Fp<C> s, d, m;
-  fp_add(s, a.c0, a.c1);
-  fp_sub(d, a.c0, a.c1);
-  fp_mul_c(m, a.c0, a.c1);
-  fp_mul_c(r.c0, s, d);
-  fp_add(r.c1, m, m);
+  fp_add(s, a0, a1);
+  fp_sub(d, a0, a1);
+  fp_mul(m, a0, a1);
+  fp_mul(s, s, d);
+  fp_add(m, m, m);
+  r.c0 = s;
+  r.c1 = m;
 }
 
 template <class C>

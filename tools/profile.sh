@@ -13,3 +13,20 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
 ncu --set full --clock-control none --import-source on -k regex:k_msm_accumulate_slices -s 3 -c 1 \
     -o gpurun_out/accumulate_${TAG} -f python bench.py --steps 1 --warmup 3 > gpurun_out/ncu_full_${TAG}.log 2>&1
 ls -la gpurun_out
+# pairing kernel: one full capture on a small batch (the kernel is long: keep n small)
+cat > /tmp/pair_probe.py <<'PY'
+import sys
+sys.path.insert(0, '.')
+import torch
+from kyber_b200 import Engine
+from oracle import bls12381 as o
+eng = Engine(0); n = 8192
+a1 = torch.frombuffer(bytearray(o.g1_to_affine_bytes(o.g1_mul(12345)) * n), dtype=torch.uint8).cuda()
+a2 = torch.frombuffer(bytearray(o.g2_to_affine_bytes(o.g2_mul(6789)) * n), dtype=torch.uint8).cuda()
+ok = torch.empty(n, dtype=torch.uint8, device='cuda')
+eng._check(eng.lib.b2k_bls12381_pairing_check_dev(eng.h, n, a1.data_ptr(), a2.data_ptr(), a1.data_ptr(), a2.data_ptr(), ok.data_ptr()))
+eng.synchronize(); print(int(ok.sum()))
+PY
+ncu --set full --clock-control none --import-source on -k regex:k_bls_pairing_check -c 1 \
+    -o gpurun_out/pairing_check_${TAG} -f python /tmp/pair_probe.py > gpurun_out/ncu_pairing_${TAG}.log 2>&1
+ls -la gpurun_out
