@@ -97,7 +97,7 @@ _BEST_THREADS = None
 
 
 def best_cpu_threads() -> int:
-    """The CPU arm uses 'all the host threads it can use': calibrate once over {C, C/2, C/4, C/8} (hyper-threads and
+    """The CPU arm uses 'all the host threads it can use': calibrate once over {C, C/2, C/4, C/8, C/16} (hyper-threads and
     container CPU quotas make the full logical count slower than fewer threads on the GPU boxes) and keep the best."""
     global _BEST_THREADS
     if _BEST_THREADS is not None:
@@ -106,11 +106,11 @@ def best_cpu_threads() -> int:
     from oracle import cpu_ref
     lib = cpu_ref.load()
     c = os.cpu_count() or 1
-    cands = sorted({max(1, c // d) for d in (1, 2, 4, 8)}, reverse=True)
+    cands = sorted({max(1, c // d) for d in (1, 2, 4, 8, 16)}, reverse=True)
     best, best_rate = c, 0.0
+    n = 4096
+    sb = wl.scalars_to_bytes(wl.prng_scalars("b2k/calib", n, wl.R_BLS12381))
     for t in cands:
-        n = max(256, 24 * t)
-        sb = wl.scalars_to_bytes(wl.prng_scalars("b2k/calib", n, wl.R_BLS12381))
         t0 = time.perf_counter()
         cpu_ref.g1_mul_batch(lib, sb, wl.G1_BLS12381_AFFINE * n, t)
         rate = n / (time.perf_counter() - t0)

@@ -58,6 +58,7 @@ def load_library() -> C.CDLL:
 
 
 HOST_FUNCS = [
+    "b2k_bn256_g1_mul_batch", "b2k_bn256_g1_msm", "b2k_bn256_g2_mul_batch", "b2k_bn256_g2_msm",
     "b2k_bls12381_g1_msm_affine", "b2k_bls12381_g2_msm_affine",
     "b2k_bls12381_g2_mul_batch", "b2k_bls12381_g2_mul_batch_affine", "b2k_bls12381_g2_msm",
     "b2k_bls12381_g1_decompress", "b2k_bls12381_g2_decompress",
@@ -244,6 +245,17 @@ class Engine:
         n = len(scalars) // 32
         assert len(scalars) == 32 * n and len(points) == 64 * n
         return self.call_host("b2k_bn254_g1_mul_batch", n, scalars, points, 64 * n)
+
+    # -- bn256 (G1 64 B, G2 128 B operands and results) ------------------------------------------------------
+    def bn256_call(self, name: str, scalars: bytes, points: bytes, point_len: int, out_len: int) -> bytes:
+        n = len(scalars) // 32
+        assert len(scalars) == 32 * n and len(points) == point_len * n
+        return self.call_host(name, n, scalars, points, out_len)
+
+    def bn256_g1_mul_batch(self, s, p): return self.bn256_call("b2k_bn256_g1_mul_batch", s, p, 64, 64 * (len(s) // 32))
+    def bn256_g1_msm(self, s, p): return self.bn256_call("b2k_bn256_g1_msm", s, p, 64, 64)
+    def bn256_g2_mul_batch(self, s, p): return self.bn256_call("b2k_bn256_g2_mul_batch", s, p, 128, 128 * (len(s) // 32))
+    def bn256_g2_msm(self, s, p): return self.bn256_call("b2k_bn256_g2_msm", s, p, 128, 128)
 
     def ed25519_mul_batch(self, scalars_le: bytes, points: bytes) -> bytes:
         """n x edwards25519 Point.Mul: raw little-endian 32-byte scalars, 32-byte compressed points -> 32 B each"""

@@ -54,7 +54,7 @@ int b2k_bn254_recover_commit(b2k_ctx* ctx, size_t t, const uint32_t* indices /*[
                              uint8_t* out /*[64]*/) {
   if (!ctx || !indices || !points || !out || t == 0 || t >= (size_t(1) << 31)) return B2K_ERR_ARG;
   CK(cudaSetDevice(ctx->device));
-  MsmPlan pl = make_plan(t, ctx->force_c);
+  MsmPlan pl = make_plan(t, ctx->force_c, Bn254G1::SCALAR_BITS);
   size_t extra = pad256(t * 4) + pad256(t * 32) + pad256(t * 64) + 1024;
   int rc = arena_reserve(ctx, msm_scratch_bytes<Bn254G1>(t, pl, ctx->force_L) + extra);
   if (rc) return rc;

@@ -29,6 +29,7 @@ struct Bls381G2 {
   using FC = Bls381Fp;
   using F = BFp2;
   using ScalarField = Bls381Fr;
+  static constexpr int SCALAR_BITS = 255;
   static constexpr int IN_BYTES = 192;
   static constexpr int OUT_BYTES = 96;
   B2K_D static void load(Affine<F>& r, const uint8_t* p) { g2_load(r, p); }

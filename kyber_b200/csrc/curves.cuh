@@ -38,6 +38,7 @@ struct Bls381G1 {
   using FC = Bls381Fp;
   using F = Fp<Bls381Fp>;
   using ScalarField = Bls381Fr;
+  static constexpr int SCALAR_BITS = 255;
   static constexpr int IN_BYTES = 96;
   static constexpr int OUT_BYTES = 48;
 
@@ -80,6 +81,7 @@ struct Bn254G1 {
   using FC = Bn254Fp;
   using F = Fp<Bn254Fp>;
   using ScalarField = Bn254Fr;
+  static constexpr int SCALAR_BITS = 254;
   static constexpr int IN_BYTES = 64;
   static constexpr int OUT_BYTES = 64;
 

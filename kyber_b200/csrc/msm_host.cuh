@@ -25,22 +25,23 @@ inline int arena_reserve(b2k_ctx* ctx, size_t bytes) { return b2k_arena_reserve(
 template <class T>
 T* arena_take(b2k_ctx* ctx, size_t count) { return reinterpret_cast<T*>(b2k_arena_take(ctx, count * sizeof(T))); }
 inline size_t pad256(size_t b) { return (b + 255) & ~size_t(255); }
-inline int pick_window(size_t n) {
+inline int pick_window(size_t n, int scalar_bits) {
   // minimise  W * (10 n + 40 * 2^(c-1))  field multiplications (mixed add ~10, bucket reduce ~40/bucket)
   int best = 4;
   double bestc = 1e300;
   for (int c = 4; c <= 16; c++) {
-    int W = (256 + c - 1) / c;
+    int W = (scalar_bits + c) / c;
     double cost = (double)W * (10.0 * (double)n + 40.0 * (double)(1u << (c - 1)));
     if (cost < bestc) { bestc = cost; best = c; }
   }
   return best;
 }
 
-inline MsmPlan make_plan(size_t n, int force_c) {
+// scalar_bits = bit length of the group order: signed-digit recoding needs windows for scalar_bits + 1 bits
+inline MsmPlan make_plan(size_t n, int force_c, int scalar_bits) {
   MsmPlan pl;
-  pl.c = force_c ? force_c : pick_window(n);
-  pl.W = (256 + pl.c - 1) / pl.c;
+  pl.c = force_c ? force_c : pick_window(n, scalar_bits);
+  pl.W = (scalar_bits + pl.c) / pl.c;
   pl.nb = 1 << (pl.c - 1);
   size_t total = (size_t)pl.W * pl.nb;
   int m = 1;
@@ -171,7 +172,7 @@ int msm_dev(b2k_ctx* ctx, size_t n, const void* d_scalars, const void* d_points,
     return B2K_ERR_ARG;
   }
   CK(cudaSetDevice(ctx->device));
-  MsmPlan pl = make_plan(n, ctx->force_c);
+  MsmPlan pl = make_plan(n, ctx->force_c, CV::SCALAR_BITS);
   int rc = arena_reserve(ctx, msm_scratch_bytes<CV>(n, pl, ctx->force_L));
   if (rc) return rc;
   return msm_enqueue<CV>(ctx, n, pl, (const uint8_t*)d_scalars, (const uint8_t*)d_points, (uint8_t*)d_out, affine_out);
@@ -184,7 +185,7 @@ int msm_host(b2k_ctx* ctx, size_t n, const uint8_t* scalars, const uint8_t* poin
     return B2K_ERR_ARG;
   }
   CK(cudaSetDevice(ctx->device));
-  MsmPlan pl = make_plan(n, ctx->force_c);
+  MsmPlan pl = make_plan(n, ctx->force_c, CV::SCALAR_BITS);
   size_t in_bytes = pad256(n * 32) + pad256(n * (size_t)CV::IN_BYTES) + 256;
   int rc = arena_reserve(ctx, msm_scratch_bytes<CV>(n, pl, ctx->force_L) + in_bytes);
   if (rc) return rc;

@@ -1,0 +1,55 @@
+"""GPU parity on the reference's ONLY byte-exact scalar-mul / MSM vectors on a pairing curve: the BDN fixtures on
+bn256 (sign/bdn/bdn_vartime_test.go:24-48, :90-135).  Signatures = x*H(m) through mul_batch, aggregate signature
+and aggregate key through the MSM with BDN coefficients (c_i + 1); every byte must equal the Go fixture."""
+import json
+import os
+
+import pytest
+
+from oracle import bdn, bn256 as o
+
+pytestmark = pytest.mark.gpu
+FX = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "bdn_bn256_fixtures.json")))
+
+
+def _sc(vals):
+    return b"".join((v % o.ORDER).to_bytes(32, "big") for v in vals)
+
+
+def test_signatures_are_the_fixture_bytes(engine):
+    f = FX["fixtures"]
+    hm = o.g1_marshal(o.hash_to_g1(f["msg"].encode()))        # bn256 Hash stays host-side (try-and-increment SHA-256)
+    privs = [int(x, 16) for x in f["private"]]
+    out = engine.bn256_g1_mul_batch(_sc(privs), hm * 3)       # sig_i = x_i * H(m)   (bls.Sign, sign/bls/bls.go:67-80)
+    assert [out[64 * i:64 * i + 64].hex() for i in range(3)] == f["sig"]
+    base2 = o.g2_marshal(o.G2)
+    pk = engine.bn256_g2_mul_batch(_sc(privs), base2 * 3)     # public keys x_i * G2
+    assert [pk[128 * i:128 * i + 128].hex() for i in range(3)] == f["public"]
+
+
+def test_aggregate_signature_and_key_are_the_fixture_bytes(engine):
+    f = FX["fixtures"]
+    pub_bytes = [bytes.fromhex(x) for x in f["public"]]
+    coefs = bdn.hash_point_to_r(pub_bytes, o.ORDER)           # host-side, as in Go
+    en = f["mask_enabled"]
+    scal = _sc([coefs[i] + 1 for i in en])                    # c_i * S_i + S_i = (c_i + 1) * S_i
+    sigs = b"".join(bytes.fromhex(f["sig"][i]) for i in en)
+    assert engine.bn256_g1_msm(scal, sigs).hex() == f["agg_sig"]
+    keys = b"".join(pub_bytes[i] for i in en)
+    assert engine.bn256_g2_msm(scal, keys).hex() == f["agg_key"]
+    for c in (4, 9, 16):
+        engine.set_msm_window(c)
+        try:
+            assert engine.bn256_g1_msm(scal, sigs).hex() == f["agg_sig"]
+        finally:
+            engine.set_msm_window(0)
+
+
+def test_hash_point_to_r_reference_vector(engine):
+    f = FX["hash_point_to_r"]
+    base2 = o.g2_marshal(o.G2)
+    pubs = engine.bn256_g2_mul_batch(_sc([1, 2, 3]), base2 * 3)
+    pub_bytes = [pubs[128 * i:128 * i + 128] for i in range(3)]
+    coefs = bdn.hash_point_to_r(pub_bytes, o.ORDER)
+    assert ["%x" % c for c in coefs] == f["coefs"]
+    assert engine.bn256_g2_msm(_sc([c + 1 for c in coefs]), pubs).hex() == f["agg_key"]
