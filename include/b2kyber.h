@@ -175,6 +175,33 @@ int b2k_bn254_g1_msm_dev(b2k_ctx* ctx, size_t n, const void* d_scalars, const vo
 int b2k_bn254_recover_commit(b2k_ctx* ctx, size_t t, const uint32_t* indices /*[t]*/, const uint8_t* points /*[t][64]*/,
                              uint8_t* out /*[64]*/);
 
+/* ---- bn254 G2 and pairing --------------------------------------------------------------------------------- */
+/* G2 operands/results: 128 B x.imag||x.real||y.imag||y.real, infinity all-zero (pairing/bn254/point.go:428-455).
+ * replaces: bn254 twistPoint.Mul, pairing/bn254/twist.go:167-181 */
+int b2k_bn254_g2_mul_batch(b2k_ctx* ctx, size_t n, const uint8_t* scalars /*[n][32]*/, const uint8_t* points /*[n][128]*/,
+                           uint8_t* out /*[n][128]*/);
+int b2k_bn254_g2_msm(b2k_ctx* ctx, size_t n, const uint8_t* scalars, const uint8_t* points, uint8_t* out /*[128]*/);
+/* gt[i] = e(g1[i], g2[i]) as the 384-byte GT MarshalBinary (pairing/bn254/point.go:625-656); an infinity operand
+ * gives the identity.  replaces: bn254 Suite.Pair -> optimalAte -> miller + finalExponentiation,
+ * pairing/bn254/suite.go:133-136, optate.go:124-271.  GT bytes are source-pinned (the in-tree Go fixes them). */
+int b2k_bn254_pair(b2k_ctx* ctx, size_t n, const uint8_t* g1 /*[n][64]*/, const uint8_t* g2 /*[n][128]*/,
+                   uint8_t* gt /*[n][384]*/);
+/* ok[i] = ( e(a1,a2) == e(b1,b2) ).  replaces: bn254 Suite.ValidatePairing, pairing/bn254/suite.go:138-144 */
+int b2k_bn254_pairing_check(b2k_ctx* ctx, size_t n, const uint8_t* a1 /*[n][64]*/, const uint8_t* a2 /*[n][128]*/,
+                            const uint8_t* b1, const uint8_t* b2, uint8_t* ok /*[n]*/);
+
+/* ---- bn256 (pairing/bn256: the curve of the reference's byte-exact BDN fixtures) --------------------------- */
+/* G1 64 B x||y, G2 128 B x.imag||x.real||y.imag||y.real (pairing/bn256/point.go:170-192, :423-452), operands
+ * and results alike.  replaces: bn256 curvePoint.Mul (curve.go:189-203), twistPoint.Mul (twist.go:162-175) and the
+ * Mul+Add loops of sign/bdn (bdn.go:126-181, mask.go:57-61) on this curve. */
+int b2k_bn256_g1_mul_batch(b2k_ctx* ctx, size_t n, const uint8_t* scalars, const uint8_t* points, uint8_t* out /*[n][64]*/);
+int b2k_bn256_g1_msm(b2k_ctx* ctx, size_t n, const uint8_t* scalars, const uint8_t* points, uint8_t* out /*[64]*/);
+int b2k_bn256_g2_mul_batch(b2k_ctx* ctx, size_t n, const uint8_t* scalars, const uint8_t* points, uint8_t* out /*[n][128]*/);
+int b2k_bn256_g2_msm(b2k_ctx* ctx, size_t n, const uint8_t* scalars, const uint8_t* points, uint8_t* out /*[128]*/);
+
+/* Launch-bound variant of the BLS12-381 pairing kernels (0 = default).  Tuning aid. */
+int b2k_set_pairing_variant(b2k_ctx* ctx, int variant);
+
 /* ---- edwards25519 ---------------------------------------------------------------------------------------- */
 /* out[i] = scalars[i] * points[i] on edwards25519.  scalars: RAW 256-bit little-endian integers (the reference
  * does not reduce on UnmarshalBinary, group/edwards25519/scalar.go:226-233); points and results: 32-byte

@@ -47,6 +47,7 @@ def load_library() -> C.CDLL:
     sigs["b2k_bls12381_hash_to_g1_dev"] = (C.c_int, [vp, sz, vp, vp, vp, C.c_uint32, vp])
     sigs["b2k_bls12381_verify_g1sig"] = (C.c_int, [vp, sz, vp, vp, vp, vp, C.c_uint32, vp, vp])
     sigs["b2k_bls12381_verify_g1sig_dev"] = (C.c_int, [vp, sz, vp, vp, vp, vp, C.c_uint32, vp, vp])
+    sigs["b2k_bn254_pairing_check"] = (C.c_int, [vp, sz, vp, vp, vp, vp, vp])
     sigs["b2k_bn254_recover_commit"] = (C.c_int, [vp, sz, vp, vp, vp])
     host3 = (C.c_int, [vp, sz, vp, vp, vp])
     for name in HOST_FUNCS + DEV_FUNCS:
@@ -58,6 +59,7 @@ def load_library() -> C.CDLL:
 
 
 HOST_FUNCS = [
+    "b2k_bn254_pair", "b2k_bn254_g2_mul_batch", "b2k_bn254_g2_msm",
     "b2k_bn256_g1_mul_batch", "b2k_bn256_g1_msm", "b2k_bn256_g2_mul_batch", "b2k_bn256_g2_msm",
     "b2k_bls12381_g1_msm_affine", "b2k_bls12381_g2_msm_affine",
     "b2k_bls12381_g2_mul_batch", "b2k_bls12381_g2_mul_batch_affine", "b2k_bls12381_g2_msm",
@@ -262,6 +264,21 @@ class Engine:
         n = len(scalars_le) // 32
         assert len(scalars_le) == 32 * n and len(points) == 32 * n
         return self.call_host("b2k_ed25519_mul_batch", n, scalars_le, points, 32 * n)
+
+    def bn254_pair(self, g1: bytes, g2: bytes) -> bytes:
+        n = len(g1) // 64
+        assert len(g1) == 64 * n and len(g2) == 128 * n
+        return self.call_host("b2k_bn254_pair", n, g1, g2, 384 * n)
+
+    def bn254_pairing_check(self, a1: bytes, a2: bytes, b1: bytes, b2: bytes) -> bytes:
+        n = len(a1) // 64
+        out = bytearray(n)
+        bufs = [_buf(x) for x in (a1, a2, b1, b2, out)]
+        self._check(self.lib.b2k_bn254_pairing_check(self.h, n, *[b[0] for b in bufs]))
+        return bytes(out)
+
+    def bn254_g2_mul_batch(self, s, p): return self.call_host("b2k_bn254_g2_mul_batch", len(s) // 32, s, p, 128 * (len(s) // 32))
+    def bn254_g2_msm(self, s, p): return self.call_host("b2k_bn254_g2_msm", len(s) // 32, s, p, 128)
 
     def bn254_recover_commit(self, indices, points: bytes) -> bytes:
         """share.RecoverCommit over bn254 G1: indices = share indices I_i (x_i = I_i + 1), points [t][64] -> 64 B"""

@@ -1,0 +1,112 @@
+// b2k_bn254_pairing.cu -- C ABI entry points for bn254: batched pairings and G2 Point.Mul / MSM.
+#include "msm_host.cuh"
+#include "bn_pairing.cuh"
+using namespace b2k_host;
+
+namespace b2k {
+
+// bn254 G2 (pairing/bn254/twist.go:167-181 twistPoint.Mul; wire format point.go:428-455)
+struct Bn254G2 {
+  using FC = Bn254Fp;
+  using F = NFp2;
+  using ScalarField = Bn254Fr;
+  static constexpr int SCALAR_BITS = 254;
+  static constexpr int IN_BYTES = 128;
+  static constexpr int OUT_BYTES = 128;
+  B2K_D static void load(Affine<F>& r, const uint8_t* p) { bn254_g2_load(r, p); }
+  B2K_D static void store(uint8_t* out, const Affine<F>& p) {
+    NFp t;
+    fp_from_mont(t, p.x.c1); fp_store_be(out, t);
+    fp_from_mont(t, p.x.c0); fp_store_be(out + 32, t);
+    fp_from_mont(t, p.y.c1); fp_store_be(out + 64, t);
+    fp_from_mont(t, p.y.c0); fp_store_be(out + 96, t);
+  }
+  B2K_D static void store_affine(uint8_t* out, const Affine<F>& p) { store(out, p); }
+};
+
+__global__ void __launch_bounds__(64, 4) k_bn254_pair(size_t n, const uint8_t* __restrict__ g1, const uint8_t* __restrict__ g2,
+                                                      uint8_t* __restrict__ gt) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Affine<NFp> P;
+  Affine<NFp2> Q;
+  bn254_g1_load(P, g1 + 64 * i);
+  bn254_g2_load(Q, g2 + 128 * i);
+  NFp12 f, e;
+  bn254_miller_loop<1>(f, &P, &Q);
+  bn254_final_exponentiation(e, f);
+  if (aff_is_inf(P) || aff_is_inf(Q)) fp12_set_one(e);      // optate.go:267-269
+  bn254_gt_store(gt + 384 * i, e);
+}
+
+// ok[i] = e(a1,a2) == e(b1,b2): the reference computes two full pairings and compares bytes
+// (pairing/bn254/suite.go:138-144); one product of Miller loops + one final exponentiation gives the same boolean.
+__global__ void __launch_bounds__(64, 4) k_bn254_pairing_check(size_t n, const uint8_t* __restrict__ a1,
+                                                               const uint8_t* __restrict__ a2, const uint8_t* __restrict__ b1,
+                                                               const uint8_t* __restrict__ b2, uint8_t* __restrict__ ok) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Affine<NFp> P[2];
+  Affine<NFp2> Q[2];
+  bn254_g1_load(P[0], a1 + 64 * i);
+  bn254_g2_load(Q[0], a2 + 128 * i);
+  bn254_g1_load(P[1], b1 + 64 * i);
+  bn254_g2_load(Q[1], b2 + 128 * i);
+  fp_neg(P[1].y, P[1].y);
+  NFp12 f, e;
+  bn254_miller_loop<2>(f, P, Q);
+  bn254_final_exponentiation(e, f);
+  ok[i] = fp12_is_one(e) ? 1 : 0;
+}
+
+}  // namespace b2k
+
+extern "C" {
+
+int b2k_bn254_pair(b2k_ctx* ctx, size_t n, const uint8_t* g1, const uint8_t* g2, uint8_t* gt) {
+  if (!ctx || !g1 || !g2 || !gt || n == 0) return B2K_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  int rc = arena_reserve(ctx, n * (64 + 128 + 384) + 4096);
+  if (rc) return rc;
+  uint8_t* d1 = arena_take<uint8_t>(ctx, n * 64);
+  uint8_t* d2 = arena_take<uint8_t>(ctx, n * 128);
+  uint8_t* dg = arena_take<uint8_t>(ctx, n * 384);
+  cudaStream_t st = ctx->stream;
+  CK(cudaMemcpyAsync(d1, g1, n * 64, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(d2, g2, n * 128, cudaMemcpyHostToDevice, st));
+  k_bn254_pair<<<(unsigned)((n + 63) / 64), 64, 0, st>>>(n, d1, d2, dg);
+  CK(cudaGetLastError());
+  ctx->launches += 1;
+  CK(cudaMemcpyAsync(gt, dg, n * 384, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return B2K_OK;
+}
+
+int b2k_bn254_pairing_check(b2k_ctx* ctx, size_t n, const uint8_t* a1, const uint8_t* a2, const uint8_t* b1,
+                            const uint8_t* b2, uint8_t* ok) {
+  if (!ctx || !a1 || !a2 || !b1 || !b2 || !ok || n == 0) return B2K_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  int rc = arena_reserve(ctx, n * (2 * 64 + 2 * 128 + 1) + 8192);
+  if (rc) return rc;
+  uint8_t* da1 = arena_take<uint8_t>(ctx, n * 64);
+  uint8_t* da2 = arena_take<uint8_t>(ctx, n * 128);
+  uint8_t* db1 = arena_take<uint8_t>(ctx, n * 64);
+  uint8_t* db2 = arena_take<uint8_t>(ctx, n * 128);
+  uint8_t* dok = arena_take<uint8_t>(ctx, n);
+  cudaStream_t st = ctx->stream;
+  CK(cudaMemcpyAsync(da1, a1, n * 64, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(da2, a2, n * 128, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(db1, b1, n * 64, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(db2, b2, n * 128, cudaMemcpyHostToDevice, st));
+  k_bn254_pairing_check<<<(unsigned)((n + 63) / 64), 64, 0, st>>>(n, da1, da2, db1, db2, dok);
+  CK(cudaGetLastError());
+  ctx->launches += 1;
+  CK(cudaMemcpyAsync(ok, dok, n, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return B2K_OK;
+}
+
+int b2k_bn254_g2_mul_batch(b2k_ctx* c, size_t n, const uint8_t* s, const uint8_t* p, uint8_t* o) { return mul_batch_host<Bn254G2, false>(c, n, s, p, o); }
+int b2k_bn254_g2_msm(b2k_ctx* c, size_t n, const uint8_t* s, const uint8_t* p, uint8_t* o) { return msm_host<Bn254G2>(c, n, s, p, o); }
+
+}  // extern "C"

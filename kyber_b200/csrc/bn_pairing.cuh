@@ -1,0 +1,265 @@
+// bn_pairing.cuh -- bn254 optimal-ate pairing (D-type twist, signed-digit loop over 6u+2, two Frobenius
+// steps, final exponentiation with the exact exponent (p^12-1)/n).
+//
+// Replaces the in-tree reference pairing:
+//   miller                 pairing/bn254/optate.go:124-207   (lineFunctionDouble :54-94, lineFunctionAdd :5-52,
+//                                                             mulLine :96-114, digit table :117-120)
+//   finalExponentiation    pairing/bn254/optate.go:212-261   (easy part + the y0..y6 chain = exact exponent)
+//   Suite.Pair / ValidatePairing   pairing/bn254/suite.go:133-144
+//   GT MarshalBinary       pairing/bn254/point.go:625-656    (384 B, x.x.x first)
+// Same kernel structure as the BLS12-381 pairing (pairing.cuh): Jacobian twist point over Fp2, lines scaled
+// by Fp2 factors (killed by the final exponentiation), sparse line multiplication, cyclotomic squarings.
+// D-type twist: psi(x',y') = (x' w^2, y' w^3), so a line at P is  l3 + l1 w + l0 w^3  with
+//   doubling:  l0 = 3X^3 - 2Y^2,   l1 = -(3X^2 Z^2) xP,   l3 = (Z3 Z^2) yP
+//   addition:  l0 = r x2 - Z3 y2,  l1 = -r xP,            l3 = Z3 yP
+// i.e. the sparse Fp12 element  c0 = (l3, 0, 0),  c1 = (l1, l0, 0)  -- the reference's (a t + b) w + c with
+// a ~ l0, b ~ l1, c ~ l3.  GT bytes equal those of a line-by-line restatement of the Go source (tests/).
+#pragma once
+#include "ec.cuh"
+
+namespace b2k {
+
+using NT = Bn254Tower;
+using NFp = Fp<Bn254Fp>;
+using NFp2 = Fp2<Bn254Fp>;
+using NFp6 = Fp6<NT>;
+using NFp12 = Fp12<NT>;
+
+constexpr uint64_t BN254_U = 4965661367192848881ULL;
+
+struct BnLine { NFp2 l0, l1, l3; };
+
+// f *= l3 + (l1 + l0 t) w
+B2K_NI void fp12_mul_line_d(NFp12& f, const BnLine& l) {
+  NFp6 A, B, C;
+  NFp2 s;
+  fp6_mul_by_01(A, f.c1, l.l1, l.l0);            // f1 * (l1 + l0 t)
+  fp6_mul_fp2(B, f.c0, l.l3);                    // f0 * l3
+  fp2_add(s, l.l1, l.l3);
+  fp6_add(C, f.c0, f.c1);
+  fp6_mul_by_01(C, C, s, l.l0);                  // (f0 + f1)(l3 + l1 + l0 t)
+  fp6_sub(C, C, A);
+  fp6_sub(f.c1, C, B);
+  fp6_mul_v(A, A);
+  fp6_add(f.c0, B, A);
+}
+
+B2K_NI void bn_double_step(BnLine& l, Jac<NFp2>& T, const Affine<NFp>& P) {
+  NFp2 A, B, C, D, E, ZZ, t;
+  fp2_sqr(A, T.X);
+  fp2_sqr(B, T.Y);
+  fp2_sqr(C, B);
+  fp2_sqr(ZZ, T.Z);
+  fp2_add(D, T.X, B); fp2_sqr(D, D); fp2_sub(D, D, A); fp2_sub(D, D, C); fp2_dbl(D, D);
+  fp2_dbl(E, A); fp2_add(E, E, A);
+  fp2_mul(l.l0, E, T.X); fp2_sub(l.l0, l.l0, B); fp2_sub(l.l0, l.l0, B);
+  fp2_mul(t, E, ZZ); fp2_mul_fp(t, t, P.x); fp2_neg(l.l1, t);
+  fp2_mul(t, T.Y, T.Z); fp2_dbl(T.Z, t);
+  fp2_mul(t, T.Z, ZZ); fp2_mul_fp(l.l3, t, P.y);
+  fp2_sqr(A, E); fp2_sub(A, A, D); fp2_sub(A, A, D);
+  fp2_dbl(C, C); fp2_dbl(C, C); fp2_dbl(C, C);
+  fp2_sub(D, D, A); fp2_mul(D, E, D); fp2_sub(T.Y, D, C);
+  T.X = A;
+}
+
+B2K_NI void bn_add_step(BnLine& l, Jac<NFp2>& T, const Affine<NFp2>& Q, const Affine<NFp>& P) {
+  NFp2 ZZ, U2, S2, H, R, HH, HHH, V, t;
+  fp2_sqr(ZZ, T.Z);
+  fp2_mul(U2, Q.x, ZZ);
+  fp2_mul(S2, Q.y, T.Z); fp2_mul(S2, S2, ZZ);
+  fp2_sub(H, U2, T.X);
+  fp2_sub(R, S2, T.Y);
+  fp2_sqr(HH, H);
+  fp2_mul(HHH, H, HH);
+  fp2_mul(V, T.X, HH);
+  fp2_mul(T.Z, T.Z, H);
+  fp2_mul(l.l0, R, Q.x); fp2_mul(t, T.Z, Q.y); fp2_sub(l.l0, l.l0, t);
+  fp2_mul_fp(t, R, P.x); fp2_neg(l.l1, t);
+  fp2_mul_fp(l.l3, T.Z, P.y);
+  fp2_sqr(t, R); fp2_sub(t, t, HHH); fp2_sub(t, t, V); fp2_sub(t, t, V);
+  fp2_sub(V, V, t); fp2_mul(V, R, V);
+  fp2_mul(HHH, T.Y, HHH);
+  fp2_sub(T.Y, V, HHH);
+  T.X = t;
+}
+
+#define B2K_BN_COEF(J, K, dst)                                                       \
+  {                                                                                  \
+    _Pragma("unroll") for (int q = 0; q < 8; q++) {                                  \
+      (dst).c0.v[q] = Bn254Fp::frob##J##_##K##_c0(q);                                \
+      (dst).c1.v[q] = Bn254Fp::frob##J##_##K##_c1(q);                                \
+    }                                                                                \
+  }
+
+// digits of 6u+2, least significant first (pairing/bn254/optate.go:117-120; data)
+B2K_D int bn254_loop_digit(int i) {
+  const int8_t d[65] = {0, 0, 0, 1, 0, 1, 0, -1, 0, 0, 1, -1, 0, 0, 1, 0, 0, 1, 1, 0, -1, 0, 0, 1, 0, -1, 0, 0, 0, 0, 1, 1,
+                        1, 0, 0, -1, 0, 0, 1, 0, 0, 0, 0, 0, -1, 0, 0, 1, 1, 0, 0, -1, 0, 0, 0, 1, 1, 0, -1, 0, 0, 1, 0, 1, 1};
+  return d[i];
+}
+
+// f = prod_i f_{6u+2,Q_i}(P_i) * l_{T,pi(Q_i)} * l_{T+pi(Q_i), -pi^2(Q_i)}; pairs with an infinity member give 1
+template <int NPAIRS>
+B2K_D void bn254_miller_loop(NFp12& f, const Affine<NFp>* P, const Affine<NFp2>* Q) {
+  Jac<NFp2> T[NPAIRS];
+  Affine<NFp2> Qn[NPAIRS];
+  bool live[NPAIRS];
+#pragma unroll
+  for (int i = 0; i < NPAIRS; i++) {
+    live[i] = !(aff_is_inf(P[i]) || aff_is_inf(Q[i]));
+    T[i].X = Q[i].x; T[i].Y = Q[i].y; fp2_set_one(T[i].Z);
+    Qn[i].x = Q[i].x; fp2_neg(Qn[i].y, Q[i].y);
+  }
+  fp12_set_one(f);
+  BnLine l;
+  for (int i = 64; i > 0; i--) {
+    if (i != 64) fp12_sqr(f, f);
+#pragma unroll
+    for (int k = 0; k < NPAIRS; k++) {
+      if (!live[k]) continue;
+      bn_double_step(l, T[k], P[k]);
+      fp12_mul_line_d(f, l);
+    }
+    const int d = bn254_loop_digit(i - 1);
+    if (d == 0) continue;
+#pragma unroll
+    for (int k = 0; k < NPAIRS; k++) {
+      if (!live[k]) continue;
+      bn_add_step(l, T[k], d > 0 ? Q[k] : Qn[k], P[k]);
+      fp12_mul_line_d(f, l);
+    }
+  }
+  // Frobenius steps: Q1 = (conj(x) xi^((p-1)/3), conj(y) xi^((p-1)/2)),  -Q2 = (x xi^((p^2-1)/3), y)
+  NFp2 g13, g12, g23;
+  B2K_BN_COEF(1, 2, g13);
+  B2K_BN_COEF(1, 3, g12);
+  B2K_BN_COEF(2, 2, g23);
+#pragma unroll
+  for (int k = 0; k < NPAIRS; k++) {
+    if (!live[k]) continue;
+    Affine<NFp2> q1, mq2;
+    NFp2 c;
+    fp2_conj(c, Q[k].x); fp2_mul(q1.x, c, g13);
+    fp2_conj(c, Q[k].y); fp2_mul(q1.y, c, g12);
+    fp2_mul(mq2.x, Q[k].x, g23);
+    mq2.y = Q[k].y;
+    bn_add_step(l, T[k], q1, P[k]);
+    fp12_mul_line_d(f, l);
+    bn_add_step(l, T[k], mq2, P[k]);
+    fp12_mul_line_d(f, l);
+  }
+}
+
+// f^(p^J) on the w-power basis (slots: w^0 c0.c0, w^1 c1.c0, w^2 c0.c1, w^3 c1.c1, w^4 c0.c2, w^5 c1.c2)
+template <int J>
+B2K_NI void bn254_frobenius(NFp12& r, const NFp12& f) {
+  NFp2 g, a;
+  a = f.c0.c0; if (J & 1) fp2_conj(a, a); r.c0.c0 = a;
+#define B2K_BN_FROB_SLOT(K, slot)                                 \
+  B2K_BN_COEF_SEL(K, g);                                          \
+  a = f.slot; if (J & 1) fp2_conj(a, a); fp2_mul(r.slot, a, g);
+#define B2K_BN_COEF_SEL(K, dst)                                   \
+  if (J == 1) B2K_BN_COEF(1, K, dst) else if (J == 2) B2K_BN_COEF(2, K, dst) else B2K_BN_COEF(3, K, dst)
+  B2K_BN_FROB_SLOT(1, c1.c0)
+  B2K_BN_FROB_SLOT(2, c0.c1)
+  B2K_BN_FROB_SLOT(3, c1.c1)
+  B2K_BN_FROB_SLOT(4, c0.c2)
+  B2K_BN_FROB_SLOT(5, c1.c2)
+#undef B2K_BN_FROB_SLOT
+#undef B2K_BN_COEF_SEL
+}
+
+B2K_D void bn_fp4_sqr(NFp2& c0, NFp2& c1, const NFp2& a, const NFp2& b) {
+  NFp2 t0, t1, t2;
+  fp2_sqr(t0, a);
+  fp2_sqr(t1, b);
+  NT::mul_xi(t2, t1);
+  fp2_add(c0, t2, t0);
+  fp2_add(t2, a, b);
+  fp2_sqr(t2, t2);
+  fp2_sub(t2, t2, t0);
+  fp2_sub(c1, t2, t1);
+}
+
+// Granger-Scott squaring in the cyclotomic subgroup (same slot assignment as pairing.cuh)
+B2K_NI void bn254_cyclotomic_sqr(NFp12& r, const NFp12& f) {
+  NFp2 z0 = f.c0.c0, z4 = f.c0.c1, z3 = f.c0.c2, z2 = f.c1.c0, z1 = f.c1.c1, z5 = f.c1.c2;
+  NFp2 t0, t1, t2, t3;
+  bn_fp4_sqr(t0, t1, z0, z1);
+  fp2_sub(z0, t0, z0); fp2_dbl(z0, z0); fp2_add(z0, z0, t0);
+  fp2_add(z1, t1, z1); fp2_dbl(z1, z1); fp2_add(z1, z1, t1);
+  bn_fp4_sqr(t0, t1, z2, z3);
+  bn_fp4_sqr(t2, t3, z4, z5);
+  fp2_sub(z4, t0, z4); fp2_dbl(z4, z4); fp2_add(z4, z4, t0);
+  fp2_add(z5, t1, z5); fp2_dbl(z5, z5); fp2_add(z5, z5, t1);
+  NT::mul_xi(t0, t3);
+  fp2_add(z2, t0, z2); fp2_dbl(z2, z2); fp2_add(z2, z2, t0);
+  fp2_sub(z3, t2, z3); fp2_dbl(z3, z3); fp2_add(z3, z3, t2);
+  r.c0.c0 = z0; r.c0.c1 = z4; r.c0.c2 = z3;
+  r.c1.c0 = z2; r.c1.c1 = z1; r.c1.c2 = z5;
+}
+
+B2K_NI void bn254_pow_u(NFp12& r, const NFp12& a) {
+  NFp12 acc = a;
+  for (int b = 61; b >= 0; b--) {            // u has 63 bits, top bit consumed by acc = a
+    bn254_cyclotomic_sqr(acc, acc);
+    if ((BN254_U >> b) & 1) fp12_mul(acc, acc, a);
+  }
+  r = acc;
+}
+
+// easy part (p^6-1)(p^2+1), then the hard part  y0 y1^2 y2^6 y3^12 y4^18 y5^30 y6^36  (optate.go:212-261)
+B2K_D void bn254_final_exponentiation(NFp12& r, const NFp12& in) {
+  NFp12 t0, t1, fp1, fp2v, fp3, fu, fu2, fu3, y0, y2, y3, y4, y6, tmp;
+  fp12_inv(t0, in);
+  fp12_conj(t1, in);
+  fp12_mul(t1, t1, t0);
+  bn254_frobenius<2>(t0, t1);
+  fp12_mul(t1, t1, t0);                               // t1 = f^((p^6-1)(p^2+1))
+  bn254_frobenius<1>(fp1, t1);
+  bn254_frobenius<2>(fp2v, t1);
+  bn254_frobenius<1>(fp3, fp2v);
+  bn254_pow_u(fu, t1);
+  bn254_pow_u(fu2, fu);
+  bn254_pow_u(fu3, fu2);
+  bn254_frobenius<1>(y3, fu);   fp12_conj(y3, y3);
+  bn254_frobenius<1>(tmp, fu2); fp12_mul(y4, fu, tmp); fp12_conj(y4, y4);
+  bn254_frobenius<1>(tmp, fu3); fp12_mul(y6, fu3, tmp); fp12_conj(y6, y6);
+  bn254_frobenius<2>(y2, fu2);
+  fp12_mul(y0, fp1, fp2v); fp12_mul(y0, y0, fp3);
+  // y1 = conj(t1), y5 = conj(fu2)
+  fp12_sqr(t0, y6); fp12_mul(t0, t0, y4); fp12_conj(tmp, fu2); fp12_mul(t0, t0, tmp);      // t0 = y6^2 y4 y5
+  NFp12 s;
+  fp12_mul(s, y3, tmp); fp12_mul(s, s, t0);                                                // s = y3 y5 t0
+  fp12_mul(t0, t0, y2);
+  fp12_sqr(s, s); fp12_mul(s, s, t0); fp12_sqr(s, s);
+  fp12_conj(tmp, t1);
+  fp12_mul(t0, s, tmp);                                                                    // t0 = s y1
+  fp12_mul(s, s, y0);
+  fp12_sqr(t0, t0);
+  fp12_mul(r, t0, s);
+}
+
+// ---- codecs --------------------------------------------------------------------------------------------------
+B2K_D void bn254_g1_load(Affine<NFp>& r, const uint8_t* p) {          // x||y, 32-byte big-endian each
+  NFp t;
+  fp_load_be(t, p); fp_to_mont(r.x, t);
+  fp_load_be(t, p + 32); fp_to_mont(r.y, t);
+}
+B2K_D void bn254_g2_load(Affine<NFp2>& r, const uint8_t* p) {         // x.imag||x.real||y.imag||y.real
+  NFp t;
+  fp_load_be(t, p); fp_to_mont(r.x.c1, t);
+  fp_load_be(t, p + 32); fp_to_mont(r.x.c0, t);
+  fp_load_be(t, p + 64); fp_to_mont(r.y.c1, t);
+  fp_load_be(t, p + 96); fp_to_mont(r.y.c0, t);
+}
+B2K_D void bn254_gt_store(uint8_t* out, const NFp12& f) {             // 384 B, highest coefficient first
+  const NFp2* order[6] = {&f.c1.c2, &f.c1.c1, &f.c1.c0, &f.c0.c2, &f.c0.c1, &f.c0.c0};
+  for (int i = 0; i < 6; i++) {
+    NFp t;
+    fp_from_mont(t, order[i]->c1); fp_store_be(out + 64 * i, t);
+    fp_from_mont(t, order[i]->c0); fp_store_be(out + 64 * i + 32, t);
+  }
+}
+
+}  // namespace b2k
