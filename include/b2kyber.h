@@ -145,6 +145,20 @@ int b2k_bls12381_verify_g1sig(b2k_ctx* ctx, size_t n, const uint8_t* pks /*[n][9
 int b2k_bls12381_verify_g1sig_dev(b2k_ctx* ctx, size_t n, const void* d_pks, const void* d_msgs, const void* d_offsets,
                                   const void* d_dst, uint32_t dst_len, const void* d_sigs, void* d_ok);
 
+/* Same for the scheme with signatures on G2 and keys on G1 (bls.NewSchemeOnG2, sign/bls/bls.go:48-59; the drand
+ * default): hash_to_curve onto G2, suite BLS12381G2_XMD:SHA-256_SSWU_RO_ (kilic.G2Elt.Hash, kilic/g2.go:160-169,
+ * default DST "BLS_SIG_BLS12381G2_XMD:SHA-256_SSWU_RO_NUL_" g2.go:18), out 192 B operand form; verification is
+ * ValidatePairing(G1 base, sig, pk, H(m)), keys 48 B compressed, signatures 96 B compressed. */
+int b2k_bls12381_hash_to_g2(b2k_ctx* ctx, size_t n, const uint8_t* msgs, const uint32_t* offsets /*[n+1]*/,
+                            const uint8_t* dst, uint32_t dst_len, uint8_t* out /*[n][192]*/);
+int b2k_bls12381_hash_to_g2_dev(b2k_ctx* ctx, size_t n, const void* d_msgs, const void* d_offsets, const void* d_dst,
+                                uint32_t dst_len, void* d_out);
+int b2k_bls12381_verify_g2sig(b2k_ctx* ctx, size_t n, const uint8_t* pks /*[n][48]*/, const uint8_t* msgs,
+                              const uint32_t* offsets /*[n+1]*/, const uint8_t* dst, uint32_t dst_len,
+                              const uint8_t* sigs /*[n][96]*/, uint8_t* ok /*[n]*/);
+int b2k_bls12381_verify_g2sig_dev(b2k_ctx* ctx, size_t n, const void* d_pks, const void* d_msgs, const void* d_offsets,
+                                  const void* d_dst, uint32_t dst_len, const void* d_sigs, void* d_ok);
+
 /* ---- BLS12-381 pairings ---------------------------------------------------------------------------- */
 /* gt[i] = e(g1[i], g2[i]); g2 operands are 192 B: x.c1||x.c0||y.c1||y.c0.  GT = 576 B, 12 x 48 B
  * big-endian, highest tower coefficient first (kilic/gt.go:115-117), exponent exactly (p^12-1)/r.

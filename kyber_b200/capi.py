@@ -45,6 +45,10 @@ def load_library() -> C.CDLL:
     sigs["b2k_bls12381_pairing_check_dev"] = (C.c_int, [vp, sz, vp, vp, vp, vp, vp])
     sigs["b2k_bls12381_hash_to_g1"] = (C.c_int, [vp, sz, vp, vp, vp, C.c_uint32, vp])
     sigs["b2k_bls12381_hash_to_g1_dev"] = (C.c_int, [vp, sz, vp, vp, vp, C.c_uint32, vp])
+    sigs["b2k_bls12381_hash_to_g2"] = (C.c_int, [vp, sz, vp, vp, vp, C.c_uint32, vp])
+    sigs["b2k_bls12381_hash_to_g2_dev"] = (C.c_int, [vp, sz, vp, vp, vp, C.c_uint32, vp])
+    sigs["b2k_bls12381_verify_g2sig"] = (C.c_int, [vp, sz, vp, vp, vp, vp, C.c_uint32, vp, vp])
+    sigs["b2k_bls12381_verify_g2sig_dev"] = (C.c_int, [vp, sz, vp, vp, vp, vp, C.c_uint32, vp, vp])
     sigs["b2k_bls12381_verify_g1sig"] = (C.c_int, [vp, sz, vp, vp, vp, vp, C.c_uint32, vp, vp])
     sigs["b2k_bls12381_verify_g1sig_dev"] = (C.c_int, [vp, sz, vp, vp, vp, vp, C.c_uint32, vp, vp])
     sigs["b2k_bn254_pairing_check"] = (C.c_int, [vp, sz, vp, vp, vp, vp, vp])
@@ -216,6 +220,26 @@ class Engine:
         bufs = [_buf(x) for x in (blob, offs, dst, out)]
         self._check(self.lib.b2k_bls12381_hash_to_g1(self.h, n, bufs[0][0], bufs[1][0], bufs[2][0], len(dst), bufs[3][0]))
         return bytes(out)
+
+    def bls12381_hash_to_g2(self, msgs, dst: bytes) -> bytes:
+        """msgs: list of bytes -> operand bytes [n][192]"""
+        n = len(msgs)
+        blob, offs = self._pack_msgs(msgs)
+        out = bytearray(192 * n)
+        bufs = [_buf(x) for x in (blob, offs, dst, out)]
+        self._check(self.lib.b2k_bls12381_hash_to_g2(self.h, n, bufs[0][0], bufs[1][0], bufs[2][0], len(dst), bufs[3][0]))
+        return bytes(out)
+
+    def bls12381_verify_g2sig(self, pks: bytes, msgs, dst: bytes, sigs: bytes) -> bytes:
+        """n x bls.Verify (sigs on G2): pks [n][48] compressed G1, sigs [n][96] compressed G2 -> ok flags [n]"""
+        n = len(msgs)
+        assert len(pks) == 48 * n and len(sigs) == 96 * n
+        blob, offs = self._pack_msgs(msgs)
+        ok = bytearray(n)
+        bufs = [_buf(x) for x in (pks, blob, offs, dst, sigs, ok)]
+        self._check(self.lib.b2k_bls12381_verify_g2sig(self.h, n, bufs[0][0], bufs[1][0], bufs[2][0], bufs[3][0], len(dst),
+                                                       bufs[4][0], bufs[5][0]))
+        return bytes(ok)
 
     def bls12381_verify_g1sig(self, pks: bytes, msgs, dst: bytes, sigs: bytes) -> bytes:
         """n x bls.Verify (sigs on G1): pks [n][96] compressed G2, sigs [n][48] compressed G1 -> ok flags [n]"""

@@ -37,8 +37,8 @@ static __global__ void __launch_bounds__(BLOCK, MINB) k_bls_pairing_check(size_t
   Affine<BFp2> Q[2];
   Bls381G1::load(P[0], a1 + 96 * i);
   g2_load(Q[0], a2 + 192 * i);
-  Bls381G1::load(P[1], b1 + 96 * i);
-  g2_load(Q[1], b2 + (b2_broadcast ? 0 : 192 * i));
+  Bls381G1::load(P[1], b1 + ((b2_broadcast & 2) ? 0 : 96 * i));      // bit 1: b1 is one shared operand
+  g2_load(Q[1], b2 + ((b2_broadcast & 1) ? 0 : 192 * i));           // bit 0: b2 is one shared operand
   fp_neg(P[1].y, P[1].y);
   BFp12 f, e;
   miller_loop<2>(f, P, Q);

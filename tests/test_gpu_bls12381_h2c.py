@@ -60,3 +60,20 @@ def test_verify_batch_with_corrupted_entries(engine):
     pks[17], want[17] = pks[18], 0                                                            # someone else's key
     ok = engine.bls12381_verify_g1sig(b"".join(pks), msgs, h.DST_G1, b"".join(sigs))
     assert list(ok) == want
+
+
+def test_hash_to_g2_and_drand_kat_on_device(engine):
+    """signatures on G2 (the drand default): hash-to-G2 parity and the reference's KAT kilic/suite_test.go:48-72."""
+    from oracle import h2c_bls12381_g2 as h2
+    rng = random.Random(53)
+    msgs = [b"", b"abc", rng.randbytes(32), rng.randbytes(100)]
+    out = engine.bls12381_hash_to_g2(msgs, h.DST_G2)
+    for i, m in enumerate(msgs):
+        assert out[192 * i:192 * i + 192] == o.g2_to_affine_bytes(h2.hash_to_g2(m, h.DST_G2)), i
+    k = KAT["sig_on_g2"]
+    msg = hashlib.sha256(bytes.fromhex(k["prev_sig"]) + (k["round"]).to_bytes(8, "big")).digest()
+    pk, sig = bytes.fromhex(k["pk_g1"]), bytes.fromhex(k["sig_g2"])
+    assert engine.bls12381_verify_g2sig(pk, [msg], h.DST_G2, sig) == b"\x01"
+    assert engine.bls12381_verify_g2sig(pk, [msg], h.DST_G1, sig) == b"\x00"          # wrong domain
+    bad = msg[:-1] + bytes([msg[-1] ^ 1])
+    assert engine.bls12381_verify_g2sig(pk * 2, [msg, bad], h.DST_G2, sig * 2) == b"\x01\x00"

@@ -51,3 +51,30 @@ def test_sig_on_g1_verifies_only_with_g2_domain():
     msg = hashlib.sha256((k["round"]).to_bytes(8, "big")).digest()
     assert not o.validate_pairing(h.hash_to_g1(msg, h.DST_G1), pk, sig, o.G2)
     assert o.validate_pairing(h.hash_to_g1(msg, h.DST_G2), pk, sig, o.G2)
+
+
+def test_hash_to_g2_isogeny_cofactor_and_drand_kat():
+    from oracle import h2c_bls12381_g2 as h2
+    import random
+    rng = random.Random(4)
+    # isogeny lands on E2 and is a homomorphism
+    pts = []
+    while len(pts) < 2:
+        x = (rng.randrange(o.P), rng.randrange(o.P))
+        y = o.f2_sqrt(o.f2_add(o.f2_add(o.f2_mul(o.f2_sqr(x), x), o.f2_mul(h2.A2, x)), h2.B2))
+        if y is not None:
+            pts.append((x, y))
+    for p in pts:
+        assert o.g2_is_on_curve(h2.iso_map(p))
+    # cofactor clearing: endomorphism form == multiplication by h_eff, result in G2
+    q = h2.iso_map(pts[0])
+    c = h2.clear_cofactor(q)
+    assert c == h2._g2_mul_any(h2.H_EFF_G2, q) and o.g2_in_subgroup(c)
+    # drand KAT, signatures on G2 (kilic/suite_test.go:48-72): e(G1 base, sig) == e(pk, H(msg))
+    k = KAT["sig_on_g2"]
+    pk = o.g1_decompress(bytes.fromhex(k["pk_g1"]))
+    sig = o.g2_decompress(bytes.fromhex(k["sig_g2"]))
+    msg = hashlib.sha256(bytes.fromhex(k["prev_sig"]) + (k["round"]).to_bytes(8, "big")).digest()
+    hm = h2.hash_to_g2(msg)
+    assert o.g2_in_subgroup(hm)
+    assert o.validate_pairing(o.G1, sig, pk, hm)

@@ -88,6 +88,53 @@ def derive():
 def limbs(v): return ", ".join("0x%08xu" % ((v >> (32 * i)) & 0xFFFFFFFF) for i in range(12))
 
 
+# ---- G2: 3-isogeny E2' -> E2 over Fp2 (elements are (c0, c1)) ----------------------------------------------
+def f2add(a, b): return ((a[0] + b[0]) % P, (a[1] + b[1]) % P)
+def f2sub(a, b): return ((a[0] - b[0]) % P, (a[1] - b[1]) % P)
+def f2neg(a): return (-a[0] % P, -a[1] % P)
+def f2mul(a, b): return ((a[0] * b[0] - a[1] * b[1]) % P, (a[0] * b[1] + a[1] * b[0]) % P)
+def f2muls(a, k): return (a[0] * k % P, a[1] * k % P)
+def f2inv(a):
+    n = pow((a[0] * a[0] + a[1] * a[1]) % P, P - 2, P)
+    return (a[0] * n % P, -a[1] * n % P)
+Z2 = (0, 0)
+A2, B2, ZZ2 = (0, 240), (1012, 1012), ((-2) % P, (-1) % P)
+
+
+def derive_g2():
+    """x0 = the Fp2-rational root of psi3 of E2', v = 2(3x0^2 + A), u = 4(x0^3 + A x0 + B)."""
+    psi3 = [f2neg(f2mul(A2, A2)), f2muls(B2, 12), f2muls(A2, 6), Z2, (3, 0)]
+    def pmul2(a, b):
+        r = [Z2] * (len(a) + len(b) - 1)
+        for i, x in enumerate(a):
+            for j, y in enumerate(b): r[i + j] = f2add(r[i + j], f2mul(x, y))
+        return r
+    def pmod2(a, m):
+        a = a[:]; dm = len(m) - 1; inv = f2inv(m[-1])
+        while len(a) - 1 >= dm:
+            c = f2mul(a[-1], inv); sh = len(a) - 1 - dm
+            for i in range(dm + 1): a[sh + i] = f2sub(a[sh + i], f2mul(c, m[i]))
+            a.pop()
+        while len(a) > 1 and a[-1] == Z2: a.pop()
+        return a or [Z2]
+    r = [(1, 0)]
+    for bit in bin(P * P)[2:]:
+        r = pmod2(pmul2(r, r), psi3)
+        if bit == "1": r = pmod2(pmul2(r, [Z2, (1, 0)]), psi3)
+    a = r + [Z2] * (2 - len(r))
+    a[1] = f2sub(a[1], (1, 0))
+    while len(a) > 1 and a[-1] == Z2: a.pop()
+    b = psi3
+    while not (len(a) == 1 and a[0] == Z2): b, a = a, pmod2(b, a)
+    assert len(b) == 2
+    x0 = f2neg(f2mul(b[0], f2inv(b[1])))
+    v = f2muls(f2add(f2muls(f2mul(x0, x0), 3), A2), 2)
+    u = f2muls(f2add(f2add(f2mul(f2mul(x0, x0), x0), f2mul(A2, x0)), B2), 4)
+    assert f2sub(A2, f2muls(v, 5)) == Z2
+    assert f2mul(f2sub(B2, f2muls(f2add(u, f2mul(x0, v)), 7)), f2inv((4, 4))) == (729, 0)
+    return x0, v, u
+
+
 def main():
     xn, xd, yn, yd = derive()
     Rm = 1 << 384
@@ -102,6 +149,13 @@ def main():
     for name, v in (("SSWU_A", A), ("SSWU_B", B), ("SSWU_Z", 11), ("SSWU_NEG_B_OVER_A", (-B) * pow(A, P - 2, P) % P),
                     ("SSWU_B_OVER_ZA", B * pow(11 * A, P - 2, P) % P), ("TWO_POW_256", (1 << 256) % P)):
         o.write("B2K_TABLE uint32_t %s[12] = {%s};\n" % (name, limbs(v * Rm % P)))
+    x0, v, u = derive_g2()
+    o.write("// G2 (BLS12381G2_XMD:SHA-256_SSWU_RO_): Fp2 constants as {c0 limbs, c1 limbs}.  iso_map(x,y) with d = x - x0:\n"
+            "//   X = (x d^2 + v d + u) / (3d)^2 ,  Y = -y (d^3 - v d - 2u) / (3d)^3   (Velu, normalised by u = -3)\n")
+    for name, val in (("ISO_G2_X0", x0), ("ISO_G2_V", v), ("ISO_G2_U", u), ("ISO_G2_2U", f2muls(u, 2)), ("SSWU2_A", A2), ("SSWU2_B", B2),
+                      ("SSWU2_Z", ZZ2), ("SSWU2_NEG_B_OVER_A", f2mul(f2neg(B2), f2inv(A2))),
+                      ("SSWU2_B_OVER_ZA", f2mul(B2, f2inv(f2mul(ZZ2, A2))))):
+        o.write("B2K_TABLE uint32_t %s[2][12] = {{%s}, {%s}};\n" % (name, limbs(val[0] * Rm % P), limbs(val[1] * Rm % P)))
     o.write("}  // namespace b2k\n")
 
 
