@@ -65,6 +65,11 @@ int b2k_set_msm_window(b2k_ctx* ctx, int c);
  * (0 = balanced slices [default], 1 = one thread per bucket).  Testing / tuning aids. */
 int b2k_set_msm_slice(b2k_ctx* ctx, int slice_len);
 int b2k_set_msm_variant(b2k_ctx* ctx, int one_thread_per_bucket);
+/* Window groups of an experimental overlapped MSM tail (default 1 = off; measured slower on B200): the windows are accumulated in `groups` launches, top
+ * group first, and the bucket reduction of each group runs on a second, high-priority stream while the next
+ * group accumulates.  1 = strictly serial pipeline, in which b2k_last_timings reports every stage separately;
+ * with groups > 1, [4] spans all accumulate launches, [9] is the exposed remainder of the reduction, [5],[6] ~ 0. */
+int b2k_set_msm_groups(b2k_ctx* ctx, int groups);
 /* Number of kernels launched by this context so far. */
 uint64_t b2k_launch_count(const b2k_ctx* ctx);
 

@@ -38,6 +38,7 @@ def load_library() -> C.CDLL:
         "b2k_set_msm_slice": (C.c_int, [vp, C.c_int]),
         "b2k_set_msm_variant": (C.c_int, [vp, C.c_int]),
         "b2k_set_pairing_variant": (C.c_int, [vp, C.c_int]),
+        "b2k_set_msm_groups": (C.c_int, [vp, C.c_int]),
     }
     sigs["b2k_bls12381_pair"] = (C.c_int, [vp, sz, vp, vp, vp])
     sigs["b2k_bls12381_pair_dev"] = (C.c_int, [vp, sz, vp, vp, vp])
@@ -139,6 +140,10 @@ class Engine:
 
     def set_msm_slice(self, L: int):
         self._check(self.lib.b2k_set_msm_slice(self.h, L))
+
+    def set_msm_groups(self, groups: int):
+        """window groups of the overlapped MSM tail; 1 = serial pipeline (per-stage timings meaningful)"""
+        self._check(self.lib.b2k_set_msm_groups(self.h, groups))
 
     def set_msm_variant(self, one_thread_per_bucket: bool):
         self._check(self.lib.b2k_set_msm_variant(self.h, int(one_thread_per_bucket)))

@@ -75,6 +75,12 @@ int b2k_create(int device, b2k_ctx** out) {
             cudaMallocHost(&ctx->h_flags, 256) == cudaSuccess &&
             cudaMemset(ctx->d_flags, 0, 256) == cudaSuccess;
   for (int i = 0; ok && i < N_EV; i++) ok = cudaEventCreate(&ctx->ev[i]) == cudaSuccess;
+  for (int i = 0; ok && i < 10; i++) ok = cudaEventCreateWithFlags(&ctx->gev[i], cudaEventDisableTiming) == cudaSuccess;
+  if (ok) {
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);      // hi = greatest priority (numerically lowest)
+    ok = cudaStreamCreateWithPriority(&ctx->stream2, cudaStreamNonBlocking, hi) == cudaSuccess;
+  }
   if (!ok) { delete ctx; return B2K_ERR_CUDA; }
   ctx->own_stream = true;
   *ctx->h_flags = 0;
@@ -90,6 +96,8 @@ void b2k_destroy(b2k_ctx* ctx) {
   if (ctx->d_flags) cudaFree(ctx->d_flags);
   if (ctx->h_flags) cudaFreeHost(ctx->h_flags);
   for (int i = 0; i < N_EV; i++) cudaEventDestroy(ctx->ev[i]);
+  for (int i = 0; i < 10; i++) cudaEventDestroy(ctx->gev[i]);
+  if (ctx->stream2) { cudaStreamSynchronize(ctx->stream2); cudaStreamDestroy(ctx->stream2); }
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -135,6 +143,12 @@ uint64_t b2k_launch_count(const b2k_ctx* ctx) { return ctx ? ctx->launches : 0; 
 int b2k_set_msm_slice(b2k_ctx* ctx, int L) {
   if (!ctx || L < 0 || L > 4096) return B2K_ERR_ARG;
   ctx->force_L = L;
+  return B2K_OK;
+}
+
+int b2k_set_msm_groups(b2k_ctx* ctx, int groups) {
+  if (!ctx || groups < 1 || groups > 8) return B2K_ERR_ARG;
+  ctx->msm_groups = groups;
   return B2K_OK;
 }
 

@@ -23,6 +23,10 @@ struct b2k_ctx {
   int force_c = 0;
   int force_L = 0;      // slice length override (0 = automatic)
   int use_v1 = 0;       // 1 = one-thread-per-bucket accumulate (kept for A/B measurements)
+  cudaStream_t stream2 = nullptr;   // high-priority side stream: bucket reduction of one window group overlaps the next accumulate
+  cudaEvent_t gev[10];              // group hand-over events
+  int msm_groups = 1;               // window groups of the overlapped MSM tail; measured SLOWER than the serial pipeline on
+                                    // B200 (accumulate blocks fill the register file, nothing co-resides): kept as an experiment
   int pair_variant = 0; // launch-bound variant of the pairing kernels (tuning aid)
   uint64_t launches = 0;
   std::string err;

@@ -1,6 +1,7 @@
 // kernels.cuh -- __global__ wrappers around the per-thread bodies of msm.cuh (sm_100a).
 #pragma once
 #include "msm.cuh"
+#include "fp_inv.cuh"
 
 namespace b2k {
 
@@ -203,6 +204,54 @@ __global__ void __launch_bounds__(128) k_msm_fixup_big(uint32_t L, const uint32_
   }
 }
 
+// ---- grouped variants: the windows are processed in G groups (top group first) so that the bucket
+// reduction of one group (second stream) overlaps the accumulate pass of the next (main stream) -------------
+// ranges[g] = first slice of group g (the slice holding the first sorted entry of its lowest window),
+// ranges[G] = number of slices.  A slice shared by two groups belongs to the upper one, which runs first.
+static __global__ void k_msm_group_ranges(int G, int W, int nb, uint32_t L, uint32_t total,
+                                          const uint32_t* __restrict__ offs, uint32_t* __restrict__ ranges) {
+  if (threadIdx.x || blockIdx.x) return;
+  for (int g = 0; g < G; g++) ranges[g] = offs[(size_t)(g * W / G) * nb] / L;
+  ranges[G] = (offs[total] + L - 1) / L;
+}
+
+template <class CV>
+__global__ void __launch_bounds__(128) k_msm_accumulate_slices_range(const uint32_t* __restrict__ ranges, int g, uint32_t L,
+                                                                     uint32_t total,
+                                                                     const Affine<typename CV::F>* __restrict__ pts,
+                                                                     const uint32_t* __restrict__ offs,
+                                                                     const uint32_t* __restrict__ entries,
+                                                                     Xyzz<typename CV::F>* __restrict__ buckets,
+                                                                     Xyzz<typename CV::F>* __restrict__ spart) {
+  uint32_t j = ranges[g] + blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= ranges[g + 1]) return;
+  msm_accumulate_slice<CV>(j, L, total, pts, offs, entries, buckets, spart);
+}
+
+template <class CV>
+__global__ void __launch_bounds__(128) k_msm_fixup_range(uint32_t gid_lo, uint32_t gid_hi, uint32_t L,
+                                                         const uint32_t* __restrict__ offs,
+                                                         Xyzz<typename CV::F>* __restrict__ buckets,
+                                                         const Xyzz<typename CV::F>* __restrict__ spart,
+                                                         uint32_t* __restrict__ big_count, uint32_t* __restrict__ big_list) {
+  uint32_t g = gid_lo + blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= gid_hi) return;
+  if (msm_fixup_bucket<CV, 64>(g, L, offs, buckets, spart)) big_list[atomicAdd(big_count, 1u)] = g;
+}
+
+template <class CV>
+__global__ void __launch_bounds__(128) k_msm_reduce_chunks_range(MsmPlan pl, int w_lo, int w_cnt,
+                                                                 const Xyzz<typename CV::F>* __restrict__ buckets,
+                                                                 Xyzz<typename CV::F>* __restrict__ partials) {
+  int T = pl.nb / pl.m;
+  size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (id >= (size_t)w_cnt * T) return;
+  int w = w_lo + (int)(id / T), t = (int)(id % T);
+  Xyzz<typename CV::F> out;
+  msm_reduce_chunk<CV>(out, buckets + (size_t)w * pl.nb, t, pl.m);
+  partials[(size_t)w * T + t] = out;
+}
+
 // ---- MSM stage 5: per-chunk running sums ---------------------------------------------------------
 template <class CV>
 __global__ void __launch_bounds__(128) k_msm_reduce_chunks(MsmPlan pl, const Xyzz<typename CV::F>* __restrict__ buckets,
@@ -219,10 +268,10 @@ __global__ void __launch_bounds__(128) k_msm_reduce_chunks(MsmPlan pl, const Xyz
 // ---- MSM stage 6: per-window sum of the partials (one block per window) --------------------------
 template <class CV>
 __global__ void __launch_bounds__(128) k_msm_window_sum(int T, const Xyzz<typename CV::F>* __restrict__ partials,
-                                                        Xyzz<typename CV::F>* __restrict__ wsum) {
+                                                        Xyzz<typename CV::F>* __restrict__ wsum, int w_lo = 0) {
   using X = Xyzz<typename CV::F>;
   __shared__ X sm[128];
-  int tid = threadIdx.x, w = blockIdx.x;
+  int tid = threadIdx.x, w = w_lo + blockIdx.x;
   X acc;
   xyzz_set_inf(acc);
   for (int t = tid; t < T; t += 128) {
@@ -240,6 +289,24 @@ __global__ void __launch_bounds__(128) k_msm_window_sum(int T, const Xyzz<typena
     __syncthreads();
   }
   if (tid == 0) wsum[w] = sm[0];
+}
+
+// single-thread inversions of the serial tail use the binary extended Euclid (fp_inv.cuh)
+template <class C> B2K_D void f_inv_vt(Fp<C>& r, const Fp<C>& a) { fp_inv_vartime(r, a); }
+template <class C> B2K_D void f_inv_vt(Fp2<C>& r, const Fp2<C>& a) {
+  Fp<C> n, t;
+  fp_sqr_c(n, a.c0); fp_sqr_c(t, a.c1); fp_add(n, n, t);
+  fp_inv_vartime(n, n);
+  fp_mul_c(r.c0, a.c0, n); fp_mul_c(t, a.c1, n); fp_neg(r.c1, t);
+}
+template <class F>
+B2K_D void xyzz_to_affine_vt(Affine<F>& r, const Xyzz<F>& p) {
+  if (xyzz_is_inf(p)) { aff_set_inf(r); return; }
+  F t, ti, a;
+  f_mul(t, p.ZZ, p.ZZZ);
+  f_inv_vt(ti, t);
+  f_mul(a, ti, p.ZZZ); f_mul(r.x, p.X, a);      // X / ZZ
+  f_mul(a, ti, p.ZZ);  f_mul(r.y, p.Y, a);      // Y / ZZZ
 }
 
 // ---- MSM stage 7: Horner over windows, affine, wire bytes ------------------------------------------
@@ -297,7 +364,7 @@ __global__ void __launch_bounds__(128) k_msm_final(MsmPlan pl, const Xyzz<typena
   if (threadIdx.x == 0) {
     Xyzz<F> r = acc;
     Affine<F> a;
-    xyzz_to_affine(a, r);
+    xyzz_to_affine_vt(a, r);
     if (affine_out) CV::store_affine(out, a);
     else CV::store(out, a);
   }

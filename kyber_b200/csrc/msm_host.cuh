@@ -138,6 +138,38 @@ int msm_enqueue(b2k_ctx* ctx, size_t n, const MsmPlan& pl, const uint8_t* d_scal
   k_scan_finish<<<sblocks, 1024, 0, st>>>((uint32_t)total, bsum, offs, cursor); nl += 3;
   CK(cudaEventRecord(ctx->ev[3], st));
   k_msm_scatter<CV><<<gb_n, 256, 0, st>>>(n, d_scalars, pl, cursor, entries); nl++;
+  const int G = (!ctx->use_v1 && ctx->msm_groups > 1 && pl.W >= 2 * ctx->msm_groups && ctx->stream2) ? ctx->msm_groups : 1;
+  if (G > 1) {
+    // ---- overlapped tail: groups of windows, top group first; reduction of group g on stream2 while the main
+    //      stream accumulates group g-1.  ms[4] = all accumulate launches, ms[5] = what is left after them.
+    cudaStream_t s2 = ctx->stream2;
+    uint32_t* ranges = bsum + 900;                 // G+1 words
+    uint32_t* bigc = bsum + 920;                   // one counter per group
+    CK(cudaMemsetAsync(buckets, 0, total * sizeof(Xyzz<F>), st));
+    CK(cudaMemsetAsync(bigc, 0, 64, st));
+    k_msm_group_ranges<<<1, 32, 0, st>>>(G, pl.W, pl.nb, L, (uint32_t)total, offs, ranges); nl++;
+    CK(cudaEventRecord(ctx->ev[4], st));
+    for (int g = G - 1; g >= 0; g--) {
+      const int w_lo = g * pl.W / G, w_hi = (g + 1) * pl.W / G, w_cnt = w_hi - w_lo;
+      k_msm_accumulate_slices_range<CV><<<(smax + 127) / 128, 128, 0, st>>>(ranges, g, L, (uint32_t)total, pts, offs, entries, buckets, spart); nl++;
+      CK(cudaEventRecord(ctx->gev[g], st));
+      CK(cudaStreamWaitEvent(s2, ctx->gev[g], 0));
+      const uint32_t gid_lo = (uint32_t)((size_t)w_lo * pl.nb), gid_hi = (uint32_t)((size_t)w_hi * pl.nb);
+      k_msm_fixup_range<CV><<<(gid_hi - gid_lo + 127) / 128, 128, 0, s2>>>(gid_lo, gid_hi, L, offs, buckets, spart, bigc + g, big_list + gid_lo);
+      k_msm_fixup_big<CV><<<64, 128, 0, s2>>>(L, offs, buckets, spart, bigc + g, big_list + gid_lo);
+      size_t nch = (size_t)w_cnt * T;
+      k_msm_reduce_chunks_range<CV><<<(unsigned)((nch + 127) / 128), 128, 0, s2>>>(pl, w_lo, w_cnt, buckets, partials);
+      k_msm_window_sum<CV><<<w_cnt, 128, 0, s2>>>(T, partials, wsum, w_lo); nl += 4;
+    }
+    CK(cudaEventRecord(ctx->ev[9], st));           // end of the accumulate launches
+    CK(cudaEventRecord(ctx->gev[G], s2));
+    CK(cudaStreamWaitEvent(st, ctx->gev[G], 0));
+    CK(cudaEventRecord(ctx->ev[5], st));
+    CK(cudaEventRecord(ctx->ev[6], st));
+    CK(cudaEventRecord(ctx->ev[7], st));
+    k_msm_final<CV><<<1, 128, 0, st>>>(pl, wsum, d_out, affine_out); nl++;
+    CK(cudaEventRecord(ctx->ev[8], st));
+  } else {
   if (ctx->use_v1) {
     CK(cudaEventRecord(ctx->ev[4], st));
     k_msm_accumulate<CV><<<(unsigned)((total + 127) / 128), 128, 0, st>>>(total, pts, offs, entries, buckets); nl++;
@@ -159,6 +191,7 @@ int msm_enqueue(b2k_ctx* ctx, size_t n, const MsmPlan& pl, const uint8_t* d_scal
   CK(cudaEventRecord(ctx->ev[7], st));
   k_msm_final<CV><<<1, 128, 0, st>>>(pl, wsum, d_out, affine_out); nl++;
   CK(cudaEventRecord(ctx->ev[8], st));
+  }
   CK(cudaGetLastError());
   ctx->launches += (uint64_t)nl;
   ctx->timings_valid = true;

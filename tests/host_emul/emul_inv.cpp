@@ -1,0 +1,9 @@
+// Host emulation of the variable-time inversion (test infrastructure only).
+#include "../../kyber_b200/csrc/constants.cuh"
+#include "../../kyber_b200/csrc/fp_inv.cuh"
+using namespace b2k;
+extern "C" {
+void emul_fp381_inv_vartime(const uint32_t* a, uint32_t* r) { Fp<Bls381Fp> x, z; for (int i = 0; i < 12; i++) x.v[i] = a[i]; fp_inv_vartime(z, x); for (int i = 0; i < 12; i++) r[i] = z.v[i]; }
+void emul_fp254_inv_vartime(const uint32_t* a, uint32_t* r) { Fp<Bn254Fp> x, z; for (int i = 0; i < 8; i++) x.v[i] = a[i]; fp_inv_vartime(z, x); for (int i = 0; i < 8; i++) r[i] = z.v[i]; }
+void emul_fp256_inv_vartime(const uint32_t* a, uint32_t* r) { Fp<Bn256Fp> x, z; for (int i = 0; i < 10; i++) x.v[i] = a[i]; fp_inv_vartime(z, x); for (int i = 0; i < 10; i++) r[i] = z.v[i]; }
+}
