@@ -223,7 +223,7 @@ def run_reference_arm(args):
                        "step": f"bounded sample of {n_sample} pairs"},
             "cpu_baseline": dict(last, value=v),
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "pairings": cpu_pairing_run(max(64, 4 * threads), threads),
+            "pairings": cpu_pairing_run(max(1024, 32 * threads), threads),
             "gpu_launches": 0}
     print(json.dumps(line))
     return 0
@@ -432,7 +432,7 @@ def run_ours(args):
             line["cpu_baseline"] = cpu_reference_run(max(4096, 384 * threads), threads)
             line["cpu_baseline"]["logical_cpus"] = os.cpu_count()
             if "pairings" in line:
-                line["pairings"]["cpu_baseline"] = cpu_pairing_run(max(64, 4 * threads), threads)
+                line["pairings"]["cpu_baseline"] = cpu_pairing_run(max(1024, 32 * threads), threads)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
