@@ -70,6 +70,8 @@ int b2k_set_msm_variant(b2k_ctx* ctx, int one_thread_per_bucket);
  * group accumulates.  1 = strictly serial pipeline, in which b2k_last_timings reports every stage separately;
  * with groups > 1, [4] spans all accumulate launches, [9] is the exposed remainder of the reduction, [5],[6] ~ 0. */
 int b2k_set_msm_groups(b2k_ctx* ctx, int groups);
+/* Resident bucket-accumulate blocks per SM (4..6; launch bound => register cap).  Tuning aid. */
+int b2k_set_msm_occupancy(b2k_ctx* ctx, int blocks_per_sm);
 /* Number of kernels launched by this context so far. */
 uint64_t b2k_launch_count(const b2k_ctx* ctx);
 

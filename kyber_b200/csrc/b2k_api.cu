@@ -146,6 +146,12 @@ int b2k_set_msm_slice(b2k_ctx* ctx, int L) {
   return B2K_OK;
 }
 
+int b2k_set_msm_occupancy(b2k_ctx* ctx, int blocks_per_sm) {
+  if (!ctx || blocks_per_sm < 4 || blocks_per_sm > 6) return B2K_ERR_ARG;
+  ctx->acc_minb = blocks_per_sm;
+  return B2K_OK;
+}
+
 int b2k_set_msm_groups(b2k_ctx* ctx, int groups) {
   if (!ctx || groups < 1 || groups > 8) return B2K_ERR_ARG;
   ctx->msm_groups = groups;

@@ -27,6 +27,7 @@ struct b2k_ctx {
   cudaEvent_t gev[10];              // group hand-over events
   int msm_groups = 1;               // window groups of the overlapped MSM tail; measured SLOWER than the serial pipeline on
                                     // B200 (accumulate blocks fill the register file, nothing co-resides): kept as an experiment
+  int acc_minb = 4;                 // resident accumulate blocks per SM (launch bound), tuning aid
   int pair_variant = 0; // launch-bound variant of the pairing kernels (tuning aid)
   uint64_t launches = 0;
   std::string err;

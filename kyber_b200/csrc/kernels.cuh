@@ -145,8 +145,8 @@ __global__ void __launch_bounds__(128) k_msm_accumulate(size_t total, const Affi
 }
 
 // ---- MSM stage 4 (v2): fixed-length slices of the sorted entries (balanced, skew-proof) ------------
-template <class CV>
-__global__ void __launch_bounds__(128) k_msm_accumulate_slices(uint32_t nslices, uint32_t L, uint32_t total,
+template <class CV, int MINB>
+__global__ void __launch_bounds__(128, MINB) k_msm_accumulate_slices(uint32_t nslices, uint32_t L, uint32_t total,
                                                                const Affine<typename CV::F>* __restrict__ pts,
                                                                const uint32_t* __restrict__ offs,
                                                                const uint32_t* __restrict__ entries,

@@ -178,7 +178,11 @@ int msm_enqueue(b2k_ctx* ctx, size_t n, const MsmPlan& pl, const uint8_t* d_scal
     CK(cudaMemsetAsync(buckets, 0, total * sizeof(Xyzz<F>), st));
     CK(cudaMemsetAsync(big_count, 0, 4, st));
     CK(cudaEventRecord(ctx->ev[4], st));
-    k_msm_accumulate_slices<CV><<<(smax + 127) / 128, 128, 0, st>>>(smax, L, (uint32_t)total, pts, offs, entries, buckets, spart); nl++;
+    // resident blocks per SM (register cap 65536/(128*MINB)): 4 -> no spills, 5/6 -> more warps, small spills
+    if (ctx->acc_minb == 5) k_msm_accumulate_slices<CV, 5><<<(smax + 127) / 128, 128, 0, st>>>(smax, L, (uint32_t)total, pts, offs, entries, buckets, spart);
+    else if (ctx->acc_minb == 6) k_msm_accumulate_slices<CV, 6><<<(smax + 127) / 128, 128, 0, st>>>(smax, L, (uint32_t)total, pts, offs, entries, buckets, spart);
+    else k_msm_accumulate_slices<CV, 4><<<(smax + 127) / 128, 128, 0, st>>>(smax, L, (uint32_t)total, pts, offs, entries, buckets, spart);
+    nl++;
     CK(cudaEventRecord(ctx->ev[9], st));
     k_msm_fixup<CV><<<(unsigned)((total + 127) / 128), 128, 0, st>>>((uint32_t)total, L, offs, buckets, spart, big_count, big_list);
     k_msm_fixup_big<CV><<<256, 128, 0, st>>>(L, offs, buckets, spart, big_count, big_list); nl += 2;

@@ -1,0 +1,168 @@
+"""CPU tests: the DEVICE code of every kernel family compiled for the host (tests/host_emul/*.cpp, PTX carry
+primitives emulated in ptx.cuh) and checked against the oracle and the reference's fixtures -- the same bodies the
+sm_100a kernels run, exercised without a GPU.  (tests/test_abi_and_host.py covers the field and MSM bodies.)"""
+import ctypes
+import hashlib
+import json
+import os
+import random
+import subprocess
+
+import pytest
+
+from oracle import bls12381 as o
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EMU = os.path.join(ROOT, "tests", "host_emul")
+CSRC = os.path.join(ROOT, "kyber_b200", "csrc")
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def _lib(name):
+    src = os.path.join(EMU, name + ".cpp")
+    so = os.path.join(EMU, "lib" + name + ".so")
+    newest = max([os.path.getmtime(src)] + [os.path.getmtime(os.path.join(CSRC, f)) for f in os.listdir(CSRC) if f.endswith(".cuh")])
+    if not os.path.exists(so) or os.path.getmtime(so) < newest:
+        subprocess.run(["g++", "-O2", "-shared", "-fPIC", "-std=c++17", "-DB2K_HOST_EMUL", "-Wno-unknown-pragmas", src, "-o", so],
+                       check=True)
+    return ctypes.CDLL(so)
+
+
+@pytest.fixture(scope="module")
+def emul():
+    return _lib("emul")
+
+
+def test_bls12381_pairing_bodies(emul):
+    rng = random.Random(4)
+    a, b = rng.randrange(o.R), rng.randrange(o.R)
+    P, Q = o.g1_mul(a), o.g2_mul(b)
+    out = ctypes.create_string_buffer(576)
+    emul.emul_bls12381_pair(o.g1_to_affine_bytes(P), o.g2_to_affine_bytes(Q), out)
+    assert out.raw == o.gt_to_bytes(o.pairing(P, Q))
+    emul.emul_bls12381_pair(bytes(96), o.g2_to_affine_bytes(Q), out)
+    assert out.raw == o.gt_to_bytes(o.F12_ONE)
+    args = [o.g1_to_affine_bytes(P), o.g2_to_affine_bytes(Q), o.g1_to_affine_bytes(o.g1_mul(a * b % o.R)), o.g2_to_affine_bytes(o.G2)]
+    assert emul.emul_bls12381_pairing_check(*args) == 1
+    args[2] = o.g1_to_affine_bytes(o.g1_mul(a * b + 1))
+    assert emul.emul_bls12381_pairing_check(*args) == 0
+
+
+def test_decompress_bodies_on_the_zcash_fixtures(emul):
+    d = json.load(open(os.path.join(GOLD, "bls12381_deserialization.json")))
+    for grp, fn, n_in, n_out, dec, toaff in (("G1", "emul_bls12381_g1_decompress", 48, 96, o.g1_decompress, o.g1_to_affine_bytes),
+                                             ("G2", "emul_bls12381_g2_decompress", 96, 192, o.g2_decompress, o.g2_to_affine_bytes)):
+        seen = 0
+        for v in d[grp]:
+            try:
+                raw = bytes.fromhex(v["input"])
+            except ValueError:
+                continue
+            if len(raw) != n_in:
+                continue
+            out = ctypes.create_string_buffer(n_out)
+            ok = getattr(emul, fn)(raw, out)
+            assert bool(ok) == v["valid"], (grp, v["name"])
+            if ok:
+                assert out.raw == toaff(dec(raw))
+            seen += 1
+        assert seen >= 13
+
+
+def test_g2_mul_and_msm_bodies(emul):
+    rng = random.Random(3)
+    n = 8
+    ks = [0, 1, o.R - 1] + [rng.randrange(o.R) for _ in range(n - 3)]
+    pts = [o.g2_mul(rng.randrange(1, o.R)) for _ in range(n)]
+    pts[4] = None
+    sb = b"".join(o.scalar_to_bytes(k) for k in ks)
+    pb = b"".join(o.g2_to_affine_bytes(p) for p in pts)
+    out = ctypes.create_string_buffer(96 * n)
+    emul.emul_bls12381_g2_mul_batch(ctypes.c_size_t(n), sb, pb, out)
+    acc = None
+    for i in range(n):
+        r = o.g2_mul(ks[i], pts[i])
+        assert out.raw[96 * i:96 * i + 96] == o.g2_compress(r)
+        acc = o.g2_add(acc, r)
+    o96 = ctypes.create_string_buffer(96)
+    assert emul.emul_bls12381_g2_msm(ctypes.c_size_t(n), sb, pb, 8, 8, 3, o96) == 0 and o96.raw == o.g2_compress(acc)
+
+
+def test_balanced_slice_accumulate_bodies(emul):
+    rng = random.Random(9)
+    n = 40
+    pts = [o.g1_mul(rng.randrange(1, o.R)) for _ in range(n)]
+    pb = b"".join(o.g1_to_affine_bytes(p) for p in pts)
+    for ks in ([rng.randrange(o.R) for _ in range(n)], [0x123456789ABCDEF] * n, [rng.randrange(1 << 20) for _ in range(n)]):
+        sb = b"".join(o.scalar_to_bytes(k) for k in ks)
+        want = o.g1_compress(o.g1_msm(ks, pts))
+        for c, m, L in ((4, 2, 1), (8, 1, 7), (13, 32, 5), (16, 32, 2)):
+            o48 = ctypes.create_string_buffer(48)
+            assert emul.emul_bls12381_g1_msm_v2(ctypes.c_size_t(n), sb, pb, c, m, L, o48) == 0 and o48.raw == want, (c, m, L)
+
+
+def test_hash_to_curve_bodies():
+    from oracle import h2c_bls12381 as h, h2c_bls12381_g2 as h2
+    l1, l2 = _lib("emul_h2c"), _lib("emul_h2c_g2")
+    rng = random.Random(5)
+    for msg, dst in ((b"", h.DST_G1), (b"abc", h.DST_G2), (rng.randbytes(119), b"X"), (rng.randbytes(56), h.DST_G1)):
+        o128 = ctypes.create_string_buffer(128)
+        l1.emul_expand_xmd_128(msg, len(msg), dst, len(dst), o128)
+        assert o128.raw == h.expand_message_xmd(msg, dst, 128)
+        out = ctypes.create_string_buffer(96)
+        l1.emul_bls12381_hash_to_g1(msg, len(msg), dst, len(dst), out)
+        assert out.raw == o.g1_to_affine_bytes(h.hash_to_g1(msg, dst))
+    for msg, dst in ((b"", h.DST_G2), (rng.randbytes(77), b"Y")):
+        out = ctypes.create_string_buffer(192)
+        l2.emul_bls12381_hash_to_g2(msg, len(msg), dst, len(dst), out)
+        assert out.raw == o.g2_to_affine_bytes(h2.hash_to_g2(msg, dst))
+
+
+def test_isogeny_tool_and_oracle_derivations_agree():
+    """tools/derive_isogeny.py (standalone, feeds the device constants) and oracle/h2c_bls12381.py derive the same map."""
+    import importlib.util
+    from oracle import h2c_bls12381 as h, h2c_bls12381_g2 as h2
+    spec = importlib.util.spec_from_file_location("derive_isogeny", os.path.join(ROOT, "tools", "derive_isogeny.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    xn, xd, yn, yd = mod.derive()
+    assert (xn, xd, yn, yd) == (h.ISO_XNUM, h.ISO_XDEN, h.ISO_YNUM, h.ISO_YDEN)
+    x0, v, u = mod.derive_g2()
+    assert x0 == h2.X0 and v == h2._VQ and u == h2._UQ
+
+
+def test_bn254_pairing_bodies():
+    from oracle import bn254 as c, bn254_pairing as b
+    lib = _lib("emul_bn")
+    rng = random.Random(8)
+    for x, y in ((1, 1), (rng.randrange(c.ORDER), rng.randrange(c.ORDER))):
+        P, Q = c.g1_mul(x), b.g2_mul(y)
+        out = ctypes.create_string_buffer(384)
+        lib.emul_bn254_pair(c.g1_marshal(P), b.g2_marshal(Q), out)
+        assert out.raw == b.gt_to_bytes(b.pairing(P, Q))
+    x, y = rng.randrange(c.ORDER), rng.randrange(c.ORDER)
+    args = [c.g1_marshal(c.g1_mul(x)), b.g2_marshal(b.g2_mul(y)), c.g1_marshal(c.g1_mul(x * y % c.ORDER)), b.g2_marshal(b.G2)]
+    assert lib.emul_bn254_pairing_check(*args) == 1
+
+
+def test_ed25519_and_inversion_bodies():
+    from oracle import ed25519 as ed
+    lib = _lib("emul_ed")
+    t8 = bytes.fromhex("c7176a703d4dd84fba3c0b760d10670f2a2053fa2c39ccc64ec7fd7792ac037a")
+    for pt in (ed.encode(ed.BASE), t8, ed.encode(ed.add(ed.scalar_mult(77), ed.decode(t8)))):
+        for k in (0, 1, ed.L, ed.L + 5, (1 << 255) - 1, 0x1234567890ABCDEF):
+            out = ctypes.create_string_buffer(32)
+            assert lib.emul_ed25519_mul(k.to_bytes(32, "little"), pt, out) == 1
+            assert out.raw == ed.point_mul(k.to_bytes(32, "little"), pt)
+    assert lib.emul_ed25519_mul((1).to_bytes(32, "little"), (2).to_bytes(32, "little"), ctypes.create_string_buffer(32)) == 0
+    inv = _lib("emul_inv")
+    rng = random.Random(3)
+    for name, p, n in (("fp381", o.P, 12), ("fp254", 21888242871839275222246405745257275088696311157297823662689037894645226208583, 8),
+                       ("fp256", 65000549695646603732796438742359905742825358107623003571877145026864184071783, 10)):
+        R = 1 << (32 * n)
+        for a in [0, 1, p - 1] + [rng.randrange(p) for _ in range(40)]:
+            am = a * R % p
+            inp = (ctypes.c_uint32 * n)(*[(am >> (32 * i)) & 0xFFFFFFFF for i in range(n)])
+            out = (ctypes.c_uint32 * n)()
+            getattr(inv, f"emul_{name}_inv_vartime")(inp, out)
+            assert sum(int(x) << (32 * i) for i, x in enumerate(out)) == (pow(a, -1, p) * R % p if a else 0)
