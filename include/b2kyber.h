@@ -196,6 +196,22 @@ int b2k_bn254_g1_msm_dev(b2k_ctx* ctx, size_t n, const void* d_scalars, const vo
 int b2k_bn254_recover_commit(b2k_ctx* ctx, size_t t, const uint32_t* indices /*[t]*/, const uint8_t* points /*[t][64]*/,
                              uint8_t* out /*[64]*/);
 
+/* ---- threshold BLS on BLS12-381: share.RecoverCommit and share.PubPoly.Eval --------------------------------- */
+/* RecoverCommit over G1 (points [t][96], out 48 B) or G2 ([t][192], out 96 B): Lagrange weights and MSM on the
+ * device, exactly as b2k_bn254_recover_commit.  replaces: share.RecoverCommit (share/poly.go:449-476) as called by
+ * tbls.Recover (sign/tbls/tbls.go:141) on the signature group. */
+int b2k_bls12381_g1_recover_commit(b2k_ctx* ctx, size_t t, const uint32_t* indices /*[t]*/, const uint8_t* points /*[t][96]*/,
+                                   uint8_t* out /*[48]*/);
+int b2k_bls12381_g2_recover_commit(b2k_ctx* ctx, size_t t, const uint32_t* indices /*[t]*/, const uint8_t* points /*[t][192]*/,
+                                   uint8_t* out /*[96]*/);
+/* out[i] = sum_j (indices[i] + 1)^j * commits[j]  (Horner), operand form in and out.
+ * replaces: share.PubPoly.Eval / Shares (share/poly.go:340-357) -- t Point.Mul + t Add per index -- the
+ * per-partial-signature cost of tbls.Recover (sign/tbls/tbls.go:126) and of DKG/VSS share verification. */
+int b2k_bls12381_g1_pubpoly_eval(b2k_ctx* ctx, size_t t, const uint8_t* commits /*[t][96]*/, size_t n,
+                                 const uint32_t* indices /*[n]*/, uint8_t* out /*[n][96]*/);
+int b2k_bls12381_g2_pubpoly_eval(b2k_ctx* ctx, size_t t, const uint8_t* commits /*[t][192]*/, size_t n,
+                                 const uint32_t* indices /*[n]*/, uint8_t* out /*[n][192]*/);
+
 /* ---- bn254 G2 and pairing --------------------------------------------------------------------------------- */
 /* G2 operands/results: 128 B x.imag||x.real||y.imag||y.real, infinity all-zero (pairing/bn254/point.go:428-455).
  * replaces: bn254 twistPoint.Mul, pairing/bn254/twist.go:167-181 */

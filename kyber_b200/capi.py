@@ -55,6 +55,10 @@ def load_library() -> C.CDLL:
     sigs["b2k_bls12381_verify_g1sig_dev"] = (C.c_int, [vp, sz, vp, vp, vp, vp, C.c_uint32, vp, vp])
     sigs["b2k_bn254_pairing_check"] = (C.c_int, [vp, sz, vp, vp, vp, vp, vp])
     sigs["b2k_bn254_recover_commit"] = (C.c_int, [vp, sz, vp, vp, vp])
+    sigs["b2k_bls12381_g1_recover_commit"] = (C.c_int, [vp, sz, vp, vp, vp])
+    sigs["b2k_bls12381_g2_recover_commit"] = (C.c_int, [vp, sz, vp, vp, vp])
+    sigs["b2k_bls12381_g1_pubpoly_eval"] = (C.c_int, [vp, sz, vp, sz, vp, vp])
+    sigs["b2k_bls12381_g2_pubpoly_eval"] = (C.c_int, [vp, sz, vp, sz, vp, vp])
     host3 = (C.c_int, [vp, sz, vp, vp, vp])
     for name in HOST_FUNCS + DEV_FUNCS:
         sigs[name] = host3
@@ -316,6 +320,24 @@ class Engine:
         t = len(indices)
         assert len(points) == 64 * t
         return self.call_host("b2k_bn254_recover_commit", t, struct.pack("<%dI" % t, *indices), points, 64)
+
+    def bls12381_recover_commit(self, group: int, indices, points: bytes) -> bytes:
+        """share.RecoverCommit over BLS12-381 G1 (group=1, points [t][96] -> 48 B) or G2 (group=2, [t][192] -> 96 B)"""
+        import struct
+        t = len(indices)
+        plen, olen = (96, 48) if group == 1 else (192, 96)
+        assert len(points) == plen * t
+        return self.call_host(f"b2k_bls12381_g{group}_recover_commit", t, struct.pack("<%dI" % t, *indices), points, olen)
+
+    def bls12381_pubpoly_eval(self, group: int, commits: bytes, indices) -> bytes:
+        """PubPoly.Eval for every index: sum_j (I+1)^j C_j; commits [t][96|192] operand form -> [n][96|192]"""
+        import struct
+        plen = 96 if group == 1 else 192
+        t, n = len(commits) // plen, len(indices)
+        out = bytearray(plen * n)
+        bufs = [_buf(x) for x in (commits, struct.pack("<%dI" % n, *indices), out)]
+        self._check(getattr(self.lib, f"b2k_bls12381_g{group}_pubpoly_eval")(self.h, t, bufs[0][0], n, bufs[1][0], bufs[2][0]))
+        return bytes(out)
 
     def bn254_g1_msm(self, scalars: bytes, points: bytes) -> bytes:
         n = len(scalars) // 32

@@ -1,22 +1,25 @@
-// b2k_share.cu -- share.RecoverCommit on the device (bn254 G1): Lagrange weights + MSM.
+// b2k_share.cu -- share.RecoverCommit and share.PubPoly.Eval on the device.
 //
-// Replaces share.RecoverCommit, /root/reference share/poly.go:449-476: the O(t^2) mod.Int products
-// (num *= x_j, den *= x_j - x_i, poly.go:464-470), the t modular inversions (num.Div, :471) and the
-// t Point.Mul + Add (:471-472).  The caller (Go: xyCommit, poly.go:418-445) still sorts the shares by index
-// and passes the first t (index, point) pairs; x_i = index_i + 1.
+// RecoverCommit (reference share/poly.go:449-476): the O(t^2) mod.Int products (num *= x_j, den *= x_j - x_i,
+// :464-470), the t modular inversions (num.Div, :471) and the t Point.Mul + Add (:471-472) -> Lagrange kernel + MSM.
+// The caller (Go: xyCommit, poly.go:418-445) still sorts the shares by index and passes the first t
+// (index, point) pairs; x_i = index_i + 1.
+// PubPoly.Eval / Shares (poly.go:340-357): v = sum_j x^j C_j by Horner, one thread per evaluation index; this is the
+// per-partial-signature cost of tbls.Recover (sign/tbls/tbls.go:118-151: public.Eval(idx) for every share).
 #include "msm_host.cuh"
+#include "codec.cuh"
 using namespace b2k_host;
 
 namespace b2k {
 
-using Fr254 = Fp<Bn254Fr>;
-
 // lambda_i = prod_{j != i} x_j / (x_j - x_i)  mod r, written as 32-byte big-endian scalars
+template <class FR>
 __global__ void __launch_bounds__(128) k_lagrange_at_zero(uint32_t t, const uint32_t* __restrict__ idx,
                                                           uint8_t* __restrict__ scalars, uint32_t* flags) {
+  using S = Fp<FR>;
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= t) return;
-  Fr254 num, den, xi, xj, d;
+  S num, den, xi, xj, d;
   fp_set_one(num);
   fp_set_one(den);
   fp_set_zero(xi);
@@ -45,36 +48,91 @@ __global__ void __launch_bounds__(128) k_lagrange_at_zero(uint32_t t, const uint
   }
 }
 
+// out[i] = sum_j (idx_i + 1)^j C_j  (Horner: v = x v + C_j, poly.go:343-346), operand form
+template <class CV>
+__global__ void __launch_bounds__(128) k_pubpoly_eval(uint32_t t, const Affine<typename CV::F>* __restrict__ commits, uint32_t n,
+                                                      const uint32_t* __restrict__ idx, uint8_t* __restrict__ out) {
+  using F = typename CV::F;
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint64_t x = (uint64_t)idx[i] + 1u;
+  int top = 63;
+  while (top > 0 && !((x >> top) & 1)) top--;
+  Jac<F> v;
+  jac_set_inf(v);
+  for (int j = (int)t - 1; j >= 0; j--) {
+    Jac<F> acc = v;                             // x * v by double-and-add over the bits of x (top bit consumed)
+    for (int b = top - 1; b >= 0; b--) {
+      jac_dbl(acc, acc);
+      if ((x >> b) & 1) jac_add(acc, acc, v);
+    }
+    Affine<F> c = commits[j];
+    jac_madd(v, acc, c);
+  }
+  Affine<F> a;
+  jac_to_affine(a, v);
+  CV::store_affine(out + (size_t)CV::IN_BYTES * i, a);
+}
+
 }  // namespace b2k
 
-extern "C" {
-
-// out = sum_i lambda_i * points[i],  lambda_i from the share indices (x_i = idx_i + 1)
-int b2k_bn254_recover_commit(b2k_ctx* ctx, size_t t, const uint32_t* indices /*[t]*/, const uint8_t* points /*[t][64]*/,
-                             uint8_t* out /*[64]*/) {
+template <class CV, class FR>
+static int recover_commit(b2k_ctx* ctx, size_t t, const uint32_t* indices, const uint8_t* points, uint8_t* out) {
   if (!ctx || !indices || !points || !out || t == 0 || t >= (size_t(1) << 31)) return B2K_ERR_ARG;
   CK(cudaSetDevice(ctx->device));
-  MsmPlan pl = make_plan(t, ctx->force_c, Bn254G1::SCALAR_BITS);
-  size_t extra = pad256(t * 4) + pad256(t * 32) + pad256(t * 64) + 1024;
-  int rc = arena_reserve(ctx, msm_scratch_bytes<Bn254G1>(t, pl, ctx->force_L) + extra);
+  MsmPlan pl = make_plan(t, ctx->force_c, CV::SCALAR_BITS);
+  size_t extra = pad256(t * 4) + pad256(t * 32) + pad256(t * (size_t)CV::IN_BYTES) + 1024;
+  int rc = arena_reserve(ctx, msm_scratch_bytes<CV>(t, pl, ctx->force_L) + extra);
   if (rc) return rc;
   uint32_t* d_idx = arena_take<uint32_t>(ctx, t);
   uint8_t* d_s = arena_take<uint8_t>(ctx, t * 32);
-  uint8_t* d_p = arena_take<uint8_t>(ctx, t * 64);
+  uint8_t* d_p = arena_take<uint8_t>(ctx, t * (size_t)CV::IN_BYTES);
   uint8_t* d_o = arena_take<uint8_t>(ctx, 256);
   cudaStream_t st = ctx->stream;
   CK(cudaMemsetAsync(ctx->d_flags, 0, 4, st));
   CK(cudaMemcpyAsync(d_idx, indices, t * 4, cudaMemcpyHostToDevice, st));
-  CK(cudaMemcpyAsync(d_p, points, t * 64, cudaMemcpyHostToDevice, st));
-  k_lagrange_at_zero<<<(unsigned)((t + 127) / 128), 128, 0, st>>>((uint32_t)t, d_idx, d_s, ctx->d_flags);
+  CK(cudaMemcpyAsync(d_p, points, t * (size_t)CV::IN_BYTES, cudaMemcpyHostToDevice, st));
+  k_lagrange_at_zero<FR><<<(unsigned)((t + 127) / 128), 128, 0, st>>>((uint32_t)t, d_idx, d_s, ctx->d_flags);
   ctx->launches += 1;
-  rc = msm_enqueue<Bn254G1>(ctx, t, pl, d_s, d_p, d_o);
+  rc = msm_enqueue<CV>(ctx, t, pl, d_s, d_p, d_o);
   if (rc) return rc;
-  CK(cudaMemcpyAsync(out, d_o, 64, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(out, d_o, CV::OUT_BYTES, cudaMemcpyDeviceToHost, st));
   CK(cudaMemcpyAsync(ctx->h_flags, ctx->d_flags, 4, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
   if (*ctx->h_flags & 4u) { ctx->err = "duplicate share index"; return B2K_ERR_ARG; }
   return check_flags(ctx);
 }
+
+template <class CV>
+static int pubpoly_eval(b2k_ctx* ctx, size_t t, const uint8_t* commits, size_t n, const uint32_t* indices, uint8_t* out) {
+  using F = typename CV::F;
+  if (!ctx || !commits || !indices || !out || t == 0 || n == 0 || t >= (size_t(1) << 31) || n >= (size_t(1) << 31)) return B2K_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  int rc = arena_reserve(ctx, pad256(t * (size_t)CV::IN_BYTES) + pad256(t * sizeof(Affine<F>)) + pad256(n * 4) +
+                                  pad256(n * (size_t)CV::IN_BYTES) + 4096);
+  if (rc) return rc;
+  uint8_t* d_c = arena_take<uint8_t>(ctx, t * (size_t)CV::IN_BYTES);
+  auto* d_cm = arena_take<Affine<F>>(ctx, t);
+  uint32_t* d_idx = arena_take<uint32_t>(ctx, n);
+  uint8_t* d_o = arena_take<uint8_t>(ctx, n * (size_t)CV::IN_BYTES);
+  cudaStream_t st = ctx->stream;
+  CK(cudaMemcpyAsync(d_c, commits, t * (size_t)CV::IN_BYTES, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(d_idx, indices, n * 4, cudaMemcpyHostToDevice, st));
+  k_load_points<CV><<<(unsigned)((t + 255) / 256), 256, 0, st>>>(t, d_c, d_cm);
+  k_pubpoly_eval<CV><<<(unsigned)((n + 127) / 128), 128, 0, st>>>((uint32_t)t, d_cm, (uint32_t)n, d_idx, d_o);
+  CK(cudaGetLastError());
+  ctx->launches += 2;
+  CK(cudaMemcpyAsync(out, d_o, n * (size_t)CV::IN_BYTES, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return B2K_OK;
+}
+
+extern "C" {
+
+int b2k_bn254_recover_commit(b2k_ctx* c, size_t t, const uint32_t* idx, const uint8_t* pts, uint8_t* out) { return recover_commit<Bn254G1, Bn254Fr>(c, t, idx, pts, out); }
+int b2k_bls12381_g1_recover_commit(b2k_ctx* c, size_t t, const uint32_t* idx, const uint8_t* pts, uint8_t* out) { return recover_commit<Bls381G1, Bls381Fr>(c, t, idx, pts, out); }
+int b2k_bls12381_g2_recover_commit(b2k_ctx* c, size_t t, const uint32_t* idx, const uint8_t* pts, uint8_t* out) { return recover_commit<Bls381G2, Bls381Fr>(c, t, idx, pts, out); }
+int b2k_bls12381_g1_pubpoly_eval(b2k_ctx* c, size_t t, const uint8_t* commits, size_t n, const uint32_t* idx, uint8_t* out) { return pubpoly_eval<Bls381G1>(c, t, commits, n, idx, out); }
+int b2k_bls12381_g2_pubpoly_eval(b2k_ctx* c, size_t t, const uint8_t* commits, size_t n, const uint32_t* idx, uint8_t* out) { return pubpoly_eval<Bls381G2>(c, t, commits, n, idx, out); }
 
 }  // extern "C"

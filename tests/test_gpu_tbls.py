@@ -1,0 +1,84 @@
+"""GPU parity for the threshold-BLS path: share.PubPoly.Eval for many indices
+(share/poly.go:340-357), share.RecoverCommit on BLS12-381 G1/G2 (share/poly.go:449-476) and the whole of
+tbls.Recover (sign/tbls/tbls.go:118-151): evaluate the public polynomial at every signer index, verify every partial
+signature, recover the group signature by Lagrange interpolation -- and the result must be the ordinary BLS signature
+of the group secret."""
+import random
+
+import pytest
+
+from kyber_b200 import workload as wl
+from oracle import bls12381 as o
+from oracle import h2c_bls12381 as h
+from oracle import share_poly
+
+pytestmark = pytest.mark.gpu
+
+
+class _G1:
+    ORDER = o.R
+    g1_add = staticmethod(o.g1_add)
+    g1_mul = staticmethod(o.g1_mul)
+
+
+def _poly_eval(coeffs, x):
+    acc = 0
+    for c in reversed(coeffs):
+        acc = (acc * x + c) % o.R
+    return acc
+
+
+def test_pubpoly_eval_g1_and_g2(engine):
+    rng = random.Random(81)
+    t = 9
+    coeffs = [rng.randrange(o.R) for _ in range(t)]
+    idx = [0, 1, 5, 77, 4095, 2 ** 31]
+    c1 = b"".join(o.g1_to_affine_bytes(o.g1_mul(c)) for c in coeffs)           # PriPoly.Commit: C_j = a_j * G
+    out = engine.bls12381_pubpoly_eval(1, c1, idx)
+    for k, i in enumerate(idx):
+        assert out[96 * k:96 * k + 96] == o.g1_to_affine_bytes(o.g1_mul(_poly_eval(coeffs, i + 1))), i
+    c2 = b"".join(o.g2_to_affine_bytes(o.g2_mul(c)) for c in coeffs)
+    out = engine.bls12381_pubpoly_eval(2, c2, idx[:4])
+    for k, i in enumerate(idx[:4]):
+        assert out[192 * k:192 * k + 192] == o.g2_to_affine_bytes(o.g2_mul(_poly_eval(coeffs, i + 1))), i
+
+
+def test_recover_commit_bls12381(engine):
+    rng = random.Random(82)
+    t = 40
+    coeffs = [rng.randrange(o.R) for _ in range(t)]
+    idx = sorted(rng.sample(range(200), t))
+    ys = [_poly_eval(coeffs, i + 1) for i in idx]
+    p1 = engine.bls12381_g1_mul_batch_affine(wl.scalars_to_bytes(ys), wl.G1_BLS12381_AFFINE * t)
+    assert engine.bls12381_recover_commit(1, idx, p1) == o.g1_compress(o.g1_mul(coeffs[0]))
+    shares = [(i, o.g1_from_affine_bytes(p1[96 * k:96 * k + 96])) for k, i in enumerate(idx)]
+    assert engine.bls12381_recover_commit(1, idx, p1) == o.g1_compress(share_poly.recover_commit(_G1, shares, t))
+    p2 = engine.bls12381_g2_mul_batch_affine(wl.scalars_to_bytes(ys), o.g2_to_affine_bytes(o.G2) * t)
+    assert engine.bls12381_recover_commit(2, idx, p2) == o.g2_compress(o.g2_mul(coeffs[0]))
+
+
+def test_tbls_recover_flow(engine):
+    """t-of-n threshold BLS, signatures on G1 / keys on G2: all heavy steps on the engine."""
+    rng = random.Random(83)
+    t, n = 16, 24
+    coeffs = [rng.randrange(o.R) for _ in range(t)]                 # secret polynomial; group secret = coeffs[0]
+    msg = b"threshold message"
+    hm = h.hash_to_g1(msg)
+    pub_commits = b"".join(o.g2_to_affine_bytes(o.g2_mul(c)) for c in coeffs)     # PubPoly on G2
+    signers = list(range(n))
+    shares = [_poly_eval(coeffs, i + 1) for i in signers]
+    part = engine.bls12381_g1_mul_batch(wl.scalars_to_bytes(shares), o.g1_to_affine_bytes(hm) * n)   # partial sigs (48 B)
+    part = bytearray(part)
+    part[48 * 3:48 * 4] = part[48 * 4:48 * 5]                        # signer 3 sends a wrong partial signature
+    # tbls.Recover: public.Eval(idx) for every share (n evaluations of a degree t-1 commitment polynomial)
+    pk_aff = engine.bls12381_pubpoly_eval(2, pub_commits, signers)
+    pk_c = engine.bls12381_g2_mul_batch(b"".join((1).to_bytes(32, "big") for _ in range(n)), pk_aff)   # compress
+    ok = engine.bls12381_verify_g1sig(pk_c, [msg] * n, h.DST_G1, bytes(part))
+    assert list(ok) == [0 if i == 3 else 1 for i in range(n)]
+    good = [i for i in signers if ok[i]][:t]
+    pts, okd = engine.bls12381_g1_decompress(b"".join(bytes(part[48 * i:48 * i + 48]) for i in good))
+    assert set(okd) == {1}
+    sig = engine.bls12381_recover_commit(1, good, pts)
+    assert sig == o.g1_compress(o.g1_mul(coeffs[0], hm))             # = bls.Sign(group secret, msg)
+    group_pk = o.g2_compress(o.g2_mul(coeffs[0]))
+    assert engine.bls12381_verify_g1sig(group_pk, [msg], h.DST_G1, sig) == b"\x01"
