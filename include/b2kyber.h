@@ -72,6 +72,8 @@ int b2k_set_msm_variant(b2k_ctx* ctx, int one_thread_per_bucket);
 int b2k_set_msm_groups(b2k_ctx* ctx, int groups);
 /* Resident bucket-accumulate blocks per SM (4..6; launch bound => register cap).  Tuning aid. */
 int b2k_set_msm_occupancy(b2k_ctx* ctx, int blocks_per_sm);
+/* Buckets per thread in the chunked bucket reduction (power of two, 0 = automatic).  Tuning aid. */
+int b2k_set_msm_chunk(b2k_ctx* ctx, int m);
 /* Number of kernels launched by this context so far. */
 uint64_t b2k_launch_count(const b2k_ctx* ctx);
 

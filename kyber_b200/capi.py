@@ -40,6 +40,7 @@ def load_library() -> C.CDLL:
         "b2k_set_pairing_variant": (C.c_int, [vp, C.c_int]),
         "b2k_set_msm_groups": (C.c_int, [vp, C.c_int]),
         "b2k_set_msm_occupancy": (C.c_int, [vp, C.c_int]),
+        "b2k_set_msm_chunk": (C.c_int, [vp, C.c_int]),
     }
     sigs["b2k_bls12381_pair"] = (C.c_int, [vp, sz, vp, vp, vp])
     sigs["b2k_bls12381_pair_dev"] = (C.c_int, [vp, sz, vp, vp, vp])

@@ -146,6 +146,12 @@ int b2k_set_msm_slice(b2k_ctx* ctx, int L) {
   return B2K_OK;
 }
 
+int b2k_set_msm_chunk(b2k_ctx* ctx, int m) {
+  if (!ctx || m < 0 || m > 32768) return B2K_ERR_ARG;
+  ctx->force_m = m;
+  return B2K_OK;
+}
+
 int b2k_set_msm_occupancy(b2k_ctx* ctx, int blocks_per_sm) {
   if (!ctx || blocks_per_sm < 4 || blocks_per_sm > 6) return B2K_ERR_ARG;
   ctx->acc_minb = blocks_per_sm;

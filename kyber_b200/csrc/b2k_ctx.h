@@ -21,6 +21,7 @@ struct b2k_ctx {
   cudaEvent_t ev[B2K_N_EV];
   bool timings_valid = false;
   int force_c = 0;
+  int force_m = 0;      // bucket-reduction chunk override (0 = automatic)
   int force_L = 0;      // slice length override (0 = automatic)
   int use_v1 = 0;       // 1 = one-thread-per-bucket accumulate (kept for A/B measurements)
   cudaStream_t stream2 = nullptr;   // high-priority side stream: bucket reduction of one window group overlaps the next accumulate

@@ -38,14 +38,15 @@ inline int pick_window(size_t n, int scalar_bits) {
 }
 
 // scalar_bits = bit length of the group order: signed-digit recoding needs windows for scalar_bits + 1 bits
-inline MsmPlan make_plan(size_t n, int force_c, int scalar_bits) {
+inline MsmPlan make_plan(size_t n, int force_c, int scalar_bits, int force_m = 0) {
   MsmPlan pl;
   pl.c = force_c ? force_c : pick_window(n, scalar_bits);
   pl.W = (scalar_bits + pl.c) / pl.c;
   pl.nb = 1 << (pl.c - 1);
   size_t total = (size_t)pl.W * pl.nb;
   int m = 1;
-  while (m < 64 && m * 2 <= pl.nb && total / (size_t)(m * 2) >= 16384) m *= 2;
+  while (m < 64 && m * 2 <= pl.nb && total / (size_t)(m * 2) >= 32768) m *= 2;   // >= 32k reduction threads (measured best)
+  if (force_m > 0 && force_m <= pl.nb && (force_m & (force_m - 1)) == 0) m = force_m;
   pl.m = m;
   memset(pl.K, 0, sizeof pl.K);
   for (int w = 0; w < pl.W; w++) {
@@ -209,7 +210,7 @@ int msm_dev(b2k_ctx* ctx, size_t n, const void* d_scalars, const void* d_points,
     return B2K_ERR_ARG;
   }
   CK(cudaSetDevice(ctx->device));
-  MsmPlan pl = make_plan(n, ctx->force_c, CV::SCALAR_BITS);
+  MsmPlan pl = make_plan(n, ctx->force_c, CV::SCALAR_BITS, ctx->force_m);
   int rc = arena_reserve(ctx, msm_scratch_bytes<CV>(n, pl, ctx->force_L));
   if (rc) return rc;
   return msm_enqueue<CV>(ctx, n, pl, (const uint8_t*)d_scalars, (const uint8_t*)d_points, (uint8_t*)d_out, affine_out);
@@ -222,7 +223,7 @@ int msm_host(b2k_ctx* ctx, size_t n, const uint8_t* scalars, const uint8_t* poin
     return B2K_ERR_ARG;
   }
   CK(cudaSetDevice(ctx->device));
-  MsmPlan pl = make_plan(n, ctx->force_c, CV::SCALAR_BITS);
+  MsmPlan pl = make_plan(n, ctx->force_c, CV::SCALAR_BITS, ctx->force_m);
   size_t in_bytes = pad256(n * 32) + pad256(n * (size_t)CV::IN_BYTES) + 256;
   int rc = arena_reserve(ctx, msm_scratch_bytes<CV>(n, pl, ctx->force_L) + in_bytes);
   if (rc) return rc;

@@ -9,10 +9,9 @@ pts = eng.bls12381_g1_mul_batch_affine(wl.scalars_to_bytes(a), wl.G1_BLS12381_AF
 sb = wl.scalars_to_bytes(s)
 exp = o.g1_compress(o.g1_mul(wl.dot_mod(s, a, o.R)))
 names = ["load", "count", "scan", "scatter", "accum", "reduce", "wsum", "final", "total", "fixup/tail"]
-for occ in (4, 5, 6):
-    for L in (64, 32, 48):
-        eng._check(eng.lib.b2k_set_msm_occupancy(eng.h, occ)); eng.set_msm_slice(L)
-        for rep in range(3):
-            got = eng.bls12381_g1_msm(sb, pts)
-        tm = eng.last_timings()
-        print(f"occ={occ} L={L} ok={got == exp} " + " ".join(f"{k}={v:.3f}" for k, v in zip(names, tm)), flush=True)
+for m in (0, 4, 8, 16, 32, 64, 128):
+    eng._check(eng.lib.b2k_set_msm_chunk(eng.h, m))
+    for rep in range(3):
+        got = eng.bls12381_g1_msm(sb, pts)
+    tm = eng.last_timings()
+    print(f"m={m} ok={got == exp} " + " ".join(f"{k}={v:.3f}" for k, v in zip(names, tm)), flush=True)
