@@ -237,6 +237,10 @@ int b2k_bn256_g1_mul_batch(b2k_ctx* ctx, size_t n, const uint8_t* scalars, const
 int b2k_bn256_g1_msm(b2k_ctx* ctx, size_t n, const uint8_t* scalars, const uint8_t* points, uint8_t* out /*[64]*/);
 int b2k_bn256_g2_mul_batch(b2k_ctx* ctx, size_t n, const uint8_t* scalars, const uint8_t* points, uint8_t* out /*[n][128]*/);
 int b2k_bn256_g2_msm(b2k_ctx* ctx, size_t n, const uint8_t* scalars, const uint8_t* points, uint8_t* out /*[128]*/);
+/* bn256 pairing: the twin of the bn254 one (pairing/bn256/optate.go:126-274, suite.go:99-109); GT 384 B. */
+int b2k_bn256_pair(b2k_ctx* ctx, size_t n, const uint8_t* g1 /*[n][64]*/, const uint8_t* g2 /*[n][128]*/, uint8_t* gt /*[n][384]*/);
+int b2k_bn256_pairing_check(b2k_ctx* ctx, size_t n, const uint8_t* a1, const uint8_t* a2, const uint8_t* b1,
+                            const uint8_t* b2, uint8_t* ok /*[n]*/);
 
 /* Launch-bound variant of the BLS12-381 pairing kernels (0 = default).  Tuning aid. */
 int b2k_set_pairing_variant(b2k_ctx* ctx, int variant);

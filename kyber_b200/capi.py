@@ -55,6 +55,7 @@ def load_library() -> C.CDLL:
     sigs["b2k_bls12381_verify_g1sig"] = (C.c_int, [vp, sz, vp, vp, vp, vp, C.c_uint32, vp, vp])
     sigs["b2k_bls12381_verify_g1sig_dev"] = (C.c_int, [vp, sz, vp, vp, vp, vp, C.c_uint32, vp, vp])
     sigs["b2k_bn254_pairing_check"] = (C.c_int, [vp, sz, vp, vp, vp, vp, vp])
+    sigs["b2k_bn256_pairing_check"] = (C.c_int, [vp, sz, vp, vp, vp, vp, vp])
     sigs["b2k_bn254_recover_commit"] = (C.c_int, [vp, sz, vp, vp, vp])
     sigs["b2k_bls12381_g1_recover_commit"] = (C.c_int, [vp, sz, vp, vp, vp])
     sigs["b2k_bls12381_g2_recover_commit"] = (C.c_int, [vp, sz, vp, vp, vp])
@@ -70,7 +71,7 @@ def load_library() -> C.CDLL:
 
 
 HOST_FUNCS = [
-    "b2k_bn254_pair", "b2k_bn254_g2_mul_batch", "b2k_bn254_g2_msm",
+    "b2k_bn254_pair", "b2k_bn254_g2_mul_batch", "b2k_bn254_g2_msm", "b2k_bn256_pair",
     "b2k_bn256_g1_mul_batch", "b2k_bn256_g1_msm", "b2k_bn256_g2_mul_batch", "b2k_bn256_g2_msm",
     "b2k_bls12381_g1_msm_affine", "b2k_bls12381_g2_msm_affine",
     "b2k_bls12381_g2_mul_batch", "b2k_bls12381_g2_mul_batch_affine", "b2k_bls12381_g2_msm",
@@ -293,6 +294,17 @@ class Engine:
     def bn256_g1_msm(self, s, p): return self.bn256_call("b2k_bn256_g1_msm", s, p, 64, 64)
     def bn256_g2_mul_batch(self, s, p): return self.bn256_call("b2k_bn256_g2_mul_batch", s, p, 128, 128 * (len(s) // 32))
     def bn256_g2_msm(self, s, p): return self.bn256_call("b2k_bn256_g2_msm", s, p, 128, 128)
+
+    def bn256_pair(self, g1: bytes, g2: bytes) -> bytes:
+        n = len(g1) // 64
+        return self.call_host("b2k_bn256_pair", n, g1, g2, 384 * n)
+
+    def bn256_pairing_check(self, a1: bytes, a2: bytes, b1: bytes, b2: bytes) -> bytes:
+        n = len(a1) // 64
+        out = bytearray(n)
+        bufs = [_buf(x) for x in (a1, a2, b1, b2, out)]
+        self._check(self.lib.b2k_bn256_pairing_check(self.h, n, *[b[0] for b in bufs]))
+        return bytes(out)
 
     def ed25519_mul_batch(self, scalars_le: bytes, points: bytes) -> bytes:
         """n x edwards25519 Point.Mul: raw little-endian 32-byte scalars, 32-byte compressed points -> 32 B each"""

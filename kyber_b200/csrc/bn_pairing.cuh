@@ -1,4 +1,4 @@
-// bn_pairing.cuh -- bn254 optimal-ate pairing (D-type twist, signed-digit loop over 6u+2, two Frobenius
+// bn_pairing.cuh -- BN optimal-ate pairing for bn254 and its twin bn256 (D-type twist, signed-digit loop over 6u+2, two Frobenius
 // steps, final exponentiation with the exact exponent (p^12-1)/n).
 //
 // Replaces the in-tree reference pairing:
@@ -19,20 +19,84 @@
 
 namespace b2k {
 
+// xi = 3 + u (pairing/bn256/gfp2.go:103-118):  (3 a0 - a1) + (3 a1 + a0) u
+struct Bn256Tower {
+  using Base = Bn256Fp;
+  B2K_D static void mul_xi(Fp2<Base>& r, const Fp2<Base>& a) {
+    Fp<Base> t0, t1, n0, n1;
+    fp_add(t0, a.c0, a.c0); fp_add(t0, t0, a.c0);
+    fp_add(t1, a.c1, a.c1); fp_add(t1, t1, a.c1);
+    fp_sub(n0, t0, a.c1);
+    fp_add(n1, t1, a.c0);
+    r.c0 = n0; r.c1 = n1;
+  }
+};
+
+// Pairing configurations: tower, u, digit table of 6u+2 (least significant first) and 32-byte codecs.
+struct Bn254Pair {
+  using T = Bn254Tower;
+  using FC = Bn254Fp;
+  static constexpr uint64_t U = 4965661367192848881ULL;
+  static constexpr int NDIG = 65;
+  B2K_D static int digit(int i) {   // pairing/bn254/optate.go:117-120 (data)
+    const int8_t d[65] = {0, 0, 0, 1, 0, 1, 0, -1, 0, 0, 1, -1, 0, 0, 1, 0, 0, 1, 1, 0, -1, 0, 0, 1, 0, -1, 0, 0, 0, 0, 1, 1,
+                          1, 0, 0, -1, 0, 0, 1, 0, 0, 0, 0, 0, -1, 0, 0, 1, 1, 0, 0, -1, 0, 0, 0, 1, 1, 0, -1, 0, 0, 1, 0, 1, 1};
+    return d[i];
+  }
+  B2K_D static void load32(Fp<FC>& r, const uint8_t* p) { Fp<FC> t; fp_load_be(t, p); fp_to_mont(r, t); }
+  B2K_D static void store32(uint8_t* p, const Fp<FC>& a) { Fp<FC> t; fp_from_mont(t, a); fp_store_be(p, t); }
+};
+
+struct Bn256Pair {
+  using T = Bn256Tower;
+  using FC = Bn256Fp;
+  static constexpr uint64_t U = 6518589491078791937ULL;
+  static constexpr int NDIG = 66;
+  B2K_D static int digit(int i) {   // pairing/bn256/optate.go:117-122 (data)
+    const int8_t d[66] = {0, 0, 0, 1, 0, 0, 0, 0, 0, 1, 0, 0, 1, 0, 0, 0, -1, 0, 1, 0, 1, 0, 0, 0, 0, 1, 0, 1, 0, 0, 0, -1, 0,
+                          1, 0, 0, 0, 1, 0, -1, 0, 0, 0, -1, 0, 1, 0, 0, 0, 0, 0, 1, 0, 0, -1, 0, -1, 0, 0, 0, 0, 1, 0, 0, 0, 1};
+    return d[i];
+  }
+  B2K_D static void load32(Fp<FC>& r, const uint8_t* p) {   // 32 bytes big-endian into 10 limbs
+    Fp<FC> t;
+    t.v[8] = 0; t.v[9] = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      const uint8_t* q = p + 4 * (7 - j);
+      t.v[j] = ((uint32_t)q[0] << 24) | ((uint32_t)q[1] << 16) | ((uint32_t)q[2] << 8) | q[3];
+    }
+    fp_to_mont(r, t);
+  }
+  B2K_D static void store32(uint8_t* p, const Fp<FC>& a) {
+    Fp<FC> t;
+    fp_from_mont(t, a);
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      uint8_t* q = p + 4 * (7 - j);
+      q[0] = (uint8_t)(t.v[j] >> 24); q[1] = (uint8_t)(t.v[j] >> 16); q[2] = (uint8_t)(t.v[j] >> 8); q[3] = (uint8_t)t.v[j];
+    }
+  }
+};
+
+template <class P> using PFp = Fp<typename P::FC>;
+template <class P> using PFp2 = Fp2<typename P::FC>;
+template <class P> using PFp6 = Fp6<typename P::T>;
+template <class P> using PFp12 = Fp12<typename P::T>;
+
+// bn254 shorthands (used by the kernels of b2k_bn254_pairing.cu)
 using NT = Bn254Tower;
 using NFp = Fp<Bn254Fp>;
 using NFp2 = Fp2<Bn254Fp>;
 using NFp6 = Fp6<NT>;
 using NFp12 = Fp12<NT>;
 
-constexpr uint64_t BN254_U = 4965661367192848881ULL;
-
-struct BnLine { NFp2 l0, l1, l3; };
+template <class P> struct BnLine { PFp2<P> l0, l1, l3; };
 
 // f *= l3 + (l1 + l0 t) w
-B2K_NI void fp12_mul_line_d(NFp12& f, const BnLine& l) {
-  NFp6 A, B, C;
-  NFp2 s;
+template <class P>
+B2K_NI void fp12_mul_line_d(PFp12<P>& f, const BnLine<P>& l) {
+  PFp6<P> A, B, C;
+  PFp2<P> s;
   fp6_mul_by_01(A, f.c1, l.l1, l.l0);            // f1 * (l1 + l0 t)
   fp6_mul_fp2(B, f.c0, l.l3);                    // f0 * l3
   fp2_add(s, l.l1, l.l3);
@@ -44,8 +108,9 @@ B2K_NI void fp12_mul_line_d(NFp12& f, const BnLine& l) {
   fp6_add(f.c0, B, A);
 }
 
-B2K_NI void bn_double_step(BnLine& l, Jac<NFp2>& T, const Affine<NFp>& P) {
-  NFp2 A, B, C, D, E, ZZ, t;
+template <class PC>
+B2K_NI void bn_double_step(BnLine<PC>& l, Jac<PFp2<PC>>& T, const Affine<PFp<PC>>& P) {
+  PFp2<PC> A, B, C, D, E, ZZ, t;
   fp2_sqr(A, T.X);
   fp2_sqr(B, T.Y);
   fp2_sqr(C, B);
@@ -62,8 +127,9 @@ B2K_NI void bn_double_step(BnLine& l, Jac<NFp2>& T, const Affine<NFp>& P) {
   T.X = A;
 }
 
-B2K_NI void bn_add_step(BnLine& l, Jac<NFp2>& T, const Affine<NFp2>& Q, const Affine<NFp>& P) {
-  NFp2 ZZ, U2, S2, H, R, HH, HHH, V, t;
+template <class PC>
+B2K_NI void bn_add_step(BnLine<PC>& l, Jac<PFp2<PC>>& T, const Affine<PFp2<PC>>& Q, const Affine<PFp<PC>>& P) {
+  PFp2<PC> ZZ, U2, S2, H, R, HH, HHH, V, t;
   fp2_sqr(ZZ, T.Z);
   fp2_mul(U2, Q.x, ZZ);
   fp2_mul(S2, Q.y, T.Z); fp2_mul(S2, S2, ZZ);
@@ -85,22 +151,16 @@ B2K_NI void bn_add_step(BnLine& l, Jac<NFp2>& T, const Affine<NFp2>& Q, const Af
 
 #define B2K_BN_COEF(J, K, dst)                                                       \
   {                                                                                  \
-    _Pragma("unroll") for (int q = 0; q < 8; q++) {                                  \
-      (dst).c0.v[q] = Bn254Fp::frob##J##_##K##_c0(q);                                \
-      (dst).c1.v[q] = Bn254Fp::frob##J##_##K##_c1(q);                                \
+    _Pragma("unroll") for (int q = 0; q < PC::FC::N; q++) {                          \
+      (dst).c0.v[q] = PC::FC::frob##J##_##K##_c0(q);                                 \
+      (dst).c1.v[q] = PC::FC::frob##J##_##K##_c1(q);                                 \
     }                                                                                \
   }
 
-// digits of 6u+2, least significant first (pairing/bn254/optate.go:117-120; data)
-B2K_D int bn254_loop_digit(int i) {
-  const int8_t d[65] = {0, 0, 0, 1, 0, 1, 0, -1, 0, 0, 1, -1, 0, 0, 1, 0, 0, 1, 1, 0, -1, 0, 0, 1, 0, -1, 0, 0, 0, 0, 1, 1,
-                        1, 0, 0, -1, 0, 0, 1, 0, 0, 0, 0, 0, -1, 0, 0, 1, 1, 0, 0, -1, 0, 0, 0, 1, 1, 0, -1, 0, 0, 1, 0, 1, 1};
-  return d[i];
-}
-
 // f = prod_i f_{6u+2,Q_i}(P_i) * l_{T,pi(Q_i)} * l_{T+pi(Q_i), -pi^2(Q_i)}; pairs with an infinity member give 1
-template <int NPAIRS>
-B2K_D void bn254_miller_loop(NFp12& f, const Affine<NFp>* P, const Affine<NFp2>* Q) {
+template <class PC, int NPAIRS>
+B2K_D void bn_miller_loop(PFp12<PC>& f, const Affine<PFp<PC>>* P, const Affine<PFp2<PC>>* Q) {
+  using NFp2 = PFp2<PC>;
   Jac<NFp2> T[NPAIRS];
   Affine<NFp2> Qn[NPAIRS];
   bool live[NPAIRS];
@@ -111,22 +171,22 @@ B2K_D void bn254_miller_loop(NFp12& f, const Affine<NFp>* P, const Affine<NFp2>*
     Qn[i].x = Q[i].x; fp2_neg(Qn[i].y, Q[i].y);
   }
   fp12_set_one(f);
-  BnLine l;
-  for (int i = 64; i > 0; i--) {
-    if (i != 64) fp12_sqr(f, f);
+  BnLine<PC> l;
+  for (int i = PC::NDIG - 1; i > 0; i--) {
+    if (i != PC::NDIG - 1) fp12_sqr(f, f);
 #pragma unroll
     for (int k = 0; k < NPAIRS; k++) {
       if (!live[k]) continue;
-      bn_double_step(l, T[k], P[k]);
-      fp12_mul_line_d(f, l);
+      bn_double_step<PC>(l, T[k], P[k]);
+      fp12_mul_line_d<PC>(f, l);
     }
-    const int d = bn254_loop_digit(i - 1);
+    const int d = PC::digit(i - 1);
     if (d == 0) continue;
 #pragma unroll
     for (int k = 0; k < NPAIRS; k++) {
       if (!live[k]) continue;
-      bn_add_step(l, T[k], d > 0 ? Q[k] : Qn[k], P[k]);
-      fp12_mul_line_d(f, l);
+      bn_add_step<PC>(l, T[k], d > 0 ? Q[k] : Qn[k], P[k]);
+      fp12_mul_line_d<PC>(f, l);
     }
   }
   // Frobenius steps: Q1 = (conj(x) xi^((p-1)/3), conj(y) xi^((p-1)/2)),  -Q2 = (x xi^((p^2-1)/3), y)
@@ -143,17 +203,17 @@ B2K_D void bn254_miller_loop(NFp12& f, const Affine<NFp>* P, const Affine<NFp2>*
     fp2_conj(c, Q[k].y); fp2_mul(q1.y, c, g12);
     fp2_mul(mq2.x, Q[k].x, g23);
     mq2.y = Q[k].y;
-    bn_add_step(l, T[k], q1, P[k]);
-    fp12_mul_line_d(f, l);
-    bn_add_step(l, T[k], mq2, P[k]);
-    fp12_mul_line_d(f, l);
+    bn_add_step<PC>(l, T[k], q1, P[k]);
+    fp12_mul_line_d<PC>(f, l);
+    bn_add_step<PC>(l, T[k], mq2, P[k]);
+    fp12_mul_line_d<PC>(f, l);
   }
 }
 
 // f^(p^J) on the w-power basis (slots: w^0 c0.c0, w^1 c1.c0, w^2 c0.c1, w^3 c1.c1, w^4 c0.c2, w^5 c1.c2)
-template <int J>
-B2K_NI void bn254_frobenius(NFp12& r, const NFp12& f) {
-  NFp2 g, a;
+template <class PC, int J>
+B2K_NI void bn_frobenius(PFp12<PC>& r, const PFp12<PC>& f) {
+  PFp2<PC> g, a;
   a = f.c0.c0; if (J & 1) fp2_conj(a, a); r.c0.c0 = a;
 #define B2K_BN_FROB_SLOT(K, slot)                                 \
   B2K_BN_COEF_SEL(K, g);                                          \
@@ -169,11 +229,12 @@ B2K_NI void bn254_frobenius(NFp12& r, const NFp12& f) {
 #undef B2K_BN_COEF_SEL
 }
 
-B2K_D void bn_fp4_sqr(NFp2& c0, NFp2& c1, const NFp2& a, const NFp2& b) {
-  NFp2 t0, t1, t2;
+template <class PC>
+B2K_D void bn_fp4_sqr(PFp2<PC>& c0, PFp2<PC>& c1, const PFp2<PC>& a, const PFp2<PC>& b) {
+  PFp2<PC> t0, t1, t2;
   fp2_sqr(t0, a);
   fp2_sqr(t1, b);
-  NT::mul_xi(t2, t1);
+  PC::T::mul_xi(t2, t1);
   fp2_add(c0, t2, t0);
   fp2_add(t2, a, b);
   fp2_sqr(t2, t2);
@@ -182,54 +243,57 @@ B2K_D void bn_fp4_sqr(NFp2& c0, NFp2& c1, const NFp2& a, const NFp2& b) {
 }
 
 // Granger-Scott squaring in the cyclotomic subgroup (same slot assignment as pairing.cuh)
-B2K_NI void bn254_cyclotomic_sqr(NFp12& r, const NFp12& f) {
-  NFp2 z0 = f.c0.c0, z4 = f.c0.c1, z3 = f.c0.c2, z2 = f.c1.c0, z1 = f.c1.c1, z5 = f.c1.c2;
-  NFp2 t0, t1, t2, t3;
-  bn_fp4_sqr(t0, t1, z0, z1);
+template <class PC>
+B2K_NI void bn_cyclotomic_sqr(PFp12<PC>& r, const PFp12<PC>& f) {
+  PFp2<PC> z0 = f.c0.c0, z4 = f.c0.c1, z3 = f.c0.c2, z2 = f.c1.c0, z1 = f.c1.c1, z5 = f.c1.c2;
+  PFp2<PC> t0, t1, t2, t3;
+  bn_fp4_sqr<PC>(t0, t1, z0, z1);
   fp2_sub(z0, t0, z0); fp2_dbl(z0, z0); fp2_add(z0, z0, t0);
   fp2_add(z1, t1, z1); fp2_dbl(z1, z1); fp2_add(z1, z1, t1);
-  bn_fp4_sqr(t0, t1, z2, z3);
-  bn_fp4_sqr(t2, t3, z4, z5);
+  bn_fp4_sqr<PC>(t0, t1, z2, z3);
+  bn_fp4_sqr<PC>(t2, t3, z4, z5);
   fp2_sub(z4, t0, z4); fp2_dbl(z4, z4); fp2_add(z4, z4, t0);
   fp2_add(z5, t1, z5); fp2_dbl(z5, z5); fp2_add(z5, z5, t1);
-  NT::mul_xi(t0, t3);
+  PC::T::mul_xi(t0, t3);
   fp2_add(z2, t0, z2); fp2_dbl(z2, z2); fp2_add(z2, z2, t0);
   fp2_sub(z3, t2, z3); fp2_dbl(z3, z3); fp2_add(z3, z3, t2);
   r.c0.c0 = z0; r.c0.c1 = z4; r.c0.c2 = z3;
   r.c1.c0 = z2; r.c1.c1 = z1; r.c1.c2 = z5;
 }
 
-B2K_NI void bn254_pow_u(NFp12& r, const NFp12& a) {
-  NFp12 acc = a;
-  for (int b = 61; b >= 0; b--) {            // u has 63 bits, top bit consumed by acc = a
-    bn254_cyclotomic_sqr(acc, acc);
-    if ((BN254_U >> b) & 1) fp12_mul(acc, acc, a);
+template <class PC>
+B2K_NI void bn_pow_u(PFp12<PC>& r, const PFp12<PC>& a) {
+  PFp12<PC> acc = a;
+  for (int b = 61; b >= 0; b--) {            // u has 63 bits (both curves), top bit consumed by acc = a
+    bn_cyclotomic_sqr<PC>(acc, acc);
+    if ((PC::U >> b) & 1) fp12_mul(acc, acc, a);
   }
   r = acc;
 }
 
 // easy part (p^6-1)(p^2+1), then the hard part  y0 y1^2 y2^6 y3^12 y4^18 y5^30 y6^36  (optate.go:212-261)
-B2K_D void bn254_final_exponentiation(NFp12& r, const NFp12& in) {
-  NFp12 t0, t1, fp1, fp2v, fp3, fu, fu2, fu3, y0, y2, y3, y4, y6, tmp;
+template <class PC>
+B2K_D void bn_final_exponentiation(PFp12<PC>& r, const PFp12<PC>& in) {
+  PFp12<PC> t0, t1, fp1, fp2v, fp3, fu, fu2, fu3, y0, y2, y3, y4, y6, tmp;
   fp12_inv(t0, in);
   fp12_conj(t1, in);
   fp12_mul(t1, t1, t0);
-  bn254_frobenius<2>(t0, t1);
+  bn_frobenius<PC, 2>(t0, t1);
   fp12_mul(t1, t1, t0);                               // t1 = f^((p^6-1)(p^2+1))
-  bn254_frobenius<1>(fp1, t1);
-  bn254_frobenius<2>(fp2v, t1);
-  bn254_frobenius<1>(fp3, fp2v);
-  bn254_pow_u(fu, t1);
-  bn254_pow_u(fu2, fu);
-  bn254_pow_u(fu3, fu2);
-  bn254_frobenius<1>(y3, fu);   fp12_conj(y3, y3);
-  bn254_frobenius<1>(tmp, fu2); fp12_mul(y4, fu, tmp); fp12_conj(y4, y4);
-  bn254_frobenius<1>(tmp, fu3); fp12_mul(y6, fu3, tmp); fp12_conj(y6, y6);
-  bn254_frobenius<2>(y2, fu2);
+  bn_frobenius<PC, 1>(fp1, t1);
+  bn_frobenius<PC, 2>(fp2v, t1);
+  bn_frobenius<PC, 1>(fp3, fp2v);
+  bn_pow_u<PC>(fu, t1);
+  bn_pow_u<PC>(fu2, fu);
+  bn_pow_u<PC>(fu3, fu2);
+  bn_frobenius<PC, 1>(y3, fu);   fp12_conj(y3, y3);
+  bn_frobenius<PC, 1>(tmp, fu2); fp12_mul(y4, fu, tmp); fp12_conj(y4, y4);
+  bn_frobenius<PC, 1>(tmp, fu3); fp12_mul(y6, fu3, tmp); fp12_conj(y6, y6);
+  bn_frobenius<PC, 2>(y2, fu2);
   fp12_mul(y0, fp1, fp2v); fp12_mul(y0, y0, fp3);
   // y1 = conj(t1), y5 = conj(fu2)
   fp12_sqr(t0, y6); fp12_mul(t0, t0, y4); fp12_conj(tmp, fu2); fp12_mul(t0, t0, tmp);      // t0 = y6^2 y4 y5
-  NFp12 s;
+  PFp12<PC> s;
   fp12_mul(s, y3, tmp); fp12_mul(s, s, t0);                                                // s = y3 y5 t0
   fp12_mul(t0, t0, y2);
   fp12_sqr(s, s); fp12_mul(s, s, t0); fp12_sqr(s, s);
@@ -240,26 +304,24 @@ B2K_D void bn254_final_exponentiation(NFp12& r, const NFp12& in) {
   fp12_mul(r, t0, s);
 }
 
-// ---- codecs --------------------------------------------------------------------------------------------------
-B2K_D void bn254_g1_load(Affine<NFp>& r, const uint8_t* p) {          // x||y, 32-byte big-endian each
-  NFp t;
-  fp_load_be(t, p); fp_to_mont(r.x, t);
-  fp_load_be(t, p + 32); fp_to_mont(r.y, t);
+// ---- codecs (32-byte big-endian field elements; G2 imaginary part first; GT 384 B highest coefficient first) ------
+template <class PC>
+B2K_D void bn_g1_load(Affine<PFp<PC>>& r, const uint8_t* p) { PC::load32(r.x, p); PC::load32(r.y, p + 32); }
+template <class PC>
+B2K_D void bn_g2_load(Affine<PFp2<PC>>& r, const uint8_t* p) {
+  PC::load32(r.x.c1, p); PC::load32(r.x.c0, p + 32); PC::load32(r.y.c1, p + 64); PC::load32(r.y.c0, p + 96);
 }
-B2K_D void bn254_g2_load(Affine<NFp2>& r, const uint8_t* p) {         // x.imag||x.real||y.imag||y.real
-  NFp t;
-  fp_load_be(t, p); fp_to_mont(r.x.c1, t);
-  fp_load_be(t, p + 32); fp_to_mont(r.x.c0, t);
-  fp_load_be(t, p + 64); fp_to_mont(r.y.c1, t);
-  fp_load_be(t, p + 96); fp_to_mont(r.y.c0, t);
+template <class PC>
+B2K_D void bn_gt_store(uint8_t* out, const PFp12<PC>& f) {
+  const PFp2<PC>* order[6] = {&f.c1.c2, &f.c1.c1, &f.c1.c0, &f.c0.c2, &f.c0.c1, &f.c0.c0};
+  for (int i = 0; i < 6; i++) { PC::store32(out + 64 * i, order[i]->c1); PC::store32(out + 64 * i + 32, order[i]->c0); }
 }
-B2K_D void bn254_gt_store(uint8_t* out, const NFp12& f) {             // 384 B, highest coefficient first
-  const NFp2* order[6] = {&f.c1.c2, &f.c1.c1, &f.c1.c0, &f.c0.c2, &f.c0.c1, &f.c0.c0};
-  for (int i = 0; i < 6; i++) {
-    NFp t;
-    fp_from_mont(t, order[i]->c1); fp_store_be(out + 64 * i, t);
-    fp_from_mont(t, order[i]->c0); fp_store_be(out + 64 * i + 32, t);
-  }
-}
+
+// bn254 names kept for the existing call sites
+template <int NPAIRS> B2K_D void bn254_miller_loop(NFp12& f, const Affine<NFp>* P, const Affine<NFp2>* Q) { bn_miller_loop<Bn254Pair, NPAIRS>(f, P, Q); }
+B2K_D void bn254_final_exponentiation(NFp12& r, const NFp12& in) { bn_final_exponentiation<Bn254Pair>(r, in); }
+B2K_D void bn254_g1_load(Affine<NFp>& r, const uint8_t* p) { bn_g1_load<Bn254Pair>(r, p); }
+B2K_D void bn254_g2_load(Affine<NFp2>& r, const uint8_t* p) { bn_g2_load<Bn254Pair>(r, p); }
+B2K_D void bn254_gt_store(uint8_t* out, const NFp12& f) { bn_gt_store<Bn254Pair>(out, f); }
 
 }  // namespace b2k

@@ -22,3 +22,14 @@ int emul_bn254_pairing_check(const uint8_t* a1, const uint8_t* a2, const uint8_t
   return fp12_is_one(e) ? 1 : 0;
 }
 }
+
+extern "C" void emul_bn256_pair(const uint8_t* g1, const uint8_t* g2, uint8_t* gt384) {
+  using PC = Bn256Pair;
+  Affine<PFp<PC>> P; Affine<PFp2<PC>> Q;
+  bn_g1_load<PC>(P, g1); bn_g2_load<PC>(Q, g2);
+  PFp12<PC> f, e;
+  bn_miller_loop<PC, 1>(f, &P, &Q);
+  bn_final_exponentiation<PC>(e, f);
+  if (aff_is_inf(P) || aff_is_inf(Q)) fp12_set_one(e);
+  bn_gt_store<PC>(gt384, e);
+}

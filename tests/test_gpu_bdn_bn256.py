@@ -53,3 +53,21 @@ def test_hash_point_to_r_reference_vector(engine):
     coefs = bdn.hash_point_to_r(pub_bytes, o.ORDER)
     assert ["%x" % c for c in coefs] == f["coefs"]
     assert engine.bn256_g2_msm(_sc([c + 1 for c in coefs]), pubs).hex() == f["agg_key"]
+
+
+def test_bn256_pairing_and_full_bdn_verification(engine):
+    """bn256 pairing on the device: GT bytes vs the restatement of pairing/bn256/optate.go, then the whole BDN flow of
+    the fixtures: every signature verifies (bls.Verify: e(H(m), X) == e(sig, G2 base), sign/bls/bls.go:36-38,82-96) and
+    so does the aggregate signature under the aggregate key."""
+    from oracle import bn256_pairing as bp
+    f = FX["fixtures"]
+    gt = engine.bn256_pair(o.g1_marshal(o.G1) + o.g1_marshal(o.g1_mul(7)), o.g2_marshal(o.G2) + o.g2_marshal(o.g2_mul(11)))
+    assert gt[:384] == bp.gt_to_bytes(bp.pairing(o.G1, o.G2))
+    assert gt[384:] == bp.gt_to_bytes(bp.pairing(o.g1_mul(7), o.g2_mul(11)))
+    hm = o.g1_marshal(o.hash_to_g1(f["msg"].encode()))
+    base2 = o.g2_marshal(o.G2)
+    sigs = [bytes.fromhex(x) for x in f["sig"]] + [bytes.fromhex(f["agg_sig"]), bytes.fromhex(f["sig"][0])]
+    keys = [bytes.fromhex(x) for x in f["public"]] + [bytes.fromhex(f["agg_key"]), bytes.fromhex(f["public"][1])]
+    n = len(sigs)
+    ok = engine.bn256_pairing_check(hm * n, b"".join(keys), b"".join(sigs), base2 * n)
+    assert list(ok) == [1, 1, 1, 1, 0]          # three signatures, the aggregate, and a signature under the wrong key

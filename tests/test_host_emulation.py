@@ -143,6 +143,13 @@ def test_bn254_pairing_bodies():
     x, y = rng.randrange(c.ORDER), rng.randrange(c.ORDER)
     args = [c.g1_marshal(c.g1_mul(x)), b.g2_marshal(b.g2_mul(y)), c.g1_marshal(c.g1_mul(x * y % c.ORDER)), b.g2_marshal(b.G2)]
     assert lib.emul_bn254_pairing_check(*args) == 1
+    # bn256 twin (pairing/bn256/optate.go): same templates, xi = i+3, 10-limb field, its own digit table
+    from oracle import bn256 as c6, bn256_pairing as b6
+    for x, y in ((1, 1), (rng.randrange(c6.ORDER), rng.randrange(c6.ORDER))):
+        P, Q = c6.g1_mul(x), b6.g2_mul(y)
+        out = ctypes.create_string_buffer(384)
+        lib.emul_bn256_pair(c6.g1_marshal(P), c6.g2_marshal(Q), out)
+        assert out.raw == b6.gt_to_bytes(b6.pairing(P, Q))
 
 
 def test_ed25519_and_inversion_bodies():
