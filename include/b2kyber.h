@@ -170,9 +170,9 @@ int b2k_bls12381_verify_g2sig_dev(b2k_ctx* ctx, size_t n, const void* d_pks, con
 
 /* ---- BLS12-381 pairings ---------------------------------------------------------------------------- */
 /* gt[i] = e(g1[i], g2[i]); g2 operands are 192 B: x.c1||x.c0||y.c1||y.c0.  GT = 576 B, 12 x 48 B
- * big-endian, highest tower coefficient first (kilic/gt.go:115-117), exponent exactly (p^12-1)/r.
- * An infinity operand gives the GT identity.   replaces: kilic.Suite.Pair, kilic/suite.go:70-75
- * NOTE: GT byte parity with the Go back-ends is UNPINNED (the reference has no GT byte fixture). */
+ * big-endian, highest tower coefficient first (kilic/gt.go:115-117), final exponent 3 (p^12-1)/r as in the
+ * reference's back-ends.  An infinity operand gives the GT identity.   replaces: kilic.Suite.Pair, kilic/suite.go:70-75
+ * Byte order and exponent are pinned by the reference vector encrypt/ibe/ibe_test.go:202-245 (see tests/). */
 int b2k_bls12381_pair(b2k_ctx* ctx, size_t n, const uint8_t* g1 /*[n][96]*/, const uint8_t* g2 /*[n][192]*/,
                       uint8_t* gt /*[n][576]*/);
 int b2k_bls12381_pair_dev(b2k_ctx* ctx, size_t n, const void* d_g1, const void* d_g2, void* d_gt);

@@ -1,5 +1,5 @@
 // pairing.cuh -- BLS12-381 optimal-ate pairing: Miller loop over |x| with inversion-free line
-// functions, final exponentiation with exponent exactly (p^12-1)/r, GT codec.
+// functions, final exponentiation (exponent 3 (p^12-1)/r, the convention of the reference back-ends), GT codec.
 //
 // Replaces (reference call sites; the arithmetic itself is third-party in the reference):
 //   kilic.Suite.Pair             pairing/bls12381/kilic/suite.go:70-75   (Engine.AddPair + Result)
@@ -205,30 +205,50 @@ B2K_NI void fp12_pow_u64(BFp12& r, const BFp12& a, uint64_t e) {
   r = acc;
 }
 
-// f^((p^12-1)/r), exponent EXACT (GT bytes are defined by it):
-//   easy part  m = f^((p^6-1)(p^2+1))
-//   hard part  (p^4-p^2+1)/r = l0 + l1 p + l2 p^2 + l3 p^3,  l3 = (x-1)^2/3, l2 = l3 x, l1 = l2 x - l3,
-//              l0 = l1 x + 1   (x = -BLS_X_ABS; inverses in the cyclotomic subgroup are conjugates)
+// Final exponentiation.  GT convention = the one every BLS12-381 back-end of the reference shares and the
+// reference's only GT-dependent vector pins (encrypt/ibe/ibe_test.go:202-245, decrypts only with this value and
+// the byte order of gt_store): exponent 3 (p^12-1)/r, i.e. the standard pairing cubed.  With
+//   3 (p^4-p^2+1)/r = (x-1)^2 (x+p) (x^2+p^2-1) + 3
+// the hard part is five exponentiations by |x| (x < 0: inverses in the cyclotomic subgroup are conjugates).
+B2K_D void fp12_pow_x(BFp12& r, const BFp12& a) {        // a^x, x = -|x|
+  fp12_pow_u64(r, a, BLS_X_ABS);
+  fp12_conj(r, r);
+}
+
 B2K_D void final_exponentiation(BFp12& r, const BFp12& f) {
-  BFp12 m, t, y3, y2, y1, y0;
+  BFp12 m, t, a, b, c;
   fp12_inv(t, f);
   fp12_conj(m, f);
   fp12_mul(m, m, t);                      // f^(p^6-1)
   fp12_frobenius<2>(t, m);
   fp12_mul(m, t, m);                      // ^(p^2+1)
-  // y3 = m^(e3 (|x|+1))
+  fp12_pow_x(b, m); fp12_conj(t, m); fp12_mul(b, b, t);              // b = m^(x-1)
+  fp12_pow_x(a, b); fp12_conj(t, b); fp12_mul(a, a, t);              // a = m^((x-1)^2)
+  fp12_pow_x(c, a); fp12_frobenius<1>(t, a); fp12_mul(c, c, t);      // c = a^(x+p)
+  fp12_pow_x(b, c); fp12_pow_x(a, b);                                // a = c^(x^2)
+  fp12_frobenius<2>(t, c); fp12_mul(a, a, t);
+  fp12_conj(t, c); fp12_mul(a, a, t);                                // a = c^(x^2+p^2-1)
+  fp12_cyclotomic_sqr(t, m); fp12_mul(t, t, m);                      // m^3
+  fp12_mul(r, a, t);
+}
+
+// The same with the plain exponent (p^12-1)/r (kept for cross-checks: final_exponentiation == this cubed).
+//   hard part  (p^4-p^2+1)/r = l0 + l1 p + l2 p^2 + l3 p^3,  l3 = (x-1)^2/3, l2 = l3 x, l1 = l2 x - l3, l0 = l1 x + 1
+B2K_D void final_exponentiation_exact(BFp12& r, const BFp12& f) {
+  BFp12 m, t, y3, y2, y1, y0;
+  fp12_inv(t, f);
+  fp12_conj(m, f);
+  fp12_mul(m, m, t);
+  fp12_frobenius<2>(t, m);
+  fp12_mul(m, t, m);
   fp12_pow_u64(t, m, BLS_E3);
   fp12_pow_u64(y3, t, BLS_X_ABS);
   fp12_mul(y3, y3, t);
-  // y2 = y3^x
   fp12_pow_u64(y2, y3, BLS_X_ABS); fp12_conj(y2, y2);
-  // y1 = y2^x * y3^-1
   fp12_pow_u64(y1, y2, BLS_X_ABS); fp12_conj(y1, y1);
   fp12_conj(t, y3); fp12_mul(y1, y1, t);
-  // y0 = y1^x * m
   fp12_pow_u64(y0, y1, BLS_X_ABS); fp12_conj(y0, y0);
   fp12_mul(y0, y0, m);
-  // r = y0 * frob(y1) * frob2(y2) * frob3(y3)
   fp12_frobenius<1>(t, y1); fp12_mul(y0, y0, t);
   fp12_frobenius<2>(t, y2); fp12_mul(y0, y0, t);
   fp12_frobenius<3>(t, y3); fp12_mul(r, y0, t);
@@ -245,7 +265,8 @@ B2K_D void g2_load(Affine<BFp2>& r, const uint8_t* p) {
 }
 
 // GT, 576 B: 12 x 48 B big-endian, highest tower coefficient first (c1.c2.c1 ... c0.c0.c0),
-// the kilic layout (gt.go:115-117).  PARITY UNPINNED against the reference (no GT byte fixture).
+// the kilic layout (gt.go:115-117).  Layout AND exponent are pinned by the reference vector
+// encrypt/ibe/ibe_test.go:202-245 (reproduced in tests/).
 B2K_D void gt_store(uint8_t* out, const BFp12& f) {
   const BFp2* order[6] = {&f.c1.c2, &f.c1.c1, &f.c1.c0, &f.c0.c2, &f.c0.c1, &f.c0.c0};
   for (int i = 0; i < 6; i++) {

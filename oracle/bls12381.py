@@ -21,9 +21,10 @@ anchors on the reference's own call sites and fixtures:
 
 Parity status: G1/G2 bytes are pinned by the 36 ZCash deserialisation fixtures
 (pairing/bls12381/deserialization_tests) and by the drand KATs (kilic/suite_test.go:17-106,
-bls12381_test.go:877-904) -- see tests/test_oracle_bls12381.py.  GT BYTES: PARITY UNPINNED
-(SURVEY.md F7): no reference fixture records GT bytes; we use exponent exactly (p^12-1)/r and the
-kilic byte order (highest tower coefficient first) from the public library layout.
+bls12381_test.go:877-904) -- see tests/test_oracle_bls12381.py.  GT BYTES: pinned by the one vector of the
+reference that depends on them, encrypt/ibe/ibe_test.go:202-245 (skipped in-tree, but self-validating: the
+ciphertext decrypts to deadbeef... only with pairing_reference = exponent 3(p^12-1)/r and the kilic byte order,
+highest tower coefficient first).
 """
 from __future__ import annotations
 
@@ -494,8 +495,30 @@ def final_exponentiation(f):
 
 
 def pairing(p1, q2):
-    """e(P, Q), P in G1, Q in G2 -- Suite.Pair (kilic/suite.go:70-75)."""
+    """The textbook optimal-ate pairing e(P, Q) with exponent exactly (p^12-1)/r (algebraic tests use this)."""
     return final_exponentiation(miller_loop(p1, q2))
+
+
+def final_exponentiation_cubed(f):
+    """f^(3 (p^12-1)/r) via 3(p^4-p^2+1)/r = (x-1)^2 (x+p)(x^2+p^2-1) + 3 (x = -X_ABS)."""
+    m = f12_mul(f12_conj(f), f12_inv(f))
+    m = f12_mul(f12_frobenius(m, 2), m)
+
+    def powx(a):
+        return f12_conj(f12_pow(a, X_ABS))
+    b = f12_mul(powx(m), f12_conj(m))
+    a = f12_mul(powx(b), f12_conj(b))
+    c = f12_mul(powx(a), f12_frobenius(a, 1))
+    d = f12_mul(f12_mul(powx(powx(c)), f12_frobenius(c, 2)), f12_conj(c))
+    return f12_mul(d, f12_mul(f12_sqr(m), m))
+
+
+def pairing_reference(p1, q2):
+    """Suite.Pair as the reference's BLS12-381 back-ends compute it (kilic/suite.go:70-75, circl/suite.go:27-30):
+    the pairing with exponent 3 (p^12-1)/r, i.e. pairing(P,Q)^3.  This convention -- and the byte order of
+    gt_to_bytes -- is PINNED by the reference's only GT-dependent vector, encrypt/ibe/ibe_test.go:202-245
+    (TestBackwardsInteropWithTypescript; skipped in-tree but self-validating): see tests/test_oracle_bls12381.py."""
+    return final_exponentiation_cubed(miller_loop(p1, q2))
 
 
 def validate_pairing(p1, p2, inv1, inv2) -> bool:
@@ -508,7 +531,7 @@ def validate_pairing(p1, p2, inv1, inv2) -> bool:
 def gt_to_bytes(f) -> bytes:
     """576 B = 12 x 48 B big-endian, highest tower coefficient first:
     c1.c2.c1, c1.c2.c0, c1.c1.c1, ..., c0.c0.c1, c0.c0.c0   (kilic fp12 toBytes order).
-    PARITY UNPINNED against the reference (no fixture holds GT bytes)."""
+    Pinned (together with the cubed exponent of pairing_reference) by the IBE vector of the reference."""
     out = b""
     for c6 in (f[1], f[0]):
         for c2 in (c6[2], c6[1], c6[0]):

@@ -527,18 +527,21 @@ static void fp12_pow_u64(fp12* r, const fp12* a, uint64_t e) {
   *r = acc;
 }
 #define X_ABS 0xd201000000010000ULL
-#define E3 0x460055555555aaabULL
+static void fp12_pow_x(fp12* r, const fp12* a) { fp12_pow_u64(r, a, X_ABS); fp12_conj(r, r); }   /* a^x, x < 0 */
+/* exponent 3 (p^12-1)/r, the GT convention of the reference back-ends (pinned by encrypt/ibe/ibe_test.go:202-245,
+ * see oracle/bls12381.py pairing_reference): hard part (x-1)^2 (x+p) (x^2+p^2-1) + 3 */
 static void final_exp(fp12* r, const fp12* f) {
-  fp12 m, t, y3, y2, y1, y0;
+  fp12 m, t, a, b, c;
   fp12_inv(&t, f); fp12_conj(&m, f); fp12_mul(&m, &m, &t);
   fp12_frob(&t, &m); fp12_frob(&t, &t); fp12_mul(&m, &t, &m);
-  fp12_pow_u64(&t, &m, E3); fp12_pow_u64(&y3, &t, X_ABS); fp12_mul(&y3, &y3, &t);
-  fp12_pow_u64(&y2, &y3, X_ABS); fp12_conj(&y2, &y2);
-  fp12_pow_u64(&y1, &y2, X_ABS); fp12_conj(&y1, &y1); fp12_conj(&t, &y3); fp12_mul(&y1, &y1, &t);
-  fp12_pow_u64(&y0, &y1, X_ABS); fp12_conj(&y0, &y0); fp12_mul(&y0, &y0, &m);
-  fp12_frob(&t, &y1); fp12_mul(&y0, &y0, &t);
-  fp12_frob(&t, &y2); fp12_frob(&t, &t); fp12_mul(&y0, &y0, &t);
-  fp12_frob(&t, &y3); fp12_frob(&t, &t); fp12_frob(&t, &t); fp12_mul(r, &y0, &t);
+  fp12_pow_x(&b, &m); fp12_conj(&t, &m); fp12_mul(&b, &b, &t);
+  fp12_pow_x(&a, &b); fp12_conj(&t, &b); fp12_mul(&a, &a, &t);
+  fp12_pow_x(&c, &a); fp12_frob(&t, &a); fp12_mul(&c, &c, &t);
+  fp12_pow_x(&b, &c); fp12_pow_x(&a, &b);
+  fp12_frob(&t, &c); fp12_frob(&t, &t); fp12_mul(&a, &a, &t);
+  fp12_conj(&t, &c); fp12_mul(&a, &a, &t);
+  fp12_sqr(&t, &m); fp12_mul(&t, &t, &m);
+  fp12_mul(r, &a, &t);
 }
 typedef struct { fp2 X, Y, Z; } jac2;
 typedef struct { fp2 x, y; int inf; } aff2;

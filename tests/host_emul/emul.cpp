@@ -121,6 +121,20 @@ void emul_bls12381_pair(const uint8_t* g1, const uint8_t* g2, uint8_t* gt576) {
   final_exponentiation(e, f);
   gt_store(gt576, e);
 }
+// final_exponentiation (exponent 3(p^12-1)/r) == final_exponentiation_exact cubed, on a Miller-loop output
+int emul_bls12381_final_exp_is_exact_cubed(const uint8_t* g1, const uint8_t* g2) {
+  Affine<BFp> P; Affine<BFp2> Q;
+  Bls381G1::load(P, g1); g2_load(Q, g2);
+  BFp12 f, e, x, x3;
+  miller_loop<1>(f, &P, &Q);
+  final_exponentiation(e, f);
+  final_exponentiation_exact(x, f);
+  fp12_sqr(x3, x); fp12_mul(x3, x3, x);
+  uint8_t a[576], b[576];
+  gt_store(a, e); gt_store(b, x3);
+  for (int i = 0; i < 576; i++) if (a[i] != b[i]) return 0;
+  return 1;
+}
 // e(a1,a2) == e(b1,b2)
 int emul_bls12381_pairing_check(const uint8_t* a1, const uint8_t* a2, const uint8_t* b1, const uint8_t* b2) {
   Affine<BFp> P[2]; Affine<BFp2> Q[2];

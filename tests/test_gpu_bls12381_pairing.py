@@ -1,5 +1,5 @@
-"""GPU parity: BLS12-381 pairings through the C ABI vs the Python oracle (GT bytes with the exact
-exponent, pairing-equation booleans).  Mirrors the reference's pairing property tests
+"""GPU parity: BLS12-381 pairings through the C ABI vs the Python oracle (GT bytes in the reference's
+convention -- exponent 3(p^12-1)/r, pinned by its IBE vector --, pairing-equation booleans).  Mirrors the reference's pairing property tests
 (pairing/bls12381/bls12381_test.go:448-474 bilinearity, :580-631 product identity) and
 Suite.ValidatePairing semantics (kilic/suite.go:57-68)."""
 import random
@@ -22,7 +22,26 @@ def test_pair_gt_bytes_match_oracle(engine):
     g2 = b"".join(o.g2_to_affine_bytes(q) for _, q in pairs)
     gt = engine.bls12381_pair(g1, g2)
     for i, (p, q) in enumerate(pairs):
-        assert gt[576 * i:576 * (i + 1)] == o.gt_to_bytes(o.pairing(p, q)), i
+        assert gt[576 * i:576 * (i + 1)] == o.gt_to_bytes(o.pairing_reference(p, q)), i
+
+
+def test_reference_ibe_vector_decrypts_with_device_gt_bytes(engine):
+    """encrypt/ibe/ibe_test.go:202-245: the reference's one GT-byte-dependent vector, with decompression (device),
+    the pairing (device) and GT.MarshalBinary (device) all on the product path; only SHA-256/xor on the host
+    (ibe.go:98-134 DecryptCCAonG1 steps 1-2)."""
+    import hashlib
+    beacon = bytes.fromhex(
+        "86ecea71376e78abd19aaf0ad52f462a6483626563b1023bd04815a7b953da888c74f5bf6ee672a5688603ab310026230522898f33f23a7de363c66f90ffd49e"
+        "c77ebf7f6c1478a9ecd6e714b4d532ab43d044da0a16fed13b4791d7fc999e2b")
+    U = bytes.fromhex("a5ddec5fa76795d5a28f0869e6a620248c94c112beb8135b11d5614a2b6845c5a4128e3dfe4328d7a6e70b2dea3d7f25")
+    V, W = bytes.fromhex("89f0e6cf2b27371017dddeff43ab2263"), bytes.fromhex("d767e14f5e3e1738a6c50725c4f0d1b6")
+    g1, ok1 = engine.bls12381_g1_decompress(U)
+    g2, ok2 = engine.bls12381_g2_decompress(beacon)
+    assert ok1 == b"\x01" and ok2 == b"\x01"
+    gt = engine.bls12381_pair(g1, g2)
+    sigma = bytes(a ^ b for a, b in zip(hashlib.sha256(b"IBE-H2" + gt).digest()[:16], V))
+    msg = bytes(a ^ b for a, b in zip(hashlib.sha256(b"IBE-H4" + sigma).digest()[:16], W))
+    assert msg.hex() == "deadbeef" * 4
 
 
 def test_pairing_bilinearity_on_device(engine):
