@@ -255,6 +255,17 @@ int b2k_ed25519_mul_batch(b2k_ctx* ctx, size_t n, const uint8_t* scalars /*[n][3
                           const uint8_t* points /*[n][32]*/, uint8_t* out /*[n][32]*/);
 int b2k_ed25519_mul_batch_dev(b2k_ctx* ctx, size_t n, const void* d_scalars, const void* d_points, void* d_out);
 
+/* ---- sign/bdn: rogue-key coefficients (HOST function: no context, no device work) ------------------------- */
+/* out[i] = c_i (+1 if add_one) as a 32-byte big-endian scalar, where c_0..c_{n-1} are the first 16 n bytes of
+ * BLAKE2Xs (unkeyed, output length unknown) over pubs[0] || ... || pubs[n-1], 16 bytes per key read little-endian
+ * (= reversed + SetBytes on the big-endian mod.Int of every pairing suite).  c_i < 2^128 < group order: no reduction.
+ * replaces: bdn.hashPointToR, sign/bdn/bdn.go:29-63; with add_one = 1 the factors (c_i + 1) of the loops
+ * bdn.AggregateSignatures (bdn.go:126-161) and NewMask (mask.go:57-61), whose sums are the *_msm entry points above
+ * applied to (factors, signatures) / (factors, public keys) of the enabled participants.
+ * The absorb phase is one sequential hash chain, so it runs on the host exactly as in the reference. */
+int b2k_bdn_coefficients(size_t n, const uint8_t* pubs /*[n][pub_len] MarshalBinary bytes*/, size_t pub_len, int add_one,
+                         uint8_t* out /*[n][32] BE*/);
+
 #ifdef __cplusplus
 }
 #endif

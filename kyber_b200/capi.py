@@ -306,6 +306,21 @@ class Engine:
         self._check(self.lib.b2k_bn256_pairing_check(self.h, n, *[b[0] for b in bufs]))
         return bytes(out)
 
+    @staticmethod
+    def bdn_coefficients(pubs: bytes, pub_len: int, add_one: bool = False) -> bytes:
+        """sign/bdn hashPointToR (bdn.go:29-63) over the marshalled public keys -> n x 32-byte big-endian c_i (+1).
+        Host function of the library (no device work); static: needs no context."""
+        lib = load_library()
+        n = len(pubs) // pub_len
+        assert len(pubs) == n * pub_len
+        out = C.create_string_buffer(32 * n)
+        lib.b2k_bdn_coefficients.restype = C.c_int
+        lib.b2k_bdn_coefficients.argtypes = [C.c_size_t, C.c_char_p, C.c_size_t, C.c_int, C.c_char_p]
+        rc = lib.b2k_bdn_coefficients(n, pubs, pub_len, 1 if add_one else 0, out)
+        if rc != 0:
+            raise ValueError("b2k_bdn_coefficients: rc=%d" % rc)
+        return out.raw
+
     def ed25519_mul_batch(self, scalars_le: bytes, points: bytes) -> bytes:
         """n x edwards25519 Point.Mul: raw little-endian 32-byte scalars, 32-byte compressed points -> 32 B each"""
         n = len(scalars_le) // 32

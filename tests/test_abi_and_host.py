@@ -111,3 +111,32 @@ def test_device_msm_bodies_under_host_emulation(emul):
         o48 = ctypes.create_string_buffer(48)
         assert emul.emul_bls12381_g1_msm(ctypes.c_size_t(n), sb, pb, c, m, o48) == 0
         assert o48.raw == exp, (c, m)
+
+
+def test_bdn_coefficients_host_function_matches_reference_vector_and_oracle():
+    """b2k_bdn_coefficients (host C++ BLAKE2Xs in the library) == the reference vector of
+    sign/bdn/bdn_vartime_test.go:24-48 (coefficients for G2 base, 2*base, 3*base on bn256) == the oracle, incl. ragged
+    sizes around the 64-byte block and 32-byte squeeze boundaries and the multi-threaded squeeze."""
+    import json
+    import random
+    from kyber_b200.capi import Engine
+    from oracle import bdn, bn256 as o
+    fx = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "bdn_bn256_fixtures.json")))["hash_point_to_r"]
+    pubs = b"".join(o.g2_marshal(o.g2_mul(k)) for k in (1, 2, 3))
+    got = Engine.bdn_coefficients(pubs, 128)
+    assert [got[32 * i:32 * i + 32].hex().lstrip("0") for i in range(3)] == [c.lstrip("0") for c in fx["coefs"]]
+    plus = Engine.bdn_coefficients(pubs, 128, add_one=True)
+    assert [int.from_bytes(plus[32 * i:32 * i + 32], "big") for i in range(3)] == [int(c, 16) + 1 for c in fx["coefs"]]
+    rng = random.Random(5)
+    for n, plen in ((0, 48), (1, 1), (1, 64), (2, 32), (3, 48), (5, 96), (9000, 48)):
+        blob = bytes(rng.getrandbits(8) for _ in range(n * plen))
+        want = bdn.hash_point_to_r([blob[plen * i:plen * (i + 1)] for i in range(n)], 1 << 255) if n < 100 else None
+        got = Engine.bdn_coefficients(blob, plen)
+        assert len(got) == 32 * n
+        if want is not None:
+            assert [int.from_bytes(got[32 * i:32 * i + 32], "big") for i in range(n)] == want
+        else:      # large n: threaded squeeze == the stream prefix property (first coefficients do not depend on n's parity)
+            stream = bdn.blake2xs(blob, 16 * 64)
+            assert [got[32 * i + 16:32 * i + 32][::-1] for i in range(64)] == [stream[16 * i:16 * i + 16] for i in range(64)]
+            tail = bdn.blake2xs(blob, 16 * n)[-16:]
+            assert got[-16:][::-1] == tail

@@ -30,9 +30,11 @@ def test_signatures_are_the_fixture_bytes(engine):
 def test_aggregate_signature_and_key_are_the_fixture_bytes(engine):
     f = FX["fixtures"]
     pub_bytes = [bytes.fromhex(x) for x in f["public"]]
-    coefs = bdn.hash_point_to_r(pub_bytes, o.ORDER)           # host-side, as in Go
+    coefs = bdn.hash_point_to_r(pub_bytes, o.ORDER)           # oracle (checker)
     en = f["mask_enabled"]
-    scal = _sc([coefs[i] + 1 for i in en])                    # c_i * S_i + S_i = (c_i + 1) * S_i
+    fac = engine.bdn_coefficients(b"".join(pub_bytes), 128, add_one=True)   # product: host BLAKE2Xs inside the library
+    scal = b"".join(fac[32 * i:32 * i + 32] for i in en)      # c_i * S_i + S_i = (c_i + 1) * S_i
+    assert scal == _sc([coefs[i] + 1 for i in en])
     sigs = b"".join(bytes.fromhex(f["sig"][i]) for i in en)
     assert engine.bn256_g1_msm(scal, sigs).hex() == f["agg_sig"]
     keys = b"".join(pub_bytes[i] for i in en)
@@ -52,7 +54,8 @@ def test_hash_point_to_r_reference_vector(engine):
     pub_bytes = [pubs[128 * i:128 * i + 128] for i in range(3)]
     coefs = bdn.hash_point_to_r(pub_bytes, o.ORDER)
     assert ["%x" % c for c in coefs] == f["coefs"]
-    assert engine.bn256_g2_msm(_sc([c + 1 for c in coefs]), pubs).hex() == f["agg_key"]
+    assert engine.bdn_coefficients(pubs, 128) == _sc(coefs)
+    assert engine.bn256_g2_msm(engine.bdn_coefficients(pubs, 128, add_one=True), pubs).hex() == f["agg_key"]
 
 
 def test_bn256_pairing_and_full_bdn_verification(engine):
