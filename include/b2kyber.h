@@ -255,6 +255,21 @@ int b2k_ed25519_mul_batch(b2k_ctx* ctx, size_t n, const uint8_t* scalars /*[n][3
                           const uint8_t* points /*[n][32]*/, uint8_t* out /*[n][32]*/);
 int b2k_ed25519_mul_batch_dev(b2k_ctx* ctx, size_t n, const void* d_scalars, const void* d_points, void* d_out);
 
+/* ---- hash-to-G1 on the BN curves ------------------------------------------------------------------------- */
+/* out[i] = Hash(msg_i) as 64 bytes x||y; msgs/offsets as in b2k_bls12381_hash_to_g1 (offsets[n+1], msg_i =
+ * msgs[offsets[i] .. offsets[i+1])).
+ * bn254: expand_message_xmd(Keccak-256) -> 2 field elements -> Shallue-van de Woestijne map -> add; dst as given
+ *   (the suite default is "BN254G1_XMD:KECCAK-256_SVDW_RO_", pairing/bn254/suite.go:43).
+ *   replaces: pointG1.Hash / hashToPoint, pairing/bn254/point.go:208-285 (per message in bls.Sign/Verify on bn254)
+ * bn256: x = SHA-256(m) mod p, try-and-increment, y = (x^3+3)^((p+1)/4).
+ *   replaces: pointG1.Hash / hashToPoint, pairing/bn256/point.go:261-312 (per message in sign/bls, sign/bdn on bn256) */
+int b2k_bn254_hash_to_g1(b2k_ctx* ctx, size_t n, const uint8_t* msgs, const uint32_t* offsets, const uint8_t* dst,
+                         uint32_t dst_len, uint8_t* out /*[n][64]*/);
+int b2k_bn254_hash_to_g1_dev(b2k_ctx* ctx, size_t n, const void* d_msgs, const void* d_offsets, const void* d_dst,
+                             uint32_t dst_len, void* d_out);
+int b2k_bn256_hash_to_g1(b2k_ctx* ctx, size_t n, const uint8_t* msgs, const uint32_t* offsets, uint8_t* out /*[n][64]*/);
+int b2k_bn256_hash_to_g1_dev(b2k_ctx* ctx, size_t n, const void* d_msgs, const void* d_offsets, void* d_out);
+
 /* ---- sign/bdn: rogue-key coefficients (HOST function: no context, no device work) ------------------------- */
 /* out[i] = c_i (+1 if add_one) as a 32-byte big-endian scalar, where c_0..c_{n-1} are the first 16 n bytes of
  * BLAKE2Xs (unkeyed, output length unknown) over pubs[0] || ... || pubs[n-1], 16 bytes per key read little-endian

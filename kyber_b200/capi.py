@@ -233,6 +233,28 @@ class Engine:
         self._check(self.lib.b2k_bls12381_hash_to_g1(self.h, n, bufs[0][0], bufs[1][0], bufs[2][0], len(dst), bufs[3][0]))
         return bytes(out)
 
+    def bn254_hash_to_g1(self, msgs, dst: bytes = b"BN254G1_XMD:KECCAK-256_SVDW_RO_") -> bytes:
+        """bn254 pointG1.Hash (Keccak-256 XMD + SvdW) for a list of messages -> [n][64] x||y"""
+        n = len(msgs)
+        blob, offs = self._pack_msgs(msgs)
+        out = bytearray(64 * n)
+        bufs = [_buf(x) for x in (blob, offs, dst, out)]
+        self.lib.b2k_bn254_hash_to_g1.restype = C.c_int
+        self.lib.b2k_bn254_hash_to_g1.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
+        self._check(self.lib.b2k_bn254_hash_to_g1(self.h, n, bufs[0][0], bufs[1][0], bufs[2][0], len(dst), bufs[3][0]))
+        return bytes(out)
+
+    def bn256_hash_to_g1(self, msgs) -> bytes:
+        """bn256 pointG1.Hash (SHA-256 try-and-increment) for a list of messages -> [n][64] x||y"""
+        n = len(msgs)
+        blob, offs = self._pack_msgs(msgs)
+        out = bytearray(64 * n)
+        bufs = [_buf(x) for x in (blob, offs, out)]
+        self.lib.b2k_bn256_hash_to_g1.restype = C.c_int
+        self.lib.b2k_bn256_hash_to_g1.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]
+        self._check(self.lib.b2k_bn256_hash_to_g1(self.h, n, bufs[0][0], bufs[1][0], bufs[2][0]))
+        return bytes(out)
+
     def bls12381_hash_to_g2(self, msgs, dst: bytes) -> bytes:
         """msgs: list of bytes -> operand bytes [n][192]"""
         n = len(msgs)

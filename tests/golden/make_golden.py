@@ -9,6 +9,8 @@ Sources:
       driven in the reference by pairing/bls12381/bls12381_test.go:74-186)
   pairing/bls12381/kilic/suite_test.go:17-72                     (drand signature KATs)
   pairing/bls12381/bls12381_test.go:877-904                      (TestSignatureEdgeCase)
+  pairing/bn254/point_test.go:14-124, test_vectors_test.go       (bn254 Keccak/SvdW hash-to-G1 vectors)
+  encrypt/ibe/ibe_test.go:202-245                                (the one GT-byte dependent vector; inlined in the tests)
 """
 import glob
 import json
@@ -35,6 +37,31 @@ def go_bytes(src, var):
     return bytes(int(x, 16) for x in re.findall(r"0x([0-9a-fA-F]+)", m.group(1))).hex()
 
 
+def bn254_hash_vectors():
+    pt = open(f"{REF}/pairing/bn254/point_test.go").read()
+    tv = open(f"{REF}/pairing/bn254/test_vectors_test.go").read()
+    h2p_dst = re.search(r'domain := \[\]byte\("([^"]+)"\)', pt).group(1)
+    msg1 = re.search(r'Hash\(\[\]byte\("([^"]+)"\)\)', pt).group(1)
+    hexes = re.findall(r'hex\.DecodeString\("([0-9a-f]+)"\)', pt)
+    expand = re.search(r'func TestExpandMsg.*?dst := \[\]byte\("([^"]+)"\).*?DecodeString\("([0-9a-f]+)"\).*?!= "([0-9a-f]+)"', pt, re.S)
+    f_dst = re.search(r'func TestHashToField.*?dst := \[\]byte\("([^"]+)"\)', pt, re.S).group(1)
+    m_dst = re.search(r'func TestMapToPoint.*?dst := \[\]byte\("([^"]+)"\)', pt, re.S).group(1)
+    h2f_src, m2p_src = tv.split("var mapToPointTestVectors")
+    h2f = [{"msg": m, "x": x, "y": y} for m, x, y in
+           re.findall(r'Msg:\s*"([0-9a-f]*)",\s*RefX:\s*"([0-9a-f]+)",\s*RefY:\s*"([0-9a-f]+)"', h2f_src)]
+    m2p = [{"u": u, "x": x, "y": y} for u, x, y in   # first 200 of 1000 keep the fixture small
+           re.findall(r'U:\s*"(\d+)",\s*RefX:\s*"(\d+)",\s*RefY:\s*"(\d+)"', m2p_src)][:200]
+    out = {
+        "_source": "pairing/bn254/point_test.go:14-124 + test_vectors_test.go (data only)",
+        "hash_to_point": {"dst": h2p_dst, "cases": [{"msg_hex": msg1.encode().hex(), "point": hexes[0]},
+                                                    {"msg_hex": hexes[1], "point": hexes[2]}]},
+        "expand_msg": {"dst": expand.group(1), "msg_hex": expand.group(2), "len": 96, "out": expand.group(3)},
+        "hash_to_field": {"dst": f_dst, "cases": h2f},
+        "map_to_point": {"dst": m_dst, "cases": m2p},
+    }
+    json.dump(out, open(os.path.join(HERE, "bn254_hash_vectors.json"), "w"), indent=1)
+
+
 def main():
     json.dump({"G1": yaml_vectors("G1", "pubkey"), "G2": yaml_vectors("G2", "signature")},
               open(os.path.join(HERE, "bls12381_deserialization.json"), "w"), indent=1)
@@ -51,6 +78,7 @@ def main():
                          "note": "bls12381_test.go:877-904 TestSignatureEdgeCase: sigs on G1, default G1 DST"},
     }
     json.dump(kat, open(os.path.join(HERE, "bls12381_signature_kats.json"), "w"), indent=1)
+    bn254_hash_vectors()
     print("wrote golden fixtures")
 
 

@@ -18,7 +18,8 @@ def _sc(vals):
 
 def test_signatures_are_the_fixture_bytes(engine):
     f = FX["fixtures"]
-    hm = o.g1_marshal(o.hash_to_g1(f["msg"].encode()))        # bn256 Hash stays host-side (try-and-increment SHA-256)
+    hm = engine.bn256_hash_to_g1([f["msg"].encode()])         # device: SHA-256 try-and-increment (bn256/point.go:261-312)
+    assert hm == o.g1_marshal(o.hash_to_g1(f["msg"].encode()))
     privs = [int(x, 16) for x in f["private"]]
     out = engine.bn256_g1_mul_batch(_sc(privs), hm * 3)       # sig_i = x_i * H(m)   (bls.Sign, sign/bls/bls.go:67-80)
     assert [out[64 * i:64 * i + 64].hex() for i in range(3)] == f["sig"]
@@ -67,7 +68,7 @@ def test_bn256_pairing_and_full_bdn_verification(engine):
     gt = engine.bn256_pair(o.g1_marshal(o.G1) + o.g1_marshal(o.g1_mul(7)), o.g2_marshal(o.G2) + o.g2_marshal(o.g2_mul(11)))
     assert gt[:384] == bp.gt_to_bytes(bp.pairing(o.G1, o.G2))
     assert gt[384:] == bp.gt_to_bytes(bp.pairing(o.g1_mul(7), o.g2_mul(11)))
-    hm = o.g1_marshal(o.hash_to_g1(f["msg"].encode()))
+    hm = engine.bn256_hash_to_g1([f["msg"].encode()])
     base2 = o.g2_marshal(o.G2)
     sigs = [bytes.fromhex(x) for x in f["sig"]] + [bytes.fromhex(f["agg_sig"]), bytes.fromhex(f["sig"][0])]
     keys = [bytes.fromhex(x) for x in f["public"]] + [bytes.fromhex(f["agg_key"]), bytes.fromhex(f["public"][1])]

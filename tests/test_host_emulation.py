@@ -174,3 +174,36 @@ def test_ed25519_and_inversion_bodies():
             out = (ctypes.c_uint32 * n)()
             getattr(inv, f"emul_{name}_inv_vartime")(inp, out)
             assert sum(int(x) << (32 * i) for i, x in enumerate(out)) == (pow(a, -1, p) * R % p if a else 0)
+
+
+def test_bn_hash_to_g1_bodies_against_reference_vectors():
+    """bn_hash.cuh on the host: Keccak-256, expand_message_xmd, hashToField, the SvdW map and the full bn254 hash against
+    the reference's vectors (pairing/bn254/point_test.go:14-124, test_vectors_test.go); bn256 try-and-increment against
+    the oracle, which the byte-exact BDN signature fixtures pin (tests/test_oracle_bdn_bn256.py)."""
+    from oracle import bn254_hash as bh, bn256 as o6
+    lib = _lib("emul_bn_hash")
+    fx = json.load(open(os.path.join(GOLD, "bn254_hash_vectors.json")))
+    out32, out64, out96 = (ctypes.create_string_buffer(k) for k in (32, 64, 96))
+    for m in (b"", b"abc", bytes(135), bytes(136), bytes(137), bytes(range(256)) * 3):
+        lib.emul_keccak256(m, len(m), out32)
+        assert out32.raw == bh.keccak256(m)
+    e = fx["expand_msg"]
+    lib.emul_bn254_expand_96(bytes.fromhex(e["msg_hex"]), len(e["msg_hex"]) // 2, e["dst"].encode(), len(e["dst"]), out96)
+    assert out96.raw.hex() == e["out"]
+    dst = fx["hash_to_field"]["dst"].encode()
+    for c in fx["hash_to_field"]["cases"]:
+        m = bytes.fromhex(c["msg"])
+        lib.emul_bn254_hash_to_field(m, len(m), dst, len(dst), out64)
+        assert out64.raw.hex() == c["x"] + c["y"]
+    for c in fx["map_to_point"]["cases"]:
+        lib.emul_bn254_map_to_point(int(c["u"]).to_bytes(32, "big"), out64)
+        assert out64.raw == int(c["x"]).to_bytes(32, "big") + int(c["y"]).to_bytes(32, "big")
+    dst = fx["hash_to_point"]["dst"].encode()
+    for c in fx["hash_to_point"]["cases"]:
+        m = bytes.fromhex(c["msg_hex"])
+        lib.emul_bn254_hash_to_g1(m, len(m), dst, len(dst), out64)
+        assert out64.raw.hex() == c["point"]
+    bdn_msg = json.load(open(os.path.join(GOLD, "bdn_bn256_fixtures.json")))["fixtures"]["msg"].encode()
+    for m in (bdn_msg, b"", b"x" * 200, bytes(range(64))):
+        lib.emul_bn256_hash_to_g1(m, len(m), out64)
+        assert out64.raw == o6.g1_marshal(o6.hash_to_g1(m))
