@@ -70,6 +70,9 @@ int b2k_set_msm_variant(b2k_ctx* ctx, int one_thread_per_bucket);
  * group accumulates.  1 = strictly serial pipeline, in which b2k_last_timings reports every stage separately;
  * with groups > 1, [4] spans all accumulate launches, [9] is the exposed remainder of the reduction, [5],[6] ~ 0. */
 int b2k_set_msm_groups(b2k_ctx* ctx, int groups);
+/* BLS12-381 G1 MSM front end: 1 (default) = split every scalar with the curve endomorphism (k P = k1 P + k2 (-phi P),
+ * 127-bit k1, k2: half the windows), 0 = plain 255-bit pipeline.  Same results; kept switchable for A/B timing. */
+int b2k_set_msm_glv(b2k_ctx* ctx, int on);
 /* Resident bucket-accumulate blocks per SM (4..6; launch bound => register cap).  Tuning aid. */
 int b2k_set_msm_occupancy(b2k_ctx* ctx, int blocks_per_sm);
 /* Buckets per thread in the chunked bucket reduction (power of two, 0 = automatic).  Tuning aid. */

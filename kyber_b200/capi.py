@@ -37,6 +37,7 @@ def load_library() -> C.CDLL:
         "b2k_launch_count": (C.c_uint64, [vp]),
         "b2k_set_msm_slice": (C.c_int, [vp, C.c_int]),
         "b2k_set_msm_variant": (C.c_int, [vp, C.c_int]),
+        "b2k_set_msm_glv": (C.c_int, [vp, C.c_int]),
         "b2k_set_pairing_variant": (C.c_int, [vp, C.c_int]),
         "b2k_set_msm_groups": (C.c_int, [vp, C.c_int]),
         "b2k_set_msm_occupancy": (C.c_int, [vp, C.c_int]),
@@ -154,6 +155,10 @@ class Engine:
 
     def set_msm_variant(self, one_thread_per_bucket: bool):
         self._check(self.lib.b2k_set_msm_variant(self.h, int(one_thread_per_bucket)))
+
+    def set_msm_glv(self, on: bool):
+        """BLS12-381 G1 MSM: endomorphism split on (default) / off (plain 255-bit pipeline)"""
+        self._check(self.lib.b2k_set_msm_glv(self.h, int(on)))
 
     def last_timings(self):
         arr = (C.c_float * 16)()

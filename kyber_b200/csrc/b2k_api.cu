@@ -158,6 +158,12 @@ int b2k_set_msm_occupancy(b2k_ctx* ctx, int blocks_per_sm) {
   return B2K_OK;
 }
 
+int b2k_set_msm_glv(b2k_ctx* ctx, int on) {
+  if (!ctx) return B2K_ERR_ARG;
+  ctx->use_glv = on ? 1 : 0;
+  return B2K_OK;
+}
+
 int b2k_set_msm_groups(b2k_ctx* ctx, int groups) {
   if (!ctx || groups < 1 || groups > 8) return B2K_ERR_ARG;
   ctx->msm_groups = groups;

@@ -23,6 +23,7 @@ struct b2k_ctx {
   int force_c = 0;
   int force_m = 0;      // bucket-reduction chunk override (0 = automatic)
   int force_L = 0;      // slice length override (0 = automatic)
+  int use_glv = 1;      // BLS12-381 G1 MSM: split scalars with the curve endomorphism (0 = plain 255-bit pipeline, for A/B)
   int use_v1 = 0;       // 1 = one-thread-per-bucket accumulate (kept for A/B measurements)
   cudaStream_t stream2 = nullptr;   // high-priority side stream: bucket reduction of one window group overlaps the next accumulate
   cudaEvent_t gev[10];              // group hand-over events

@@ -80,9 +80,9 @@ template <class CV, class FR>
 static int recover_commit(b2k_ctx* ctx, size_t t, const uint32_t* indices, const uint8_t* points, uint8_t* out) {
   if (!ctx || !indices || !points || !out || t == 0 || t >= (size_t(1) << 31)) return B2K_ERR_ARG;
   CK(cudaSetDevice(ctx->device));
-  MsmPlan pl = make_plan(t, ctx->force_c, CV::SCALAR_BITS, ctx->force_m);
+  MsmPlan pl = msm_plan<CV>(ctx, t);
   size_t extra = pad256(t * 4) + pad256(t * 32) + pad256(t * (size_t)CV::IN_BYTES) + 1024;
-  int rc = arena_reserve(ctx, msm_scratch_bytes<CV>(t, pl, ctx->force_L) + extra);
+  int rc = arena_reserve(ctx, msm_scratch_bytes<CV>(msm_virtual_n<CV>(ctx, t), pl, ctx->force_L) + extra);
   if (rc) return rc;
   uint32_t* d_idx = arena_take<uint32_t>(ctx, t);
   uint8_t* d_s = arena_take<uint8_t>(ctx, t * 32);

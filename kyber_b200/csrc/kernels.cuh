@@ -19,6 +19,39 @@ __global__ void __launch_bounds__(256) k_load_points(size_t n, const uint8_t* __
   pts[i] = p;
 }
 
+// ---- GLV front end (BLS12-381 G1): operand conversion + scalar split in one pass ------------------------------
+// pts[i] = +-P_i, pts[n+i] = +-(-phi(P_i)) = (beta x, -+y); vscalars[i], vscalars[n+i] = the two 127-bit magnitudes as
+// 32-byte big-endian scalars, so that the digit/sort stages run unchanged over 2n (scalar, point) pairs.
+static __global__ void __launch_bounds__(256) k_glv_prepare_bls381(size_t n, const uint8_t* __restrict__ scalars,
+                                                                   const uint8_t* __restrict__ wire,
+                                                                   Affine<Fp<Bls381Fp>>* __restrict__ pts,
+                                                                   uint8_t* __restrict__ vscalars, uint32_t* flags) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  using F = Fp<Bls381Fp>;
+  Scalar256 k;
+  scalar_load_be(k, scalars + 32 * i);
+  if (!scalar_in_range<Bls381Fr>(k)) {
+    atomicOr(flags, FLAG_SCALAR_RANGE);
+    for (int j = 0; j < 8; j++) k.v[j] = 0;
+  }
+  GlvSplit sp;
+  glv_split_bls381(sp, k);
+  Affine<F> p0, p, e;
+  Bls381G1::load(p0, wire + (size_t)Bls381G1::IN_BYTES * i);
+  glv_points_bls381(p, e, p0, sp);
+  pts[i] = p;
+  pts[n + i] = e;
+  uint8_t* o1 = vscalars + 32 * i;
+  uint8_t* o2 = vscalars + 32 * (n + i);
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    const uint32_t a = sp.k1.v[7 - j], b = sp.k2.v[7 - j];
+    o1[4 * j] = (uint8_t)(a >> 24); o1[4 * j + 1] = (uint8_t)(a >> 16); o1[4 * j + 2] = (uint8_t)(a >> 8); o1[4 * j + 3] = (uint8_t)a;
+    o2[4 * j] = (uint8_t)(b >> 24); o2[4 * j + 1] = (uint8_t)(b >> 16); o2[4 * j + 2] = (uint8_t)(b >> 8); o2[4 * j + 3] = (uint8_t)b;
+  }
+}
+
 // ---- independent scalar multiplications ----------------------------------------------------------
 template <class CV, bool AFFINE_OUT>
 __global__ void __launch_bounds__(128) k_mul_batch(size_t n, const uint8_t* __restrict__ scalars,

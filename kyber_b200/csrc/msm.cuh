@@ -96,6 +96,97 @@ B2K_D void msm_horner(Xyzz<typename CV::F>& out, const Xyzz<typename CV::F>* wsu
   out = acc;
 }
 
+// ---- GLV split for BLS12-381 G1 ---------------------------------------------------------------------
+// phi(x, y) = (beta x, y) acts on G1 as multiplication by lambda = -x^2 (x the curve parameter, r = x^4 - x^2 + 1), so with
+// k (or r - k, whichever is smaller) = q X2 +- rem,  X2 = x^2,  |rem| <= X2/2:
+//      k P = s ( +-rem P + q (-phi(P)) ),     rem, q < 2^127.
+// The MSM then runs over 2n points and 127-bit scalars: half the windows to reduce and half the doublings in the final
+// Horner chain for the same number of bucket additions.  (The reference's bn254 Mul uses the same idea on one point,
+// pairing/bn254/curve.go:196-218 with lattice.go:47-108; here the split is exact division by x^2.)
+struct GlvSplit { Scalar256 k1, k2; bool neg1, neg2; };
+
+constexpr int GLV_BITS_BLS381 = 127;
+
+// out[0..na+nb) = a * b   (32-bit limbs, plain C: runs unchanged in the host emulation)
+B2K_D void limbs_mul(uint32_t* out, const uint32_t* a, int na, const uint32_t* b, int nb) {
+  for (int i = 0; i < na + nb; i++) out[i] = 0;
+  for (int i = 0; i < na; i++) {
+    uint64_t carry = 0;
+    for (int j = 0; j < nb; j++) {
+      uint64_t t = (uint64_t)a[i] * b[j] + out[i + j] + carry;
+      out[i + j] = (uint32_t)t;
+      carry = t >> 32;
+    }
+    out[i + nb] = (uint32_t)carry;
+  }
+}
+// a -= b over n limbs, returns the borrow
+B2K_D uint32_t limbs_sub(uint32_t* a, const uint32_t* b, int n) {
+  uint64_t br = 0;
+  for (int i = 0; i < n; i++) {
+    uint64_t d = (uint64_t)a[i] - b[i] - br;
+    a[i] = (uint32_t)d;
+    br = (d >> 32) & 1u;
+  }
+  return (uint32_t)br;
+}
+B2K_D bool limbs_geq(const uint32_t* a, const uint32_t* b, int n) {
+  for (int i = n - 1; i >= 0; i--) {
+    if (a[i] > b[i]) return true;
+    if (a[i] < b[i]) return false;
+  }
+  return true;
+}
+
+B2K_D void glv_split_bls381(GlvSplit& out, const Scalar256& k) {
+  // x^2 = 0xac45a401 0001a402 00000001 00000000 (128 bits), mu = floor(2^256 / x^2) (129 bits)
+  const uint32_t XX[5] = {0x00000000u, 0x00000001u, 0x0001a402u, 0xac45a401u, 0u};
+  const uint32_t MU[5] = {0xf6cfee2eu, 0x63f6e522u, 0xe01faaddu, 0x7c6becf1u, 0x1u};
+  uint32_t kk[8], t[8];
+  bool neg = false;
+  for (int j = 0; j < 8; j++) { kk[j] = k.v[j]; t[j] = Bls381Fr::mod(j); }
+  limbs_sub(t, kk, 8);                              // r - k  (k < r is checked by the caller)
+  if (!limbs_geq(t, kk, 8)) { for (int j = 0; j < 8; j++) kk[j] = t[j]; neg = true; }
+  uint32_t prod[13], q[5], qx[10], rem[5];
+  limbs_mul(prod, kk, 8, MU, 5);
+  for (int j = 0; j < 5; j++) q[j] = prod[8 + j];   // floor(kk mu / 2^256) in {Q-1, Q}
+  limbs_mul(qx, q, 5, XX, 5);
+  for (int j = 0; j < 5; j++) rem[j] = kk[j];
+  limbs_sub(rem, qx, 5);                            // kk - q x^2 < 2 x^2 < 2^129: 160 bits are enough
+  if (limbs_geq(rem, XX, 5)) {
+    limbs_sub(rem, XX, 5);
+    uint32_t c = 1; for (int j = 0; j < 5 && c; j++) { q[j] += c; c = (q[j] == 0); }
+  }
+  // balance: 2 rem > x^2  ->  rem = x^2 - rem, q += 1, sign flipped
+  uint32_t dbl[5];
+  for (int j = 4; j > 0; j--) dbl[j] = (rem[j] << 1) | (rem[j - 1] >> 31);
+  dbl[0] = rem[0] << 1;
+  bool negr = false;
+  if (!limbs_geq(XX, dbl, 5)) {
+    uint32_t x2[5];
+    for (int j = 0; j < 5; j++) x2[j] = XX[j];
+    limbs_sub(x2, rem, 5);
+    for (int j = 0; j < 5; j++) rem[j] = x2[j];
+    uint32_t c = 1; for (int j = 0; j < 5 && c; j++) { q[j] += c; c = (q[j] == 0); }
+    negr = true;
+  }
+  for (int j = 0; j < 8; j++) { out.k1.v[j] = j < 4 ? rem[j] : 0u; out.k2.v[j] = j < 4 ? q[j] : 0u; }
+  out.neg1 = neg != negr;
+  out.neg2 = neg;
+}
+
+// the two points of the split: p1 = +-P, p2 = +-(-phi(P)) = (beta x, -+y); infinity (0,0) maps to itself
+B2K_D void glv_points_bls381(Affine<Fp<Bls381Fp>>& p1, Affine<Fp<Bls381Fp>>& p2, const Affine<Fp<Bls381Fp>>& p, const GlvSplit& sp) {
+  Fp<Bls381Fp> beta;
+#pragma unroll
+  for (int j = 0; j < 12; j++) beta.v[j] = Bls381Fp::beta(j);
+  fp_mul(p2.x, p.x, beta);
+  p2.y = p.y;
+  if (!sp.neg2) fp_neg(p2.y, p2.y);
+  p1 = p;
+  if (sp.neg1) fp_neg(p1.y, p1.y);
+}
+
 // ---- independent scalar multiplication -----------------------------------------------------------
 // k*P, MSB-first double-and-add over the 256-bit scalar (Jacobian, mixed additions).
 template <class CV>

@@ -75,7 +75,23 @@ inline int check_flags(b2k_ctx* ctx) {
   return B2K_OK;
 }
 
+// ---- GLV front end: which curves have it, and the problem the pipeline then sees ----------------------------------
+template <class CV> struct GlvTraits { static constexpr bool enabled = false; static constexpr int bits = 0; };
+template <> struct GlvTraits<Bls381G1> { static constexpr bool enabled = true; static constexpr int bits = GLV_BITS_BLS381; };
+
+template <class CV>
+inline bool msm_uses_glv(const b2k_ctx* ctx, size_t n) { return GlvTraits<CV>::enabled && ctx->use_glv && n < (size_t(1) << 30); }
+// number of (scalar, point) pairs the sort/accumulate stages process
+template <class CV>
+inline size_t msm_virtual_n(const b2k_ctx* ctx, size_t n) { return msm_uses_glv<CV>(ctx, n) ? 2 * n : n; }
+template <class CV>
+inline MsmPlan msm_plan(const b2k_ctx* ctx, size_t n) {
+  const bool g = msm_uses_glv<CV>(ctx, n);
+  return make_plan(g ? 2 * n : n, ctx->force_c, g ? GlvTraits<CV>::bits : CV::SCALAR_BITS, ctx->force_m);
+}
+
 // ------------------------------------------------------------------------------------------------
+// n = number of pairs the pipeline processes (msm_virtual_n)
 template <class CV>
 size_t msm_scratch_bytes(size_t n, const MsmPlan& pl, int force_L) {
   using F = typename CV::F;
@@ -83,6 +99,7 @@ size_t msm_scratch_bytes(size_t n, const MsmPlan& pl, int force_L) {
   size_t T = pl.nb / pl.m;
   size_t b = 0;
   b += pad256(n * sizeof(Affine<F>));
+  b += pad256(n * 32);                            // split scalars (GLV front end)
   b += pad256((total + 1) * 4) * 3;               // counts, offs, cursor
   b += pad256(n * (size_t)pl.W * 4);              // entries
   b += pad256(total * sizeof(Xyzz<F>));           // buckets
@@ -95,15 +112,20 @@ size_t msm_scratch_bytes(size_t n, const MsmPlan& pl, int force_L) {
 }
 
 // Enqueue the whole MSM on ctx->stream. d_scalars/d_points/d_out are device pointers; scratch must
-// already be reserved (arena) for msm_scratch_bytes().
+// already be reserved (arena) for msm_scratch_bytes(msm_virtual_n(n)) and pl must come from msm_plan(n).
 template <class CV>
-int msm_enqueue(b2k_ctx* ctx, size_t n, const MsmPlan& pl, const uint8_t* d_scalars, const uint8_t* d_points,
+int msm_enqueue(b2k_ctx* ctx, size_t n_in, const MsmPlan& pl, const uint8_t* d_scalars_in, const uint8_t* d_points,
                 uint8_t* d_out, int affine_out = 0) {
   using F = typename CV::F;
   cudaStream_t st = ctx->stream;
+  const bool glv = msm_uses_glv<CV>(ctx, n_in);
+  const size_t n = glv ? 2 * n_in : n_in;          // pairs seen by the digit / sort / accumulate stages
   size_t total = (size_t)pl.W * pl.nb;
   int T = pl.nb / pl.m;
   auto* pts = arena_take<Affine<F>>(ctx, n);
+  uint8_t* vsc = glv ? arena_take<uint8_t>(ctx, n * 32) : nullptr;
+  const uint8_t* d_scalars = glv ? vsc : d_scalars_in;
+  if (glv && !vsc) { ctx->err = "scratch arena too small"; return B2K_ERR_ARG; }
   auto* counts = arena_take<uint32_t>(ctx, total + 1);
   auto* offs = arena_take<uint32_t>(ctx, total + 1);
   auto* cursor = arena_take<uint32_t>(ctx, total + 1);
@@ -130,7 +152,13 @@ int msm_enqueue(b2k_ctx* ctx, size_t n, const MsmPlan& pl, const uint8_t* d_scal
   int nl = 0;
   CK(cudaEventRecord(ctx->ev[0], st));
   CK(cudaMemsetAsync(counts, 0, (total + 1) * 4, st));
-  k_load_points<CV><<<gb_n, 256, 0, st>>>(n, d_points, pts); nl++;
+  if constexpr (GlvTraits<CV>::enabled) {
+    if (glv) k_glv_prepare_bls381<<<(unsigned)((n_in + 255) / 256), 256, 0, st>>>(n_in, d_scalars_in, d_points, pts, vsc, ctx->d_flags);
+    else k_load_points<CV><<<gb_n, 256, 0, st>>>(n, d_points, pts);
+  } else {
+    k_load_points<CV><<<gb_n, 256, 0, st>>>(n, d_points, pts);
+  }
+  nl++;
   CK(cudaEventRecord(ctx->ev[1], st));
   k_msm_count<CV><<<gb_n, 256, 0, st>>>(n, d_scalars, pl, counts, ctx->d_flags); nl++;
   CK(cudaEventRecord(ctx->ev[2], st));
@@ -210,8 +238,8 @@ int msm_dev(b2k_ctx* ctx, size_t n, const void* d_scalars, const void* d_points,
     return B2K_ERR_ARG;
   }
   CK(cudaSetDevice(ctx->device));
-  MsmPlan pl = make_plan(n, ctx->force_c, CV::SCALAR_BITS, ctx->force_m);
-  int rc = arena_reserve(ctx, msm_scratch_bytes<CV>(n, pl, ctx->force_L));
+  MsmPlan pl = msm_plan<CV>(ctx, n);
+  int rc = arena_reserve(ctx, msm_scratch_bytes<CV>(msm_virtual_n<CV>(ctx, n), pl, ctx->force_L));
   if (rc) return rc;
   return msm_enqueue<CV>(ctx, n, pl, (const uint8_t*)d_scalars, (const uint8_t*)d_points, (uint8_t*)d_out, affine_out);
 }
@@ -223,9 +251,9 @@ int msm_host(b2k_ctx* ctx, size_t n, const uint8_t* scalars, const uint8_t* poin
     return B2K_ERR_ARG;
   }
   CK(cudaSetDevice(ctx->device));
-  MsmPlan pl = make_plan(n, ctx->force_c, CV::SCALAR_BITS, ctx->force_m);
+  MsmPlan pl = msm_plan<CV>(ctx, n);
   size_t in_bytes = pad256(n * 32) + pad256(n * (size_t)CV::IN_BYTES) + 256;
-  int rc = arena_reserve(ctx, msm_scratch_bytes<CV>(n, pl, ctx->force_L) + in_bytes);
+  int rc = arena_reserve(ctx, msm_scratch_bytes<CV>(msm_virtual_n<CV>(ctx, n), pl, ctx->force_L) + in_bytes);
   if (rc) return rc;
   auto* d_s = arena_take<uint8_t>(ctx, n * 32);
   auto* d_p = arena_take<uint8_t>(ctx, n * (size_t)CV::IN_BYTES);

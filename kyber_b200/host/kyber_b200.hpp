@@ -373,4 +373,83 @@ class SchemeOnG1 {
   const Suite& s_;
 };
 
+// ---- sign/bdn on the engine (signatures on G1, public keys on G2: bdn.NewSchemeOnG1, sign/bdn/bdn.go:74-87) -------------
+namespace bdn {
+
+// bdn.Mask (sign/bdn/mask.go:13-140), the participation bitmask over a roster, plus the rogue-key factors c_i + 1 of every
+// roster member (hashPointToR, bdn.go:29-63, through b2k_bdn_coefficients).  The reference precomputes the terms
+// (c_i + 1) * PK_i with a Mul+Add loop at construction (mask.go:57-61); here they are folded into the one MSM of
+// AggregatePublicKeys.
+class Mask {
+ public:
+  Mask(const Suite& suite, std::vector<G2Elt> publics) : publics_(std::move(publics)), mask_((publics_.size() + 7) / 8, 0) {
+    (void)suite;
+    const size_t n = publics_.size();
+    Bytes blob(96 * n), fac(32 * n);
+    for (size_t i = 0; i < n; i++) { Bytes b = publics_[i].MarshalBinary(); std::memcpy(&blob[96 * i], b.data(), 96); }
+    if (b2k_bdn_coefficients(n, blob.data(), 96, 1, fac.data()) != B2K_OK) throw std::runtime_error("bdn: failed to hash public keys");
+    factors_.resize(n);
+    for (size_t i = 0; i < n; i++) factors_[i].UnmarshalBinary(Bytes(fac.begin() + 32 * i, fac.begin() + 32 * (i + 1)));
+  }
+  int Len() const { return (int)mask_.size(); }
+  Bytes MaskBytes() const { return mask_; }
+  void SetMask(const Bytes& m) { if (m.size() != mask_.size()) throw std::runtime_error("mismatching mask lengths"); mask_ = m; }
+  bool GetBit(int i) const { range(i); return (mask_[i / 8] >> (i & 7)) & 1; }
+  void SetBit(int i, bool enable) {
+    range(i);
+    if (enable) mask_[i / 8] |= (uint8_t)(1u << (i & 7)); else mask_[i / 8] &= (uint8_t)~(1u << (i & 7));
+  }
+  int CountEnabled() const { int c = 0; for (size_t i = 0; i < publics_.size(); i++) c += GetBit((int)i); return c; }
+  int CountTotal() const { return (int)publics_.size(); }
+  const std::vector<G2Elt>& Publics() const { return publics_; }
+  const std::vector<Scalar>& Factors() const { return factors_; }       // c_i + 1
+ private:
+  void range(int i) const { if (i < 0 || (size_t)i >= publics_.size()) throw std::runtime_error("index out of range"); }
+  std::vector<G2Elt> publics_;
+  std::vector<Scalar> factors_;
+  Bytes mask_;
+};
+
+class SchemeOnG1 {
+ public:
+  explicit SchemeOnG1(const Suite& s) : s_(s), bls_(s) {}
+  Bytes Sign(const Scalar& x, const Bytes& msg) const { return bls_.Sign(x, msg); }
+  bool Verify(const Point& X, const Bytes& msg, const Bytes& sig) const { return bls_.Verify(X, msg, sig); }
+  // sum over the enabled signers of (c_i + 1) * S_i, signatures given in roster order of the enabled bits (bdn.go:126-161);
+  // a count mismatch or an undecodable signature is an error, as in Go.
+  G1Elt AggregateSignatures(const std::vector<Bytes>& sigs, const Mask& mask) const {
+    std::vector<Scalar> f;
+    std::vector<G1Elt> pts;
+    size_t k = 0;
+    for (int i = 0; i < mask.CountTotal(); i++) {
+      if (!mask.GetBit(i)) continue;
+      if (k >= sigs.size()) throw std::runtime_error("length of signatures and public keys must match");
+      G1Elt sg(s_.engine());
+      sg.UnmarshalBinary(sigs[k++]);
+      f.push_back(mask.Factors()[i]);
+      pts.push_back(sg);
+    }
+    if (k != sigs.size()) throw std::runtime_error("length of signatures and public keys must match");
+    if (pts.empty()) { G1Elt z(s_.engine()); z.Null(); return z; }
+    return s_.G1().MSM(f, pts);
+  }
+  // sum over the enabled signers of (c_i + 1) * PK_i (bdn.go:166-181 with the terms of mask.go:57-61)
+  G2Elt AggregatePublicKeys(const Mask& mask) const {
+    std::vector<Scalar> f;
+    std::vector<G2Elt> pts;
+    for (int i = 0; i < mask.CountTotal(); i++) {
+      if (!mask.GetBit(i)) continue;
+      f.push_back(mask.Factors()[i]);
+      pts.push_back(mask.Publics()[i]);
+    }
+    if (pts.empty()) { G2Elt z(s_.engine()); z.Null(); return z; }
+    return s_.G2().MSM(f, pts);
+  }
+ private:
+  const Suite& s_;
+  b200::SchemeOnG1 bls_;
+};
+
+}  // namespace bdn
+
 }  // namespace b200

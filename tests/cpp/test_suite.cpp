@@ -130,6 +130,38 @@ int main() {
   G2Elt epk(eng); epk.UnmarshalBinary(Bytes(pkb, pkb + 96));
   CHECK("bls.TestSignatureEdgeCase", scheme.Verify(epk, Bytes(mb, mb + 32), Bytes(sgb, sgb + 48)));
 
+  // sign/bdn (sign/bdn/bdn_test.go: TestBDN_AggregateSignatures, _SubsetSignature, _RogueAttack shape): aggregate
+  // signature of a subset verifies under the aggregate key of the same subset and under no other; the engine's MSM
+  // equals the reference's Mul+Add loop with the coefficients c_i + 1.
+  {
+    bdn::SchemeOnG1 bs(suite);
+    const int n = 5;
+    std::vector<Scalar> sks; std::vector<G2Elt> pks; std::vector<Bytes> all_sigs;
+    for (int i = 0; i < n; i++) { sks.push_back(pick(rng)); G2Elt k(eng); k.Mul(sks[i], nullptr); pks.push_back(k); all_sigs.push_back(bs.Sign(sks[i], msg)); }
+    bdn::Mask mask(suite, pks);
+    CHECK("bdn.mask_len", mask.Len() == 1 && mask.CountEnabled() == 0 && mask.CountTotal() == n);
+    mask.SetBit(0, true); mask.SetBit(2, true); mask.SetBit(4, true);
+    std::vector<Bytes> sub = {all_sigs[0], all_sigs[2], all_sigs[4]};
+    G1Elt asig = bs.AggregateSignatures(sub, mask);
+    G2Elt akey = bs.AggregatePublicKeys(mask);
+    CHECK("bdn.aggregate_verifies", bs.Verify(akey, msg, asig.MarshalBinary()));
+    // loop form of the reference: sum (c_i * S_i + S_i)
+    G1Elt loop(eng); loop.Null();
+    for (int i : {0, 2, 4}) { G1Elt sgi(eng); sgi.UnmarshalBinary(all_sigs[i]); G1Elt t(eng); t.Mul(mask.Factors()[i], &sgi); loop.Add(loop, t); }
+    CHECK("bdn.msm_equals_reference_loop", loop.Equal(asig));
+    bdn::Mask other(suite, pks); other.SetBit(0, true); other.SetBit(1, true); other.SetBit(4, true);
+    CHECK("bdn.wrong_subset_key_fails", !bs.Verify(bs.AggregatePublicKeys(other), msg, asig.MarshalBinary()));
+    bool err = false;
+    try { bs.AggregateSignatures({all_sigs[0]}, mask); } catch (const std::runtime_error&) { err = true; }
+    CHECK("bdn.signature_count_mismatch_is_error", err);
+    err = false;
+    try { mask.SetBit(n, true); } catch (const std::runtime_error&) { err = true; }
+    CHECK("bdn.mask_index_out_of_range_is_error", err);
+    // plain sum of keys (no coefficients) must NOT verify the BDN aggregate: the coefficients are in effect
+    G2Elt plain(eng); plain.Null(); for (int i : {0, 2, 4}) plain.Add(plain, pks[i]);
+    CHECK("bdn.plain_key_sum_fails", !bs.Verify(plain, msg, asig.MarshalBinary()));
+  }
+
   printf("%s: %d failure(s)\n", fails ? "FAILED" : "PASSED", fails);
   return fails ? 1 : 0;
 }

@@ -105,6 +105,31 @@ static int emul_msm(size_t n, const uint8_t* scalars, const uint8_t* pts, int c,
 extern "C" {
 void emul_bls12381_g1_mul_batch(size_t n, const uint8_t* s, const uint8_t* p, uint8_t* o) { emul_mul_batch<Bls381G1>(n, s, p, o); }
 int emul_bls12381_g1_msm(size_t n, const uint8_t* s, const uint8_t* p, int c, int m, uint8_t* o) { return emul_msm<Bls381G1>(n, s, p, c, m, o); }
+// GLV front end + the same pipeline over the 2n split pairs
+int emul_bls12381_g1_msm_glv(size_t n, const uint8_t* s, const uint8_t* p, int c, int m, int L, uint8_t* o) {
+  std::vector<uint8_t> vs(64 * n), vp(192 * n);
+  for (size_t i = 0; i < n; i++) {
+    Scalar256 k; scalar_load_be(k, s + 32 * i);
+    if (!scalar_in_range<Bls381Fr>(k)) return -3;
+    GlvSplit sp; glv_split_bls381(sp, k);
+    Affine<Fp<Bls381Fp>> p0, p1, p2;
+    Bls381G1::load(p0, p + 96 * i);
+    glv_points_bls381(p1, p2, p0, sp);
+    Bls381G1::store_affine(&vp[96 * i], p1); Bls381G1::store_affine(&vp[96 * (n + i)], p2);
+    for (int j = 0; j < 8; j++) for (int b = 0; b < 4; b++) {
+      vs[32 * i + 4 * j + b] = (uint8_t)(sp.k1.v[7 - j] >> (24 - 8 * b));
+      vs[32 * (n + i) + 4 * j + b] = (uint8_t)(sp.k2.v[7 - j] >> (24 - 8 * b));
+    }
+  }
+  return emul_msm<Bls381G1>(2 * n, vs.data(), vp.data(), c, m, o, L);
+}
+// k -> k1 (32 B BE), k2 (32 B BE), flags bit0 = neg1, bit1 = neg2
+int emul_glv_split_bls381(const uint8_t* k32, uint8_t* k1, uint8_t* k2) {
+  Scalar256 k; scalar_load_be(k, k32);
+  GlvSplit sp; glv_split_bls381(sp, k);
+  for (int j = 0; j < 8; j++) for (int b = 0; b < 4; b++) { k1[4 * j + b] = (uint8_t)(sp.k1.v[7 - j] >> (24 - 8 * b)); k2[4 * j + b] = (uint8_t)(sp.k2.v[7 - j] >> (24 - 8 * b)); }
+  return (sp.neg1 ? 1 : 0) | (sp.neg2 ? 2 : 0);
+}
 int emul_bls12381_g1_msm_v2(size_t n, const uint8_t* s, const uint8_t* p, int c, int m, int L, uint8_t* o) { return emul_msm<Bls381G1>(n, s, p, c, m, o, L); }
 void emul_bn254_g1_mul_batch(size_t n, const uint8_t* s, const uint8_t* p, uint8_t* o) { emul_mul_batch<Bn254G1>(n, s, p, o); }
 int emul_bn254_g1_msm(size_t n, const uint8_t* s, const uint8_t* p, int c, int m, uint8_t* o) { return emul_msm<Bn254G1>(n, s, p, c, m, o); }

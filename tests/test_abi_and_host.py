@@ -113,6 +113,39 @@ def test_device_msm_bodies_under_host_emulation(emul):
         assert o48.raw == exp, (c, m)
 
 
+def test_glv_front_end_under_host_emulation(emul):
+    """The endomorphism split of the BLS12-381 G1 MSM: k = s1 k1 + s2 k2 x^2 (mod r) with k1, k2 < 2^127 for edge and
+    random scalars, phi(P) = (beta x, y) = [-x^2] P, and the whole split pipeline == the oracle MSM."""
+    import random
+    from oracle import bls12381 as o
+    rng = random.Random(12)
+    x2 = o.X_ABS ** 2
+    edge = [0, 1, 2, x2 - 1, x2, x2 + 1, x2 // 2, x2 // 2 + 1, (o.R - 1) // 2, (o.R + 1) // 2, o.R - 1, o.R - 2, o.R - x2, 3 * x2 + x2 // 2,
+            (1 << 254) - 1, 1 << 128, (1 << 128) - 1]
+    k1b, k2b = ctypes.create_string_buffer(32), ctypes.create_string_buffer(32)
+    for k in edge + [rng.randrange(o.R) for _ in range(300)]:
+        fl = emul.emul_glv_split_bls381(k.to_bytes(32, "big"), k1b, k2b)
+        k1, k2 = int.from_bytes(k1b.raw, "big"), int.from_bytes(k2b.raw, "big")
+        assert k1 < 1 << 127 and k2 < 1 << 127, hex(k)
+        s1 = -1 if fl & 1 else 1
+        s2 = -1 if fl & 2 else 1
+        assert (s1 * k1 + s2 * k2 * x2 - k) % o.R == 0, hex(k)
+    # the second point of the split is -phi(P) = [x^2] P
+    n = 19
+    ks = [0, 1, o.R - 1, x2, o.R - x2] + [rng.randrange(o.R) for _ in range(n - 5)]
+    pts = [o.g1_mul(rng.randrange(1, o.R)) for _ in range(n)]
+    pts[3] = None
+    pts[6], ks[6] = pts[5], ks[5]
+    pts[8], ks[8] = o.g1_neg(pts[7]), ks[7]
+    sb = b"".join(o.scalar_to_bytes(k) for k in ks)
+    pb = b"".join(o.g1_to_affine_bytes(p) for p in pts)
+    exp = o.g1_compress(o.g1_msm(ks, pts))
+    for c, m, L in ((4, 2, 0), (9, 8, 4), (16, 32, 3)):
+        o48 = ctypes.create_string_buffer(48)
+        assert emul.emul_bls12381_g1_msm_glv(ctypes.c_size_t(n), sb, pb, c, m, L, o48) == 0
+        assert o48.raw == exp, (c, m, L)
+
+
 def test_bdn_coefficients_host_function_matches_reference_vector_and_oracle():
     """b2k_bdn_coefficients (host C++ BLAKE2Xs in the library) == the reference vector of
     sign/bdn/bdn_vartime_test.go:24-48 (coefficients for G2 base, 2*base, 3*base on bn256) == the oracle, incl. ragged

@@ -131,3 +131,36 @@ def test_msm_variants_agree(engine):
     finally:
         engine.set_msm_variant(False)
     assert v1 == engine.bls12381_g1_msm(sb, pts) == o.g1_compress(o.g1_mul(wl.dot_mod(s, a, o.R)))
+
+
+@pytest.mark.parametrize("dist_name", ["uniform", "edges", "bdn128", "equal"])
+def test_msm_endomorphism_split_on_and_off_agree(engine, dist_name):
+    """The GLV front end (default) and the plain 255-bit pipeline give the same bytes as the oracle: uniform scalars,
+    scalars at the split's edges (multiples of x^2, halves, r-1 ...), 128-bit BDN factors, one repeated scalar."""
+    n = 4100
+    rng = random.Random(78)
+    x2 = o.X_ABS ** 2
+    a = wl.prng_scalars("b2k/test-a", n, o.R)
+    if dist_name == "uniform":
+        s = wl.prng_scalars("b2k/test-g", n, o.R)
+    elif dist_name == "edges":
+        base = [0, 1, x2 - 1, x2, x2 + 1, x2 // 2, x2 // 2 + 1, (o.R - 1) // 2, (o.R + 1) // 2, o.R - 1, o.R - x2, o.R - x2 // 2, (1 << 254) - 3]
+        s = [base[i % len(base)] + (i // len(base)) * x2 for i in range(n)]
+        s = [v % o.R for v in s]
+    elif dist_name == "bdn128":
+        s = [rng.randrange(1 << 128) + 1 for _ in range(n)]
+    else:
+        s = [0x5A5A5A5A5A5A5A5A5A5A5A5A5A5A5A5A5A5A5A5A5A5A5A5A5A5A5A5A5A5A] * n
+    pts = engine.bls12381_g1_mul_batch_affine(wl.scalars_to_bytes(a), wl.G1_BLS12381_AFFINE * n)
+    want = o.g1_compress(o.g1_mul(wl.dot_mod(s, a, o.R)))
+    sb = wl.scalars_to_bytes(s)
+    for glv in (True, False):
+        for c in (0, 7, 16):
+            engine.set_msm_glv(glv)
+            engine.set_msm_window(c)
+            try:
+                got = engine.bls12381_g1_msm(sb, pts)
+            finally:
+                engine.set_msm_glv(True)
+                engine.set_msm_window(0)
+            assert got == want, (dist_name, glv, c)
