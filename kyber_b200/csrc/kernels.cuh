@@ -42,13 +42,12 @@ static __global__ void __launch_bounds__(256) k_glv_prepare_bls381(size_t n, con
   glv_points_bls381(p, e, p0, sp);
   pts[i] = p;
   pts[n + i] = e;
-  uint8_t* o1 = vscalars + 32 * i;
-  uint8_t* o2 = vscalars + 32 * (n + i);
+  uint32_t* o1 = reinterpret_cast<uint32_t*>(vscalars + 32 * i);          // big-endian bytes = byte-swapped words, top first
+  uint32_t* o2 = reinterpret_cast<uint32_t*>(vscalars + 32 * (n + i));
 #pragma unroll
   for (int j = 0; j < 8; j++) {
-    const uint32_t a = sp.k1.v[7 - j], b = sp.k2.v[7 - j];
-    o1[4 * j] = (uint8_t)(a >> 24); o1[4 * j + 1] = (uint8_t)(a >> 16); o1[4 * j + 2] = (uint8_t)(a >> 8); o1[4 * j + 3] = (uint8_t)a;
-    o2[4 * j] = (uint8_t)(b >> 24); o2[4 * j + 1] = (uint8_t)(b >> 16); o2[4 * j + 2] = (uint8_t)(b >> 8); o2[4 * j + 3] = (uint8_t)b;
+    o1[j] = __byte_perm(sp.k1.v[7 - j], 0, 0x0123);
+    o2[j] = __byte_perm(sp.k2.v[7 - j], 0, 0x0123);
   }
 }
 

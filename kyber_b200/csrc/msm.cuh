@@ -107,35 +107,49 @@ struct GlvSplit { Scalar256 k1, k2; bool neg1, neg2; };
 
 constexpr int GLV_BITS_BLS381 = 127;
 
-// out[0..na+nb) = a * b   (32-bit limbs, plain C: runs unchanged in the host emulation)
-B2K_D void limbs_mul(uint32_t* out, const uint32_t* a, int na, const uint32_t* b, int nb) {
-  for (int i = 0; i < na + nb; i++) out[i] = 0;
-  for (int i = 0; i < na; i++) {
+// out[0..NA+NB) = a * b   (32-bit limbs, plain C: runs unchanged in the host emulation; sizes are compile-time so that
+// everything unrolls into registers)
+template <int NA, int NB>
+B2K_D void limbs_mul(uint32_t* out, const uint32_t* a, const uint32_t* b) {
+#pragma unroll
+  for (int i = 0; i < NA + NB; i++) out[i] = 0;
+#pragma unroll
+  for (int i = 0; i < NA; i++) {
     uint64_t carry = 0;
-    for (int j = 0; j < nb; j++) {
+#pragma unroll
+    for (int j = 0; j < NB; j++) {
       uint64_t t = (uint64_t)a[i] * b[j] + out[i + j] + carry;
       out[i + j] = (uint32_t)t;
       carry = t >> 32;
     }
-    out[i + nb] = (uint32_t)carry;
+    out[i + NB] = (uint32_t)carry;
   }
 }
-// a -= b over n limbs, returns the borrow
-B2K_D uint32_t limbs_sub(uint32_t* a, const uint32_t* b, int n) {
+// a -= b over N limbs, returns the borrow
+template <int N>
+B2K_D uint32_t limbs_sub(uint32_t* a, const uint32_t* b) {
   uint64_t br = 0;
-  for (int i = 0; i < n; i++) {
+#pragma unroll
+  for (int i = 0; i < N; i++) {
     uint64_t d = (uint64_t)a[i] - b[i] - br;
     a[i] = (uint32_t)d;
     br = (d >> 32) & 1u;
   }
   return (uint32_t)br;
 }
-B2K_D bool limbs_geq(const uint32_t* a, const uint32_t* b, int n) {
-  for (int i = n - 1; i >= 0; i--) {
-    if (a[i] > b[i]) return true;
-    if (a[i] < b[i]) return false;
-  }
-  return true;
+// a >= b  <=>  a - b does not borrow
+template <int N>
+B2K_D bool limbs_geq(const uint32_t* a, const uint32_t* b) {
+  uint64_t br = 0;
+#pragma unroll
+  for (int i = 0; i < N; i++) br = (((uint64_t)a[i] - b[i] - br) >> 32) & 1u;
+  return br == 0;
+}
+template <int N>
+B2K_D void limbs_inc(uint32_t* a) {
+  uint32_t c = 1;
+#pragma unroll
+  for (int j = 0; j < N; j++) { a[j] += c; c = (c && a[j] == 0) ? 1u : 0u; }
 }
 
 B2K_D void glv_split_bls381(GlvSplit& out, const Scalar256& k) {
@@ -144,32 +158,43 @@ B2K_D void glv_split_bls381(GlvSplit& out, const Scalar256& k) {
   const uint32_t MU[5] = {0xf6cfee2eu, 0x63f6e522u, 0xe01faaddu, 0x7c6becf1u, 0x1u};
   uint32_t kk[8], t[8];
   bool neg = false;
+#pragma unroll
   for (int j = 0; j < 8; j++) { kk[j] = k.v[j]; t[j] = Bls381Fr::mod(j); }
-  limbs_sub(t, kk, 8);                              // r - k  (k < r is checked by the caller)
-  if (!limbs_geq(t, kk, 8)) { for (int j = 0; j < 8; j++) kk[j] = t[j]; neg = true; }
+  limbs_sub<8>(t, kk);                              // r - k  (k < r is checked by the caller)
+  if (!limbs_geq<8>(t, kk)) {
+#pragma unroll
+    for (int j = 0; j < 8; j++) kk[j] = t[j];
+    neg = true;
+  }
   uint32_t prod[13], q[5], qx[10], rem[5];
-  limbs_mul(prod, kk, 8, MU, 5);
+  limbs_mul<8, 5>(prod, kk, MU);
+#pragma unroll
   for (int j = 0; j < 5; j++) q[j] = prod[8 + j];   // floor(kk mu / 2^256) in {Q-1, Q}
-  limbs_mul(qx, q, 5, XX, 5);
+  limbs_mul<5, 5>(qx, q, XX);
+#pragma unroll
   for (int j = 0; j < 5; j++) rem[j] = kk[j];
-  limbs_sub(rem, qx, 5);                            // kk - q x^2 < 2 x^2 < 2^129: 160 bits are enough
-  if (limbs_geq(rem, XX, 5)) {
-    limbs_sub(rem, XX, 5);
-    uint32_t c = 1; for (int j = 0; j < 5 && c; j++) { q[j] += c; c = (q[j] == 0); }
+  limbs_sub<5>(rem, qx);                            // kk - q x^2 < 2 x^2 < 2^129: 160 bits are enough
+  if (limbs_geq<5>(rem, XX)) {
+    limbs_sub<5>(rem, XX);
+    limbs_inc<5>(q);
   }
   // balance: 2 rem > x^2  ->  rem = x^2 - rem, q += 1, sign flipped
   uint32_t dbl[5];
+#pragma unroll
   for (int j = 4; j > 0; j--) dbl[j] = (rem[j] << 1) | (rem[j - 1] >> 31);
   dbl[0] = rem[0] << 1;
   bool negr = false;
-  if (!limbs_geq(XX, dbl, 5)) {
+  if (!limbs_geq<5>(XX, dbl)) {
     uint32_t x2[5];
+#pragma unroll
     for (int j = 0; j < 5; j++) x2[j] = XX[j];
-    limbs_sub(x2, rem, 5);
+    limbs_sub<5>(x2, rem);
+#pragma unroll
     for (int j = 0; j < 5; j++) rem[j] = x2[j];
-    uint32_t c = 1; for (int j = 0; j < 5 && c; j++) { q[j] += c; c = (q[j] == 0); }
+    limbs_inc<5>(q);
     negr = true;
   }
+#pragma unroll
   for (int j = 0; j < 8; j++) { out.k1.v[j] = j < 4 ? rem[j] : 0u; out.k2.v[j] = j < 4 ? q[j] : 0u; }
   out.neg1 = neg != negr;
   out.neg2 = neg;

@@ -104,7 +104,7 @@ size_t msm_scratch_bytes(size_t n, const MsmPlan& pl, int force_L) {
   b += pad256(n * (size_t)pl.W * 4);              // entries
   b += pad256(total * sizeof(Xyzz<F>));           // buckets
   b += pad256((size_t)pl.W * T * sizeof(Xyzz<F>));  // partials
-  b += pad256((size_t)pl.W * sizeof(Xyzz<F>));    // window sums
+  b += pad256((size_t)pl.W * (1 + 128) * sizeof(Xyzz<F>));    // window sums + their sub-block partials
   size_t smax = (n * (size_t)pl.W) / (size_t)slice_len(n, pl, force_L) + 2;
   b += pad256(2 * smax * sizeof(Xyzz<F>));        // slice partials (worst case: smallest automatic L)
   b += pad256((total + 1) * 4) + pad256(4096);    // big-bucket list, block sums
@@ -133,6 +133,11 @@ int msm_enqueue(b2k_ctx* ctx, size_t n_in, const MsmPlan& pl, const uint8_t* d_s
   auto* buckets = arena_take<Xyzz<F>>(ctx, total);
   auto* partials = arena_take<Xyzz<F>>(ctx, (size_t)pl.W * T);
   auto* wsum = arena_take<Xyzz<F>>(ctx, pl.W);
+  // window sum in two levels when a window has many chunk partials: S sub-blocks of >= 512 partials each
+  int S = T >= 1024 ? T / 512 : 1;
+  if (S > 128) S = 128;
+  auto* wpart = arena_take<Xyzz<F>>(ctx, (size_t)pl.W * 128);
+  if (!wpart) { ctx->err = "scratch arena too small"; return B2K_ERR_ARG; }
   if (!pts || !counts || !offs || !cursor || !entries || !buckets || !partials || !wsum) {
     ctx->err = "scratch arena too small";
     return B2K_ERR_ARG;
@@ -220,7 +225,12 @@ int msm_enqueue(b2k_ctx* ctx, size_t n_in, const MsmPlan& pl, const uint8_t* d_s
   size_t nchunks = (size_t)pl.W * T;
   k_msm_reduce_chunks<CV><<<(unsigned)((nchunks + 127) / 128), 128, 0, st>>>(pl, buckets, partials); nl++;
   CK(cudaEventRecord(ctx->ev[6], st));
-  k_msm_window_sum<CV><<<pl.W, 128, 0, st>>>(T, partials, wsum); nl++;
+  if (S > 1) {
+    k_msm_window_sum<CV><<<pl.W * S, 128, 0, st>>>(T / S, partials, wpart);      // (w, s) -> wpart[w S + s]
+    k_msm_window_sum<CV><<<pl.W, 128, 0, st>>>(S, wpart, wsum); nl += 2;
+  } else {
+    k_msm_window_sum<CV><<<pl.W, 128, 0, st>>>(T, partials, wsum); nl++;
+  }
   CK(cudaEventRecord(ctx->ev[7], st));
   k_msm_final<CV><<<1, 128, 0, st>>>(pl, wsum, d_out, affine_out); nl++;
   CK(cudaEventRecord(ctx->ev[8], st));
