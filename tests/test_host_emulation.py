@@ -207,3 +207,4 @@ def test_bn_hash_to_g1_bodies_against_reference_vectors():
     for m in (bdn_msg, b"", b"x" * 200, bytes(range(64))):
         lib.emul_bn256_hash_to_g1(m, len(m), out64)
         assert out64.raw == o6.g1_marshal(o6.hash_to_g1(m))
+
