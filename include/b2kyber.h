@@ -122,6 +122,15 @@ int b2k_bls12381_g2_msm_dev(b2k_ctx* ctx, size_t n, const void* d_scalars, const
 /* MSM with the sum in OPERAND form (G1 96 B / G2 192 B), host buffers: what the adapter's Point.Add / Sub use
  * (unit scalars) so that results stay in operand form between operations. */
 int b2k_bls12381_g1_msm_affine(b2k_ctx* ctx, size_t n, const uint8_t* scalars, const uint8_t* points, uint8_t* out /*[96]*/);
+/* Asynchronous form of b2k_bls12381_g1_msm: the H2D copies, the MSM and the D2H copy of the result are ENQUEUED on the
+ * context's stream and the call returns.  scalars, points and out must stay valid until b2k_wait(ctx) returns (and should
+ * be page-locked, otherwise the copies do not overlap anything).  b2k_wait blocks until everything enqueued on the
+ * context is done and returns the deferred status of the last MSM (B2K_ERR_SCALAR_RANGE ...).  Two contexts used
+ * alternately (async on A, async on B, wait A, async on A, ...) keep the PCIe copies of one batch under the kernels
+ * of the other: this is how a caller with a stream of batches (goroutines verifying aggregates, share/poly recoveries)
+ * should drive the library; the blocking form is this followed by b2k_wait. */
+int b2k_bls12381_g1_msm_async(b2k_ctx* ctx, size_t n, const uint8_t* scalars, const uint8_t* points, uint8_t* out);
+int b2k_wait(b2k_ctx* ctx);
 int b2k_bls12381_g2_msm_affine(b2k_ctx* ctx, size_t n, const uint8_t* scalars, const uint8_t* points, uint8_t* out /*[192]*/);
 
 /* ---- BLS12-381 UnmarshalBinary (decompress + subgroup check) --------------------------------------------- */

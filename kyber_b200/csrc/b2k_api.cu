@@ -182,6 +182,8 @@ int b2k_bls12381_g1_mul_batch_dev(b2k_ctx* c, size_t n, const void* s, const voi
 int b2k_bls12381_g1_mul_batch_affine_dev(b2k_ctx* c, size_t n, const void* s, const void* p, void* o) { return mul_batch_dev<Bls381G1, true>(c, n, s, p, o); }
 int b2k_bls12381_g1_msm(b2k_ctx* c, size_t n, const uint8_t* s, const uint8_t* p, uint8_t* o) { return msm_host<Bls381G1>(c, n, s, p, o); }
 int b2k_bls12381_g1_msm_affine(b2k_ctx* c, size_t n, const uint8_t* s, const uint8_t* p, uint8_t* o) { return msm_host<Bls381G1>(c, n, s, p, o, 1); }
+int b2k_bls12381_g1_msm_async(b2k_ctx* c, size_t n, const uint8_t* s, const uint8_t* p, uint8_t* o) { return msm_host<Bls381G1>(c, n, s, p, o, 0, false); }
+int b2k_wait(b2k_ctx* c) { return msm_wait(c); }
 int b2k_bls12381_g1_msm_dev(b2k_ctx* c, size_t n, const void* s, const void* p, void* o) { return msm_dev<Bls381G1>(c, n, s, p, o); }
 int b2k_bls12381_g1_msm_affine_dev(b2k_ctx* c, size_t n, const void* s, const void* p, void* o) { return msm_dev<Bls381G1>(c, n, s, p, o, 1); }
 

@@ -254,8 +254,11 @@ int msm_dev(b2k_ctx* ctx, size_t n, const void* d_scalars, const void* d_points,
   return msm_enqueue<CV>(ctx, n, pl, (const uint8_t*)d_scalars, (const uint8_t*)d_points, (uint8_t*)d_out, affine_out);
 }
 
+// Host-buffer MSM.  wait = false: everything (H2D copies, pipeline, D2H of the result and of the status word) is only
+// ENQUEUED on the context's stream; the caller collects the status with msm_wait() (b2k_wait).  With page-locked host
+// buffers the copies of one context overlap the kernels of another: two contexts alternate to keep PCIe and the SMs busy.
 template <class CV>
-int msm_host(b2k_ctx* ctx, size_t n, const uint8_t* scalars, const uint8_t* points, uint8_t* out, int affine_out = 0) {
+int msm_host(b2k_ctx* ctx, size_t n, const uint8_t* scalars, const uint8_t* points, uint8_t* out, int affine_out = 0, bool wait = true) {
   if (!ctx || !scalars || !points || !out || n == 0 || n >= (size_t(1) << 31)) {
     if (ctx) ctx->err = "bad argument";
     return B2K_ERR_ARG;
@@ -275,6 +278,14 @@ int msm_host(b2k_ctx* ctx, size_t n, const uint8_t* scalars, const uint8_t* poin
   if (rc) return rc;
   CK(cudaMemcpyAsync(out, d_o, affine_out ? CV::IN_BYTES : CV::OUT_BYTES, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaMemcpyAsync(ctx->h_flags, ctx->d_flags, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  if (!wait) return B2K_OK;
+  CK(cudaStreamSynchronize(ctx->stream));
+  return check_flags(ctx);
+}
+
+inline int msm_wait(b2k_ctx* ctx) {
+  if (!ctx) return B2K_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
   CK(cudaStreamSynchronize(ctx->stream));
   return check_flags(ctx);
 }

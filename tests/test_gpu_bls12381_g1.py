@@ -164,3 +164,37 @@ def test_msm_endomorphism_split_on_and_off_agree(engine, dist_name):
                 engine.set_msm_glv(True)
                 engine.set_msm_window(0)
             assert got == want, (dist_name, glv, c)
+
+
+def test_msm_async_two_contexts_and_deferred_status(engine):
+    """b2k_bls12381_g1_msm_async + b2k_wait: two contexts driven alternately by one thread give the oracle's bytes for
+    every submitted batch; an out-of-range scalar surfaces at b2k_wait (as B2K_ERR_SCALAR_RANGE), not at submission."""
+    import ctypes
+    from kyber_b200.capi import Engine, B2KError
+    other = Engine(0)
+    engs = [engine, other]
+    n = 1500
+    a = wl.prng_scalars("b2k/test-a", n, o.R)
+    pts = engine.bls12381_g1_mul_batch_affine(wl.scalars_to_bytes(a), wl.G1_BLS12381_AFFINE * n)
+    batches, outs, wants = [], [], []
+    for k in range(5):
+        s = wl.prng_scalars("b2k/test-async-%d" % k, n, o.R)
+        batches.append(ctypes.create_string_buffer(wl.scalars_to_bytes(s), 32 * n))
+        outs.append(ctypes.create_string_buffer(48))
+        wants.append(o.g1_compress(o.g1_mul(wl.dot_mod(s, a, o.R))))
+    pbuf = ctypes.create_string_buffer(pts, 96 * n)
+    for k in range(5):
+        e = engs[k % 2]
+        if k >= 2:
+            e._check(e.lib.b2k_wait(e.h))
+            assert outs[k - 2].raw == wants[k - 2]
+        e._check(e.lib.b2k_bls12381_g1_msm_async(e.h, n, batches[k], pbuf, outs[k]))
+    for k in (3, 4):
+        e = engs[k % 2]
+        e._check(e.lib.b2k_wait(e.h))
+        assert outs[k].raw == wants[k]
+    bad = ctypes.create_string_buffer(o.R.to_bytes(32, "big") + bytes(32 * (n - 1)), 32 * n)
+    engine._check(engine.lib.b2k_bls12381_g1_msm_async(engine.h, n, bad, pbuf, outs[0]))      # accepted ...
+    with pytest.raises(B2KError) as ei:
+        engine._check(engine.lib.b2k_wait(engine.h))                                           # ... reported here
+    assert ei.value.code == -3

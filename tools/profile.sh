@@ -12,7 +12,10 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
 # the top kernel, once
 ncu --set full --clock-control none --import-source on -k regex:k_msm_accumulate_slices -s 3 -c 1 \
     -o gpurun_out/accumulate_${TAG} -f python bench.py --steps 1 --warmup 3 > gpurun_out/ncu_full_${TAG}.log 2>&1
-ls -la gpurun_out
+# gpurun_out/ travels back only below 64 MiB: keep the text pages, drop the report
+ncu -i gpurun_out/accumulate_${TAG}.ncu-rep --page details > gpurun_out/${TAG}_accumulate_ncu_details.txt 2>&1
+ncu -i gpurun_out/accumulate_${TAG}.ncu-rep --page raw --csv > gpurun_out/${TAG}_accumulate_ncu_raw.csv 2>&1
+rm -f gpurun_out/accumulate_${TAG}.ncu-rep
 # pairing kernel: one full capture on a small batch (the kernel is long: keep n small)
 cat > /tmp/pair_probe.py <<'PY'
 import sys
@@ -29,4 +32,7 @@ eng.synchronize(); print(int(ok.sum()))
 PY
 ncu --set full --clock-control none --import-source on -k regex:k_bls_pairing_check -c 1 \
     -o gpurun_out/pairing_check_${TAG} -f python /tmp/pair_probe.py > gpurun_out/ncu_pairing_${TAG}.log 2>&1
+ncu -i gpurun_out/pairing_check_${TAG}.ncu-rep --page details > gpurun_out/${TAG}_pairing_check_ncu_details.txt 2>&1
+ncu -i gpurun_out/pairing_check_${TAG}.ncu-rep --page raw --csv > gpurun_out/${TAG}_pairing_check_ncu_raw.csv 2>&1
+rm -f gpurun_out/pairing_check_${TAG}.ncu-rep
 ls -la gpurun_out
