@@ -279,6 +279,8 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the one JSON line (NCCL prints its version banner there)
         dist.init_process_group("nccl", device_id=dev)
 
     n = 1 << LOG_N
@@ -398,12 +400,12 @@ def run_ours(args):
     e1.record(stream)
     barrier()
     e2e_blocking_ms = e0.elapsed_time(e1) / min(args.steps, 5)
-    # (b) the asynchronous entry point on two contexts used alternately by ONE host thread: submit step k on context k % 2
-    #     (H2D of scalars+points, MSM, D2H of the result, all enqueued), collect step k-2 first.  The copies of one step run
+    # (b) the asynchronous entry point on NE contexts used in turn by ONE host thread: submit step k on context k % NE
+    #     (H2D of scalars+points, MSM, D2H of the result, all enqueued), collect step k-NE first.  The copies of one step run
     #     under the kernels of the other.  Every step still moves its 128 MiB host->device and its result device->host
     #     inside the timed region.  Timed on the device: start event at the head of context 0's stream, end events behind
     #     the last enqueued work of each context.
-    NE = min(2, NC)
+    NE = max(1, min(int(os.environ.get("B2K_E2E_INFLIGHT", "3")), NC))
     e2e_status = []
 
     def e2e_submit(k: int):
@@ -478,7 +480,7 @@ def run_ours(args):
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * 128, "d2h_bytes_per_step": 52,
                         "ms_per_step": e2e_ms / args.steps, "callers": 1, "steps_in_flight": NE,
                         "blocking_ms_per_step": e2e_blocking_ms,
-                        "note": "b2k_bls12381_g1_msm_async + b2k_wait on 2 contexts used alternately by one host thread "
+                        "note": f"b2k_bls12381_g1_msm_async + b2k_wait on {NE} contexts used in turn by one host thread "
                                 "(pinned host buffers; H2D of all inputs and D2H of the result inside the timed region every "
                                 "step; per-rank local MSM); blocking_ms_per_step = the blocking b2k_bls12381_g1_msm back to back"},
                 "gpu_launches": int(launches),
