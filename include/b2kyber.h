@@ -56,7 +56,8 @@ int b2k_synchronize(b2k_ctx* ctx);
 /* Device-side durations (ms, CUDA events on the context's stream) of the stages of the LAST MSM call:
  * [0] load/convert points  [1] digits+histogram  [2] scan  [3] scatter  [4] bucket accumulate
  * [5] chunk reduce  [6] window sum  [7] final (Horner + encode)  [8] whole pipeline
- * [9] fix-up of buckets cut by slice boundaries ([4] is the accumulate kernel alone).
+ * [9] fix-up of buckets cut by slice boundaries ([4] is the accumulate pass alone: affine rounds + XYZZ slices)
+ * [10] the affine pair-tree rounds inside [4] (0 when they are off).
  * Returns the number of entries written (<= max). Synchronises the stream. */
 int b2k_last_timings(b2k_ctx* ctx, float* ms, int max);
 /* Override the MSM window size (0 = automatic).  Testing / tuning aid. */
@@ -73,6 +74,11 @@ int b2k_set_msm_groups(b2k_ctx* ctx, int groups);
 /* BLS12-381 G1 MSM front end: 1 (default) = split every scalar with the curve endomorphism (k P = k1 P + k2 (-phi P),
  * 127-bit k1, k2: half the windows), 0 = plain 255-bit pipeline.  Same results; kept switchable for A/B timing. */
 int b2k_set_msm_glv(b2k_ctx* ctx, int on);
+/* Affine pair-tree rounds in front of the XYZZ bucket slices (BLS12-381 G1 MSM): every round replaces the operands of
+ * each bucket by the sums of neighbouring pairs, computed as batched AFFINE additions (6 field products each instead of
+ * 10) around one inversion per thread.  rounds: -1 = automatic (default), 0 = off, 1..8; batch: additions per thread
+ * (8..64, 0 = automatic).  Same result bytes either way; kept switchable for A/B timing. */
+int b2k_set_msm_affine(b2k_ctx* ctx, int rounds, int batch);
 /* Resident bucket-accumulate blocks per SM (4..6; launch bound => register cap).  Tuning aid. */
 int b2k_set_msm_occupancy(b2k_ctx* ctx, int blocks_per_sm);
 /* Buckets per thread in the chunked bucket reduction (power of two, 0 = automatic).  Tuning aid. */
@@ -225,6 +231,22 @@ int b2k_bls12381_g1_pubpoly_eval(b2k_ctx* ctx, size_t t, const uint8_t* commits 
                                  const uint32_t* indices /*[n]*/, uint8_t* out /*[n][96]*/);
 int b2k_bls12381_g2_pubpoly_eval(b2k_ctx* ctx, size_t t, const uint8_t* commits /*[t][192]*/, size_t n,
                                  const uint32_t* indices /*[n]*/, uint8_t* out /*[n][192]*/);
+
+/* ---- share.PubPoly.Check over a batch of deals: the verification loops of share/vss and share/dkg ---------------------
+ * For dealer d (m of them) with commitments commits[d][0..t) and private shares (indices[d][k], shares[d][k]), k < n:
+ *     ok[d][k] = ( sum_j (indices[d][k] + 1)^j commits[d][j]  ==  shares[d][k] * B ),   B = the group's base point.
+ * One thread per (d, k): Horner evaluation, base-point multiplication and a projective comparison on the device.
+ * shares: 32-byte big-endian scalars; a share not below the group order gives ok = 0 (the reference drops such a deal
+ * at UnmarshalBinary).  commits in operand form ([96] / [192] / [64] bytes), ok: one byte per check.
+ * replaces: PubPoly.Check (share/poly.go:405-409) = Eval + Mul + Equal, run once per received deal / response /
+ * justification in share/vss/pedersen/vss.go:636-645 and share/dkg/pedersen/dkg.go:489-494, 826-834, 965 -- an
+ * n x n x t scalar-multiplication workload at key generation / resharing time, sequential in the reference. */
+int b2k_bls12381_g1_pubpoly_check(b2k_ctx* ctx, size_t m, size_t t, const uint8_t* commits /*[m][t][96]*/, size_t n,
+                                  const uint32_t* indices /*[m][n]*/, const uint8_t* shares /*[m][n][32]*/, uint8_t* ok /*[m][n]*/);
+int b2k_bls12381_g2_pubpoly_check(b2k_ctx* ctx, size_t m, size_t t, const uint8_t* commits /*[m][t][192]*/, size_t n,
+                                  const uint32_t* indices /*[m][n]*/, const uint8_t* shares /*[m][n][32]*/, uint8_t* ok /*[m][n]*/);
+int b2k_bn254_pubpoly_check(b2k_ctx* ctx, size_t m, size_t t, const uint8_t* commits /*[m][t][64]*/, size_t n,
+                            const uint32_t* indices /*[m][n]*/, const uint8_t* shares /*[m][n][32]*/, uint8_t* ok /*[m][n]*/);
 
 /* ---- bn254 G2 and pairing --------------------------------------------------------------------------------- */
 /* G2 operands/results: 128 B x.imag||x.real||y.imag||y.real, infinity all-zero (pairing/bn254/point.go:428-455).

@@ -42,6 +42,7 @@ def load_library() -> C.CDLL:
         "b2k_set_msm_groups": (C.c_int, [vp, C.c_int]),
         "b2k_set_msm_occupancy": (C.c_int, [vp, C.c_int]),
         "b2k_set_msm_chunk": (C.c_int, [vp, C.c_int]),
+        "b2k_set_msm_affine": (C.c_int, [vp, C.c_int, C.c_int]),
     }
     sigs["b2k_bls12381_pair"] = (C.c_int, [vp, sz, vp, vp, vp])
     sigs["b2k_bls12381_pair_dev"] = (C.c_int, [vp, sz, vp, vp, vp])
@@ -62,6 +63,8 @@ def load_library() -> C.CDLL:
     sigs["b2k_bls12381_g2_recover_commit"] = (C.c_int, [vp, sz, vp, vp, vp])
     sigs["b2k_bls12381_g1_pubpoly_eval"] = (C.c_int, [vp, sz, vp, sz, vp, vp])
     sigs["b2k_bls12381_g2_pubpoly_eval"] = (C.c_int, [vp, sz, vp, sz, vp, vp])
+    for nm in ("b2k_bls12381_g1_pubpoly_check", "b2k_bls12381_g2_pubpoly_check", "b2k_bn254_pubpoly_check"):
+        sigs[nm] = (C.c_int, [vp, sz, sz, vp, sz, vp, vp, vp])
     host3 = (C.c_int, [vp, sz, vp, vp, vp])
     for name in HOST_FUNCS + DEV_FUNCS:
         sigs[name] = host3
@@ -159,6 +162,10 @@ class Engine:
     def set_msm_glv(self, on: bool):
         """BLS12-381 G1 MSM: endomorphism split on (default) / off (plain 255-bit pipeline)"""
         self._check(self.lib.b2k_set_msm_glv(self.h, int(on)))
+
+    def set_msm_affine(self, rounds: int = -1, batch: int = 0):
+        """affine pair-tree rounds of the BLS12-381 G1 MSM: -1 automatic, 0 off, 1..8 forced; batch = additions per thread"""
+        self._check(self.lib.b2k_set_msm_affine(self.h, int(rounds), int(batch)))
 
     def last_timings(self):
         arr = (C.c_float * 16)()
@@ -392,6 +399,21 @@ class Engine:
         out = bytearray(plen * n)
         bufs = [_buf(x) for x in (commits, struct.pack("<%dI" % n, *indices), out)]
         self._check(getattr(self.lib, f"b2k_bls12381_g{group}_pubpoly_eval")(self.h, t, bufs[0][0], n, bufs[1][0], bufs[2][0]))
+        return bytes(out)
+
+    def pubpoly_check(self, curve: str, commits: bytes, t: int, indices, shares: bytes) -> bytes:
+        """PubPoly.Check for m dealers x n shares (share/poly.go:405-409, the DKG/VSS verification loops): curve in
+        {"bls12381_g1", "bls12381_g2", "bn254"}; commits [m][t][96|192|64], indices m rows of n, shares [m][n][32] BE
+        -> m*n bytes (1 = the share matches the dealer's commitments)"""
+        import struct
+        plen = {"bls12381_g1": 96, "bls12381_g2": 192, "bn254": 64}[curve]
+        m = len(commits) // (plen * t)
+        flat = [i for row in indices for i in row]
+        n = len(flat) // m
+        assert len(commits) == m * t * plen and len(flat) == m * n and len(shares) == 32 * m * n
+        out = bytearray(m * n)
+        bufs = [_buf(x) for x in (commits, struct.pack("<%dI" % (m * n), *flat), shares, out)]
+        self._check(getattr(self.lib, f"b2k_{curve}_pubpoly_check")(self.h, m, t, bufs[0][0], n, bufs[1][0], bufs[2][0], bufs[3][0]))
         return bytes(out)
 
     def bn254_g1_msm(self, scalars: bytes, points: bytes) -> bytes:

@@ -129,7 +129,15 @@ int b2k_last_timings(b2k_ctx* ctx, float* ms, int max) {
   }
   if (n < max) { CK(cudaEventElapsedTime(&ms[8], ctx->ev[0], ctx->ev[8])); n++; }
   if (n < max) { CK(cudaEventElapsedTime(&ms[9], ctx->ev[9], ctx->ev[5])); n++; }
+  if (n < max) { CK(cudaEventElapsedTime(&ms[10], ctx->ev[4], ctx->ev[10])); n++; }
   return n;
+}
+
+int b2k_set_msm_affine(b2k_ctx* ctx, int rounds, int batch) {
+  if (!ctx || rounds < -1 || rounds > 8 || batch < 0 || batch > 64) return B2K_ERR_ARG;
+  ctx->affine_rounds = rounds;
+  ctx->affine_batch = batch;
+  return B2K_OK;
 }
 
 int b2k_set_msm_window(b2k_ctx* ctx, int c) {

@@ -29,6 +29,8 @@ struct b2k_ctx {
   cudaEvent_t gev[10];              // group hand-over events
   int msm_groups = 1;               // window groups of the overlapped MSM tail; measured SLOWER than the serial pipeline on
                                     // B200 (accumulate blocks fill the register file, nothing co-resides): kept as an experiment
+  int affine_rounds = -1;           // affine pair-tree rounds before the XYZZ slices: -1 = automatic, 0 = off (A/B), 1..8 forced
+  int affine_batch = 0;             // outputs (batched affine additions) per thread of a round, 8..64; 0 = automatic
   int acc_minb = 4;                 // resident accumulate blocks per SM (launch bound), tuning aid
   int pair_variant = 0; // launch-bound variant of the pairing kernels (tuning aid)
   uint64_t launches = 0;

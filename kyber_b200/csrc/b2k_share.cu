@@ -74,6 +74,61 @@ __global__ void __launch_bounds__(128) k_pubpoly_eval(uint32_t t, const Affine<t
   CV::store_affine(out + (size_t)CV::IN_BYTES * i, a);
 }
 
+// PubPoly.Check for a batch of dealers (share/poly.go:405-409 as run once per received deal by
+// share/vss/pedersen/vss.go:636-645 and share/dkg/pedersen/dkg.go:489-494, 826-834): thread (d, k) evaluates dealer d's
+// commitment polynomial at idx[d][k] + 1 by Horner, multiplies the base point by the private share and compares the two
+// results projectively (no inversion).  A share that is not below the group order fails its check (the reference drops
+// such a deal when UnmarshalBinary errors, dkg.go:484-487).
+template <class CV>
+__global__ void __launch_bounds__(128) k_pubpoly_check(uint32_t m, uint32_t t, const Affine<typename CV::F>* __restrict__ commits,
+                                                       uint32_t n, const uint32_t* __restrict__ idx,
+                                                       const uint8_t* __restrict__ shares, uint8_t* __restrict__ ok, int use_glv) {
+  using F = typename CV::F;
+  size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (id >= (size_t)m * n) return;
+  const uint32_t d = (uint32_t)(id / n);
+  const uint64_t x = (uint64_t)idx[id] + 1u;
+  int top = 63;
+  while (top > 0 && !((x >> top) & 1)) top--;
+  Jac<F> v;
+  jac_set_inf(v);
+  const Affine<F>* cm = commits + (size_t)d * t;
+  for (int j = (int)t - 1; j >= 0; j--) {
+    Jac<F> acc = v;
+    for (int b = top - 1; b >= 0; b--) {
+      jac_dbl(acc, acc);
+      if ((x >> b) & 1) jac_add(acc, acc, v);
+    }
+    Affine<F> c = cm[j];
+    jac_madd(v, acc, c);
+  }
+  Scalar256 k;
+  scalar_load_be(k, shares + 32 * id);
+  if (!scalar_in_range<typename CV::ScalarField>(k)) { ok[id] = 0; return; }
+  Affine<F> g;
+  CV::generator(g);
+  Jac<F> w;
+  if constexpr (MulGlv<CV>::enabled) {
+    if (use_glv) scalar_mul_glv_bls381(w, k, g, InvBingcd{});
+    else scalar_mul<CV>(w, k, g);
+  } else {
+    scalar_mul<CV>(w, k, g);
+  }
+  // v == w  <=>  both infinite, or X_v Z_w^2 == X_w Z_v^2 and Y_v Z_w^3 == Y_w Z_v^3
+  bool same;
+  if (jac_is_inf(v) || jac_is_inf(w)) same = jac_is_inf(v) && jac_is_inf(w);
+  else {
+    F zv2, zw2, a, b;
+    f_sqr(zv2, v.Z); f_sqr(zw2, w.Z);
+    f_mul(a, v.X, zw2); f_mul(b, w.X, zv2);
+    same = f_eq(a, b);
+    f_mul(zv2, zv2, v.Z); f_mul(zw2, zw2, w.Z);
+    f_mul(a, v.Y, zw2); f_mul(b, w.Y, zv2);
+    same = same && f_eq(a, b);
+  }
+  ok[id] = same ? 1 : 0;
+}
+
 }  // namespace b2k
 
 template <class CV, class FR>
@@ -82,7 +137,7 @@ static int recover_commit(b2k_ctx* ctx, size_t t, const uint32_t* indices, const
   CK(cudaSetDevice(ctx->device));
   MsmPlan pl = msm_plan<CV>(ctx, t);
   size_t extra = pad256(t * 4) + pad256(t * 32) + pad256(t * (size_t)CV::IN_BYTES) + 1024;
-  int rc = arena_reserve(ctx, msm_scratch_bytes<CV>(msm_virtual_n<CV>(ctx, t), pl, ctx->force_L) + extra);
+  int rc = arena_reserve(ctx, msm_scratch_bytes<CV>(ctx, msm_virtual_n<CV>(ctx, t), pl) + extra);
   if (rc) return rc;
   uint32_t* d_idx = arena_take<uint32_t>(ctx, t);
   uint8_t* d_s = arena_take<uint8_t>(ctx, t * 32);
@@ -127,8 +182,40 @@ static int pubpoly_eval(b2k_ctx* ctx, size_t t, const uint8_t* commits, size_t n
   return B2K_OK;
 }
 
+template <class CV>
+static int pubpoly_check(b2k_ctx* ctx, size_t m, size_t t, const uint8_t* commits, size_t n, const uint32_t* indices,
+                         const uint8_t* shares, uint8_t* ok) {
+  using F = typename CV::F;
+  if (!ctx || !commits || !indices || !shares || !ok || m == 0 || t == 0 || n == 0 || m * t >= (size_t(1) << 31) ||
+      m * n >= (size_t(1) << 31)) return B2K_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  const size_t mt = m * t, mn = m * n;
+  int rc = arena_reserve(ctx, pad256(mt * (size_t)CV::IN_BYTES) + pad256(mt * sizeof(Affine<F>)) + pad256(mn * 4) +
+                                  pad256(mn * 32) + pad256(mn) + 4096);
+  if (rc) return rc;
+  uint8_t* d_c = arena_take<uint8_t>(ctx, mt * (size_t)CV::IN_BYTES);
+  auto* d_cm = arena_take<Affine<F>>(ctx, mt);
+  uint32_t* d_idx = arena_take<uint32_t>(ctx, mn);
+  uint8_t* d_s = arena_take<uint8_t>(ctx, mn * 32);
+  uint8_t* d_ok = arena_take<uint8_t>(ctx, mn);
+  cudaStream_t st = ctx->stream;
+  CK(cudaMemcpyAsync(d_c, commits, mt * (size_t)CV::IN_BYTES, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(d_idx, indices, mn * 4, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(d_s, shares, mn * 32, cudaMemcpyHostToDevice, st));
+  k_load_points<CV><<<(unsigned)((mt + 255) / 256), 256, 0, st>>>(mt, d_c, d_cm);
+  k_pubpoly_check<CV><<<(unsigned)((mn + 127) / 128), 128, 0, st>>>((uint32_t)m, (uint32_t)t, d_cm, (uint32_t)n, d_idx, d_s, d_ok, ctx->use_glv);
+  CK(cudaGetLastError());
+  ctx->launches += 2;
+  CK(cudaMemcpyAsync(ok, d_ok, mn, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return B2K_OK;
+}
+
 extern "C" {
 
+int b2k_bls12381_g1_pubpoly_check(b2k_ctx* c, size_t m, size_t t, const uint8_t* commits, size_t n, const uint32_t* idx, const uint8_t* shares, uint8_t* ok) { return pubpoly_check<Bls381G1>(c, m, t, commits, n, idx, shares, ok); }
+int b2k_bls12381_g2_pubpoly_check(b2k_ctx* c, size_t m, size_t t, const uint8_t* commits, size_t n, const uint32_t* idx, const uint8_t* shares, uint8_t* ok) { return pubpoly_check<Bls381G2>(c, m, t, commits, n, idx, shares, ok); }
+int b2k_bn254_pubpoly_check(b2k_ctx* c, size_t m, size_t t, const uint8_t* commits, size_t n, const uint32_t* idx, const uint8_t* shares, uint8_t* ok) { return pubpoly_check<Bn254G1>(c, m, t, commits, n, idx, shares, ok); }
 int b2k_bn254_recover_commit(b2k_ctx* c, size_t t, const uint32_t* idx, const uint8_t* pts, uint8_t* out) { return recover_commit<Bn254G1, Bn254Fr>(c, t, idx, pts, out); }
 int b2k_bls12381_g1_recover_commit(b2k_ctx* c, size_t t, const uint32_t* idx, const uint8_t* pts, uint8_t* out) { return recover_commit<Bls381G1, Bls381Fr>(c, t, idx, pts, out); }
 int b2k_bls12381_g2_recover_commit(b2k_ctx* c, size_t t, const uint32_t* idx, const uint8_t* pts, uint8_t* out) { return recover_commit<Bls381G2, Bls381Fr>(c, t, idx, pts, out); }

@@ -52,6 +52,13 @@ struct Bls381G2 {
     fp_from_mont(t, p.y.c1); fp_store_be(out + 96, t);
     fp_from_mont(t, p.y.c0); fp_store_be(out + 144, t);
   }
+  B2K_D static void generator(Affine<F>& g) {
+#pragma unroll
+    for (int j = 0; j < 12; j++) {
+      g.x.c0.v[j] = Bls381Fp::g2x0(j); g.x.c1.v[j] = Bls381Fp::g2x1(j);
+      g.y.c0.v[j] = Bls381Fp::g2y0(j); g.y.c1.v[j] = Bls381Fp::g2y1(j);
+    }
+  }
 };
 
 // ---- multiplication by |x| = 0xd201000000010000 (64-bit, weight 6) -------------------------------------

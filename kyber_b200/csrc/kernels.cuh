@@ -2,6 +2,7 @@
 #pragma once
 #include "msm.cuh"
 #include "fp_inv.cuh"
+#include "msm_affine.cuh"
 
 namespace b2k {
 
@@ -52,21 +53,44 @@ static __global__ void __launch_bounds__(256) k_glv_prepare_bls381(size_t n, con
 }
 
 // ---- independent scalar multiplications ----------------------------------------------------------
+// warp-wide inversions go through the branch-free binary GCD (fp_inv.cuh): every lane inverts at the same time
+struct InvBingcd { template <class F> B2K_D void operator()(F& r, const F& a) const { f_inv_bg(r, a); } };
+template <class F>
+B2K_D void jac_to_affine_bg(Affine<F>& r, const Jac<F>& p) {
+  if (jac_is_inf(p)) { aff_set_inf(r); return; }
+  F zi, zi2;
+  f_inv_bg(zi, p.Z);
+  f_sqr(zi2, zi);
+  f_mul(r.x, p.X, zi2);
+  f_mul(zi2, zi2, zi);
+  f_mul(r.y, p.Y, zi2);
+}
+template <class CV> struct MulGlv { static constexpr bool enabled = false; };
+template <> struct MulGlv<Bls381G1> { static constexpr bool enabled = true; };
+
 template <class CV, bool AFFINE_OUT>
 __global__ void __launch_bounds__(128) k_mul_batch(size_t n, const uint8_t* __restrict__ scalars,
                                                    const uint8_t* __restrict__ wire, uint8_t* __restrict__ out,
-                                                   uint32_t* flags) {
+                                                   uint32_t* flags, int use_glv) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   Scalar256 k;
   scalar_load_be(k, scalars + 32 * i);
-  if (!scalar_in_range<typename CV::ScalarField>(k)) atomicOr(flags, FLAG_SCALAR_RANGE);
+  if (!scalar_in_range<typename CV::ScalarField>(k)) {
+    atomicOr(flags, FLAG_SCALAR_RANGE);
+    for (int j = 0; j < 8; j++) k.v[j] = 0;
+  }
   Affine<typename CV::F> p;
   CV::load(p, wire + (size_t)CV::IN_BYTES * i);
   Jac<typename CV::F> r;
-  scalar_mul<CV>(r, k, p);
+  if constexpr (MulGlv<CV>::enabled) {
+    if (use_glv) scalar_mul_glv_bls381(r, k, p, InvBingcd{});
+    else scalar_mul<CV>(r, k, p);
+  } else {
+    scalar_mul<CV>(r, k, p);
+  }
   Affine<typename CV::F> a;
-  jac_to_affine(a, r);
+  jac_to_affine_bg(a, r);
   if (AFFINE_OUT) CV::store_affine(out + (size_t)CV::IN_BYTES * i, a);
   else CV::store(out + (size_t)CV::OUT_BYTES * i, a);
 }
@@ -187,6 +211,37 @@ __global__ void __launch_bounds__(128, MINB) k_msm_accumulate_slices(uint32_t ns
   uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= nslices) return;
   msm_accumulate_slice<CV>(j, L, total, pts, offs, entries, buckets, spart);
+}
+
+// same over the output of the affine pair-tree rounds (the operands themselves, already sorted by bucket)
+template <class CV, int MINB>
+__global__ void __launch_bounds__(128, MINB) k_msm_accumulate_slices_direct(uint32_t nslices, uint32_t L, uint32_t total,
+                                                                      const Affine<typename CV::F>* __restrict__ pts,
+                                                                      const uint32_t* __restrict__ offs,
+                                                                      Xyzz<typename CV::F>* __restrict__ buckets,
+                                                                      Xyzz<typename CV::F>* __restrict__ spart) {
+  uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= nslices) return;
+  msm_accumulate_slice<CV, true>(j, L, total, pts, offs, nullptr, buckets, spart);
+}
+
+// ---- MSM stage 4a: affine pair-tree rounds (msm_affine.cuh) ---------------------------------------------------
+// operand count of every bucket after one round
+static __global__ void __launch_bounds__(256) k_pt_counts(uint32_t total, const uint32_t* __restrict__ offs_in,
+                                                          uint32_t* __restrict__ counts) {
+  uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g < total) counts[g] = (offs_in[g + 1] - offs_in[g] + 1u) >> 1;
+}
+// one thread = B consecutive outputs: B batched affine additions around one inversion
+template <class CV, bool FIRST>
+__global__ void __launch_bounds__(128, 4) k_msm_pairtree_round(uint32_t B, uint32_t total,
+                                                               const Affine<typename CV::F>* __restrict__ in,
+                                                               const uint32_t* __restrict__ entries,
+                                                               const uint32_t* __restrict__ offs_in,
+                                                               const uint32_t* __restrict__ offs_out,
+                                                               Affine<typename CV::F>* __restrict__ out) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  msm_pairtree_round<CV, FIRST>(t, B, total, in, entries, offs_in, offs_out, out);
 }
 
 // buckets cut by slice boundaries: add their partials (<= 64 serially, larger ones go to a work list)

@@ -229,6 +229,76 @@ B2K_D void scalar_mul(Jac<typename CV::F>& r, const Scalar256& k, const Affine<t
   r = acc;
 }
 
+// ---- independent scalar multiplication on BLS12-381 G1 with the endomorphism -----------------------------------------
+// k P = +-k1 P + k2 (-phi P) with 127-bit k1, k2 (glv_split_bls381), both walked together in signed radix-16 digits over
+// ONE affine table {P, 2P .. 8P} (phi maps the table: x -> beta x): 33 x (4 doublings + 2 mixed additions) instead of
+// 255 doublings + ~128 additions, and every lane of a warp does the same work in every step (a double-and-add loop pays
+// the addition whenever ANY lane has a set bit).  The table is normalised with one batched inversion.
+// Requires P in the order-r subgroup (operands are what UnmarshalBinary accepted, kilic/g1.go:127-131), like the MSM's
+// front end; the reference's bn254 Mul uses the same decomposition (pairing/bn254/curve.go:196-218).
+template <class F, class INV>
+B2K_D void scalar_mul_glv_bls381(Jac<F>& r, const Scalar256& k, const Affine<F>& p, INV inv_fn) {
+  if (aff_is_inf(p)) { jac_set_inf(r); return; }
+  GlvSplit sp;
+  glv_split_bls381(sp, k);
+  // table j P, j = 1..8: Jacobian chain, then to affine with one inversion (Z_1 = 1)
+  Jac<F> tj[8];
+  jac_from_affine(tj[0], p);
+  jac_dbl(tj[1], tj[0]);
+  for (int j = 2; j < 8; j++) jac_madd(tj[j], tj[j - 1], p);
+  Affine<F> tab[8];
+  tab[0] = p;
+  {
+    F pre[8], acc, zi, zi2;
+    f_set_one(acc);
+    for (int j = 1; j < 8; j++) { pre[j] = acc; f_mul(acc, acc, tj[j].Z); }     // j P is never infinity for j < r
+    inv_fn(acc, acc);
+    for (int j = 7; j >= 1; j--) {
+      f_mul(zi, acc, pre[j]);
+      f_mul(acc, acc, tj[j].Z);
+      f_sqr(zi2, zi);
+      f_mul(tab[j].x, tj[j].X, zi2);
+      f_mul(zi2, zi2, zi);
+      f_mul(tab[j].y, tj[j].Y, zi2);
+    }
+  }
+  // s' = s + 0x888..8 (33 nibbles): nibble_i(s') - 8 is the signed digit; kept top-aligned in 5 limbs (160 bits >= 132 + 28)
+  uint32_t d1[5], d2[5];
+  {
+    const uint32_t KK[5] = {0x88888888u, 0x88888888u, 0x88888888u, 0x88888888u, 0x8u};
+    uint64_t c1 = 0, c2 = 0;
+    uint32_t a1[5], a2[5];
+    for (int j = 0; j < 5; j++) {
+      uint64_t t1 = (uint64_t)(j < 4 ? sp.k1.v[j] : 0u) + KK[j] + c1; a1[j] = (uint32_t)t1; c1 = t1 >> 32;
+      uint64_t t2 = (uint64_t)(j < 4 ? sp.k2.v[j] : 0u) + KK[j] + c2; a2[j] = (uint32_t)t2; c2 = t2 >> 32;
+    }
+    for (int j = 4; j > 0; j--) { d1[j] = (a1[j] << 28) | (a1[j - 1] >> 4); d2[j] = (a2[j] << 28) | (a2[j - 1] >> 4); }
+    d1[0] = a1[0] << 28; d2[0] = a2[0] << 28;
+  }
+  F beta;
+  for (int j = 0; j < F::N; j++) beta.v[j] = Bls381Fp::beta(j);
+  Jac<F> acc;
+  jac_set_inf(acc);
+  for (int i = 32; i >= 0; i--) {
+    if (i != 32) { jac_dbl(acc, acc); jac_dbl(acc, acc); jac_dbl(acc, acc); jac_dbl(acc, acc); }
+    const int e1 = (int)(d1[4] >> 28) - 8, e2 = (int)(d2[4] >> 28) - 8;
+    for (int j = 4; j > 0; j--) { d1[j] = (d1[j] << 4) | (d1[j - 1] >> 28); d2[j] = (d2[j] << 4) | (d2[j - 1] >> 28); }
+    d1[0] <<= 4; d2[0] <<= 4;
+    if (e1) {                                       // +-|e1| P, sign = neg1 xor (e1 < 0)
+      Affine<F> q = tab[(e1 < 0 ? -e1 : e1) - 1];
+      if (sp.neg1 != (e1 < 0)) f_neg(q.y, q.y);
+      jac_madd(acc, acc, q);
+    }
+    if (e2) {                                       // +-|e2| (-phi P) = (beta x, -+y): y keeps its sign iff neg2 xor (e2 < 0)
+      Affine<F> q = tab[(e2 < 0 ? -e2 : e2) - 1];
+      f_mul(q.x, q.x, beta);
+      if (sp.neg2 == (e2 < 0)) f_neg(q.y, q.y);
+      jac_madd(acc, acc, q);
+    }
+  }
+  r = acc;
+}
+
 }  // namespace b2k
 
 // =================================================================================================
@@ -259,7 +329,8 @@ B2K_D void msm_slice_flush(const Xyzz<typename CV::F>& acc, uint32_t g, uint32_t
   else spart[2 * (size_t)j + (s < b ? 0 : 1)] = acc;
 }
 
-template <class CV>
+// DIRECT: the sorted operands themselves are in pts[] (output of the affine pair-tree rounds, msm_affine.cuh), no entries
+template <class CV, bool DIRECT = false>
 B2K_D void msm_accumulate_slice(uint32_t j, uint32_t L, uint32_t total, const Affine<typename CV::F>* pts,
                                 const uint32_t* offs, const uint32_t* entries,
                                 Xyzz<typename CV::F>* buckets, Xyzz<typename CV::F>* spart) {
@@ -277,9 +348,14 @@ B2K_D void msm_accumulate_slice(uint32_t j, uint32_t L, uint32_t total, const Af
       xyzz_set_inf(acc);
       do { g++; gs = ge; ge = offs[g + 1]; } while (ge <= pos);
     }
-    uint32_t v = entries[pos];
-    Affine<typename CV::F> q = pts[v & 0x7fffffffu];
-    xyzz_madd(acc, acc, q, (v >> 31) != 0);
+    if (DIRECT) {
+      Affine<typename CV::F> q = pts[pos];
+      xyzz_madd(acc, acc, q, false);
+    } else {
+      uint32_t v = entries[pos];
+      Affine<typename CV::F> q = pts[v & 0x7fffffffu];
+      xyzz_madd(acc, acc, q, (v >> 31) != 0);
+    }
   }
   msm_slice_flush<CV>(acc, g, gs, ge, j, b, e, buckets, spart);
 }

@@ -58,14 +58,14 @@ inline MsmPlan make_plan(size_t n, int force_c, int scalar_bits, int force_m = 0
 
 // slice length of the balanced accumulate: 64 additions per thread when there is enough work to fill
 // the chip (>= 128k slices), shorter slices for small problems
-inline uint32_t slice_len(size_t n, const MsmPlan& pl, int force_L) {
+inline uint32_t slice_len_entries(size_t e, int force_L) {
   if (force_L > 0) return (uint32_t)force_L;
-  size_t e = n * (size_t)pl.W;
   size_t L = e / 131072;
   if (L > 64) L = 64;
   if (L < 4) L = 4;
   return (uint32_t)L;
 }
+inline uint32_t slice_len(size_t n, const MsmPlan& pl, int force_L) { return slice_len_entries(n * (size_t)pl.W, force_L); }
 
 
 inline int check_flags(b2k_ctx* ctx) {
@@ -90,10 +90,48 @@ inline MsmPlan msm_plan(const b2k_ctx* ctx, size_t n) {
   return make_plan(g ? 2 * n : n, ctx->force_c, g ? GlvTraits<CV>::bits : CV::SCALAR_BITS, ctx->force_m);
 }
 
+// ---- affine pair-tree rounds in front of the XYZZ slices (msm_affine.cuh): which curves, how many, how wide ----------
+template <class CV> struct AffineTraits { static constexpr bool enabled = false; };
+template <> struct AffineTraits<Bls381G1> { static constexpr bool enabled = true; };
+constexpr int PT_MAX_ROUNDS = 8;
+struct AffinePlan {
+  int R = 0;                            // rounds
+  uint32_t B[PT_MAX_ROUNDS] = {};       // outputs per thread
+  size_t bound[PT_MAX_ROUNDS + 1] = {}; // host-side upper bound of the operand count before round r (bound[R]: what the slices see)
+};
+// n = pairs the pipeline processes (msm_virtual_n)
+template <class CV>
+inline AffinePlan affine_plan(const b2k_ctx* ctx, size_t n, const MsmPlan& pl) {
+  AffinePlan ap;
+  ap.bound[0] = n * (size_t)pl.W;
+  if (!AffineTraits<CV>::enabled || ctx->use_v1 || ctx->msm_groups > 1) return ap;
+  const size_t total = (size_t)pl.W * pl.nb;
+  int R = ctx->affine_rounds;
+  if (R < 0) {                          // automatic: worth it for big problems; leave ~4..8 operands per bucket to the slices
+    R = 0;
+    if (ap.bound[0] >= (size_t(1) << 20)) {
+      const size_t avg = ap.bound[0] / total;
+      while (R < PT_MAX_ROUNDS && (avg >> R) >= 8) R++;
+    }
+  }
+  if (R > PT_MAX_ROUNDS) R = PT_MAX_ROUNDS;
+  ap.R = R;
+  for (int r = 0; r < R; r++) {
+    ap.bound[r + 1] = (ap.bound[r] + total) / 2 + 1;   // ceil(k/2) summed over the buckets
+    size_t B = ctx->affine_batch > 0 ? (size_t)ctx->affine_batch : ap.bound[r + 1] / 75776;   // 148 SMs x 512 threads
+    if (ctx->affine_batch <= 0 && B < 32) B = 32;       // one inversion per thread: keep it amortised
+    if (B < 1) B = 1;
+    if (B > (size_t)PT_MAXB) B = PT_MAXB;
+    ap.B[r] = (uint32_t)B;
+  }
+  return ap;
+}
+
 // ------------------------------------------------------------------------------------------------
 // n = number of pairs the pipeline processes (msm_virtual_n)
 template <class CV>
-size_t msm_scratch_bytes(size_t n, const MsmPlan& pl, int force_L) {
+size_t msm_scratch_bytes(const b2k_ctx* ctx, size_t n, const MsmPlan& pl) {
+  const int force_L = ctx->force_L;
   using F = typename CV::F;
   size_t total = (size_t)pl.W * pl.nb;
   size_t T = pl.nb / pl.m;
@@ -108,6 +146,12 @@ size_t msm_scratch_bytes(size_t n, const MsmPlan& pl, int force_L) {
   size_t smax = (n * (size_t)pl.W) / (size_t)slice_len(n, pl, force_L) + 2;
   b += pad256(2 * smax * sizeof(Xyzz<F>));        // slice partials (worst case: smallest automatic L)
   b += pad256((total + 1) * 4) + pad256(4096);    // big-bucket list, block sums
+  const AffinePlan ap = affine_plan<CV>(ctx, n, pl);
+  if (ap.R > 0) {
+    b += 2 * pad256((total + 1) * 4);             // bucket offsets of the rounds (ping-pong)
+    b += pad256(ap.bound[1] * sizeof(Affine<F>));
+    if (ap.R > 1) b += pad256(ap.bound[2] * sizeof(Affine<F>));
+  }
   return b + 8192;
 }
 
@@ -151,6 +195,16 @@ int msm_enqueue(b2k_ctx* ctx, size_t n_in, const MsmPlan& pl, const uint8_t* d_s
     ctx->err = "scratch arena too small / too many buckets";
     return B2K_ERR_ARG;
   }
+  const AffinePlan ap = affine_plan<CV>(ctx, n, pl);
+  uint32_t* offs_rt[2] = {nullptr, nullptr};
+  Affine<F>* aff_rt[2] = {nullptr, nullptr};
+  if (ap.R > 0) {
+    offs_rt[0] = arena_take<uint32_t>(ctx, total + 1);
+    offs_rt[1] = arena_take<uint32_t>(ctx, total + 1);
+    aff_rt[0] = arena_take<Affine<F>>(ctx, ap.bound[1]);
+    if (ap.R > 1) aff_rt[1] = arena_take<Affine<F>>(ctx, ap.bound[2]);
+    if (!offs_rt[0] || !offs_rt[1] || !aff_rt[0] || (ap.R > 1 && !aff_rt[1])) { ctx->err = "scratch arena too small"; return B2K_ERR_ARG; }
+  }
   uint32_t* big_count = bsum + 1023;      // last word of the block-sum page is never a block sum (<= 1023 blocks used)
   unsigned gb_n = (unsigned)((n + 255) / 256);
   unsigned sblocks = (unsigned)((total + 1023) / 1024);
@@ -183,6 +237,7 @@ int msm_enqueue(b2k_ctx* ctx, size_t n_in, const MsmPlan& pl, const uint8_t* d_s
     CK(cudaMemsetAsync(bigc, 0, 64, st));
     k_msm_group_ranges<<<1, 32, 0, st>>>(G, pl.W, pl.nb, L, (uint32_t)total, offs, ranges); nl++;
     CK(cudaEventRecord(ctx->ev[4], st));
+    CK(cudaEventRecord(ctx->ev[10], st));
     for (int g = G - 1; g >= 0; g--) {
       const int w_lo = g * pl.W / G, w_hi = (g + 1) * pl.W / G, w_cnt = w_hi - w_lo;
       k_msm_accumulate_slices_range<CV><<<(smax + 127) / 128, 128, 0, st>>>(ranges, g, L, (uint32_t)total, pts, offs, entries, buckets, spart); nl++;
@@ -206,12 +261,43 @@ int msm_enqueue(b2k_ctx* ctx, size_t n_in, const MsmPlan& pl, const uint8_t* d_s
   } else {
   if (ctx->use_v1) {
     CK(cudaEventRecord(ctx->ev[4], st));
+    CK(cudaEventRecord(ctx->ev[10], st));
     k_msm_accumulate<CV><<<(unsigned)((total + 127) / 128), 128, 0, st>>>(total, pts, offs, entries, buckets); nl++;
     CK(cudaEventRecord(ctx->ev[9], st));
   } else {
     CK(cudaMemsetAsync(buckets, 0, total * sizeof(Xyzz<F>), st));
     CK(cudaMemsetAsync(big_count, 0, 4, st));
     CK(cudaEventRecord(ctx->ev[4], st));
+    if (ap.R > 0) {
+      if constexpr (AffineTraits<CV>::enabled) {
+        // ---- affine pair-tree rounds: operands of every bucket halve per round; the slices below finish the rest
+        const uint32_t* offs_cur = offs;
+        const Affine<F>* in_cur = pts;
+        for (int r = 0; r < ap.R; r++) {
+          uint32_t* offs_nxt = offs_rt[r & 1];
+          Affine<F>* out = aff_rt[r & 1];
+          k_pt_counts<<<(unsigned)((total + 255) / 256), 256, 0, st>>>((uint32_t)total, offs_cur, counts);
+          k_scan_blocks<<<sblocks, 1024, 0, st>>>((uint32_t)total, counts, offs_nxt, bsum);
+          k_scan_tops<<<1, 1024, 0, st>>>(sblocks, (uint32_t)total, bsum, offs_nxt);
+          k_scan_finish<<<sblocks, 1024, 0, st>>>((uint32_t)total, bsum, offs_nxt, cursor);
+          const size_t threads = (ap.bound[r + 1] + ap.B[r] - 1) / ap.B[r];
+          if (r == 0) k_msm_pairtree_round<CV, true><<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(ap.B[r], (uint32_t)total, in_cur, entries, offs_cur, offs_nxt, out);
+          else k_msm_pairtree_round<CV, false><<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(ap.B[r], (uint32_t)total, in_cur, nullptr, offs_cur, offs_nxt, out);
+          nl += 5;
+          offs_cur = offs_nxt;
+          in_cur = out;
+        }
+        CK(cudaEventRecord(ctx->ev[10], st));        // end of the rounds
+        const uint32_t La = slice_len_entries(ap.bound[ap.R], ctx->force_L);
+        const uint32_t sa = (uint32_t)((ap.bound[ap.R] + La - 1) / La) + 1;     // <= smax: spart is large enough
+        k_msm_accumulate_slices_direct<CV, 4><<<(sa + 127) / 128, 128, 0, st>>>(sa, La, (uint32_t)total, in_cur, offs_cur, buckets, spart);
+        nl++;
+        CK(cudaEventRecord(ctx->ev[9], st));
+        k_msm_fixup<CV><<<(unsigned)((total + 127) / 128), 128, 0, st>>>((uint32_t)total, La, offs_cur, buckets, spart, big_count, big_list);
+        k_msm_fixup_big<CV><<<256, 128, 0, st>>>(La, offs_cur, buckets, spart, big_count, big_list); nl += 2;
+      }
+    } else {
+    CK(cudaEventRecord(ctx->ev[10], st));
     // resident blocks per SM (register cap 65536/(128*MINB)): 4 -> no spills, 5/6 -> more warps, small spills
     if (ctx->acc_minb == 5) k_msm_accumulate_slices<CV, 5><<<(smax + 127) / 128, 128, 0, st>>>(smax, L, (uint32_t)total, pts, offs, entries, buckets, spart);
     else if (ctx->acc_minb == 6) k_msm_accumulate_slices<CV, 6><<<(smax + 127) / 128, 128, 0, st>>>(smax, L, (uint32_t)total, pts, offs, entries, buckets, spart);
@@ -220,6 +306,7 @@ int msm_enqueue(b2k_ctx* ctx, size_t n_in, const MsmPlan& pl, const uint8_t* d_s
     CK(cudaEventRecord(ctx->ev[9], st));
     k_msm_fixup<CV><<<(unsigned)((total + 127) / 128), 128, 0, st>>>((uint32_t)total, L, offs, buckets, spart, big_count, big_list);
     k_msm_fixup_big<CV><<<256, 128, 0, st>>>(L, offs, buckets, spart, big_count, big_list); nl += 2;
+    }
   }
   CK(cudaEventRecord(ctx->ev[5], st));
   size_t nchunks = (size_t)pl.W * T;
@@ -249,7 +336,7 @@ int msm_dev(b2k_ctx* ctx, size_t n, const void* d_scalars, const void* d_points,
   }
   CK(cudaSetDevice(ctx->device));
   MsmPlan pl = msm_plan<CV>(ctx, n);
-  int rc = arena_reserve(ctx, msm_scratch_bytes<CV>(msm_virtual_n<CV>(ctx, n), pl, ctx->force_L));
+  int rc = arena_reserve(ctx, msm_scratch_bytes<CV>(ctx, msm_virtual_n<CV>(ctx, n), pl));
   if (rc) return rc;
   return msm_enqueue<CV>(ctx, n, pl, (const uint8_t*)d_scalars, (const uint8_t*)d_points, (uint8_t*)d_out, affine_out);
 }
@@ -266,7 +353,7 @@ int msm_host(b2k_ctx* ctx, size_t n, const uint8_t* scalars, const uint8_t* poin
   CK(cudaSetDevice(ctx->device));
   MsmPlan pl = msm_plan<CV>(ctx, n);
   size_t in_bytes = pad256(n * 32) + pad256(n * (size_t)CV::IN_BYTES) + 256;
-  int rc = arena_reserve(ctx, msm_scratch_bytes<CV>(msm_virtual_n<CV>(ctx, n), pl, ctx->force_L) + in_bytes);
+  int rc = arena_reserve(ctx, msm_scratch_bytes<CV>(ctx, msm_virtual_n<CV>(ctx, n), pl) + in_bytes);
   if (rc) return rc;
   auto* d_s = arena_take<uint8_t>(ctx, n * 32);
   auto* d_p = arena_take<uint8_t>(ctx, n * (size_t)CV::IN_BYTES);
@@ -298,7 +385,7 @@ int mul_batch_dev(b2k_ctx* ctx, size_t n, const void* d_scalars, const void* d_p
   }
   CK(cudaSetDevice(ctx->device));
   k_mul_batch<CV, AFF><<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(
-      n, (const uint8_t*)d_scalars, (const uint8_t*)d_points, (uint8_t*)d_out, ctx->d_flags);
+      n, (const uint8_t*)d_scalars, (const uint8_t*)d_points, (uint8_t*)d_out, ctx->d_flags, ctx->use_glv);
   CK(cudaGetLastError());
   ctx->launches += 1;
   return B2K_OK;

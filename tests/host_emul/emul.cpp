@@ -33,6 +33,7 @@ FIELD_API(fp254, Bn254Fp)
 // ------------------------------------------------------------------------------------------------
 // curve-level emulation: run the per-thread kernel bodies in plain loops
 #include "../../kyber_b200/csrc/msm.cuh"
+#include "../../kyber_b200/csrc/msm_affine.cuh"
 #include <vector>
 #include <cstring>
 
@@ -47,8 +48,20 @@ static void emul_mul_batch(size_t n, const uint8_t* scalars, const uint8_t* pts,
   }
 }
 
+struct EmulInv { template <class F> void operator()(F& r, const F& a) const { f_inv_bg(r, a); } };
+static void emul_mul_batch_glv(size_t n, const uint8_t* scalars, const uint8_t* pts, uint8_t* out) {
+  using CV = Bls381G1;
+  for (size_t i = 0; i < n; i++) {
+    Scalar256 k; scalar_load_be(k, scalars + 32 * i);
+    Affine<CV::F> p; CV::load(p, pts + CV::IN_BYTES * i);
+    Jac<CV::F> r; scalar_mul_glv_bls381(r, k, p, EmulInv{});
+    Affine<CV::F> a; jac_to_affine(a, r);
+    CV::store(out + CV::OUT_BYTES * i, a);
+  }
+}
+
 template <class CV>
-static int emul_msm(size_t n, const uint8_t* scalars, const uint8_t* pts, int c, int m, uint8_t* out, int L = 0) {
+static int emul_msm(size_t n, const uint8_t* scalars, const uint8_t* pts, int c, int m, uint8_t* out, int L = 0, int rounds = 0, int PB = 8) {
   using F = typename CV::F;
   MsmPlan pl; pl.c = c; pl.W = (256 + c - 1) / c; pl.nb = 1 << (c - 1); pl.m = m;
   // K = sum_w 2^(c-1) 2^(cw)
@@ -78,10 +91,27 @@ static int emul_msm(size_t n, const uint8_t* scalars, const uint8_t* pts, int c,
     for (size_t g = 0; g < total; g++) msm_accumulate_bucket<CV>(B[g], P.data(), entries.data(), offs[g], offs[g + 1]);
   } else {   // v2: fixed-length slices + fix-up (buckets start as all-zero = infinity, like cudaMemset)
     memset((void*)B.data(), 0, total * sizeof(Xyzz<F>));
+    // affine pair-tree rounds (msm_affine.cuh): every round halves the operand list of every bucket
+    std::vector<Affine<F>> cur;
+    for (int r = 0; r < rounds; r++) {
+      std::vector<uint32_t> no(total + 1, 0);
+      for (size_t g = 0; g < total; g++) no[g + 1] = no[g] + ((offs[g + 1] - offs[g] + 1) >> 1);
+      std::vector<Affine<F>> nxt(no[total] + 1);
+      uint32_t T = (no[total] + PB - 1) / PB + 1;      // one thread past the end: must be a no-op
+      for (uint32_t t = 0; t < T; t++) {
+        if (r == 0) msm_pairtree_round<CV, true>(t, (uint32_t)PB, (uint32_t)total, P.data(), entries.data(), offs.data(), no.data(), nxt.data());
+        else msm_pairtree_round<CV, false>(t, (uint32_t)PB, (uint32_t)total, cur.data(), nullptr, offs.data(), no.data(), nxt.data());
+      }
+      cur.swap(nxt);
+      offs.swap(no);
+    }
     uint32_t E = offs[total];
     uint32_t S = (E + L - 1) / L;
     std::vector<Xyzz<F>> spart(2 * (size_t)S + 2);
-    for (uint32_t j = 0; j < S; j++) msm_accumulate_slice<CV>(j, (uint32_t)L, (uint32_t)total, P.data(), offs.data(), entries.data(), B.data(), spart.data());
+    for (uint32_t j = 0; j < S; j++) {
+      if (rounds) msm_accumulate_slice<CV, true>(j, (uint32_t)L, (uint32_t)total, cur.data(), offs.data(), nullptr, B.data(), spart.data());
+      else msm_accumulate_slice<CV>(j, (uint32_t)L, (uint32_t)total, P.data(), offs.data(), entries.data(), B.data(), spart.data());
+    }
     for (size_t g = 0; g < total; g++) {
       bool big = msm_fixup_bucket<CV, 3>((uint32_t)g, (uint32_t)L, offs.data(), B.data(), spart.data());
       if (big) {   // emulate the block-parallel path serially
@@ -103,6 +133,7 @@ static int emul_msm(size_t n, const uint8_t* scalars, const uint8_t* pts, int c,
 }
 
 extern "C" {
+void emul_bls12381_g1_mul_batch_glv(size_t n, const uint8_t* s, const uint8_t* p, uint8_t* o) { emul_mul_batch_glv(n, s, p, o); }
 void emul_bls12381_g1_mul_batch(size_t n, const uint8_t* s, const uint8_t* p, uint8_t* o) { emul_mul_batch<Bls381G1>(n, s, p, o); }
 int emul_bls12381_g1_msm(size_t n, const uint8_t* s, const uint8_t* p, int c, int m, uint8_t* o) { return emul_msm<Bls381G1>(n, s, p, c, m, o); }
 // GLV front end + the same pipeline over the 2n split pairs
@@ -130,6 +161,9 @@ int emul_glv_split_bls381(const uint8_t* k32, uint8_t* k1, uint8_t* k2) {
   for (int j = 0; j < 8; j++) for (int b = 0; b < 4; b++) { k1[4 * j + b] = (uint8_t)(sp.k1.v[7 - j] >> (24 - 8 * b)); k2[4 * j + b] = (uint8_t)(sp.k2.v[7 - j] >> (24 - 8 * b)); }
   return (sp.neg1 ? 1 : 0) | (sp.neg2 ? 2 : 0);
 }
+// balanced slices after `rounds` affine pair-tree rounds with PB outputs per thread
+int emul_bls12381_g1_msm_affine(size_t n, const uint8_t* s, const uint8_t* p, int c, int m, int L, int rounds, int PB, uint8_t* o) { return emul_msm<Bls381G1>(n, s, p, c, m, o, L, rounds, PB); }
+int emul_bn254_g1_msm_affine(size_t n, const uint8_t* s, const uint8_t* p, int c, int m, int L, int rounds, int PB, uint8_t* o) { return emul_msm<Bn254G1>(n, s, p, c, m, o, L, rounds, PB); }
 int emul_bls12381_g1_msm_v2(size_t n, const uint8_t* s, const uint8_t* p, int c, int m, int L, uint8_t* o) { return emul_msm<Bls381G1>(n, s, p, c, m, o, L); }
 void emul_bn254_g1_mul_batch(size_t n, const uint8_t* s, const uint8_t* p, uint8_t* o) { emul_mul_batch<Bn254G1>(n, s, p, o); }
 int emul_bn254_g1_msm(size_t n, const uint8_t* s, const uint8_t* p, int c, int m, uint8_t* o) { return emul_msm<Bn254G1>(n, s, p, c, m, o); }

@@ -30,6 +30,12 @@ def test_c2_msm_2_pow_20(engine):
             assert engine.bls12381_g1_msm(wl.scalars_to_bytes(s), pts) == want
         finally:
             engine.set_msm_groups(1)
+    for rounds in (0, 2):                      # affine pair-tree rounds off / forced (default: automatic, above)
+        engine.set_msm_affine(rounds, 0)
+        try:
+            assert engine.bls12381_g1_msm(wl.scalars_to_bytes(s), pts) == want
+        finally:
+            engine.set_msm_affine(-1, 0)
 
 
 def test_c3_65536_signatures_mode_a_and_b(engine):

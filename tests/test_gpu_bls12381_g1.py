@@ -119,6 +119,50 @@ def test_msm_skewed_scalar_distributions(engine, dist_name):
         assert got == want, (dist_name, c, L)
 
 
+@pytest.mark.parametrize("dist_name", ["uniform", "equal", "small", "two_values", "bdn128"])
+def test_msm_affine_pair_tree_rounds_agree(engine, dist_name):
+    """The affine pair-tree rounds (batched affine additions around one inversion per thread, msm_affine.cuh) in front
+    of the XYZZ slices: forced on at small sizes, every round count and batch width, on uniform and skewed scalar sets
+    with repeated points, P / -P pairs and operands at infinity in the same bucket -- same bytes as the oracle."""
+    n = 3000
+    rng = random.Random(79)
+    a = wl.prng_scalars("b2k/test-a", n, o.R)
+    a[10] = a[11] = a[12]                     # equal points (P + P inside a bucket when their scalars agree)
+    a[20] = o.R - a[21]                       # P and -P
+    a[30] = 0                                 # operand at infinity
+    if dist_name == "uniform":
+        s = wl.prng_scalars("b2k/test-aff", n, o.R)
+        s[10] = s[11] = s[12]
+        s[20] = s[21]
+    elif dist_name == "equal":
+        s = [0x1D2C3B4A59687] * n
+    elif dist_name == "small":
+        s = [rng.randrange(1 << 20) for _ in range(n)]
+    elif dist_name == "two_values":
+        s = [rng.choice([1, o.R - 1]) for _ in range(n)]
+    else:
+        s = [rng.randrange(1 << 128) + 1 for _ in range(n)]
+    pts = engine.bls12381_g1_mul_batch_affine(wl.scalars_to_bytes(a), wl.G1_BLS12381_AFFINE * n)
+    want = o.g1_compress(o.g1_mul(wl.dot_mod(s, a, o.R)))
+    sb = wl.scalars_to_bytes(s)
+    for rounds, batch, c, L in ((1, 8, 0, 0), (2, 33, 8, 3), (3, 64, 6, 0), (5, 1, 5, 2), (8, 17, 4, 0), (4, 0, 16, 0)):
+        engine.set_msm_affine(rounds, batch)
+        engine.set_msm_window(c)
+        engine.set_msm_slice(L)
+        try:
+            got = engine.bls12381_g1_msm(sb, pts)
+        finally:
+            engine.set_msm_affine(-1, 0)
+            engine.set_msm_window(0)
+            engine.set_msm_slice(0)
+        assert got == want, (dist_name, rounds, batch, c, L)
+    engine.set_msm_affine(0, 0)               # off: the plain XYZZ pipeline
+    try:
+        assert engine.bls12381_g1_msm(sb, pts) == want
+    finally:
+        engine.set_msm_affine(-1, 0)
+
+
 def test_msm_variants_agree(engine):
     n = 2000
     a = wl.prng_scalars("b2k/test-a", n, o.R)

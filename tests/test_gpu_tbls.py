@@ -57,6 +57,41 @@ def test_recover_commit_bls12381(engine):
     assert engine.bls12381_recover_commit(2, idx, p2) == o.g2_compress(o.g2_mul(coeffs[0]))
 
 
+def test_pubpoly_check_batch_of_deals(engine):
+    """the share-verification loops of share/vss and share/dkg (PubPoly.Check, share/poly.go:405-409,
+    once per deal in vss.go:636-645 / dkg.go:489-494) as one batch: m dealers, each with its own commitment polynomial,
+    n shares each; corrupted shares, a share for the wrong index and an out-of-range share must be the only failures."""
+    rng = random.Random(84)
+    m, t, n = 5, 7, 11
+    from oracle import bn254 as o4
+    for curve, order, commit in (("bls12381_g1", o.R, lambda c: o.g1_to_affine_bytes(o.g1_mul(c))),
+                                 ("bls12381_g2", o.R, lambda c: o.g2_to_affine_bytes(o.g2_mul(c))),
+                                 ("bn254", o4.ORDER, lambda c: o4.g1_marshal(o4.g1_mul(c)))):
+        polys = [[rng.randrange(order) for _ in range(t)] for _ in range(m)]
+        polys[3][0] = 0                                            # a zero coefficient: commitment at infinity
+        idx = [[rng.randrange(0, 1000) for _ in range(n)] for _ in range(m)]
+        idx[0][0] = 0
+        idx[1][1] = 2 ** 32 - 1                                     # x = 2^32
+        def ev(cs, x):
+            acc = 0
+            for c in reversed(cs):
+                acc = (acc * x + c) % order
+            return acc
+        sh = [[ev(polys[d], idx[d][k] + 1) for k in range(n)] for d in range(m)]
+        bad = {(0, 3), (2, 0), (4, 10), (1, 5), (3, 7)}
+        sh[0][3] = (sh[0][3] + 1) % order                           # corrupted share
+        sh[2][0] = ev(polys[1], idx[2][0] + 1)                      # share of another dealer's polynomial
+        sh[4][10] = ev(polys[4], idx[4][10] + 2)                    # share for the wrong index
+        raw = [[v.to_bytes(32, "big") for v in row] for row in sh]
+        raw[1][5] = order.to_bytes(32, "big")                       # not below the group order
+        raw[3][7] = bytes(32) if sh[3][7] else (1).to_bytes(32, "big")
+        commits = b"".join(commit(c) for cs in polys for c in cs)
+        ok = engine.pubpoly_check(curve, commits, t, idx, b"".join(b for row in raw for b in row))
+        for d in range(m):
+            for k in range(n):
+                assert ok[d * n + k] == (0 if (d, k) in bad else 1), (curve, d, k)
+
+
 def test_tbls_recover_flow(engine):
     """t-of-n threshold BLS, signatures on G1 / keys on G2: all heavy steps on the engine."""
     rng = random.Random(83)

@@ -102,6 +102,59 @@ def test_balanced_slice_accumulate_bodies(emul):
             assert emul.emul_bls12381_g1_msm_v2(ctypes.c_size_t(n), sb, pb, c, m, L, o48) == 0 and o48.raw == want, (c, m, L)
 
 
+def test_glv_windowed_scalar_mul_body(emul):
+    """scalar_mul_glv_bls381 (k_mul_batch's BLS12-381 G1 path): endomorphism split + signed radix-16 digits over one
+    affine table -- edge scalars of the split and of the digit recoding, infinity operand."""
+    rng = random.Random(21)
+    x2 = o.X_ABS ** 2
+    ks = [0, 1, 2, 7, 8, 9, 15, 16, 17, x2 - 1, x2, x2 + 1, x2 // 2, x2 // 2 + 1, 8 * x2 + 8, (o.R - 1) // 2, (o.R + 1) // 2,
+          o.R - 1, o.R - 2, o.R - x2, int("8" * 32, 16), int("7" * 32, 16), int("f" * 31, 16), (1 << 127) - 1, 1 << 127]
+    ks += [rng.randrange(o.R) for _ in range(40)]
+    n = len(ks)
+    pts = [o.g1_mul(rng.randrange(1, o.R)) for _ in range(n)]
+    pts[3] = None
+    sb = b"".join(o.scalar_to_bytes(k) for k in ks)
+    pb = b"".join(o.g1_to_affine_bytes(p) for p in pts)
+    out = ctypes.create_string_buffer(48 * n)
+    emul.emul_bls12381_g1_mul_batch_glv(ctypes.c_size_t(n), sb, pb, out)
+    for i in range(n):
+        assert out.raw[48 * i:48 * i + 48] == o.g1_compress(o.g1_mul(ks[i], pts[i])), (i, hex(ks[i]))
+
+
+def test_affine_pair_tree_round_bodies(emul):
+    """msm_affine.cuh: R pair-tree rounds (batched affine additions, one inversion per thread) followed by the balanced
+    XYZZ slices give the oracle's MSM, including the exceptional cases of the affine group law: repeated points in one
+    bucket (P + P), P and -P in one bucket, operands at infinity, all-equal scalars (one bucket per window)."""
+    rng = random.Random(11)
+    n = 48
+    pts = [o.g1_mul(rng.randrange(1, o.R)) for _ in range(n)]
+    pts[5] = None
+    pts[6] = pts[7] = pts[8] = pts[9]                     # the same point four times
+    pts[10] = o.g1_neg(pts[11])                           # P and -P
+    pb = b"".join(o.g1_to_affine_bytes(p) for p in pts)
+    sets = ([rng.randrange(o.R) for _ in range(n)], [0x123456789ABCDEF] * n, [rng.randrange(1 << 9) for _ in range(n)])
+    for ks in sets:
+        sb = b"".join(o.scalar_to_bytes(k) for k in ks)
+        want = o.g1_compress(o.g1_msm(ks, pts))
+        for c, m, L, rounds, pbatch in ((4, 2, 3, 1, 1), (4, 2, 2, 2, 3), (5, 4, 4, 3, 8), (8, 8, 5, 6, 64), (3, 2, 1, 9, 5)):
+            o48 = ctypes.create_string_buffer(48)
+            rc = emul.emul_bls12381_g1_msm_affine(ctypes.c_size_t(n), sb, pb, c, m, L, rounds, pbatch, o48)
+            assert rc == 0 and o48.raw == want, (c, m, L, rounds, pbatch)
+    # bn254 (8-limb field) through the same template
+    from oracle import bn254 as o4
+    pts4 = [o4.g1_mul(rng.randrange(1, o4.ORDER)) for _ in range(12)]
+    pts4[3] = pts4[4]
+    ks4 = [7] * 6 + [rng.randrange(o4.ORDER) for _ in range(6)]
+    sb4 = b"".join(k.to_bytes(32, "big") for k in ks4)
+    pb4 = b"".join(o4.g1_marshal(p) for p in pts4)
+    acc = None
+    for k, p4 in zip(ks4, pts4):
+        acc = o4.g1_add(acc, o4.g1_mul(k, p4))
+    o64 = ctypes.create_string_buffer(64)
+    assert emul.emul_bn254_g1_msm_affine(ctypes.c_size_t(12), sb4, pb4, 4, 2, 3, 2, 4, o64) == 0
+    assert o64.raw == o4.g1_marshal(acc)
+
+
 def test_hash_to_curve_bodies():
     from oracle import h2c_bls12381 as h, h2c_bls12381_g2 as h2
     l1, l2 = _lib("emul_h2c"), _lib("emul_h2c_g2")
@@ -174,6 +227,22 @@ def test_ed25519_and_inversion_bodies():
             out = (ctypes.c_uint32 * n)()
             getattr(inv, f"emul_{name}_inv_vartime")(inp, out)
             assert sum(int(x) << (32 * i) for i, x in enumerate(out)) == (pow(a, -1, p) * R % p if a else 0)
+    # branch-free binary GCD on 64-bit approximations (fp_inv_bingcd): edge values, short operands, many random ones
+    for name, p, n in (("fp381", o.P, 12), ("fp254", 21888242871839275222246405745257275088696311157297823662689037894645226208583, 8),
+                       ("fp256", 65000549695646603732796438742359905742825358107623003571877145026864184071783, 10),
+                       ("fp25519", 2 ** 255 - 19, 8)):
+        R = 1 << (32 * n)
+        Ri = pow(R, -1, p)
+        cases = [0, 1, 2, 3, p - 1, p - 2, (p - 1) // 2, (p + 1) // 2, 1 << (p.bit_length() - 1), (1 << (p.bit_length() - 1)) - 1]
+        cases += [rng.randrange(1, 1 << k) for k in range(1, p.bit_length(), 5) for _ in range(2)]
+        cases += [rng.randrange(p) for _ in range(1500)]
+        fn = getattr(inv, f"emul_{name}_inv_bingcd")
+        for am in cases:                       # am = the Montgomery representative itself (so short VALUES reach the loop)
+            a = am * Ri % p
+            inp = (ctypes.c_uint32 * n)(*[(am >> (32 * i)) & 0xFFFFFFFF for i in range(n)])
+            out = (ctypes.c_uint32 * n)()
+            fn(inp, out)
+            assert sum(int(x) << (32 * i) for i, x in enumerate(out)) == (pow(a, -1, p) * R % p if a else 0), (name, am)
 
 
 def test_bn_hash_to_g1_bodies_against_reference_vectors():
