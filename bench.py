@@ -202,6 +202,29 @@ def gpu_pairing_run(eng, torch, dev, n: int, steps: int):
             "checks_per_sec": n / (ms * 1e-3)}
 
 
+def gpu_mul_batch_run(eng, torch, dev, d_scal, d_pts, n: int, steps: int, scalars, a):
+    """independent Point.Mul: out[i] = s_i * P_i for the step's n resident (scalar, point) pairs, no summation
+    (reported beside the MSM number); a sample of the outputs is checked against the oracle."""
+    from oracle import bls12381 as o
+    out = torch.empty(n * 48, dtype=torch.uint8, device=dev)
+
+    def step():
+        eng.call_dev("b2k_bls12381_g1_mul_batch_dev", n, d_scal.data_ptr(), d_pts.data_ptr(), out.data_ptr())
+    step(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    res = out.cpu()
+    for i in (0, n // 2, n - 1):
+        assert bytes(res[48 * i:48 * i + 48].tolist()) == o.g1_compress(o.g1_mul(scalars[i] * a[i] % o.R)), "mul_batch differs from the oracle"
+    return {"value": n / (ms * 1e-3), "unit": "scalar-muls/s", "ms_per_step": ms,
+            "workload": f"{n} independent BLS12-381 G1 Point.Mul (random 255-bit scalars, distinct points), 48-byte compressed results",
+            "kernel": "k_mul_batch<Bls381G1>: endomorphism split, signed radix-16 digits over one affine table per point"}
+
+
 def gpu_verify_run(eng, torch, dev, n: int, steps: int):
     """BASELINE configs[2] mode A: n independent bls.Verify (signatures on G1) per step, inputs resident in HBM:
     2 UnmarshalBinary (subgroup checks) + hash-to-G1 + ValidatePairing each; one corrupted signature must fail."""
@@ -463,7 +486,8 @@ def run_ours(args):
         value = world * n / (ms_step * 1e-3)
         e2e_value = world * n / (e2e_ms / args.steps * 1e-3)
         tm = [sum(x[i] for x in acc_ms) / len(acc_ms) for i in range(len(acc_ms[0]))]
-        c_bits = 16 if LOG_N >= 18 else None
+        plan = eng.last_msm_plan()                                         # what the timed MSMs actually ran with
+        c_bits = plan["c"]
         peak, peak_src = load_peaks()
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
@@ -486,12 +510,18 @@ def run_ours(args):
                 "gpu_launches": int(launches),
                 "clocks": clocks,
                 "stages_ms": dict(zip(["load", "digits_hist", "scan", "scatter", "accumulate", "reduce_chunks",
-                                       "window_sum", "final", "pipeline", "fixup"], [round(x, 4) for x in tm]))}
+                                       "window_sum", "final", "pipeline", "fixup", "accumulate_affine_rounds"],
+                                      [round(x, 4) for x in tm])),
+                "msm_plan": plan}
         if c_bits:
-            W = 256 // c_bits                                             # bucket additions per pair; the
-            nbuckets = (W // 2) * (1 << (c_bits - 1))                     # endomorphism split halves the WINDOWS, not the additions
-            alg_bytes = n * W * 100 + nbuckets * 144                      # 100 B per addition + 144 B per bucket
+            nv = n * (2 if plan["glv"] else 1)                            # pairs after the endomorphism split
+            adds = nv * plan["W"]                                         # bucket additions (16 per input pair at c = 16)
+            nbuckets = plan["W"] * plan["buckets_per_window"]
+            alg_bytes = adds * 100 + nbuckets * 144                       # 100 B per addition + 144 B per bucket
             acc = tm[4] * 1e-3
+            R = plan["affine_rounds"]
+            left = adds / (1 << R) + (nbuckets if R else 0)               # operands the XYZZ slices still see after R halvings
+            products = (adds - left) * 6 + left * 10                      # affine addition 6, mixed XYZZ addition 10 field products
             traffic = None
             tp = os.path.join(ROOT, "profiles", "accumulate_traffic.json")
             if os.path.exists(tp):
@@ -499,18 +529,26 @@ def run_ours(args):
                     traffic = json.load(open(tp)).get("dram_bytes_per_launch")
                 except Exception:
                     traffic = None
-            line["roofline"] = {"bound": "hbm", "kernel": "k_msm_accumulate_slices", "achieved": alg_bytes / acc / 1e9,
+            kern = (f"bucket-accumulate pass: k_msm_pairtree_round x{R} (batched affine additions) + k_msm_accumulate_slices_direct"
+                    if R else "k_msm_accumulate_slices")
+            line["roofline"] = {"bound": "hbm", "kernel": kern, "achieved": alg_bytes / acc / 1e9,
                                 "peak": peak, "unit": "GB/s", "frac": alg_bytes / acc / 1e9 / peak,
                                 "traffic": traffic, "peak_source": peak_src,
                                 "algorithmic_bytes": alg_bytes, "kernel_ms": tm[4], "window_bits": c_bits,
-                                "note": "integer-ALU bound kernel (SURVEY.md F9): see `integer_roofline` and DESIGN.md section 4",
+                                "affine_rounds_ms": tm[10] if len(tm) > 10 else None,
+                                "note": "integer-ALU bound pass (SURVEY.md F9): see `integer_roofline` and DESIGN.md section 4; "
+                                        "`traffic` is the ncu DRAM bytes of the whole pass (all its launches) for one MSM",
                                 "integer_roofline": {
                                     "bound": "fma-heavy pipe (IMAD.WIDE, 4 cycles per warp instruction)",
-                                    "achieved": n * W * 10 / acc, "peak": 3.04e10, "unit": "381-bit Montgomery products/s",
-                                    "frac": n * W * 10 / acc / 3.04e10,
+                                    "achieved": products / acc, "peak": 3.04e10, "unit": "381-bit Montgomery products/s",
+                                    "frac": products / acc / 3.04e10,
                                     "peak_source": "measured: tools/probe/fpmul_probe.cu on B200 (profiles/r01_pipe_probes.txt)",
-                                    "work": "n*W mixed XYZZ additions x 10 field products"}}
+                                    "work": f"{int(adds - left)} affine additions x 6 + {int(left)} mixed XYZZ additions x 10 field products "
+                                            "(operand counts after the rounds estimated as adds / 2^R + buckets); the pass did the work of "
+                                            f"{adds} XYZZ additions (x 10) of the previous design",
+                                    "xyzz_equivalent_frac": adds * 10 / acc / 3.04e10}}
         if world == 1 and not os.environ.get("B2K_SKIP_PAIRINGS"):
+            line["independent_muls"] = gpu_mul_batch_run(eng, torch, dev, d_scal, d_pts, n, max(2, min(args.steps, 3)), s, a)
             line["pairings"] = gpu_pairing_run(eng, torch, dev, 1 << 16, max(2, min(args.steps, 5)))
             line["bls_verify"] = gpu_verify_run(eng, torch, dev, 1 << 16, max(2, min(args.steps, 3)))
         if world == 1 and not os.environ.get("B2K_SKIP_CPU_BASELINE"):

@@ -60,6 +60,10 @@ int b2k_synchronize(b2k_ctx* ctx);
  * [10] the affine pair-tree rounds inside [4] (0 when they are off).
  * Returns the number of entries written (<= max). Synchronises the stream. */
 int b2k_last_timings(b2k_ctx* ctx, float* ms, int max);
+/* Parameters the LAST MSM of this context ran with: [0] window bits c  [1] windows W  [2] buckets per window
+ * [3] reduction chunk  [4] slice length of the XYZZ pass  [5] affine pair-tree rounds R  [6..13] additions per thread of
+ * round 0..7  [14] 1 when the endomorphism split was used.  Returns the number of entries written. */
+int b2k_last_msm_plan(const b2k_ctx* ctx, int* out, int max);
 /* Override the MSM window size (0 = automatic).  Testing / tuning aid. */
 int b2k_set_msm_window(b2k_ctx* ctx, int c);
 /* Slice length of the balanced bucket-accumulate (0 = automatic) and the accumulate variant
@@ -81,6 +85,8 @@ int b2k_set_msm_glv(b2k_ctx* ctx, int on);
 int b2k_set_msm_affine(b2k_ctx* ctx, int rounds, int batch);
 /* Resident bucket-accumulate blocks per SM (4..6; launch bound => register cap).  Tuning aid. */
 int b2k_set_msm_occupancy(b2k_ctx* ctx, int blocks_per_sm);
+/* Resident blocks per SM of the BLS12-381 G1 Point.Mul batch kernel (0 = unconstrained [default], 3, 4).  Tuning aid. */
+int b2k_set_mul_occupancy(b2k_ctx* ctx, int blocks_per_sm);
 /* Buckets per thread in the chunked bucket reduction (power of two, 0 = automatic).  Tuning aid. */
 int b2k_set_msm_chunk(b2k_ctx* ctx, int m);
 /* Number of kernels launched by this context so far. */
@@ -275,6 +281,17 @@ int b2k_bn256_g2_msm(b2k_ctx* ctx, size_t n, const uint8_t* scalars, const uint8
 int b2k_bn256_pair(b2k_ctx* ctx, size_t n, const uint8_t* g1 /*[n][64]*/, const uint8_t* g2 /*[n][128]*/, uint8_t* gt /*[n][384]*/);
 int b2k_bn256_pairing_check(b2k_ctx* ctx, size_t n, const uint8_t* a1, const uint8_t* a2, const uint8_t* b1,
                             const uint8_t* b2, uint8_t* ok /*[n]*/);
+
+/* ---- UnmarshalBinary validation for whole batches of BN points (wire-format gate of the Mul / MSM / pairing entry points)
+ * ok[i] = 1 when the reference's UnmarshalBinary would accept in[i] (all-zero = the point at infinity is accepted):
+ *   bn254 G1: coordinates below p, on y^2 = x^3 + 3                      pairing/bn254/point.go:146-185, gfp.go:101-119
+ *   bn254 G2: coordinates below p, on the twist, killed by the group order  point.go:473-514, twist.go:50-66
+ *   bn256 G1/G2: NO range check (values reduce mod p), on the curve / twist, no order check
+ *                                                                        pairing/bn256/point.go:206-238, 469-506 */
+int b2k_bn254_g1_unmarshal_check(b2k_ctx* ctx, size_t n, const uint8_t* in /*[n][64]*/, uint8_t* ok /*[n]*/);
+int b2k_bn254_g2_unmarshal_check(b2k_ctx* ctx, size_t n, const uint8_t* in /*[n][128]*/, uint8_t* ok /*[n]*/);
+int b2k_bn256_g1_unmarshal_check(b2k_ctx* ctx, size_t n, const uint8_t* in /*[n][64]*/, uint8_t* ok /*[n]*/);
+int b2k_bn256_g2_unmarshal_check(b2k_ctx* ctx, size_t n, const uint8_t* in /*[n][128]*/, uint8_t* ok /*[n]*/);
 
 /* Launch-bound variant of the BLS12-381 pairing kernels (0 = default).  Tuning aid. */
 int b2k_set_pairing_variant(b2k_ctx* ctx, int variant);

@@ -7,7 +7,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libb2kyber.so")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC"]
-UNITS = ["b2k_api.cu", "b2k_bn254.cu", "b2k_g2.cu", "b2k_pairing.cu", "b2k_h2c.cu", "b2k_share.cu", "b2k_ed25519.cu", "b2k_bn256.cu", "b2k_bn254_pairing.cu", "b2k_bdn.cu", "b2k_bn_hash.cu"]
+UNITS = ["b2k_api.cu", "b2k_bn254.cu", "b2k_g2.cu", "b2k_pairing.cu", "b2k_h2c.cu", "b2k_share.cu", "b2k_ed25519.cu", "b2k_bn256.cu", "b2k_bn254_pairing.cu", "b2k_bdn.cu", "b2k_bn_hash.cu", "b2k_bn_codec.cu"]
 
 
 def _nvcc() -> str:
@@ -49,8 +49,9 @@ def build(force: bool = False, verbose: bool = False) -> str:
             sys.stderr.write(out)
         if p.returncode:
             raise RuntimeError(f"nvcc failed on {u}")
-    cmd = [_nvcc(), "-shared", "-o", LIB, *objs, "-lcudart"]
+    cmd = [_nvcc(), "-shared", "-o", LIB + ".tmp", *objs, "-lcudart"]
     subprocess.run(cmd, check=True)
+    os.replace(LIB + ".tmp", LIB)          # atomic: a reader (or a snapshot of the tree) never sees a half-written library
     with open(stamp_file, "w") as f:
         f.write(stamp)
     return LIB

@@ -43,6 +43,7 @@ def load_library() -> C.CDLL:
         "b2k_set_msm_occupancy": (C.c_int, [vp, C.c_int]),
         "b2k_set_msm_chunk": (C.c_int, [vp, C.c_int]),
         "b2k_set_msm_affine": (C.c_int, [vp, C.c_int, C.c_int]),
+        "b2k_last_msm_plan": (C.c_int, [vp, C.POINTER(C.c_int), C.c_int]),
     }
     sigs["b2k_bls12381_pair"] = (C.c_int, [vp, sz, vp, vp, vp])
     sigs["b2k_bls12381_pair_dev"] = (C.c_int, [vp, sz, vp, vp, vp])
@@ -63,6 +64,8 @@ def load_library() -> C.CDLL:
     sigs["b2k_bls12381_g2_recover_commit"] = (C.c_int, [vp, sz, vp, vp, vp])
     sigs["b2k_bls12381_g1_pubpoly_eval"] = (C.c_int, [vp, sz, vp, sz, vp, vp])
     sigs["b2k_bls12381_g2_pubpoly_eval"] = (C.c_int, [vp, sz, vp, sz, vp, vp])
+    for nm in ("b2k_bn254_g1_unmarshal_check", "b2k_bn254_g2_unmarshal_check", "b2k_bn256_g1_unmarshal_check", "b2k_bn256_g2_unmarshal_check"):
+        sigs[nm] = (C.c_int, [vp, sz, vp, vp])
     for nm in ("b2k_bls12381_g1_pubpoly_check", "b2k_bls12381_g2_pubpoly_check", "b2k_bn254_pubpoly_check"):
         sigs[nm] = (C.c_int, [vp, sz, sz, vp, sz, vp, vp, vp])
     host3 = (C.c_int, [vp, sz, vp, vp, vp])
@@ -166,6 +169,15 @@ class Engine:
     def set_msm_affine(self, rounds: int = -1, batch: int = 0):
         """affine pair-tree rounds of the BLS12-381 G1 MSM: -1 automatic, 0 off, 1..8 forced; batch = additions per thread"""
         self._check(self.lib.b2k_set_msm_affine(self.h, int(rounds), int(batch)))
+
+    def last_msm_plan(self) -> dict:
+        """parameters of the last MSM: window bits, windows, chunk, slice length, affine rounds and their batch widths"""
+        arr = (C.c_int * 16)()
+        n = self.lib.b2k_last_msm_plan(self.h, arr, 16)
+        if n < 0:
+            self._check(n)
+        return {"c": arr[0], "W": arr[1], "buckets_per_window": arr[2], "chunk": arr[3], "slice_len": arr[4],
+                "affine_rounds": arr[5], "affine_batch": [arr[6 + r] for r in range(arr[5])], "glv": bool(arr[14])}
 
     def last_timings(self):
         arr = (C.c_float * 16)()
@@ -399,6 +411,16 @@ class Engine:
         out = bytearray(plen * n)
         bufs = [_buf(x) for x in (commits, struct.pack("<%dI" % n, *indices), out)]
         self._check(getattr(self.lib, f"b2k_bls12381_g{group}_pubpoly_eval")(self.h, t, bufs[0][0], n, bufs[1][0], bufs[2][0]))
+        return bytes(out)
+
+    def bn_unmarshal_check(self, curve: str, group: int, data: bytes) -> bytes:
+        """UnmarshalBinary validation of a batch: curve in {"bn254", "bn256"}, group 1 ([n][64]) or 2 ([n][128]) -> n bytes"""
+        plen = 64 if group == 1 else 128
+        n = len(data) // plen
+        assert n * plen == len(data)
+        out = bytearray(n)
+        bufs = [_buf(x) for x in (data, out)]
+        self._check(getattr(self.lib, f"b2k_{curve}_g{group}_unmarshal_check")(self.h, n, bufs[0][0], bufs[1][0]))
         return bytes(out)
 
     def pubpoly_check(self, curve: str, commits: bytes, t: int, indices, shares: bytes) -> bytes:

@@ -133,6 +133,13 @@ int b2k_last_timings(b2k_ctx* ctx, float* ms, int max) {
   return n;
 }
 
+int b2k_last_msm_plan(const b2k_ctx* ctx, int* out, int max) {
+  if (!ctx || !out || max <= 0) return B2K_ERR_ARG;
+  int n = max < 15 ? max : 15;
+  for (int i = 0; i < n; i++) out[i] = ctx->last_plan[i];
+  return n;
+}
+
 int b2k_set_msm_affine(b2k_ctx* ctx, int rounds, int batch) {
   if (!ctx || rounds < -1 || rounds > 8 || batch < 0 || batch > 64) return B2K_ERR_ARG;
   ctx->affine_rounds = rounds;
@@ -163,6 +170,12 @@ int b2k_set_msm_chunk(b2k_ctx* ctx, int m) {
 int b2k_set_msm_occupancy(b2k_ctx* ctx, int blocks_per_sm) {
   if (!ctx || blocks_per_sm < 4 || blocks_per_sm > 6) return B2K_ERR_ARG;
   ctx->acc_minb = blocks_per_sm;
+  return B2K_OK;
+}
+
+int b2k_set_mul_occupancy(b2k_ctx* ctx, int blocks_per_sm) {
+  if (!ctx || (blocks_per_sm != 0 && blocks_per_sm != 3 && blocks_per_sm != 4)) return B2K_ERR_ARG;
+  ctx->mul_minb = blocks_per_sm;
   return B2K_OK;
 }
 

@@ -5,25 +5,6 @@ using namespace b2k_host;
 
 namespace b2k {
 
-// bn254 G2 (pairing/bn254/twist.go:167-181 twistPoint.Mul; wire format point.go:428-455)
-struct Bn254G2 {
-  using FC = Bn254Fp;
-  using F = NFp2;
-  using ScalarField = Bn254Fr;
-  static constexpr int SCALAR_BITS = 254;
-  static constexpr int IN_BYTES = 128;
-  static constexpr int OUT_BYTES = 128;
-  B2K_D static void load(Affine<F>& r, const uint8_t* p) { bn254_g2_load(r, p); }
-  B2K_D static void store(uint8_t* out, const Affine<F>& p) {
-    NFp t;
-    fp_from_mont(t, p.x.c1); fp_store_be(out, t);
-    fp_from_mont(t, p.x.c0); fp_store_be(out + 32, t);
-    fp_from_mont(t, p.y.c1); fp_store_be(out + 64, t);
-    fp_from_mont(t, p.y.c0); fp_store_be(out + 96, t);
-  }
-  B2K_D static void store_affine(uint8_t* out, const Affine<F>& p) { store(out, p); }
-};
-
 __global__ void __launch_bounds__(64, 4) k_bn254_pair(size_t n, const uint8_t* __restrict__ g1, const uint8_t* __restrict__ g2,
                                                       uint8_t* __restrict__ gt) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -31,8 +31,10 @@ struct b2k_ctx {
                                     // B200 (accumulate blocks fill the register file, nothing co-resides): kept as an experiment
   int affine_rounds = -1;           // affine pair-tree rounds before the XYZZ slices: -1 = automatic, 0 = off (A/B), 1..8 forced
   int affine_batch = 0;             // outputs (batched affine additions) per thread of a round, 8..64; 0 = automatic
+  int mul_minb = 0;                 // BLS12-381 G1 Point.Mul batches: resident blocks per SM (0 = compiler's choice, 3, 4), tuning aid
   int acc_minb = 4;                 // resident accumulate blocks per SM (launch bound), tuning aid
   int pair_variant = 0; // launch-bound variant of the pairing kernels (tuning aid)
+  int last_plan[16] = {};           // what the last MSM ran with: c, W, buckets/window, chunk, slice length, affine rounds, their batch widths
   uint64_t launches = 0;
   std::string err;
 };

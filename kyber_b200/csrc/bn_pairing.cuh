@@ -324,4 +324,23 @@ B2K_D void bn254_g1_load(Affine<NFp>& r, const uint8_t* p) { bn_g1_load<Bn254Pai
 B2K_D void bn254_g2_load(Affine<NFp2>& r, const uint8_t* p) { bn_g2_load<Bn254Pair>(r, p); }
 B2K_D void bn254_gt_store(uint8_t* out, const NFp12& f) { bn_gt_store<Bn254Pair>(out, f); }
 
+// bn254 G2 (pairing/bn254/twist.go:167-181 twistPoint.Mul; wire format point.go:428-455)
+struct Bn254G2 {
+  using FC = Bn254Fp;
+  using F = NFp2;
+  using ScalarField = Bn254Fr;
+  static constexpr int SCALAR_BITS = 254;
+  static constexpr int IN_BYTES = 128;
+  static constexpr int OUT_BYTES = 128;
+  B2K_D static void load(Affine<F>& r, const uint8_t* p) { bn254_g2_load(r, p); }
+  B2K_D static void store(uint8_t* out, const Affine<F>& p) {
+    NFp t;
+    fp_from_mont(t, p.x.c1); fp_store_be(out, t);
+    fp_from_mont(t, p.x.c0); fp_store_be(out + 32, t);
+    fp_from_mont(t, p.y.c1); fp_store_be(out + 64, t);
+    fp_from_mont(t, p.y.c0); fp_store_be(out + 96, t);
+  }
+  B2K_D static void store_affine(uint8_t* out, const Affine<F>& p) { store(out, p); }
+};
+
 }  // namespace b2k

@@ -261,9 +261,16 @@ B2K_NI void fp_pow_const(Fp<C>& r, const Fp<C>& a) {
   r = acc;
 }
 
-// Fermat inverse a^(p-2); inverse of 0 is 0.
+// Fermat inverse a^(p-2); inverse of 0 is 0.  Kept as the independent cross-check of fp_inv (tests/host_emul).
 template <class C>
-B2K_D void fp_inv(Fp<C>& r, const Fp<C>& a) { fp_pow_const<C, typename C::ExpPm2>(r, a); }
+B2K_D void fp_inv_fermat(Fp<C>& r, const Fp<C>& a) { fp_pow_const<C, typename C::ExpPm2>(r, a); }
+
+// The inversion every kernel uses: branch-free binary GCD on 64-bit approximations (fp_inv.cuh, included at the end of
+// this file) -- about a tenth of the Fermat ladder's multiply-pipe time, most of it on the otherwise idle integer ALU.
+// Same contract: Montgomery in, Montgomery out, inverse of 0 is 0.
+template <class C> B2K_NI void fp_inv_bingcd(Fp<C>& out, const Fp<C>& x);
+template <class C>
+B2K_D void fp_inv(Fp<C>& r, const Fp<C>& a) { fp_inv_bingcd(r, a); }
 
 // canonical comparison helper: is (canonical, non-Montgomery) a > (p-1)/2 ?
 template <class C>
@@ -305,3 +312,5 @@ B2K_D void fp_store_be(uint8_t* p, const Fp<C>& a) {
 }
 
 }  // namespace b2k
+
+#include "fp_inv.cuh"

@@ -130,6 +130,7 @@ B2K_D void mp_lin2_mont30(uint32_t* r, const uint32_t* x, uint32_t fx, const uin
 template <class C>
 B2K_NI void fp_inv_bingcd(Fp<C>& out, const Fp<C>& x) {
   constexpr int N = C::N;
+  static_assert(C::BITS <= 32 * C::N - 1, "the modulus must leave the top bit of the limb vector free");
   constexpr int ROUNDS = (2 * C::BITS - 1 + 29) / 30;
   using namespace detail;
   uint32_t a[N], b[N], u[N], v[N];

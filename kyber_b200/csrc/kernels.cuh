@@ -68,8 +68,8 @@ B2K_D void jac_to_affine_bg(Affine<F>& r, const Jac<F>& p) {
 template <class CV> struct MulGlv { static constexpr bool enabled = false; };
 template <> struct MulGlv<Bls381G1> { static constexpr bool enabled = true; };
 
-template <class CV, bool AFFINE_OUT>
-__global__ void __launch_bounds__(128) k_mul_batch(size_t n, const uint8_t* __restrict__ scalars,
+template <class CV, bool AFFINE_OUT, int MINB = 1>
+__global__ void __launch_bounds__(128, MINB) k_mul_batch(size_t n, const uint8_t* __restrict__ scalars,
                                                    const uint8_t* __restrict__ wire, uint8_t* __restrict__ out,
                                                    uint32_t* flags, int use_glv) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -85,9 +85,9 @@ __global__ void __launch_bounds__(128) k_mul_batch(size_t n, const uint8_t* __re
   Jac<typename CV::F> r;
   if constexpr (MulGlv<CV>::enabled) {
     if (use_glv) scalar_mul_glv_bls381(r, k, p, InvBingcd{});
-    else scalar_mul<CV>(r, k, p);
+    else scalar_mul_w4<CV>(r, k, p, InvBingcd{});
   } else {
-    scalar_mul<CV>(r, k, p);
+    scalar_mul_w4<CV>(r, k, p, InvBingcd{});
   }
   Affine<typename CV::F> a;
   jac_to_affine_bg(a, r);

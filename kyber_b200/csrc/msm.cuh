@@ -229,6 +229,64 @@ B2K_D void scalar_mul(Jac<typename CV::F>& r, const Scalar256& k, const Affine<t
   r = acc;
 }
 
+// ---- independent scalar multiplication, fixed signed windows (every curve) ---------------------------------------------
+// k P over signed radix-16 digits of the full 256-bit scalar and one affine table {P .. 8P}: 65 x (4 doublings + 1 mixed
+// addition), the same instruction stream in every lane (scalar_mul above pays an addition per bit as soon as ONE lane of
+// the warp has that bit set).  Valid for any k < 2^256 and any point of the curve: j P != infinity is only assumed for
+// j <= 8 when the table is normalised (true in the prime-order groups on this path; the exceptional cases of the additions
+// themselves are handled by jac_madd).
+template <class CV, class INV>
+B2K_D void scalar_mul_w4(Jac<typename CV::F>& r, const Scalar256& k, const Affine<typename CV::F>& p, INV inv_fn) {
+  using F = typename CV::F;
+  if (aff_is_inf(p)) { jac_set_inf(r); return; }
+  Affine<F> tab[8];
+  tab[0] = p;
+  {
+    Jac<F> tj[8];
+    jac_from_affine(tj[0], p);
+    jac_dbl(tj[1], tj[0]);
+    for (int j = 2; j < 8; j++) jac_madd(tj[j], tj[j - 1], p);
+    F pre[8], acc, zi, zi2;
+    f_set_one(acc);
+    for (int j = 1; j < 8; j++) { pre[j] = acc; f_mul(acc, acc, tj[j].Z); }
+    inv_fn(acc, acc);
+    for (int j = 7; j >= 1; j--) {
+      f_mul(zi, acc, pre[j]);
+      f_mul(acc, acc, tj[j].Z);
+      f_sqr(zi2, zi);
+      f_mul(tab[j].x, tj[j].X, zi2);
+      f_mul(zi2, zi2, zi);
+      f_mul(tab[j].y, tj[j].Y, zi2);
+    }
+  }
+  // s' = s + 0x888..8 (65 nibbles = 260 bits), top-aligned in 9 limbs; nibble_i(s') - 8 is the signed digit
+  uint32_t d[9];
+  {
+    uint32_t a[9];
+    uint64_t c = 0;
+    for (int j = 0; j < 9; j++) {
+      uint64_t t = (uint64_t)(j < 8 ? k.v[j] : 0u) + (j < 8 ? 0x88888888u : 0x8u) + c;
+      a[j] = (uint32_t)t; c = t >> 32;
+    }
+    for (int j = 8; j > 0; j--) d[j] = (a[j] << 28) | (a[j - 1] >> 4);
+    d[0] = a[0] << 28;
+  }
+  Jac<F> acc;
+  jac_set_inf(acc);
+  for (int i = 64; i >= 0; i--) {
+    if (i != 64) { jac_dbl(acc, acc); jac_dbl(acc, acc); jac_dbl(acc, acc); jac_dbl(acc, acc); }
+    const int e = (int)(d[8] >> 28) - 8;
+    for (int j = 8; j > 0; j--) d[j] = (d[j] << 4) | (d[j - 1] >> 28);
+    d[0] <<= 4;
+    if (e) {
+      Affine<F> q = tab[(e < 0 ? -e : e) - 1];
+      if (e < 0) f_neg(q.y, q.y);
+      jac_madd(acc, acc, q);
+    }
+  }
+  r = acc;
+}
+
 // ---- independent scalar multiplication on BLS12-381 G1 with the endomorphism -----------------------------------------
 // k P = +-k1 P + k2 (-phi P) with 127-bit k1, k2 (glv_split_bls381), both walked together in signed radix-16 digits over
 // ONE affine table {P, 2P .. 8P} (phi maps the table: x -> beta x): 33 x (4 doublings + 2 mixed additions) instead of

@@ -144,9 +144,13 @@ size_t msm_scratch_bytes(const b2k_ctx* ctx, size_t n, const MsmPlan& pl) {
   b += pad256((size_t)pl.W * T * sizeof(Xyzz<F>));  // partials
   b += pad256((size_t)pl.W * (1 + 128) * sizeof(Xyzz<F>));    // window sums + their sub-block partials
   size_t smax = (n * (size_t)pl.W) / (size_t)slice_len(n, pl, force_L) + 2;
+  const AffinePlan ap = affine_plan<CV>(ctx, n, pl);
+  if (ap.R > 0) {                                 // the slices after the rounds may be shorter, hence more numerous
+    size_t sa = ap.bound[ap.R] / (size_t)slice_len_entries(ap.bound[ap.R], force_L) + 2;
+    if (sa > smax) smax = sa;
+  }
   b += pad256(2 * smax * sizeof(Xyzz<F>));        // slice partials (worst case: smallest automatic L)
   b += pad256((total + 1) * 4) + pad256(4096);    // big-bucket list, block sums
-  const AffinePlan ap = affine_plan<CV>(ctx, n, pl);
   if (ap.R > 0) {
     b += 2 * pad256((total + 1) * 4);             // bucket offsets of the rounds (ping-pong)
     b += pad256(ap.bound[1] * sizeof(Affine<F>));
@@ -188,14 +192,16 @@ int msm_enqueue(b2k_ctx* ctx, size_t n_in, const MsmPlan& pl, const uint8_t* d_s
   }
   const uint32_t L = slice_len(n, pl, ctx->force_L);
   const uint32_t smax = (uint32_t)((n * (size_t)pl.W + L - 1) / L) + 1;
-  auto* spart = arena_take<Xyzz<F>>(ctx, 2 * (size_t)smax);
+  const AffinePlan ap = affine_plan<CV>(ctx, n, pl);
+  const uint32_t La = ap.R > 0 ? slice_len_entries(ap.bound[ap.R], ctx->force_L) : L;
+  const uint32_t sa = ap.R > 0 ? (uint32_t)((ap.bound[ap.R] + La - 1) / La) + 1 : 0;      // slices after the affine rounds
+  auto* spart = arena_take<Xyzz<F>>(ctx, 2 * (size_t)(sa > smax ? sa : smax));
   auto* big_list = arena_take<uint32_t>(ctx, total + 1);
   auto* bsum = arena_take<uint32_t>(ctx, 1024);
   if (!spart || !big_list || !bsum || total > 1024u * 1024u) {
     ctx->err = "scratch arena too small / too many buckets";
     return B2K_ERR_ARG;
   }
-  const AffinePlan ap = affine_plan<CV>(ctx, n, pl);
   uint32_t* offs_rt[2] = {nullptr, nullptr};
   Affine<F>* aff_rt[2] = {nullptr, nullptr};
   if (ap.R > 0) {
@@ -204,6 +210,14 @@ int msm_enqueue(b2k_ctx* ctx, size_t n_in, const MsmPlan& pl, const uint8_t* d_s
     aff_rt[0] = arena_take<Affine<F>>(ctx, ap.bound[1]);
     if (ap.R > 1) aff_rt[1] = arena_take<Affine<F>>(ctx, ap.bound[2]);
     if (!offs_rt[0] || !offs_rt[1] || !aff_rt[0] || (ap.R > 1 && !aff_rt[1])) { ctx->err = "scratch arena too small"; return B2K_ERR_ARG; }
+  }
+  {
+    int* lp = ctx->last_plan;
+    lp[0] = pl.c; lp[1] = pl.W; lp[2] = pl.nb; lp[3] = pl.m;
+    lp[4] = (int)La;
+    lp[5] = ap.R;
+    for (int r = 0; r < PT_MAX_ROUNDS; r++) lp[6 + r] = r < ap.R ? (int)ap.B[r] : 0;
+    lp[14] = glv ? 1 : 0;
   }
   uint32_t* big_count = bsum + 1023;      // last word of the block-sum page is never a block sum (<= 1023 blocks used)
   unsigned gb_n = (unsigned)((n + 255) / 256);
@@ -288,8 +302,6 @@ int msm_enqueue(b2k_ctx* ctx, size_t n_in, const MsmPlan& pl, const uint8_t* d_s
           in_cur = out;
         }
         CK(cudaEventRecord(ctx->ev[10], st));        // end of the rounds
-        const uint32_t La = slice_len_entries(ap.bound[ap.R], ctx->force_L);
-        const uint32_t sa = (uint32_t)((ap.bound[ap.R] + La - 1) / La) + 1;     // <= smax: spart is large enough
         k_msm_accumulate_slices_direct<CV, 4><<<(sa + 127) / 128, 128, 0, st>>>(sa, La, (uint32_t)total, in_cur, offs_cur, buckets, spart);
         nl++;
         CK(cudaEventRecord(ctx->ev[9], st));
@@ -384,7 +396,13 @@ int mul_batch_dev(b2k_ctx* ctx, size_t n, const void* d_scalars, const void* d_p
     return B2K_ERR_ARG;
   }
   CK(cudaSetDevice(ctx->device));
-  k_mul_batch<CV, AFF><<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(
+  const unsigned grid = (unsigned)((n + 127) / 128);
+  bool launched = false;
+  if constexpr (MulGlv<CV>::enabled) {            // BLS12-381 G1: resident blocks per SM selectable (register cap), tuning aid
+    if (ctx->mul_minb == 3) { k_mul_batch<CV, AFF, 3><<<grid, 128, 0, ctx->stream>>>(n, (const uint8_t*)d_scalars, (const uint8_t*)d_points, (uint8_t*)d_out, ctx->d_flags, ctx->use_glv); launched = true; }
+    else if (ctx->mul_minb == 4) { k_mul_batch<CV, AFF, 4><<<grid, 128, 0, ctx->stream>>>(n, (const uint8_t*)d_scalars, (const uint8_t*)d_points, (uint8_t*)d_out, ctx->d_flags, ctx->use_glv); launched = true; }
+  }
+  if (!launched) k_mul_batch<CV, AFF><<<grid, 128, 0, ctx->stream>>>(
       n, (const uint8_t*)d_scalars, (const uint8_t*)d_points, (uint8_t*)d_out, ctx->d_flags, ctx->use_glv);
   CK(cudaGetLastError());
   ctx->launches += 1;

@@ -452,4 +452,69 @@ class SchemeOnG1 {
 
 }  // namespace bdn
 
+// ---- share (share/poly.go) on the engine, over BLS12-381 G1 (the group drand keeps its distributed key in) ----------------
+namespace share {
+
+struct PriShare { uint32_t I; Scalar V; };       // share/poly.go:29-32
+struct PubShare { uint32_t I; G1Elt V; };        // share/poly.go:299-302
+
+// share.PubPoly (poly.go:304-409) with base point = the group generator: Eval is Horner over the commitments at x = i + 1
+// (poly.go:340-347), Check compares it with V * B (poly.go:405-409).  EvalBatch / CheckBatch are the batch extension the
+// verification loops of share/vss and share/dkg re-point to (one device call for every share of every dealer).
+class PubPoly {
+ public:
+  PubPoly(const Suite& s, std::vector<G1Elt> commits) : s_(s), commits_(std::move(commits)) {
+    if (commits_.empty()) throw std::logic_error("share: empty commitment vector");
+  }
+  int Threshold() const { return (int)commits_.size(); }
+  const G1Elt& Commit() const { return commits_[0]; }                                     // poly.go:335-338
+  PubShare Eval(uint32_t i) const { return EvalBatch({i})[0]; }
+  std::vector<PubShare> EvalBatch(const std::vector<uint32_t>& idx) const {
+    const size_t t = commits_.size(), n = idx.size();
+    Bytes cb(96 * t), out(96 * n);
+    for (size_t j = 0; j < t; j++) std::memcpy(&cb[96 * j], commits_[j].aff_.data(), 96);
+    s_.engine()->check(b2k_bls12381_g1_pubpoly_eval(s_.engine()->ctx(), t, cb.data(), n, idx.data(), out.data()));
+    std::vector<PubShare> r;
+    for (size_t k = 0; k < n; k++) { PubShare ps{idx[k], G1Elt(s_.engine())}; std::memcpy(ps.V.aff_.data(), &out[96 * k], 96); r.push_back(ps); }
+    return r;
+  }
+  bool Check(const PriShare& sh) const { return CheckBatch({this}, {{sh}})[0][0]; }
+  // ok[d][k] = polys[d]->Check(shares[d][k]); every dealer must bring the same number of shares and the same threshold
+  static std::vector<std::vector<bool>> CheckBatch(const std::vector<const PubPoly*>& polys, const std::vector<std::vector<PriShare>>& shares) {
+    const size_t m = polys.size();
+    if (m == 0 || shares.size() != m) throw std::logic_error("share: dealers and share lists must match");
+    const size_t t = polys[0]->commits_.size(), n = shares[0].size();
+    Bytes cb(96 * m * t), sb(32 * m * n), ok(m * n);
+    std::vector<uint32_t> idx(m * n);
+    for (size_t d = 0; d < m; d++) {
+      if (polys[d]->commits_.size() != t || shares[d].size() != n) throw std::logic_error("share: ragged batch");
+      for (size_t j = 0; j < t; j++) std::memcpy(&cb[96 * (d * t + j)], polys[d]->commits_[j].aff_.data(), 96);
+      for (size_t k = 0; k < n; k++) { idx[d * n + k] = shares[d][k].I; Bytes b = shares[d][k].V.MarshalBinary(); std::memcpy(&sb[32 * (d * n + k)], b.data(), 32); }
+    }
+    const Suite& s = polys[0]->s_;
+    s.engine()->check(b2k_bls12381_g1_pubpoly_check(s.engine()->ctx(), m, t, cb.data(), n, idx.data(), sb.data(), ok.data()));
+    std::vector<std::vector<bool>> r(m, std::vector<bool>(n));
+    for (size_t d = 0; d < m; d++) for (size_t k = 0; k < n; k++) r[d][k] = ok[d * n + k] != 0;
+    return r;
+  }
+ private:
+  const Suite& s_;
+  std::vector<G1Elt> commits_;
+};
+
+// share.RecoverCommit (poly.go:449-476): the caller passes the first t shares after xyCommit's sort by index (poly.go:418-445)
+inline G1Elt RecoverCommit(const Suite& s, const std::vector<PubShare>& shares) {
+  const size_t t = shares.size();
+  if (t == 0) throw std::runtime_error("share: not enough good public shares to reconstruct secret commitment");
+  std::vector<uint32_t> idx(t);
+  Bytes pb(96 * t), out(48);
+  for (size_t k = 0; k < t; k++) { idx[k] = shares[k].I; std::memcpy(&pb[96 * k], shares[k].V.aff_.data(), 96); }
+  s.engine()->check(b2k_bls12381_g1_recover_commit(s.engine()->ctx(), t, idx.data(), pb.data(), out.data()));
+  G1Elt r(s.engine());
+  r.UnmarshalBinary(out);
+  return r;
+}
+
+}  // namespace share
+
 }  // namespace b200

@@ -2,6 +2,7 @@
 // the reference's own generic tests: testGroup (pairing/bls12381/bls12381_test.go:196-418 = util/test/test.go:
 // 325-401), the pairing property tests (:448-474, :580-631) and sign/bls tests (sign/bls/bls_test.go).
 // Run by tests/test_gpu_cpp_host.py on the GPU box.  Prints "ok <name>" per check; exit code != 0 on failure.
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <random>
@@ -160,6 +161,34 @@ int main() {
     // plain sum of keys (no coefficients) must NOT verify the BDN aggregate: the coefficients are in effect
     G2Elt plain(eng); plain.Null(); for (int i : {0, 2, 4}) plain.Add(plain, pks[i]);
     CHECK("bdn.plain_key_sum_fails", !bs.Verify(plain, msg, asig.MarshalBinary()));
+  }
+
+  // share (share/poly_test.go shape: TestPublicCheck, TestPublicRecovery): commitments of a random polynomial, every private
+  // share checks against them, a wrong share does not, t public shares recover the commitment of the secret
+  {
+    const int t = 4, n = 6;
+    std::vector<Scalar> coef; std::vector<G1Elt> commits;
+    for (int j = 0; j < t; j++) { coef.push_back(pick(rng)); G1Elt c(eng); c.Mul(coef[j], nullptr); commits.push_back(c); }
+    share::PubPoly pub(suite, commits);
+    auto eval = [&](uint32_t i) { Scalar x, acc; x.SetInt64((int64_t)i + 1); acc.Zero(); for (int j = t - 1; j >= 0; j--) { acc.Mul(acc, x); acc.Add(acc, coef[j]); } return acc; };
+    std::vector<share::PriShare> pri;
+    for (uint32_t i = 0; i < (uint32_t)n; i++) pri.push_back({i, eval(i)});
+    bool all = true;
+    for (auto& sh : pri) all = all && pub.Check(sh);
+    CHECK("share.check_every_share", all);
+    share::PriShare bad = pri[2]; bad.V.Add(bad.V, one);
+    CHECK("share.check_rejects_wrong_share", !pub.Check(bad));
+    G1Elt v3(eng); v3.Mul(pri[3].V, nullptr);
+    CHECK("share.eval_equals_share_times_base", pub.Eval(3).V.Equal(v3));
+    std::vector<G1Elt> commits2 = commits; commits2[1].Mul(pick(rng), nullptr);
+    share::PubPoly pub2(suite, commits2);
+    auto grid = share::PubPoly::CheckBatch({&pub, &pub2}, {pri, pri});
+    bool row0 = true, row1 = false;
+    for (int k = 0; k < n; k++) { row0 = row0 && grid[0][k]; row1 = row1 || grid[1][k]; }
+    CHECK("share.check_batch_two_dealers", row0 && !row1);
+    std::vector<share::PubShare> pubs = pub.EvalBatch({5, 1, 2, 4});
+    std::sort(pubs.begin(), pubs.end(), [](const share::PubShare& a, const share::PubShare& b) { return a.I < b.I; });
+    CHECK("share.recover_commit", share::RecoverCommit(suite, pubs).Equal(pub.Commit()));
   }
 
   printf("%s: %d failure(s)\n", fails ? "FAILED" : "PASSED", fails);

@@ -19,6 +19,9 @@ extern "C" {
   void emul_##name##_inv(const uint32_t* a, uint32_t* r) {                                         \
     Fp<C> x, z; for (int i = 0; i < C::N; i++) x.v[i] = a[i];                                      \
     fp_inv(z, x); for (int i = 0; i < C::N; i++) r[i] = z.v[i]; }                                  \
+  void emul_##name##_inv_fermat(const uint32_t* a, uint32_t* r) {                                  \
+    Fp<C> x, z; for (int i = 0; i < C::N; i++) x.v[i] = a[i];                                      \
+    fp_inv_fermat(z, x); for (int i = 0; i < C::N; i++) r[i] = z.v[i]; }                           \
   void emul_##name##_to_mont(const uint32_t* a, uint32_t* r) {                                     \
     Fp<C> x, z; for (int i = 0; i < C::N; i++) x.v[i] = a[i];                                      \
     fp_to_mont(z, x); for (int i = 0; i < C::N; i++) r[i] = z.v[i]; }                              \
@@ -56,6 +59,17 @@ static void emul_mul_batch_glv(size_t n, const uint8_t* scalars, const uint8_t* 
     Affine<CV::F> p; CV::load(p, pts + CV::IN_BYTES * i);
     Jac<CV::F> r; scalar_mul_glv_bls381(r, k, p, EmulInv{});
     Affine<CV::F> a; jac_to_affine(a, r);
+    CV::store(out + CV::OUT_BYTES * i, a);
+  }
+}
+
+template <class CV>
+static void emul_mul_batch_w4(size_t n, const uint8_t* scalars, const uint8_t* pts, uint8_t* out) {
+  for (size_t i = 0; i < n; i++) {
+    Scalar256 k; scalar_load_be(k, scalars + 32 * i);
+    Affine<typename CV::F> p; CV::load(p, pts + CV::IN_BYTES * i);
+    Jac<typename CV::F> r; scalar_mul_w4<CV>(r, k, p, EmulInv{});
+    Affine<typename CV::F> a; jac_to_affine(a, r);
     CV::store(out + CV::OUT_BYTES * i, a);
   }
 }
@@ -133,6 +147,8 @@ static int emul_msm(size_t n, const uint8_t* scalars, const uint8_t* pts, int c,
 }
 
 extern "C" {
+void emul_bls12381_g1_mul_batch_w4(size_t n, const uint8_t* s, const uint8_t* p, uint8_t* o) { emul_mul_batch_w4<Bls381G1>(n, s, p, o); }
+void emul_bn254_g1_mul_batch_w4(size_t n, const uint8_t* s, const uint8_t* p, uint8_t* o) { emul_mul_batch_w4<Bn254G1>(n, s, p, o); }
 void emul_bls12381_g1_mul_batch_glv(size_t n, const uint8_t* s, const uint8_t* p, uint8_t* o) { emul_mul_batch_glv(n, s, p, o); }
 void emul_bls12381_g1_mul_batch(size_t n, const uint8_t* s, const uint8_t* p, uint8_t* o) { emul_mul_batch<Bls381G1>(n, s, p, o); }
 int emul_bls12381_g1_msm(size_t n, const uint8_t* s, const uint8_t* p, int c, int m, uint8_t* o) { return emul_msm<Bls381G1>(n, s, p, c, m, o); }
@@ -222,6 +238,7 @@ int emul_bls12381_g2_decompress(const uint8_t* in96, uint8_t* out192) {
   if (ok) Bls381G2::store_affine(out192, a);
   return ok ? 1 : 0;
 }
+void emul_bls12381_g2_mul_batch_w4(size_t n, const uint8_t* s, const uint8_t* p, uint8_t* o) { emul_mul_batch_w4<Bls381G2>(n, s, p, o); }
 void emul_bls12381_g2_mul_batch(size_t n, const uint8_t* s, const uint8_t* p, uint8_t* o) { emul_mul_batch<Bls381G2>(n, s, p, o); }
 int emul_bls12381_g2_msm(size_t n, const uint8_t* s, const uint8_t* p, int c, int m, int L, uint8_t* o) { return emul_msm<Bls381G2>(n, s, p, c, m, o, L); }
 }

@@ -86,7 +86,9 @@ def test_device_field_code_under_host_emulation(emul):
             assert val(out) == (a - b) % p
         for a in vals[:12]:
             out = (ctypes.c_uint32 * n)()
-            getattr(emul, f"emul_{name}_inv")(lim(a * R % p), out)
+            getattr(emul, f"emul_{name}_inv")(lim(a * R % p), out)                 # binary GCD (what the kernels use)
+            assert val(out) == (pow(a, -1, p) * R % p if a else 0)
+            getattr(emul, f"emul_{name}_inv_fermat")(lim(a * R % p), out)          # a^(p-2): the independent cross-check
             assert val(out) == (pow(a, -1, p) * R % p if a else 0)
 
 

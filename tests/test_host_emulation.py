@@ -121,6 +121,37 @@ def test_glv_windowed_scalar_mul_body(emul):
         assert out.raw[48 * i:48 * i + 48] == o.g1_compress(o.g1_mul(ks[i], pts[i])), (i, hex(ks[i]))
 
 
+def test_fixed_window_scalar_mul_bodies(emul):
+    """scalar_mul_w4 (k_mul_batch on every curve): signed radix-16 digits of the whole 256-bit scalar over one affine
+    table -- BLS12-381 G1 and G2, bn254 G1; edge scalars of the recoding (runs of 8s, 7s, fs, top nibble), infinity."""
+    from oracle import bn254 as o4
+    rng = random.Random(22)
+    edge = [0, 1, 2, 7, 8, 9, 15, 16, 17, int("8" * 60, 16), int("7" * 63, 16), int("f" * 62, 16), (1 << 254) + 8]
+    ks = [k % o.R for k in edge] + [o.R - 1, o.R - 8] + [rng.randrange(o.R) for _ in range(12)]
+    n = len(ks)
+    pts = [o.g1_mul(rng.randrange(1, o.R)) for _ in range(n)]
+    pts[4] = None
+    sb = b"".join(o.scalar_to_bytes(k) for k in ks)
+    out = ctypes.create_string_buffer(48 * n)
+    emul.emul_bls12381_g1_mul_batch_w4(ctypes.c_size_t(n), sb, b"".join(o.g1_to_affine_bytes(p) for p in pts), out)
+    for i in range(n):
+        assert out.raw[48 * i:48 * i + 48] == o.g1_compress(o.g1_mul(ks[i], pts[i])), (i, hex(ks[i]))
+    m = 6
+    p2 = [o.g2_mul(rng.randrange(1, o.R)) for _ in range(m)]
+    out2 = ctypes.create_string_buffer(96 * m)
+    emul.emul_bls12381_g2_mul_batch_w4(ctypes.c_size_t(m), b"".join(o.scalar_to_bytes(k) for k in ks[-m:]),
+                                       b"".join(o.g2_to_affine_bytes(p) for p in p2), out2)
+    for i in range(m):
+        assert out2.raw[96 * i:96 * i + 96] == o.g2_compress(o.g2_mul(ks[-m:][i], p2[i])), i
+    k4 = [k % o4.ORDER for k in edge] + [o4.ORDER - 1] + [rng.randrange(o4.ORDER) for _ in range(6)]
+    p4 = [o4.g1_mul(rng.randrange(1, o4.ORDER)) for _ in range(len(k4))]
+    out4 = ctypes.create_string_buffer(64 * len(k4))
+    emul.emul_bn254_g1_mul_batch_w4(ctypes.c_size_t(len(k4)), b"".join(k.to_bytes(32, "big") for k in k4),
+                                    b"".join(o4.g1_marshal(p) for p in p4), out4)
+    for i in range(len(k4)):
+        assert out4.raw[64 * i:64 * i + 64] == o4.g1_marshal(o4.g1_mul(k4[i], p4[i])), i
+
+
 def test_affine_pair_tree_round_bodies(emul):
     """msm_affine.cuh: R pair-tree rounds (batched affine additions, one inversion per thread) followed by the balanced
     XYZZ slices give the oracle's MSM, including the exceptional cases of the affine group law: repeated points in one

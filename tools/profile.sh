@@ -9,9 +9,11 @@ export B2K_SKIP_PAIRINGS=1
 # every launch with its device time (cold-cache, serialised: compare SHARES, not absolutes)
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_${TAG}.csv \
     python bench.py --steps 2 --warmup 3 > gpurun_out/bench_under_ncu_${TAG}.log 2>&1
-# the top kernel, once
-ncu --set full --clock-control none --import-source on -k regex:k_msm_accumulate_slices -s 3 -c 1 \
-    -o gpurun_out/accumulate_${TAG} -f python bench.py --steps 1 --warmup 3 > gpurun_out/ncu_full_${TAG}.log 2>&1
+python tools/summarize_launches.py gpurun_out/launches_${TAG}.csv > gpurun_out/${TAG}_launches_summary.txt 2>&1
+# the bucket-accumulate pass of ONE MSM, once: every pair-tree round + the XYZZ slices (skip the 3 warm-up MSMs' launches)
+NK=${B2K_PROFILE_PASS_KERNELS:-5}
+ncu --set full --clock-control none --import-source on -k "regex:k_msm_pairtree_round|k_msm_accumulate_slices" -s $((3 * NK)) -c $NK \
+    -o gpurun_out/accumulate_${TAG} -f python bench.py --steps 1 --warmup 3 --contexts 1 > gpurun_out/ncu_full_${TAG}.log 2>&1
 # gpurun_out/ travels back only below 64 MiB: keep the text pages, drop the report
 ncu -i gpurun_out/accumulate_${TAG}.ncu-rep --page details > gpurun_out/${TAG}_accumulate_ncu_details.txt 2>&1
 ncu -i gpurun_out/accumulate_${TAG}.ncu-rep --page raw --csv > gpurun_out/${TAG}_accumulate_ncu_raw.csv 2>&1
