@@ -62,7 +62,8 @@ int b2k_synchronize(b2k_ctx* ctx);
 int b2k_last_timings(b2k_ctx* ctx, float* ms, int max);
 /* Parameters the LAST MSM of this context ran with: [0] window bits c  [1] windows W  [2] buckets per window
  * [3] reduction chunk  [4] slice length of the XYZZ pass  [5] affine pair-tree rounds R  [6..13] additions per thread of
- * round 0..7  [14] 1 when the endomorphism split was used.  Returns the number of entries written. */
+ * round 0..7  [14] 1 when the endomorphism split was used  [15] 1 when the rounds ran as three kernels each.
+ * Returns the number of entries written. */
 int b2k_last_msm_plan(const b2k_ctx* ctx, int* out, int max);
 /* Override the MSM window size (0 = automatic).  Testing / tuning aid. */
 int b2k_set_msm_window(b2k_ctx* ctx, int c);
@@ -81,8 +82,11 @@ int b2k_set_msm_glv(b2k_ctx* ctx, int on);
 /* Affine pair-tree rounds in front of the XYZZ bucket slices (BLS12-381 G1 MSM): every round replaces the operands of
  * each bucket by the sums of neighbouring pairs, computed as batched AFFINE additions (6 field products each instead of
  * 10) around one inversion per thread.  rounds: -1 = automatic (default), 0 = off, 1..8; batch: additions per thread
- * (8..64, 0 = automatic).  Same result bytes either way; kept switchable for A/B timing. */
+ * (8..64 fused / ..1024 split, 0 = automatic).  Same result bytes either way; kept switchable for A/B timing. */
 int b2k_set_msm_affine(b2k_ctx* ctx, int rounds, int batch);
+/* 1 (default) = every affine round runs as three kernels (forward prefix products, one inversion per thread, backward
+ * additions; batch up to 1024), 0 = one fused kernel per round (batch up to 64, prefix products in local memory).  A/B aid. */
+int b2k_set_msm_affine_split(b2k_ctx* ctx, int split);
 /* Resident bucket-accumulate blocks per SM (4..6; launch bound => register cap).  Tuning aid. */
 int b2k_set_msm_occupancy(b2k_ctx* ctx, int blocks_per_sm);
 /* Resident blocks per SM of the BLS12-381 G1 Point.Mul batch kernel (0 = unconstrained [default], 3, 4).  Tuning aid. */

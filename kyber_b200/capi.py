@@ -44,6 +44,8 @@ def load_library() -> C.CDLL:
         "b2k_set_msm_chunk": (C.c_int, [vp, C.c_int]),
         "b2k_set_msm_affine": (C.c_int, [vp, C.c_int, C.c_int]),
         "b2k_last_msm_plan": (C.c_int, [vp, C.POINTER(C.c_int), C.c_int]),
+        "b2k_set_msm_affine_split": (C.c_int, [vp, C.c_int]),
+        "b2k_set_mul_occupancy": (C.c_int, [vp, C.c_int]),
     }
     sigs["b2k_bls12381_pair"] = (C.c_int, [vp, sz, vp, vp, vp])
     sigs["b2k_bls12381_pair_dev"] = (C.c_int, [vp, sz, vp, vp, vp])
@@ -170,6 +172,13 @@ class Engine:
         """affine pair-tree rounds of the BLS12-381 G1 MSM: -1 automatic, 0 off, 1..8 forced; batch = additions per thread"""
         self._check(self.lib.b2k_set_msm_affine(self.h, int(rounds), int(batch)))
 
+    def set_msm_affine_split(self, split: bool):
+        """affine rounds as three kernels each (True, default) or one fused kernel (False)"""
+        self._check(self.lib.b2k_set_msm_affine_split(self.h, int(split)))
+
+    def set_mul_occupancy(self, blocks_per_sm: int):
+        self._check(self.lib.b2k_set_mul_occupancy(self.h, int(blocks_per_sm)))
+
     def last_msm_plan(self) -> dict:
         """parameters of the last MSM: window bits, windows, chunk, slice length, affine rounds and their batch widths"""
         arr = (C.c_int * 16)()
@@ -177,7 +186,8 @@ class Engine:
         if n < 0:
             self._check(n)
         return {"c": arr[0], "W": arr[1], "buckets_per_window": arr[2], "chunk": arr[3], "slice_len": arr[4],
-                "affine_rounds": arr[5], "affine_batch": [arr[6 + r] for r in range(arr[5])], "glv": bool(arr[14])}
+                "affine_rounds": arr[5], "affine_batch": [arr[6 + r] for r in range(arr[5])], "glv": bool(arr[14]),
+                "affine_split": bool(arr[15])}
 
     def last_timings(self):
         arr = (C.c_float * 16)()

@@ -135,15 +135,21 @@ int b2k_last_timings(b2k_ctx* ctx, float* ms, int max) {
 
 int b2k_last_msm_plan(const b2k_ctx* ctx, int* out, int max) {
   if (!ctx || !out || max <= 0) return B2K_ERR_ARG;
-  int n = max < 15 ? max : 15;
+  int n = max < 16 ? max : 16;
   for (int i = 0; i < n; i++) out[i] = ctx->last_plan[i];
   return n;
 }
 
 int b2k_set_msm_affine(b2k_ctx* ctx, int rounds, int batch) {
-  if (!ctx || rounds < -1 || rounds > 8 || batch < 0 || batch > 64) return B2K_ERR_ARG;
+  if (!ctx || rounds < -1 || rounds > 8 || batch < 0 || batch > 1024) return B2K_ERR_ARG;
   ctx->affine_rounds = rounds;
   ctx->affine_batch = batch;
+  return B2K_OK;
+}
+
+int b2k_set_msm_affine_split(b2k_ctx* ctx, int split) {
+  if (!ctx || (split != 0 && split != 1)) return B2K_ERR_ARG;
+  ctx->affine_split = split;
   return B2K_OK;
 }
 

@@ -30,6 +30,7 @@ struct b2k_ctx {
   int msm_groups = 1;               // window groups of the overlapped MSM tail; measured SLOWER than the serial pipeline on
                                     // B200 (accumulate blocks fill the register file, nothing co-resides): kept as an experiment
   int affine_rounds = -1;           // affine pair-tree rounds before the XYZZ slices: -1 = automatic, 0 = off (A/B), 1..8 forced
+  int affine_split = 1;             // 1 = every round as three kernels (forward products / inversions / backward additions), 0 = one fused kernel
   int affine_batch = 0;             // outputs (batched affine additions) per thread of a round, 8..64; 0 = automatic
   int mul_minb = 0;                 // BLS12-381 G1 Point.Mul batches: resident blocks per SM (0 = compiler's choice, 3, 4), tuning aid
   int acc_minb = 4;                 // resident accumulate blocks per SM (launch bound), tuning aid

@@ -244,6 +244,29 @@ __global__ void __launch_bounds__(128, 4) k_msm_pairtree_round(uint32_t B, uint3
   msm_pairtree_round<CV, FIRST>(t, B, total, in, entries, offs_in, offs_out, out);
 }
 
+// the same round split by phase (msm_affine.cuh): T = threads of the launch = stride of pre[]
+template <class CV, bool FIRST>
+__global__ void __launch_bounds__(128, 5) k_pt_forward(uint32_t B, uint32_t total, const Affine<typename CV::F>* __restrict__ in,
+                                                       const uint32_t* __restrict__ entries, const uint32_t* __restrict__ offs_in,
+                                                       const uint32_t* __restrict__ offs_out, typename CV::F* __restrict__ pre,
+                                                       typename CV::F* __restrict__ accs) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  msm_pairtree_forward<CV, FIRST>(t, B, gridDim.x * blockDim.x, total, in, entries, offs_in, offs_out, pre, accs);
+}
+template <class F>
+__global__ void __launch_bounds__(128, 4) k_pt_invert(uint32_t B, uint32_t total, const uint32_t* __restrict__ offs_out, F* __restrict__ accs) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  msm_pairtree_invert<F>(t, B, total, offs_out, accs);
+}
+template <class CV, bool FIRST>
+__global__ void __launch_bounds__(128, 4) k_pt_backward(uint32_t B, uint32_t total, const Affine<typename CV::F>* __restrict__ in,
+                                                        const uint32_t* __restrict__ entries, const uint32_t* __restrict__ offs_in,
+                                                        const uint32_t* __restrict__ offs_out, const typename CV::F* __restrict__ pre,
+                                                        const typename CV::F* __restrict__ accs, Affine<typename CV::F>* __restrict__ out) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  msm_pairtree_backward<CV, FIRST>(t, B, gridDim.x * blockDim.x, total, in, entries, offs_in, offs_out, pre, accs, out);
+}
+
 // buckets cut by slice boundaries: add their partials (<= 64 serially, larger ones go to a work list)
 template <class CV>
 __global__ void __launch_bounds__(128) k_msm_fixup(uint32_t total, uint32_t L, const uint32_t* __restrict__ offs,

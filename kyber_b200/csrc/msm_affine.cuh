@@ -114,4 +114,93 @@ B2K_D void msm_pairtree_round(uint32_t t, uint32_t B, uint32_t total, const Affi
   }
 }
 
+// ---- the same round as three kernels (forward products / inversions / backward additions) ------------------------------
+// One fused kernel keeps three very different code regions (one inlined product; the 2 000-instruction inversion; five
+// inlined products) resident at once and runs them all at the register budget of the widest; split, every phase has
+// compact code and its own occupancy, the prefix products travel through a coalesced global array pre[j * T + t] and the
+// running product / its inverse through accs[t].  The forward pass reads only the x coordinates (dx is all it needs;
+// x = 0 or dx = 0 fall back to the full classification).
+template <class CV, bool FIRST>
+B2K_D void pt_denominator(typename CV::F& d, const Affine<typename CV::F>* in, const uint32_t* entries, uint32_t a, uint32_t end) {
+  using F = typename CV::F;
+  f_set_one(d);
+  if (a + 1 >= end) return;                           // single operand: carried over
+  F x1, x2, dx;
+  if (FIRST) { x1 = in[entries[a] & 0x7fffffffu].x; x2 = in[entries[a + 1] & 0x7fffffffu].x; }
+  else { x1 = in[a].x; x2 = in[a + 1].x; }
+  f_sub(dx, x2, x1);
+  if (!f_is_zero(x1) && !f_is_zero(x2) && !f_is_zero(dx)) { d = dx; return; }
+  Affine<F> p1, p2;                                   // rare: possible infinity / doubling / cancellation
+  const bool pair = pt_fetch<CV, FIRST>(p1, p2, in, entries, a, end);
+  pt_classify(d, p1, p2, pair);
+}
+
+// forward: T = number of threads of the round (stride of pre[]); thread t leaves its running product in accs[t]
+template <class CV, bool FIRST>
+B2K_D void msm_pairtree_forward(uint32_t t, uint32_t B, uint32_t T, uint32_t total, const Affine<typename CV::F>* in,
+                                const uint32_t* entries, const uint32_t* offs_in, const uint32_t* offs_out,
+                                typename CV::F* pre, typename CV::F* accs) {
+  using F = typename CV::F;
+  const uint32_t nout = offs_out[total];
+  const uint32_t q0 = t * B;
+  if (q0 >= nout) return;
+  const uint32_t q1 = (nout - q0 < B) ? nout : q0 + B;
+  uint32_t g = msm_find_bucket(offs_out, total, q0);
+  uint32_t os = offs_out[g], oe = offs_out[g + 1], is = offs_in[g], ie = offs_in[g + 1];
+  F acc;
+  f_set_one(acc);
+  for (uint32_t q = q0; q < q1; q++) {
+    while (q >= oe) { g++; os = oe; oe = offs_out[g + 1]; is = ie; ie = offs_in[g + 1]; }
+    F d;
+    pt_denominator<CV, FIRST>(d, in, entries, is + 2 * (q - os), ie);
+    pre[(size_t)(q - q0) * T + t] = acc;
+    f_mul(acc, acc, d);
+  }
+  accs[t] = acc;
+}
+
+// inversions: one per thread that has outputs
+template <class F>
+B2K_D void msm_pairtree_invert(uint32_t t, uint32_t B, uint32_t total, const uint32_t* offs_out, F* accs) {
+  if ((uint64_t)t * B >= offs_out[total]) return;
+  F v = accs[t], r;
+  f_inv_bg(r, v);
+  accs[t] = r;
+}
+
+// backward: the additions themselves
+template <class CV, bool FIRST>
+B2K_D void msm_pairtree_backward(uint32_t t, uint32_t B, uint32_t T, uint32_t total, const Affine<typename CV::F>* in,
+                                 const uint32_t* entries, const uint32_t* offs_in, const uint32_t* offs_out,
+                                 const typename CV::F* pre, const typename CV::F* accs, Affine<typename CV::F>* out) {
+  using F = typename CV::F;
+  const uint32_t nout = offs_out[total];
+  const uint32_t q0 = t * B;
+  if (q0 >= nout) return;
+  const uint32_t q1 = (nout - q0 < B) ? nout : q0 + B;
+  uint32_t g = msm_find_bucket(offs_out, total, q1 - 1);
+  uint32_t os = offs_out[g], oe = offs_out[g + 1], is = offs_in[g], ie = offs_in[g + 1];
+  (void)oe;
+  F inv = accs[t];
+  for (uint32_t q = q1; q-- > q0;) {
+    while (q < os) { g--; os = offs_out[g]; ie = is; is = offs_in[g]; }
+    Affine<F> p1, p2, r;
+    F d, dinv, lam, tt;
+    const bool pair = pt_fetch<CV, FIRST>(p1, p2, in, entries, is + 2 * (q - os), ie);
+    const int kind = pt_classify(d, p1, p2, pair);
+    F pj = pre[(size_t)(q - q0) * T + t];
+    f_mul(dinv, inv, pj);
+    if (q > q0) f_mul(inv, inv, d);
+    if (kind == PT_DBL) { f_sqr(tt, p1.x); f_dbl(lam, tt); f_add(tt, lam, tt); }
+    else f_sub(tt, p2.y, p1.y);
+    f_mul(lam, tt, dinv);
+    f_sqr(r.x, lam); f_sub(r.x, r.x, p1.x); f_sub(r.x, r.x, p2.x);
+    f_sub(tt, p1.x, r.x); f_mul(r.y, lam, tt); f_sub(r.y, r.y, p1.y);
+    if (kind == PT_COPY1) r = p1;
+    else if (kind == PT_COPY2) r = p2;
+    else if (kind == PT_INF) aff_set_inf(r);
+    out[q] = r;
+  }
+}
+
 }  // namespace b2k

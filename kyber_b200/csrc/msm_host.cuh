@@ -98,6 +98,9 @@ struct AffinePlan {
   int R = 0;                            // rounds
   uint32_t B[PT_MAX_ROUNDS] = {};       // outputs per thread
   size_t bound[PT_MAX_ROUNDS + 1] = {}; // host-side upper bound of the operand count before round r (bound[R]: what the slices see)
+  uint32_t T[PT_MAX_ROUNDS] = {};       // threads of round r (multiple of the block size)
+  size_t pre_elems = 0;                 // split rounds: field elements of the prefix-product array (max over the rounds)
+  uint32_t max_T = 0;
 };
 // n = pairs the pipeline processes (msm_virtual_n)
 template <class CV>
@@ -107,11 +110,11 @@ inline AffinePlan affine_plan(const b2k_ctx* ctx, size_t n, const MsmPlan& pl) {
   if (!AffineTraits<CV>::enabled || ctx->use_v1 || ctx->msm_groups > 1) return ap;
   const size_t total = (size_t)pl.W * pl.nb;
   int R = ctx->affine_rounds;
-  if (R < 0) {                          // automatic: worth it for big problems; leave ~4..8 operands per bucket to the slices
-    R = 0;
+  if (R < 0) {                          // automatic: big problems only; measured best at C2 (64 operands per bucket): 2 rounds, the
+    R = 0;                              // later, smaller rounds no longer fill the chip and the XYZZ slices take over
     if (ap.bound[0] >= (size_t(1) << 20)) {
       const size_t avg = ap.bound[0] / total;
-      while (R < PT_MAX_ROUNDS && (avg >> R) >= 8) R++;
+      while (R < PT_MAX_ROUNDS && (avg >> R) >= 32) R++;
     }
   }
   if (R > PT_MAX_ROUNDS) R = PT_MAX_ROUNDS;
@@ -121,8 +124,12 @@ inline AffinePlan affine_plan(const b2k_ctx* ctx, size_t n, const MsmPlan& pl) {
     size_t B = ctx->affine_batch > 0 ? (size_t)ctx->affine_batch : ap.bound[r + 1] / 75776;   // 148 SMs x 512 threads
     if (ctx->affine_batch <= 0 && B < 32) B = 32;       // one inversion per thread: keep it amortised
     if (B < 1) B = 1;
-    if (B > (size_t)PT_MAXB) B = PT_MAXB;
+    const size_t bmax = ctx->affine_split ? 1024 : (size_t)PT_MAXB;    // the fused kernel keeps B prefix products in local memory
+    if (B > bmax) B = bmax;
     ap.B[r] = (uint32_t)B;
+    ap.T[r] = (uint32_t)(((ap.bound[r + 1] + B - 1) / B + 127) / 128 * 128);
+    if ((size_t)ap.T[r] * B > ap.pre_elems) ap.pre_elems = (size_t)ap.T[r] * B;
+    if (ap.T[r] > ap.max_T) ap.max_T = ap.T[r];
   }
   return ap;
 }
@@ -155,6 +162,7 @@ size_t msm_scratch_bytes(const b2k_ctx* ctx, size_t n, const MsmPlan& pl) {
     b += 2 * pad256((total + 1) * 4);             // bucket offsets of the rounds (ping-pong)
     b += pad256(ap.bound[1] * sizeof(Affine<F>));
     if (ap.R > 1) b += pad256(ap.bound[2] * sizeof(Affine<F>));
+    if (ctx->affine_split) b += pad256(ap.pre_elems * sizeof(F)) + pad256((size_t)ap.max_T * sizeof(F));
   }
   return b + 8192;
 }
@@ -211,6 +219,13 @@ int msm_enqueue(b2k_ctx* ctx, size_t n_in, const MsmPlan& pl, const uint8_t* d_s
     if (ap.R > 1) aff_rt[1] = arena_take<Affine<F>>(ctx, ap.bound[2]);
     if (!offs_rt[0] || !offs_rt[1] || !aff_rt[0] || (ap.R > 1 && !aff_rt[1])) { ctx->err = "scratch arena too small"; return B2K_ERR_ARG; }
   }
+  F* pt_pre = nullptr;
+  F* pt_accs = nullptr;
+  if (ap.R > 0 && ctx->affine_split) {
+    pt_pre = arena_take<F>(ctx, ap.pre_elems);
+    pt_accs = arena_take<F>(ctx, ap.max_T);
+    if (!pt_pre || !pt_accs) { ctx->err = "scratch arena too small"; return B2K_ERR_ARG; }
+  }
   {
     int* lp = ctx->last_plan;
     lp[0] = pl.c; lp[1] = pl.W; lp[2] = pl.nb; lp[3] = pl.m;
@@ -218,6 +233,7 @@ int msm_enqueue(b2k_ctx* ctx, size_t n_in, const MsmPlan& pl, const uint8_t* d_s
     lp[5] = ap.R;
     for (int r = 0; r < PT_MAX_ROUNDS; r++) lp[6 + r] = r < ap.R ? (int)ap.B[r] : 0;
     lp[14] = glv ? 1 : 0;
+    lp[15] = (ap.R > 0 && ctx->affine_split) ? 1 : 0;
   }
   uint32_t* big_count = bsum + 1023;      // last word of the block-sum page is never a block sum (<= 1023 blocks used)
   unsigned gb_n = (unsigned)((n + 255) / 256);
@@ -294,10 +310,19 @@ int msm_enqueue(b2k_ctx* ctx, size_t n_in, const MsmPlan& pl, const uint8_t* d_s
           k_scan_blocks<<<sblocks, 1024, 0, st>>>((uint32_t)total, counts, offs_nxt, bsum);
           k_scan_tops<<<1, 1024, 0, st>>>(sblocks, (uint32_t)total, bsum, offs_nxt);
           k_scan_finish<<<sblocks, 1024, 0, st>>>((uint32_t)total, bsum, offs_nxt, cursor);
-          const size_t threads = (ap.bound[r + 1] + ap.B[r] - 1) / ap.B[r];
-          if (r == 0) k_msm_pairtree_round<CV, true><<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(ap.B[r], (uint32_t)total, in_cur, entries, offs_cur, offs_nxt, out);
-          else k_msm_pairtree_round<CV, false><<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(ap.B[r], (uint32_t)total, in_cur, nullptr, offs_cur, offs_nxt, out);
-          nl += 5;
+          const unsigned grid = ap.T[r] / 128;
+          if (ctx->affine_split) {
+            if (r == 0) k_pt_forward<CV, true><<<grid, 128, 0, st>>>(ap.B[r], (uint32_t)total, in_cur, entries, offs_cur, offs_nxt, pt_pre, pt_accs);
+            else k_pt_forward<CV, false><<<grid, 128, 0, st>>>(ap.B[r], (uint32_t)total, in_cur, nullptr, offs_cur, offs_nxt, pt_pre, pt_accs);
+            k_pt_invert<F><<<grid, 128, 0, st>>>(ap.B[r], (uint32_t)total, offs_nxt, pt_accs);
+            if (r == 0) k_pt_backward<CV, true><<<grid, 128, 0, st>>>(ap.B[r], (uint32_t)total, in_cur, entries, offs_cur, offs_nxt, pt_pre, pt_accs, out);
+            else k_pt_backward<CV, false><<<grid, 128, 0, st>>>(ap.B[r], (uint32_t)total, in_cur, nullptr, offs_cur, offs_nxt, pt_pre, pt_accs, out);
+            nl += 7;
+          } else {
+            if (r == 0) k_msm_pairtree_round<CV, true><<<grid, 128, 0, st>>>(ap.B[r], (uint32_t)total, in_cur, entries, offs_cur, offs_nxt, out);
+            else k_msm_pairtree_round<CV, false><<<grid, 128, 0, st>>>(ap.B[r], (uint32_t)total, in_cur, nullptr, offs_cur, offs_nxt, out);
+            nl += 5;
+          }
           offs_cur = offs_nxt;
           in_cur = out;
         }

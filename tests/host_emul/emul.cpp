@@ -75,7 +75,7 @@ static void emul_mul_batch_w4(size_t n, const uint8_t* scalars, const uint8_t* p
 }
 
 template <class CV>
-static int emul_msm(size_t n, const uint8_t* scalars, const uint8_t* pts, int c, int m, uint8_t* out, int L = 0, int rounds = 0, int PB = 8) {
+static int emul_msm(size_t n, const uint8_t* scalars, const uint8_t* pts, int c, int m, uint8_t* out, int L = 0, int rounds = 0, int PB = 8, bool split = false) {
   using F = typename CV::F;
   MsmPlan pl; pl.c = c; pl.W = (256 + c - 1) / c; pl.nb = 1 << (c - 1); pl.m = m;
   // K = sum_w 2^(c-1) 2^(cw)
@@ -112,6 +112,18 @@ static int emul_msm(size_t n, const uint8_t* scalars, const uint8_t* pts, int c,
       for (size_t g = 0; g < total; g++) no[g + 1] = no[g] + ((offs[g + 1] - offs[g] + 1) >> 1);
       std::vector<Affine<F>> nxt(no[total] + 1);
       uint32_t T = (no[total] + PB - 1) / PB + 1;      // one thread past the end: must be a no-op
+      if (split) {                                     // three kernels per round: forward / invert / backward
+        std::vector<F> pre((size_t)T * PB), accs(T);
+        for (uint32_t t = 0; t < T; t++) {
+          if (r == 0) msm_pairtree_forward<CV, true>(t, (uint32_t)PB, T, (uint32_t)total, P.data(), entries.data(), offs.data(), no.data(), pre.data(), accs.data());
+          else msm_pairtree_forward<CV, false>(t, (uint32_t)PB, T, (uint32_t)total, cur.data(), nullptr, offs.data(), no.data(), pre.data(), accs.data());
+        }
+        for (uint32_t t = 0; t < T; t++) msm_pairtree_invert<F>(t, (uint32_t)PB, (uint32_t)total, no.data(), accs.data());
+        for (uint32_t t = 0; t < T; t++) {
+          if (r == 0) msm_pairtree_backward<CV, true>(t, (uint32_t)PB, T, (uint32_t)total, P.data(), entries.data(), offs.data(), no.data(), pre.data(), accs.data(), nxt.data());
+          else msm_pairtree_backward<CV, false>(t, (uint32_t)PB, T, (uint32_t)total, cur.data(), nullptr, offs.data(), no.data(), pre.data(), accs.data(), nxt.data());
+        }
+      } else
       for (uint32_t t = 0; t < T; t++) {
         if (r == 0) msm_pairtree_round<CV, true>(t, (uint32_t)PB, (uint32_t)total, P.data(), entries.data(), offs.data(), no.data(), nxt.data());
         else msm_pairtree_round<CV, false>(t, (uint32_t)PB, (uint32_t)total, cur.data(), nullptr, offs.data(), no.data(), nxt.data());
@@ -179,6 +191,7 @@ int emul_glv_split_bls381(const uint8_t* k32, uint8_t* k1, uint8_t* k2) {
 }
 // balanced slices after `rounds` affine pair-tree rounds with PB outputs per thread
 int emul_bls12381_g1_msm_affine(size_t n, const uint8_t* s, const uint8_t* p, int c, int m, int L, int rounds, int PB, uint8_t* o) { return emul_msm<Bls381G1>(n, s, p, c, m, o, L, rounds, PB); }
+int emul_bls12381_g1_msm_affine_split(size_t n, const uint8_t* s, const uint8_t* p, int c, int m, int L, int rounds, int PB, uint8_t* o) { return emul_msm<Bls381G1>(n, s, p, c, m, o, L, rounds, PB, true); }
 int emul_bn254_g1_msm_affine(size_t n, const uint8_t* s, const uint8_t* p, int c, int m, int L, int rounds, int PB, uint8_t* o) { return emul_msm<Bn254G1>(n, s, p, c, m, o, L, rounds, PB); }
 int emul_bls12381_g1_msm_v2(size_t n, const uint8_t* s, const uint8_t* p, int c, int m, int L, uint8_t* o) { return emul_msm<Bls381G1>(n, s, p, c, m, o, L); }
 void emul_bn254_g1_mul_batch(size_t n, const uint8_t* s, const uint8_t* p, uint8_t* o) { emul_mul_batch<Bn254G1>(n, s, p, o); }

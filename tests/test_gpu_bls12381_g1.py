@@ -145,17 +145,20 @@ def test_msm_affine_pair_tree_rounds_agree(engine, dist_name):
     pts = engine.bls12381_g1_mul_batch_affine(wl.scalars_to_bytes(a), wl.G1_BLS12381_AFFINE * n)
     want = o.g1_compress(o.g1_mul(wl.dot_mod(s, a, o.R)))
     sb = wl.scalars_to_bytes(s)
-    for rounds, batch, c, L in ((1, 8, 0, 0), (2, 33, 8, 3), (3, 64, 6, 0), (5, 1, 5, 2), (8, 17, 4, 0), (4, 0, 16, 0)):
-        engine.set_msm_affine(rounds, batch)
-        engine.set_msm_window(c)
-        engine.set_msm_slice(L)
-        try:
-            got = engine.bls12381_g1_msm(sb, pts)
-        finally:
-            engine.set_msm_affine(-1, 0)
-            engine.set_msm_window(0)
-            engine.set_msm_slice(0)
-        assert got == want, (dist_name, rounds, batch, c, L)
+    for split in (True, False):               # every round as three kernels (default) / as one fused kernel
+        for rounds, batch, c, L in ((1, 8, 0, 0), (2, 33, 8, 3), (3, 64, 6, 0), (5, 1, 5, 2), (8, 17, 4, 0), (4, 0, 16, 0), (2, 300, 7, 0)):
+            engine.set_msm_affine_split(split)
+            engine.set_msm_affine(rounds, batch)
+            engine.set_msm_window(c)
+            engine.set_msm_slice(L)
+            try:
+                got = engine.bls12381_g1_msm(sb, pts)
+            finally:
+                engine.set_msm_affine_split(True)
+                engine.set_msm_affine(-1, 0)
+                engine.set_msm_window(0)
+                engine.set_msm_slice(0)
+            assert got == want, (dist_name, split, rounds, batch, c, L)
     engine.set_msm_affine(0, 0)               # off: the plain XYZZ pipeline
     try:
         assert engine.bls12381_g1_msm(sb, pts) == want

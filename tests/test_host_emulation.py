@@ -162,6 +162,8 @@ def test_affine_pair_tree_round_bodies(emul):
     pts[5] = None
     pts[6] = pts[7] = pts[8] = pts[9]                     # the same point four times
     pts[10] = o.g1_neg(pts[11])                           # P and -P
+    pts[13] = (0, 2)                                      # on the curve with x = 0 (outside G1: only the group law matters here)
+    pts[14] = (0, o.P - 2)
     pb = b"".join(o.g1_to_affine_bytes(p) for p in pts)
     sets = ([rng.randrange(o.R) for _ in range(n)], [0x123456789ABCDEF] * n, [rng.randrange(1 << 9) for _ in range(n)])
     for ks in sets:
@@ -171,6 +173,9 @@ def test_affine_pair_tree_round_bodies(emul):
             o48 = ctypes.create_string_buffer(48)
             rc = emul.emul_bls12381_g1_msm_affine(ctypes.c_size_t(n), sb, pb, c, m, L, rounds, pbatch, o48)
             assert rc == 0 and o48.raw == want, (c, m, L, rounds, pbatch)
+            o48 = ctypes.create_string_buffer(48)        # the round as three kernels (forward x-only / invert / backward)
+            rc = emul.emul_bls12381_g1_msm_affine_split(ctypes.c_size_t(n), sb, pb, c, m, L, rounds, 3 * pbatch, o48)
+            assert rc == 0 and o48.raw == want, ("split", c, m, L, rounds, pbatch)
     # bn254 (8-limb field) through the same template
     from oracle import bn254 as o4
     pts4 = [o4.g1_mul(rng.randrange(1, o4.ORDER)) for _ in range(12)]

@@ -1,4 +1,5 @@
-"""A/B: 2^20 independent BLS12-381 G1 Point.Mul (k_mul_batch) with the endomorphism + windowed path on and off."""
+"""A/B: 2^20 independent BLS12-381 G1 Point.Mul (k_mul_batch): endomorphism + windows (default) vs plain windows, and the
+resident-blocks variants of the kernel."""
 import sys, os, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -15,10 +16,10 @@ pts = torch.frombuffer(bytearray(pts_b), dtype=torch.uint8).cuda()
 sc = torch.frombuffer(bytearray(wl.scalars_to_bytes(s)), dtype=torch.uint8).cuda()
 out = torch.zeros(48 * n, dtype=torch.uint8, device="cuda")
 ref = None
-for glv in (1, 0, 1):
+for glv, occ in ((1, 0), (1, 3), (1, 4), (0, 0), (0, 3)):
     eng.set_msm_glv(bool(glv))
+    eng.set_mul_occupancy(occ)
     eng.call_dev("b2k_bls12381_g1_mul_batch_dev", n, sc.data_ptr(), pts.data_ptr(), out.data_ptr()); eng.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     K = 3
@@ -31,4 +32,4 @@ for glv in (1, 0, 1):
         ref = got
         for i in (0, 1, n // 3, n - 1):
             assert got[48 * i:48 * i + 48] == o.g1_compress(o.g1_mul(s[i] * a[i] % o.R)), i
-    print("glv", glv, "ms", round(dt * 1e3, 2), "muls/s %.3e" % (n / dt), "same" if got == ref else "DIFFERENT", flush=True)
+    print("glv", glv, "blocks/SM", occ, "ms", round(dt * 1e3, 2), "muls/s %.3e" % (n / dt), "same" if got == ref else "DIFFERENT", flush=True)
