@@ -110,11 +110,11 @@ inline AffinePlan affine_plan(const b2k_ctx* ctx, size_t n, const MsmPlan& pl) {
   if (!AffineTraits<CV>::enabled || ctx->use_v1 || ctx->msm_groups > 1) return ap;
   const size_t total = (size_t)pl.W * pl.nb;
   int R = ctx->affine_rounds;
-  if (R < 0) {                          // automatic: big problems only; measured best at C2 (64 operands per bucket): 2 rounds, the
+  if (R < 0) {                          // automatic: big problems only; measured best at C2 (64 operands per bucket): 3 rounds --
     R = 0;                              // later, smaller rounds no longer fill the chip and the XYZZ slices take over
     if (ap.bound[0] >= (size_t(1) << 20)) {
       const size_t avg = ap.bound[0] / total;
-      while (R < PT_MAX_ROUNDS && (avg >> R) >= 32) R++;
+      while (R < PT_MAX_ROUNDS && (avg >> R) >= 16) R++;
     }
   }
   if (R > PT_MAX_ROUNDS) R = PT_MAX_ROUNDS;

@@ -30,11 +30,12 @@ for r in body:
         "grid": r[col["Grid Size"]], "block": r[col["Block Size"]],
         "duration_ms": (num(r, "gpu__time_duration.sum") or 0) * 1e3,
         "dram_read": num(r, "dram__bytes_read.sum"), "dram_write": num(r, "dram__bytes_write.sum"),
-        "fmaheavy_pct": num(r, "sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_active"),
-        "alu_pct": num(r, "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active"),
+        "fmaheavy_cycles_pct": num(r, "sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_elapsed"),
+        "fma_inst_pct": num(r, "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active"),
+        "alu_inst_pct": num(r, "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active"),
         "ipc": num(r, "sm__inst_executed.avg.per_cycle_active"),
         "registers": num(r, "launch__registers_per_thread"),
-        "local_bytes_ld": num(r, "smsp__inst_executed_op_local_ld.sum"),
+        "dram_throughput_pct": num(r, "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"),
     })
 tot_r = sum(k["dram_read"] or 0 for k in kern)
 tot_w = sum(k["dram_write"] or 0 for k in kern)

@@ -10,13 +10,15 @@ export B2K_SKIP_PAIRINGS=1
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_${TAG}.csv \
     python bench.py --steps 2 --warmup 3 > gpurun_out/bench_under_ncu_${TAG}.log 2>&1
 python tools/summarize_launches.py gpurun_out/launches_${TAG}.csv > gpurun_out/${TAG}_launches_summary.txt 2>&1
-# the bucket-accumulate pass of ONE MSM, once: every pair-tree round + the XYZZ slices (skip the 3 warm-up MSMs' launches)
-NK=${B2K_PROFILE_PASS_KERNELS:-5}
-ncu --set full --clock-control none --import-source on -k "regex:k_msm_pairtree_round|k_msm_accumulate_slices" -s $((3 * NK)) -c $NK \
+# the bucket-accumulate pass of ONE MSM, once: the three kernels of every affine pair-tree round + the XYZZ slices
+# (NK = 3 R + 1 launches per MSM; skip the first 3 MSMs)
+NK=${B2K_PROFILE_PASS_KERNELS:-10}
+ncu --set full --clock-control none --import-source on -k "regex:k_pt_forward|k_pt_invert|k_pt_backward|k_msm_accumulate_slices" -s $((3 * NK)) -c $NK \
     -o gpurun_out/accumulate_${TAG} -f python bench.py --steps 1 --warmup 3 --contexts 1 > gpurun_out/ncu_full_${TAG}.log 2>&1
 # gpurun_out/ travels back only below 64 MiB: keep the text pages, drop the report
 ncu -i gpurun_out/accumulate_${TAG}.ncu-rep --page details > gpurun_out/${TAG}_accumulate_ncu_details.txt 2>&1
 ncu -i gpurun_out/accumulate_${TAG}.ncu-rep --page raw --csv > gpurun_out/${TAG}_accumulate_ncu_raw.csv 2>&1
+python tools/ncu_traffic.py gpurun_out/${TAG}_accumulate_ncu_raw.csv ${TAG} > gpurun_out/accumulate_traffic.json 2> gpurun_out/ncu_traffic_${TAG}.err
 rm -f gpurun_out/accumulate_${TAG}.ncu-rep
 # pairing kernel: one full capture on a small batch (the kernel is long: keep n small)
 cat > /tmp/pair_probe.py <<'PY'
