@@ -290,7 +290,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     from kyber_b200 import Engine, workload as wl
-    from kyber_b200.multi import msm_sharded
+    from kyber_b200.multi import msm_sharded, msm_bucket_exchange
     from oracle import bls12381 as o
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -346,8 +346,37 @@ def run_ours(args):
     finals = [d_final] + [torch.zeros(64, dtype=torch.uint8, device=dev) for _ in range(NC - 1)]
     partials = [d_out] + [torch.zeros(96, dtype=torch.uint8, device=dev) for _ in range(NC - 1)]
 
+    # multi-GPU shape 1 (partial-bucket exchange, kyber_b200/multi.py): per-context exchange buffers
+    xplan = eng.bls12381_g1_msm_bucket_plan(n)
+    XC, XW, XNB, XEB = xplan["c"], xplan["W"], xplan["buckets_per_window"], xplan["bucket_bytes"]
+    can_exchange = world > 1 and XW % world == 0
+    use_buckets = can_exchange and args.exchange == "buckets"
+    if can_exchange:
+        xbuckets = [torch.empty(XW * XNB * XEB, dtype=torch.uint8, device=dev) for _ in range(NC)]
+        xwsum = [torch.empty((XW // world) * XEB, dtype=torch.uint8, device=dev) for _ in range(NC)]
+
+    def step_device_buckets(k: int = 0):
+        """the same sharded MSM through the partial-bucket exchange: buckets -> ncclAllToAll -> fused add + reduce of the
+        windows this rank owns -> ncclAllGather of the window sums -> Horner"""
+        e, fin, xb, xw = engines[k % NC], finals[k % NC], xbuckets[k % NC], xwsum[k % NC]
+        with torch.cuda.stream(streams[k % NC]):
+            def local_buckets():
+                e.bls12381_g1_msm_buckets_dev(n, d_scal.data_ptr(), d_pts.data_ptr(), xb.data_ptr(), xb.numel())
+                return xb
+
+            def reduce_windows(recv, parts, w_cnt):
+                e.bls12381_g1_msm_reduce_windows_dev(XC, w_cnt, parts, recv.data_ptr(), xw.data_ptr())
+                return xw
+
+            def finish(allws):
+                e.bls12381_g1_msm_finish_dev(XC, XW, allws.data_ptr(), fin.data_ptr())
+                return fin
+            msm_bucket_exchange(local_buckets, reduce_windows, finish, XW, XNB, XEB)
+
     def step_device(k: int = 0):
         """one pass of the hot path, inputs resident in HBM, issued on context k % NC"""
+        if use_buckets:
+            return step_device_buckets(k)
         e, fin, part = engines[k % NC], finals[k % NC], partials[k % NC]
         with torch.cuda.stream(streams[k % NC]):
             if world == 1:
@@ -388,6 +417,26 @@ def run_ours(args):
     barrier()
     dev_ms = max(ev0.elapsed_time(ev) for ev in ends)
     launches = sum(e.launch_count() for e in engines) - launches0
+    # the other exchange shape, timed the same way (both are reported; --exchange picks the headline one)
+    alt_ms = None
+    if can_exchange:
+        alt = step_device if use_buckets else step_device_buckets
+        if use_buckets:
+            use_buckets = False                                   # step_device now runs the result exchange
+        for k in range(3 * NC):
+            alt(k)
+        barrier()
+        ev_x = torch.cuda.Event(enable_timing=True)
+        ends_x = [torch.cuda.Event(enable_timing=True) for _ in range(NC)]
+        ev_x.record(stream)
+        for k in range(args.steps):
+            alt(k)
+        for st, ev in zip(streams, ends_x):
+            ev.record(st)
+        barrier()
+        alt_ms = max(ev_x.elapsed_time(ev) for ev in ends_x) / args.steps
+        alt_got = bytes(finals[(args.steps - 1) % NC][:48].cpu().tolist())
+        use_buckets = can_exchange and args.exchange == "buckets"
     # the same K steps on ONE context (no overlap): single-MSM latency
     ev_a, ev_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev_a.record(stream)
@@ -474,12 +523,15 @@ def run_ours(args):
     else:
         total_dot = my_dot
     assert got == o.g1_compress(o.g1_mul(total_dot)), "device MSM result differs from the oracle"
+    if alt_ms is not None:
+        assert alt_got == got, "the two multi-GPU exchange shapes disagree"
 
     # ---- max over ranks ---------------------------------------------------------------------------------
-    t = torch.tensor([dev_ms, e2e_ms], dtype=torch.float64, device=dev)
+    t = torch.tensor([dev_ms, e2e_ms, alt_ms or 0.0], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dev_ms, e2e_ms = float(t[0]), float(t[1])
+    alt_ms = float(t[2]) if alt_ms is not None else None
 
     if rank == 0:
         ms_step = dev_ms / args.steps
@@ -496,7 +548,9 @@ def run_ours(args):
                                        "(BASELINE.json configs[1]); seed b2k/c2",
                            "pairs_per_gpu": n, "parallelism": f"shard{world}" if world > 1 else "single",
                            "l2": "no flush: each step streams >400 MB (128 MiB inputs + sort + buckets) > 126 MB L2",
-                           "exchange": "1 x ncclAllGather of 96 B/rank + add" if world > 1 else "none",
+                           "exchange": ("none" if world == 1 else
+                                        f"partial buckets: ncclAllToAll of {XW * XNB * XEB} B/rank + fused add/reduce + ncclAllGather of "
+                                        f"{XW * XEB} B + Horner" if use_buckets else "1 x ncclAllGather of 96 B/rank + add"),
                            "steps_in_flight": NC,
                            "overlap": f"{NC} independent steps in flight on {NC} contexts/streams; "
                                       "single_step_latency_ms is one step alone"},
@@ -513,6 +567,15 @@ def run_ours(args):
                                        "window_sum", "final", "pipeline", "fixup", "accumulate_affine_rounds"],
                                       [round(x, 4) for x in tm])),
                 "msm_plan": plan}
+        if alt_ms is not None:
+            shapes = {"result_exchange_ms_per_step": alt_ms if use_buckets else ms_step,
+                      "bucket_exchange_ms_per_step": ms_step if use_buckets else alt_ms,
+                      "bucket_exchange_bytes_per_rank": XW * XNB * XEB * (world - 1) // world,
+                      "headline": args.exchange,
+                      "note": "same sharded MSM, same bytes out; result = every rank finishes its MSM, ncclAllGather of 96 B, add; "
+                              "buckets = ncclAllToAll of the partial buckets (raw limbs), bucket-wise EC add fused into the reduction of the "
+                              "W/G windows a rank owns, ncclAllGather of the window sums, Horner (north_star's shape)"}
+            line["multi_gpu_exchange"] = shapes
         if c_bits:
             nv = n * (2 if plan["glv"] else 1)                            # pairs after the endomorphism split
             adds = nv * plan["W"]                                         # bucket additions (16 per input pair at c = 16)
@@ -569,6 +632,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--exchange", default="result", choices=["result", "buckets"],
+                    help="multi-GPU exchange shape of the headline step (the other one is timed and reported beside it)")
     ap.add_argument("--contexts", type=int, default=3, help="independent steps in flight (streams); 1 = strictly serial")
     args = ap.parse_args()
     if args.impl == "reference":

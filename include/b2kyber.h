@@ -121,6 +121,27 @@ int b2k_bls12381_g1_msm_dev(b2k_ctx* ctx, size_t n, const void* d_scalars, const
 int b2k_bls12381_g1_msm_affine_dev(b2k_ctx* ctx, size_t n, const void* d_scalars, const void* d_points,
                                    void* d_out /*[96]*/);
 
+/* ---- multi-GPU MSM by partial-bucket exchange (the shape BASELINE.json's north_star names; SURVEY.md 8e shape 1) ----
+ * A sharded MSM (each rank holds n of the pairs of one sum, e.g. the 2^24-term aggregate of config C5) as three
+ * device-side steps around two collectives issued by the host (kyber_b200/multi.py: msm_bucket_exchange):
+ *   msm_buckets_dev         this rank's pairs -> its W x 2^(c-1) PARTIAL buckets, raw Montgomery limbs
+ *                           (plan[3] bytes per bucket: XYZZ coordinates, 4 x 48 B), window-major
+ *   ncclAllToAll            rank g receives windows [g W/G, (g+1) W/G) of every rank  (= reduce-scatter without the
+ *                           reduction: NCCL cannot add curve points)
+ *   msm_reduce_windows_dev  d_recv = [parts][w_cnt][2^(c-1)] buckets; the bucket-wise EC addition of the `parts`
+ *                           partials is fused into the running-sum reduction; d_wsum = [w_cnt] window sums
+ *   ncclAllGather           all W window sums on every rank
+ *   msm_finish_dev          Horner over the windows, affine, wire bytes (48 B compressed, or 96 B operand form)
+ * Replaces the same Mul+Add loops as b2k_bls12381_g1_msm (share/poly.go:461-473, sign/bdn/bdn.go:126-161) when the
+ * terms live on several GPUs.  plan = {c, W, buckets per window, bytes per bucket}; all ranks must obtain the same
+ * plan (same n and switches), which bucket_plan lets the host check before sizing its buffers. */
+int b2k_bls12381_g1_msm_bucket_plan(b2k_ctx* ctx, size_t n, int* plan /*[4]*/);
+int b2k_bls12381_g1_msm_buckets_dev(b2k_ctx* ctx, size_t n, const void* d_scalars, const void* d_points,
+                                    void* d_buckets, size_t cap_bytes, int* plan /*[4], may be NULL*/);
+int b2k_bls12381_g1_msm_reduce_windows_dev(b2k_ctx* ctx, int c, int w_cnt, int parts, const void* d_recv,
+                                           void* d_wsum /*[w_cnt][plan[3]]*/);
+int b2k_bls12381_g1_msm_finish_dev(b2k_ctx* ctx, int c, int W, const void* d_wsum, void* d_out, int affine_out);
+
 /* ---- BLS12-381 G2 ------------------------------------------------------------------------------------ */
 /* replaces: kilic.G2Elt.Mul, pairing/bls12381/kilic/g2.go:109-115 (public keys / signatures on G2:
  * bdn.NewMask terms sign/bdn/mask.go:58-61, bdn.AggregateSignatures on G2).  Operands 192 B

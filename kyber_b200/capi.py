@@ -70,6 +70,10 @@ def load_library() -> C.CDLL:
         sigs[nm] = (C.c_int, [vp, sz, vp, vp])
     for nm in ("b2k_bls12381_g1_pubpoly_check", "b2k_bls12381_g2_pubpoly_check", "b2k_bn254_pubpoly_check"):
         sigs[nm] = (C.c_int, [vp, sz, sz, vp, sz, vp, vp, vp])
+    sigs["b2k_bls12381_g1_msm_bucket_plan"] = (C.c_int, [vp, sz, C.POINTER(C.c_int)])
+    sigs["b2k_bls12381_g1_msm_buckets_dev"] = (C.c_int, [vp, sz, vp, vp, vp, sz, C.POINTER(C.c_int)])
+    sigs["b2k_bls12381_g1_msm_reduce_windows_dev"] = (C.c_int, [vp, C.c_int, C.c_int, C.c_int, vp, vp])
+    sigs["b2k_bls12381_g1_msm_finish_dev"] = (C.c_int, [vp, C.c_int, C.c_int, vp, vp, C.c_int])
     host3 = (C.c_int, [vp, sz, vp, vp, vp])
     for name in HOST_FUNCS + DEV_FUNCS:
         sigs[name] = host3
@@ -198,6 +202,22 @@ class Engine:
 
     def launch_count(self) -> int:
         return int(self.lib.b2k_launch_count(self.h))
+
+    # -- multi-GPU MSM by partial-bucket exchange (device pointers; see kyber_b200/multi.py) ---------
+    def bls12381_g1_msm_bucket_plan(self, n: int) -> dict:
+        arr = (C.c_int * 4)()
+        self._check(self.lib.b2k_bls12381_g1_msm_bucket_plan(self.h, n, arr))
+        return {"c": arr[0], "W": arr[1], "buckets_per_window": arr[2], "bucket_bytes": arr[3]}
+
+    def bls12381_g1_msm_buckets_dev(self, n: int, d_scalars: int, d_points: int, d_buckets: int, cap_bytes: int):
+        self._check(self.lib.b2k_bls12381_g1_msm_buckets_dev(self.h, n, C.c_void_p(d_scalars), C.c_void_p(d_points),
+                                                             C.c_void_p(d_buckets), cap_bytes, None))
+
+    def bls12381_g1_msm_reduce_windows_dev(self, c: int, w_cnt: int, parts: int, d_recv: int, d_wsum: int):
+        self._check(self.lib.b2k_bls12381_g1_msm_reduce_windows_dev(self.h, c, w_cnt, parts, C.c_void_p(d_recv), C.c_void_p(d_wsum)))
+
+    def bls12381_g1_msm_finish_dev(self, c: int, W: int, d_wsum: int, d_out: int, affine_out: bool = False):
+        self._check(self.lib.b2k_bls12381_g1_msm_finish_dev(self.h, c, W, C.c_void_p(d_wsum), C.c_void_p(d_out), 1 if affine_out else 0))
 
     # -- BLS12-381 G1 -----------------------------------------------------------------------------
     def bls12381_g1_mul_batch(self, scalars: bytes, points: bytes) -> bytes:

@@ -214,5 +214,10 @@ int b2k_wait(b2k_ctx* c) { return msm_wait(c); }
 int b2k_bls12381_g1_msm_dev(b2k_ctx* c, size_t n, const void* s, const void* p, void* o) { return msm_dev<Bls381G1>(c, n, s, p, o); }
 int b2k_bls12381_g1_msm_affine_dev(b2k_ctx* c, size_t n, const void* s, const void* p, void* o) { return msm_dev<Bls381G1>(c, n, s, p, o, 1); }
 
+int b2k_bls12381_g1_msm_bucket_plan(b2k_ctx* c, size_t n, int* plan) { return msm_bucket_plan<Bls381G1>(c, n, plan); }
+int b2k_bls12381_g1_msm_buckets_dev(b2k_ctx* c, size_t n, const void* s, const void* p, void* b, size_t cap, int* plan) { return msm_buckets_dev<Bls381G1>(c, n, s, p, b, cap, plan); }
+int b2k_bls12381_g1_msm_reduce_windows_dev(b2k_ctx* c, int cbits, int w_cnt, int parts, const void* recv, void* wsum) { return msm_reduce_windows_dev<Bls381G1>(c, cbits, w_cnt, parts, recv, wsum); }
+int b2k_bls12381_g1_msm_finish_dev(b2k_ctx* c, int cbits, int W, const void* wsum, void* out, int affine_out) { return msm_finish_dev<Bls381G1>(c, cbits, W, wsum, out, affine_out); }
+
 
 }  // extern "C"

@@ -375,6 +375,21 @@ __global__ void __launch_bounds__(128) k_msm_reduce_chunks(MsmPlan pl, const Xyz
   partials[id] = out;
 }
 
+// bucket exchange: chunk reduction of w_cnt windows whose buckets are the sum of `parts` received partial arrays,
+// recv layout [part][w_cnt][nb] (what ncclAllToAll leaves on the rank owning these windows)
+template <class CV>
+__global__ void __launch_bounds__(128) k_msm_reduce_chunks_parts(int nb, int m, int w_cnt, int parts,
+                                                                 const Xyzz<typename CV::F>* __restrict__ recv,
+                                                                 Xyzz<typename CV::F>* __restrict__ partials) {
+  int T = nb / m;
+  size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (id >= (size_t)w_cnt * T) return;
+  int w = (int)(id / T), t = (int)(id % T);
+  Xyzz<typename CV::F> out;
+  msm_reduce_chunk_parts<CV>(out, recv + (size_t)w * nb, parts, (size_t)w_cnt * nb, t, m);
+  partials[id] = out;
+}
+
 // ---- MSM stage 6: per-window sum of the partials (one block per window) --------------------------
 template <class CV>
 __global__ void __launch_bounds__(128) k_msm_window_sum(int T, const Xyzz<typename CV::F>* __restrict__ partials,

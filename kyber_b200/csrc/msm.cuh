@@ -83,6 +83,32 @@ B2K_D void msm_reduce_chunk(Xyzz<typename CV::F>& out, const Xyzz<typename CV::F
   out = acc;
 }
 
+// Multi-GPU bucket exchange (SURVEY 8e shape 1): the buckets of a window arrive as `parts` partial arrays, one per
+// rank, laid out [part][stride]; the bucket-wise EC addition of the partials is fused into the chunk reduction, which
+// reads the receive buffer of the all-to-all directly.  B points at bucket 0 of the window inside part 0.
+template <class CV>
+B2K_D void msm_reduce_chunk_parts(Xyzz<typename CV::F>& out, const Xyzz<typename CV::F>* B, int parts, size_t stride, int t, int m) {
+  using X = Xyzz<typename CV::F>;
+  X run, acc;
+  xyzz_set_inf(run);
+  xyzz_set_inf(acc);
+  for (int k = m - 1; k >= 0; k--) {
+    X b = B[t * m + k];
+    for (int p = 1; p < parts; p++) {
+      X q = B[(size_t)p * stride + (size_t)(t * m + k)];
+      xyzz_add(b, b, q);
+    }
+    xyzz_add(run, run, b);
+    xyzz_add(acc, acc, run);
+  }
+  if (t != 0) {
+    X off;
+    xyzz_mul_small(off, run, (uint32_t)(t * m));
+    xyzz_add(acc, acc, off);
+  }
+  out = acc;
+}
+
 // ---- final: Horner over window sums --------------------------------------------------------------
 template <class CV>
 B2K_D void msm_horner(Xyzz<typename CV::F>& out, const Xyzz<typename CV::F>* wsum, int W, int c) {

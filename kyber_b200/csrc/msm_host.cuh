@@ -171,7 +171,7 @@ size_t msm_scratch_bytes(const b2k_ctx* ctx, size_t n, const MsmPlan& pl) {
 // already be reserved (arena) for msm_scratch_bytes(msm_virtual_n(n)) and pl must come from msm_plan(n).
 template <class CV>
 int msm_enqueue(b2k_ctx* ctx, size_t n_in, const MsmPlan& pl, const uint8_t* d_scalars_in, const uint8_t* d_points,
-                uint8_t* d_out, int affine_out = 0) {
+                uint8_t* d_out, int affine_out = 0, Xyzz<typename CV::F>* ext_buckets = nullptr) {
   using F = typename CV::F;
   cudaStream_t st = ctx->stream;
   const bool glv = msm_uses_glv<CV>(ctx, n_in);
@@ -186,7 +186,9 @@ int msm_enqueue(b2k_ctx* ctx, size_t n_in, const MsmPlan& pl, const uint8_t* d_s
   auto* offs = arena_take<uint32_t>(ctx, total + 1);
   auto* cursor = arena_take<uint32_t>(ctx, total + 1);
   auto* entries = arena_take<uint32_t>(ctx, n * (size_t)pl.W);
-  auto* buckets = arena_take<Xyzz<F>>(ctx, total);
+  auto* own_buckets = arena_take<Xyzz<F>>(ctx, total);
+  // bucket exchange (multi-GPU shape 1): the pipeline stops after the fix-up and leaves the W x 2^(c-1) buckets in the caller's buffer
+  auto* buckets = ext_buckets ? ext_buckets : own_buckets;
   auto* partials = arena_take<Xyzz<F>>(ctx, (size_t)pl.W * T);
   auto* wsum = arena_take<Xyzz<F>>(ctx, pl.W);
   // window sum in two levels when a window has many chunk partials: S sub-blocks of >= 512 partials each
@@ -194,7 +196,7 @@ int msm_enqueue(b2k_ctx* ctx, size_t n_in, const MsmPlan& pl, const uint8_t* d_s
   if (S > 128) S = 128;
   auto* wpart = arena_take<Xyzz<F>>(ctx, (size_t)pl.W * 128);
   if (!wpart) { ctx->err = "scratch arena too small"; return B2K_ERR_ARG; }
-  if (!pts || !counts || !offs || !cursor || !entries || !buckets || !partials || !wsum) {
+  if (!pts || !counts || !offs || !cursor || !entries || !own_buckets || !partials || !wsum) {
     ctx->err = "scratch arena too small";
     return B2K_ERR_ARG;
   }
@@ -256,7 +258,7 @@ int msm_enqueue(b2k_ctx* ctx, size_t n_in, const MsmPlan& pl, const uint8_t* d_s
   k_scan_finish<<<sblocks, 1024, 0, st>>>((uint32_t)total, bsum, offs, cursor); nl += 3;
   CK(cudaEventRecord(ctx->ev[3], st));
   k_msm_scatter<CV><<<gb_n, 256, 0, st>>>(n, d_scalars, pl, cursor, entries); nl++;
-  const int G = (!ctx->use_v1 && ctx->msm_groups > 1 && pl.W >= 2 * ctx->msm_groups && ctx->stream2) ? ctx->msm_groups : 1;
+  const int G = (!ext_buckets && !ctx->use_v1 && ctx->msm_groups > 1 && pl.W >= 2 * ctx->msm_groups && ctx->stream2) ? ctx->msm_groups : 1;
   if (G > 1) {
     // ---- overlapped tail: groups of windows, top group first; reduction of group g on stream2 while the main
     //      stream accumulates group g-1.  ms[4] = all accumulate launches, ms[5] = what is left after them.
@@ -346,6 +348,15 @@ int msm_enqueue(b2k_ctx* ctx, size_t n_in, const MsmPlan& pl, const uint8_t* d_s
     }
   }
   CK(cudaEventRecord(ctx->ev[5], st));
+  if (ext_buckets) {                       // the tail runs after the exchange (msm_reduce_windows_dev / msm_finish_dev)
+    CK(cudaEventRecord(ctx->ev[6], st));
+    CK(cudaEventRecord(ctx->ev[7], st));
+    CK(cudaEventRecord(ctx->ev[8], st));
+    CK(cudaGetLastError());
+    ctx->launches += (uint64_t)nl;
+    ctx->timings_valid = true;
+    return B2K_OK;
+  }
   size_t nchunks = (size_t)pl.W * T;
   k_msm_reduce_chunks<CV><<<(unsigned)((nchunks + 127) / 128), 128, 0, st>>>(pl, buckets, partials); nl++;
   CK(cudaEventRecord(ctx->ev[6], st));
@@ -376,6 +387,94 @@ int msm_dev(b2k_ctx* ctx, size_t n, const void* d_scalars, const void* d_points,
   int rc = arena_reserve(ctx, msm_scratch_bytes<CV>(ctx, msm_virtual_n<CV>(ctx, n), pl));
   if (rc) return rc;
   return msm_enqueue<CV>(ctx, n, pl, (const uint8_t*)d_scalars, (const uint8_t*)d_points, (uint8_t*)d_out, affine_out);
+}
+
+// ---- multi-GPU bucket exchange (SURVEY 8e shape 1) ---------------------------------------------------------------------
+// Three device-side steps around the two collectives the host issues (kyber_b200/multi.py: msm_bucket_exchange):
+//   msm_buckets_dev        pairs of this rank -> its W x 2^(c-1) partial buckets (raw Xyzz limbs, Montgomery form)
+//   [ncclAllToAll]         rank g receives windows [g W/G, (g+1) W/G) of every rank
+//   msm_reduce_windows_dev sum of the G partials fused into the chunk reduction, then the window sums of these windows
+//   [ncclAllGather]        W window sums (W x sizeof(Xyzz)) on every rank
+//   msm_finish_dev         Horner over the windows, affine, wire bytes
+// plan_out = {c, W, buckets per window, bytes per bucket}; every rank must run the same plan (same n class, same switches).
+template <class CV>
+int msm_buckets_dev(b2k_ctx* ctx, size_t n, const void* d_scalars, const void* d_points, void* d_buckets, size_t cap_bytes, int* plan_out) {
+  using X = Xyzz<typename CV::F>;
+  if (!ctx || !d_scalars || !d_points || !d_buckets || n == 0 || n >= (size_t(1) << 31)) {
+    if (ctx) ctx->err = "bad argument";
+    return B2K_ERR_ARG;
+  }
+  CK(cudaSetDevice(ctx->device));
+  MsmPlan pl = msm_plan<CV>(ctx, n);
+  if (plan_out) { plan_out[0] = pl.c; plan_out[1] = pl.W; plan_out[2] = pl.nb; plan_out[3] = (int)sizeof(X); }
+  if (cap_bytes < (size_t)pl.W * pl.nb * sizeof(X) || (reinterpret_cast<uintptr_t>(d_buckets) & 15)) {
+    ctx->err = "bucket buffer too small or not 16-byte aligned";
+    return B2K_ERR_ARG;
+  }
+  int rc = arena_reserve(ctx, msm_scratch_bytes<CV>(ctx, msm_virtual_n<CV>(ctx, n), pl));
+  if (rc) return rc;
+  return msm_enqueue<CV>(ctx, n, pl, (const uint8_t*)d_scalars, (const uint8_t*)d_points, nullptr, 0, reinterpret_cast<X*>(d_buckets));
+}
+
+// bucket-count query for sizing the exchange buffers before the first call
+template <class CV>
+int msm_bucket_plan(b2k_ctx* ctx, size_t n, int* plan_out) {
+  if (!ctx || !plan_out || n == 0) return B2K_ERR_ARG;
+  MsmPlan pl = msm_plan<CV>(ctx, n);
+  plan_out[0] = pl.c; plan_out[1] = pl.W; plan_out[2] = pl.nb; plan_out[3] = (int)sizeof(Xyzz<typename CV::F>);
+  return B2K_OK;
+}
+
+template <class CV>
+int msm_reduce_windows_dev(b2k_ctx* ctx, int c, int w_cnt, int parts, const void* d_recv, void* d_wsum) {
+  using X = Xyzz<typename CV::F>;
+  if (!ctx || !d_recv || !d_wsum || c < 2 || c > 16 || w_cnt < 1 || w_cnt > 64 || parts < 1 || parts > 64) {
+    if (ctx) ctx->err = "bad argument";
+    return B2K_ERR_ARG;
+  }
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  const int nb = 1 << (c - 1);
+  int m = 1;                                       // chunk: keep >= 16k reduction threads for the few windows of one rank
+  while (m < 64 && m * 2 <= nb && ((size_t)w_cnt * nb) / (size_t)(m * 2) >= 16384) m *= 2;
+  if (ctx->force_m > 0 && ctx->force_m <= nb && (ctx->force_m & (ctx->force_m - 1)) == 0) m = ctx->force_m;
+  const int T = nb / m;
+  int S = T >= 1024 ? T / 512 : 1;
+  if (S > 128) S = 128;
+  int rc = arena_reserve(ctx, pad256((size_t)w_cnt * T * sizeof(X)) + pad256((size_t)w_cnt * 128 * sizeof(X)) + 4096);
+  if (rc) return rc;
+  auto* partials = arena_take<X>(ctx, (size_t)w_cnt * T);
+  auto* wpart = arena_take<X>(ctx, (size_t)w_cnt * 128);
+  if (!partials || !wpart) { ctx->err = "scratch arena too small"; return B2K_ERR_ARG; }
+  const size_t nchunks = (size_t)w_cnt * T;
+  k_msm_reduce_chunks_parts<CV><<<(unsigned)((nchunks + 127) / 128), 128, 0, st>>>(nb, m, w_cnt, parts, reinterpret_cast<const X*>(d_recv), partials);
+  if (S > 1) {
+    k_msm_window_sum<CV><<<w_cnt * S, 128, 0, st>>>(T / S, partials, wpart);
+    k_msm_window_sum<CV><<<w_cnt, 128, 0, st>>>(S, wpart, reinterpret_cast<X*>(d_wsum));
+    ctx->launches += 3;
+  } else {
+    k_msm_window_sum<CV><<<w_cnt, 128, 0, st>>>(T, partials, reinterpret_cast<X*>(d_wsum));
+    ctx->launches += 2;
+  }
+  CK(cudaGetLastError());
+  return B2K_OK;
+}
+
+template <class CV>
+int msm_finish_dev(b2k_ctx* ctx, int c, int W, const void* d_wsum, void* d_out, int affine_out) {
+  using X = Xyzz<typename CV::F>;
+  if (!ctx || !d_wsum || !d_out || c < 2 || c > 16 || W < 1 || W > 128) {
+    if (ctx) ctx->err = "bad argument";
+    return B2K_ERR_ARG;
+  }
+  CK(cudaSetDevice(ctx->device));
+  MsmPlan pl;
+  memset(&pl, 0, sizeof pl);
+  pl.c = c; pl.W = W; pl.nb = 1 << (c - 1); pl.m = 1;
+  k_msm_final<CV><<<1, 128, 0, ctx->stream>>>(pl, reinterpret_cast<const X*>(d_wsum), (uint8_t*)d_out, affine_out);
+  CK(cudaGetLastError());
+  ctx->launches += 1;
+  return B2K_OK;
 }
 
 // Host-buffer MSM.  wait = false: everything (H2D copies, pipeline, D2H of the result and of the status word) is only

@@ -1,4 +1,13 @@
-"""Multi-GPU MSM: shard the (scalar, point) pairs across ranks, ONE collective, then add.
+"""Multi-GPU MSM: shard the (scalar, point) pairs across ranks; two exchange shapes.
+
+Shape 2 (`msm_sharded`, default of bench.py): every rank finishes its own MSM, ONE all-gather of 96-byte results, add.
+Shape 1 (`msm_bucket_exchange`, the shape BASELINE.json's north_star names): the ranks exchange their PARTIAL
+BUCKETS.  NCCL cannot reduce curve points, so the "all-reduce of partial bucket sums" is spelled out as its two
+halves with the reduction done by our own kernel: an all-to-all of raw limb buffers (rank g receives windows
+[g W/G, (g+1) W/G) of every rank: a reduce-scatter without the reduction), ONE kernel that reads the receive buffer
+and fuses the bucket-wise EC additions into the running-sum reduction of those windows, then an all-gather of the
+W window sums and the Horner recombination on every rank.  The bucket reduction is thereby split G ways.
+
 
 The MSM is a sum of independent terms, so it shards by pairs with no data-path collective until the end
 (shape 2): rank r reduces pairs [lo_r, hi_r) to one affine partial sum (96 B), one
@@ -37,3 +46,28 @@ def msm_sharded(local_partial: Callable[[], torch.Tensor], combine: Callable[[to
     gathered = torch.empty(world * point_bytes, dtype=torch.uint8, device=part.device)
     dist.all_gather_into_tensor(gathered, part.contiguous(), group=group)
     return combine(gathered, world)
+
+
+def msm_bucket_exchange(local_buckets: Callable[[], torch.Tensor],
+                        reduce_windows: Callable[[torch.Tensor, int, int], torch.Tensor],
+                        finish: Callable[[torch.Tensor], torch.Tensor],
+                        W: int, buckets_per_window: int, bucket_bytes: int, group=None) -> torch.Tensor:
+    """Shape 1.  local_buckets() -> uint8[W * buckets_per_window * bucket_bytes], window-major partial buckets of
+    this rank; reduce_windows(recv uint8[parts][w_cnt][buckets_per_window][bucket_bytes], parts, w_cnt) ->
+    uint8[w_cnt * bucket_bytes] window sums of the windows this rank owns; finish(uint8[W * bucket_bytes]) -> result.
+    Rank g owns windows [g * W/G, (g+1) * W/G); W must be a multiple of the world size."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if W % world:
+        raise ValueError(f"bucket exchange needs the window count ({W}) to be a multiple of the world size ({world})")
+    w_cnt = W // world
+    buckets = local_buckets()
+    assert buckets.dtype == torch.uint8 and buckets.numel() == W * buckets_per_window * bucket_bytes
+    if world == 1:
+        return finish(reduce_windows(buckets, 1, w_cnt))
+    recv = torch.empty_like(buckets)
+    dist.all_to_all_single(recv, buckets, group=group)      # equal splits: chunk j of `buckets` (windows of rank j) -> rank j
+    mine = reduce_windows(recv, world, w_cnt)
+    assert mine.dtype == torch.uint8 and mine.numel() == w_cnt * bucket_bytes
+    wsums = torch.empty(W * bucket_bytes, dtype=torch.uint8, device=mine.device)
+    dist.all_gather_into_tensor(wsums, mine.contiguous(), group=group)
+    return finish(wsums)

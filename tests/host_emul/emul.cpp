@@ -74,15 +74,21 @@ static void emul_mul_batch_w4(size_t n, const uint8_t* scalars, const uint8_t* p
   }
 }
 
-template <class CV>
-static int emul_msm(size_t n, const uint8_t* scalars, const uint8_t* pts, int c, int m, uint8_t* out, int L = 0, int rounds = 0, int PB = 8, bool split = false) {
-  using F = typename CV::F;
+static MsmPlan emul_plan(int c, int m) {
   MsmPlan pl; pl.c = c; pl.W = (256 + c - 1) / c; pl.nb = 1 << (c - 1); pl.m = m;
   // K = sum_w 2^(c-1) 2^(cw)
-  { unsigned __int128 dummy = 0; (void)dummy;
-    uint32_t K[9] = {0};
-    for (int w = 0; w < pl.W; w++) { int bit = c * w + c - 1; if (bit < 288) K[bit >> 5] |= 1u << (bit & 31); }
-    memcpy(pl.K, K, sizeof K); }
+  uint32_t K[9] = {0};
+  for (int w = 0; w < pl.W; w++) { int bit = c * w + c - 1; if (bit < 288) K[bit >> 5] |= 1u << (bit & 31); }
+  memcpy(pl.K, K, sizeof K);
+  return pl;
+}
+
+// digits, counting sort, (affine rounds,) accumulate, fix-up: the W x 2^(c-1) buckets of these pairs
+template <class CV>
+static int emul_msm_buckets(size_t n, const uint8_t* scalars, const uint8_t* pts, const MsmPlan& pl, std::vector<Xyzz<typename CV::F>>& B,
+                            int L = 0, int rounds = 0, int PB = 8, bool split = false) {
+  using F = typename CV::F;
+  const int c = pl.c;
   std::vector<Affine<F>> P(n);
   for (size_t i = 0; i < n; i++) CV::load(P[i], pts + CV::IN_BYTES * i);
   size_t total = (size_t)pl.W * pl.nb;
@@ -100,7 +106,7 @@ static int emul_msm(size_t n, const uint8_t* scalars, const uint8_t* pts, int c,
     uint32_t sp[9]; msm_recode(sp, s, pl.K);
     for (int w = 0; w < pl.W; w++) { int d = msm_digit(sp, c, w); if (d) { size_t g = (size_t)w * pl.nb + (d < 0 ? -d : d) - 1; entries[cursor[g]++] = (uint32_t)i | (d < 0 ? 0x80000000u : 0); } }
   }
-  std::vector<Xyzz<F>> B(total);
+  B.assign(total, Xyzz<F>());
   if (L == 0) {
     for (size_t g = 0; g < total; g++) msm_accumulate_bucket<CV>(B[g], P.data(), entries.data(), offs[g], offs[g + 1]);
   } else {   // v2: fixed-length slices + fix-up (buckets start as all-zero = infinity, like cudaMemset)
@@ -148,6 +154,16 @@ static int emul_msm(size_t n, const uint8_t* scalars, const uint8_t* pts, int c,
       }
     }
   }
+  return 0;
+}
+
+template <class CV>
+static int emul_msm(size_t n, const uint8_t* scalars, const uint8_t* pts, int c, int m, uint8_t* out, int L = 0, int rounds = 0, int PB = 8, bool split = false) {
+  using F = typename CV::F;
+  MsmPlan pl = emul_plan(c, m);
+  std::vector<Xyzz<F>> B;
+  int rc = emul_msm_buckets<CV>(n, scalars, pts, pl, B, L, rounds, PB, split);
+  if (rc) return rc;
   int T = pl.nb / m;
   std::vector<Xyzz<F>> part((size_t)pl.W * T), wsum(pl.W);
   for (int w = 0; w < pl.W; w++) for (int t = 0; t < T; t++) msm_reduce_chunk<CV>(part[(size_t)w * T + t], &B[(size_t)w * pl.nb], t, m);
@@ -158,7 +174,52 @@ static int emul_msm(size_t n, const uint8_t* scalars, const uint8_t* pts, int c,
   return 0;
 }
 
+// Multi-GPU bucket exchange (msm_host.cuh: msm_buckets_dev / msm_reduce_windows_dev / msm_finish_dev) with `world`
+// virtual ranks: contiguous shards of the pairs -> partial buckets per rank -> "all-to-all" (rank g gets windows
+// [g wc, (g+1) wc) of every rank, layout [part][wc][nb]) -> msm_reduce_chunk_parts + window sums -> "all-gather" -> Horner.
+template <class CV>
+static int emul_msm_exchange(size_t n, const uint8_t* scalars, const uint8_t* pts, int c, int m, int L, int rounds, int PB, int world, uint8_t* out) {
+  using F = typename CV::F;
+  using X = Xyzz<F>;
+  MsmPlan pl = emul_plan(c, m);
+  if (world < 1 || pl.W % world) return -2;
+  const int wc = pl.W / world;
+  std::vector<std::vector<X>> Bs(world);
+  for (int r = 0; r < world; r++) {
+    size_t lo = n * r / world, hi = n * (r + 1) / world;
+    if (hi > lo) {
+      int rc = emul_msm_buckets<CV>(hi - lo, scalars + 32 * lo, pts + CV::IN_BYTES * lo, pl, Bs[r], L, rounds, PB, true);
+      if (rc) return rc;
+    } else {
+      Bs[r].resize((size_t)pl.W * pl.nb);
+      memset((void*)Bs[r].data(), 0, Bs[r].size() * sizeof(X));
+    }
+  }
+  std::vector<X> wsum(pl.W);
+  const int T = pl.nb / m;
+  for (int g = 0; g < world; g++) {
+    std::vector<X> recv((size_t)world * wc * pl.nb);
+    for (int p = 0; p < world; p++) memcpy((void*)&recv[(size_t)p * wc * pl.nb], (const void*)&Bs[p][(size_t)g * wc * pl.nb], (size_t)wc * pl.nb * sizeof(X));
+    for (int w = 0; w < wc; w++) {
+      X a; xyzz_set_inf(a);
+      for (int t = 0; t < T; t++) {
+        X part;
+        msm_reduce_chunk_parts<CV>(part, &recv[(size_t)w * pl.nb], world, (size_t)wc * pl.nb, t, m);
+        xyzz_add(a, a, part);
+      }
+      wsum[g * wc + w] = a;
+    }
+  }
+  X r; msm_horner<CV>(r, wsum.data(), pl.W, c);
+  Affine<F> a; xyzz_to_affine(a, r);
+  CV::store(out, a);
+  return 0;
+}
+
 extern "C" {
+int emul_bls12381_g1_msm_exchange(size_t n, const uint8_t* s, const uint8_t* p, int c, int m, int L, int rounds, int PB, int world, uint8_t* o) {
+  return emul_msm_exchange<Bls381G1>(n, s, p, c, m, L, rounds, PB, world, o);
+}
 void emul_bls12381_g1_mul_batch_w4(size_t n, const uint8_t* s, const uint8_t* p, uint8_t* o) { emul_mul_batch_w4<Bls381G1>(n, s, p, o); }
 void emul_bn254_g1_mul_batch_w4(size_t n, const uint8_t* s, const uint8_t* p, uint8_t* o) { emul_mul_batch_w4<Bn254G1>(n, s, p, o); }
 void emul_bls12381_g1_mul_batch_glv(size_t n, const uint8_t* s, const uint8_t* p, uint8_t* o) { emul_mul_batch_glv(n, s, p, o); }

@@ -191,6 +191,33 @@ def test_affine_pair_tree_round_bodies(emul):
     assert o64.raw == o4.g1_marshal(acc)
 
 
+def test_bucket_exchange_bodies(emul):
+    """Multi-GPU shape 1 (msm_host.cuh: msm_buckets_dev -> all-to-all -> msm_reduce_windows_dev -> all-gather ->
+    msm_finish_dev) with 1, 2, 4 and 8 virtual ranks: the partial buckets of the ranks, summed inside the chunk
+    reduction (msm_reduce_chunk_parts), give the oracle's MSM -- including the same point (and P, -P) landing in the
+    same bucket on different ranks, a rank without pairs, and all-equal scalars."""
+    rng = random.Random(23)
+    n = 36
+    pts = [o.g1_mul(rng.randrange(1, o.R)) for _ in range(n)]
+    pts[20] = pts[2]                                      # same point, different ranks for world >= 2
+    pts[30] = o.g1_neg(pts[3])
+    pts[7] = None
+    pb = b"".join(o.g1_to_affine_bytes(p) for p in pts)
+    base = [rng.randrange(o.R) for _ in range(n)]
+    base[20] = base[2]
+    base[30] = base[3]
+    for ks in (base, [0x0FEDCBA987654321] * n, [rng.randrange(1 << 11) for _ in range(n)]):
+        sb = b"".join(o.scalar_to_bytes(k) for k in ks)
+        want = o.g1_compress(o.g1_msm(ks, pts))
+        for c, m, L, rounds, pbatch, world in ((4, 2, 3, 0, 1, 1), (4, 1, 2, 1, 3, 2), (8, 8, 5, 2, 4, 4), (16, 64, 2, 0, 1, 8),
+                                               (4, 4, 0, 0, 1, 64)):
+            o48 = ctypes.create_string_buffer(48)
+            rc = emul.emul_bls12381_g1_msm_exchange(ctypes.c_size_t(n), sb, pb, c, m, L, rounds, pbatch, world, o48)
+            assert rc == 0 and o48.raw == want, (c, m, L, rounds, pbatch, world)
+    o48 = ctypes.create_string_buffer(48)                 # window count not a multiple of the world size: refused
+    assert emul.emul_bls12381_g1_msm_exchange(ctypes.c_size_t(n), sb, pb, 13, 2, 3, 0, 1, 8, o48) == -2
+
+
 def test_hash_to_curve_bodies():
     from oracle import h2c_bls12381 as h, h2c_bls12381_g2 as h2
     l1, l2 = _lib("emul_h2c"), _lib("emul_h2c_g2")
