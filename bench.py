@@ -632,7 +632,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--exchange", default="result", choices=["result", "buckets"],
+    ap.add_argument("--exchange", default="buckets", choices=["result", "buckets"],
                     help="multi-GPU exchange shape of the headline step (the other one is timed and reported beside it)")
     ap.add_argument("--contexts", type=int, default=3, help="independent steps in flight (streams); 1 = strictly serial")
     args = ap.parse_args()

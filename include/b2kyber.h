@@ -93,6 +93,10 @@ int b2k_set_msm_occupancy(b2k_ctx* ctx, int blocks_per_sm);
 int b2k_set_mul_occupancy(b2k_ctx* ctx, int blocks_per_sm);
 /* Buckets per thread in the chunked bucket reduction (power of two, 0 = automatic).  Tuning aid. */
 int b2k_set_msm_chunk(b2k_ctx* ctx, int m);
+/* Bucket reduction in one level (chunks of m buckets, a small scalar multiplication per chunk) or two (the scalar
+ * multiplications move to the second level, which has m1 times fewer operands).  levels: 0 = automatic, 1, 2; m1, m2 = chunk
+ * sizes of the two levels (powers of two, 0 = default 8 and 4).  Same result bytes either way; A/B and tuning aid. */
+int b2k_set_msm_reduce(b2k_ctx* ctx, int levels, int m1, int m2);
 /* Number of kernels launched by this context so far. */
 uint64_t b2k_launch_count(const b2k_ctx* ctx);
 

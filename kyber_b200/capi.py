@@ -42,6 +42,7 @@ def load_library() -> C.CDLL:
         "b2k_set_msm_groups": (C.c_int, [vp, C.c_int]),
         "b2k_set_msm_occupancy": (C.c_int, [vp, C.c_int]),
         "b2k_set_msm_chunk": (C.c_int, [vp, C.c_int]),
+        "b2k_set_msm_reduce": (C.c_int, [vp, C.c_int, C.c_int, C.c_int]),
         "b2k_set_msm_affine": (C.c_int, [vp, C.c_int, C.c_int]),
         "b2k_last_msm_plan": (C.c_int, [vp, C.POINTER(C.c_int), C.c_int]),
         "b2k_set_msm_affine_split": (C.c_int, [vp, C.c_int]),
@@ -183,15 +184,19 @@ class Engine:
     def set_mul_occupancy(self, blocks_per_sm: int):
         self._check(self.lib.b2k_set_mul_occupancy(self.h, int(blocks_per_sm)))
 
+    def set_msm_reduce(self, levels: int = 0, m1: int = 0, m2: int = 0):
+        """bucket reduction in one or two levels (0 = automatic); A/B and tuning aid"""
+        self._check(self.lib.b2k_set_msm_reduce(self.h, int(levels), int(m1), int(m2)))
+
     def last_msm_plan(self) -> dict:
         """parameters of the last MSM: window bits, windows, chunk, slice length, affine rounds and their batch widths"""
-        arr = (C.c_int * 16)()
-        n = self.lib.b2k_last_msm_plan(self.h, arr, 16)
+        arr = (C.c_int * 20)()
+        n = self.lib.b2k_last_msm_plan(self.h, arr, 20)
         if n < 0:
             self._check(n)
         return {"c": arr[0], "W": arr[1], "buckets_per_window": arr[2], "chunk": arr[3], "slice_len": arr[4],
                 "affine_rounds": arr[5], "affine_batch": [arr[6 + r] for r in range(arr[5])], "glv": bool(arr[14]),
-                "affine_split": bool(arr[15])}
+                "affine_split": bool(arr[15]), "reduce_levels": arr[16], "reduce_chunks": [arr[17], arr[18]] if arr[16] == 2 else [arr[17]]}
 
     def last_timings(self):
         arr = (C.c_float * 16)()

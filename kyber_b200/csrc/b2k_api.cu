@@ -135,7 +135,7 @@ int b2k_last_timings(b2k_ctx* ctx, float* ms, int max) {
 
 int b2k_last_msm_plan(const b2k_ctx* ctx, int* out, int max) {
   if (!ctx || !out || max <= 0) return B2K_ERR_ARG;
-  int n = max < 16 ? max : 16;
+  int n = max < 20 ? max : 20;
   for (int i = 0; i < n; i++) out[i] = ctx->last_plan[i];
   return n;
 }
@@ -173,6 +173,15 @@ int b2k_set_msm_chunk(b2k_ctx* ctx, int m) {
   return B2K_OK;
 }
 
+int b2k_set_msm_reduce(b2k_ctx* ctx, int levels, int m1, int m2) {
+  auto pow2 = [](int v) { return v > 0 && (v & (v - 1)) == 0; };
+  if (!ctx || levels < 0 || levels > 2 || (m1 != 0 && (!pow2(m1) || m1 > 64)) || (m2 != 0 && (!pow2(m2) || m2 > 64))) return B2K_ERR_ARG;
+  ctx->reduce_levels = levels;
+  ctx->reduce_m1 = m1;
+  ctx->reduce_m2 = m2;
+  return B2K_OK;
+}
+
 int b2k_set_msm_occupancy(b2k_ctx* ctx, int blocks_per_sm) {
   if (!ctx || blocks_per_sm < 4 || blocks_per_sm > 6) return B2K_ERR_ARG;
   ctx->acc_minb = blocks_per_sm;
@@ -203,10 +212,6 @@ int b2k_set_msm_variant(b2k_ctx* ctx, int v1) {
   return B2K_OK;
 }
 
-int b2k_bls12381_g1_mul_batch(b2k_ctx* c, size_t n, const uint8_t* s, const uint8_t* p, uint8_t* o) { return mul_batch_host<Bls381G1, false>(c, n, s, p, o); }
-int b2k_bls12381_g1_mul_batch_affine(b2k_ctx* c, size_t n, const uint8_t* s, const uint8_t* p, uint8_t* o) { return mul_batch_host<Bls381G1, true>(c, n, s, p, o); }
-int b2k_bls12381_g1_mul_batch_dev(b2k_ctx* c, size_t n, const void* s, const void* p, void* o) { return mul_batch_dev<Bls381G1, false>(c, n, s, p, o); }
-int b2k_bls12381_g1_mul_batch_affine_dev(b2k_ctx* c, size_t n, const void* s, const void* p, void* o) { return mul_batch_dev<Bls381G1, true>(c, n, s, p, o); }
 int b2k_bls12381_g1_msm(b2k_ctx* c, size_t n, const uint8_t* s, const uint8_t* p, uint8_t* o) { return msm_host<Bls381G1>(c, n, s, p, o); }
 int b2k_bls12381_g1_msm_affine(b2k_ctx* c, size_t n, const uint8_t* s, const uint8_t* p, uint8_t* o) { return msm_host<Bls381G1>(c, n, s, p, o, 1); }
 int b2k_bls12381_g1_msm_async(b2k_ctx* c, size_t n, const uint8_t* s, const uint8_t* p, uint8_t* o) { return msm_host<Bls381G1>(c, n, s, p, o, 0, false); }

@@ -34,8 +34,10 @@ struct b2k_ctx {
   int affine_batch = 0;             // outputs (batched affine additions) per thread of a round, 8..64; 0 = automatic
   int mul_minb = 0;                 // BLS12-381 G1 Point.Mul batches: resident blocks per SM (0 = compiler's choice, 3, 4), tuning aid
   int acc_minb = 4;                 // resident accumulate blocks per SM (launch bound), tuning aid
+  int reduce_levels = 0;            // bucket reduction: 0 = automatic (two levels for >= 4096 buckets per window), 1, 2
+  int reduce_m1 = 0, reduce_m2 = 0; // chunk sizes of the two levels (0 = 8 and 4), tuning aid
   int pair_variant = 0; // launch-bound variant of the pairing kernels (tuning aid)
-  int last_plan[16] = {};           // what the last MSM ran with: c, W, buckets/window, chunk, slice length, affine rounds, their batch widths
+  int last_plan[20] = {};           // what the last MSM ran with: c, W, buckets/window, chunk, slice length, affine rounds, their batch widths
   uint64_t launches = 0;
   std::string err;
 };

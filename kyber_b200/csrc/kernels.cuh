@@ -390,6 +390,35 @@ __global__ void __launch_bounds__(128) k_msm_reduce_chunks_parts(int nb, int m, 
   partials[id] = out;
 }
 
+// ---- two-level bucket reduction (msm.cuh: msm_reduce_l1 / msm_reduce_l2) ---------------------------------------------------
+// partials layout per window: [T1 = nb/m1 level-1 sums][T2 = T1/m2 level-2 sums], TP = T1 + T2; runs: [w_cnt][T1]
+template <class CV>
+__global__ void __launch_bounds__(128) k_msm_reduce_l1(int nb, int m1, int m2, int w_cnt, int parts,
+                                                       const Xyzz<typename CV::F>* __restrict__ buckets,
+                                                       Xyzz<typename CV::F>* __restrict__ partials,
+                                                       Xyzz<typename CV::F>* __restrict__ runs) {
+  const int T1 = nb / m1, TP = T1 + T1 / m2;
+  size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (id >= (size_t)w_cnt * T1) return;
+  int w = (int)(id / T1), t = (int)(id % T1);
+  Xyzz<typename CV::F> acc, run;
+  msm_reduce_l1<CV>(acc, run, buckets + (size_t)w * nb, parts, (size_t)w_cnt * nb, t, m1);
+  partials[(size_t)w * TP + t] = acc;
+  runs[id] = run;
+}
+template <class CV>
+__global__ void __launch_bounds__(128) k_msm_reduce_l2(int nb, int m1, int m2, int log2_m1, int w_cnt,
+                                                       const Xyzz<typename CV::F>* __restrict__ runs,
+                                                       Xyzz<typename CV::F>* __restrict__ partials) {
+  const int T1 = nb / m1, T2 = T1 / m2, TP = T1 + T2;
+  size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (id >= (size_t)w_cnt * T2) return;
+  int w = (int)(id / T2), u = (int)(id % T2);
+  Xyzz<typename CV::F> out;
+  msm_reduce_l2<CV>(out, runs + (size_t)w * T1, u, m2, log2_m1);
+  partials[(size_t)w * TP + T1 + u] = out;
+}
+
 // ---- MSM stage 6: per-window sum of the partials (one block per window) --------------------------
 template <class CV>
 __global__ void __launch_bounds__(128) k_msm_window_sum(int T, const Xyzz<typename CV::F>* __restrict__ partials,

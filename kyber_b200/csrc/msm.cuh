@@ -109,6 +109,56 @@ B2K_D void msm_reduce_chunk_parts(Xyzz<typename CV::F>& out, const Xyzz<typename
   out = acc;
 }
 
+// ---- two-level bucket reduction ---------------------------------------------------------------------------------------
+// The chunk offset (t m) * run of msm_reduce_chunk is a ~13-bit double-and-add PER CHUNK: half of the single-level
+// reduction's field products, and divergent inside a warp.  Two levels move it to where there are m1 times fewer operands:
+//   level 1, chunk t of m1 buckets:   acc_t = sum_j (j+1) B[t m1 + j],   run_t = sum_j B[t m1 + j]          (no scalar mul)
+//   window sum = sum_t acc_t + m1 * sum_t t * run_t
+//   level 2, chunk u of m2 runs:      m1 * sum_v (u m2 + v) run_{u m2 + v}     (running sums + ONE small scalar mul per m1 m2 buckets)
+// Both outputs go into one partials array ([T1 level-1 sums][T1/m2 level-2 sums] per window) that k_msm_window_sum adds up.
+// `parts`/`stride`: the bucket is the sum of `parts` partial arrays (multi-GPU bucket exchange), 1/0 otherwise.
+template <class CV>
+B2K_D void msm_reduce_l1(Xyzz<typename CV::F>& acc_out, Xyzz<typename CV::F>& run_out, const Xyzz<typename CV::F>* B,
+                         int parts, size_t stride, int t, int m1) {
+  using X = Xyzz<typename CV::F>;
+  X run, acc;
+  xyzz_set_inf(run);
+  xyzz_set_inf(acc);
+  for (int k = m1 - 1; k >= 0; k--) {
+    X b = B[t * m1 + k];
+    for (int p = 1; p < parts; p++) {
+      X q = B[(size_t)p * stride + (size_t)(t * m1 + k)];
+      xyzz_add(b, b, q);
+    }
+    xyzz_add(run, run, b);
+    xyzz_add(acc, acc, run);
+  }
+  acc_out = acc;
+  run_out = run;
+}
+// R = the T1 level-1 run sums of one window; out = m1 * sum_{v < m2} (u m2 + v) R[u m2 + v],  m1 = 2^log2_m1
+template <class CV>
+B2K_D void msm_reduce_l2(Xyzz<typename CV::F>& out, const Xyzz<typename CV::F>* R, int u, int m2, int log2_m1) {
+  using X = Xyzz<typename CV::F>;
+  X run, acc;
+  xyzz_set_inf(run);
+  xyzz_set_inf(acc);
+  for (int v = m2 - 1; v >= 1; v--) {
+    X b = R[u * m2 + v];
+    xyzz_add(run, run, b);
+    xyzz_add(acc, acc, run);      // after the loop: acc = sum v R[u m2 + v]
+  }
+  if (u != 0) {
+    X b = R[u * m2];
+    xyzz_add(run, run, b);        // run = sum R
+    X off;
+    xyzz_mul_small(off, run, (uint32_t)(u * m2));
+    xyzz_add(acc, acc, off);
+  }
+  for (int i = 0; i < log2_m1; i++) xyzz_dbl(acc, acc);
+  out = acc;
+}
+
 // ---- final: Horner over window sums --------------------------------------------------------------
 template <class CV>
 B2K_D void msm_horner(Xyzz<typename CV::F>& out, const Xyzz<typename CV::F>* wsum, int W, int c) {

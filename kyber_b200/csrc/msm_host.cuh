@@ -68,6 +68,41 @@ inline uint32_t slice_len_entries(size_t e, int force_L) {
 inline uint32_t slice_len(size_t n, const MsmPlan& pl, int force_L) { return slice_len_entries(n * (size_t)pl.W, force_L); }
 
 
+// ---- bucket reduction: one level (chunks of pl.m buckets, a small scalar multiplication per chunk) or two levels
+// (msm.cuh: msm_reduce_l1 / msm_reduce_l2: the scalar multiplications move to the level with m1 times fewer operands) ----
+struct ReducePlan {
+  int levels = 1;
+  int m1 = 1, m2 = 1, log2_m1 = 0;
+  int T1 = 0;      // level-1 chunks (= run sums) per window
+  int TP = 0;      // partials per window that the window sum adds up
+};
+inline ReducePlan reduce_plan(const b2k_ctx* ctx, int nb, int single_m) {
+  ReducePlan rp;
+  // defaults measured at C2 (profiles/r01i_reduce_ab.txt): (8, 4) -> 6.54 ms per pipelined MSM against 7.04 for one level
+  int m1 = ctx->reduce_m1 > 0 ? ctx->reduce_m1 : 8, m2 = ctx->reduce_m2 > 0 ? ctx->reduce_m2 : 4;
+  const bool fits = nb >= 4096 && nb % (m1 * m2) == 0;
+  const bool two = ctx->reduce_levels == 2 ? (nb % (m1 * m2) == 0 && nb / (m1 * m2) >= 1) : (ctx->reduce_levels == 0 && fits);
+  if (two) {
+    rp.levels = 2; rp.m1 = m1; rp.m2 = m2;
+    while ((1 << rp.log2_m1) < m1) rp.log2_m1++;
+    rp.T1 = nb / m1;
+    rp.TP = rp.T1 + rp.T1 / m2;
+  } else {
+    rp.m1 = single_m; rp.T1 = nb / single_m; rp.TP = rp.T1;
+  }
+  return rp;
+}
+// sub-blocks of the two-level window sum: S blocks of TP / S partials each
+inline int window_sum_split(int TP) {
+  int S = 1;
+  if (TP >= 1024) {
+    S = TP / 512;
+    if (S > 128) S = 128;
+    while (S > 1 && TP % S) S--;
+  }
+  return S;
+}
+
 inline int check_flags(b2k_ctx* ctx) {
   uint32_t f = *ctx->h_flags;
   if (f & FLAG_SCALAR_RANGE) { ctx->err = "scalar not below the group order"; return B2K_ERR_SCALAR_RANGE; }
@@ -149,6 +184,10 @@ size_t msm_scratch_bytes(const b2k_ctx* ctx, size_t n, const MsmPlan& pl) {
   b += pad256(n * (size_t)pl.W * 4);              // entries
   b += pad256(total * sizeof(Xyzz<F>));           // buckets
   b += pad256((size_t)pl.W * T * sizeof(Xyzz<F>));  // partials
+  {
+    const ReducePlan rp = reduce_plan(ctx, pl.nb, pl.m);
+    b += pad256((size_t)pl.W * (size_t)(rp.TP + rp.T1) * sizeof(Xyzz<F>));   // two-level partials + run sums
+  }
   b += pad256((size_t)pl.W * (1 + 128) * sizeof(Xyzz<F>));    // window sums + their sub-block partials
   size_t smax = (n * (size_t)pl.W) / (size_t)slice_len(n, pl, force_L) + 2;
   const AffinePlan ap = affine_plan<CV>(ctx, n, pl);
@@ -189,14 +228,15 @@ int msm_enqueue(b2k_ctx* ctx, size_t n_in, const MsmPlan& pl, const uint8_t* d_s
   auto* own_buckets = arena_take<Xyzz<F>>(ctx, total);
   // bucket exchange (multi-GPU shape 1): the pipeline stops after the fix-up and leaves the W x 2^(c-1) buckets in the caller's buffer
   auto* buckets = ext_buckets ? ext_buckets : own_buckets;
-  auto* partials = arena_take<Xyzz<F>>(ctx, (size_t)pl.W * T);
+  const ReducePlan rp = reduce_plan(ctx, pl.nb, pl.m);
+  auto* partials = arena_take<Xyzz<F>>(ctx, (size_t)pl.W * (size_t)(rp.TP > T ? rp.TP : T));
+  auto* runs = arena_take<Xyzz<F>>(ctx, (size_t)pl.W * rp.T1);
   auto* wsum = arena_take<Xyzz<F>>(ctx, pl.W);
   // window sum in two levels when a window has many chunk partials: S sub-blocks of >= 512 partials each
-  int S = T >= 1024 ? T / 512 : 1;
-  if (S > 128) S = 128;
+  const int S = window_sum_split(rp.TP);
   auto* wpart = arena_take<Xyzz<F>>(ctx, (size_t)pl.W * 128);
   if (!wpart) { ctx->err = "scratch arena too small"; return B2K_ERR_ARG; }
-  if (!pts || !counts || !offs || !cursor || !entries || !own_buckets || !partials || !wsum) {
+  if (!pts || !counts || !offs || !cursor || !entries || !own_buckets || !partials || !runs || !wsum) {
     ctx->err = "scratch arena too small";
     return B2K_ERR_ARG;
   }
@@ -236,6 +276,7 @@ int msm_enqueue(b2k_ctx* ctx, size_t n_in, const MsmPlan& pl, const uint8_t* d_s
     for (int r = 0; r < PT_MAX_ROUNDS; r++) lp[6 + r] = r < ap.R ? (int)ap.B[r] : 0;
     lp[14] = glv ? 1 : 0;
     lp[15] = (ap.R > 0 && ctx->affine_split) ? 1 : 0;
+    lp[16] = rp.levels; lp[17] = rp.m1; lp[18] = rp.levels == 2 ? rp.m2 : 0;
   }
   uint32_t* big_count = bsum + 1023;      // last word of the block-sum page is never a block sum (<= 1023 blocks used)
   unsigned gb_n = (unsigned)((n + 255) / 256);
@@ -357,14 +398,20 @@ int msm_enqueue(b2k_ctx* ctx, size_t n_in, const MsmPlan& pl, const uint8_t* d_s
     ctx->timings_valid = true;
     return B2K_OK;
   }
-  size_t nchunks = (size_t)pl.W * T;
-  k_msm_reduce_chunks<CV><<<(unsigned)((nchunks + 127) / 128), 128, 0, st>>>(pl, buckets, partials); nl++;
+  if (rp.levels == 2) {
+    const size_t n1 = (size_t)pl.W * rp.T1, n2 = (size_t)pl.W * (rp.T1 / rp.m2);
+    k_msm_reduce_l1<CV><<<(unsigned)((n1 + 127) / 128), 128, 0, st>>>(pl.nb, rp.m1, rp.m2, pl.W, 1, buckets, partials, runs);
+    k_msm_reduce_l2<CV><<<(unsigned)((n2 + 127) / 128), 128, 0, st>>>(pl.nb, rp.m1, rp.m2, rp.log2_m1, pl.W, runs, partials); nl += 2;
+  } else {
+    size_t nchunks = (size_t)pl.W * T;
+    k_msm_reduce_chunks<CV><<<(unsigned)((nchunks + 127) / 128), 128, 0, st>>>(pl, buckets, partials); nl++;
+  }
   CK(cudaEventRecord(ctx->ev[6], st));
   if (S > 1) {
-    k_msm_window_sum<CV><<<pl.W * S, 128, 0, st>>>(T / S, partials, wpart);      // (w, s) -> wpart[w S + s]
+    k_msm_window_sum<CV><<<pl.W * S, 128, 0, st>>>(rp.TP / S, partials, wpart);      // (w, s) -> wpart[w S + s]
     k_msm_window_sum<CV><<<pl.W, 128, 0, st>>>(S, wpart, wsum); nl += 2;
   } else {
-    k_msm_window_sum<CV><<<pl.W, 128, 0, st>>>(T, partials, wsum); nl++;
+    k_msm_window_sum<CV><<<pl.W, 128, 0, st>>>(rp.TP, partials, wsum); nl++;
   }
   CK(cudaEventRecord(ctx->ev[7], st));
   k_msm_final<CV><<<1, 128, 0, st>>>(pl, wsum, d_out, affine_out); nl++;
@@ -435,26 +482,36 @@ int msm_reduce_windows_dev(b2k_ctx* ctx, int c, int w_cnt, int parts, const void
   CK(cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
   const int nb = 1 << (c - 1);
-  int m = 1;                                       // chunk: keep >= 16k reduction threads for the few windows of one rank
+  int m = 1;                                       // single-level chunk: keep >= 16k reduction threads for the few windows of one rank
   while (m < 64 && m * 2 <= nb && ((size_t)w_cnt * nb) / (size_t)(m * 2) >= 16384) m *= 2;
   if (ctx->force_m > 0 && ctx->force_m <= nb && (ctx->force_m & (ctx->force_m - 1)) == 0) m = ctx->force_m;
-  const int T = nb / m;
-  int S = T >= 1024 ? T / 512 : 1;
-  if (S > 128) S = 128;
-  int rc = arena_reserve(ctx, pad256((size_t)w_cnt * T * sizeof(X)) + pad256((size_t)w_cnt * 128 * sizeof(X)) + 4096);
+  const ReducePlan rp = reduce_plan(ctx, nb, m);
+  const int S = window_sum_split(rp.TP);
+  int rc = arena_reserve(ctx, pad256((size_t)w_cnt * rp.TP * sizeof(X)) + pad256((size_t)w_cnt * rp.T1 * sizeof(X)) +
+                                  pad256((size_t)w_cnt * 128 * sizeof(X)) + 4096);
   if (rc) return rc;
-  auto* partials = arena_take<X>(ctx, (size_t)w_cnt * T);
+  auto* partials = arena_take<X>(ctx, (size_t)w_cnt * rp.TP);
+  auto* runs = arena_take<X>(ctx, (size_t)w_cnt * rp.T1);
   auto* wpart = arena_take<X>(ctx, (size_t)w_cnt * 128);
-  if (!partials || !wpart) { ctx->err = "scratch arena too small"; return B2K_ERR_ARG; }
-  const size_t nchunks = (size_t)w_cnt * T;
-  k_msm_reduce_chunks_parts<CV><<<(unsigned)((nchunks + 127) / 128), 128, 0, st>>>(nb, m, w_cnt, parts, reinterpret_cast<const X*>(d_recv), partials);
-  if (S > 1) {
-    k_msm_window_sum<CV><<<w_cnt * S, 128, 0, st>>>(T / S, partials, wpart);
-    k_msm_window_sum<CV><<<w_cnt, 128, 0, st>>>(S, wpart, reinterpret_cast<X*>(d_wsum));
-    ctx->launches += 3;
-  } else {
-    k_msm_window_sum<CV><<<w_cnt, 128, 0, st>>>(T, partials, reinterpret_cast<X*>(d_wsum));
+  if (!partials || !runs || !wpart) { ctx->err = "scratch arena too small"; return B2K_ERR_ARG; }
+  const X* recv = reinterpret_cast<const X*>(d_recv);
+  if (rp.levels == 2) {
+    const size_t n1 = (size_t)w_cnt * rp.T1, n2 = (size_t)w_cnt * (rp.T1 / rp.m2);
+    k_msm_reduce_l1<CV><<<(unsigned)((n1 + 127) / 128), 128, 0, st>>>(nb, rp.m1, rp.m2, w_cnt, parts, recv, partials, runs);
+    k_msm_reduce_l2<CV><<<(unsigned)((n2 + 127) / 128), 128, 0, st>>>(nb, rp.m1, rp.m2, rp.log2_m1, w_cnt, runs, partials);
     ctx->launches += 2;
+  } else {
+    const size_t nchunks = (size_t)w_cnt * rp.T1;
+    k_msm_reduce_chunks_parts<CV><<<(unsigned)((nchunks + 127) / 128), 128, 0, st>>>(nb, m, w_cnt, parts, recv, partials);
+    ctx->launches += 1;
+  }
+  if (S > 1) {
+    k_msm_window_sum<CV><<<w_cnt * S, 128, 0, st>>>(rp.TP / S, partials, wpart);
+    k_msm_window_sum<CV><<<w_cnt, 128, 0, st>>>(S, wpart, reinterpret_cast<X*>(d_wsum));
+    ctx->launches += 2;
+  } else {
+    k_msm_window_sum<CV><<<w_cnt, 128, 0, st>>>(rp.TP, partials, reinterpret_cast<X*>(d_wsum));
+    ctx->launches += 1;
   }
   CK(cudaGetLastError());
   return B2K_OK;

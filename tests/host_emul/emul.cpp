@@ -178,7 +178,7 @@ static int emul_msm(size_t n, const uint8_t* scalars, const uint8_t* pts, int c,
 // virtual ranks: contiguous shards of the pairs -> partial buckets per rank -> "all-to-all" (rank g gets windows
 // [g wc, (g+1) wc) of every rank, layout [part][wc][nb]) -> msm_reduce_chunk_parts + window sums -> "all-gather" -> Horner.
 template <class CV>
-static int emul_msm_exchange(size_t n, const uint8_t* scalars, const uint8_t* pts, int c, int m, int L, int rounds, int PB, int world, uint8_t* out) {
+static int emul_msm_exchange(size_t n, const uint8_t* scalars, const uint8_t* pts, int c, int m, int L, int rounds, int PB, int world, uint8_t* out, int m2 = 0) {
   using F = typename CV::F;
   using X = Xyzz<F>;
   MsmPlan pl = emul_plan(c, m);
@@ -202,6 +202,21 @@ static int emul_msm_exchange(size_t n, const uint8_t* scalars, const uint8_t* pt
     for (int p = 0; p < world; p++) memcpy((void*)&recv[(size_t)p * wc * pl.nb], (const void*)&Bs[p][(size_t)g * wc * pl.nb], (size_t)wc * pl.nb * sizeof(X));
     for (int w = 0; w < wc; w++) {
       X a; xyzz_set_inf(a);
+      if (m2 > 0) {     // two-level reduction (msm_reduce_l1 / msm_reduce_l2): the window sum is the sum of all T + T/m2 partials
+        if (T % m2) return -2;
+        int lg = 0; while ((1 << lg) < m) lg++;
+        std::vector<X> runs(T);
+        for (int t = 0; t < T; t++) {
+          X part;
+          msm_reduce_l1<CV>(part, runs[t], &recv[(size_t)w * pl.nb], world, (size_t)wc * pl.nb, t, m);
+          xyzz_add(a, a, part);
+        }
+        for (int u = 0; u < T / m2; u++) {
+          X part;
+          msm_reduce_l2<CV>(part, runs.data(), u, m2, lg);
+          xyzz_add(a, a, part);
+        }
+      } else
       for (int t = 0; t < T; t++) {
         X part;
         msm_reduce_chunk_parts<CV>(part, &recv[(size_t)w * pl.nb], world, (size_t)wc * pl.nb, t, m);
@@ -217,6 +232,13 @@ static int emul_msm_exchange(size_t n, const uint8_t* scalars, const uint8_t* pt
 }
 
 extern "C" {
+// two-level bucket reduction (m1, m2), single rank or `world` virtual ranks
+int emul_bls12381_g1_msm_reduce2(size_t n, const uint8_t* s, const uint8_t* p, int c, int m1, int m2, int L, int world, uint8_t* o) {
+  return emul_msm_exchange<Bls381G1>(n, s, p, c, m1, L, 0, 1, world, o, m2);
+}
+int emul_bn254_g1_msm_reduce2(size_t n, const uint8_t* s, const uint8_t* p, int c, int m1, int m2, int L, uint8_t* o) {
+  return emul_msm_exchange<Bn254G1>(n, s, p, c, m1, L, 0, 1, 1, o, m2);
+}
 int emul_bls12381_g1_msm_exchange(size_t n, const uint8_t* s, const uint8_t* p, int c, int m, int L, int rounds, int PB, int world, uint8_t* o) {
   return emul_msm_exchange<Bls381G1>(n, s, p, c, m, L, rounds, PB, world, o);
 }

@@ -218,6 +218,36 @@ def test_bucket_exchange_bodies(emul):
     assert emul.emul_bls12381_g1_msm_exchange(ctypes.c_size_t(n), sb, pb, 13, 2, 3, 0, 1, 8, o48) == -2
 
 
+def test_two_level_bucket_reduction_bodies(emul):
+    """msm.cuh: msm_reduce_l1 / msm_reduce_l2 (window sum = sum of the level-1 running sums + m1 * sum_t t * run_t, the second
+    term reduced again in chunks of m2 with one small scalar multiplication per chunk) against the oracle, for several chunk
+    shapes incl. m2 = 1 and a whole window in one level-2 chunk, skewed scalars, and combined with the bucket exchange."""
+    rng = random.Random(29)
+    n = 30
+    pts = [o.g1_mul(rng.randrange(1, o.R)) for _ in range(n)]
+    pts[4] = pts[5]
+    pts[9] = None
+    pb = b"".join(o.g1_to_affine_bytes(p) for p in pts)
+    for ks in ([rng.randrange(o.R) for _ in range(n)], [o.R - 1] * n, [rng.randrange(1 << 13) for _ in range(n)]):
+        sb = b"".join(o.scalar_to_bytes(k) for k in ks)
+        want = o.g1_compress(o.g1_msm(ks, pts))
+        for c, m1, m2, L, world in ((4, 2, 2, 0, 1), (4, 1, 8, 2, 1), (8, 4, 4, 3, 1), (8, 8, 16, 0, 1), (8, 2, 1, 5, 1),
+                                    (16, 4, 4, 2, 1), (8, 4, 4, 3, 4), (16, 4, 8, 2, 8)):
+            o48 = ctypes.create_string_buffer(48)
+            rc = emul.emul_bls12381_g1_msm_reduce2(ctypes.c_size_t(n), sb, pb, c, m1, m2, L, world, o48)
+            assert rc == 0 and o48.raw == want, (c, m1, m2, L, world)
+    from oracle import bn254 as o4
+    pts4 = [o4.g1_mul(rng.randrange(1, o4.ORDER)) for _ in range(10)]
+    ks4 = [rng.randrange(o4.ORDER) for _ in range(10)]
+    acc = None
+    for k, p4 in zip(ks4, pts4):
+        acc = o4.g1_add(acc, o4.g1_mul(k, p4))
+    o64 = ctypes.create_string_buffer(64)
+    assert emul.emul_bn254_g1_msm_reduce2(ctypes.c_size_t(10), b"".join(k.to_bytes(32, "big") for k in ks4),
+                                          b"".join(o4.g1_marshal(p) for p in pts4), 8, 4, 4, 3, o64) == 0
+    assert o64.raw == o4.g1_marshal(acc)
+
+
 def test_hash_to_curve_bodies():
     from oracle import h2c_bls12381 as h, h2c_bls12381_g2 as h2
     l1, l2 = _lib("emul_h2c"), _lib("emul_h2c_g2")
