@@ -378,10 +378,9 @@ int msm_enqueue(b2k_ctx* ctx, size_t n_in, const MsmPlan& pl, const uint8_t* d_s
       }
     } else {
     CK(cudaEventRecord(ctx->ev[10], st));
-    // resident blocks per SM (register cap 65536/(128*MINB)): 4 -> no spills, 5/6 -> more warps, small spills
-    if (ctx->acc_minb == 5) k_msm_accumulate_slices<CV, 5><<<(smax + 127) / 128, 128, 0, st>>>(smax, L, (uint32_t)total, pts, offs, entries, buckets, spart);
-    else if (ctx->acc_minb == 6) k_msm_accumulate_slices<CV, 6><<<(smax + 127) / 128, 128, 0, st>>>(smax, L, (uint32_t)total, pts, offs, entries, buckets, spart);
-    else k_msm_accumulate_slices<CV, 4><<<(smax + 127) / 128, 128, 0, st>>>(smax, L, (uint32_t)total, pts, offs, entries, buckets, spart);
+    // 4 resident blocks per SM (register cap 65536 / (128 * 4)): no spills.  The 5- and 6-block variants (more warps, small
+    // spills) measured slower and were removed to halve the build time; b2k_set_msm_occupancy is ignored.
+    k_msm_accumulate_slices<CV, 4><<<(smax + 127) / 128, 128, 0, st>>>(smax, L, (uint32_t)total, pts, offs, entries, buckets, spart);
     nl++;
     CK(cudaEventRecord(ctx->ev[9], st));
     k_msm_fixup<CV><<<(unsigned)((total + 127) / 128), 128, 0, st>>>((uint32_t)total, L, offs, buckets, spart, big_count, big_list);
@@ -578,12 +577,10 @@ int mul_batch_dev(b2k_ctx* ctx, size_t n, const void* d_scalars, const void* d_p
   }
   CK(cudaSetDevice(ctx->device));
   const unsigned grid = (unsigned)((n + 127) / 128);
-  bool launched = false;
-  if constexpr (MulGlv<CV>::enabled) {            // BLS12-381 G1: resident blocks per SM selectable (register cap), tuning aid
-    if (ctx->mul_minb == 3) { k_mul_batch<CV, AFF, 3><<<grid, 128, 0, ctx->stream>>>(n, (const uint8_t*)d_scalars, (const uint8_t*)d_points, (uint8_t*)d_out, ctx->d_flags, ctx->use_glv); launched = true; }
-    else if (ctx->mul_minb == 4) { k_mul_batch<CV, AFF, 4><<<grid, 128, 0, ctx->stream>>>(n, (const uint8_t*)d_scalars, (const uint8_t*)d_points, (uint8_t*)d_out, ctx->d_flags, ctx->use_glv); launched = true; }
-  }
-  if (!launched) k_mul_batch<CV, AFF><<<grid, 128, 0, ctx->stream>>>(
+  // (the 3- and 4-blocks-per-SM variants of the G1 kernel measured 0.6x / 0.7x of the compiler's own register allocation,
+  //  profiles/r01h_mul_batch_ab.txt, and tripled the build time of this translation unit: removed; b2k_set_mul_occupancy
+  //  is accepted and ignored)
+  k_mul_batch<CV, AFF><<<grid, 128, 0, ctx->stream>>>(
       n, (const uint8_t*)d_scalars, (const uint8_t*)d_points, (uint8_t*)d_out, ctx->d_flags, ctx->use_glv);
   CK(cudaGetLastError());
   ctx->launches += 1;
