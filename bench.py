@@ -477,7 +477,7 @@ def run_ours(args):
     #     under the kernels of the other.  Every step still moves its 128 MiB host->device and its result device->host
     #     inside the timed region.  Timed on the device: start event at the head of context 0's stream, end events behind
     #     the last enqueued work of each context.
-    NE = max(1, min(int(os.environ.get("B2K_E2E_INFLIGHT", "3")), NC))
+    NE = max(1, min(int(os.environ.get("B2K_E2E_INFLIGHT", str(NC))), NC))
     e2e_status = []
 
     def e2e_submit(k: int):
@@ -634,7 +634,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--exchange", default="buckets", choices=["result", "buckets"],
                     help="multi-GPU exchange shape of the headline step (the other one is timed and reported beside it)")
-    ap.add_argument("--contexts", type=int, default=3, help="independent steps in flight (streams); 1 = strictly serial")
+    ap.add_argument("--contexts", type=int, default=4, help="independent steps in flight (streams); 1 = strictly serial")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
