@@ -22,7 +22,8 @@
  *     the caller (one context per goroutine/thread), several contexts may be used concurrently
  *   - there is NO CPU fallback: without a usable sm_100 device b2k_create fails
  *   - *_dev variants take DEVICE pointers (same layouts) and only enqueue work on the context's
- *     stream; they exist so a caller that keeps batches resident in HBM pays no PCIe traffic
+ *     stream; they exist so a caller that keeps batches resident in HBM pays no PCIe traffic;
+ *     data errors of enqueued work (scalar >= order, malformed point) are collected by b2k_wait
  */
 #ifndef B2KYBER_H
 #define B2KYBER_H
@@ -170,7 +171,10 @@ int b2k_bls12381_g1_msm_affine(b2k_ctx* ctx, size_t n, const uint8_t* scalars, c
  * context is done and returns the deferred status of the last MSM (B2K_ERR_SCALAR_RANGE ...).  Two contexts used
  * alternately (async on A, async on B, wait A, async on A, ...) keep the PCIe copies of one batch under the kernels
  * of the other: this is how a caller with a stream of batches (goroutines verifying aggregates, share/poly recoveries)
- * should drive the library; the blocking form is this followed by b2k_wait. */
+ * should drive the library; the blocking form is this followed by b2k_wait.
+ * b2k_wait is also the status query after *_dev calls (which only enqueue and therefore cannot report data errors themselves):
+ * the device status word is sticky across them; b2k_wait synchronises, returns B2K_ERR_SCALAR_RANGE / B2K_ERR_POINT if any
+ * call since the previous b2k_wait (or host-buffer call) saw such an operand, and clears it. */
 int b2k_bls12381_g1_msm_async(b2k_ctx* ctx, size_t n, const uint8_t* scalars, const uint8_t* points, uint8_t* out);
 int b2k_wait(b2k_ctx* ctx);
 int b2k_bls12381_g2_msm_affine(b2k_ctx* ctx, size_t n, const uint8_t* scalars, const uint8_t* points, uint8_t* out /*[192]*/);

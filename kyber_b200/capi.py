@@ -32,6 +32,7 @@ def load_library() -> C.CDLL:
         "b2k_version": (C.c_char_p, []),
         "b2k_set_stream": (C.c_int, [vp, vp]),
         "b2k_synchronize": (C.c_int, [vp]),
+        "b2k_wait": (C.c_int, [vp]),
         "b2k_last_timings": (C.c_int, [vp, C.POINTER(C.c_float), C.c_int]),
         "b2k_set_msm_window": (C.c_int, [vp, C.c_int]),
         "b2k_launch_count": (C.c_uint64, [vp]),
@@ -152,6 +153,10 @@ class Engine:
 
     def set_stream(self, cuda_stream: int):
         self._check(self.lib.b2k_set_stream(self.h, C.c_void_p(cuda_stream)))
+
+    def wait(self):
+        """synchronise and raise the deferred status (scalar range / malformed point) of everything enqueued since the last wait"""
+        self._check(self.lib.b2k_wait(self.h))
 
     def synchronize(self):
         self._check(self.lib.b2k_synchronize(self.h))

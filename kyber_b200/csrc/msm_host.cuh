@@ -562,9 +562,13 @@ int msm_host(b2k_ctx* ctx, size_t n, const uint8_t* scalars, const uint8_t* poin
   return check_flags(ctx);
 }
 
+// Also the status query of the *_dev entry points, which only enqueue: the device status word (scalar range, malformed
+// point) is sticky across them, fetched and cleared here.
 inline int msm_wait(b2k_ctx* ctx) {
   if (!ctx) return B2K_ERR_ARG;
   CK(cudaSetDevice(ctx->device));
+  CK(cudaMemcpyAsync(ctx->h_flags, ctx->d_flags, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemsetAsync(ctx->d_flags, 0, 4, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   return check_flags(ctx);
 }

@@ -101,3 +101,28 @@ def test_bucket_exchange_driver_world_1(engine):
     assert bytes(out.cpu().tolist()) == o.g1_compress(o.g1_mul(wl.dot_mod(s, a, o.R)))
     with pytest.raises(Exception):                               # bucket buffer too small: refused, not overrun
         engine.bls12381_g1_msm_buckets_dev(n, d_s.data_ptr(), d_p.data_ptr(), buckets.data_ptr(), buckets.numel() - 1)
+
+
+def test_dev_entry_points_report_data_errors_at_wait(engine):
+    """*_dev calls only enqueue; an out-of-range scalar surfaces at b2k_wait (sticky status word), once."""
+    import torch
+    from kyber_b200.capi import B2KError
+    n = 2048
+    a, s, d_s, d_p, dev = _setup(engine, n, "b2k/xchg-bad")
+    bad = d_s.clone()
+    bad[32 * 7:32 * 8] = torch.frombuffer(bytearray(o.R.to_bytes(32, "big")), dtype=torch.uint8).to(dev)
+    out = torch.zeros(48, dtype=torch.uint8, device=dev)
+    plan = engine.bls12381_g1_msm_bucket_plan(n)
+    buckets = torch.empty(plan["W"] * plan["buckets_per_window"] * plan["bucket_bytes"], dtype=torch.uint8, device=dev)
+    torch.cuda.synchronize()
+    engine.wait()                                                # clean slate
+    for call in (lambda sc: engine.call_dev("b2k_bls12381_g1_msm_dev", n, sc.data_ptr(), d_p.data_ptr(), out.data_ptr()),
+                 lambda sc: engine.bls12381_g1_msm_buckets_dev(n, sc.data_ptr(), d_p.data_ptr(), buckets.data_ptr(), buckets.numel())):
+        call(bad)                                                # accepted ...
+        with pytest.raises(B2KError) as ei:
+            engine.wait()                                        # ... reported here
+        assert ei.value.code == -3
+        engine.wait()                                            # cleared
+        call(d_s)
+        engine.wait()
+    assert bytes(out.cpu().tolist()) == o.g1_compress(o.g1_mul(wl.dot_mod(s, a, o.R)))
