@@ -88,7 +88,9 @@ int b2k_set_msm_affine(b2k_ctx* ctx, int rounds, int batch);
 /* 1 (default) = every affine round runs as three kernels (forward prefix products, one inversion per thread, backward
  * additions; batch up to 1024), 0 = one fused kernel per round (batch up to 64, prefix products in local memory).  A/B aid. */
 int b2k_set_msm_affine_split(b2k_ctx* ctx, int split);
-/* Resident bucket-accumulate blocks per SM.  The 5/6-block variants measured slower than 4 and were removed: accepted, ignored. */
+/* Register cap of the inversion kernel of the affine rounds: 4 [default] = uncapped; 5 = 96 registers, so that its single wave
+ * leaves one block slot per SM for a product kernel of another MSM in flight (measured: no gain; kept for A/B).  (The 5/6-block variants of the XYZZ kernel
+ * measured slower than 4 and were removed.) */
 int b2k_set_msm_occupancy(b2k_ctx* ctx, int blocks_per_sm);
 /* Resident blocks per SM of the BLS12-381 G1 Point.Mul batch kernel.  The constrained variants measured 0.6-0.7x of the
  * compiler's own allocation and were removed: accepted, ignored. */

@@ -33,7 +33,9 @@ struct b2k_ctx {
   int affine_split = 1;             // 1 = every round as three kernels (forward products / inversions / backward additions), 0 = one fused kernel
   int affine_batch = 0;             // outputs (batched affine additions) per thread of a round, 8..64; 0 = automatic
   int mul_minb = 0;                 // BLS12-381 G1 Point.Mul batches: resident blocks per SM (0 = compiler's choice, 3, 4), tuning aid
-  int acc_minb = 4;                 // resident accumulate blocks per SM (launch bound), tuning aid
+  int acc_minb = 4;                 // register cap of the inversion kernel of the affine rounds: 4 = uncapped (99 registers), 5 = 96 registers
+                                    // (leaves a block slot per SM for another MSM's product kernel: measured no gain,
+                                    // profiles/r01i_inversion_overlap_ab.txt); b2k_set_msm_occupancy, A/B aid
   int reduce_levels = 0;            // bucket reduction: 0 = automatic (two levels for >= 4096 buckets per window), 1, 2
   int reduce_m1 = 0, reduce_m2 = 0; // chunk sizes of the two levels (0 = 8 and 4), tuning aid
   int pair_variant = 0; // launch-bound variant of the pairing kernels (tuning aid)

@@ -253,8 +253,11 @@ __global__ void __launch_bounds__(128, 5) k_pt_forward(uint32_t B, uint32_t tota
   uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   msm_pairtree_forward<CV, FIRST>(t, B, gridDim.x * blockDim.x, total, in, entries, offs_in, offs_out, pre, accs);
 }
-template <class F>
-__global__ void __launch_bounds__(128, 4) k_pt_invert(uint32_t B, uint32_t total, const uint32_t* __restrict__ offs_out, F* __restrict__ accs) {
+// MINB = 5 caps the kernel at 96 registers: its one wave of 4 blocks per SM then leaves exactly one 128-register block slot,
+// so a product kernel of ANOTHER MSM in flight (another context) can run under this latency-bound inversion pass.
+// Measured on B200 with 4 MSMs in flight: 6.26-6.34 ms per MSM either way (profiles/r01i_inversion_overlap_ab.txt): off by default.
+template <class F, int MINB = 4>
+__global__ void __launch_bounds__(128, MINB) k_pt_invert(uint32_t B, uint32_t total, const uint32_t* __restrict__ offs_out, F* __restrict__ accs) {
   uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   msm_pairtree_invert<F>(t, B, total, offs_out, accs);
 }

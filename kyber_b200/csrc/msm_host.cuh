@@ -357,7 +357,8 @@ int msm_enqueue(b2k_ctx* ctx, size_t n_in, const MsmPlan& pl, const uint8_t* d_s
           if (ctx->affine_split) {
             if (r == 0) k_pt_forward<CV, true><<<grid, 128, 0, st>>>(ap.B[r], (uint32_t)total, in_cur, entries, offs_cur, offs_nxt, pt_pre, pt_accs);
             else k_pt_forward<CV, false><<<grid, 128, 0, st>>>(ap.B[r], (uint32_t)total, in_cur, nullptr, offs_cur, offs_nxt, pt_pre, pt_accs);
-            k_pt_invert<F><<<grid, 128, 0, st>>>(ap.B[r], (uint32_t)total, offs_nxt, pt_accs);
+            if (ctx->acc_minb == 5) k_pt_invert<F, 5><<<grid, 128, 0, st>>>(ap.B[r], (uint32_t)total, offs_nxt, pt_accs);
+            else k_pt_invert<F, 4><<<grid, 128, 0, st>>>(ap.B[r], (uint32_t)total, offs_nxt, pt_accs);
             if (r == 0) k_pt_backward<CV, true><<<grid, 128, 0, st>>>(ap.B[r], (uint32_t)total, in_cur, entries, offs_cur, offs_nxt, pt_pre, pt_accs, out);
             else k_pt_backward<CV, false><<<grid, 128, 0, st>>>(ap.B[r], (uint32_t)total, in_cur, nullptr, offs_cur, offs_nxt, pt_pre, pt_accs, out);
             nl += 7;
