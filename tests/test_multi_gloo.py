@@ -141,3 +141,24 @@ def test_bucket_exchange_two_ranks_gloo():
     for p in procs:
         p.join(timeout=60)
     assert sorted(res) == [(0, True), (1, True)]
+
+
+def test_bucket_exchange_without_process_group():
+    """world 1 (no torch.distributed): local buckets -> reduce -> finish, no collective; window counts that do not split are refused"""
+    from kyber_b200.multi import msm_bucket_exchange
+    calls = []
+
+    def local_buckets():
+        calls.append("buckets")
+        return torch.arange(6 * 4 * 2, dtype=torch.uint8)
+
+    def reduce_windows(recv, parts, w_cnt):
+        calls.append(("reduce", parts, w_cnt, recv.numel()))
+        return recv.view(6, 4, 2)[:, 0, :].reshape(-1).clone()
+
+    def finish(ws):
+        calls.append(("finish", ws.numel()))
+        return ws
+
+    out = msm_bucket_exchange(local_buckets, reduce_windows, finish, 6, 4, 2)
+    assert calls == ["buckets", ("reduce", 1, 6, 48), ("finish", 12)] and out.numel() == 12
