@@ -34,3 +34,22 @@ def test_montgomery_product_matches_bigints():
     b = m.budget()
     assert b["fp64_pipe_cycles"] < b["imad_form_pipe_cycles"]      # the FP64 form alone is shorter on ITS pipe ...
     assert b["issue_slots"] > 3 * b["imad_form_issue_slots"]       # ... but needs several times the issue slots: hence warp specialisation
+
+
+def test_cuda_header_host_build_matches_model(tmp_path):
+    """tools/probe/fp_dfma.cuh (the header the sm_100a probe kernel is built from) compiled for the host -- fma() under
+    FE_TOWARDZERO standing in for fma.rz.f64 -- gives a b R^-1 mod p limb for limb."""
+    import ctypes
+    import subprocess
+    so = str(tmp_path / "libfp_dfma_host.so")
+    subprocess.run(["g++", "-O2", "-frounding-math", "-shared", "-fPIC", "-std=c++17",
+                    os.path.join(ROOT, "tools", "probe", "fp_dfma_host.cpp"), "-o", so], check=True)
+    lib = ctypes.CDLL(so)
+    A = ctypes.c_uint64 * 8
+    rng = random.Random(11)
+    rinv = pow(m.R, -1, m.P)
+    ops = [0, 1, m.P - 1, m.P - 2, 1 << 380]
+    for a, b in [(a, b) for a in ops for b in ops] + [(rng.randrange(m.P), rng.randrange(m.P)) for _ in range(500)]:
+        out = A()
+        assert lib.dfma_mont_mul(A(*m.to_limbs(a)), A(*m.to_limbs(b)), out) == 0
+        assert m.from_limbs(list(out)) == a * b * rinv % m.P
