@@ -36,15 +36,65 @@ def test_montgomery_product_matches_bigints():
     assert b["issue_slots"] > 3 * b["imad_form_issue_slots"]       # ... but needs several times the issue slots: hence warp specialisation
 
 
-def test_cuda_header_host_build_matches_model(tmp_path):
-    """tools/probe/fp_dfma.cuh (the header the sm_100a probe kernel is built from) compiled for the host -- fma() under
-    FE_TOWARDZERO standing in for fma.rz.f64 -- gives a b R^-1 mod p limb for limb."""
+def _host_lib(tmp_path):
     import ctypes
     import subprocess
     so = str(tmp_path / "libfp_dfma_host.so")
     subprocess.run(["g++", "-O2", "-frounding-math", "-shared", "-fPIC", "-std=c++17",
                     os.path.join(ROOT, "tools", "probe", "fp_dfma_host.cpp"), "-o", so], check=True)
-    lib = ctypes.CDLL(so)
+    return ctypes.CDLL(so)
+
+
+def test_mixed_xyzz_addition_on_the_fp64_field(tmp_path):
+    """tools/probe/ec_dfma.cuh: field add/sub and the mixed XYZZ addition of the accumulate pass on the FP64-pipe field give the
+    oracle's group law, incl. accumulator at infinity, P + P (reported), P + (-P)."""
+    import ctypes
+    from oracle import bls12381 as o
+    lib = _host_lib(tmp_path)
+    A8, A16, A32 = ctypes.c_uint64 * 8, ctypes.c_uint64 * 16, ctypes.c_uint64 * 32
+    rng = random.Random(13)
+    mont = lambda x: m.to_limbs(x * m.R % m.P)
+    unmont = lambda limbs: m.from_limbs(limbs) * pow(m.R, -1, m.P) % m.P
+    for _ in range(200):
+        a, b = rng.randrange(m.P), rng.randrange(m.P)
+        s_, d_ = A8(), A8()
+        lib.dfma_add_sub(A8(*m.to_limbs(a)), A8(*m.to_limbs(b)), s_, d_)
+        assert m.from_limbs(list(s_)) == (a + b) % m.P and m.from_limbs(list(d_)) == (a - b) % m.P
+    for a, b in ((0, 0), (m.P - 1, m.P - 1), (0, m.P - 1), (m.P - 1, 0), (5, 5)):
+        s_, d_ = A8(), A8()
+        lib.dfma_add_sub(A8(*m.to_limbs(a)), A8(*m.to_limbs(b)), s_, d_)
+        assert m.from_limbs(list(s_)) == (a + b) % m.P and m.from_limbs(list(d_)) == (a - b) % m.P
+    one = A8(*mont(1))
+
+    def xyzz(pt, z):
+        x, y = pt
+        return mont(x * z * z % m.P) + mont(y * z * z * z % m.P) + mont(z * z % m.P) + mont(z * z * z % m.P)
+
+    def affine_of(acc):
+        X, Y, ZZ, ZZZ = (unmont(list(acc[8 * i:8 * i + 8])) for i in range(4))
+        if ZZ == 0:
+            return None
+        return (X * pow(ZZ, -1, m.P) % m.P, Y * pow(ZZZ, -1, m.P) % m.P)
+
+    for _ in range(25):
+        p1, p2 = o.g1_mul(rng.randrange(1, o.R)), o.g1_mul(rng.randrange(1, o.R))
+        acc = A32(*xyzz(p1, rng.randrange(1, m.P)))
+        assert lib.dfma_xyzz_madd(acc, A16(*(mont(p2[0]) + mont(p2[1]))), one) == 0
+        assert affine_of(acc) == o.g1_add(p1, p2)
+    p1 = o.g1_mul(12345)
+    acc = A32(*([0] * 32))                                            # accumulator at infinity
+    assert lib.dfma_xyzz_madd(acc, A16(*(mont(p1[0]) + mont(p1[1]))), one) == 1 and affine_of(acc) == p1
+    acc = A32(*xyzz(p1, 77))                                          # P + P: reported, left to the doubling path
+    assert lib.dfma_xyzz_madd(acc, A16(*(mont(p1[0]) + mont(p1[1]))), one) == 2
+    n1 = o.g1_neg(p1)
+    assert lib.dfma_xyzz_madd(acc, A16(*(mont(n1[0]) + mont(n1[1]))), one) == 3 and affine_of(acc) is None
+
+
+def test_cuda_header_host_build_matches_model(tmp_path):
+    """tools/probe/fp_dfma.cuh (the header the sm_100a probe kernel is built from) compiled for the host -- fma() under
+    FE_TOWARDZERO standing in for fma.rz.f64 -- gives a b R^-1 mod p limb for limb."""
+    import ctypes
+    lib = _host_lib(tmp_path)
     A = ctypes.c_uint64 * 8
     rng = random.Random(11)
     rinv = pow(m.R, -1, m.P)
