@@ -103,3 +103,22 @@ def test_cuda_header_host_build_matches_model(tmp_path):
         out = A()
         assert lib.dfma_mont_mul(A(*m.to_limbs(a)), A(*m.to_limbs(b)), out) == 0
         assert m.from_limbs(list(out)) == a * b * rinv % m.P
+
+
+def test_radix_2_384_variant_shares_the_library_representation(tmp_path):
+    """mont_mul384 (seven 52-bit reduction steps + one 20-bit step) takes and returns the library's own representation --
+    12 x 32-bit limbs of x 2^384 mod p, re-packed, no conversion product -- and equals a b 2^-384 mod p; model and header agree."""
+    import ctypes
+    lib = _host_lib(tmp_path)
+    A12 = ctypes.c_uint32 * 12
+    rng = random.Random(17)
+    rinv = pow(1 << 384, -1, m.P)
+    u32 = lambda x: [(x >> (32 * i)) & 0xffffffff for i in range(12)]
+    ops = [0, 1, m.P - 1, m.P - 2, 1 << 380, (1 << 381) - 1 - (1 << 200)]
+    ops = [x % m.P for x in ops]
+    for a, b in [(a, b) for a in ops for b in ops] + [(rng.randrange(m.P), rng.randrange(m.P)) for _ in range(600)]:
+        want = a * b * rinv % m.P
+        assert m.from_limbs(m.mont_mul_r384(m.to_limbs(a), m.to_limbs(b))) == want
+        out = A12()
+        assert lib.dfma_mont_mul384_u32(A12(*u32(a)), A12(*u32(b)), out) == 0
+        assert sum(int(v) << (32 * i) for i, v in enumerate(out)) == want

@@ -109,6 +109,54 @@ def mont_mul(a_limbs, b_limbs, stats=None):
     return to_limbs(r)
 
 
+def mont_mul_r384(a_limbs, b_limbs):
+    """a b 2^-384 mod p on the same 52-bit limbs: seven 52-bit reduction steps and one 20-bit step (7 * 52 + 20 = 384), so that the
+    FP64-form field shares its Montgomery radix with the library's 12 x 32-bit form (fp.cuh) and values move between the two
+    by re-packing bits only.  Same limb products, same accumulators; the result is shifted right by 20 bits at the end."""
+    col = [0] * (2 * LIMBS + 1)
+    bias = [0] * (2 * LIMBS + 1)
+
+    def acc(k, a, b, skip_lo=False):
+        h, l = limb_product(a, b)
+        if not skip_lo:
+            col[k] = (col[k] + l) & U64; bias[k] += EXP_LO
+        col[k + 1] = (col[k + 1] + h) & U64; bias[k + 1] += EXP_HI
+        return l & MASK
+
+    for i in range(LIMBS):
+        for j in range(LIMBS):
+            acc(i + j, a_limbs[i], b_limbs[j])
+    carry = 0
+    for k in range(LIMBS):
+        qbits = BITS if k < LIMBS - 1 else 20
+        qmask = (1 << qbits) - 1
+        t = ((col[k] - bias[k]) & U64) + carry
+        assert t < (1 << 64)
+        q = ((t & qmask) * NPRIME) & qmask
+        for j in range(LIMBS):
+            if j == 0:
+                t += acc(k, q, P_LIMBS[0], skip_lo=True)
+            else:
+                acc(k + j, q, P_LIMBS[j])
+        assert t & qmask == 0
+        if k < LIMBS - 1:
+            carry = t >> BITS
+        else:
+            col[k], bias[k], carry = t, 0, 0                     # the last column keeps its upper 32 bits
+    wide, carry = 0, 0
+    for k in range(LIMBS - 1, 2 * LIMBS + 1):
+        t = ((col[k] - bias[k]) & U64) + carry
+        assert t < (1 << 64)
+        wide |= (t & MASK) << (BITS * (k - (LIMBS - 1)))
+        carry = t >> BITS
+    assert carry == 0
+    r = wide >> 20
+    if r >= P:
+        r -= P
+    assert r < P
+    return to_limbs(r)
+
+
 def budget():
     """pipe / issue accounting per product: returns a dict of cycles per SM sub-partition"""
     prods = 2 * LIMBS * LIMBS                                   # a*b and q*p

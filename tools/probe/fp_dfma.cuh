@@ -120,4 +120,85 @@ DF_D void mont_mul(Fp& r, const Fp& a, const Fp& b) {
   for (int k = 0; k < L; k++) r.v[k] = limb_to_double(borrow ? out[k] : d[k]);
 }
 
+// r = a b 2^-384 mod p: the library's Montgomery radix (fp.cuh, 12 x 32-bit limbs), so that a value moves between the two forms
+// by re-packing bits only (from_u32 / to_u32 below).  Seven 52-bit reduction steps and one 20-bit step (7 * 52 + 20 = 384); the
+// columns from the seventh upward are shifted right by 20 bits at the end.  Same 128 limb products as mont_mul.
+DF_D void mont_mul384(Fp& r, const Fp& a, const Fp& b) {
+  uint64_t col[2 * L + 1], bias[2 * L + 1];
+#pragma unroll
+  for (int k = 0; k < 2 * L + 1; k++) { col[k] = 0; bias[k] = 0; }
+#pragma unroll
+  for (int i = 0; i < L; i++) {
+#pragma unroll
+    for (int j = 0; j < L; j++) {
+      uint64_t h, l;
+      limb_product(a.v[i], b.v[j], h, l);
+      col[i + j] += l; bias[i + j] += EXP_LO;
+      col[i + j + 1] += h; bias[i + j + 1] += EXP_HI;
+    }
+  }
+  uint64_t carry = 0;
+#pragma unroll
+  for (int k = 0; k < L; k++) {
+    const uint64_t qmask = k < L - 1 ? MASK : ((1ull << 20) - 1);
+    uint64_t t = col[k] - bias[k] + carry;
+    const uint64_t q = ((t & qmask) * NPRIME) & qmask;
+    const double qd = limb_to_double(q);
+#pragma unroll
+    for (int j = 0; j < L; j++) {
+      uint64_t h, l;
+      limb_product(qd, limb_to_double(p_limb(j)), h, l);
+      if (j == 0) t += l & MASK;
+      else { col[k + j] += l; bias[k + j] += EXP_LO; }
+      col[k + j + 1] += h; bias[k + j + 1] += EXP_HI;
+    }
+    if (k < L - 1) carry = t >> 52;
+    else { col[k] = t; bias[k] = 0; carry = 0; }                 // low 20 bits are zero, the rest belongs to the result
+  }
+  uint64_t w[L + 2];                                             // columns 7 .. 16 as 52-bit limbs
+#pragma unroll
+  for (int k = 0; k < L + 2; k++) {
+    const uint64_t t = col[L - 1 + k] - bias[L - 1 + k] + carry;
+    w[k] = t & MASK;
+    carry = t >> 52;
+  }
+  uint64_t out[L];
+#pragma unroll
+  for (int k = 0; k < L; k++) out[k] = ((w[k] >> 20) | (w[k + 1] << 32)) & MASK;
+  uint64_t d[L];
+  uint64_t borrow = 0;
+#pragma unroll
+  for (int k = 0; k < L; k++) {
+    const uint64_t s = out[k] - p_limb(k) - borrow;
+    d[k] = s & MASK;
+    borrow = (s >> 63) & 1;
+  }
+#pragma unroll
+  for (int k = 0; k < L; k++) r.v[k] = limb_to_double(borrow ? out[k] : d[k]);
+}
+
+// 12 x 32-bit little-endian limbs (the library's Fp<Bls381Fp>::v) <-> 8 x 52-bit double limbs: the same integer, re-packed
+DF_D void from_u32(Fp& r, const uint32_t* v) {
+#pragma unroll
+  for (int i = 0; i < L; i++) {
+    const int bit = 52 * i, w = bit >> 5, sh = bit & 31;
+    uint64_t x = (uint64_t)v[w] >> sh;
+    if (w + 1 < 12) x |= (uint64_t)v[w + 1] << (32 - sh);
+    if (w + 2 < 12 && sh > 12) x |= (uint64_t)v[w + 2] << (64 - sh);
+    r.v[i] = limb_to_double(x & MASK);
+  }
+}
+DF_D void to_u32(uint32_t* v, const Fp& a) {
+  uint64_t x[L];
+#pragma unroll
+  for (int i = 0; i < L; i++) x[i] = bits(a.v[i] + TWO52) & MASK;
+#pragma unroll
+  for (int w = 0; w < 12; w++) {
+    const int bit = 32 * w, i = bit / 52, sh = bit % 52;
+    uint64_t y = x[i] >> sh;
+    if (sh > 20 && i + 1 < L) y |= x[i + 1] << (52 - sh);
+    v[w] = (uint32_t)y;
+  }
+}
+
 }  // namespace dfma

@@ -19,6 +19,15 @@ int dfma_mont_mul(const uint64_t* a, const uint64_t* b, uint64_t* out) {
   store(out, r);
   return 0;
 }
+// library form in and out: 12 x 32-bit limbs of x 2^384 mod p
+int dfma_mont_mul384_u32(const uint32_t* a, const uint32_t* b, uint32_t* out) {
+  Rz rz;
+  dfma::Fp x, y, r;
+  dfma::from_u32(x, a); dfma::from_u32(y, b);
+  dfma::mont_mul384(r, x, y);
+  dfma::to_u32(out, r);
+  return 0;
+}
 int dfma_add_sub(const uint64_t* a, const uint64_t* b, uint64_t* sum, uint64_t* diff) {
   Rz rz;
   dfma::Fp r;
