@@ -122,3 +122,30 @@ def test_radix_2_384_variant_shares_the_library_representation(tmp_path):
         out = A12()
         assert lib.dfma_mont_mul384_u32(A12(*u32(a)), A12(*u32(b)), out) == 0
         assert sum(int(v) << (32 * i) for i, v in enumerate(out)) == want
+
+
+def test_mixed_addition_on_library_values(tmp_path):
+    """xyzz_madd<R384>: accumulator and operand in the LIBRARY's layout (12 x 32-bit limbs, Montgomery radix 2^384, the Xyzz / Affine
+    of kyber_b200/csrc/ec.cuh) go through re-pack -> FP64-form addition -> re-pack and give the oracle's sum: what a warp of the
+    future dual-pipe accumulate kernel does to a bucket."""
+    import ctypes
+    from oracle import bls12381 as o
+    lib = _host_lib(tmp_path)
+    R384 = 1 << 384
+    u32 = lambda x: [(x >> (32 * i)) & 0xffffffff for i in range(12)]
+    mont = lambda x: u32(x * R384 % m.P)
+    val = lambda w: sum(int(v) << (32 * i) for i, v in enumerate(w)) * pow(R384, -1, m.P) % m.P
+    A12, A24, A48 = ctypes.c_uint32 * 12, ctypes.c_uint32 * 24, ctypes.c_uint32 * 48
+    one = A12(*mont(1))
+    rng = random.Random(19)
+    for _ in range(20):
+        p1, p2 = o.g1_mul(rng.randrange(1, o.R)), o.g1_mul(rng.randrange(1, o.R))
+        z = rng.randrange(1, m.P)
+        acc = A48(*(mont(p1[0] * z * z % m.P) + mont(p1[1] * z * z * z % m.P) + mont(z * z % m.P) + mont(z * z * z % m.P)))
+        assert lib.dfma_xyzz_madd384_u32(acc, A24(*(mont(p2[0]) + mont(p2[1]))), one) == 0
+        X, Y, ZZ, ZZZ = (val(acc[12 * i:12 * i + 12]) for i in range(4))
+        assert (X * pow(ZZ, -1, m.P) % m.P, Y * pow(ZZZ, -1, m.P) % m.P) == o.g1_add(p1, p2)
+    acc = A48(*([0] * 48))
+    p1 = o.g1_mul(99)
+    assert lib.dfma_xyzz_madd384_u32(acc, A24(*(mont(p1[0]) + mont(p1[1]))), one) == 1
+    assert (val(acc[0:12]), val(acc[12:24]), val(acc[24:36])) == (p1[0], p1[1], 1)

@@ -54,11 +54,18 @@ struct Xyzz { Fp X, Y, ZZ, ZZZ; };     // x = X / ZZ, y = Y / ZZZ; infinity: ZZ 
 
 // acc += p.  Returns 0 = done, 1 = acc was infinity (acc := p done here), 2 = same point (the caller doubles on the rare path),
 // 3 = opposite points (acc := infinity done here).  Same case analysis as ec.cuh: xyzz_add_mixed.
+// R384 = false: products by mont_mul (radix 2^416); true: mont_mul384 (the library's radix 2^384: operands are re-packed library values)
+template <bool R384 = false>
+DF_D void mul_sel(Fp& r, const Fp& a, const Fp& b) {
+  if (R384) mont_mul384(r, a, b);
+  else mont_mul(r, a, b);
+}
+template <bool R384 = false>
 DF_D int xyzz_madd(Xyzz& acc, const Affine& p, const Fp& one_mont) {
   if (fp_is_zero(acc.ZZ)) { acc.X = p.x; acc.Y = p.y; acc.ZZ = one_mont; acc.ZZZ = one_mont; return 1; }
   Fp U2, S2, P, Rr, PP, PPP, Q, t, X3, Y3;
-  mont_mul(U2, p.x, acc.ZZ);
-  mont_mul(S2, p.y, acc.ZZZ);
+  mul_sel<R384>(U2, p.x, acc.ZZ);
+  mul_sel<R384>(S2, p.y, acc.ZZZ);
   fp_sub(P, U2, acc.X);
   fp_sub(Rr, S2, acc.Y);
   if (fp_is_zero(P)) {
@@ -68,20 +75,20 @@ DF_D int xyzz_madd(Xyzz& acc, const Affine& p, const Fp& one_mont) {
     acc.ZZZ = acc.ZZ;
     return 3;
   }
-  mont_mul(PP, P, P);
-  mont_mul(PPP, P, PP);
-  mont_mul(Q, acc.X, PP);
-  mont_mul(X3, Rr, Rr);
+  mul_sel<R384>(PP, P, P);
+  mul_sel<R384>(PPP, P, PP);
+  mul_sel<R384>(Q, acc.X, PP);
+  mul_sel<R384>(X3, Rr, Rr);
   fp_sub(X3, X3, PPP);
   fp_sub(X3, X3, Q);
   fp_sub(X3, X3, Q);
   fp_sub(t, Q, X3);
-  mont_mul(Y3, Rr, t);
-  mont_mul(t, acc.Y, PPP);
+  mul_sel<R384>(Y3, Rr, t);
+  mul_sel<R384>(t, acc.Y, PPP);
   fp_sub(Y3, Y3, t);
-  mont_mul(t, acc.ZZ, PP);
+  mul_sel<R384>(t, acc.ZZ, PP);
   acc.ZZ = t;
-  mont_mul(t, acc.ZZZ, PPP);
+  mul_sel<R384>(t, acc.ZZZ, PPP);
   acc.ZZZ = t;
   acc.X = X3;
   acc.Y = Y3;

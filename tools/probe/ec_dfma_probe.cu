@@ -11,7 +11,7 @@ __global__ void __launch_bounds__(128, 3) k_dfma_madd_chain(const double* __rest
     dfma::Affine p;
     const double* src = in + dfma::L + ((t * 31 + k) % 4096) * 2 * dfma::L;
     for (int i = 0; i < dfma::L; i++) { p.x.v[i] = src[i]; p.y.v[i] = src[dfma::L + i]; }
-    rare += dfma::xyzz_madd(acc, p, one) == 2;
+    rare += dfma::xyzz_madd<true>(acc, p, one) == 2;
   }
   for (int i = 0; i < dfma::L; i++) out[t * 4 * dfma::L + i] = acc.X.v[i] + acc.Y.v[i] + acc.ZZ.v[i] + acc.ZZZ.v[i] + rare;
 }

@@ -40,8 +40,21 @@ int dfma_xyzz_madd(uint64_t* acc, const uint64_t* p, const uint64_t* one) {
   Rz rz;
   dfma::Xyzz a{load(acc), load(acc + 8), load(acc + 16), load(acc + 24)};
   dfma::Affine q{load(p), load(p + 8)};
-  const int rc = dfma::xyzz_madd(a, q, load(one));
+  const int rc = dfma::xyzz_madd<false>(a, q, load(one));
   store(acc, a.X); store(acc + 8, a.Y); store(acc + 16, a.ZZ); store(acc + 24, a.ZZZ);
+  return rc;
+}
+// the same on LIBRARY values: acc = 4 x 12 u32 limbs (Xyzz<Fp> of ec.cuh, Montgomery radix 2^384), p = 2 x 12, one = 2^384 mod p
+int dfma_xyzz_madd384_u32(uint32_t* acc, const uint32_t* p, const uint32_t* one) {
+  Rz rz;
+  dfma::Xyzz a;
+  dfma::Affine q;
+  dfma::Fp o;
+  dfma::from_u32(a.X, acc); dfma::from_u32(a.Y, acc + 12); dfma::from_u32(a.ZZ, acc + 24); dfma::from_u32(a.ZZZ, acc + 36);
+  dfma::from_u32(q.x, p); dfma::from_u32(q.y, p + 12);
+  dfma::from_u32(o, one);
+  const int rc = dfma::xyzz_madd<true>(a, q, o);
+  dfma::to_u32(acc, a.X); dfma::to_u32(acc + 12, a.Y); dfma::to_u32(acc + 24, a.ZZ); dfma::to_u32(acc + 36, a.ZZZ);
   return rc;
 }
 }
