@@ -149,3 +149,31 @@ def test_mixed_addition_on_library_values(tmp_path):
     p1 = o.g1_mul(99)
     assert lib.dfma_xyzz_madd384_u32(acc, A24(*(mont(p1[0]) + mont(p1[1]))), one) == 1
     assert (val(acc[0:12]), val(acc[12:24]), val(acc[24:36])) == (p1[0], p1[1], 1)
+
+
+def test_fp64_slice_body_in_the_msm_pipeline(tmp_path):
+    """tools/probe/msm_slice_fp64.cuh under host emulation (tests/host_emul/emul_fp64.cpp): the balanced-slice accumulate body on the
+    FP64-form field, for all slices (mode 1) or for alternate groups of slices next to the IMAD-form body (mode 2, what a
+    warp-specialised kernel does), gives the oracle's MSM -- incl. an operand at infinity, the same point three times in one
+    bucket (the doubling path) and P, -P in one bucket."""
+    import ctypes
+    import subprocess
+    from oracle import bls12381 as o
+    so = str(tmp_path / "libemul_fp64.so")
+    subprocess.run(["g++", "-O2", "-frounding-math", "-shared", "-fPIC", "-std=c++17", "-DB2K_HOST_EMUL", "-Wno-unknown-pragmas",
+                    os.path.join(ROOT, "tests", "host_emul", "emul_fp64.cpp"), "-o", so], check=True)
+    lib = ctypes.CDLL(so)
+    rng = random.Random(41)
+    n = 40
+    pts = [o.g1_mul(rng.randrange(1, o.R)) for _ in range(n)]
+    pts[3] = None
+    pts[6] = pts[7] = pts[8]
+    pts[10] = o.g1_neg(pts[11])
+    pb = b"".join(o.g1_to_affine_bytes(p) for p in pts)
+    for ks in ([rng.randrange(o.R) for _ in range(n)], [0x123456789ABCDEF] * n, [rng.randrange(1 << 20) for _ in range(n)]):
+        sb = b"".join(o.scalar_to_bytes(k) for k in ks)
+        want = o.g1_compress(o.g1_msm(ks, pts))
+        for c, mm, L in ((4, 2, 1), (8, 1, 7), (13, 32, 5), (16, 32, 2)):
+            for mode in (0, 1, 2):
+                o48 = ctypes.create_string_buffer(48)
+                assert lib.emul_bls12381_g1_msm_fp64(ctypes.c_size_t(n), sb, pb, c, mm, L, mode, o48) == 0 and o48.raw == want, (c, mm, L, mode)
