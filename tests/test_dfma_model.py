@@ -177,3 +177,38 @@ def test_fp64_slice_body_in_the_msm_pipeline(tmp_path):
             for mode in (0, 1, 2):
                 o48 = ctypes.create_string_buffer(48)
                 assert lib.emul_bls12381_g1_msm_fp64(ctypes.c_size_t(n), sb, pb, c, mm, L, mode, o48) == 0 and o48.raw == want, (c, mm, L, mode)
+
+
+def test_library_ec_templates_instantiate_on_the_fp64_field(tmp_path):
+    """tools/probe/fpd_overloads.cuh puts the FP64-form field behind the library's generic field interface (f_mul, f_sub ...), so the
+    EC templates of kyber_b200/csrc/ec.cuh -- xyzz_madd with both signs, xyzz_add, xyzz_dbl -- and the inversion instantiate on it
+    unchanged; every result must equal, limb for limb after re-packing, the 12 x 32-bit instantiation (host emulation), incl. the
+    accumulator or the operand at infinity, equal points and opposite points."""
+    import ctypes
+    import subprocess
+    from oracle import bls12381 as o
+    so = str(tmp_path / "libemul_fpd.so")
+    subprocess.run(["g++", "-O2", "-frounding-math", "-shared", "-fPIC", "-std=c++17", "-DB2K_HOST_EMUL", "-Wno-unknown-pragmas",
+                    os.path.join(ROOT, "tests", "host_emul", "emul_fpd.cpp"), "-o", so], check=True)
+    lib = ctypes.CDLL(so)
+    P, R384 = o.P, 1 << 384
+    u32 = lambda x: [(x >> (32 * i)) & 0xffffffff for i in range(12)]
+    mont = lambda x: u32(x * R384 % P)
+    A24, A48 = ctypes.c_uint32 * 24, ctypes.c_uint32 * 48
+
+    def xyzz(pt, z):
+        if pt is None:
+            return mont(1) + mont(1) + [0] * 24
+        return mont(pt[0] * z * z % P) + mont(pt[1] * z ** 3 % P) + mont(z * z % P) + mont(z ** 3 % P)
+
+    rng = random.Random(5)
+    for k in range(30):
+        p1, p2, p3 = (o.g1_mul(rng.randrange(1, o.R)) for _ in range(3))
+        if k == 1: p2 = p1
+        if k == 2: p2 = o.g1_neg(p1)
+        if k == 3: p1 = None
+        if k == 4: p2 = None
+        if k == 5: p3 = p1
+        q = [0] * 24 if p2 is None else mont(p2[0]) + mont(p2[1])
+        rc = lib.emul_fpd_ec_agree(A48(*xyzz(p1, rng.randrange(1, P))), A24(*q), A48(*xyzz(p3, rng.randrange(1, P))))
+        assert rc == 0, (k, rc)
