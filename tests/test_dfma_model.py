@@ -212,3 +212,33 @@ def test_library_ec_templates_instantiate_on_the_fp64_field(tmp_path):
         q = [0] * 24 if p2 is None else mont(p2[0]) + mont(p2[1])
         rc = lib.emul_fpd_ec_agree(A48(*xyzz(p1, rng.randrange(1, P))), A24(*q), A48(*xyzz(p3, rng.randrange(1, P))))
         assert rc == 0, (k, rc)
+
+
+def test_pair_tree_rounds_instantiate_on_the_fp64_field(tmp_path):
+    """The affine pair-tree rounds of the accumulate pass (kyber_b200/csrc/msm_affine.cuh: msm_pairtree_forward / invert / backward,
+    UNCHANGED templates) instantiated on the FP64-form field through tools/probe/fpd_overloads.cuh, followed by the library's XYZZ
+    slices, give the oracle's MSM -- same exceptional inputs as the IMAD-form test (operand at infinity, one point four times,
+    P and -P, points with x = 0, all-equal and short scalars)."""
+    import ctypes
+    import subprocess
+    from oracle import bls12381 as o
+    so = str(tmp_path / "libemul_fp64b.so")
+    subprocess.run(["g++", "-O2", "-frounding-math", "-shared", "-fPIC", "-std=c++17", "-DB2K_HOST_EMUL", "-Wno-unknown-pragmas",
+                    os.path.join(ROOT, "tests", "host_emul", "emul_fp64.cpp"), "-o", so], check=True)
+    lib = ctypes.CDLL(so)
+    rng = random.Random(11)
+    n = 48
+    pts = [o.g1_mul(rng.randrange(1, o.R)) for _ in range(n)]
+    pts[5] = None
+    pts[6] = pts[7] = pts[8] = pts[9]
+    pts[10] = o.g1_neg(pts[11])
+    pts[13] = (0, 2)
+    pts[14] = (0, o.P - 2)
+    pb = b"".join(o.g1_to_affine_bytes(p) for p in pts)
+    for ks in ([rng.randrange(o.R) for _ in range(n)], [0x123456789ABCDEF] * n, [rng.randrange(1 << 9) for _ in range(n)]):
+        sb = b"".join(o.scalar_to_bytes(k) for k in ks)
+        want = o.g1_compress(o.g1_msm(ks, pts))
+        for c, mm, L, rounds, pbatch in ((4, 2, 3, 1, 3), (4, 2, 2, 2, 9), (5, 4, 4, 3, 24), (8, 8, 5, 6, 64), (3, 2, 1, 9, 5)):
+            o48 = ctypes.create_string_buffer(48)
+            rc = lib.emul_bls12381_g1_msm_rounds_fp64(ctypes.c_size_t(n), sb, pb, c, mm, L, rounds, pbatch, o48)
+            assert rc == 0 and o48.raw == want, (c, mm, L, rounds, pbatch)

@@ -5,6 +5,7 @@
 #pragma once
 #include "../../kyber_b200/csrc/tower.cuh"
 #include "../../kyber_b200/csrc/ec.cuh"
+#include "../../kyber_b200/csrc/fp_inv.cuh"
 #include "ec_dfma.cuh"
 
 namespace b2k {
@@ -39,11 +40,15 @@ B2K_D bool f_eq(const FpD& a, const FpD& b) {
   return e;
 }
 B2K_D void f_set_one(FpD& r) { b2k::Fp<b2k::Bls381Fp> o; b2k::fp_set_one(o); fpd_load(r, o); }
+B2K_D void f_inv_bg(FpD& r, const FpD& a) { b2k::Fp<b2k::Bls381Fp> t, u; fpd_store(t, a); b2k::fp_inv_bingcd(u, t); fpd_load(r, u); }
 B2K_D void f_inv(FpD& r, const FpD& a) { b2k::Fp<b2k::Bls381Fp> t, u; fpd_store(t, a); b2k::fp_inv(u, t); fpd_load(r, u); }
 
 }  // namespace dfma
 
 namespace b2k {
+
+// the curve tag the MSM templates (msm_affine.cuh: pair-tree rounds) need: only the field type
+struct Bls381G1D { using F = FpD; };
 
 template <class T> struct FpdConv;
 template <> struct FpdConv<Affine<FpD>> {
