@@ -5,6 +5,7 @@
 #include "../../kyber_b200/csrc/constants.cuh"
 #include "../../kyber_b200/csrc/fp.cuh"
 #include "../../tools/probe/fpd_overloads.cuh"
+#include "../../tools/probe/msm_slice_fp64.cuh"
 using namespace b2k;
 using F = Fp<Bls381Fp>;
 
@@ -34,6 +35,16 @@ extern "C" int emul_fpd_ec_agree(const uint32_t* acc, const uint32_t* q, const u
   }
   { Xyzz<F> w; Xyzz<FpD> wd; Xyzz<F> back; xyzz_add(w, a, b); xyzz_add(wd, ad, bd); FpdConv<Xyzz<FpD>>::store(back, wd); if (!same(w, back)) bad |= 4; }
   { Xyzz<F> w; Xyzz<FpD> wd; Xyzz<F> back; xyzz_dbl(w, a); xyzz_dbl(wd, ad); FpdConv<Xyzz<FpD>>::store(back, wd); if (!same(w, back)) bad |= 8; }
+  for (int neg = 0; neg < 2; neg++) {      // the hand-ordered FP64-form addition of ec_dfma.cuh (what dual_pipe_probe.cu compares by memcmp)
+    Xyzz<F> w, back;
+    xyzz_madd(w, a, p, neg != 0);
+    dfma::Xyzz acc;
+    if (xyzz_is_inf(a)) fp64_set_inf(acc); else fp64_load_xyzz(acc, a);
+    dfma::Fp one; { F o; f_set_one(o); dfma::from_u32(one, o.v); }
+    fp64_madd(acc, p, neg != 0, one);
+    fp64_store_xyzz(back, acc);
+    if (!same(w, back)) bad |= 32 << neg;
+  }
   { F i1, i2; FpD id; fp_inv(i1, a.ZZ); f_inv(id, ad.ZZ); fpd_store(i2, id); if (!fp_eq(i1, i2)) bad |= 16; }
   std::fesetround(old);
   return bad;
