@@ -24,6 +24,8 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# several contexts per rank, each with device-side waits on flags other streams / ranks set: one hardware queue per stream
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 METRIC = "bls12381_g1_scalar_muls_per_sec"
 UNIT = "scalar-muls/s"
@@ -291,8 +293,7 @@ def run_reference_arm(args):
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    from kyber_b200 import Engine, workload as wl
-    from kyber_b200.multi import msm_sharded, msm_bucket_exchange
+    from kyber_b200 import Comm, Engine, workload as wl
     from oracle import bls12381 as o
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -308,7 +309,9 @@ def run_ours(args):
             os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the one JSON line (NCCL prints its version banner there)
         dist.init_process_group("nccl", device_id=dev)
 
-    n = 1 << LOG_N
+    # BASELINE.json configs[4] (C5) is 2^24 pairs over 8 GPUs = 2^21 per GPU; configs[1] (C2) is 2^20 on one GPU (also used at 2 and 4)
+    log_n = LOG_N if "B2K_BENCH_LOGN" in os.environ else (21 if world == 8 else 20)
+    n = 1 << log_n
     eng = Engine(local)
     stream = torch.cuda.current_stream()
     eng.set_stream(stream.cuda_stream)
@@ -330,9 +333,6 @@ def run_ours(args):
     for i in (0, n // 3, n - 1):
         assert bytes(h_pts[96 * i:96 * i + 96].tolist()) == o.g1_to_affine_bytes(o.g1_mul(a[i])), "bad input point"
     d_scal = h_scal.to(dev)
-    d_out = torch.zeros(96, dtype=torch.uint8, device=dev)
-    d_ones = torch.frombuffer(bytearray(b"".join((1).to_bytes(32, "big") for _ in range(world))),
-                              dtype=torch.uint8).to(dev)
     d_final = torch.zeros(64, dtype=torch.uint8, device=dev)
     my_dot = wl.dot_mod(s, a, o.R)
 
@@ -346,57 +346,59 @@ def run_ours(args):
         e2.set_stream(st.cuda_stream)
         engines.append(e2)
     finals = [d_final] + [torch.zeros(64, dtype=torch.uint8, device=dev) for _ in range(NC - 1)]
-    partials = [d_out] + [torch.zeros(96, dtype=torch.uint8, device=dev) for _ in range(NC - 1)]
 
-    # multi-GPU shape 1 (partial-bucket exchange, kyber_b200/multi.py): per-context exchange buffers
+    # ---- multi-GPU: the sharded MSM lives in the library (include/b2kyber.h: b2k_comm_*, b2k_bls12381_g1_msm_sharded_*).
+    # One communicator per in-flight context; "peer" = slabs mapped with CUDA IPC, the fused reduction pulls the partial buckets
+    # over NVLink; "nccl" = the same exchange through ncclSend/ncclRecv + ncclAllGather issued by the library.
+    comms = {"peer": [], "nccl": []}
     xplan = eng.bls12381_g1_msm_bucket_plan(n)
     XC, XW, XNB, XEB = xplan["c"], xplan["W"], xplan["buckets_per_window"], xplan["bucket_bytes"]
     can_exchange = world > 1 and XW % world == 0
-    use_buckets = can_exchange and args.exchange == "buckets"
-    if can_exchange:
-        xbuckets = [torch.empty(XW * XNB * XEB, dtype=torch.uint8, device=dev) for _ in range(NC)]
-        xwsum = [torch.empty((XW // world) * XEB, dtype=torch.uint8, device=dev) for _ in range(NC)]
-
-    def step_device_buckets(k: int = 0):
-        """the same sharded MSM through the partial-bucket exchange: buckets -> ncclAllToAll -> fused add + reduce of the
-        windows this rank owns -> ncclAllGather of the window sums -> Horner"""
-        e, fin, xb, xw = engines[k % NC], finals[k % NC], xbuckets[k % NC], xwsum[k % NC]
-        with torch.cuda.stream(streams[k % NC]):
-            def local_buckets():
-                e.bls12381_g1_msm_buckets_dev(n, d_scal.data_ptr(), d_pts.data_ptr(), xb.data_ptr(), xb.numel())
-                return xb
-
-            def reduce_windows(recv, parts, w_cnt):
-                e.bls12381_g1_msm_reduce_windows_dev(XC, w_cnt, parts, recv.data_ptr(), xw.data_ptr())
-                return xw
-
-            def finish(allws):
-                e.bls12381_g1_msm_finish_dev(XC, XW, allws.data_ptr(), fin.data_ptr())
-                return fin
-            msm_bucket_exchange(local_buckets, reduce_windows, finish, XW, XNB, XEB)
+    if world > 1:
+        for e in engines:
+            c = Comm(e, world, rank)
+            blobs = [None] * world
+            dist.all_gather_object(blobs, c.export())
+            c.connect(b"".join(blobs))
+            comms["peer"].append(c)
+        if can_exchange and not os.environ.get("B2K_SKIP_NCCL"):
+            for e in engines:
+                c = Comm(e, world, rank)
+                ids = [Comm.nccl_unique_id(e.lib) if rank == 0 else None]
+                dist.broadcast_object_list(ids, src=0)
+                c.use_nccl(ids[0])
+                comms["nccl"].append(c)
+    # headline shape of the multi-GPU step: the partial-bucket exchange north_star names, on the peer transport
+    mode = {"shape": 0 if (can_exchange and args.exchange == "buckets") else 1, "transport": "peer"}
 
     def step_device(k: int = 0):
         """one pass of the hot path, inputs resident in HBM, issued on context k % NC"""
-        if use_buckets:
-            return step_device_buckets(k)
-        e, fin, part = engines[k % NC], finals[k % NC], partials[k % NC]
-        with torch.cuda.stream(streams[k % NC]):
-            if world == 1:
-                e.call_dev("b2k_bls12381_g1_msm_dev", n, d_scal.data_ptr(), d_pts.data_ptr(), fin.data_ptr())
-            else:
-                def local_partial():
-                    e.call_dev("b2k_bls12381_g1_msm_affine_dev", n, d_scal.data_ptr(), d_pts.data_ptr(), part.data_ptr())
-                    return part
-
-                def combine(gathered, w):                          # add the partials: MSM with unit scalars
-                    e.call_dev("b2k_bls12381_g1_msm_dev", w, d_ones.data_ptr(), gathered.data_ptr(), fin.data_ptr())
-                    return fin
-                msm_sharded(local_partial, combine)                # the ONE exchange: ncclAllGather of world x 96 B
+        j = k % NC
+        if world == 1:
+            engines[j].call_dev("b2k_bls12381_g1_msm_dev", n, d_scal.data_ptr(), d_pts.data_ptr(), finals[j].data_ptr())
+        else:
+            comms[mode["transport"]][j].msm_sharded_dev(n, d_scal.data_ptr(), d_pts.data_ptr(), finals[j].data_ptr(), mode["shape"])
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def timed(steps: int, warm: int):
+        """device time of `steps` steps issued round-robin on the NC contexts (max over the contexts' end events)"""
+        for k in range(warm * NC):
+            step_device(k)
+        barrier()
+        ev0 = torch.cuda.Event(enable_timing=True)
+        ends = [torch.cuda.Event(enable_timing=True) for _ in range(NC)]
+        barrier()
+        ev0.record(stream)                   # every stream is idle here (barrier above)
+        for k in range(steps):
+            step_device(k)
+        for st, ev in zip(streams, ends):
+            ev.record(st)
+        barrier()
+        return max(ev0.elapsed_time(ev) for ev in ends)
 
     # ---- device-resident timing --------------------------------------------------------------------
     for k in range(max(args.warmup, 3) * NC):
@@ -407,177 +409,193 @@ def run_ours(args):
         sampler.start()
         time.sleep(0.25)
     launches0 = sum(e.launch_count() for e in engines)
-    ev0 = torch.cuda.Event(enable_timing=True)
-    ends = [torch.cuda.Event(enable_timing=True) for _ in range(NC)]
     acc_ms = []
-    barrier()
-    ev0.record(stream)                       # every stream is idle here (barrier above)
-    for k in range(args.steps):
-        step_device(k)
-    for st, ev in zip(streams, ends):
-        ev.record(st)
-    barrier()
-    dev_ms = max(ev0.elapsed_time(ev) for ev in ends)
+    dev_ms = timed(args.steps, 0)
     launches = sum(e.launch_count() for e in engines) - launches0
-    # the other exchange shape, timed the same way (both are reported; --exchange picks the headline one)
-    alt_ms = None
-    if can_exchange:
-        alt = step_device if use_buckets else step_device_buckets
-        if use_buckets:
-            use_buckets = False                                   # step_device now runs the result exchange
-        for k in range(3 * NC):
-            alt(k)
-        barrier()
-        ev_x = torch.cuda.Event(enable_timing=True)
-        ends_x = [torch.cuda.Event(enable_timing=True) for _ in range(NC)]
-        ev_x.record(stream)
-        for k in range(args.steps):
-            alt(k)
-        for st, ev in zip(streams, ends_x):
-            ev.record(st)
-        barrier()
-        alt_ms = max(ev_x.elapsed_time(ev) for ev in ends_x) / args.steps
-        alt_got = bytes(finals[(args.steps - 1) % NC][:48].cpu().tolist())
-        use_buckets = can_exchange and args.exchange == "buckets"
+    head_got = bytes(finals[(args.steps - 1) % NC][:48].cpu().tolist())
+    # the other exchange shapes / transports, timed the same way (all reported; --exchange picks the headline one)
+    alts = {}
+    if world > 1:
+        variants = [("result_exchange_peer", 1, "peer")]
+        if can_exchange:
+            variants.append(("bucket_exchange_peer", 0, "peer"))
+            if comms["nccl"]:
+                variants.append(("bucket_exchange_nccl", 0, "nccl"))
+        head = dict(mode)
+        for name, shape, transport in variants:
+            if shape == head["shape"] and transport == head["transport"]:
+                alts[name] = (dev_ms / args.steps, head_got)
+                continue
+            mode.update(shape=shape, transport=transport)
+            ms = timed(args.steps, 3) / args.steps
+            alts[name] = (ms, bytes(finals[(args.steps - 1) % NC][:48].cpu().tolist()))
+        mode.update(head)
     # the same K steps on ONE context (no overlap): single-MSM latency
     ev_a, ev_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
     ev_a.record(stream)
     for _ in range(min(args.steps, 5)):
         step_device(0)
     ev_b.record(stream)
     barrier()
     serial_ms = ev_a.elapsed_time(ev_b) / min(args.steps, 5)
-    # stage timings of the last MSM (CUDA events recorded on the same stream inside the library)
+    # stage timings of the last local MSM (CUDA events recorded on the same stream inside the library)
     for _ in range(3):
         eng.call_dev("b2k_bls12381_g1_msm_dev", n, d_scal.data_ptr(), d_pts.data_ptr(), d_final.data_ptr())
         acc_ms.append(eng.last_timings())
     barrier()
+    # a sustained run (seconds, not a burst): the same step for >= 3 s, its own clock sample
+    sustained = None
+    if world == 1 and not os.environ.get("B2K_SKIP_SUSTAINED"):
+        est = dev_ms / args.steps
+        ks = max(args.steps, int(3000.0 / est) + 1)
+        samp2 = ClockSampler(local)
+        samp2.start()
+        time.sleep(0.2)
+        sus_ms = timed(ks, 0)
+        sustained = {"value": n * ks / (sus_ms * 1e-3), "unit": UNIT, "steps": ks, "seconds": sus_ms * 1e-3,
+                     "ms_per_step": sus_ms / ks, "clocks": samp2.finish()}
     # ---- end-to-end through the host C ABI (pinned host buffers) -----------------------------------
     hs_ptr, hp_ptr = h_scal.data_ptr(), h_pts.data_ptr()
-    h_res = torch.zeros(64, dtype=torch.uint8).pin_memory()
+    h_results = [torch.zeros(64, dtype=torch.uint8).pin_memory() for _ in range(NC)]
+    h_res = h_results[0]
+    e2e_comms = comms["peer"] if (world > 1 and can_exchange) else None
 
-    h_results = [h_res] + [torch.zeros(64, dtype=torch.uint8).pin_memory() for _ in range(NC - 1)]
+    def e2e_submit(k: int, NE: int):
+        j = k % NE
+        e = engines[j]
+        if world == 1:
+            e._check(e.lib.b2k_bls12381_g1_msm_async(e.h, n, ctypes.c_void_p(hs_ptr), ctypes.c_void_p(hp_ptr),
+                                                     ctypes.c_void_p(h_results[j].data_ptr())))
+        else:                                    # the SHARDED MSM from host buffers: H2D of the shard, buckets, exchange, sum, D2H
+            e2e_comms[j].msm_sharded_async(n, hs_ptr, hp_ptr, h_results[j].data_ptr())
 
-    def step_e2e(k: int = 0):
-        e = engines[k % NC]
-        e._check(e.lib.b2k_bls12381_g1_msm(e.h, n, ctypes.c_void_p(hs_ptr), ctypes.c_void_p(hp_ptr),
-                                           ctypes.c_void_p(h_results[k % NC].data_ptr())))
-
-    for _ in range(2):
-        step_e2e()
-    barrier()
-    # (a) one caller, blocking calls back to back: what a strictly synchronous user of the C ABI sees
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for _ in range(min(args.steps, 5)):
-        step_e2e()
-    e1.record(stream)
-    barrier()
-    e2e_blocking_ms = e0.elapsed_time(e1) / min(args.steps, 5)
-    # (b) the asynchronous entry point on NE contexts used in turn by ONE host thread: submit step k on context k % NE
-    #     (H2D of scalars+points, MSM, D2H of the result, all enqueued), collect step k-NE first.  The copies of one step run
-    #     under the kernels of the other.  Every step still moves its 128 MiB host->device and its result device->host
-    #     inside the timed region.  Timed on the device: start event at the head of context 0's stream, end events behind
-    #     the last enqueued work of each context.
-    NE = max(1, min(int(os.environ.get("B2K_E2E_INFLIGHT", str(NC))), NC))
     e2e_status = []
 
-    def e2e_submit(k: int):
-        e = engines[k % NE]
-        e._check(e.lib.b2k_bls12381_g1_msm_async(e.h, n, ctypes.c_void_p(hs_ptr), ctypes.c_void_p(hp_ptr),
-                                                 ctypes.c_void_p(h_results[k % NE].data_ptr())))
-
-    def e2e_collect(k: int):
+    def e2e_collect(k: int, NE: int):
         e = engines[k % NE]
         e._check(e.lib.b2k_wait(e.h))
         e2e_status.append(bytes(h_results[k % NE][:48].tolist()))
 
-    for k in range(2 * NE):
-        e2e_submit(k)
-        e2e_collect(k)
-    barrier()
-    ev_start = torch.cuda.Event(enable_timing=True)
-    ev_ends = [torch.cuda.Event(enable_timing=True) for _ in range(NE)]
-    ev_start.record(streams[0])
-    for k in range(args.steps):
-        if k >= NE:
-            e2e_collect(k - NE)
-        e2e_submit(k)
-    for j in range(NE):
-        ev_ends[j].record(streams[j])
-    for k in range(max(0, args.steps - NE), args.steps):
-        e2e_collect(k)
-    barrier()
-    e2e_ms = max(ev_start.elapsed_time(ev) for ev in ev_ends)
+    have_e2e = world == 1 or e2e_comms is not None
+    e2e_ms = e2e_blocking_ms = 0.0
+    NE = max(1, min(int(os.environ.get("B2K_E2E_INFLIGHT", str(NC))), NC))
+    if have_e2e:
+        for _ in range(2):
+            e2e_submit(0, 1); e2e_collect(0, 1)
+        barrier()
+        # (a) one caller, blocking back to back: what a strictly synchronous user of the C ABI sees
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(min(args.steps, 5)):
+            e2e_submit(0, 1); e2e_collect(0, 1)
+        e1.record(stream)
+        barrier()
+        e2e_blocking_ms = e0.elapsed_time(e1) / min(args.steps, 5)
+        # (b) the asynchronous entry point on NE contexts used in turn by ONE host thread: submit step k on context k % NE (H2D of
+        #     scalars+points, MSM [+ exchange], D2H of the result, all enqueued), collect step k-NE first.  Every step still moves
+        #     its inputs host->device and its result device->host inside the timed region.  Timed on the device.
+        for _ in range(2):
+            for k in range(NE):
+                e2e_submit(k, NE)
+            for k in range(NE):
+                e2e_collect(k, NE)
+        barrier()
+        del e2e_status[:]
+        ev_start = torch.cuda.Event(enable_timing=True)
+        ev_ends = [torch.cuda.Event(enable_timing=True) for _ in range(NE)]
+        ev_start.record(streams[0])
+        for k in range(args.steps):
+            if k >= NE:
+                e2e_collect(k - NE, NE)
+            e2e_submit(k, NE)
+        for j in range(NE):
+            ev_ends[j].record(streams[j])
+        for k in range(max(0, args.steps - NE), args.steps):
+            e2e_collect(k, NE)
+        barrier()
+        e2e_ms = max(ev_start.elapsed_time(ev) for ev in ev_ends)
     clocks = sampler.finish() if rank == 0 else None
 
     # ---- correctness of what was timed ---------------------------------------------------------------
-    want_e2e = o.g1_compress(o.g1_mul(my_dot))
-    assert bytes(h_res[:48].tolist()) == want_e2e, "e2e MSM result differs from the oracle"
-    assert e2e_status and all(x == want_e2e for x in e2e_status), "an asynchronous e2e step returned a wrong result"
-    step_device()
-    barrier()
-    got = bytes(d_final[:48].cpu().tolist())
     if world > 1:
         dots = [None] * world
         dist.all_gather_object(dots, my_dot)
         total_dot = sum(dots) % o.R
     else:
         total_dot = my_dot
-    assert got == o.g1_compress(o.g1_mul(total_dot)), "device MSM result differs from the oracle"
-    if alt_ms is not None:
-        assert alt_got == got, "the two multi-GPU exchange shapes disagree"
+    want = o.g1_compress(o.g1_mul(total_dot))
+    assert head_got == want, "device MSM result differs from the oracle"
+    if have_e2e:
+        assert bytes(h_res[:48].tolist()) == want, "e2e MSM result differs from the oracle"
+        assert e2e_status and all(x == want for x in e2e_status), "an asynchronous e2e step returned a wrong result"
+    for name, (_, got_alt) in alts.items():
+        assert got_alt == want, f"multi-GPU variant {name} disagrees with the oracle"
 
     # ---- max over ranks ---------------------------------------------------------------------------------
-    t = torch.tensor([dev_ms, e2e_ms, alt_ms or 0.0], dtype=torch.float64, device=dev)
+    names = sorted(alts)
+    t = torch.tensor([dev_ms, e2e_ms, e2e_blocking_ms, serial_ms] + [alts[k][0] for k in names], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_ms = float(t[0]), float(t[1])
-    alt_ms = float(t[2]) if alt_ms is not None else None
+    dev_ms, e2e_ms, e2e_blocking_ms, serial_ms = (float(t[i]) for i in range(4))
+    alt_ms = {k: float(t[4 + i]) for i, k in enumerate(names)}
 
     if rank == 0:
         ms_step = dev_ms / args.steps
         value = world * n / (ms_step * 1e-3)
-        e2e_value = world * n / (e2e_ms / args.steps * 1e-3)
         tm = [sum(x[i] for x in acc_ms) / len(acc_ms) for i in range(len(acc_ms[0]))]
         plan = eng.last_msm_plan()                                         # what the timed MSMs actually ran with
         c_bits = plan["c"]
         peak, peak_src = load_peaks()
+        cfg_name = ("BASELINE.json configs[4] (C5): 2^24 pairs sharded over 8 GPUs" if (world == 8 and log_n == 21) else
+                    "BASELINE.json configs[1] (C2)" + (" per GPU" if world > 1 else ""))
+        if world == 1:
+            xdesc = "none"
+        elif mode["shape"] == 0:
+            xdesc = (f"partial buckets ({XW * XNB * XEB} B per rank) left in the rank's exchange slab; rank g's fused add+reduce kernel PULLS "
+                     f"windows [g W/G, (g+1) W/G) of every rank over NVLink (CUDA-IPC-mapped peer memory, device-side flag words), pushes "
+                     f"{XW // world} window sums to every peer, Horner on every rank; no host-issued collective")
+        else:
+            xdesc = "every rank finishes its MSM, pushes its 96-byte result into every peer's slab, adds the N results"
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-                "config": {"workload": f"BLS12-381 G1 MSM, 2^{LOG_N} random (scalar,point) pairs per GPU "
-                                       "(BASELINE.json configs[1]); seed b2k/c2",
-                           "pairs_per_gpu": n, "parallelism": f"shard{world}" if world > 1 else "single",
+                "config": {"workload": f"BLS12-381 G1 MSM, 2^{log_n} random (scalar,point) pairs per GPU ({cfg_name}); seed b2k/c2",
+                           "pairs_per_gpu": n, "pairs_total": n * world,
+                           "parallelism": f"shard{world}" if world > 1 else "single",
                            "l2": "no flush: each step streams >400 MB (128 MiB inputs + sort + buckets) > 126 MB L2",
-                           "exchange": ("none" if world == 1 else
-                                        f"partial buckets: ncclAllToAll of {XW * XNB * XEB} B/rank + fused add/reduce + ncclAllGather of "
-                                        f"{XW * XEB} B + Horner" if use_buckets else "1 x ncclAllGather of 96 B/rank + add"),
+                           "exchange": xdesc,
                            "steps_in_flight": NC,
                            "overlap": f"{NC} independent steps in flight on {NC} contexts/streams; "
                                       "single_step_latency_ms is one step alone"},
                 "single_step_latency_ms": serial_ms,
-                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * 128, "d2h_bytes_per_step": 52,
-                        "ms_per_step": e2e_ms / args.steps, "callers": 1, "steps_in_flight": NE,
-                        "blocking_ms_per_step": e2e_blocking_ms,
-                        "note": f"b2k_bls12381_g1_msm_async + b2k_wait on {NE} contexts used in turn by one host thread "
-                                "(pinned host buffers; H2D of all inputs and D2H of the result inside the timed region every "
-                                "step; per-rank local MSM); blocking_ms_per_step = the blocking b2k_bls12381_g1_msm back to back"},
                 "gpu_launches": int(launches),
                 "clocks": clocks,
                 "stages_ms": dict(zip(["load", "digits_hist", "scan", "scatter", "accumulate", "reduce_chunks",
                                        "window_sum", "final", "pipeline", "fixup", "accumulate_affine_rounds"],
                                       [round(x, 4) for x in tm])),
                 "msm_plan": plan}
-        if alt_ms is not None:
-            shapes = {"result_exchange_ms_per_step": alt_ms if use_buckets else ms_step,
-                      "bucket_exchange_ms_per_step": ms_step if use_buckets else alt_ms,
-                      "bucket_exchange_bytes_per_rank": XW * XNB * XEB * (world - 1) // world,
-                      "headline": args.exchange,
-                      "note": "same sharded MSM, same bytes out; result = every rank finishes its MSM, ncclAllGather of 96 B, add; "
-                              "buckets = ncclAllToAll of the partial buckets (raw limbs), bucket-wise EC add fused into the reduction of the "
-                              "W/G windows a rank owns, ncclAllGather of the window sums, Horner (north_star's shape)"}
-            line["multi_gpu_exchange"] = shapes
+        if have_e2e:
+            e2e_value = world * n / (e2e_ms / args.steps * 1e-3)
+            line["e2e"] = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * 128, "d2h_bytes_per_step": 52,
+                           "ms_per_step": e2e_ms / args.steps, "callers": 1, "steps_in_flight": NE,
+                           "blocking_ms_per_step": e2e_blocking_ms,
+                           "note": ("b2k_bls12381_g1_msm_async + b2k_wait" if world == 1 else
+                                    "b2k_bls12381_g1_msm_sharded_async + b2k_wait (the SHARDED MSM: H2D of the rank's shard, partial buckets, "
+                                    "the exchange over peer memory, the sum of all ranks, D2H on every rank)") +
+                                   f" on {NE} contexts used in turn by one host thread per rank (pinned host buffers; H2D of all inputs and "
+                                   "D2H of the result inside the timed region every step; h2d/d2h bytes are per rank); "
+                                   "blocking_ms_per_step = submit + wait back to back on one context"}
+        if sustained:
+            line["sustained"] = sustained
+        if world > 1:
+            line["multi_gpu_exchange"] = {
+                "ms_per_step": alt_ms, "headline": ("bucket_exchange_peer" if mode["shape"] == 0 else "result_exchange_peer"),
+                "bucket_exchange_bytes_pulled_per_rank": XW * XNB * XEB * (world - 1) // world if can_exchange else None,
+                "note": "same sharded MSM, same bytes out, all inside the library (b2k_bls12381_g1_msm_sharded_dev): *_peer = exchange slabs mapped "
+                        "with CUDA IPC, device-side flags, the fused add+reduce kernel reads the peers' buckets over NVLink; bucket_exchange_nccl = "
+                        "the same exchange as grouped ncclSend/ncclRecv (all-to-all) + ncclAllGather issued by the library (libnccl.so.2 via dlopen); "
+                        "result_exchange = every rank finishes its own MSM and the 96-byte results travel"}
         if c_bits:
             nv = n * (2 if plan["glv"] else 1)                            # pairs after the endomorphism split
             adds = nv * plan["W"]                                         # bucket additions (16 per input pair at c = 16)
@@ -589,12 +607,12 @@ def run_ours(args):
             products = (adds - left) * 6 + left * 10                      # affine addition 6, mixed XYZZ addition 10 field products
             traffic = None
             tp = os.path.join(ROOT, "profiles", "accumulate_traffic.json")
-            if os.path.exists(tp):
+            if os.path.exists(tp) and log_n == 20:
                 try:
                     traffic = json.load(open(tp)).get("dram_bytes_per_launch")
                 except Exception:
                     traffic = None
-            kern = (f"bucket-accumulate pass: k_msm_pairtree_round x{R} (batched affine additions) + k_msm_accumulate_slices_direct"
+            kern = (f"bucket-accumulate pass: k_pt_forward/k_pt_invert/k_pt_backward x{R} (batched affine additions) + k_msm_accumulate_slices_direct"
                     if R else "k_msm_accumulate_slices")
             line["roofline"] = {"bound": "hbm", "kernel": kern, "achieved": alg_bytes / acc / 1e9,
                                 "peak": peak, "unit": "GB/s", "frac": alg_bytes / acc / 1e9 / peak,
@@ -602,10 +620,8 @@ def run_ours(args):
                                 "algorithmic_bytes": alg_bytes, "kernel_ms": tm[4], "window_bits": c_bits,
                                 "affine_rounds_ms": tm[10] if len(tm) > 10 else None,
                                 "note": "integer-ALU bound pass (SURVEY.md F9): see `integer_roofline` and DESIGN.md section 4; "
-                                        "`traffic` is the ncu DRAM bytes of the whole pass (all its launches) for one MSM: with the affine rounds on it is "
-                                        "~6x the algorithmic bytes by design (every round streams its operands twice and writes the halved "
-                                        "list: idle DRAM bandwidth traded for field products, the real bottleneck); with the rounds off the "
-                                        "single XYZZ kernel moves ~the algorithmic bytes once",
+                                        "`traffic` is the ncu DRAM bytes of the whole pass (all its launches) for one 2^20 MSM "
+                                        "(profiles/accumulate_traffic.json, captured with the same kernels)",
                                 "integer_roofline": {
                                     "bound": "fma-heavy pipe (IMAD.WIDE, 4 cycles per warp instruction)",
                                     "achieved": products / acc, "peak": 3.04e10, "unit": "381-bit Montgomery products/s",
@@ -627,11 +643,40 @@ def run_ours(args):
                 line["pairings"]["cpu_baseline"] = cpu_pairing_run(max(1024, 32 * threads), threads)
         print(json.dumps(line))
     if world > 1:
+        barrier()
+        for cs in comms.values():
+            for c in cs:
+                c.close()
         dist.destroy_process_group()
     return 0
 
 
 def main():
+    # stdout carries exactly ONE JSON line: libraries (NCCL's version banner, torch.distributed) write to fd 1 too, so everything
+    # else goes to stderr and the line is written to the saved descriptor at the end
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(os.dup(2), "w")
+    buf = []
+    import builtins
+    orig_print = builtins.print
+
+    def capture(*a, **k):
+        if k.get("file") in (None, sys.stdout) and len(a) == 1 and isinstance(a[0], str) and a[0].startswith("{"):
+            buf.append(a[0])
+        else:
+            orig_print(*a, **k)
+    builtins.print = capture
+    try:
+        rc = _main()
+    finally:
+        builtins.print = orig_print
+        for line in buf[-1:]:
+            os.write(real_stdout, (line + "\n").encode())
+    return rc
+
+
+def _main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)

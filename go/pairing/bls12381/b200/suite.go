@@ -19,19 +19,20 @@ import (
 	"go.dedis.ch/kyber/v4/xof/blake2xb"
 )
 
-// Suite implements pairing.Suite (pairing/pairing.go:8-20), shaped like kilic.Suite (kilic/suite.go).
+// Suite implements pairing.Suite (pairing/pairing.go:8-20), shaped like kilic.Suite (kilic/suite.go:17-106).
 type Suite struct {
 	domainG1, domainG2 []byte
 }
 
-type groupG1 struct{ dst []byte }
-type groupG2 struct{ dst []byte }
-
+// NewBLS12381Suite is the default suite; NewBLS12381SuiteWithDST fixes the hash-to-curve tags (kilic/suite.go:32-46).
 func NewBLS12381Suite() pairing.Suite { return &Suite{} }
+func NewBLS12381SuiteWithDST(dstG1, dstG2 []byte) pairing.Suite {
+	return &Suite{domainG1: dstG1, domainG2: dstG2}
+}
 
-func (s *Suite) G1() kyber.Group { return &groupG1{dst: s.domainG1} }
-func (s *Suite) G2() kyber.Group { return &groupG2{dst: s.domainG2} }
-func (s *Suite) GT() kyber.Group { return &groupGT{} }
+func (s *Suite) G1() kyber.Group { return NewGroupG1(s.domainG1...) }
+func (s *Suite) G2() kyber.Group { return NewGroupG2(s.domainG2...) }
+func (s *Suite) GT() kyber.Group { return NewGroupGT() }
 
 // ValidatePairing: e(p1,p2) == e(inv1,inv2) (kilic/suite.go:57-68), one 2-pair Miller loop + one final exp.
 func (s *Suite) ValidatePairing(p1, p2, inv1, inv2 kyber.Point) bool {
@@ -41,15 +42,14 @@ func (s *Suite) ValidatePairing(p1, p2, inv1, inv2 kyber.Point) bool {
 // Pair returns e(p1,p2) as a GT element (kilic/suite.go:70-75).
 func (s *Suite) Pair(p1, p2 kyber.Point) kyber.Point {
 	gt := newEmptyGT()
-	e := getEngine()
-	e.mu.Lock()
-	defer e.mu.Unlock()
 	a, b := p1.(*G1Elt).aff, p2.(*G2Elt).aff
-	e.check(C.b2k_bls12381_pair(e.ctx, 1, ptr(a[:]), ptr(b[:]), ptr(gt.b[:])))
+	with(func(e *engine) {
+		e.check(C.b2k_bls12381_pair(e.ctx, 1, ptr(a[:]), ptr(b[:]), ptr(gt.b[:])))
+	})
 	return gt
 }
 
-func (s *Suite) Read(r io.Reader, objs ...interface{}) error  { panic("Suite.Read(): deprecated in dedis") }  // kilic/suite.go:78-90
+func (s *Suite) Read(r io.Reader, objs ...interface{}) error  { panic("Suite.Read(): deprecated in dedis") } // kilic/suite.go:78-90
 func (s *Suite) Write(w io.Writer, objs ...interface{}) error { panic("Suite.Write(): deprecated in dedis") }
 func (s *Suite) Hash() hash.Hash                             { return sha256.New() }
 func (s *Suite) XOF(seed []byte) kyber.XOF                   { return blake2xb.New(seed) }

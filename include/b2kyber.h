@@ -21,6 +21,10 @@
  *   - a context owns one CUDA stream and its scratch memory; calls on one context are serialised by
  *     the caller (one context per goroutine/thread), several contexts may be used concurrently
  *   - there is NO CPU fallback: without a usable sm_100 device b2k_create fails
+ *   - operand points are re-validated where that is cheap: canonical coordinates (< p, where the reference's Unmarshal checks
+ *     that: BLS12-381, bn254) and the curve equation; a violation -> B2K_ERR_POINT (the point is treated as infinity).  Membership
+ *     in the order-r subgroup is NOT re-checked (a scalar multiplication per point): like in the reference that is the job of
+ *     UnmarshalBinary, i.e. of b2k_*_decompress / b2k_*_unmarshal_check; the endomorphism paths (G1 Mul / MSM) assume it
  *   - *_dev variants take DEVICE pointers (same layouts) and only enqueue work on the context's
  *     stream; they exist so a caller that keeps batches resident in HBM pays no PCIe traffic;
  *     data errors of enqueued work (scalar >= order, malformed point) are collected by b2k_wait
@@ -43,7 +47,8 @@ enum {
   B2K_ERR_ARG = -2,           /* null pointer / size out of range */
   B2K_ERR_SCALAR_RANGE = -3,  /* some scalar >= group order */
   B2K_ERR_NO_DEVICE = -4,     /* no sm_100 device */
-  B2K_ERR_POINT = -5          /* some operand point is malformed (coordinate >= p or not on curve) */
+  B2K_ERR_POINT = -5,         /* some operand point is malformed (coordinate >= p or not on curve) */
+  B2K_ERR_COMM = -6           /* multi-GPU exchange: a peer rank did not arrive (b2k_comm_*), reported by b2k_wait */
 };
 
 /* ---- lifetime ------------------------------------------------------------------------------ */
@@ -150,6 +155,44 @@ int b2k_bls12381_g1_msm_reduce_windows_dev(b2k_ctx* ctx, int c, int w_cnt, int p
                                            void* d_wsum /*[w_cnt][plan[3]]*/);
 int b2k_bls12381_g1_msm_finish_dev(b2k_ctx* ctx, int c, int W, const void* d_wsum, void* d_out, int affine_out);
 
+/* ---- the sharded MSM as ONE call per rank: the `b2k_msm_multi_gpu` of SURVEY.md 8(b), and 8(e) ------------------------
+ * Replaces the same loops (share/poly.go:461-473, sign/bdn/bdn.go:126-161) when the terms of one sum are partitioned over
+ * the GPUs of a box (BASELINE.json configs[4]: 2^24 pairs, 2^21 per GPU).  A communicator belongs to one context (= one
+ * rank) and owns that rank's EXCHANGE SLAB, a stable device allocation every peer maps (peer access inside one process,
+ * CUDA IPC across processes).  A step then needs no host-side collective at all:
+ *   partial buckets into the own slab -> release-store of the step number into every peer's flag word -> spin on the own
+ *   flag words -> ONE kernel pulls windows [g W/G, (g+1) W/G) of every rank out of the peers' slabs over NVLink and fuses
+ *   the G-way EC addition into the running-sum reduction -> window sums pushed to every peer -> Horner on every rank.
+ * All of it is enqueued on the context's stream; ranks must issue their steps on a communicator in the same order.  A peer
+ * that never arrives makes the waiting kernel give up after ~10 s and b2k_wait return B2K_ERR_COMM (no device hang).
+ * Wiring:  one process per GPU (torchrun, MPI):  create -> export -> all-gather the blobs out of band -> connect;
+ *          one process, ngpu contexts (the cgo adapter):  create x ngpu -> connect_local.
+ * b2k_comm_use_nccl swaps the transport of the bucket exchange for NCCL (grouped ncclSend/ncclRecv = all-to-all, then
+ * ncclAllGather of the window sums; libnccl.so.2 is resolved at run time with dlopen; one rank per process; the 128-byte id
+ * comes from b2k_nccl_unique_id on rank 0 and travels out of band) -- the shape north_star words literally, kept for A/B.
+ * shape: 0 = partial-bucket exchange (W must be a multiple of the rank count), 1 = result exchange (every rank finishes
+ * its MSM, 96-byte results are pushed to every peer and added; any rank count; peer transport only). */
+#define B2K_MAX_RANKS 16
+#define B2K_COMM_BLOB_BYTES 128
+typedef struct b2k_comm b2k_comm;
+int b2k_comm_create(b2k_ctx* ctx, int nranks, int rank, b2k_comm** out);
+int b2k_comm_export(b2k_comm* comm, uint8_t* blob /*[B2K_COMM_BLOB_BYTES]*/);
+int b2k_comm_connect(b2k_comm* comm, const uint8_t* blobs /*[nranks][B2K_COMM_BLOB_BYTES], rank order*/);
+int b2k_comm_connect_local(b2k_comm** comms /*[nranks], rank order*/, int nranks);
+int b2k_nccl_unique_id(uint8_t* id /*[128]*/);
+int b2k_comm_use_nccl(b2k_comm* comm, const uint8_t* id /*[128]*/);
+void b2k_comm_destroy(b2k_comm* comm);
+int b2k_comm_last_plan(const b2k_comm* comm, int* plan /*[4]: c, W, buckets per window, bytes per bucket*/);
+/* this rank's n pairs (DEVICE buffers) -> the 48-byte sum over ALL ranks in d_out on every rank; enqueue only */
+int b2k_bls12381_g1_msm_sharded_dev(b2k_comm* comm, size_t n, const void* d_scalars, const void* d_points,
+                                    void* d_out /*[48]*/, int shape);
+/* the same from (page-locked) HOST buffers, result to host; enqueue only, collect with b2k_wait(ctx of the communicator) */
+int b2k_bls12381_g1_msm_sharded_async(b2k_comm* comm, size_t n, const uint8_t* scalars, const uint8_t* points,
+                                      uint8_t* out /*[48]*/);
+/* one process driving ngpu ranks: partitions the n pairs contiguously, runs the sharded MSM on every communicator, waits */
+int b2k_bls12381_g1_msm_multi_gpu(b2k_comm** comms /*[ngpu], rank order*/, int ngpu, size_t n, const uint8_t* scalars /*[n][32]*/,
+                                  const uint8_t* points /*[n][96]*/, uint8_t* out /*[48]*/);
+
 /* ---- BLS12-381 G2 ------------------------------------------------------------------------------------ */
 /* replaces: kilic.G2Elt.Mul, pairing/bls12381/kilic/g2.go:109-115 (public keys / signatures on G2:
  * bdn.NewMask terms sign/bdn/mask.go:58-61, bdn.AggregateSignatures on G2).  Operands 192 B
@@ -243,6 +286,39 @@ int b2k_bls12381_pairing_check(b2k_ctx* ctx, size_t n, const uint8_t* a1 /*[n][9
                                const uint8_t* b1 /*[n][96]*/, const uint8_t* b2 /*[n][192]*/, uint8_t* ok /*[n]*/);
 int b2k_bls12381_pairing_check_dev(b2k_ctx* ctx, size_t n, const void* d_a1, const void* d_a2, const void* d_b1,
                                    const void* d_b2, void* d_ok);
+
+/* ---- the target group as a kyber.Group, Miller / Finalize, products of pairings, G1 / G2 Add ------------------------------
+ * GT is written additively in kyber: Add = Fp12 product, Neg = inverse, Mul = exponentiation, Null = 1
+ * (pairing/bls12381/kilic/gt.go:33-83; pairing/bn254/point.go:560-623).  Elements travel as their MarshalBinary bytes
+ * (BLS12-381: 576 B, kilic/gt.go:115-117; bn254/bn256: 384 B, pairing/bn254/point.go:625-656); a coefficient >= p raises
+ * B2K_ERR_POINT where the reference's Unmarshal range-checks (BLS12-381, bn254).  gt_exp takes 32-byte big-endian scalars
+ * below the group order and is valid for any Fp12 element (plain square-and-multiply).
+ * miller / final_exp (finalize): pointGT.Miller and pointGT.Finalize (pairing/bn254/point.go:768-786) -- exported by the
+ * reference so that a caller can multiply several Miller values and pay ONE final exponentiation; miller(...) output fed to
+ * final_exp(...) equals pair(...).  An operand at infinity gives 1 (pairing/bn254/optate.go:267-269).
+ * pairing_product_check: ok[0] = ( prod_i e(g1[i], g2[i]) == 1 ), n Miller loops, a product tree, ONE final exponentiation
+ * (SURVEY.md 8e); Suite.ValidatePairing(p1, p2, q1, q2) is the n = 2 case with q1 negated (kilic/suite.go:57-68).
+ * pairing_product: the same product as GT bytes (e.g. n-signer aggregate checks that compare against a stored value).
+ * g{1,2}_add_batch: out[i] = a[i] + b[i] (negate_b = 0) or a[i] - b[i] (negate_b = 1), operand form in and out, every
+ * exceptional case of the group law handled (kilic/g1.go:92-108, g2.go:91-107: Point.Add / Sub / Neg, one at a time in Go). */
+int b2k_bls12381_gt_mul(b2k_ctx* ctx, size_t n, const uint8_t* a /*[n][576]*/, const uint8_t* b /*[n][576]*/, uint8_t* out /*[n][576]*/);
+int b2k_bls12381_gt_inv(b2k_ctx* ctx, size_t n, const uint8_t* a /*[n][576]*/, uint8_t* out /*[n][576]*/);
+int b2k_bls12381_gt_exp(b2k_ctx* ctx, size_t n, const uint8_t* scalars /*[n][32]*/, const uint8_t* a /*[n][576]*/, uint8_t* out /*[n][576]*/);
+int b2k_bn254_gt_mul(b2k_ctx* ctx, size_t n, const uint8_t* a /*[n][384]*/, const uint8_t* b /*[n][384]*/, uint8_t* out /*[n][384]*/);
+int b2k_bn254_gt_inv(b2k_ctx* ctx, size_t n, const uint8_t* a /*[n][384]*/, uint8_t* out /*[n][384]*/);
+int b2k_bn254_gt_exp(b2k_ctx* ctx, size_t n, const uint8_t* scalars /*[n][32]*/, const uint8_t* a /*[n][384]*/, uint8_t* out /*[n][384]*/);
+int b2k_bls12381_miller(b2k_ctx* ctx, size_t n, const uint8_t* g1 /*[n][96]*/, const uint8_t* g2 /*[n][192]*/, uint8_t* out /*[n][576]*/);
+int b2k_bls12381_final_exp(b2k_ctx* ctx, size_t n, const uint8_t* in /*[n][576]*/, uint8_t* out /*[n][576]*/);
+int b2k_bls12381_pairing_product_check(b2k_ctx* ctx, size_t n, const uint8_t* g1 /*[n][96]*/, const uint8_t* g2 /*[n][192]*/, uint8_t* ok /*[1]*/);
+int b2k_bls12381_pairing_product(b2k_ctx* ctx, size_t n, const uint8_t* g1 /*[n][96]*/, const uint8_t* g2 /*[n][192]*/, uint8_t* gt /*[576]*/);
+int b2k_bn254_miller(b2k_ctx* ctx, size_t n, const uint8_t* g1 /*[n][64]*/, const uint8_t* g2 /*[n][128]*/, uint8_t* out /*[n][384]*/);
+int b2k_bn254_finalize(b2k_ctx* ctx, size_t n, const uint8_t* in /*[n][384]*/, uint8_t* out /*[n][384]*/);
+int b2k_bn254_pairing_product_check(b2k_ctx* ctx, size_t n, const uint8_t* g1 /*[n][64]*/, const uint8_t* g2 /*[n][128]*/, uint8_t* ok /*[1]*/);
+int b2k_bn256_miller(b2k_ctx* ctx, size_t n, const uint8_t* g1 /*[n][64]*/, const uint8_t* g2 /*[n][128]*/, uint8_t* out /*[n][384]*/);
+int b2k_bn256_finalize(b2k_ctx* ctx, size_t n, const uint8_t* in /*[n][384]*/, uint8_t* out /*[n][384]*/);
+int b2k_bn256_pairing_product_check(b2k_ctx* ctx, size_t n, const uint8_t* g1 /*[n][64]*/, const uint8_t* g2 /*[n][128]*/, uint8_t* ok /*[1]*/);
+int b2k_bls12381_g1_add_batch(b2k_ctx* ctx, size_t n, const uint8_t* a /*[n][96]*/, const uint8_t* b /*[n][96]*/, int negate_b, uint8_t* out /*[n][96]*/);
+int b2k_bls12381_g2_add_batch(b2k_ctx* ctx, size_t n, const uint8_t* a /*[n][192]*/, const uint8_t* b /*[n][192]*/, int negate_b, uint8_t* out /*[n][192]*/);
 
 /* ---- bn254 G1 (share.RecoverCommit config: t = 1024 over bn254 G1) ------------------------------ */
 /* replaces bn254 curvePoint.Mul, pairing/bn254/curve.go:196-218 */

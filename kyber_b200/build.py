@@ -7,7 +7,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libb2kyber.so")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC"]
-UNITS = ["b2k_api.cu", "b2k_g1_mul.cu", "b2k_bn254.cu", "b2k_g2.cu", "b2k_pairing.cu", "b2k_h2c.cu", "b2k_share.cu", "b2k_ed25519.cu", "b2k_bn256.cu", "b2k_bn254_pairing.cu", "b2k_bdn.cu", "b2k_bn_hash.cu", "b2k_bn_codec.cu"]
+UNITS = ["b2k_api.cu", "b2k_g1_mul.cu", "b2k_bn254.cu", "b2k_g2.cu", "b2k_pairing.cu", "b2k_h2c.cu", "b2k_share.cu", "b2k_ed25519.cu", "b2k_bn256.cu", "b2k_bn254_pairing.cu", "b2k_bdn.cu", "b2k_bn_hash.cu", "b2k_bn_codec.cu", "b2k_multi.cu", "b2k_gt.cu"]
 
 
 def _nvcc() -> str:
@@ -17,43 +17,71 @@ def _nvcc() -> str:
     raise RuntimeError("nvcc not found")
 
 
-def _stamp() -> str:
+def _hash_files(paths) -> str:
+    import re
     h = hashlib.sha256()
-    for root in (CSRC, os.path.join(HERE, "..", "include")):
-        for fn in sorted(os.listdir(root)):
-            if fn.endswith((".cu", ".cuh", ".h")):
-                with open(os.path.join(root, fn), "rb") as f:
-                    h.update(fn.encode()); h.update(f.read())
+    for p in paths:
+        with open(p, "rb") as f:
+            data = f.read()
+        if p.endswith("b2kyber.h"):            # the public header is mostly documentation: comment edits do not recompile
+            data = re.sub(rb"/\*.*?\*/", b"", data, flags=re.S)
+        h.update(os.path.basename(p).encode()); h.update(data)
     h.update(" ".join(NVCC_FLAGS).encode())
     return h.hexdigest()
 
 
+def _headers():
+    out = []
+    for root in (CSRC, os.path.join(HERE, "..", "include")):
+        out += [os.path.join(root, fn) for fn in sorted(os.listdir(root)) if fn.endswith((".cuh", ".h"))]
+    return out
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile kyber_b200/libb2kyber.so if sources changed. Returns the library path."""
-    stamp_file = LIB + ".stamp"
-    stamp = _stamp()
-    if not force and os.path.exists(LIB) and os.path.exists(stamp_file) and open(stamp_file).read() == stamp:
-        return LIB
-    objs = []
-    procs = []
+    """Compile kyber_b200/libb2kyber.so.  Incremental per translation unit: a unit is recompiled when its own source or ANY
+    header changed (stamp next to the object), the library is relinked when an object changed.  Returns the library path."""
+    hdrs = _headers()
+    objs, procs = [], []
     for u in UNITS:
+        src = os.path.join(CSRC, u)
         obj = os.path.join(CSRC, u.replace(".cu", ".o"))
-        cmd = [_nvcc(), *NVCC_FLAGS, "-c", os.path.join(CSRC, u), "-o", obj]
+        objs.append(obj)
+        stamp = _hash_files([src] + hdrs)
+        sf = obj + ".stamp"
+        if not force and os.path.exists(obj) and os.path.exists(sf) and open(sf).read() == stamp:
+            continue
+        if not force and os.path.exists(obj) and not os.path.exists(sf) and \
+                os.path.getmtime(obj) > max(os.path.getmtime(p) for p in [src] + hdrs):
+            with open(sf, "w") as f:          # an object newer than all of its inputs (built before stamps existed): adopt it
+                f.write(stamp)
+            continue
+        cmd = [_nvcc(), *NVCC_FLAGS, "-c", src, "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas"); cmd.insert(2, "-v")
-        procs.append((u, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
-        objs.append(obj)
-    for u, p in procs:
+        if os.path.exists(sf):
+            os.remove(sf)
+        procs.append((u, sf, stamp, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    failed = None
+    for u, sf, stamp, p in procs:
         out, _ = p.communicate()
         if verbose or p.returncode:
             sys.stderr.write(out)
         if p.returncode:
-            raise RuntimeError(f"nvcc failed on {u}")
-    cmd = [_nvcc(), "-shared", "-o", LIB + ".tmp", *objs, "-lcudart"]
+            failed = failed or u
+        else:
+            with open(sf, "w") as f:
+                f.write(stamp)
+    if failed:
+        raise RuntimeError(f"nvcc failed on {failed}")
+    link_stamp = _hash_files([o + ".stamp" for o in objs])
+    lf = LIB + ".stamp"
+    if not procs and not force and os.path.exists(LIB) and os.path.exists(lf) and open(lf).read() == link_stamp:
+        return LIB
+    cmd = [_nvcc(), "-shared", "-o", LIB + ".tmp", *objs, "-lcudart", "-ldl"]
     subprocess.run(cmd, check=True)
     os.replace(LIB + ".tmp", LIB)          # atomic: a reader (or a snapshot of the tree) never sees a half-written library
-    with open(stamp_file, "w") as f:
-        f.write(stamp)
+    with open(lf, "w") as f:
+        f.write(link_stamp)
     return LIB
 
 

@@ -10,7 +10,8 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libb2kyber.so")
 
-B2K_OK, ERR_CUDA, ERR_ARG, ERR_SCALAR_RANGE, ERR_NO_DEVICE, ERR_POINT = 0, -1, -2, -3, -4, -5
+B2K_OK, ERR_CUDA, ERR_ARG, ERR_SCALAR_RANGE, ERR_NO_DEVICE, ERR_POINT, ERR_COMM = 0, -1, -2, -3, -4, -5, -6
+COMM_BLOB_BYTES, MAX_RANKS = 128, 16
 
 
 class B2KError(RuntimeError):
@@ -76,6 +77,28 @@ def load_library() -> C.CDLL:
     sigs["b2k_bls12381_g1_msm_buckets_dev"] = (C.c_int, [vp, sz, vp, vp, vp, sz, C.POINTER(C.c_int)])
     sigs["b2k_bls12381_g1_msm_reduce_windows_dev"] = (C.c_int, [vp, C.c_int, C.c_int, C.c_int, vp, vp])
     sigs["b2k_bls12381_g1_msm_finish_dev"] = (C.c_int, [vp, C.c_int, C.c_int, vp, vp, C.c_int])
+    for cv in ("bls12381", "bn254"):
+        sigs[f"b2k_{cv}_gt_mul"] = (C.c_int, [vp, sz, vp, vp, vp])
+        sigs[f"b2k_{cv}_gt_inv"] = (C.c_int, [vp, sz, vp, vp])
+        sigs[f"b2k_{cv}_gt_exp"] = (C.c_int, [vp, sz, vp, vp, vp])
+    for nm in ("b2k_bls12381_miller", "b2k_bn254_miller", "b2k_bn256_miller", "b2k_bls12381_pairing_product_check",
+               "b2k_bls12381_pairing_product", "b2k_bn254_pairing_product_check", "b2k_bn256_pairing_product_check"):
+        sigs[nm] = (C.c_int, [vp, sz, vp, vp, vp])
+    for nm in ("b2k_bls12381_final_exp", "b2k_bn254_finalize", "b2k_bn256_finalize"):
+        sigs[nm] = (C.c_int, [vp, sz, vp, vp])
+    for nm in ("b2k_bls12381_g1_add_batch", "b2k_bls12381_g2_add_batch"):
+        sigs[nm] = (C.c_int, [vp, sz, vp, vp, C.c_int, vp])
+    sigs["b2k_comm_create"] = (C.c_int, [vp, C.c_int, C.c_int, C.POINTER(vp)])
+    sigs["b2k_comm_export"] = (C.c_int, [vp, vp])
+    sigs["b2k_comm_connect"] = (C.c_int, [vp, vp])
+    sigs["b2k_comm_connect_local"] = (C.c_int, [C.POINTER(vp), C.c_int])
+    sigs["b2k_nccl_unique_id"] = (C.c_int, [vp])
+    sigs["b2k_comm_use_nccl"] = (C.c_int, [vp, vp])
+    sigs["b2k_comm_destroy"] = (None, [vp])
+    sigs["b2k_comm_last_plan"] = (C.c_int, [vp, C.POINTER(C.c_int)])
+    sigs["b2k_bls12381_g1_msm_sharded_dev"] = (C.c_int, [vp, sz, vp, vp, vp, C.c_int])
+    sigs["b2k_bls12381_g1_msm_sharded_async"] = (C.c_int, [vp, sz, vp, vp, vp])
+    sigs["b2k_bls12381_g1_msm_multi_gpu"] = (C.c_int, [C.POINTER(vp), C.c_int, sz, vp, vp, vp])
     host3 = (C.c_int, [vp, sz, vp, vp, vp])
     for name in HOST_FUNCS + DEV_FUNCS:
         sigs[name] = host3
@@ -392,6 +415,52 @@ class Engine:
         self._check(self.lib.b2k_bn256_pairing_check(self.h, n, *[b[0] for b in bufs]))
         return bytes(out)
 
+    # -- target group, Miller / Finalize, products of pairings, point additions (b2k_gt.cu) --------------------------------------
+    GT_BYTES = {"bls12381": 576, "bn254": 384, "bn256": 384}
+    G1_BYTES = {"bls12381": 96, "bn254": 64, "bn256": 64}
+    G2_BYTES = {"bls12381": 192, "bn254": 128, "bn256": 128}
+
+    def _call_bufs(self, name: str, n: int, ins, out_len: int, extra=()) -> bytes:
+        out = bytearray(out_len)
+        keep = [_buf(b) for b in ins]
+        po, ko = _buf(out)
+        self._check(getattr(self.lib, name)(self.h, n, *[k[0] for k in keep], *extra, po))
+        return bytes(out)
+
+    def gt_mul(self, curve: str, a: bytes, b: bytes) -> bytes:
+        n = len(a) // self.GT_BYTES[curve]
+        return self._call_bufs(f"b2k_{curve}_gt_mul", n, (a, b), len(a))
+
+    def gt_inv(self, curve: str, a: bytes) -> bytes:
+        n = len(a) // self.GT_BYTES[curve]
+        return self._call_bufs(f"b2k_{curve}_gt_inv", n, (a,), len(a))
+
+    def gt_exp(self, curve: str, scalars: bytes, a: bytes) -> bytes:
+        n = len(a) // self.GT_BYTES[curve]
+        return self._call_bufs(f"b2k_{curve}_gt_exp", n, (scalars, a), len(a))
+
+    def miller(self, curve: str, g1: bytes, g2: bytes) -> bytes:
+        n = len(g1) // self.G1_BYTES[curve]
+        return self._call_bufs(f"b2k_{curve}_miller", n, (g1, g2), n * self.GT_BYTES[curve])
+
+    def final_exp(self, curve: str, f: bytes) -> bytes:
+        n = len(f) // self.GT_BYTES[curve]
+        return self._call_bufs("b2k_bls12381_final_exp" if curve == "bls12381" else f"b2k_{curve}_finalize", n, (f,), len(f))
+
+    def pairing_product_check(self, curve: str, g1: bytes, g2: bytes) -> bool:
+        n = len(g1) // self.G1_BYTES[curve]
+        return self._call_bufs(f"b2k_{curve}_pairing_product_check", n, (g1, g2), 1) == b"\x01"
+
+    def bls12381_pairing_product(self, g1: bytes, g2: bytes) -> bytes:
+        return self._call_bufs("b2k_bls12381_pairing_product", len(g1) // 96, (g1, g2), 576)
+
+    def bls12381_add_batch(self, group: int, a: bytes, b: bytes, negate_b: bool = False) -> bytes:
+        pb = 96 if group == 1 else 192
+        out = bytearray(len(a))
+        pa, k1 = _buf(a); pbb, k2 = _buf(b); po, k3 = _buf(out)
+        self._check(getattr(self.lib, f"b2k_bls12381_g{group}_add_batch")(self.h, len(a) // pb, pa, pbb, 1 if negate_b else 0, po))
+        return bytes(out)
+
     @staticmethod
     def bdn_coefficients(pubs: bytes, pub_len: int, add_one: bool = False) -> bytes:
         """sign/bdn hashPointToR (bdn.go:29-63) over the marshalled public keys -> n x 32-byte big-endian c_i (+1).
@@ -482,3 +551,85 @@ class Engine:
         n = len(scalars) // 32
         assert len(scalars) == 32 * n and len(points) == 64 * n
         return self.call_host("b2k_bn254_g1_msm", n, scalars, points, 64)
+
+
+class Comm:
+    """One rank of the sharded MSM (include/b2kyber.h: b2k_comm_*): owns the rank's exchange slab on the engine's device.
+
+    Wiring, one process per GPU:   c = Comm(eng, world, rank); blobs = all_gather(c.export()); c.connect(b"".join(blobs))
+    one process, several engines:  comms = [Comm(e, n, r) ...]; Comm.connect_local(comms)
+    """
+
+    def __init__(self, eng: Engine, nranks: int, rank: int):
+        self.eng, self.nranks, self.rank = eng, nranks, rank
+        h = C.c_void_p()
+        eng._check(eng.lib.b2k_comm_create(eng.h, nranks, rank, C.byref(h)))
+        self.h = h
+
+    def export(self) -> bytes:
+        buf = C.create_string_buffer(COMM_BLOB_BYTES)
+        self.eng._check(self.eng.lib.b2k_comm_export(self.h, C.cast(buf, C.c_void_p)))
+        return buf.raw
+
+    def connect(self, blobs: bytes):
+        assert len(blobs) == self.nranks * COMM_BLOB_BYTES
+        p, keep = _buf(blobs)
+        self.eng._check(self.eng.lib.b2k_comm_connect(self.h, p))
+
+    @staticmethod
+    def connect_local(comms):
+        arr = (C.c_void_p * len(comms))(*[c.h for c in comms])
+        comms[0].eng._check(comms[0].eng.lib.b2k_comm_connect_local(arr, len(comms)))
+
+    def use_nccl(self, unique_id: bytes):
+        p, keep = _buf(unique_id)
+        self.eng._check(self.eng.lib.b2k_comm_use_nccl(self.h, p))
+
+    @staticmethod
+    def nccl_unique_id(lib=None) -> bytes:
+        lib = lib or load_library()
+        buf = C.create_string_buffer(128)
+        if lib.b2k_nccl_unique_id(C.cast(buf, C.c_void_p)) != 0:
+            raise B2KError(-1, "b2k_nccl_unique_id failed (libnccl.so.2 not loadable)")
+        return buf.raw
+
+    def last_plan(self):
+        a = (C.c_int * 4)()
+        self.eng._check(self.eng.lib.b2k_comm_last_plan(self.h, a))
+        return {"c": a[0], "W": a[1], "buckets_per_window": a[2], "bucket_bytes": a[3]}
+
+    def msm_sharded_dev(self, n: int, d_scalars: int, d_points: int, d_out: int, shape: int = 0):
+        """this rank's n resident pairs -> 48-byte sum over all ranks at d_out (enqueue only)"""
+        self.eng._check(self.eng.lib.b2k_bls12381_g1_msm_sharded_dev(self.h, n, C.c_void_p(d_scalars), C.c_void_p(d_points),
+                                                                   C.c_void_p(d_out), shape))
+
+    def msm_sharded_async(self, n: int, h_scalars: int, h_points: int, h_out: int):
+        """host pointers (page-locked); collect with eng.wait()"""
+        self.eng._check(self.eng.lib.b2k_bls12381_g1_msm_sharded_async(self.h, n, C.c_void_p(h_scalars), C.c_void_p(h_points),
+                                                                     C.c_void_p(h_out)))
+
+    @staticmethod
+    def msm_multi_gpu(comms, scalars: bytes, points: bytes) -> bytes:
+        """one process, len(comms) GPUs: the whole sharded MSM from host buffers (b2k_bls12381_g1_msm_multi_gpu)"""
+        n = len(scalars) // 32
+        arr = (C.c_void_p * len(comms))(*[c.h for c in comms])
+        ps, k1 = _buf(scalars)
+        pp, k2 = _buf(points)
+        out = C.create_string_buffer(48)
+        rc = comms[0].eng.lib.b2k_bls12381_g1_msm_multi_gpu(arr, len(comms), n, ps, pp, C.cast(out, C.c_void_p))
+        for c in comms:
+            if rc == 0:
+                break
+            c.eng._check(rc)
+        return out.raw
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.eng.lib.b2k_comm_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

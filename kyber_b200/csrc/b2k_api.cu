@@ -76,11 +76,8 @@ int b2k_create(int device, b2k_ctx** out) {
             cudaMemset(ctx->d_flags, 0, 256) == cudaSuccess;
   for (int i = 0; ok && i < N_EV; i++) ok = cudaEventCreate(&ctx->ev[i]) == cudaSuccess;
   for (int i = 0; ok && i < 10; i++) ok = cudaEventCreateWithFlags(&ctx->gev[i], cudaEventDisableTiming) == cudaSuccess;
-  if (ok) {
-    int lo = 0, hi = 0;
-    cudaDeviceGetStreamPriorityRange(&lo, &hi);      // hi = greatest priority (numerically lowest)
-    ok = cudaStreamCreateWithPriority(&ctx->stream2, cudaStreamNonBlocking, hi) == cudaSuccess;
-  }
+  // (the high-priority side stream of the grouped-tail experiment is created on demand by b2k_set_msm_groups: an idle stream
+  //  still occupies one of the device's hardware queues, and the spin-waits of b2k_multi.cu want those for themselves)
   if (!ok) { delete ctx; return B2K_ERR_CUDA; }
   ctx->own_stream = true;
   *ctx->h_flags = 0;
@@ -202,6 +199,12 @@ int b2k_set_msm_glv(b2k_ctx* ctx, int on) {
 
 int b2k_set_msm_groups(b2k_ctx* ctx, int groups) {
   if (!ctx || groups < 1 || groups > 8) return B2K_ERR_ARG;
+  if (groups > 1 && !ctx->stream2) {
+    CK(cudaSetDevice(ctx->device));
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);      // hi = greatest priority (numerically lowest)
+    CK(cudaStreamCreateWithPriority(&ctx->stream2, cudaStreamNonBlocking, hi));
+  }
   ctx->msm_groups = groups;
   return B2K_OK;
 }
@@ -221,6 +224,8 @@ int b2k_bls12381_g1_msm_affine_dev(b2k_ctx* c, size_t n, const void* s, const vo
 
 int b2k_bls12381_g1_msm_bucket_plan(b2k_ctx* c, size_t n, int* plan) { return msm_bucket_plan<Bls381G1>(c, n, plan); }
 int b2k_bls12381_g1_msm_buckets_dev(b2k_ctx* c, size_t n, const void* s, const void* p, void* b, size_t cap, int* plan) { return msm_buckets_dev<Bls381G1>(c, n, s, p, b, cap, plan); }
+// internal (b2k_ctx.h): host-staged bucket pass for the sharded entry points of b2k_multi.cu
+int b2k_internal_bls12381_g1_msm_buckets_host(b2k_ctx* c, size_t n, const uint8_t* s, const uint8_t* p, void* b, size_t cap, int* plan) { return msm_buckets_host<Bls381G1>(c, n, s, p, b, cap, plan); }
 int b2k_bls12381_g1_msm_reduce_windows_dev(b2k_ctx* c, int cbits, int w_cnt, int parts, const void* recv, void* wsum) { return msm_reduce_windows_dev<Bls381G1>(c, cbits, w_cnt, parts, recv, wsum); }
 int b2k_bls12381_g1_msm_finish_dev(b2k_ctx* c, int cbits, int W, const void* wsum, void* out, int affine_out) { return msm_finish_dev<Bls381G1>(c, cbits, W, wsum, out, affine_out); }
 

@@ -6,13 +6,14 @@ using namespace b2k_host;
 namespace b2k {
 
 __global__ void __launch_bounds__(64, 4) k_bn254_pair(size_t n, const uint8_t* __restrict__ g1, const uint8_t* __restrict__ g2,
-                                                      uint8_t* __restrict__ gt) {
+                                                      uint8_t* __restrict__ gt, uint32_t* flags) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   Affine<NFp> P;
   Affine<NFp2> Q;
-  bn254_g1_load(P, g1 + 64 * i);
-  bn254_g2_load(Q, g2 + 128 * i);
+  bool good = load_checked<Bn254G1>(P, g1 + 64 * i);
+  good = load_checked<Bn254G2>(Q, g2 + 128 * i) && good;
+  if (!good) atomicOr(flags, FLAG_POINT);
   NFp12 f, e;
   bn254_miller_loop<1>(f, &P, &Q);
   bn254_final_exponentiation(e, f);
@@ -24,15 +25,16 @@ __global__ void __launch_bounds__(64, 4) k_bn254_pair(size_t n, const uint8_t* _
 // (pairing/bn254/suite.go:138-144); one product of Miller loops + one final exponentiation gives the same boolean.
 __global__ void __launch_bounds__(64, 4) k_bn254_pairing_check(size_t n, const uint8_t* __restrict__ a1,
                                                                const uint8_t* __restrict__ a2, const uint8_t* __restrict__ b1,
-                                                               const uint8_t* __restrict__ b2, uint8_t* __restrict__ ok) {
+                                                               const uint8_t* __restrict__ b2, uint8_t* __restrict__ ok, uint32_t* flags) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   Affine<NFp> P[2];
   Affine<NFp2> Q[2];
-  bn254_g1_load(P[0], a1 + 64 * i);
-  bn254_g2_load(Q[0], a2 + 128 * i);
-  bn254_g1_load(P[1], b1 + 64 * i);
-  bn254_g2_load(Q[1], b2 + 128 * i);
+  bool good = load_checked<Bn254G1>(P[0], a1 + 64 * i);
+  good = load_checked<Bn254G2>(Q[0], a2 + 128 * i) && good;
+  good = load_checked<Bn254G1>(P[1], b1 + 64 * i) && good;
+  good = load_checked<Bn254G2>(Q[1], b2 + 128 * i) && good;
+  if (!good) { atomicOr(flags, FLAG_POINT); ok[i] = 0; return; }
   fp_neg(P[1].y, P[1].y);
   NFp12 f, e;
   bn254_miller_loop<2>(f, P, Q);
@@ -53,14 +55,14 @@ int b2k_bn254_pair(b2k_ctx* ctx, size_t n, const uint8_t* g1, const uint8_t* g2,
   uint8_t* d2 = arena_take<uint8_t>(ctx, n * 128);
   uint8_t* dg = arena_take<uint8_t>(ctx, n * 384);
   cudaStream_t st = ctx->stream;
+  CK(cudaMemsetAsync(ctx->d_flags, 0, 4, st));
   CK(cudaMemcpyAsync(d1, g1, n * 64, cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(d2, g2, n * 128, cudaMemcpyHostToDevice, st));
-  k_bn254_pair<<<(unsigned)((n + 63) / 64), 64, 0, st>>>(n, d1, d2, dg);
+  k_bn254_pair<<<(unsigned)((n + 63) / 64), 64, 0, st>>>(n, d1, d2, dg, ctx->d_flags);
   CK(cudaGetLastError());
   ctx->launches += 1;
   CK(cudaMemcpyAsync(gt, dg, n * 384, cudaMemcpyDeviceToHost, st));
-  CK(cudaStreamSynchronize(st));
-  return B2K_OK;
+  return status_finish(ctx);
 }
 
 int b2k_bn254_pairing_check(b2k_ctx* ctx, size_t n, const uint8_t* a1, const uint8_t* a2, const uint8_t* b1,
@@ -75,16 +77,16 @@ int b2k_bn254_pairing_check(b2k_ctx* ctx, size_t n, const uint8_t* a1, const uin
   uint8_t* db2 = arena_take<uint8_t>(ctx, n * 128);
   uint8_t* dok = arena_take<uint8_t>(ctx, n);
   cudaStream_t st = ctx->stream;
+  CK(cudaMemsetAsync(ctx->d_flags, 0, 4, st));
   CK(cudaMemcpyAsync(da1, a1, n * 64, cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(da2, a2, n * 128, cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(db1, b1, n * 64, cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(db2, b2, n * 128, cudaMemcpyHostToDevice, st));
-  k_bn254_pairing_check<<<(unsigned)((n + 63) / 64), 64, 0, st>>>(n, da1, da2, db1, db2, dok);
+  k_bn254_pairing_check<<<(unsigned)((n + 63) / 64), 64, 0, st>>>(n, da1, da2, db1, db2, dok, ctx->d_flags);
   CK(cudaGetLastError());
   ctx->launches += 1;
   CK(cudaMemcpyAsync(ok, dok, n, cudaMemcpyDeviceToHost, st));
-  CK(cudaStreamSynchronize(st));
-  return B2K_OK;
+  { int rc2 = status_finish(ctx); return rc2 == B2K_ERR_POINT ? B2K_OK : rc2; }   // a malformed operand already failed its own check
 }
 
 int b2k_bn254_g2_mul_batch(b2k_ctx* c, size_t n, const uint8_t* s, const uint8_t* p, uint8_t* o) { return mul_batch_host<Bn254G2, false>(c, n, s, p, o); }

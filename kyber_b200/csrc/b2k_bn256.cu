@@ -9,13 +9,14 @@ using PC6 = Bn256Pair;
 
 // pairing/bn256/suite.go:99-105 Pair -> optimalAte (optate.go:266-274): identity when an operand is infinity
 __global__ void __launch_bounds__(64, 4) k_bn256_pair(size_t n, const uint8_t* __restrict__ g1, const uint8_t* __restrict__ g2,
-                                                      uint8_t* __restrict__ gt) {
+                                                      uint8_t* __restrict__ gt, uint32_t* flags) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   Affine<PFp<PC6>> P;
   Affine<PFp2<PC6>> Q;
-  bn_g1_load<PC6>(P, g1 + 64 * i);
-  bn_g2_load<PC6>(Q, g2 + 128 * i);
+  bool good = load_checked<Bn256G1>(P, g1 + 64 * i);
+  good = load_checked<Bn256G2>(Q, g2 + 128 * i) && good;
+  if (!good) atomicOr(flags, FLAG_POINT);
   PFp12<PC6> f, e;
   bn_miller_loop<PC6, 1>(f, &P, &Q);
   bn_final_exponentiation<PC6>(e, f);
@@ -26,15 +27,16 @@ __global__ void __launch_bounds__(64, 4) k_bn256_pair(size_t n, const uint8_t* _
 // ok[i] = e(a1,a2) == e(b1,b2)   (bn256 ValidatePairing = two pairings + Equal, suite.go:107-109)
 __global__ void __launch_bounds__(64, 4) k_bn256_pairing_check(size_t n, const uint8_t* __restrict__ a1,
                                                                const uint8_t* __restrict__ a2, const uint8_t* __restrict__ b1,
-                                                               const uint8_t* __restrict__ b2, uint8_t* __restrict__ ok) {
+                                                               const uint8_t* __restrict__ b2, uint8_t* __restrict__ ok, uint32_t* flags) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   Affine<PFp<PC6>> P[2];
   Affine<PFp2<PC6>> Q[2];
-  bn_g1_load<PC6>(P[0], a1 + 64 * i);
-  bn_g2_load<PC6>(Q[0], a2 + 128 * i);
-  bn_g1_load<PC6>(P[1], b1 + 64 * i);
-  bn_g2_load<PC6>(Q[1], b2 + 128 * i);
+  bool good = load_checked<Bn256G1>(P[0], a1 + 64 * i);
+  good = load_checked<Bn256G2>(Q[0], a2 + 128 * i) && good;
+  good = load_checked<Bn256G1>(P[1], b1 + 64 * i) && good;
+  good = load_checked<Bn256G2>(Q[1], b2 + 128 * i) && good;
+  if (!good) { atomicOr(flags, FLAG_POINT); ok[i] = 0; return; }
   fp_neg(P[1].y, P[1].y);
   PFp12<PC6> f, e;
   bn_miller_loop<PC6, 2>(f, P, Q);
@@ -58,14 +60,14 @@ int b2k_bn256_pair(b2k_ctx* ctx, size_t n, const uint8_t* g1, const uint8_t* g2,
   uint8_t* d2 = arena_take<uint8_t>(ctx, n * 128);
   uint8_t* dg = arena_take<uint8_t>(ctx, n * 384);
   cudaStream_t st = ctx->stream;
+  CK(cudaMemsetAsync(ctx->d_flags, 0, 4, st));
   CK(cudaMemcpyAsync(d1, g1, n * 64, cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(d2, g2, n * 128, cudaMemcpyHostToDevice, st));
-  k_bn256_pair<<<(unsigned)((n + 63) / 64), 64, 0, st>>>(n, d1, d2, dg);
+  k_bn256_pair<<<(unsigned)((n + 63) / 64), 64, 0, st>>>(n, d1, d2, dg, ctx->d_flags);
   CK(cudaGetLastError());
   ctx->launches += 1;
   CK(cudaMemcpyAsync(gt, dg, n * 384, cudaMemcpyDeviceToHost, st));
-  CK(cudaStreamSynchronize(st));
-  return B2K_OK;
+  return status_finish(ctx);
 }
 
 int b2k_bn256_pairing_check(b2k_ctx* ctx, size_t n, const uint8_t* a1, const uint8_t* a2, const uint8_t* b1,
@@ -80,15 +82,15 @@ int b2k_bn256_pairing_check(b2k_ctx* ctx, size_t n, const uint8_t* a1, const uin
   uint8_t* db2 = arena_take<uint8_t>(ctx, n * 128);
   uint8_t* dok = arena_take<uint8_t>(ctx, n);
   cudaStream_t st = ctx->stream;
+  CK(cudaMemsetAsync(ctx->d_flags, 0, 4, st));
   CK(cudaMemcpyAsync(da1, a1, n * 64, cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(da2, a2, n * 128, cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(db1, b1, n * 64, cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(db2, b2, n * 128, cudaMemcpyHostToDevice, st));
-  k_bn256_pairing_check<<<(unsigned)((n + 63) / 64), 64, 0, st>>>(n, da1, da2, db1, db2, dok);
+  k_bn256_pairing_check<<<(unsigned)((n + 63) / 64), 64, 0, st>>>(n, da1, da2, db1, db2, dok, ctx->d_flags);
   CK(cudaGetLastError());
   ctx->launches += 1;
   CK(cudaMemcpyAsync(ok, dok, n, cudaMemcpyDeviceToHost, st));
-  CK(cudaStreamSynchronize(st));
-  return B2K_OK;
+  { int rc2 = status_finish(ctx); return rc2 == B2K_ERR_POINT ? B2K_OK : rc2; }   // a malformed operand already failed its own check
 }
 }  // extern "C"

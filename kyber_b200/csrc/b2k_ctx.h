@@ -48,3 +48,6 @@ struct b2k_ctx {
 // take returns 256-byte aligned sub-buffers or nullptr.
 int b2k_arena_reserve(b2k_ctx* ctx, size_t bytes);
 void* b2k_arena_take(b2k_ctx* ctx, size_t bytes);
+
+// internal entry points shared between translation units (not part of include/b2kyber.h)
+extern "C" int b2k_internal_bls12381_g1_msm_buckets_host(b2k_ctx* c, size_t n, const uint8_t* s, const uint8_t* p, void* b, size_t cap, int* plan);

@@ -5,17 +5,10 @@
 #include "../../include/b2kyber.h"
 #include "b2k_ctx.h"
 #include "pairing_kernels.cuh"
+#include "msm_host.cuh"
 
 using namespace b2k;
 
-#define CK(call)                                                                       \
-  do {                                                                                 \
-    cudaError_t e_ = (call);                                                           \
-    if (e_ != cudaSuccess) {                                                           \
-      ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_);                   \
-      return B2K_ERR_CUDA;                                                             \
-    }                                                                                  \
-  } while (0)
 
 extern "C" {
 
@@ -36,13 +29,13 @@ int b2k_bls12381_pair(b2k_ctx* ctx, size_t n, const uint8_t* g1, const uint8_t* 
   uint8_t* d1 = (uint8_t*)b2k_arena_take(ctx, n * 96);
   uint8_t* d2 = (uint8_t*)b2k_arena_take(ctx, n * 192);
   uint8_t* dg = (uint8_t*)b2k_arena_take(ctx, n * 576);
+  CK(cudaMemsetAsync(ctx->d_flags, 0, 4, ctx->stream));
   CK(cudaMemcpyAsync(d1, g1, n * 96, cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyAsync(d2, g2, n * 192, cudaMemcpyHostToDevice, ctx->stream));
   rc = b2k_bls12381_pair_dev(ctx, n, d1, d2, dg);
   if (rc) return rc;
   CK(cudaMemcpyAsync(gt, dg, n * 576, cudaMemcpyDeviceToHost, ctx->stream));
-  CK(cudaStreamSynchronize(ctx->stream));
-  return B2K_OK;
+  return b2k_host::status_finish(ctx);
 }
 
 int b2k_bls12381_pairing_check_dev(b2k_ctx* ctx, size_t n, const void* a1, const void* a2, const void* b1,
@@ -66,6 +59,7 @@ int b2k_bls12381_pairing_check(b2k_ctx* ctx, size_t n, const uint8_t* a1, const 
   uint8_t* db1 = (uint8_t*)b2k_arena_take(ctx, n * 96);
   uint8_t* db2 = (uint8_t*)b2k_arena_take(ctx, n * 192);
   uint8_t* dok = (uint8_t*)b2k_arena_take(ctx, n);
+  CK(cudaMemsetAsync(ctx->d_flags, 0, 4, ctx->stream));
   CK(cudaMemcpyAsync(da1, a1, n * 96, cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyAsync(da2, a2, n * 192, cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyAsync(db1, b1, n * 96, cudaMemcpyHostToDevice, ctx->stream));
@@ -73,12 +67,14 @@ int b2k_bls12381_pairing_check(b2k_ctx* ctx, size_t n, const uint8_t* a1, const 
   rc = b2k_bls12381_pairing_check_dev(ctx, n, da1, da2, db1, db2, dok);
   if (rc) return rc;
   CK(cudaMemcpyAsync(ok, dok, n, cudaMemcpyDeviceToHost, ctx->stream));
-  CK(cudaStreamSynchronize(ctx->stream));
-  return B2K_OK;
+  {                                          // a malformed operand already made its own check fail (ok[i] = 0): like the reference's
+    int rc2 = b2k_host::status_finish(ctx);  // ValidatePairing, the call itself reports per-element booleans, not an error
+    return rc2 == B2K_ERR_POINT ? B2K_OK : rc2;
+  }
 }
 
 int b2k_set_pairing_variant(b2k_ctx* ctx, int v) {
-  if (!ctx || v < 0 || v > 5) return B2K_ERR_ARG;
+  if (!ctx || v < 0 || v > 1) return B2K_ERR_ARG;
   ctx->pair_variant = v;
   return B2K_OK;
 }

@@ -152,7 +152,8 @@ static int recover_commit(b2k_ctx* ctx, size_t t, const uint32_t* indices, const
   rc = msm_enqueue<CV>(ctx, t, pl, d_s, d_p, d_o);
   if (rc) return rc;
   CK(cudaMemcpyAsync(out, d_o, CV::OUT_BYTES, cudaMemcpyDeviceToHost, st));
-  CK(cudaMemcpyAsync(ctx->h_flags, ctx->d_flags, 4, cudaMemcpyDeviceToHost, st));
+  rc = status_fetch_async(ctx);
+  if (rc) return rc;
   CK(cudaStreamSynchronize(st));
   if (*ctx->h_flags & 4u) { ctx->err = "duplicate share index"; return B2K_ERR_ARG; }
   return check_flags(ctx);
@@ -171,15 +172,15 @@ static int pubpoly_eval(b2k_ctx* ctx, size_t t, const uint8_t* commits, size_t n
   uint32_t* d_idx = arena_take<uint32_t>(ctx, n);
   uint8_t* d_o = arena_take<uint8_t>(ctx, n * (size_t)CV::IN_BYTES);
   cudaStream_t st = ctx->stream;
+  CK(cudaMemsetAsync(ctx->d_flags, 0, 4, st));
   CK(cudaMemcpyAsync(d_c, commits, t * (size_t)CV::IN_BYTES, cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(d_idx, indices, n * 4, cudaMemcpyHostToDevice, st));
-  k_load_points<CV><<<(unsigned)((t + 255) / 256), 256, 0, st>>>(t, d_c, d_cm);
+  k_load_points<CV><<<(unsigned)((t + 255) / 256), 256, 0, st>>>(t, d_c, d_cm, ctx->d_flags);
   k_pubpoly_eval<CV><<<(unsigned)((n + 127) / 128), 128, 0, st>>>((uint32_t)t, d_cm, (uint32_t)n, d_idx, d_o);
   CK(cudaGetLastError());
   ctx->launches += 2;
   CK(cudaMemcpyAsync(out, d_o, n * (size_t)CV::IN_BYTES, cudaMemcpyDeviceToHost, st));
-  CK(cudaStreamSynchronize(st));
-  return B2K_OK;
+  return status_finish(ctx);
 }
 
 template <class CV>
@@ -199,16 +200,16 @@ static int pubpoly_check(b2k_ctx* ctx, size_t m, size_t t, const uint8_t* commit
   uint8_t* d_s = arena_take<uint8_t>(ctx, mn * 32);
   uint8_t* d_ok = arena_take<uint8_t>(ctx, mn);
   cudaStream_t st = ctx->stream;
+  CK(cudaMemsetAsync(ctx->d_flags, 0, 4, st));
   CK(cudaMemcpyAsync(d_c, commits, mt * (size_t)CV::IN_BYTES, cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(d_idx, indices, mn * 4, cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(d_s, shares, mn * 32, cudaMemcpyHostToDevice, st));
-  k_load_points<CV><<<(unsigned)((mt + 255) / 256), 256, 0, st>>>(mt, d_c, d_cm);
+  k_load_points<CV><<<(unsigned)((mt + 255) / 256), 256, 0, st>>>(mt, d_c, d_cm, ctx->d_flags);
   k_pubpoly_check<CV><<<(unsigned)((mn + 127) / 128), 128, 0, st>>>((uint32_t)m, (uint32_t)t, d_cm, (uint32_t)n, d_idx, d_s, d_ok, ctx->use_glv);
   CK(cudaGetLastError());
   ctx->launches += 2;
   CK(cudaMemcpyAsync(ok, d_ok, mn, cudaMemcpyDeviceToHost, st));
-  CK(cudaStreamSynchronize(st));
-  return B2K_OK;
+  return status_finish(ctx);
 }
 
 extern "C" {

@@ -43,6 +43,11 @@ struct Bn256G1 {
   static constexpr int IN_BYTES = 64;
   static constexpr int OUT_BYTES = 64;
   B2K_D static void load(Affine<F>& r, const uint8_t* p) { bn256_load32(r.x, p); bn256_load32(r.y, p + 32); }
+  B2K_D static bool wire_canonical(const uint8_t*) { return true; }      // bn256 reduces on Unmarshal (pairing/bn256/gfp.go:115-122)
+  B2K_D static void curve_b(F& b) {
+#pragma unroll
+    for (int j = 0; j < 10; j++) b.v[j] = FC::curve_b(j);
+  }
   B2K_D static void store(uint8_t* out, const Affine<F>& p) { bn256_store32(out, p.x); bn256_store32(out + 32, p.y); }
   B2K_D static void store_affine(uint8_t* out, const Affine<F>& p) { store(out, p); }
 };
@@ -55,6 +60,11 @@ struct Bn256G2 {
   static constexpr int IN_BYTES = 128;
   static constexpr int OUT_BYTES = 128;
   // gfP2{x, y} = x*i + y (pairing/bn256/gfp2.go:13-15): imaginary part first on the wire
+  B2K_D static bool wire_canonical(const uint8_t*) { return true; }
+  B2K_D static void curve_b(F& b) {
+#pragma unroll
+    for (int j = 0; j < 10; j++) { b.c0.v[j] = FC::twist_b_c0(j); b.c1.v[j] = FC::twist_b_c1(j); }
+  }
   B2K_D static void load(Affine<F>& r, const uint8_t* p) {
     bn256_load32(r.x.c1, p); bn256_load32(r.x.c0, p + 32);
     bn256_load32(r.y.c1, p + 64); bn256_load32(r.y.c0, p + 96);

@@ -333,6 +333,11 @@ struct Bn254G2 {
   static constexpr int IN_BYTES = 128;
   static constexpr int OUT_BYTES = 128;
   B2K_D static void load(Affine<F>& r, const uint8_t* p) { bn254_g2_load(r, p); }
+  B2K_D static bool wire_canonical(const uint8_t* p) { return wire_coords_canonical<FC, 4>(p); }
+  B2K_D static void curve_b(F& b) {
+#pragma unroll
+    for (int j = 0; j < 8; j++) { b.c0.v[j] = FC::twist_b_c0(j); b.c1.v[j] = FC::twist_b_c1(j); }
+  }
   B2K_D static void store(uint8_t* out, const Affine<F>& p) {
     NFp t;
     fp_from_mont(t, p.x.c1); fp_store_be(out, t);

@@ -33,6 +33,12 @@ struct Bls381G2 {
   static constexpr int IN_BYTES = 192;
   static constexpr int OUT_BYTES = 96;
   B2K_D static void load(Affine<F>& r, const uint8_t* p) { g2_load(r, p); }
+  B2K_D static bool wire_canonical(const uint8_t* p) { return wire_coords_canonical<FC, 4>(p); }
+  B2K_D static void curve_b(F& b) {              // 4 (1 + u)
+    BFp one, four;
+    fp_set_one(one); fp_add(four, one, one); fp_add(four, four, four);
+    b.c0 = four; b.c1 = four;
+  }
   // 96 B ZCash compressed: x.c1 || x.c0, flags in the first byte (kilic/g2.go:118-123)
   B2K_D static void store(uint8_t* out, const Affine<F>& p) {
     if (aff_is_inf(p)) {

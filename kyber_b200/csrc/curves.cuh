@@ -34,6 +34,43 @@ B2K_D bool scalar_in_range(const Scalar256& s) {
   return ptx::subc(0, 0) != 0;
 }
 
+// ---- operand validation ---------------------------------------------------------------------------------------------
+// The reference's UnmarshalBinary is where a malformed point is refused (kilic/g1.go:127-131, pairing/bn254/point.go:146-185);
+// an adapter may hand the engine affine bytes it did not obtain that way, so every entry point that consumes operand points
+// re-checks what is cheap: canonical coordinates (where the reference checks them) and the curve equation y^2 = x^3 + b
+// (3 field products per point).  A violation raises FLAG_POINT (-> B2K_ERR_POINT) and the point is treated as infinity.
+// NOT re-checked: membership in the order-r subgroup (a scalar multiplication per point) -- that stays the job of
+// *_decompress / *_unmarshal_check, exactly as in the reference.
+template <class FC, int NCOORD>
+B2K_D bool wire_coords_canonical(const uint8_t* p) {            // NCOORD big-endian field elements of 4 FC::N bytes each
+  bool ok = true;
+#pragma unroll
+  for (int c = 0; c < NCOORD; c++) {
+    Fp<FC> t;
+    fp_load_be(t, p + 4 * FC::N * c);
+    ok = ok && fp_canon_lt_mod(t);
+  }
+  return ok;
+}
+template <class CV>
+B2K_D bool aff_on_curve(const Affine<typename CV::F>& p) {       // infinity (0, 0) counts as valid
+  if (aff_is_inf(p)) return true;
+  typename CV::F y2, x3, b;
+  f_sqr(y2, p.y);
+  f_sqr(x3, p.x); f_mul(x3, x3, p.x);
+  CV::curve_b(b);
+  f_add(x3, x3, b);
+  return f_eq(y2, x3);
+}
+// operand bytes -> Montgomery affine; false (and infinity) when the operand is malformed
+template <class CV>
+B2K_D bool load_checked(Affine<typename CV::F>& r, const uint8_t* w) {
+  CV::load(r, w);
+  const bool ok = CV::wire_canonical(w) && aff_on_curve<CV>(r);
+  if (!ok) aff_set_inf(r);
+  return ok;
+}
+
 struct Bls381G1 {
   using FC = Bls381Fp;
   using F = Fp<Bls381Fp>;
@@ -41,6 +78,11 @@ struct Bls381G1 {
   static constexpr int SCALAR_BITS = 255;
   static constexpr int IN_BYTES = 96;
   static constexpr int OUT_BYTES = 48;
+  B2K_D static bool wire_canonical(const uint8_t* p) { return wire_coords_canonical<FC, 2>(p); }
+  B2K_D static void curve_b(F& b) {
+#pragma unroll
+    for (int j = 0; j < 12; j++) b.v[j] = FC::curve_b(j);
+  }
 
   // operand bytes -> Montgomery affine
   B2K_D static void load(Affine<F>& r, const uint8_t* p) {
@@ -84,6 +126,11 @@ struct Bn254G1 {
   static constexpr int SCALAR_BITS = 254;
   static constexpr int IN_BYTES = 64;
   static constexpr int OUT_BYTES = 64;
+  B2K_D static bool wire_canonical(const uint8_t* p) { return wire_coords_canonical<FC, 2>(p); }   // gfP.Unmarshal, pairing/bn254/gfp.go:101-119
+  B2K_D static void curve_b(F& b) {
+#pragma unroll
+    for (int j = 0; j < 8; j++) b.v[j] = FC::curve_b(j);
+  }
 
   B2K_D static void load(Affine<F>& r, const uint8_t* p) {
     F x, y;

@@ -93,6 +93,139 @@ B2K_D void mont_step(uint32_t* lo, uint32_t* hi, const uint32_t* a, uint32_t b) 
   hi[N - 1] = ptx::addc(hi[N - 1], 0);
 }
 
+// ---- wide (unreduced) products and the stand-alone Montgomery reduction ---------------------------------------------
+// Used by fp_sqr (N(N+1)/2 products instead of N^2 before the reduction) and by the lazily reduced Fp2 product of
+// tower.cuh (three wide products, two reductions).  Same even/odd idea as above without the sliding: E[k] sits at limb k,
+// O[k] at limb k + 1, 64-bit slots start at even indices of either array, so every 32x32 product is one multiply-add into
+// one slot and a row is two carry chains.  Rows are issued in an order in which the limb right above a chain's last slot
+// has only ever received carries (chain ends never move down), so one add absorbs the chain's carry-out.
+
+// acc[s + 2t .. s + 2t + 1] += a[j0 + 2t] * b for t < CNT as one carry chain; carry-out into acc[s + 2 CNT] if that is < LIM
+template <int CNT, int LIM>
+B2K_D void chain_mad(uint32_t* acc, int s, const uint32_t* a, int j0, uint32_t b) {
+  if (CNT <= 0) return;
+  acc[s] = ptx::mad_lo_cc(a[j0], b, acc[s]);
+  acc[s + 1] = ptx::madc_hi_cc(a[j0], b, acc[s + 1]);
+#pragma unroll
+  for (int t = 1; t < CNT; t++) {
+    acc[s + 2 * t] = ptx::madc_lo_cc(a[j0 + 2 * t], b, acc[s + 2 * t]);
+    acc[s + 2 * t + 1] = ptx::madc_hi_cc(a[j0 + 2 * t], b, acc[s + 2 * t + 1]);
+  }
+  if (s + 2 * CNT < LIM) acc[s + 2 * CNT] = ptx::addc(acc[s + 2 * CNT], 0);
+  else ptx::addc(0, 0);                      // (no carry by bound; consumes CC so that nothing stale is left behind)
+}
+
+// t[0..2N) = E + (O << 32)
+template <int N>
+B2K_D void wide_merge(uint32_t* t, const uint32_t* E, const uint32_t* O) {
+  t[0] = E[0];
+  t[1] = ptx::add_cc(E[1], O[0]);
+#pragma unroll
+  for (int k = 2; k < 2 * N - 1; k++) t[k] = ptx::addc_cc(E[k], O[k - 1]);
+  t[2 * N - 1] = ptx::addc(E[2 * N - 1], O[2 * N - 2]);
+}
+
+// t[0..2N) = a * b   (N^2 multiply-adds)
+template <int N>
+B2K_D void wide_mul(uint32_t* t, const uint32_t* a, const uint32_t* b) {
+  uint32_t E[2 * N], O[2 * N];
+#pragma unroll
+  for (int k = 0; k < 2 * N; k++) { E[k] = 0; O[k] = 0; }
+#pragma unroll
+  for (int i = 0; i < N; i += 2) {
+    chain_mad<N / 2, 2 * N>(E, i, a, 0, b[i]);          // a_even * b_i   at limbs i + j
+    chain_mad<N / 2, 2 * N>(O, i, a, 1, b[i]);          // a_odd  * b_i   at limbs i + j = (i + j - 1) + 1
+    chain_mad<N / 2, 2 * N>(O, i, a, 0, b[i + 1]);      // a_even * b_i+1 at limbs i + 1 + j
+    chain_mad<N / 2, 2 * N>(E, i + 2, a, 1, b[i + 1]);  // a_odd  * b_i+1 at limbs i + 1 + j (even)
+  }
+  wide_merge<N>(t, E, O);
+}
+
+// rows I and I + 1 of the off-diagonal triangle: row r = a_r * a_j, j = r+1, r+3, ... lands on odd limbs r + j -> O[r + j - 1],
+// j = r+2, r+4, ... on even limbs -> E[r + j]   (template recursion: the chain lengths are compile-time)
+template <int N, int I>
+B2K_D void wide_sqr_rows(uint32_t* E, uint32_t* O, const uint32_t* a) {
+  if constexpr (I + 1 < N) {
+    chain_mad<(N - I) / 2, 2 * N>(O, 2 * I, a, I + 1, a[I]);
+    chain_mad<(N - 1 - I) / 2, 2 * N>(E, 2 * I + 2, a, I + 2, a[I]);
+    chain_mad<(N - 1 - I) / 2, 2 * N>(O, 2 * I + 2, a, I + 2, a[I + 1]);
+    chain_mad<(N - 2 - I) / 2, 2 * N>(E, 2 * I + 4, a, I + 3, a[I + 1]);
+    wide_sqr_rows<N, I + 2>(E, O, a);
+  }
+}
+
+// t[0..2N) = a^2   (N(N-1)/2 off-diagonal multiply-adds, doubled by a one-bit shift, + N diagonal ones)
+template <int N>
+B2K_D void wide_sqr(uint32_t* t, const uint32_t* a) {
+  uint32_t E[2 * N], O[2 * N], m[2 * N];
+#pragma unroll
+  for (int k = 0; k < 2 * N; k++) { E[k] = 0; O[k] = 0; }
+  wide_sqr_rows<N, 0>(E, O, a);
+  wide_merge<N>(m, E, O);
+  // t = 2 m + sum_i a_i^2 2^(64 i)
+  t[0] = ptx::mad_lo_cc(a[0], a[0], 0);
+  t[1] = ptx::madc_hi_cc(a[0], a[0], m[1] << 1);      // m[0] = 0 (no product lands on limb 0)
+#pragma unroll
+  for (int i = 1; i < N; i++) {
+    t[2 * i] = ptx::madc_lo_cc(a[i], a[i], (m[2 * i] << 1) | (m[2 * i - 1] >> 31));
+    t[2 * i + 1] = ptx::madc_hi_cc(a[i], a[i], (m[2 * i + 1] << 1) | (m[2 * i] >> 31));
+  }
+  ptx::addc(0, 0);
+}
+
+// hi[j..j+1] = MOD[1 + j] * m + hi[j+2..j+3] with carry-in from CC (the /2^32 role swap fused into the odd modulus row)
+template <class C>
+B2K_D void row_madc_shift_mod(uint32_t* acc, uint32_t m) {
+  constexpr int N = C::N;
+#pragma unroll
+  for (int j = 0; j < N - 2; j += 2) {
+    acc[j] = ptx::madc_lo_cc(C::mod(1 + j), m, acc[j + 2]);
+    acc[j + 1] = ptx::madc_hi_cc(C::mod(1 + j), m, acc[j + 3]);
+  }
+  acc[N - 2] = ptx::madc_lo_cc(C::mod(N - 1), m, 0);
+  acc[N - 1] = ptx::madc_hi(C::mod(N - 1), m, 0);
+}
+
+template <class C, bool FIRST>
+B2K_D void redc_step(uint32_t* lo, uint32_t* hi) {
+  constexpr int N = C::N;
+  if (FIRST) {
+    const uint32_t m = lo[0] * C::M0;
+#pragma unroll
+    for (int j = 0; j < N; j += 2) { hi[j] = ptx::mul_lo(C::mod(1 + j), m); hi[j + 1] = ptx::mul_hi(C::mod(1 + j), m); }
+    row_mad_mod<C, 0>(lo, m);
+  } else {
+    lo[0] = ptx::add_cc(lo[0], hi[1]);      // the stray limb; its carry enters the odd row below
+    const uint32_t m = lo[0] * C::M0;
+    row_madc_shift_mod<C>(hi, m);
+    row_mad_mod<C, 0>(lo, m);
+  }
+  hi[N - 1] = ptx::addc(hi[N - 1], 0);
+}
+
+// r[0..N) = t / 2^(32N) mod p, in [0, 2p) for t < p 2^(32N)   (N^2 multiply-adds; caller finishes with fp_reduce_once)
+template <class C>
+B2K_D void redc_wide(uint32_t* r, const uint32_t* t) {
+  constexpr int N = C::N;
+  uint32_t ev[N], od[N];
+#pragma unroll
+  for (int j = 0; j < N; j++) ev[j] = t[j];
+#pragma unroll
+  for (int i = 0; i < N; i += 2) {
+    if (i == 0) redc_step<C, true>(ev, od);
+    else redc_step<C, false>(ev, od);
+    redc_step<C, false>(od, ev);
+  }
+  ev[0] = ptx::add_cc(ev[0], od[1]);        // REDC(t mod 2^(32N)) <= p ...
+#pragma unroll
+  for (int j = 1; j < N - 1; j++) ev[j] = ptx::addc_cc(ev[j], od[j + 1]);
+  ev[N - 1] = ptx::addc(ev[N - 1], 0);
+  r[0] = ptx::add_cc(ev[0], t[N]);          // ... + floor(t / 2^(32N))
+#pragma unroll
+  for (int j = 1; j < N - 1; j++) r[j] = ptx::addc_cc(ev[j], t[N + j]);
+  r[N - 1] = ptx::addc(ev[N - 1], t[2 * N - 1]);
+}
+
 }  // namespace detail
 
 // ---- comparison / conditional subtraction ---------------------------------------------------
@@ -132,15 +265,24 @@ B2K_D void fp_mul(Fp<C>& r, const Fp<C>& a, const Fp<C>& b) {
   for (int j = 0; j < N; j++) r.v[j] = ev[j];
 }
 
+// a^2: N(N+1)/2 + N^2 multiply-adds instead of 2 N^2 (BLS12-381: 222 instead of 288)
 template <class C>
-B2K_D void fp_sqr(Fp<C>& r, const Fp<C>& a) { fp_mul(r, a, a); }
+B2K_D void fp_sqr(Fp<C>& r, const Fp<C>& a) {
+  constexpr int N = C::N;
+  uint32_t t[2 * N], u[N];
+  detail::wide_sqr<N>(t, a.v);
+  detail::redc_wide<C>(u, t);
+  fp_reduce_once<C>(u);
+#pragma unroll
+  for (int j = 0; j < N; j++) r.v[j] = u[j];
+}
 
 // out-of-line copies for code that is too large to inline a 300-instruction product at every use
 // (towers, exponentiations); operands then travel through local memory.
 template <class C>
 B2K_NI void fp_mul_c(Fp<C>& r, const Fp<C>& a, const Fp<C>& b) { fp_mul(r, a, b); }
 template <class C>
-B2K_NI void fp_sqr_c(Fp<C>& r, const Fp<C>& a) { fp_mul(r, a, a); }
+B2K_NI void fp_sqr_c(Fp<C>& r, const Fp<C>& a) { fp_sqr(r, a); }
 
 template <class C>
 B2K_D void fp_add(Fp<C>& r, const Fp<C>& a, const Fp<C>& b) {

@@ -7,16 +7,16 @@
 namespace b2k {
 
 // error flag bits written by kernels
-enum : uint32_t { FLAG_SCALAR_RANGE = 1u, FLAG_POINT = 2u };
+enum : uint32_t { FLAG_SCALAR_RANGE = 1u, FLAG_POINT = 2u, FLAG_COMM_TIMEOUT = 32u };   // (4u: duplicate share index, b2k_share.cu)
 
 // ---- operand conversion: wire bytes -> Montgomery affine (AoS, one point = 2*N limbs) -----------
 template <class CV>
 __global__ void __launch_bounds__(256) k_load_points(size_t n, const uint8_t* __restrict__ wire,
-                                                     Affine<typename CV::F>* __restrict__ pts) {
+                                                     Affine<typename CV::F>* __restrict__ pts, uint32_t* flags) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   Affine<typename CV::F> p;
-  CV::load(p, wire + (size_t)CV::IN_BYTES * i);
+  if (!load_checked<CV>(p, wire + (size_t)CV::IN_BYTES * i)) atomicOr(flags, FLAG_POINT);
   pts[i] = p;
 }
 
@@ -39,7 +39,7 @@ static __global__ void __launch_bounds__(256) k_glv_prepare_bls381(size_t n, con
   GlvSplit sp;
   glv_split_bls381(sp, k);
   Affine<F> p0, p, e;
-  Bls381G1::load(p0, wire + (size_t)Bls381G1::IN_BYTES * i);
+  if (!load_checked<Bls381G1>(p0, wire + (size_t)Bls381G1::IN_BYTES * i)) atomicOr(flags, FLAG_POINT);
   glv_points_bls381(p, e, p0, sp);
   pts[i] = p;
   pts[n + i] = e;
@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(128, MINB) k_mul_batch(size_t n, const uint8_t
     for (int j = 0; j < 8; j++) k.v[j] = 0;
   }
   Affine<typename CV::F> p;
-  CV::load(p, wire + (size_t)CV::IN_BYTES * i);
+  if (!load_checked<CV>(p, wire + (size_t)CV::IN_BYTES * i)) atomicOr(flags, FLAG_POINT);
   Jac<typename CV::F> r;
   if constexpr (MulGlv<CV>::enabled) {
     if (use_glv) scalar_mul_glv_bls381(r, k, p, InvBingcd{});

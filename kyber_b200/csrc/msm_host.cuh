@@ -107,7 +107,26 @@ inline int check_flags(b2k_ctx* ctx) {
   uint32_t f = *ctx->h_flags;
   if (f & FLAG_SCALAR_RANGE) { ctx->err = "scalar not below the group order"; return B2K_ERR_SCALAR_RANGE; }
   if (f & FLAG_POINT) { ctx->err = "malformed operand point"; return B2K_ERR_POINT; }
+  if (f & FLAG_COMM_TIMEOUT) { ctx->err = "multi-GPU exchange: a peer rank did not arrive within 10 s"; return B2K_ERR_COMM; }
   return B2K_OK;
+}
+
+// host-buffer entry points: the device status word is cleared in front of the call's work, fetched AND cleared behind it
+// (a failed call must not leave a stale bit for a later *_dev sequence + b2k_wait)
+inline int status_begin(b2k_ctx* ctx) {
+  CK(cudaMemsetAsync(ctx->d_flags, 0, 4, ctx->stream));
+  return B2K_OK;
+}
+inline int status_fetch_async(b2k_ctx* ctx) {
+  CK(cudaMemcpyAsync(ctx->h_flags, ctx->d_flags, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemsetAsync(ctx->d_flags, 0, 4, ctx->stream));
+  return B2K_OK;
+}
+inline int status_finish(b2k_ctx* ctx) {
+  int rc = status_fetch_async(ctx);
+  if (rc) return rc;
+  CK(cudaStreamSynchronize(ctx->stream));
+  return check_flags(ctx);
 }
 
 // ---- GLV front end: which curves have it, and the problem the pipeline then sees ----------------------------------
@@ -286,9 +305,9 @@ int msm_enqueue(b2k_ctx* ctx, size_t n_in, const MsmPlan& pl, const uint8_t* d_s
   CK(cudaMemsetAsync(counts, 0, (total + 1) * 4, st));
   if constexpr (GlvTraits<CV>::enabled) {
     if (glv) k_glv_prepare_bls381<<<(unsigned)((n_in + 255) / 256), 256, 0, st>>>(n_in, d_scalars_in, d_points, pts, vsc, ctx->d_flags);
-    else k_load_points<CV><<<gb_n, 256, 0, st>>>(n, d_points, pts);
+    else k_load_points<CV><<<gb_n, 256, 0, st>>>(n, d_points, pts, ctx->d_flags);
   } else {
-    k_load_points<CV><<<gb_n, 256, 0, st>>>(n, d_points, pts);
+    k_load_points<CV><<<gb_n, 256, 0, st>>>(n, d_points, pts, ctx->d_flags);
   }
   nl++;
   CK(cudaEventRecord(ctx->ev[1], st));
@@ -463,6 +482,32 @@ int msm_buckets_dev(b2k_ctx* ctx, size_t n, const void* d_scalars, const void* d
   return msm_enqueue<CV>(ctx, n, pl, (const uint8_t*)d_scalars, (const uint8_t*)d_points, nullptr, 0, reinterpret_cast<X*>(d_buckets));
 }
 
+// The same from HOST buffers (page-locked for the copies to overlap other contexts' kernels): the rank's shard is staged in the
+// context's arena and the whole sequence is only enqueued.  Used by the sharded entry points of b2k_multi.cu.
+template <class CV>
+int msm_buckets_host(b2k_ctx* ctx, size_t n, const uint8_t* scalars, const uint8_t* points, void* d_buckets, size_t cap_bytes, int* plan_out) {
+  using X = Xyzz<typename CV::F>;
+  if (!ctx || !scalars || !points || !d_buckets || n == 0 || n >= (size_t(1) << 31)) {
+    if (ctx) ctx->err = "bad argument";
+    return B2K_ERR_ARG;
+  }
+  CK(cudaSetDevice(ctx->device));
+  MsmPlan pl = msm_plan<CV>(ctx, n);
+  if (plan_out) { plan_out[0] = pl.c; plan_out[1] = pl.W; plan_out[2] = pl.nb; plan_out[3] = (int)sizeof(X); }
+  if (cap_bytes < (size_t)pl.W * pl.nb * sizeof(X) || (reinterpret_cast<uintptr_t>(d_buckets) & 15)) {
+    ctx->err = "bucket buffer too small or not 16-byte aligned";
+    return B2K_ERR_ARG;
+  }
+  const size_t in_bytes = pad256(n * 32) + pad256(n * (size_t)CV::IN_BYTES) + 256;
+  int rc = arena_reserve(ctx, msm_scratch_bytes<CV>(ctx, msm_virtual_n<CV>(ctx, n), pl) + in_bytes);
+  if (rc) return rc;
+  auto* d_s = arena_take<uint8_t>(ctx, n * 32);
+  auto* d_p = arena_take<uint8_t>(ctx, n * (size_t)CV::IN_BYTES);
+  CK(cudaMemcpyAsync(d_s, scalars, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(d_p, points, n * (size_t)CV::IN_BYTES, cudaMemcpyHostToDevice, ctx->stream));
+  return msm_enqueue<CV>(ctx, n, pl, d_s, d_p, nullptr, 0, reinterpret_cast<X*>(d_buckets));
+}
+
 // bucket-count query for sizing the exchange buffers before the first call
 template <class CV>
 int msm_bucket_plan(b2k_ctx* ctx, size_t n, int* plan_out) {
@@ -557,10 +602,8 @@ int msm_host(b2k_ctx* ctx, size_t n, const uint8_t* scalars, const uint8_t* poin
   rc = msm_enqueue<CV>(ctx, n, pl, d_s, d_p, d_o, affine_out);
   if (rc) return rc;
   CK(cudaMemcpyAsync(out, d_o, affine_out ? CV::IN_BYTES : CV::OUT_BYTES, cudaMemcpyDeviceToHost, ctx->stream));
-  CK(cudaMemcpyAsync(ctx->h_flags, ctx->d_flags, 4, cudaMemcpyDeviceToHost, ctx->stream));
-  if (!wait) return B2K_OK;
-  CK(cudaStreamSynchronize(ctx->stream));
-  return check_flags(ctx);
+  if (!wait) { CK(cudaMemcpyAsync(ctx->h_flags, ctx->d_flags, 4, cudaMemcpyDeviceToHost, ctx->stream)); return B2K_OK; }   // b2k_wait fetches + clears
+  return status_finish(ctx);
 }
 
 // Also the status query of the *_dev entry points, which only enqueue: the device status word (scalar range, malformed
@@ -612,9 +655,7 @@ int mul_batch_host(b2k_ctx* ctx, size_t n, const uint8_t* scalars, const uint8_t
   rc = mul_batch_dev<CV, AFF>(ctx, n, d_s, d_p, d_o);
   if (rc) return rc;
   CK(cudaMemcpyAsync(out, d_o, n * ob, cudaMemcpyDeviceToHost, ctx->stream));
-  CK(cudaMemcpyAsync(ctx->h_flags, ctx->d_flags, 4, cudaMemcpyDeviceToHost, ctx->stream));
-  CK(cudaStreamSynchronize(ctx->stream));
-  return check_flags(ctx);
+  return status_finish(ctx);
 }
 
 

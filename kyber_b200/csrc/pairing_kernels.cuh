@@ -2,6 +2,8 @@
 #pragma once
 #include "pairing.cuh"
 #include "curves.cuh"
+#include "codec.cuh"
+#include "kernels.cuh"
 #include "b2k_ctx.h"
 
 namespace b2k {
@@ -9,13 +11,14 @@ namespace b2k {
 // gt[i] = e(g1[i], g2[i])           replaces n x Suite.Pair (kilic/suite.go:70-75)
 template <int BLOCK, int MINB>
 static __global__ void __launch_bounds__(BLOCK, MINB) k_bls_pair(size_t n, const uint8_t* __restrict__ g1, const uint8_t* __restrict__ g2,
-                                                  uint8_t* __restrict__ gt) {
+                                                  uint8_t* __restrict__ gt, uint32_t* flags) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   Affine<BFp> P;
   Affine<BFp2> Q;
-  Bls381G1::load(P, g1 + 96 * i);
-  g2_load(Q, g2 + 192 * i);
+  bool good = load_checked<Bls381G1>(P, g1 + 96 * i);
+  good = load_checked<Bls381G2>(Q, g2 + 192 * i) && good;       // a malformed operand counts as infinity: e = 1, FLAG_POINT
+  if (!good) atomicOr(flags, FLAG_POINT);
   BFp12 f, e;
   miller_loop<1>(f, &P, &Q);
   final_exponentiation(e, f);
@@ -29,16 +32,17 @@ static __global__ void __launch_bounds__(BLOCK, MINB) k_bls_pairing_check(size_t
                                                            const uint8_t* __restrict__ a2,
                                                            const uint8_t* __restrict__ b1,
                                                            const uint8_t* __restrict__ b2, uint8_t* __restrict__ ok,
-                                                           int b2_broadcast, const uint8_t* __restrict__ pre_ok) {
+                                                           int b2_broadcast, const uint8_t* __restrict__ pre_ok, uint32_t* flags) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   if (pre_ok && !pre_ok[i]) { ok[i] = 0; return; }       // an operand failed UnmarshalBinary upstream
   Affine<BFp> P[2];
   Affine<BFp2> Q[2];
-  Bls381G1::load(P[0], a1 + 96 * i);
-  g2_load(Q[0], a2 + 192 * i);
-  Bls381G1::load(P[1], b1 + ((b2_broadcast & 2) ? 0 : 96 * i));      // bit 1: b1 is one shared operand
-  g2_load(Q[1], b2 + ((b2_broadcast & 1) ? 0 : 192 * i));           // bit 0: b2 is one shared operand
+  bool good = load_checked<Bls381G1>(P[0], a1 + 96 * i);
+  good = load_checked<Bls381G2>(Q[0], a2 + 192 * i) && good;
+  good = load_checked<Bls381G1>(P[1], b1 + ((b2_broadcast & 2) ? 0 : 96 * i)) && good;      // bit 1: b1 is one shared operand
+  good = load_checked<Bls381G2>(Q[1], b2 + ((b2_broadcast & 1) ? 0 : 192 * i)) && good;     // bit 0: b2 is one shared operand
+  if (!good) { atomicOr(flags, FLAG_POINT); ok[i] = 0; return; }   // malformed operand (off the curve / coordinate >= p): the check fails
   fp_neg(P[1].y, P[1].y);
   BFp12 f, e;
   miller_loop<2>(f, P, Q);
@@ -48,22 +52,22 @@ static __global__ void __launch_bounds__(BLOCK, MINB) k_bls_pairing_check(size_t
 
 
 // launch-bound variants: (threads per block, min blocks per SM) -> register cap 65536 / (threads * blocks)
-#define B2K_PAIR_VARIANTS(X) X(0, 64, 4) X(1, 64, 8) X(2, 128, 4) X(3, 32, 16) X(4, 64, 6) X(5, 128, 3)
+#define B2K_PAIR_VARIANTS(X) X(0, 64, 4) X(1, 64, 8)     /* round 1 swept six shapes (profiles/r01*): (64, 4) won, (64, 8) kept for A/B */
 inline void launch_pair(const b2k_ctx* ctx, size_t n, const uint8_t* g1, const uint8_t* g2, uint8_t* gt) {
   switch (ctx->pair_variant) {
-#define X(ID, B, M) case ID: k_bls_pair<B, M><<<(unsigned)((n + B - 1) / B), B, 0, ctx->stream>>>(n, g1, g2, gt); break;
+#define X(ID, B, M) case ID: k_bls_pair<B, M><<<(unsigned)((n + B - 1) / B), B, 0, ctx->stream>>>(n, g1, g2, gt, ctx->d_flags); break;
     B2K_PAIR_VARIANTS(X)
 #undef X
-    default: k_bls_pair<64, 4><<<(unsigned)((n + 63) / 64), 64, 0, ctx->stream>>>(n, g1, g2, gt);
+    default: k_bls_pair<64, 4><<<(unsigned)((n + 63) / 64), 64, 0, ctx->stream>>>(n, g1, g2, gt, ctx->d_flags);
   }
 }
 inline void launch_pairing_check(const b2k_ctx* ctx, size_t n, const uint8_t* a1, const uint8_t* a2, const uint8_t* b1,
                                  const uint8_t* b2, uint8_t* ok, int b2_broadcast, const uint8_t* pre_ok) {
   switch (ctx->pair_variant) {
-#define X(ID, B, M) case ID: k_bls_pairing_check<B, M><<<(unsigned)((n + B - 1) / B), B, 0, ctx->stream>>>(n, a1, a2, b1, b2, ok, b2_broadcast, pre_ok); break;
+#define X(ID, B, M) case ID: k_bls_pairing_check<B, M><<<(unsigned)((n + B - 1) / B), B, 0, ctx->stream>>>(n, a1, a2, b1, b2, ok, b2_broadcast, pre_ok, ctx->d_flags); break;
     B2K_PAIR_VARIANTS(X)
 #undef X
-    default: k_bls_pairing_check<64, 4><<<(unsigned)((n + 63) / 64), 64, 0, ctx->stream>>>(n, a1, a2, b1, b2, ok, b2_broadcast, pre_ok);
+    default: k_bls_pairing_check<64, 4><<<(unsigned)((n + 63) / 64), 64, 0, ctx->stream>>>(n, a1, a2, b1, b2, ok, b2_broadcast, pre_ok, ctx->d_flags);
   }
 }
 

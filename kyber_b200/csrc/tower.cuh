@@ -45,6 +45,55 @@ B2K_NI void fp2_mul(Fp2<C>& r, const Fp2<C>& a, const Fp2<C>& b) {
   r.c0 = t0;
 }
 
+// Karatsuba with lazy reduction: three WIDE products (fp.cuh: detail::wide_mul, N^2 multiply-adds each) and only two
+// Montgomery reductions -- 5 N^2 multiply-adds instead of the 6 N^2 of three reduced products.
+//   c1 = (a0 + a1)(b0 + b1) - a0 b0 - a1 b1   (>= 0 as integers; the sums are left unreduced: 2p < 2^(32N), 4p^2 < p 2^(32N))
+//   c0 = a0 b0 - a1 b1                        (+ p 2^(32N) when negative: adds p to the upper half)
+// Out of line; the products are inlined so that the operands are loaded once and every intermediate stays in registers.
+// Measured on B200 (profiles/r02a_fp2_lazy_ab.txt): the one-thread-per-pairing kernel is LATENCY-bound (2 warps per scheduler), where
+// trading one reduction for ~100 add/sub instructions loses 7 %; kept for throughput-bound callers and tested in the emulation.
+template <class C>
+B2K_NI void fp2_mul_lazy(Fp2<C>& r, const Fp2<C>& a, const Fp2<C>& b) {
+  constexpr int N = C::N;
+  uint32_t t0[2 * N], t1[2 * N], s[2 * N], sa[N], sb[N];
+  detail::wide_mul<N>(t0, a.c0.v, b.c0.v);
+  detail::wide_mul<N>(t1, a.c1.v, b.c1.v);
+  sa[0] = ptx::add_cc(a.c0.v[0], a.c1.v[0]);
+#pragma unroll
+  for (int j = 1; j < N - 1; j++) sa[j] = ptx::addc_cc(a.c0.v[j], a.c1.v[j]);
+  sa[N - 1] = ptx::addc(a.c0.v[N - 1], a.c1.v[N - 1]);
+  sb[0] = ptx::add_cc(b.c0.v[0], b.c1.v[0]);
+#pragma unroll
+  for (int j = 1; j < N - 1; j++) sb[j] = ptx::addc_cc(b.c0.v[j], b.c1.v[j]);
+  sb[N - 1] = ptx::addc(b.c0.v[N - 1], b.c1.v[N - 1]);
+  detail::wide_mul<N>(s, sa, sb);
+  s[0] = ptx::sub_cc(s[0], t0[0]);
+#pragma unroll
+  for (int j = 1; j < 2 * N - 1; j++) s[j] = ptx::subc_cc(s[j], t0[j]);
+  s[2 * N - 1] = ptx::subc(s[2 * N - 1], t0[2 * N - 1]);
+  s[0] = ptx::sub_cc(s[0], t1[0]);
+#pragma unroll
+  for (int j = 1; j < 2 * N - 1; j++) s[j] = ptx::subc_cc(s[j], t1[j]);
+  s[2 * N - 1] = ptx::subc(s[2 * N - 1], t1[2 * N - 1]);
+  t0[0] = ptx::sub_cc(t0[0], t1[0]);
+#pragma unroll
+  for (int j = 1; j < 2 * N; j++) t0[j] = ptx::subc_cc(t0[j], t1[j]);
+  const uint32_t borrow = ptx::subc(0, 0);                  // all-ones if a0 b0 < a1 b1
+  t0[N] = ptx::add_cc(t0[N], C::mod(0) & borrow);
+#pragma unroll
+  for (int j = 1; j < N - 1; j++) t0[N + j] = ptx::addc_cc(t0[N + j], C::mod(j) & borrow);
+  t0[2 * N - 1] = ptx::addc(t0[2 * N - 1], C::mod(N - 1) & borrow);
+  uint32_t u[N];
+  detail::redc_wide<C>(u, s);
+  fp_reduce_once<C>(u);
+#pragma unroll
+  for (int j = 0; j < N; j++) r.c1.v[j] = u[j];
+  detail::redc_wide<C>(u, t0);
+  fp_reduce_once<C>(u);
+#pragma unroll
+  for (int j = 0; j < N; j++) r.c0.v[j] = u[j];
+}
+
 // complex squaring: 2 base multiplications (same register-resident structure)
 template <class C>
 B2K_NI void fp2_sqr(Fp2<C>& r, const Fp2<C>& a) {

@@ -3,6 +3,10 @@ import sys
 
 import pytest
 
+# the single-device tests of the sharded MSM run up to 8 ranks (contexts) on one GPU, each spinning on flags another one sets:
+# every stream needs its own hardware queue (default 8 are shared round-robin), set before CUDA initialises
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)

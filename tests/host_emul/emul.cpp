@@ -1,6 +1,7 @@
 // Host emulation of the device limb code (test infrastructure only; never loaded by the product).
 #include "../../kyber_b200/csrc/constants.cuh"
 #include "../../kyber_b200/csrc/fp.cuh"
+#include "../../kyber_b200/csrc/tower.cuh"
 using namespace b2k;
 extern "C" {
 #define FIELD_API(name, C)                                                                        \
@@ -13,6 +14,14 @@ extern "C" {
   void emul_##name##_sub(const uint32_t* a, const uint32_t* b, uint32_t* r) {                      \
     Fp<C> x, y, z; for (int i = 0; i < C::N; i++) { x.v[i] = a[i]; y.v[i] = b[i]; }                \
     fp_sub(z, x, y); for (int i = 0; i < C::N; i++) r[i] = z.v[i]; }                               \
+  void emul_##name##_sqr(const uint32_t* a, uint32_t* r) {                                         \
+    Fp<C> x, z; for (int i = 0; i < C::N; i++) x.v[i] = a[i];                                      \
+    fp_sqr(z, x); for (int i = 0; i < C::N; i++) r[i] = z.v[i]; }                                  \
+  void emul_##name##_wide_mul(const uint32_t* a, const uint32_t* b, uint32_t* t) {                 \
+    detail::wide_mul<C::N>(t, a, b); }                                                             \
+  void emul_##name##_wide_sqr(const uint32_t* a, uint32_t* t) { detail::wide_sqr<C::N>(t, a); }    \
+  void emul_##name##_redc(const uint32_t* t, uint32_t* r) {                                        \
+    detail::redc_wide<C>(r, t); fp_reduce_once<C>(r); }                                            \
   void emul_##name##_neg(const uint32_t* a, uint32_t* r) {                                         \
     Fp<C> x, z; for (int i = 0; i < C::N; i++) x.v[i] = a[i];                                      \
     fp_neg(z, x); for (int i = 0; i < C::N; i++) r[i] = z.v[i]; }                                  \
@@ -28,9 +37,20 @@ extern "C" {
   void emul_##name##_from_mont(const uint32_t* a, uint32_t* r) {                                   \
     Fp<C> x, z; for (int i = 0; i < C::N; i++) x.v[i] = a[i];                                      \
     fp_from_mont(z, x); for (int i = 0; i < C::N; i++) r[i] = z.v[i]; }
+#define FP2_LAZY_API(name, C)                                                                      \
+  void emul_##name##_fp2_mul_pair(const uint32_t* a, const uint32_t* b, uint32_t* r, uint32_t* rl) { \
+    Fp2<C> x, y, z, zl;                                                                            \
+    for (int i = 0; i < C::N; i++) { x.c0.v[i] = a[i]; x.c1.v[i] = a[C::N + i]; y.c0.v[i] = b[i]; y.c1.v[i] = b[C::N + i]; } \
+    fp2_mul(z, x, y); fp2_mul_lazy(zl, x, y);                                                      \
+    for (int i = 0; i < C::N; i++) { r[i] = z.c0.v[i]; r[C::N + i] = z.c1.v[i]; rl[i] = zl.c0.v[i]; rl[C::N + i] = zl.c1.v[i]; } }
+FP2_LAZY_API(fp381, Bls381Fp)
+FP2_LAZY_API(fp254, Bn254Fp)
+FP2_LAZY_API(fp256, Bn256Fp)
 FIELD_API(fp381, Bls381Fp)
 FIELD_API(fr381, Bls381Fr)
 FIELD_API(fp254, Bn254Fp)
+FIELD_API(fp256, Bn256Fp)
+FIELD_API(fp25519, Ed25519Fp)
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -63,7 +63,9 @@ def test_device_field_code_under_host_emulation(emul):
     rng = random.Random(1)
     fields = (("fp381", 0x1a0111ea397fe69a4b1ba7b6434bacd764774b84f38512bf6730d2a0f6b0f6241eabfffeb153ffffb9feffffffffaaab, 12),
               ("fr381", 0x73eda753299d7d483339d80809a1d80553bda402fffe5bfeffffffff00000001, 8),
-              ("fp254", 21888242871839275222246405745257275088696311157297823662689037894645226208583, 8))
+              ("fp254", 21888242871839275222246405745257275088696311157297823662689037894645226208583, 8),
+              ("fp256", 65000549695646603732796438742359905742825358107623003571877145026864184071783, 10),
+              ("fp25519", 2**255 - 19, 8))
     for name, p, n in fields:
         R = 1 << (32 * n)
         Ri = pow(R, -1, p)
@@ -80,10 +82,35 @@ def test_device_field_code_under_host_emulation(emul):
             out = (ctypes.c_uint32 * n)()
             getattr(emul, f"emul_{name}_mul")(lim(a), lim(b), out)
             assert val(out) == a * b * Ri % p
+            getattr(emul, f"emul_{name}_sqr")(lim(a), out)                          # dedicated squaring (wide_sqr + redc_wide)
+            assert val(out) == a * a * Ri % p
+            wide = (ctypes.c_uint32 * (2 * n))()
+            getattr(emul, f"emul_{name}_wide_mul")(lim(a), lim(b), wide)
+            assert val(wide) == a * b
+            getattr(emul, f"emul_{name}_redc")(wide, out)
+            assert val(out) == a * b * Ri % p
+            getattr(emul, f"emul_{name}_wide_sqr")(lim(b), wide)
+            assert val(wide) == b * b
             getattr(emul, f"emul_{name}_add")(lim(a), lim(b), out)
             assert val(out) == (a + b) % p
             getattr(emul, f"emul_{name}_sub")(lim(a), lim(b), out)
             assert val(out) == (a - b) % p
+        for _ in range(200):                                                        # wide products are exact for ANY N-limb operands
+            a, b = rng.choice((R - 1, rng.randrange(R), 2 * p - 2 if 2 * p - 2 < R else p - 1)), rng.randrange(R)
+            wide = (ctypes.c_uint32 * (2 * n))()
+            getattr(emul, f"emul_{name}_wide_mul")(lim(a), lim(b), wide)
+            assert val(wide) == a * b
+            getattr(emul, f"emul_{name}_wide_sqr")(lim(a), wide)
+            assert val(wide) == a * a
+        if name in ("fp381", "fp254", "fp256"):                                     # Fp2 product: three reduced products == lazily reduced form
+            for _ in range(200):
+                a0, a1, b0, b1 = (rng.choice(vals) for _ in range(4))
+                r1, r2 = (ctypes.c_uint32 * (2 * n))(), (ctypes.c_uint32 * (2 * n))()
+                A = (ctypes.c_uint32 * (2 * n))(*(list(lim(a0)) + list(lim(a1))))
+                B = (ctypes.c_uint32 * (2 * n))(*(list(lim(b0)) + list(lim(b1))))
+                getattr(emul, f"emul_{name}_fp2_mul_pair")(A, B, r1, r2)
+                assert list(r1) == list(r2)
+                assert val(r1[:n]) == (a0 * b0 - a1 * b1) * Ri % p and val(r1[n:]) == (a0 * b1 + a1 * b0) * Ri % p
         for a in vals[:12]:
             out = (ctypes.c_uint32 * n)()
             getattr(emul, f"emul_{name}_inv")(lim(a * R % p), out)                 # binary GCD (what the kernels use)
