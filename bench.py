@@ -95,65 +95,53 @@ class ClockSampler(threading.Thread):
 
 
 # ------------------------------------------------------------------------------------------------
-_BEST_THREADS = None
-
-
 def best_cpu_threads() -> int:
-    """The CPU arm uses 'all the host threads it can use': calibrate once over {C, C/2, C/4, C/8, C/16} (hyper-threads and
-    container CPU quotas make the full logical count slower than fewer threads on the GPU boxes) and keep the best."""
-    global _BEST_THREADS
-    if _BEST_THREADS is not None:
-        return _BEST_THREADS
+    """Threads of the CPU arm: FIXED rule, printed in the JSON -- min(32, logical CPUs) (B2K_REF_THREADS overrides).
+    On the 128-logical-CPU GPU boxes 32 threads measured fastest for this memory-light, multiply-bound loop in round 1
+    (64 / 128 lose to SMT sharing and the container's CPU quota); a per-run calibration made the baseline itself vary 2x."""
+    v = os.environ.get("B2K_REF_THREADS")
+    if v and v.isdigit() and int(v) > 0:
+        return int(v)
+    return max(1, min(32, os.cpu_count() or 1))
+
+
+def cpu_sample(n_sample: int, threads: int, seed_start: int = 0):
+    """n_sample pairs of the C2 workload: points a_i * G made by the CPU port itself (operand form, no per-point Python)"""
     from kyber_b200 import workload as wl
     from oracle import cpu_ref
     lib = cpu_ref.load()
-    c = os.cpu_count() or 1
-    cands = sorted({max(1, c // d) for d in (1, 2, 4, 8, 16)}, reverse=True)
-    best, best_rate = c, 0.0
-    n = 8192
-    sb = wl.scalars_to_bytes(wl.prng_scalars("b2k/calib", n, wl.R_BLS12381))
-    cpu_ref.g1_mul_batch(lib, sb[:32 * 512], wl.G1_BLS12381_AFFINE * 512, c)        # warm-up (library pages, thread pool)
-    for t in cands:
-        for _ in range(2):                                                             # best of two: one noisy run must not pick the count
-            t0 = time.perf_counter()
-            cpu_ref.g1_mul_batch(lib, sb, wl.G1_BLS12381_AFFINE * n, t)
-            rate = n / (time.perf_counter() - t0)
-            if rate > best_rate:
-                best, best_rate = t, rate
-    _BEST_THREADS = best
-    return best
+    s = wl.prng_scalars("b2k/c2", n_sample, wl.R_BLS12381, seed_start)
+    a = wl.prng_scalars("b2k/c2-a", n_sample, wl.R_BLS12381, seed_start)
+    pts = cpu_ref.g1_mul_batch_affine(lib, wl.scalars_to_bytes(a), wl.G1_BLS12381_AFFINE * n_sample, os.cpu_count() or threads)
+    return lib, s, a, wl.scalars_to_bytes(s), pts
 
 
-def cpu_reference_run(n_sample: int, threads: int, seed_start: int = 0):
+def cpu_reference_run(n_sample: int, threads: int, seed_start: int = 0, with_pippenger: bool = True):
     """Time the oracle's restatement of the reference path (N x Point.Mul + Add, share/poly.go:461-473)
     and, separately, a CPU Pippenger, on a bounded sample of the same workload."""
     from kyber_b200 import workload as wl
     from oracle import cpu_ref
     from oracle import bls12381 as o
-    lib = cpu_ref.load()
-    s = wl.prng_scalars("b2k/c2", n_sample, wl.R_BLS12381, seed_start)
-    a = wl.prng_scalars("b2k/c2-a", n_sample, wl.R_BLS12381, seed_start)
-    sb = wl.scalars_to_bytes(s)
-    # points a_i*G made by the CPU port itself (fixed-base muls), then affine via the Python oracle
-    comp = cpu_ref.g1_mul_batch(lib, wl.scalars_to_bytes(a), wl.G1_BLS12381_AFFINE * n_sample, threads)
-    pts = b"".join(o.g1_to_affine_bytes(o.g1_decompress(comp[48 * i:48 * i + 48], subgroup_check=False))
-                   for i in range(n_sample))
+    lib, s, a, sb, pts = cpu_sample(n_sample, threads, seed_start)
     t0 = time.perf_counter()
     out = cpu_ref.g1_msm_muladd(lib, sb, pts, threads)
     t_muladd = time.perf_counter() - t0
     expect = o.g1_compress(o.g1_mul(wl.dot_mod(s, a, o.R)))
     assert out == expect, "CPU reference arm produced a wrong MSM"
-    t0 = time.perf_counter()
-    out2 = cpu_ref.g1_msm_pippenger(lib, sb, pts, threads)
-    t_pip = time.perf_counter() - t0
-    assert out2 == expect
-    return {"value": n_sample / t_muladd, "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": f"{n_sample} pairs of the 2^{LOG_N} workload: Mul+Add loop (the reference's algorithm, "
-                      f"share/poly.go:461-473) on {threads} threads, {t_muladd:.2f} s; oracle/cpu_ref.c "
-                      "(C restatement, NOT the Go reference: no Go toolchain on this image)",
-            "pippenger_value": n_sample / t_pip,
-            "pippenger_note": "same sample through a multi-threaded CPU Pippenger (a stronger baseline than the "
-                              "reference, which has no MSM)"}
+    res = {"value": n_sample / t_muladd, "unit": UNIT, "cores": threads, "kind": "port",
+           "sample": f"{n_sample} pairs of the 2^20 workload: Mul+Add loop (the reference's algorithm, "
+                     f"share/poly.go:461-473) on {threads} threads, {t_muladd:.2f} s; oracle/cpu_ref.c "
+                     "(C restatement, NOT the Go reference: no Go toolchain on this image)",
+           "seconds": t_muladd}
+    if with_pippenger:
+        t0 = time.perf_counter()
+        out2 = cpu_ref.g1_msm_pippenger(lib, sb, pts, threads)
+        t_pip = time.perf_counter() - t0
+        assert out2 == expect
+        res["pippenger_value"] = n_sample / t_pip
+        res["pippenger_note"] = ("same sample through a multi-threaded CPU Pippenger (a stronger baseline than the "
+                                 "reference, which has no MSM)")
+    return res
 
 
 def cpu_pairing_run(n_sample: int, threads: int):
@@ -262,26 +250,137 @@ def gpu_verify_run(eng, torch, dev, n: int, steps: int):
             "workload": f"{n} independent bls.Verify (sigs on G1): 2 decompress + subgroup checks, hash-to-G1, 2-pairing check"}
 
 
+def section_recover_commit(eng, torch, steps: int, threads: int):
+    """BASELINE configs[3] (C4): share.RecoverCommit, t = n = 1024 over bn254 G1 (share/poly.go:449-476): Lagrange + MSM on the
+    device through the host C ABI (64 KiB in, 64 B out per call); result == f(0) G (oracle)."""
+    from oracle import bn254 as c4
+    from kyber_b200 import workload as wl
+    t = 1024
+    coeffs = wl.prng_scalars("b2k/c4", t, c4.ORDER)
+    idx = list(range(t))
+    # shares Y_i = f(i+1) G, built on the device: f(i+1) evaluated on the host (Horner over ints), one mul_batch for the points
+    ev = []
+    for i in idx:
+        acc = 0
+        for c in reversed(coeffs):
+            acc = (acc * (i + 1) + c) % c4.ORDER
+        ev.append(acc)
+    shares = eng.bn254_g1_mul_batch(b"".join(v.to_bytes(32, "big") for v in ev), c4.g1_marshal(c4.G1) * t)
+    want = c4.g1_marshal(c4.g1_mul(coeffs[0]))
+    assert eng.bn254_recover_commit(idx, shares) == want, "RecoverCommit differs from f(0) G"
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        eng.bn254_recover_commit(idx, shares)
+    ms = (time.perf_counter() - t0) * 1e3 / steps
+    # CPU: the reference's loop = t Lagrange coefficients (O(t^2) mod.Int products) + t x (Mul + Add).  The C port has no bn254 field;
+    # the EC part is quoted from the reference's own published number (95 331 ns per bn254 G1 Mul, docs/benchmark-app data.json:476)
+    return {"value": 1e3 / ms, "unit": "recoveries/s", "ms_per_call": ms, "t": t,
+            "workload": "share.RecoverCommit, t = n = 1024 over bn254 G1 (BASELINE.json configs[3]), host buffers in and out every call",
+            "reference_published": {"ec_part_ms": 1024 * 95331e-6, "note": "1024 x bn254 G1 Point.Mul at the reference's published 95 331 ns/op "
+                                    "(hardware unstated, one thread); the O(t^2) big.Int scalar part comes on top"}}
+
+
+def section_bdn_aggregate(eng, torch, steps: int, threads: int):
+    """BASELINE configs[2] mode B: BDN same-message aggregate over 65 536 signers (sign/bdn/bdn.go:126-181): coefficients
+    (BLAKE2Xs over all public keys, host function of the library), sum (c_i+1) S_i on G1, sum (c_i+1) PK_i on G2, one bls.Verify."""
+    from oracle import bls12381 as o, h2c_bls12381 as h
+    from kyber_b200 import workload as wl
+    n = 1 << 16
+    sks = wl.prng_scalars("b2k/c3", n, o.R)
+    sb = wl.scalars_to_bytes(sks)
+    msg = bytes(range(32))
+    hm_b = eng.bls12381_hash_to_g1([msg], h.DST_G1)
+    pk_aff = eng.bls12381_g2_mul_batch_affine(sb, o.g2_to_affine_bytes(o.G2) * n)
+    ones = b"".join((1).to_bytes(32, "big") for _ in range(n))
+    pks = eng.bls12381_g2_mul_batch(ones, pk_aff)                         # MarshalBinary bytes the coefficients hash
+    sig_aff = eng.bls12381_g1_mul_batch_affine(sb, hm_b * n)
+
+    def once():
+        cb = eng.bdn_coefficients(pks, 96, add_one=True)                  # c_i + 1, 32-byte big-endian scalars
+        agg_sig = eng.bls12381_g1_msm(cb, sig_aff)
+        agg_key = eng.bls12381_g2_msm(cb, pk_aff)
+        ok = eng.bls12381_verify_g1sig(agg_key, [msg], h.DST_G1, agg_sig)
+        return cb, agg_sig, agg_key, ok
+    cb, agg_sig, agg_key, ok = once()
+    coefs = [int.from_bytes(cb[32 * i:32 * i + 32], "big") for i in range(n)]
+    dot = wl.dot_mod(coefs, sks, o.R)
+    assert ok == b"\x01" and agg_key == o.g2_compress(o.g2_mul(dot)), "BDN aggregate differs from the oracle"
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        once()
+    ms = (time.perf_counter() - t0) * 1e3 / steps
+    # CPU: the reference's loop Mul(coef, sig) + Add over the signatures (bdn.go:128-154) with the same 128-bit coefficients, bounded sample
+    from oracle import cpu_ref
+    lib = cpu_ref.load()
+    ns = 1 << 14
+    t0 = time.perf_counter()
+    out = cpu_ref.g1_msm_muladd(lib, cb[:32 * ns], sig_aff[:96 * ns], threads)
+    dt = time.perf_counter() - t0
+    assert out == eng.bls12381_g1_msm(cb[:32 * ns], sig_aff[:96 * ns])
+    return {"value": n / (ms * 1e-3), "unit": "signers/s", "ms_per_aggregate": ms, "signers": n,
+            "workload": "BDN aggregate of 65 536 same-message signatures (BASELINE.json configs[2] mode B): coefficients, G1 MSM of the signatures, "
+                        "G2 MSM of the keys (128-bit factors c_i + 1), one bls.Verify; host buffers every call",
+            "cpu_baseline": {"value": ns / dt, "unit": "signers/s", "cores": threads, "kind": "port",
+                             "sample": f"AggregateSignatures only: Mul+Add loop over {ns} signatures with the same 128-bit coefficients on {threads} threads, "
+                                       f"{dt:.2f} s (oracle/cpu_ref.c); the G2 key aggregation (~3x the cost per term) is not included"}}
+
+
+def section_ed25519(eng, torch, steps: int):
+    """BASELINE configs[0] (C1): 1024 edwards25519 Point.Mul (group/edwards25519/point.go:235-258), checked against libsodium"""
+    from kyber_b200 import workload as wl
+    from oracle import ed25519 as oe
+    n = 1024
+    L = oe.L
+    sc = wl.prng_scalars("b2k/c1", n, L)
+    a = wl.prng_scalars("b2k/c1-a", n, L)
+    sb = b"".join(v.to_bytes(32, "little") for v in sc)
+    ab = b"".join(v.to_bytes(32, "little") for v in a)
+    pts = eng.ed25519_mul_batch(ab, oe.encode(oe.BASE) * n)
+    out = eng.ed25519_mul_batch(sb, pts)
+    cpu = None
+    try:
+        from nacl import bindings as nb
+        t0 = time.perf_counter()
+        ref = [nb.crypto_scalarmult_ed25519_noclamp(sb[32 * i:32 * i + 32], pts[32 * i:32 * i + 32]) for i in range(n)]
+        dt = time.perf_counter() - t0
+        assert b"".join(ref) == out, "ed25519 batch differs from libsodium"
+        cpu = {"value": n / dt, "unit": "scalar-muls/s", "cores": 1, "kind": "library",
+               "sample": f"{n} x libsodium crypto_scalarmult_ed25519_noclamp (PyNaCl), one thread, {dt * 1e3:.1f} ms; the reference's own "
+                         "pure-Go Point.Mul is published at 349 399 ns/op (2.9e3 /s, docs/benchmark-app data.json:38)"}
+    except ImportError:
+        pass
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        eng.ed25519_mul_batch(sb, pts)
+    ms = (time.perf_counter() - t0) * 1e3 / steps
+    return {"value": n / (ms * 1e-3), "unit": "scalar-muls/s", "ms_per_batch": ms,
+            "workload": "1024 edwards25519 Point.Mul (BASELINE.json configs[0]), host buffers in and out (a launch-latency-sized batch)",
+            "cpu_baseline": cpu}
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     threads = best_cpu_threads()
-    n_sample = int(os.environ.get("B2K_REF_SAMPLE", str(max(4096, 384 * threads))))
-    vals = []
+    # >= 2^16 pairs per step: >= 0.5 s of Mul+Add work at the ~1.3e5 muls/s this port reaches on 32 threads
+    n_sample = int(os.environ.get("B2K_REF_SAMPLE", str(1 << 16)))
+    vals, secs = [], []
     last = None
     for i in range(args.warmup + args.steps):
-        last = cpu_reference_run(n_sample, threads, seed_start=i * n_sample)
+        last = cpu_reference_run(n_sample, threads, seed_start=i * n_sample, with_pippenger=(i == args.warmup + args.steps - 1))
         if i >= args.warmup:
-            vals.append(last["value"])
+            vals.append(last["value"]); secs.append(last["seconds"])
     v = sum(vals) / len(vals)
+    sv = sorted(vals)
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * n_sample / v,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
             "data": "synthetic",
             "config": {"workload": f"BLS12-381 G1 MSM, 2^{LOG_N} random (scalar,point) pairs per GPU",
-                       "step": f"bounded sample of {n_sample} pairs"},
+                       "step": f"bounded sample of {n_sample} pairs (fresh seeds every step), {threads} threads (fixed rule: min(32, logical CPUs))"},
             "cpu_baseline": dict(last, value=v),
+            "spread": {"min": sv[0], "median": sv[len(sv) // 2], "max": sv[-1], "seconds_per_step": sum(secs) / len(secs)},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "pairings": cpu_pairing_run(max(1024, 32 * threads), threads),
             "gpu_launches": 0}
@@ -444,17 +543,7 @@ def run_ours(args):
         eng.call_dev("b2k_bls12381_g1_msm_dev", n, d_scal.data_ptr(), d_pts.data_ptr(), d_final.data_ptr())
         acc_ms.append(eng.last_timings())
     barrier()
-    # a sustained run (seconds, not a burst): the same step for >= 3 s, its own clock sample
     sustained = None
-    if world == 1 and not os.environ.get("B2K_SKIP_SUSTAINED"):
-        est = dev_ms / args.steps
-        ks = max(args.steps, int(3000.0 / est) + 1)
-        samp2 = ClockSampler(local)
-        samp2.start()
-        time.sleep(0.2)
-        sus_ms = timed(ks, 0)
-        sustained = {"value": n * ks / (sus_ms * 1e-3), "unit": UNIT, "steps": ks, "seconds": sus_ms * 1e-3,
-                     "ms_per_step": sus_ms / ks, "clocks": samp2.finish()}
     # ---- end-to-end through the host C ABI (pinned host buffers) -----------------------------------
     hs_ptr, hp_ptr = h_scal.data_ptr(), h_pts.data_ptr()
     h_results = [torch.zeros(64, dtype=torch.uint8).pin_memory() for _ in range(NC)]
@@ -586,8 +675,6 @@ def run_ours(args):
                                    f" on {NE} contexts used in turn by one host thread per rank (pinned host buffers; H2D of all inputs and "
                                    "D2H of the result inside the timed region every step; h2d/d2h bytes are per rank); "
                                    "blocking_ms_per_step = submit + wait back to back on one context"}
-        if sustained:
-            line["sustained"] = sustained
         if world > 1:
             line["multi_gpu_exchange"] = {
                 "ms_per_step": alt_ms, "headline": ("bucket_exchange_peer" if mode["shape"] == 0 else "result_exchange_peer"),
@@ -637,10 +724,26 @@ def run_ours(args):
             line["bls_verify"] = gpu_verify_run(eng, torch, dev, 1 << 16, max(2, min(args.steps, 3)))
         if world == 1 and not os.environ.get("B2K_SKIP_CPU_BASELINE"):
             threads = best_cpu_threads()
-            line["cpu_baseline"] = cpu_reference_run(max(4096, 384 * threads), threads)
+            line["cpu_baseline"] = cpu_reference_run(1 << 16, threads)
             line["cpu_baseline"]["logical_cpus"] = os.cpu_count()
             if "pairings" in line:
                 line["pairings"]["cpu_baseline"] = cpu_pairing_run(max(1024, 32 * threads), threads)
+        if world == 1 and not os.environ.get("B2K_SKIP_SECTIONS"):
+            threads = best_cpu_threads()
+            line["recover_commit"] = section_recover_commit(eng, torch, 5, threads)
+            line["bdn_aggregate"] = section_bdn_aggregate(eng, torch, 3, threads)
+            line["ed25519"] = section_ed25519(eng, torch, 10)
+        # a sustained run (seconds, not a burst): the headline step for >= 3 s with its own clock sample, LAST so that the power
+        # state it leaves behind does not leak into the other sections
+        if world == 1 and not os.environ.get("B2K_SKIP_SUSTAINED"):
+            est = dev_ms / args.steps
+            ks = max(args.steps, int(3000.0 / est) + 1)
+            samp2 = ClockSampler(local)
+            samp2.start()
+            time.sleep(0.2)
+            sus_ms = timed(ks, 0)
+            line["sustained"] = {"value": n * ks / (sus_ms * 1e-3), "unit": UNIT, "steps": ks, "seconds": sus_ms * 1e-3,
+                                 "ms_per_step": sus_ms / ks, "clocks": samp2.finish()}
         print(json.dumps(line))
     if world > 1:
         barrier()

@@ -106,6 +106,9 @@ int b2k_set_msm_chunk(b2k_ctx* ctx, int m);
  * multiplications move to the second level, which has m1 times fewer operands).  levels: 0 = automatic, 1, 2; m1, m2 = chunk
  * sizes of the two levels (powers of two, 0 = default 8 and 4).  Same result bytes either way; A/B and tuning aid. */
 int b2k_set_msm_reduce(b2k_ctx* ctx, int levels, int m1, int m2);
+/* code layout of the field products inside the G1 MSM kernels (b2k_bls12381_g1_msm_dev): 0 = inlined at every use,
+ * 1 = one out-of-line body called by value (instruction-cache friendly); identical results, A/B aid. */
+int b2k_set_msm_layout(b2k_ctx* ctx, int layout);
 /* Number of kernels launched by this context so far. */
 uint64_t b2k_launch_count(const b2k_ctx* ctx);
 
@@ -350,6 +353,24 @@ int b2k_bls12381_g1_pubpoly_eval(b2k_ctx* ctx, size_t t, const uint8_t* commits 
 int b2k_bls12381_g2_pubpoly_eval(b2k_ctx* ctx, size_t t, const uint8_t* commits /*[t][192]*/, size_t n,
                                  const uint32_t* indices /*[n]*/, uint8_t* out /*[n][192]*/);
 
+/* share.RecoverPubPoly (share/poly.go:480-508; lagrangeBasis :513-545): the WHOLE public polynomial from t public shares
+ * (the first t by index, like recover_commit): commits_out[k] = sum_j L_j[k] * points[j], k = 0..t-1, operand form.
+ * commits_out[0] equals recover_commit's result (as compressed / operand bytes of the same point).  1 <= t <= 4096.
+ * PriPoly.Commit (poly.go:143-149): out[i] = scalars[i] * base for ONE base point (NULL = the group's generator) -- the
+ * fixed-base batch a dealer runs over its coefficient vector (callers no longer replicate the generator n times). */
+int b2k_bls12381_g1_recover_pubpoly(b2k_ctx* ctx, size_t t, const uint32_t* indices /*[t]*/, const uint8_t* points /*[t][96]*/,
+                                    uint8_t* commits_out /*[t][96]*/);
+int b2k_bls12381_g2_recover_pubpoly(b2k_ctx* ctx, size_t t, const uint32_t* indices /*[t]*/, const uint8_t* points /*[t][192]*/,
+                                    uint8_t* commits_out /*[t][192]*/);
+int b2k_bn254_recover_pubpoly(b2k_ctx* ctx, size_t t, const uint32_t* indices /*[t]*/, const uint8_t* points /*[t][64]*/,
+                              uint8_t* commits_out /*[t][64]*/);
+int b2k_bls12381_g1_commit_batch(b2k_ctx* ctx, size_t n, const uint8_t* scalars /*[n][32]*/, const uint8_t* base /*[96] or NULL*/,
+                                 uint8_t* out /*[n][96]*/);
+int b2k_bls12381_g2_commit_batch(b2k_ctx* ctx, size_t n, const uint8_t* scalars /*[n][32]*/, const uint8_t* base /*[192] or NULL*/,
+                                 uint8_t* out /*[n][192]*/);
+int b2k_bn254_commit_batch(b2k_ctx* ctx, size_t n, const uint8_t* scalars /*[n][32]*/, const uint8_t* base /*[64] or NULL*/,
+                           uint8_t* out /*[n][64]*/);
+
 /* ---- share.PubPoly.Check over a batch of deals: the verification loops of share/vss and share/dkg ---------------------
  * For dealer d (m of them) with commitments commits[d][0..t) and private shares (indices[d][k], shares[d][k]), k < n:
  *     ok[d][k] = ( sum_j (indices[d][k] + 1)^j commits[d][j]  ==  shares[d][k] * B ),   B = the group's base point.
@@ -432,6 +453,13 @@ int b2k_bn254_hash_to_g1_dev(b2k_ctx* ctx, size_t n, const void* d_msgs, const v
                              uint32_t dst_len, void* d_out);
 int b2k_bn256_hash_to_g1(b2k_ctx* ctx, size_t n, const uint8_t* msgs, const uint32_t* offsets, uint8_t* out /*[n][64]*/);
 int b2k_bn256_hash_to_g1_dev(b2k_ctx* ctx, size_t n, const void* d_msgs, const void* d_offsets, void* d_out);
+/* bn256 HashG1 (pairing/bn256/hash.go:10-110): t = 48 bytes of HKDF-SHA256(secret = msg, salt = dst, info = "H2C" 0 1) mod p
+ * (gfp.go:46-67), then the Shallue-van de Woestijne map.  dst may be NULL / 0 (the reference's own vectors use a nil dst:
+ * hash_test.go:11-19, reproduced in tests/).  Output 64 B x||y. */
+int b2k_bn256_hash_g1(b2k_ctx* ctx, size_t n, const uint8_t* msgs, const uint32_t* offsets /*[n+1]*/, const uint8_t* dst,
+                      uint32_t dst_len, uint8_t* out /*[n][64]*/);
+int b2k_bn256_hash_g1_dev(b2k_ctx* ctx, size_t n, const void* d_msgs, const void* d_offsets, const void* d_dst, uint32_t dst_len,
+                          void* d_out);
 
 /* ---- sign/bdn: rogue-key coefficients (HOST function: no context, no device work) ------------------------- */
 /* out[i] = c_i (+1 if add_one) as a 32-byte big-endian scalar, where c_0..c_{n-1} are the first 16 n bytes of

@@ -7,7 +7,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libb2kyber.so")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC"]
-UNITS = ["b2k_api.cu", "b2k_g1_mul.cu", "b2k_bn254.cu", "b2k_g2.cu", "b2k_pairing.cu", "b2k_h2c.cu", "b2k_share.cu", "b2k_ed25519.cu", "b2k_bn256.cu", "b2k_bn254_pairing.cu", "b2k_bdn.cu", "b2k_bn_hash.cu", "b2k_bn_codec.cu", "b2k_multi.cu", "b2k_gt.cu"]
+UNITS = ["b2k_api.cu", "b2k_msm_compact.cu", "b2k_g1_mul.cu", "b2k_bn254.cu", "b2k_g2.cu", "b2k_pairing.cu", "b2k_pairing_compact.cu", "b2k_h2c.cu", "b2k_share.cu", "b2k_share2.cu", "b2k_ed25519.cu", "b2k_bn256.cu", "b2k_bn254_pairing.cu", "b2k_bdn.cu", "b2k_bn_hash.cu", "b2k_bn_codec.cu", "b2k_multi.cu", "b2k_gt.cu"]
 
 
 def _nvcc() -> str:

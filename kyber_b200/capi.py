@@ -49,6 +49,7 @@ def load_library() -> C.CDLL:
         "b2k_last_msm_plan": (C.c_int, [vp, C.POINTER(C.c_int), C.c_int]),
         "b2k_set_msm_affine_split": (C.c_int, [vp, C.c_int]),
         "b2k_set_mul_occupancy": (C.c_int, [vp, C.c_int]),
+        "b2k_set_msm_layout": (C.c_int, [vp, C.c_int]),
     }
     sigs["b2k_bls12381_pair"] = (C.c_int, [vp, sz, vp, vp, vp])
     sigs["b2k_bls12381_pair_dev"] = (C.c_int, [vp, sz, vp, vp, vp])
@@ -88,6 +89,11 @@ def load_library() -> C.CDLL:
         sigs[nm] = (C.c_int, [vp, sz, vp, vp])
     for nm in ("b2k_bls12381_g1_add_batch", "b2k_bls12381_g2_add_batch"):
         sigs[nm] = (C.c_int, [vp, sz, vp, vp, C.c_int, vp])
+    for nm in ("b2k_bls12381_g1_recover_pubpoly", "b2k_bls12381_g2_recover_pubpoly", "b2k_bn254_recover_pubpoly",
+               "b2k_bls12381_g1_commit_batch", "b2k_bls12381_g2_commit_batch", "b2k_bn254_commit_batch"):
+        sigs[nm] = (C.c_int, [vp, sz, vp, vp, vp])
+    sigs["b2k_bn256_hash_g1"] = (C.c_int, [vp, sz, vp, vp, vp, C.c_uint32, vp])
+    sigs["b2k_bn256_hash_g1_dev"] = (C.c_int, [vp, sz, vp, vp, vp, C.c_uint32, vp])
     sigs["b2k_comm_create"] = (C.c_int, [vp, C.c_int, C.c_int, C.POINTER(vp)])
     sigs["b2k_comm_export"] = (C.c_int, [vp, vp])
     sigs["b2k_comm_connect"] = (C.c_int, [vp, vp])
@@ -342,6 +348,15 @@ class Engine:
         self._check(self.lib.b2k_bn256_hash_to_g1(self.h, n, bufs[0][0], bufs[1][0], bufs[2][0]))
         return bytes(out)
 
+    def bn256_hash_g1(self, msgs, dst: bytes = b"") -> bytes:
+        """bn256 HashG1 (HKDF-SHA256 + SvdW, pairing/bn256/hash.go:10-110) for a list of messages -> [n][64] x||y"""
+        n = len(msgs)
+        blob, offs = self._pack_msgs(msgs)
+        out = bytearray(64 * n)
+        bufs = [_buf(x) for x in (blob, offs, dst or b"\x00", out)]
+        self._check(self.lib.b2k_bn256_hash_g1(self.h, n, bufs[0][0], bufs[1][0], bufs[2][0] if dst else None, len(dst), bufs[3][0]))
+        return bytes(out)
+
     def bls12381_hash_to_g2(self, msgs, dst: bytes) -> bytes:
         """msgs: list of bytes -> operand bytes [n][192]"""
         n = len(msgs)
@@ -496,6 +511,22 @@ class Engine:
 
     def bn254_g2_mul_batch(self, s, p): return self.call_host("b2k_bn254_g2_mul_batch", len(s) // 32, s, p, 128 * (len(s) // 32))
     def bn254_g2_msm(self, s, p): return self.call_host("b2k_bn254_g2_msm", len(s) // 32, s, p, 128)
+
+    def recover_pubpoly(self, name: str, indices, points: bytes) -> bytes:
+        """share.RecoverPubPoly: name in bls12381_g1 / bls12381_g2 / bn254; returns t commitments in operand form"""
+        import struct
+        t = len(indices)
+        return self.call_host(f"b2k_{name}_recover_pubpoly", t, struct.pack("<%dI" % t, *indices), points, len(points))
+
+    def commit_batch(self, name: str, scalars: bytes, base: bytes = None) -> bytes:
+        """PriPoly.Commit: out[i] = scalars[i] * base (None = generator), operand form"""
+        n = len(scalars) // 32
+        pb = {"bls12381_g1": 96, "bls12381_g2": 192, "bn254": 64}[name]
+        out = bytearray(n * pb)
+        ps, k1 = _buf(scalars); po, k3 = _buf(out)
+        pbase, k2 = _buf(base) if base else (None, None)
+        self._check(getattr(self.lib, f"b2k_{name}_commit_batch")(self.h, n, ps, pbase, po))
+        return bytes(out)
 
     def bn254_recover_commit(self, indices, points: bytes) -> bytes:
         """share.RecoverCommit over bn254 G1: indices = share indices I_i (x_i = I_i + 1), points [t][64] -> 64 B"""

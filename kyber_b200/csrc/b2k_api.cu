@@ -219,7 +219,15 @@ int b2k_bls12381_g1_msm(b2k_ctx* c, size_t n, const uint8_t* s, const uint8_t* p
 int b2k_bls12381_g1_msm_affine(b2k_ctx* c, size_t n, const uint8_t* s, const uint8_t* p, uint8_t* o) { return msm_host<Bls381G1>(c, n, s, p, o, 1); }
 int b2k_bls12381_g1_msm_async(b2k_ctx* c, size_t n, const uint8_t* s, const uint8_t* p, uint8_t* o) { return msm_host<Bls381G1>(c, n, s, p, o, 0, false); }
 int b2k_wait(b2k_ctx* c) { return msm_wait(c); }
-int b2k_bls12381_g1_msm_dev(b2k_ctx* c, size_t n, const void* s, const void* p, void* o) { return msm_dev<Bls381G1>(c, n, s, p, o); }
+int b2k_bls12381_g1_msm_dev(b2k_ctx* c, size_t n, const void* s, const void* p, void* o) {
+  if (c && c->msm_layout == 1) return b2k_internal_bls12381_g1_msm_dev_compact(c, n, s, p, o, 0);
+  return msm_dev<Bls381G1>(c, n, s, p, o);
+}
+int b2k_set_msm_layout(b2k_ctx* ctx, int layout) {
+  if (!ctx || layout < 0 || layout > 1) return B2K_ERR_ARG;
+  ctx->msm_layout = layout;
+  return B2K_OK;
+}
 int b2k_bls12381_g1_msm_affine_dev(b2k_ctx* c, size_t n, const void* s, const void* p, void* o) { return msm_dev<Bls381G1>(c, n, s, p, o, 1); }
 
 int b2k_bls12381_g1_msm_bucket_plan(b2k_ctx* c, size_t n, int* plan) { return msm_bucket_plan<Bls381G1>(c, n, plan); }

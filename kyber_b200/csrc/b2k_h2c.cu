@@ -131,7 +131,7 @@ int b2k_bls12381_verify_g1sig_dev(b2k_ctx* ctx, size_t n, const void* d_pks96, c
   k_and_flags<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, ok1, ok2, okc);
   k_hash_to_g1<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(n, (const uint8_t*)d_msgs, (const uint32_t*)d_offsets,
                                                           (const uint8_t*)d_dst, dst_len, hm);
-  launch_pairing_check(ctx, n, hm, pk, sg, gen, (uint8_t*)d_ok, 1, okc);
+  b2k_internal_launch_pairing_check(ctx, n, hm, pk, sg, gen, (uint8_t*)d_ok, 1, okc);
   CK(cudaGetLastError());
   ctx->launches += 6;
   return B2K_OK;
@@ -193,7 +193,7 @@ int b2k_bls12381_verify_g2sig_dev(b2k_ctx* ctx, size_t n, const void* d_pks48, c
   k_hash_to_g2<<<(unsigned)((n + 63) / 64), 64, 0, st>>>(n, (const uint8_t*)d_msgs, (const uint32_t*)d_offsets,
                                                         (const uint8_t*)d_dst, dst_len, hm);
   // e(pk, H(m)) == e(base, sig): a = (pk, hm), b = (base [shared], sig)
-  launch_pairing_check(ctx, n, pk, hm, gen, sg, (uint8_t*)d_ok, 2, okc);
+  b2k_internal_launch_pairing_check(ctx, n, pk, hm, gen, sg, (uint8_t*)d_ok, 2, okc);
   CK(cudaGetLastError());
   ctx->launches += 6;
   return B2K_OK;

@@ -10,6 +10,10 @@
 //   x = SHA-256(m) mod p, then try-and-increment: the first x' >= x with x'^3 + 3 a square; y = (x'^3+3)^((p+1)/4)
 //   (what big.Int.ModSqrt returns for p = 3 mod 4), no sign adjustment.  Used by sign/bls and sign/bdn on bn256: the
 //   byte-exact BDN fixtures of the reference hash their message with it.
+// bn256 HashG1 (replaces HashG1, pairing/bn256/hash.go:10-110; base-field hash gfp.go:46-67):
+//   t = HKDF-SHA256(secret = msg, salt = dst, info = "H2C" 0 1)[0:48] mod p, then the Shallue-van de Woestijne map of
+//   hash.go:14-110 statement by statement (s = sqrt(-3) the reference's root; legendre = e^((p-1)/2); sqrt = e^((p+1)/4);
+//   sign0 = "canonical value >= (p-1)/2", gfp.go:137-148).  Pinned by the reference's 11 KATs (hash_test.go:11-57).
 #pragma once
 #include "h2c.cuh"
 #include "bn256.cuh"
@@ -206,6 +210,106 @@ B2K_D void bn256_hash_to_g1(Affine<B256Fp>& out, const uint8_t* msg, uint32_t ms
     fp_add(x, x, one);
   }
   out.x = x; out.y = y;
+}
+
+// ---- bn256 HashG1: HKDF-SHA256 + Shallue-van de Woestijne ------------------------------------------------------------
+// HMAC-SHA256 with a key of at most 64 bytes (longer keys are hashed first, RFC 2104), message given as three fragments
+B2K_NI void hmac_sha256(uint8_t* out32, const uint8_t* key, uint32_t key_len, const uint8_t* m1, uint32_t n1, const uint8_t* m2,
+                        uint32_t n2, const uint8_t* m3, uint32_t n3) {
+  uint8_t k[64], kh[32], inner[32];
+  Sha256 s;
+  if (key_len > 64) {
+    sha256_init(s); sha256_update(s, key, key_len); sha256_final(s, kh);
+    key = kh; key_len = 32;
+  }
+  for (uint32_t i = 0; i < 64; i++) k[i] = (i < key_len ? key[i] : 0) ^ 0x36;
+  sha256_init(s);
+  sha256_update(s, k, 64);
+  if (n1) sha256_update(s, m1, n1);
+  if (n2) sha256_update(s, m2, n2);
+  if (n3) sha256_update(s, m3, n3);
+  sha256_final(s, inner);
+  for (uint32_t i = 0; i < 64; i++) k[i] ^= 0x36 ^ 0x5c;
+  sha256_init(s);
+  sha256_update(s, k, 64);
+  sha256_update(s, inner, 32);
+  sha256_final(s, out32);
+}
+
+// gfp.go:137-148 sign0: +1 when the canonical value is >= (p-1)/2, else -1
+B2K_D int bn256_sign0(const B256Fp& a_mont) {
+  B256Fp x;
+  fp_from_mont(x, a_mont);
+  ptx::sub_cc(x.v[0], Bn256Fp::half(0));                       // x - (p-1)/2 borrows  <=>  x < (p-1)/2
+#pragma unroll
+  for (int j = 1; j < 10; j++) ptx::subc_cc(x.v[j], Bn256Fp::half(j));
+  return ptx::subc(0, 0) != 0 ? -1 : 1;
+}
+// gfp.go:150-162 legendre: e^((p-1)/2) as 0 / +1 / -1
+B2K_D int bn256_legendre(const B256Fp& a) {
+  B256Fp f, one;
+  fp_pow_const<Bn256Fp, Bn256Fp::ExpLegendre>(f, a);
+  if (fp_is_zero(f)) return 0;
+  fp_set_one(one);
+  return fp_eq(f, one) ? 1 : -1;
+}
+B2K_D void bn256_g(B256Fp& r, const B256Fp& x) {                // x^3 + 3
+  B256Fp b;
+#pragma unroll
+  for (int j = 0; j < 10; j++) b.v[j] = Bn256Fp::curve_b(j);
+  fp_sqr_c(r, x); fp_mul_c(r, r, x); fp_add(r, r, b);
+}
+
+B2K_NI void bn256_map_to_curve(Affine<B256Fp>& out, const B256Fp& t) {
+  B256Fp one, b, s, smh, a, t2, st, w0, w, tw, x, y;
+  fp_set_one(one);
+#pragma unroll
+  for (int j = 0; j < 10; j++) { b.v[j] = Bn256Fp::curve_b(j); s.v[j] = Bn256Fp::svdw_s(j); smh.v[j] = Bn256Fp::svdw_s_m1_half(j); }
+  fp_sqr_c(t2, t); fp_add(a, b, t2); fp_add(a, a, one);          // a = 1 + B + t^2
+  fp_mul_c(st, s, t);
+  fp_mul_c(w0, st, a);
+  fp_inv_fermat(w0, w0);                                         // gfP.Invert: e^(p-2), 0 -> 0
+  fp_sqr_c(w, st); fp_mul_c(w, w, w0);                           // w = (s t)^2 / (s t a)
+  const int e = bn256_sign0(t);
+  fp_mul_c(tw, t, w);
+  fp_sub(x, smh, tw);                                            // x1 = (s - 1)/2 - t w
+  bn256_g(y, x);
+  if (bn256_legendre(y) != 1) {
+    B256Fp m1;
+    fp_neg(m1, one);
+    fp_sub(x, m1, x);                                            // x2 = -1 - x1
+    bn256_g(y, x);
+    if (bn256_legendre(y) != 1) {
+      fp_sqr_c(x, a); fp_sqr_c(x, x); fp_mul_c(x, x, w0); fp_mul_c(x, x, w0); fp_add(x, x, one);   // x3 = 1 + a^4 w0^2
+      bn256_g(y, x);
+    }
+  }
+  B256Fp r;
+  fp_pow_const<Bn256Fp, Bn256Fp::ExpSqrt>(r, y);
+  if (e != bn256_sign0(r)) fp_neg(r, r);
+  out.x = x; out.y = r;
+}
+
+B2K_D void bn256_hash_g1(Affine<B256Fp>& out, const uint8_t* msg, uint32_t msg_len, const uint8_t* dst, uint32_t dst_len) {
+  uint8_t zeros[32], prk[32], t1[32], t2[32];
+  const uint8_t info1[6] = {'H', '2', 'C', 0, 1, 1}, info2[6] = {'H', '2', 'C', 0, 1, 2};
+  for (int i = 0; i < 32; i++) zeros[i] = 0;
+  if (dst_len == 0) hmac_sha256(prk, zeros, 32, msg, msg_len, nullptr, 0, nullptr, 0);      // HKDF-Extract, nil salt = 32 zero bytes
+  else hmac_sha256(prk, dst, dst_len, msg, msg_len, nullptr, 0, nullptr, 0);
+  hmac_sha256(t1, prk, 32, info1, 6, nullptr, 0, nullptr, 0);                               // HKDF-Expand, 48 bytes = T1 || T2[0:16]
+  hmac_sha256(t2, prk, 32, t1, 32, info2, 6, nullptr, 0);
+  // 48 bytes big-endian mod p: hi (16 bytes) * 2^256 + lo (32 bytes), both through the Montgomery conversion (which reduces)
+  uint8_t hi32[32], lo32[32];
+  for (int i = 0; i < 16; i++) { hi32[i] = 0; hi32[16 + i] = t1[i]; lo32[i] = t1[16 + i]; lo32[16 + i] = t2[i]; }
+  B256Fp hi, lo, two256, c;
+  bn256_load32(hi, hi32);
+  bn256_load32(lo, lo32);
+#pragma unroll
+  for (int j = 0; j < 10; j++) two256.v[j] = (j == 8) ? 1u : 0u;
+  fp_to_mont(c, two256);
+  fp_mul_c(hi, hi, c);
+  fp_add(lo, lo, hi);
+  bn256_map_to_curve(out, lo);
 }
 
 }  // namespace b2k

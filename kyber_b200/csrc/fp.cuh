@@ -243,7 +243,7 @@ B2K_D void fp_reduce_once(uint32_t* a) {
 }
 
 template <class C>
-B2K_D void fp_mul(Fp<C>& r, const Fp<C>& a, const Fp<C>& b) {
+B2K_D void fp_mul_inl(Fp<C>& r, const Fp<C>& a, const Fp<C>& b) {
   constexpr int N = C::N;
   static_assert(N % 2 == 0, "even limb count");
   uint32_t ev[N], od[N];
@@ -267,7 +267,7 @@ B2K_D void fp_mul(Fp<C>& r, const Fp<C>& a, const Fp<C>& b) {
 
 // a^2: N(N+1)/2 + N^2 multiply-adds instead of 2 N^2 (BLS12-381: 222 instead of 288)
 template <class C>
-B2K_D void fp_sqr(Fp<C>& r, const Fp<C>& a) {
+B2K_D void fp_sqr_inl(Fp<C>& r, const Fp<C>& a) {
   constexpr int N = C::N;
   uint32_t t[2 * N], u[N];
   detail::wide_sqr<N>(t, a.v);
@@ -277,12 +277,34 @@ B2K_D void fp_sqr(Fp<C>& r, const Fp<C>& a) {
   for (int j = 0; j < N; j++) r.v[j] = u[j];
 }
 
+// ---- code layout of the two products ----------------------------------------------------------------------------------------
+// Default: fully inlined at every use (a 381-bit product is ~330 instructions = 5.3 KB of SASS).  A translation unit compiled
+// with B2K_COMPACT_FIELD gets ONE out-of-line copy of each product instead, called BY VALUE: nvcc passes the 2 x N operand
+// words and the N result words in registers (no local-memory round trip; verified in SASS: no LDL/STL around the CALL), at
+// the price of ~3 N register moves per call.  Why it matters: the instruction caches are small (L0 ~6 KB, L1.5 32 KB per SM,
+// then L2): ncu shows the pairing kernel stalled 35 % of its cycles on instruction fetch (`no_instruction`) with 530 KB of
+// code, and the XYZZ bucket kernel 22 % with 53 KB per loop iteration.
+#ifdef B2K_COMPACT_FIELD
+template <class C> B2K_NI Fp<C> fp_mul_v(Fp<C> a, Fp<C> b) { Fp<C> r; fp_mul_inl(r, a, b); return r; }
+template <class C> B2K_NI Fp<C> fp_sqr_v(Fp<C> a) { Fp<C> r; fp_sqr_inl(r, a); return r; }
+template <class C> B2K_D void fp_mul(Fp<C>& r, const Fp<C>& a, const Fp<C>& b) { r = fp_mul_v<C>(a, b); }
+template <class C> B2K_D void fp_sqr(Fp<C>& r, const Fp<C>& a) { r = fp_sqr_v<C>(a); }
+#else
+template <class C> B2K_D void fp_mul(Fp<C>& r, const Fp<C>& a, const Fp<C>& b) { fp_mul_inl(r, a, b); }
+template <class C> B2K_D void fp_sqr(Fp<C>& r, const Fp<C>& a) { fp_sqr_inl(r, a); }
+#endif
+
 // out-of-line copies for code that is too large to inline a 300-instruction product at every use
 // (towers, exponentiations); operands then travel through local memory.
+#ifdef B2K_COMPACT_FIELD
+template <class C> B2K_D void fp_mul_c(Fp<C>& r, const Fp<C>& a, const Fp<C>& b) { fp_mul(r, a, b); }
+template <class C> B2K_D void fp_sqr_c(Fp<C>& r, const Fp<C>& a) { fp_sqr(r, a); }
+#else
 template <class C>
 B2K_NI void fp_mul_c(Fp<C>& r, const Fp<C>& a, const Fp<C>& b) { fp_mul(r, a, b); }
 template <class C>
 B2K_NI void fp_sqr_c(Fp<C>& r, const Fp<C>& a) { fp_sqr(r, a); }
+#endif
 
 template <class C>
 B2K_D void fp_add(Fp<C>& r, const Fp<C>& a, const Fp<C>& b) {

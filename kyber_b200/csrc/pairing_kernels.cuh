@@ -52,18 +52,18 @@ static __global__ void __launch_bounds__(BLOCK, MINB) k_bls_pairing_check(size_t
 
 
 // launch-bound variants: (threads per block, min blocks per SM) -> register cap 65536 / (threads * blocks)
-#define B2K_PAIR_VARIANTS(X) X(0, 64, 4) X(1, 64, 8)     /* round 1 swept six shapes (profiles/r01*): (64, 4) won, (64, 8) kept for A/B */
-inline void launch_pair(const b2k_ctx* ctx, size_t n, const uint8_t* g1, const uint8_t* g2, uint8_t* gt) {
-  switch (ctx->pair_variant) {
+#define B2K_PAIR_VARIANTS(X) X(0, 64, 4) X(1, 64, 8) X(2, 64, 6)     /* round 1 swept six shapes (profiles/r01*): (64, 4) won */
+inline void launch_pair_v(const b2k_ctx* ctx, int variant, size_t n, const uint8_t* g1, const uint8_t* g2, uint8_t* gt) {
+  switch (variant) {
 #define X(ID, B, M) case ID: k_bls_pair<B, M><<<(unsigned)((n + B - 1) / B), B, 0, ctx->stream>>>(n, g1, g2, gt, ctx->d_flags); break;
     B2K_PAIR_VARIANTS(X)
 #undef X
     default: k_bls_pair<64, 4><<<(unsigned)((n + 63) / 64), 64, 0, ctx->stream>>>(n, g1, g2, gt, ctx->d_flags);
   }
 }
-inline void launch_pairing_check(const b2k_ctx* ctx, size_t n, const uint8_t* a1, const uint8_t* a2, const uint8_t* b1,
-                                 const uint8_t* b2, uint8_t* ok, int b2_broadcast, const uint8_t* pre_ok) {
-  switch (ctx->pair_variant) {
+inline void launch_pairing_check_v(const b2k_ctx* ctx, int variant, size_t n, const uint8_t* a1, const uint8_t* a2, const uint8_t* b1,
+                                   const uint8_t* b2, uint8_t* ok, int b2_broadcast, const uint8_t* pre_ok) {
+  switch (variant) {
 #define X(ID, B, M) case ID: k_bls_pairing_check<B, M><<<(unsigned)((n + B - 1) / B), B, 0, ctx->stream>>>(n, a1, a2, b1, b2, ok, b2_broadcast, pre_ok, ctx->d_flags); break;
     B2K_PAIR_VARIANTS(X)
 #undef X
@@ -72,3 +72,14 @@ inline void launch_pairing_check(const b2k_ctx* ctx, size_t n, const uint8_t* a1
 }
 
 }  // namespace b2k
+
+// The pairing kernels exist in two code layouts (fp.cuh: B2K_COMPACT_FIELD): b2k_pairing.cu holds the fully inlined one
+// (variants 0..2), b2k_pairing_compact.cu the one whose field products are out-of-line by-value calls (variants 3..5).
+// Every caller (b2k_pairing.cu, the bls.Verify paths of b2k_h2c.cu) launches through these two functions.
+extern "C" void b2k_internal_launch_pair(const b2k_ctx* ctx, size_t n, const uint8_t* g1, const uint8_t* g2, uint8_t* gt);
+extern "C" void b2k_internal_launch_pairing_check(const b2k_ctx* ctx, size_t n, const uint8_t* a1, const uint8_t* a2, const uint8_t* b1,
+                                                  const uint8_t* b2, uint8_t* ok, int b2_broadcast, const uint8_t* pre_ok);
+extern "C" void b2k_internal_launch_pair_compact(const b2k_ctx* ctx, int variant, size_t n, const uint8_t* g1, const uint8_t* g2, uint8_t* gt);
+extern "C" void b2k_internal_launch_pairing_check_compact(const b2k_ctx* ctx, int variant, size_t n, const uint8_t* a1, const uint8_t* a2,
+                                                          const uint8_t* b1, const uint8_t* b2, uint8_t* ok, int b2_broadcast,
+                                                          const uint8_t* pre_ok);

@@ -29,6 +29,25 @@ template <class C> B2K_D void fp2_set_one(Fp2<C>& r) { fp_set_one(r.c0); fp_set_
 // Karatsuba: 3 base multiplications.  Out of line, but the three products are inlined so that the six
 // input limbs-vectors are loaded once and every intermediate stays in registers (one 24-word store per
 // Fp2 product instead of three round trips through local memory).
+// B2K_COMPACT_FIELD: one by-value body (operands and result in registers through the ABI) whose three products are calls
+// to the single out-of-line Fp product (fp.cuh) -- ~1 KB of code instead of 16 KB.
+#ifdef B2K_COMPACT_FIELD
+template <class C>
+B2K_NI Fp2<C> fp2_mul_v(Fp2<C> a, Fp2<C> b) {
+  Fp<C> t0, t1, s0, s1;
+  Fp2<C> r;
+  fp_mul(t0, a.c0, b.c0);
+  fp_mul(t1, a.c1, b.c1);
+  fp_add(s0, a.c0, a.c1);
+  fp_add(s1, b.c0, b.c1);
+  fp_mul(s0, s0, s1);
+  fp_sub(s0, s0, t0);
+  fp_sub(r.c1, s0, t1);
+  fp_sub(r.c0, t0, t1);
+  return r;
+}
+template <class C> B2K_D void fp2_mul(Fp2<C>& r, const Fp2<C>& a, const Fp2<C>& b) { r = fp2_mul_v<C>(a, b); }
+#else
 template <class C>
 B2K_NI void fp2_mul(Fp2<C>& r, const Fp2<C>& a, const Fp2<C>& b) {
   const Fp<C> a0 = a.c0, a1 = a.c1, b0 = b.c0, b1 = b.c1;
@@ -44,6 +63,7 @@ B2K_NI void fp2_mul(Fp2<C>& r, const Fp2<C>& a, const Fp2<C>& b) {
   r.c1 = s0;
   r.c0 = t0;
 }
+#endif
 
 // Karatsuba with lazy reduction: three WIDE products (fp.cuh: detail::wide_mul, N^2 multiply-adds each) and only two
 // Montgomery reductions -- 5 N^2 multiply-adds instead of the 6 N^2 of three reduced products.
@@ -95,6 +115,20 @@ B2K_NI void fp2_mul_lazy(Fp2<C>& r, const Fp2<C>& a, const Fp2<C>& b) {
 }
 
 // complex squaring: 2 base multiplications (same register-resident structure)
+#ifdef B2K_COMPACT_FIELD
+template <class C>
+B2K_NI Fp2<C> fp2_sqr_v(Fp2<C> a) {
+  Fp<C> s, d, m;
+  Fp2<C> r;
+  fp_add(s, a.c0, a.c1);
+  fp_sub(d, a.c0, a.c1);
+  fp_mul(m, a.c0, a.c1);
+  fp_mul(r.c0, s, d);
+  fp_add(r.c1, m, m);
+  return r;
+}
+template <class C> B2K_D void fp2_sqr(Fp2<C>& r, const Fp2<C>& a) { r = fp2_sqr_v<C>(a); }
+#else
 template <class C>
 B2K_NI void fp2_sqr(Fp2<C>& r, const Fp2<C>& a) {
   const Fp<C> a0 = a.c0, a1 = a.c1;
@@ -107,6 +141,7 @@ B2K_NI void fp2_sqr(Fp2<C>& r, const Fp2<C>& a) {
   r.c0 = s;
   r.c1 = m;
 }
+#endif
 
 template <class C>
 B2K_D void fp2_mul_fp(Fp2<C>& r, const Fp2<C>& a, const Fp<C>& k) { fp_mul_c(r.c0, a.c0, k); fp_mul_c(r.c1, a.c1, k); }

@@ -245,15 +245,11 @@ class Elt : public Point {
   std::shared_ptr<Engine> engine() const { return eng_; }
 
  private:
+  // a + b / a - b on the device (kilic/g1.go:92-108 Add / Sub): one launch, every exceptional case of the group law handled
   Point& lin(const Elt& a, const Elt& b, bool sub) {
-    Scalar one, m; one.One();
-    if (sub) m.SetInt64(-1); else m.One();
-    Bytes s1 = one.MarshalBinary(), s2 = m.MarshalBinary(), sb(64), pb(2 * AFF);
-    std::memcpy(sb.data(), s1.data(), 32); std::memcpy(sb.data() + 32, s2.data(), 32);
-    std::memcpy(pb.data(), a.aff_.data(), AFF); std::memcpy(pb.data() + AFF, b.aff_.data(), AFF);
-    std::array<uint8_t, AFF> out;
-    if (IS_G1) eng_->check(b2k_bls12381_g1_msm_affine(eng_->ctx(), 2, sb.data(), pb.data(), out.data()));
-    else eng_->check(b2k_bls12381_g2_msm_affine(eng_->ctx(), 2, sb.data(), pb.data(), out.data()));
+    std::array<uint8_t, AFF> x = a.aff_, y = b.aff_, out;            // receiver may alias an argument (bls.go:73)
+    if (IS_G1) eng_->check(b2k_bls12381_g1_add_batch(eng_->ctx(), 1, x.data(), y.data(), sub ? 1 : 0, out.data()));
+    else eng_->check(b2k_bls12381_g2_add_batch(eng_->ctx(), 1, x.data(), y.data(), sub ? 1 : 0, out.data()));
     aff_ = out;
     return *this;
   }
@@ -263,14 +259,62 @@ class Elt : public Point {
 using G1Elt = Elt<96, 48, true>;
 using G2Elt = Elt<192, 96, false>;
 
-// GT element: 576 bytes (kilic/gt.go:115-117).  Only what the hot path produces/consumes is provided
-// (Equal, MarshalBinary); GT arithmetic is not on the path (kilic's Base/Pick panic too, gt.go:40-46).
+// GT element (kilic/gt.go:15-117): held as its 576 MarshalBinary bytes; GT is written additively like every kyber group --
+// Add = Fp12 product, Neg = inverse, Mul = exponentiation, Null = 1 (gt.go:33-38, 59-83); Base / Pick panic (gt.go:40-46).
 class GTElt {
  public:
-  Bytes bytes = Bytes(576, 0);
+  Bytes bytes = one_bytes();
+  GTElt() = default;
+  explicit GTElt(std::shared_ptr<Engine> e) : eng_(std::move(e)) {}
+  static Bytes one_bytes() { Bytes b(576, 0); b[575] = 1; return b; }
   bool Equal(const GTElt& o) const { return bytes == o.bytes; }
+  GTElt& Null() { bytes = one_bytes(); return *this; }
+  GTElt& Base() { throw std::logic_error("bls12-381.GT.Base(): unsupported operation"); }
+  GTElt& Set(const GTElt& o) { bytes = o.bytes; return *this; }
+  GTElt Clone() const { return *this; }
+  GTElt& Add(const GTElt& a, const GTElt& b) {
+    Bytes x = a.bytes, y = b.bytes, out(576);
+    eng()->check(b2k_bls12381_gt_mul(eng()->ctx(), 1, x.data(), y.data(), out.data()));
+    bytes = out; return *this;
+  }
+  GTElt& Neg(const GTElt& a) {
+    Bytes x = a.bytes, out(576);
+    eng()->check(b2k_bls12381_gt_inv(eng()->ctx(), 1, x.data(), out.data()));
+    bytes = out; return *this;
+  }
+  GTElt& Sub(const GTElt& a, const GTElt& b) { GTElt nb(eng_); nb.Neg(b); return Add(a, nb); }      // kilic/gt.go:66-69
+  GTElt& Mul(const Scalar& s, const GTElt& q) {
+    Bytes sb = s.MarshalBinary(), x = q.bytes, out(576);
+    eng()->check(b2k_bls12381_gt_exp(eng()->ctx(), 1, sb.data(), x.data(), out.data()));
+    bytes = out; return *this;
+  }
   Bytes MarshalBinary() const { return bytes; }
+  void UnmarshalBinary(const Bytes& b) {
+    if (b.size() != 576) throw std::runtime_error("bls12-381: wrong buffer size for a GT element");
+    GTElt t(eng_); t.bytes = b;
+    GTElt one(eng_);
+    try { one.Add(t, one); } catch (const std::logic_error&) { throw std::runtime_error("bls12-381: GT coefficient is not a canonical field element"); }
+    bytes = b;
+  }
   int MarshalSize() const { return 576; }
+  std::string String() const { return "bls12-381.GT: " + hex(bytes); }
+  void bind(std::shared_ptr<Engine> e) { eng_ = std::move(e); }
+ private:
+  const std::shared_ptr<Engine>& eng() const { if (!eng_) throw std::logic_error("GTElt: no engine bound"); return eng_; }
+  std::shared_ptr<Engine> eng_;
+};
+
+// kyber.Group for GT (kilic/group.go:74-78: "bls12-381.GT", PointLen 576, not prime-order-flagged)
+class GroupGT {
+ public:
+  explicit GroupGT(std::shared_ptr<Engine> e) : eng_(std::move(e)) {}
+  std::string String() const { return "bls12-381.GT"; }
+  int ScalarLen() const { return 32; }
+  int PointLen() const { return 576; }
+  bool IsPrimeOrder() const { return false; }
+  GTElt NewPoint() const { return GTElt(eng_); }
+ private:
+  std::shared_ptr<Engine> eng_;
 };
 
 template <class E, int AFF, int WIRE, bool IS_G1>
@@ -314,13 +358,14 @@ using GroupG2 = GroupImpl<G2Elt, 192, 96, false>;
 // pairing.Suite (pairing/pairing.go:8-20) for BLS12-381 on the B200 engine, shaped like kilic.Suite
 class Suite {
  public:
-  explicit Suite(int device = 0) : eng_(std::make_shared<Engine>(device)), g1_(eng_), g2_(eng_) {}
+  explicit Suite(int device = 0) : eng_(std::make_shared<Engine>(device)), g1_(eng_), g2_(eng_), gt_(eng_) {}
   const GroupG1& G1() const { return g1_; }
   const GroupG2& G2() const { return g2_; }
+  const GroupGT& GT() const { return gt_; }
   std::string String() const { return "bls12-381.b200"; }
   // Pair(p1, p2): p1 in G1, p2 in G2 (kilic/suite.go:70-75)
   GTElt Pair(const Point& p1, const Point& p2) const {
-    GTElt r;
+    GTElt r(eng_);
     eng_->check(b2k_bls12381_pair(eng_->ctx(), 1, G1Elt::cast(p1).aff_.data(), G2Elt::cast(p2).aff_.data(), r.bytes.data()));
     return r;
   }
@@ -343,11 +388,97 @@ class Suite {
     eng_->check(b2k_bls12381_pairing_check(eng_->ctx(), n, a1.data(), a2.data(), b1.data(), b2.data(), ok.data()));
     return std::vector<bool>(ok.begin(), ok.end());
   }
+  // prod_i e(g1[i], g2[i]) == 1: n Miller loops, ONE final exponentiation (what pointGT.Miller / Finalize are exported for,
+  // pairing/bn254/point.go:768-786)
+  bool PairingProductIsOne(const std::vector<G1Elt>& g1, const std::vector<G2Elt>& g2) const {
+    size_t n = g1.size();
+    if (g2.size() != n) throw std::logic_error("PairingProductIsOne: length mismatch");
+    if (n == 0) return true;
+    Bytes a(96 * n), b(192 * n);
+    for (size_t i = 0; i < n; i++) { std::memcpy(&a[96 * i], g1[i].aff_.data(), 96); std::memcpy(&b[192 * i], g2[i].aff_.data(), 192); }
+    uint8_t ok = 0;
+    eng_->check(b2k_bls12381_pairing_product_check(eng_->ctx(), n, a.data(), b.data(), &ok));
+    return ok != 0;
+  }
+  // Miller / Finalize: Finalize(Miller(p, q)) == Pair(p, q); several Miller values may be multiplied (GTElt::Add) first
+  GTElt Miller(const Point& p1, const Point& p2) const {
+    GTElt r(eng_);
+    eng_->check(b2k_bls12381_miller(eng_->ctx(), 1, G1Elt::cast(p1).aff_.data(), G2Elt::cast(p2).aff_.data(), r.bytes.data()));
+    return r;
+  }
+  GTElt Finalize(const GTElt& f) const {
+    GTElt r(eng_);
+    Bytes x = f.bytes;
+    eng_->check(b2k_bls12381_final_exp(eng_->ctx(), 1, x.data(), r.bytes.data()));
+    return r;
+  }
   std::shared_ptr<Engine> engine() const { return eng_; }
  private:
   std::shared_ptr<Engine> eng_;
   GroupG1 g1_;
   GroupG2 g2_;
+  GroupGT gt_;
+};
+
+// ---- group/edwards25519 on the engine: Point.Mul and its batch form (group/edwards25519/point.go:235-258) --------------------
+// Points travel as their 32-byte compressed encodings (ge.go:99-150), scalars as 32 raw little-endian bytes (scalar.go:187-189).
+namespace ed25519 {
+using PointBytes = std::array<uint8_t, 32>;
+static const PointBytes BASE = {0x58, 0x66, 0x66, 0x66, 0x66, 0x66, 0x66, 0x66, 0x66, 0x66, 0x66, 0x66, 0x66, 0x66, 0x66, 0x66,
+                                0x66, 0x66, 0x66, 0x66, 0x66, 0x66, 0x66, 0x66, 0x66, 0x66, 0x66, 0x66, 0x66, 0x66, 0x66, 0x66};
+class Curve {
+ public:
+  explicit Curve(std::shared_ptr<Engine> e) : eng_(std::move(e)) {}
+  std::string String() const { return "Ed25519"; }                 // group/edwards25519/curve.go:18-20
+  int ScalarLen() const { return 32; }
+  int PointLen() const { return 32; }
+  // out[i] = s[i] * A[i]  (n x Point.Mul; BASELINE.json configs[0])
+  std::vector<PointBytes> MulBatch(const std::vector<PointBytes>& s, const std::vector<PointBytes>& A) const {
+    size_t n = s.size();
+    if (A.size() != n) throw std::logic_error("MulBatch: length mismatch");
+    std::vector<PointBytes> out(n);
+    if (n == 0) return out;
+    eng_->check(b2k_ed25519_mul_batch(eng_->ctx(), n, s[0].data(), A[0].data(), out[0].data()));
+    return out;
+  }
+  PointBytes Mul(const PointBytes& s, const PointBytes* A) const { return MulBatch({s}, {A ? *A : BASE})[0]; }   // nil = base point
+ private:
+  std::shared_ptr<Engine> eng_;
+};
+}  // namespace ed25519
+
+// ---- one process driving several GPUs: the sharded MSM of BASELINE.json configs[4] (b2k_bls12381_g1_msm_multi_gpu) -------------
+class MultiGPU {
+ public:
+  explicit MultiGPU(int ngpu) {
+    for (int g = 0; g < ngpu; g++) {
+      b2k_ctx* c = nullptr;
+      if (b2k_create(g, &c) != 0) { close(); throw std::runtime_error("b2kyber: device unavailable"); }
+      ctxs_.push_back(c);
+      b2k_comm* cm = nullptr;
+      if (b2k_comm_create(c, ngpu, g, &cm) != 0) { close(); throw std::runtime_error(std::string("b2kyber: ") + b2k_last_error(c)); }
+      comms_.push_back(cm);
+    }
+    if (b2k_comm_connect_local(comms_.data(), ngpu) != 0) { close(); throw std::runtime_error("b2kyber: peer access between the devices is not available"); }
+  }
+  ~MultiGPU() { close(); }
+  MultiGPU(const MultiGPU&) = delete;
+  // 48-byte compressed sum of s[i] * p[i] over all devices
+  Bytes MSM(const Bytes& scalars, const Bytes& points) const {
+    size_t n = scalars.size() / 32;
+    Bytes out(48);
+    int rc = b2k_bls12381_g1_msm_multi_gpu(const_cast<b2k_comm**>(comms_.data()), (int)comms_.size(), n, scalars.data(), points.data(), out.data());
+    if (rc != 0) throw std::logic_error(std::string("b2kyber: ") + b2k_last_error(ctxs_[0]));
+    return out;
+  }
+ private:
+  void close() {
+    for (auto* c : comms_) b2k_comm_destroy(c);
+    for (auto* c : ctxs_) b2k_destroy(c);
+    comms_.clear(); ctxs_.clear();
+  }
+  std::vector<b2k_ctx*> ctxs_;
+  std::vector<b2k_comm*> comms_;
 };
 
 // sign/bls scheme on G1 (sign/bls/bls.go:33-44): Sign = x * H(m), Verify = ValidatePairing(H(m), X, sig, G2 base)

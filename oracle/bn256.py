@@ -117,5 +117,59 @@ def hash_to_g1(m: bytes):
         x += 1
 
 
+# ---- HashG1: HKDF-SHA256 to the base field, then Shallue-van de Woestijne (pairing/bn256/hash.go:10-110) -----------------
+# s = sqrt(-3): the root the reference uses, from its Montgomery limbs (pairing/bn256/constants.go:104-105, data; R = 2^256)
+SVDW_S = (0x236e675956be783b | 0x053957e6f379ab64 << 64 | 0xe60789a768f4a5c4 << 128 | 0x04f8979dd8bad754 << 192) * pow(1 << 256, -1, P) % P
+assert SVDW_S * SVDW_S % P == P - 3
+SVDW_S_M1_HALF = (SVDW_S - 1) * pow(2, -1, P) % P
+
+
+def hash_to_base(msg: bytes, dst: bytes = None) -> int:
+    """gfp.go:46-67 hashToBase: 48 bytes of HKDF-SHA256(secret = msg, salt = dst, info = "H2C" 0 1), big-endian, mod p"""
+    import hmac
+    salt = dst if dst else bytes(32)                              # Go's hkdf: a nil salt is HashLen zero bytes
+    prk = hmac.new(salt, msg, hashlib.sha256).digest()
+    info = b"H2C\x00\x01"
+    t1 = hmac.new(prk, info + b"\x01", hashlib.sha256).digest()
+    t2 = hmac.new(prk, t1 + info + b"\x02", hashlib.sha256).digest()
+    return int.from_bytes((t1 + t2)[:48], "big") % P
+
+
+def _sign0(x: int) -> int:                                        # gfp.go:137-148
+    return 1 if x >= (P - 1) // 2 else -1
+
+
+def _legendre(x: int) -> int:                                     # gfp.go:150-162
+    f = pow(x, (P - 1) // 2, P)
+    return 0 if f == 0 else 2 * (f & 1) - 1
+
+
+def map_to_curve(t: int):
+    """hash.go:14-110, statement by statement (Fermat inverse: 0 -> 0)"""
+    a = (1 + B + t * t) % P
+    st = SVDW_S * t % P
+    w0 = pow(st * a % P, P - 2, P)
+    w = st * st % P * w0 % P
+    e = _sign0(t)
+
+    def finish(x):
+        y = pow((x * x * x + B) % P, (P + 1) // 4, P)
+        if e != _sign0(y):
+            y = -y % P
+        return (x, y)
+    x1 = (SVDW_S_M1_HALF - t * w) % P
+    if _legendre((x1 ** 3 + B) % P) == 1:
+        return finish(x1)
+    x2 = (-1 - x1) % P
+    if _legendre((x2 ** 3 + B) % P) == 1:
+        return finish(x2)
+    x3 = (pow(a, 4, P) * w0 % P * w0 + 1) % P
+    return finish(x3)
+
+
+def hash_g1(msg: bytes, dst: bytes = None):
+    return map_to_curve(hash_to_base(msg, dst))
+
+
 assert (G1[1] ** 2 - G1[0] ** 3 - B) % P == 0
 assert f2_sub(f2_mul(G2[1], G2[1]), f2_add(f2_mul(f2_mul(G2[0], G2[0]), G2[0]), TWIST_B)) == (0, 0)

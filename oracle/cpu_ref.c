@@ -233,6 +233,13 @@ static void aff_store_compressed(uint8_t* out, const aff* a) {
   for (int i = 5; i >= 0; i--) { if (y[i] != ny[i]) { larger = y[i] > ny[i]; break; } }
   out[0] |= 0x80 | (larger ? 0x20 : 0);
 }
+/* operand form 96 B x||y (what the engine's *_affine entry points return); infinity = all zero */
+static void aff_store_affine(uint8_t* out, const aff* a) {
+  if (a->inf) { memset(out, 0, 96); return; }
+  fp one = {1, 0, 0, 0, 0, 0}, x, y;
+  fp_mul(x, a->x, one); fp_mul(y, a->y, one);
+  fp_to_be(out, x); fp_to_be(out + 48, y);
+}
 static void scalar_from_be(uint64_t k[4], const uint8_t* b) {
   for (int i = 0; i < 4; i++) {
     uint64_t v = 0;
@@ -337,7 +344,7 @@ static void pippenger_range(jac* out, size_t n, const uint8_t* scalars, const ui
 
 /* ---- threading ------------------------------------------------------------------------------------ */
 typedef struct {
-  int mode;  /* 0 = mul batch, 1 = Mul+Add loop partial, 2 = pippenger partial */
+  int mode;  /* 0 = mul batch, 1 = Mul+Add loop partial, 2 = pippenger partial, 3 = mul batch with operand-form output */
   size_t lo, hi;
   const uint8_t *scalars, *points;
   uint8_t* out;
@@ -363,6 +370,7 @@ static void* worker(void* arg) {
     jac r;
     g1_mul_wnaf(&r, k, &p);
     if (j->mode == 0) { aff a; jac_to_aff(&a, &r); aff_store_compressed(j->out + 48 * i, &a); }
+    else if (j->mode == 3) { aff a; jac_to_aff(&a, &r); aff_store_affine(j->out + 96 * i, &a); }
     else jac_add(&j->partial, &j->partial, &r);   /* Acc.Add(Acc, Tmp)  share/poly.go:472 */
   }
   return NULL;
@@ -393,6 +401,10 @@ static int run_jobs(int mode, size_t n, const uint8_t* scalars, const uint8_t* p
 /* n independent Point.Mul -> 48-byte MarshalBinary each */
 int cpu_g1_mul_batch(size_t n, const uint8_t* scalars, const uint8_t* points, uint8_t* out48n, int nthreads) {
   return run_jobs(0, n, scalars, points, out48n, nthreads, NULL);
+}
+/* the same with 96-byte operand-form results (bench.py builds its CPU sample with it: no per-point Python) */
+int cpu_g1_mul_batch_affine(size_t n, const uint8_t* scalars, const uint8_t* points, uint8_t* out96n, int nthreads) {
+  return run_jobs(3, n, scalars, points, out96n, nthreads, NULL);
 }
 /* the reference's way to do an MSM: loop of Mul + Add (share/poly.go:461-473) */
 int cpu_g1_msm_muladd(size_t n, const uint8_t* scalars, const uint8_t* points, uint8_t* out48, int nthreads) {

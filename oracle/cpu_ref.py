@@ -22,7 +22,7 @@ def build(force: bool = False) -> str:
 
 def load() -> C.CDLL:
     lib = C.CDLL(build())
-    for name in ("cpu_g1_mul_batch", "cpu_g1_msm_muladd", "cpu_g1_msm_pippenger"):
+    for name in ("cpu_g1_mul_batch", "cpu_g1_mul_batch_affine", "cpu_g1_msm_muladd", "cpu_g1_msm_pippenger"):
         fn = getattr(lib, name)
         fn.restype = C.c_int
         fn.argtypes = [C.c_size_t, C.c_char_p, C.c_char_p, C.c_char_p, C.c_int]
@@ -40,6 +40,10 @@ def _call(lib, name, scalars: bytes, points: bytes, out_len: int, threads: int) 
 
 def g1_mul_batch(lib, scalars: bytes, points: bytes, threads: int = 1) -> bytes:
     return _call(lib, "cpu_g1_mul_batch", scalars, points, 48 * (len(scalars) // 32), threads)
+
+
+def g1_mul_batch_affine(lib, scalars: bytes, points: bytes, threads: int = 1) -> bytes:
+    return _call(lib, "cpu_g1_mul_batch_affine", scalars, points, 96 * (len(scalars) // 32), threads)
 
 
 def g1_msm_muladd(lib, scalars: bytes, points: bytes, threads: int = 1) -> bytes:

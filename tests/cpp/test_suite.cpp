@@ -111,6 +111,54 @@ int main() {
   try { suite.Pair(qb, pa); } catch (const std::logic_error&) { panicked = true; }
   CHECK("pairing.wrong_group_panics", panicked);
 
+  // GT as a kyber.Group (kilic/gt.go:33-83): Add = product, Neg = inverse, Mul = exponentiation, Null = 1
+  {
+    CHECK("gt.group_names", suite.GT().String() == "bls12-381.GT" && suite.GT().PointLen() == 576 && !suite.GT().IsPrimeOrder());
+    GTElt ea = suite.Pair(pa, g2), eb = suite.Pair(g1, qb), one = suite.GT().NewPoint();
+    GTElt sum = suite.GT().NewPoint(); sum.Add(ea, eb);                    // e(aG1, G2) e(G1, bG2) = e(G1, G2)^(a+b)
+    Scalar apb; apb.Add(sa, sb);
+    GTElt base = suite.Pair(g1, g2), pw = suite.GT().NewPoint(); pw.Mul(apb, base);
+    CHECK("gt.add_is_product_mul_is_exp", sum.Equal(pw));
+    GTElt ng = suite.GT().NewPoint(); ng.Neg(ea);
+    GTElt z = suite.GT().NewPoint(); z.Add(ea, ng);
+    CHECK("gt.neg_gives_null", z.Equal(one));
+    GTElt df = suite.GT().NewPoint(); df.Sub(sum, eb);
+    CHECK("gt.sub", df.Equal(ea));
+    GTElt e12 = suite.GT().NewPoint(); e12.Mul(sb, ea);                     // e(aG1, G2)^b == e(aG1, bG2)
+    CHECK("gt.mul_bilinear", e12.Equal(e1));
+    GTElt al = ea.Clone(); al.Add(al, al); Scalar two(2); GTElt dbl = suite.GT().NewPoint(); dbl.Mul(two, ea);
+    CHECK("gt.aliasing_add", al.Equal(dbl));
+    GTElt rt = suite.GT().NewPoint(); rt.UnmarshalBinary(ea.MarshalBinary());
+    CHECK("gt.marshal_roundtrip", rt.Equal(ea) && ea.MarshalSize() == 576);
+    bool bad = false;
+    try { Bytes b(576, 0xff); rt.UnmarshalBinary(b); } catch (const std::runtime_error&) { bad = true; }
+    CHECK("gt.unmarshal_rejects_noncanonical", bad);
+    bool pan = false;
+    try { one.Base(); } catch (const std::logic_error&) { pan = true; }
+    CHECK("gt.base_panics", pan);
+    // Miller / Finalize and the n-pair product with one final exponentiation
+    CHECK("pairing.finalize_of_miller_is_pair", suite.Finalize(suite.Miller(pa, qb)).Equal(e1));
+    GTElt m2 = suite.GT().NewPoint(); m2.Add(suite.Miller(pa, g2), suite.Miller(g1, qb));
+    CHECK("pairing.one_final_exp_for_a_product", suite.Finalize(m2).Equal(sum));
+    G1Elt npab(eng); npab.Neg(pab);
+    CHECK("pairing.product_is_one", suite.PairingProductIsOne({pa, npab}, {qb, g2}));
+    CHECK("pairing.product_is_not_one", !suite.PairingProductIsOne({pa, pab}, {qb, g2}));
+  }
+
+  // group/edwards25519 through the engine: s*B chains and the a*(b*B) == b*(a*B) exchange of examples/dh_test.go
+  {
+    ed25519::Curve ed(eng);
+    ed25519::PointBytes sa2{}, sb2{};
+    for (int i = 0; i < 31; i++) { sa2[i] = (uint8_t)rng(); sb2[i] = (uint8_t)rng(); }
+    sa2[31] = 0x0f; sb2[31] = 0x0e;                                           // < 2^253: inside the a[31] <= 127 precondition
+    ed25519::PointBytes A = ed.Mul(sa2, nullptr), B = ed.Mul(sb2, nullptr);
+    CHECK("ed25519.dh", ed.Mul(sa2, &B) == ed.Mul(sb2, &A));
+    ed25519::PointBytes onele{}; onele[0] = 1;
+    CHECK("ed25519.one_times_base", ed.Mul(onele, nullptr) == ed25519::BASE);
+    auto outs = ed.MulBatch({sa2, sb2, onele}, {ed25519::BASE, ed25519::BASE, A});
+    CHECK("ed25519.batch", outs[0] == A && outs[1] == B && outs[2] == A);
+  }
+
   // sign/bls on G1 (sign/bls/bls.go:33-96): sign, verify, reject wrong message / key / mangled signature
   SchemeOnG1 scheme(suite);
   Scalar sk = pick(rng), sk2 = pick(rng);

@@ -11,6 +11,7 @@ Sources:
   pairing/bls12381/bls12381_test.go:877-904                      (TestSignatureEdgeCase)
   pairing/bn254/point_test.go:14-124, test_vectors_test.go       (bn254 Keccak/SvdW hash-to-G1 vectors)
   encrypt/ibe/ibe_test.go:202-245                                (the one GT-byte dependent vector; inlined in the tests)
+  pairing/bn256/hash_test.go:11-19,45-57                         (HashG1: 11 marshalled points, msg = one byte i, dst = nil)
 """
 import glob
 import json
@@ -62,6 +63,17 @@ def bn254_hash_vectors():
     json.dump(out, open(os.path.join(HERE, "bn254_hash_vectors.json"), "w"), indent=1)
 
 
+def bn256_hashg1_vectors():
+    src = open(f"{REF}/pairing/bn256/hash_test.go").read()
+    body = src.split("var marshaledHashes")[1]
+    rows = re.findall(r"\[64\]byte\{(\d[^}{]*)\}", body)
+    out = {"_source": "pairing/bn256/hash_test.go:11-19 (TestKnownHashes: HashG1([]byte{byte(i)}, nil)) and :45-57 (data only)",
+           "cases": [{"msg_hex": "%02x" % i, "dst_hex": "", "point": bytes(int(x) for x in re.findall(r"\d+", r)).hex()}
+                     for i, r in enumerate(rows)]}
+    assert len(out["cases"]) == 11 and all(len(c["point"]) == 128 for c in out["cases"])
+    json.dump(out, open(os.path.join(HERE, "bn256_hashg1_vectors.json"), "w"), indent=1)
+
+
 def main():
     json.dump({"G1": yaml_vectors("G1", "pubkey"), "G2": yaml_vectors("G2", "signature")},
               open(os.path.join(HERE, "bls12381_deserialization.json"), "w"), indent=1)
@@ -79,6 +91,7 @@ def main():
     }
     json.dump(kat, open(os.path.join(HERE, "bls12381_signature_kats.json"), "w"), indent=1)
     bn254_hash_vectors()
+    bn256_hashg1_vectors()
     print("wrote golden fixtures")
 
 

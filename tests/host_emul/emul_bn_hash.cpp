@@ -35,6 +35,14 @@ void emul_bn254_hash_to_g1(const uint8_t* msg, uint32_t len, const uint8_t* dst,
   bn254_hash_to_g1(p, msg, len, dst, dst_len);
   Bn254G1::store(out64, p);
 }
+void emul_bn256_hash_g1(const uint8_t* msg, uint32_t len, const uint8_t* dst, uint32_t dst_len, uint8_t* out64) {
+  Affine<B256Fp> p;
+  bn256_hash_g1(p, msg, len, dst, dst_len);
+  Bn256G1::store(out64, p);
+}
+void emul_hmac_sha256(const uint8_t* key, uint32_t key_len, const uint8_t* msg, uint32_t len, uint8_t* out32) {
+  hmac_sha256(out32, key, key_len, msg, len, nullptr, 0, nullptr, 0);
+}
 void emul_bn256_hash_to_g1(const uint8_t* msg, uint32_t len, uint8_t* out64) {
   Affine<B256Fp> p;
   bn256_hash_to_g1(p, msg, len);

@@ -42,6 +42,21 @@ def test_bn256_hash_matches_oracle(engine):
         assert out[64 * i:64 * i + 64] == o6.g1_marshal(o6.hash_to_g1(m)), i
 
 
+def test_bn256_hashg1_reference_kats_and_oracle(engine):
+    """bn256 HashG1 (pairing/bn256/hash.go:10-110) on the device: the reference's 11 marshalled points (hash_test.go:11-57,
+    msg = one byte i, nil dst), then ragged messages with and without a dst against the oracle"""
+    import json, os
+    fx = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "bn256_hashg1_vectors.json")))["cases"]
+    out = engine.bn256_hash_g1([bytes.fromhex(c["msg_hex"]) for c in fx])
+    assert out.hex() == "".join(c["point"] for c in fx)
+    rng = random.Random(34)
+    msgs = [b"", bytes(55), bytes(64), bytes(119), bytes(120)] + [bytes(rng.getrandbits(8) for _ in range(rng.randrange(1, 200))) for _ in range(120)]
+    for dst in (b"", b"B2K-DST", bytes(70)):
+        out = engine.bn256_hash_g1(msgs, dst)
+        for i, m in enumerate(msgs):
+            assert out[64 * i:64 * i + 64] == o6.g1_marshal(o6.hash_g1(m, dst or None)), (i, dst)
+
+
 def test_bls_sign_verify_on_bn254_all_on_device(engine):
     rng = random.Random(33)
     n = 12

@@ -117,3 +117,56 @@ def test_tbls_recover_flow(engine):
     assert sig == o.g1_compress(o.g1_mul(coeffs[0], hm))             # = bls.Sign(group secret, msg)
     group_pk = o.g2_compress(o.g2_mul(coeffs[0]))
     assert engine.bls12381_verify_g1sig(group_pk, [msg], h.DST_G1, sig) == b"\x01"
+
+
+def test_commit_batch_and_recover_pubpoly(engine):
+    """PriPoly.Commit as a fixed-base batch (share/poly.go:143-149) and share.RecoverPubPoly (poly.go:480-508): from t public
+    shares of a random polynomial the engine must return exactly the dealer's commitments a_k * G (and the oracle's
+    restatement of lagrangeBasis agrees); G1, G2 and bn254; arbitrary base point; duplicate index refused."""
+    from kyber_b200 import B2KError
+    from oracle import bn254 as c4
+    rng = random.Random(85)
+    t = 17
+    coeffs = [rng.randrange(o.R) for _ in range(t)]
+    sc = b"".join(o.scalar_to_bytes(c) for c in coeffs)
+    commits = engine.commit_batch("bls12381_g1", sc)                             # a_k * G1
+    assert commits == b"".join(o.g1_to_affine_bytes(o.g1_mul(c)) for c in coeffs)
+    H = o.g1_mul(rng.randrange(1, o.R))
+    assert engine.commit_batch("bls12381_g1", sc, o.g1_to_affine_bytes(H)) == b"".join(o.g1_to_affine_bytes(o.g1_mul(c, H)) for c in coeffs)
+    idx = sorted(rng.sample(range(100), t))
+    shares = engine.bls12381_pubpoly_eval(1, commits, idx)                       # PubPoly.Eval at the share indices
+    got = engine.recover_pubpoly("bls12381_g1", idx, shares)
+    assert got == commits
+    # the oracle's restatement of RecoverPubPoly on a small case
+    small = [(i, o.g1_from_affine_bytes(shares[96 * k:96 * k + 96])) for k, i in enumerate(idx[:5])]
+    want = share_poly.recover_pubpoly(_G1, small, 5)
+    assert engine.recover_pubpoly("bls12381_g1", idx[:5], shares[:5 * 96]) == b"".join(o.g1_to_affine_bytes(p) for p in want)
+    # commits[0] is RecoverCommit's point
+    assert o.g1_compress(o.g1_from_affine_bytes(got[:96])) == engine.bls12381_recover_commit(1, idx, shares)
+    # G2
+    c2 = engine.commit_batch("bls12381_g2", sc[:32 * 6])
+    assert c2 == b"".join(o.g2_to_affine_bytes(o.g2_mul(c)) for c in coeffs[:6])
+    sh2 = engine.bls12381_pubpoly_eval(2, c2, idx[:6])
+    assert engine.recover_pubpoly("bls12381_g2", idx[:6], sh2) == c2
+    # bn254
+    co4 = [rng.randrange(c4.ORDER) for _ in range(9)]
+    cm4 = engine.commit_batch("bn254", b"".join(c.to_bytes(32, "big") for c in co4))
+    assert cm4 == b"".join(c4.g1_marshal(c4.g1_mul(c)) for c in co4)
+    i4 = [3, 4, 9, 10, 11, 40, 41, 77, 500]
+    sh4 = b"".join(c4.g1_marshal(c4.g1_mul(sum(c * pow(i + 1, k, c4.ORDER) for k, c in enumerate(co4)) % c4.ORDER)) for i in i4)
+    assert engine.recover_pubpoly("bn254", i4, sh4) == cm4
+    with pytest.raises(B2KError):
+        engine.recover_pubpoly("bls12381_g1", [1, 2, 2], shares[:3 * 96])
+
+
+def test_recover_pubpoly_large_threshold(engine):
+    """t = 300: the master-polynomial kernel runs 300 block-synchronised steps; result = the dealer's commitments"""
+    rng = random.Random(86)
+    t = 300
+    coeffs = [rng.randrange(o.R) for _ in range(t)]
+    commits = engine.commit_batch("bls12381_g1", b"".join(o.scalar_to_bytes(c) for c in coeffs))
+    idx = sorted(rng.sample(range(2000), t))
+    shares = engine.bls12381_pubpoly_eval(1, commits, idx)
+    assert engine.recover_pubpoly("bls12381_g1", idx, shares) == commits
+    for k in (0, 1, t - 1):
+        assert commits[96 * k:96 * k + 96] == o.g1_to_affine_bytes(o.g1_mul(coeffs[k]))

@@ -365,6 +365,21 @@ def test_bn_hash_to_g1_bodies_against_reference_vectors():
         m = bytes.fromhex(c["msg_hex"])
         lib.emul_bn254_hash_to_g1(m, len(m), dst, len(dst), out64)
         assert out64.raw.hex() == c["point"]
+    # bn256 HashG1 (pairing/bn256/hash.go:10-110): HMAC-SHA256 vs hashlib, then the reference's 11 KATs (hash_test.go:11-57)
+    import hmac
+    for key, m in ((b"", b""), (bytes(32), b"abc"), (b"k" * 64, bytes(100)), (b"long key " * 20, bytes(range(200)))):
+        lib.emul_hmac_sha256(key, len(key), m, len(m), out32)
+        assert out32.raw == hmac.new(key, m, hashlib.sha256).digest()
+    for c in json.load(open(os.path.join(GOLD, "bn256_hashg1_vectors.json")))["cases"]:
+        m = bytes.fromhex(c["msg_hex"])
+        lib.emul_bn256_hash_g1(m, len(m), None, 0, out64)
+        assert out64.raw.hex() == c["point"]
+    rng = random.Random(77)
+    for _ in range(40):                                                                # non-nil dst, ragged lengths: vs the oracle
+        m = bytes(rng.getrandbits(8) for _ in range(rng.randrange(0, 150)))
+        d = bytes(rng.getrandbits(8) for _ in range(rng.choice((1, 16, 64, 65, 200))))
+        lib.emul_bn256_hash_g1(m, len(m), d, len(d), out64)
+        assert out64.raw == o6.g1_marshal(o6.hash_g1(m, d))
     bdn_msg = json.load(open(os.path.join(GOLD, "bdn_bn256_fixtures.json")))["fixtures"]["msg"].encode()
     for m in (bdn_msg, b"", b"x" * 200, bytes(range(64))):
         lib.emul_bn256_hash_to_g1(m, len(m), out64)

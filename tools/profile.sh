@@ -2,10 +2,12 @@
 # Run on the GPU box (under gpurun): launch list + one full ncu capture of the bucket-accumulate kernel.
 # Usage: tools/profile.sh <round-tag>
 set -u
-TAG=${1:-r01}
+TAG=${1:-r02}
 mkdir -p gpurun_out
 export B2K_SKIP_CPU_BASELINE=1
 export B2K_SKIP_PAIRINGS=1
+export B2K_SKIP_SECTIONS=1
+export B2K_SKIP_SUSTAINED=1
 # every launch with its device time (cold-cache, serialised: compare SHARES, not absolutes)
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_${TAG}.csv \
     python bench.py --steps 2 --warmup 3 > gpurun_out/bench_under_ncu_${TAG}.log 2>&1
@@ -20,14 +22,14 @@ ncu -i gpurun_out/accumulate_${TAG}.ncu-rep --page details > gpurun_out/${TAG}_a
 ncu -i gpurun_out/accumulate_${TAG}.ncu-rep --page raw --csv > gpurun_out/${TAG}_accumulate_ncu_raw.csv 2>&1
 python tools/ncu_traffic.py gpurun_out/${TAG}_accumulate_ncu_raw.csv ${TAG} > gpurun_out/accumulate_traffic.json 2> gpurun_out/ncu_traffic_${TAG}.err
 rm -f gpurun_out/accumulate_${TAG}.ncu-rep
-# pairing kernel: one full capture on a small batch (the kernel is long: keep n small)
+# pairing kernel: one full capture AT THE BENCHMARK SIZE (65 536 checks, the batch bench.py times)
 cat > /tmp/pair_probe.py <<'PY'
 import sys
 sys.path.insert(0, '.')
 import torch
 from kyber_b200 import Engine
 from oracle import bls12381 as o
-eng = Engine(0); n = 8192
+eng = Engine(0); n = 65536
 a1 = torch.frombuffer(bytearray(o.g1_to_affine_bytes(o.g1_mul(12345)) * n), dtype=torch.uint8).cuda()
 a2 = torch.frombuffer(bytearray(o.g2_to_affine_bytes(o.g2_mul(6789)) * n), dtype=torch.uint8).cuda()
 ok = torch.empty(n, dtype=torch.uint8, device='cuda')
