@@ -106,8 +106,9 @@ int b2k_set_msm_chunk(b2k_ctx* ctx, int m);
  * multiplications move to the second level, which has m1 times fewer operands).  levels: 0 = automatic, 1, 2; m1, m2 = chunk
  * sizes of the two levels (powers of two, 0 = default 8 and 4).  Same result bytes either way; A/B and tuning aid. */
 int b2k_set_msm_reduce(b2k_ctx* ctx, int levels, int m1, int m2);
-/* code layout of the field products inside the G1 MSM kernels (b2k_bls12381_g1_msm_dev): 0 = inlined at every use,
- * 1 = one out-of-line body called by value (instruction-cache friendly); identical results, A/B aid. */
+/* code layout of the field products inside the G1 MSM / Point.Mul kernels (b2k_bls12381_g1_msm_dev, _mul_batch*_dev):
+ * 0 = one out-of-line body called by value (instruction-cache friendly; the library default), 1 = inlined at every use
+ * (the round-1 layout); identical results, A/B aid. */
 int b2k_set_msm_layout(b2k_ctx* ctx, int layout);
 /* Number of kernels launched by this context so far. */
 uint64_t b2k_launch_count(const b2k_ctx* ctx);

@@ -6,8 +6,10 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libb2kyber.so")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-              "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC"]
-UNITS = ["b2k_api.cu", "b2k_msm_compact.cu", "b2k_g1_mul.cu", "b2k_bn254.cu", "b2k_g2.cu", "b2k_pairing.cu", "b2k_pairing_compact.cu", "b2k_h2c.cu", "b2k_share.cu", "b2k_share2.cu", "b2k_ed25519.cu", "b2k_bn256.cu", "b2k_bn254_pairing.cu", "b2k_bdn.cu", "b2k_bn_hash.cu", "b2k_bn_codec.cu", "b2k_multi.cu", "b2k_gt.cu"]
+              "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC",
+              "-Xfatbin", "-compress-all",   # the library is ~85 MB of SASS + line tables uncompressed, ~26 MB compressed
+              "-DB2K_COMPACT_FIELD=1"]     # field products as out-of-line by-value calls (fp.cuh); *_inlined.cu units undo it for A/B
+UNITS = ["b2k_api.cu", "b2k_msm_inlined.cu", "b2k_g1_mul.cu", "b2k_bn254.cu", "b2k_g2.cu", "b2k_pairing.cu", "b2k_pairing_inlined.cu", "b2k_h2c.cu", "b2k_share.cu", "b2k_share2.cu", "b2k_ed25519.cu", "b2k_bn256.cu", "b2k_bn254_pairing.cu", "b2k_bdn.cu", "b2k_bn_hash.cu", "b2k_bn_codec.cu", "b2k_multi.cu", "b2k_gt.cu"]
 
 
 def _nvcc() -> str:
@@ -30,30 +32,32 @@ def _hash_files(paths) -> str:
     return h.hexdigest()
 
 
-def _headers():
-    out = []
-    for root in (CSRC, os.path.join(HERE, "..", "include")):
-        out += [os.path.join(root, fn) for fn in sorted(os.listdir(root)) if fn.endswith((".cuh", ".h"))]
-    return out
+def _closure(src: str) -> list:
+    """The source plus every project header it reaches through #include "..." (transitively), in a stable order."""
+    import re
+    seen, todo = [], [os.path.abspath(src)]
+    while todo:
+        f = todo.pop()
+        if f in seen or not os.path.exists(f):
+            continue
+        seen.append(f)
+        with open(f, "r", errors="replace") as fh:
+            for inc in re.findall(r'^\s*#\s*include\s+"([^"]+)"', fh.read(), flags=re.M):
+                todo.append(os.path.abspath(os.path.join(os.path.dirname(f), inc)))
+    return [seen[0]] + sorted(seen[1:])
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile kyber_b200/libb2kyber.so.  Incremental per translation unit: a unit is recompiled when its own source or ANY
-    header changed (stamp next to the object), the library is relinked when an object changed.  Returns the library path."""
-    hdrs = _headers()
+    """Compile kyber_b200/libb2kyber.so.  Incremental per translation unit: a unit is recompiled when its own source or a
+    header it includes (transitively) changed (stamp next to the object), the library is relinked when an object changed.  Returns the library path."""
     objs, procs = [], []
     for u in UNITS:
         src = os.path.join(CSRC, u)
         obj = os.path.join(CSRC, u.replace(".cu", ".o"))
         objs.append(obj)
-        stamp = _hash_files([src] + hdrs)
+        stamp = _hash_files(_closure(src))
         sf = obj + ".stamp"
         if not force and os.path.exists(obj) and os.path.exists(sf) and open(sf).read() == stamp:
-            continue
-        if not force and os.path.exists(obj) and not os.path.exists(sf) and \
-                os.path.getmtime(obj) > max(os.path.getmtime(p) for p in [src] + hdrs):
-            with open(sf, "w") as f:          # an object newer than all of its inputs (built before stamps existed): adopt it
-                f.write(stamp)
             continue
         cmd = [_nvcc(), *NVCC_FLAGS, "-c", src, "-o", obj]
         if verbose:
@@ -77,7 +81,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     lf = LIB + ".stamp"
     if not procs and not force and os.path.exists(LIB) and os.path.exists(lf) and open(lf).read() == link_stamp:
         return LIB
-    cmd = [_nvcc(), "-shared", "-o", LIB + ".tmp", *objs, "-lcudart", "-ldl"]
+    cmd = [_nvcc(), "-shared", "-Wno-deprecated-gpu-targets", "-o", LIB + ".tmp", *objs, "-lcudart", "-ldl"]
     subprocess.run(cmd, check=True)
     os.replace(LIB + ".tmp", LIB)          # atomic: a reader (or a snapshot of the tree) never sees a half-written library
     with open(lf, "w") as f:

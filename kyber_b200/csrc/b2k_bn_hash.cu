@@ -11,7 +11,7 @@ __global__ void __launch_bounds__(128) k_bn254_hash_to_g1(size_t n, const uint8_
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   Affine<NFp254> a;
-  bn254_hash_to_g1(a, msgs + offs[i], offs[i + 1] - offs[i], dst, dst_len);
+  bn254_hash_to_g1(a, msgs + offs[i], (offs[i + 1] >= offs[i] ? offs[i + 1] - offs[i] : 0u), dst, dst_len);
   Bn254G1::store(out + 64 * i, a);
 }
 
@@ -20,7 +20,7 @@ __global__ void __launch_bounds__(128) k_bn256_hash_to_g1(size_t n, const uint8_
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   Affine<B256Fp> a;
-  bn256_hash_to_g1(a, msgs + offs[i], offs[i + 1] - offs[i]);
+  bn256_hash_to_g1(a, msgs + offs[i], (offs[i + 1] >= offs[i] ? offs[i + 1] - offs[i] : 0u));
   Bn256G1::store(out + 64 * i, a);
 }
 
@@ -30,7 +30,7 @@ __global__ void __launch_bounds__(128) k_bn256_hash_g1(size_t n, const uint8_t* 
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   Affine<B256Fp> a;
-  bn256_hash_g1(a, msgs + offs[i], offs[i + 1] - offs[i], dst, dst_len);
+  bn256_hash_g1(a, msgs + offs[i], (offs[i + 1] >= offs[i] ? offs[i + 1] - offs[i] : 0u), dst, dst_len);
   Bn256G1::store(out + 64 * i, a);
 }
 

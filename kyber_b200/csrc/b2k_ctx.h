@@ -16,6 +16,7 @@ struct b2k_ctx {
   cudaStream_t stream = nullptr;
   bool own_stream = false;
   b2k_arena arena;
+  b2k_arena arena_in;   // second arena: host-call inputs that must survive a nested call which re-reserves `arena` (bls.Verify wrappers)
   uint32_t* d_flags = nullptr;
   uint32_t* h_flags = nullptr;   // pinned
   cudaEvent_t ev[B2K_N_EV];
@@ -39,7 +40,7 @@ struct b2k_ctx {
   int reduce_levels = 0;            // bucket reduction: 0 = automatic (two levels for >= 4096 buckets per window), 1, 2
   int reduce_m1 = 0, reduce_m2 = 0; // chunk sizes of the two levels (0 = 8 and 4), tuning aid
   int pair_variant = 0; // launch-bound variant / code layout of the pairing kernels (tuning aid)
-  int msm_layout = 0;   // 0 = inlined field products, 1 = compact (out-of-line by-value products, b2k_msm_compact.cu): A/B aid
+  int msm_layout = 0;   // 0 = compact field products (library default), 1 = inlined at every use (b2k_msm_inlined.cu): A/B aid
   int last_plan[20] = {};           // what the last MSM ran with: c, W, buckets/window, chunk, slice length, affine rounds, their batch widths
   uint64_t launches = 0;
   std::string err;
@@ -49,7 +50,10 @@ struct b2k_ctx {
 // take returns 256-byte aligned sub-buffers or nullptr.
 int b2k_arena_reserve(b2k_ctx* ctx, size_t bytes);
 void* b2k_arena_take(b2k_ctx* ctx, size_t bytes);
+// the input arena: one buffer of at least `bytes` (grown on demand, never shrunk); nullptr on allocation failure
+void* b2k_arena_in(b2k_ctx* ctx, size_t bytes);
 
 // internal entry points shared between translation units (not part of include/b2kyber.h)
 extern "C" int b2k_internal_bls12381_g1_msm_buckets_host(b2k_ctx* c, size_t n, const uint8_t* s, const uint8_t* p, void* b, size_t cap, int* plan);
-extern "C" int b2k_internal_bls12381_g1_msm_dev_compact(b2k_ctx* c, size_t n, const void* s, const void* p, void* o, int affine_out);
+extern "C" int b2k_internal_bls12381_g1_msm_dev_inlined(b2k_ctx* c, size_t n, const void* s, const void* p, void* o, int affine_out);
+extern "C" int b2k_internal_bls12381_g1_mul_batch_dev_inlined(b2k_ctx* c, size_t n, const void* s, const void* p, void* o, int affine_out);

@@ -8,8 +8,8 @@
 //   product-of-pairings checks  prod_i e(P_i, Q_i) == 1   ("multiply Miller outputs, one final exponentiation");
 //       the 2-pair special case is Suite.ValidatePairing (kilic/suite.go:57-68, pairing/bn254/suite.go:138-144)
 //   G1 / G2 Point.Add, Sub, Neg as batches     kilic/g1.go:92-108, g2.go:91-107 (single operations in the reference)
-// One thread per element / per pair; the product check multiplies the Miller values of a block in shared memory, writes
-// one Fp12 per block, and a last block multiplies those and runs the single final exponentiation.
+// One thread per element / per pair; the product check runs the Miller kernel, multiplies the values of a block in shared
+// memory (one Fp12 per block), a last block multiplies those, and ONE final exponentiation follows.
 #include <cuda_runtime.h>
 #include <string>
 #include "../../include/b2kyber.h"
@@ -162,28 +162,29 @@ B2K_D void block_product(F12* sm, F12& v) {                       // v of thread
   }
   v = sm[0];
 }
+// partial[block] = product of the block's share of n Miller values (wire form, as k_miller wrote them).  The Miller loops run in
+// k_miller, the kernel Miller()/Pair() use: a variant that ran the loop inside this kernel (under `if (i < n)`, then the block
+// product) returned wrong products for bn254 only on the device -- bn256, BLS12-381 and the host emulation were right, and so was every
+// piece in isolation (tools/debug/tree_debug.cu, tools/debug_bn_product.py); unexplained, so the composition that is tested
+// piece by piece is the one that ships.  Cost: 384 / 576 bytes written and read per pair, nothing next to a Miller loop.
 template <class P>
-__global__ void __launch_bounds__(PROD_BLOCK) k_miller_product(size_t n, const uint8_t* __restrict__ g1, const uint8_t* __restrict__ g2,
-                                                               typename P::F12* __restrict__ partial, uint32_t* flags) {
+__global__ void __launch_bounds__(PROD_BLOCK) k_gt_block_product(size_t n, const uint8_t* __restrict__ millers, typename P::F12* __restrict__ partial) {
   extern __shared__ __align__(16) unsigned char smraw[];
   auto* sm = reinterpret_cast<typename P::F12*>(smraw);
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   typename P::F12 f;
   fp12_set_one(f);
-  if (i < n) {
-    Affine<typename P::G1::F> A;
-    Affine<typename P::G2::F> B;
-    bool good = load_checked<typename P::G1>(A, g1 + (size_t)P::G1::IN_BYTES * i);
-    good = load_checked<typename P::G2>(B, g2 + (size_t)P::G2::IN_BYTES * i) && good;
-    if (!good) atomicOr(flags, FLAG_POINT);
-    P::miller(f, A, B);
+  for (size_t i = (size_t)blockIdx.x * PROD_BLOCK + threadIdx.x; i < n; i += (size_t)gridDim.x * PROD_BLOCK) {
+    typename P::F12 m;
+    P::load(m, millers + (size_t)P::GT_BYTES * i);
+    fp12_mul(f, f, m);
   }
   block_product(sm, f);
   if (threadIdx.x == 0) partial[blockIdx.x] = f;
 }
+// product of the per-block partials -> ONE Fp12 (the product of all Miller values), written in wire form; the single final
+// exponentiation is then the ordinary k_final_exp launch over that one element
 template <class P>
-__global__ void __launch_bounds__(PROD_BLOCK) k_product_finish(size_t nparts, const typename P::F12* __restrict__ partial, uint8_t* __restrict__ ok,
-                                                               uint8_t* __restrict__ gt_out) {
+__global__ void __launch_bounds__(PROD_BLOCK) k_product_tree(size_t nparts, const typename P::F12* __restrict__ partial, uint8_t* __restrict__ f_out) {
   extern __shared__ __align__(16) unsigned char smraw[];
   auto* sm = reinterpret_cast<typename P::F12*>(smraw);
   typename P::F12 f;
@@ -193,12 +194,7 @@ __global__ void __launch_bounds__(PROD_BLOCK) k_product_finish(size_t nparts, co
     fp12_mul(f, f, p);
   }
   block_product(sm, f);
-  if (threadIdx.x == 0) {
-    typename P::F12 e;
-    P::final_exp(e, f);
-    if (ok) ok[0] = fp12_is_one(e) ? 1 : 0;
-    if (gt_out) P::store(gt_out, e);
-  }
+  if (threadIdx.x == 0) P::store(f_out, f);
 }
 
 // ---- G1 / G2 group operations on operand-form points ---------------------------------------------------------------------------
@@ -305,27 +301,39 @@ int product_check_host(b2k_ctx* ctx, size_t n, const uint8_t* g1, const uint8_t*
   if (!ctx || !g1 || !g2 || (!ok && !gt) || n == 0 || n >= (size_t(1) << 31)) { if (ctx) ctx->err = "bad argument"; return B2K_ERR_ARG; }
   CK(cudaSetDevice(ctx->device));
   const size_t b1 = (size_t)P::G1::IN_BYTES, b2 = (size_t)P::G2::IN_BYTES, gb = (size_t)P::GT_BYTES;
-  const size_t nblk = (n + b2k::PROD_BLOCK - 1) / b2k::PROD_BLOCK;
-  int rc = arena_reserve(ctx, pad256(n * b1) + pad256(n * b2) + pad256(nblk * sizeof(F12)) + pad256(gb) + 2048);
+  size_t nblk = (n + b2k::PROD_BLOCK - 1) / b2k::PROD_BLOCK;
+  if (nblk > 4096) nblk = 4096;                                              // beyond that a thread multiplies several values
+  int rc = arena_reserve(ctx, pad256(n * b1) + pad256(n * b2) + pad256(n * gb) + pad256(nblk * sizeof(F12)) + 2 * pad256(gb) + 2048);
   if (rc) return rc;
   uint8_t* d1 = arena_take<uint8_t>(ctx, n * b1);
   uint8_t* d2 = arena_take<uint8_t>(ctx, n * b2);
+  uint8_t* dm = arena_take<uint8_t>(ctx, n * gb);
   F12* parts = arena_take<F12>(ctx, nblk);
+  uint8_t* df = arena_take<uint8_t>(ctx, gb);
   uint8_t* dgt = arena_take<uint8_t>(ctx, gb);
-  uint8_t* dok = arena_take<uint8_t>(ctx, 256);
   cudaStream_t st = ctx->stream;
   rc = status_begin(ctx);
   if (rc) return rc;
   CK(cudaMemcpyAsync(d1, g1, n * b1, cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(d2, g2, n * b2, cudaMemcpyHostToDevice, st));
   const size_t smem = b2k::PROD_BLOCK * sizeof(F12);
-  k_miller_product<P><<<(unsigned)nblk, b2k::PROD_BLOCK, smem, st>>>(n, d1, d2, parts, ctx->d_flags);
-  k_product_finish<P><<<1, b2k::PROD_BLOCK, smem, st>>>(nblk, parts, ok ? dok : nullptr, gt ? dgt : nullptr);
+  k_miller<P><<<(unsigned)((n + 63) / 64), 64, 0, st>>>(n, d1, d2, dm, ctx->d_flags);
+  k_gt_block_product<P><<<(unsigned)nblk, b2k::PROD_BLOCK, smem, st>>>(n, dm, parts);
+  k_product_tree<P><<<1, b2k::PROD_BLOCK, smem, st>>>(nblk, parts, df);
+  k_final_exp<P><<<1, 64, 0, st>>>(1, df, dgt, ctx->d_flags);               // ONE final exponentiation
   CK(cudaGetLastError());
-  ctx->launches += 2;
-  if (ok) CK(cudaMemcpyAsync(ok, dok, 1, cudaMemcpyDeviceToHost, st));
-  if (gt) CK(cudaMemcpyAsync(gt, dgt, gb, cudaMemcpyDeviceToHost, st));
-  return status_finish(ctx);
+  ctx->launches += 4;
+  uint8_t hgt[576];
+  CK(cudaMemcpyAsync(gt ? gt : hgt, dgt, gb, cudaMemcpyDeviceToHost, st));
+  rc = status_finish(ctx);
+  if (rc) return rc;
+  if (ok) {
+    const uint8_t* e = gt ? gt : hgt;                                      // GT one = 0 ... 0 1 (only the last coefficient, c0.c0.c0)
+    bool one = e[gb - 1] == 1;
+    for (size_t i = 0; one && i + 1 < gb; i++) one = e[i] == 0;
+    ok[0] = one ? 1 : 0;
+  }
+  return B2K_OK;
 }
 
 template <class CV>

@@ -13,7 +13,7 @@ __global__ void __launch_bounds__(128) k_hash_to_g1(size_t n, const uint8_t* __r
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   Affine<BFp> a;
-  hash_to_g1(a, msgs + offs[i], offs[i + 1] - offs[i], dst, dst_len);
+  hash_to_g1(a, msgs + offs[i], (offs[i + 1] >= offs[i] ? offs[i + 1] - offs[i] : 0u), dst, dst_len);
   Bls381G1::store_affine(out + 96 * i, a);
 }
 
@@ -23,7 +23,7 @@ __global__ void __launch_bounds__(64) k_hash_to_g2(size_t n, const uint8_t* __re
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   Affine<BFp2> a;
-  hash_to_g2(a, msgs + offs[i], offs[i + 1] - offs[i], dst, dst_len);
+  hash_to_g2(a, msgs + offs[i], (offs[i + 1] >= offs[i] ? offs[i + 1] - offs[i] : 0u), dst, dst_len);
   Bls381G2::store_affine(out + 192 * i, a);
 }
 
@@ -73,6 +73,13 @@ __global__ void __launch_bounds__(64) k_g2_decompress_v(size_t n, const uint8_t*
 
 }  // namespace b2k
 
+// message offsets of the host entry points: non-decreasing (a decreasing pair would make a kernel read ~4 GiB)
+static int check_offsets(b2k_ctx* ctx, size_t n, const uint32_t* offsets) {
+  for (size_t i = 0; i < n; i++)
+    if (offsets[i + 1] < offsets[i]) { ctx->err = "message offsets must be non-decreasing"; return B2K_ERR_ARG; }
+  return B2K_OK;
+}
+
 extern "C" {
 
 int b2k_bls12381_hash_to_g1_dev(b2k_ctx* ctx, size_t n, const void* d_msgs, const void* d_offsets, const void* d_dst,
@@ -90,6 +97,7 @@ int b2k_bls12381_hash_to_g1(b2k_ctx* ctx, size_t n, const uint8_t* msgs, const u
                             uint32_t dst_len, uint8_t* out) {
   if (!ctx || !msgs || !offsets || !dst || !out || n == 0 || dst_len == 0 || dst_len > 255) return B2K_ERR_ARG;
   CK(cudaSetDevice(ctx->device));
+  if (check_offsets(ctx, n, offsets)) return B2K_ERR_ARG;
   size_t mbytes = offsets[n];
   int rc = arena_reserve(ctx, mbytes + (n + 1) * 4 + 256 + n * 96 + 4096);
   if (rc) return rc;
@@ -152,6 +160,7 @@ int b2k_bls12381_hash_to_g2(b2k_ctx* ctx, size_t n, const uint8_t* msgs, const u
                             uint32_t dst_len, uint8_t* out) {
   if (!ctx || !msgs || !offsets || !dst || !out || n == 0 || dst_len == 0 || dst_len > 255) return B2K_ERR_ARG;
   CK(cudaSetDevice(ctx->device));
+  if (check_offsets(ctx, n, offsets)) return B2K_ERR_ARG;
   size_t mbytes = offsets[n];
   int rc = arena_reserve(ctx, mbytes + (n + 1) * 4 + 256 + n * 192 + 4096);
   if (rc) return rc;
@@ -207,7 +216,9 @@ int b2k_bls12381_verify_g2sig(b2k_ctx* ctx, size_t n, const uint8_t* pks48, cons
   uint8_t* blob = nullptr;
   size_t o_pk = 0, o_sig = o_pk + n * 48, o_msg = o_sig + n * 96, o_off = (o_msg + mbytes + 15) & ~size_t(15),
          o_dst = o_off + (n + 1) * 4, o_ok = o_dst + 256, total = o_ok + n;
-  CK(cudaMalloc(&blob, total));
+  if (check_offsets(ctx, n, offsets)) return B2K_ERR_ARG;
+  blob = (uint8_t*)b2k_arena_in(ctx, total);        // the context's input arena (no cudaMalloc / cudaFree per call: both synchronise the device)
+  if (!blob) { ctx->err = "out of device memory"; return B2K_ERR_CUDA; }
   cudaStream_t st = ctx->stream;
   int rc = B2K_OK;
   do {
@@ -223,7 +234,6 @@ int b2k_bls12381_verify_g2sig(b2k_ctx* ctx, size_t n, const uint8_t* pks48, cons
         cudaStreamSynchronize(st) != cudaSuccess) rc = B2K_ERR_CUDA;
   } while (0);
   cudaStreamSynchronize(st);
-  cudaFree(blob);
   if (rc == B2K_ERR_CUDA) ctx->err = "CUDA failure in verify_g2sig";
   return rc;
 }
@@ -237,7 +247,9 @@ int b2k_bls12381_verify_g1sig(b2k_ctx* ctx, size_t n, const uint8_t* pks96, cons
   uint8_t* blob = nullptr;
   size_t o_pk = 0, o_sig = o_pk + n * 96, o_msg = o_sig + n * 48, o_off = (o_msg + mbytes + 15) & ~size_t(15),
          o_dst = o_off + (n + 1) * 4, o_ok = o_dst + 256, total = o_ok + n;
-  CK(cudaMalloc(&blob, total));
+  if (check_offsets(ctx, n, offsets)) return B2K_ERR_ARG;
+  blob = (uint8_t*)b2k_arena_in(ctx, total);        // the context's input arena (no cudaMalloc / cudaFree per call: both synchronise the device)
+  if (!blob) { ctx->err = "out of device memory"; return B2K_ERR_CUDA; }
   cudaStream_t st = ctx->stream;
   int rc = B2K_OK;
   do {
@@ -253,7 +265,6 @@ int b2k_bls12381_verify_g1sig(b2k_ctx* ctx, size_t n, const uint8_t* pks96, cons
         cudaStreamSynchronize(st) != cudaSuccess) rc = B2K_ERR_CUDA;
   } while (0);
   cudaStreamSynchronize(st);
-  cudaFree(blob);
   if (rc == B2K_ERR_CUDA) ctx->err = "CUDA failure in verify_g1sig";
   return rc;
 }

@@ -13,12 +13,12 @@ using namespace b2k;
 extern "C" {
 
 void b2k_internal_launch_pair(const b2k_ctx* ctx, size_t n, const uint8_t* g1, const uint8_t* g2, uint8_t* gt) {
-  if (ctx->pair_variant >= 3) b2k_internal_launch_pair_compact(ctx, ctx->pair_variant - 3, n, g1, g2, gt);
+  if (ctx->pair_variant >= 3) b2k_internal_launch_pair_inlined(ctx, ctx->pair_variant - 3, n, g1, g2, gt);
   else launch_pair_v(ctx, ctx->pair_variant, n, g1, g2, gt);
 }
 void b2k_internal_launch_pairing_check(const b2k_ctx* ctx, size_t n, const uint8_t* a1, const uint8_t* a2, const uint8_t* b1,
                                        const uint8_t* b2, uint8_t* ok, int b2_broadcast, const uint8_t* pre_ok) {
-  if (ctx->pair_variant >= 3) b2k_internal_launch_pairing_check_compact(ctx, ctx->pair_variant - 3, n, a1, a2, b1, b2, ok, b2_broadcast, pre_ok);
+  if (ctx->pair_variant >= 3) b2k_internal_launch_pairing_check_inlined(ctx, ctx->pair_variant - 3, n, a1, a2, b1, b2, ok, b2_broadcast, pre_ok);
   else launch_pairing_check_v(ctx, ctx->pair_variant, n, a1, a2, b1, b2, ok, b2_broadcast, pre_ok);
 }
 

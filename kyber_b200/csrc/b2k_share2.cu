@@ -79,16 +79,16 @@ __global__ void __launch_bounds__(128) k_lagrange_basis(uint32_t t, const uint32
     }
   }
 }
-// terms[k t + j] = scal[k][j] * y_j (Jacobian, no inversion); BCAST: one point for all (PriPoly.Commit: affine bytes out instead)
+// terms[k t + j] = scal[k][j] * y_j, normalised to affine by the same batched-per-thread pattern as k_mul_batch
 template <class CV>
 __global__ void __launch_bounds__(128) k_scale_points(size_t n, uint32_t t, const uint8_t* __restrict__ scal, const Affine<typename CV::F>* __restrict__ pts,
-                                                      Jac<typename CV::F>* __restrict__ terms, uint32_t* flags, int use_glv) {
+                                                      Affine<typename CV::F>* __restrict__ terms, uint32_t* flags, int use_glv) {
   size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (id >= n) return;
   Scalar256 k;
   scalar_load_be(k, scal + 32 * id);
   if (!scalar_in_range<typename CV::ScalarField>(k)) { atomicOr(flags, FLAG_SCALAR_RANGE); for (int w = 0; w < 8; w++) k.v[w] = 0; }
-  Affine<typename CV::F> p = pts[t ? id % t : 0];
+  Affine<typename CV::F> p = pts[id % t];
   Jac<typename CV::F> r;
   if constexpr (MulGlv<CV>::enabled) {
     if (use_glv) scalar_mul_glv_bls381(r, k, p, InvBingcd{});
@@ -96,11 +96,13 @@ __global__ void __launch_bounds__(128) k_scale_points(size_t n, uint32_t t, cons
   } else {
     scalar_mul_w4<CV>(r, k, p, InvBingcd{});
   }
-  terms[id] = r;
+  Affine<typename CV::F> a;
+  jac_to_affine_bg(a, r);
+  terms[id] = a;
 }
-// out[k] = sum_j terms[k t + j]: one block per k
+// sums[k] = sum_j terms[k t + j] (Jacobian): one block per k, mixed additions into per-thread sums, then a shared-memory tree
 template <class CV>
-__global__ void __launch_bounds__(64) k_column_sum(uint32_t t, const Jac<typename CV::F>* __restrict__ terms, uint8_t* __restrict__ out) {
+__global__ void __launch_bounds__(64) k_column_sum(uint32_t t, const Affine<typename CV::F>* __restrict__ terms, Jac<typename CV::F>* __restrict__ sums) {
   using J = Jac<typename CV::F>;
   __shared__ J sm[64];
   const int tid = threadIdx.x;
@@ -108,8 +110,8 @@ __global__ void __launch_bounds__(64) k_column_sum(uint32_t t, const Jac<typenam
   J acc;
   jac_set_inf(acc);
   for (uint32_t j = tid; j < t; j += 64) {
-    J v = terms[k * t + j];
-    jac_add(acc, acc, v);
+    Affine<typename CV::F> v = terms[k * t + j];
+    jac_madd(acc, acc, v);
   }
   sm[tid] = acc;
   __syncthreads();
@@ -121,11 +123,17 @@ __global__ void __launch_bounds__(64) k_column_sum(uint32_t t, const Jac<typenam
     }
     __syncthreads();
   }
-  if (tid == 0) {
-    Affine<typename CV::F> a;
-    jac_to_affine(a, sm[0]);
-    CV::store_affine(out + (size_t)CV::IN_BYTES * k, a);
-  }
+  if (tid == 0) sums[k] = sm[0];
+}
+// out[k] = sums[k] in operand form (one thread per commitment)
+template <class CV>
+__global__ void __launch_bounds__(128) k_sums_to_affine(uint32_t t, const Jac<typename CV::F>* __restrict__ sums, uint8_t* __restrict__ out) {
+  uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= t) return;
+  Jac<typename CV::F> s = sums[k];
+  Affine<typename CV::F> a;
+  jac_to_affine_bg(a, s);
+  CV::store_affine(out + (size_t)CV::IN_BYTES * k, a);
 }
 // out[i] = scalars[i] * B (operand form): PriPoly.Commit's loop (poly.go:145-147) over one base point
 template <class CV>
@@ -164,7 +172,7 @@ static int recover_pubpoly(b2k_ctx* ctx, size_t t, const uint32_t* indices, cons
   CK(cudaSetDevice(ctx->device));
   const size_t tt = t * t, pb = (size_t)CV::IN_BYTES;
   int rc = arena_reserve(ctx, pad256(t * 4) + pad256(t * pb) + pad256(t * sizeof(Affine<F>)) + 2 * pad256((t + 1) * sizeof(S)) + pad256(tt * sizeof(S)) +
-                                  pad256(tt * 32) + pad256(tt * sizeof(Jac<F>)) + pad256(t * pb) + 4096);
+                                  pad256(tt * 32) + pad256(tt * sizeof(Affine<F>)) + pad256(t * sizeof(Jac<F>)) + pad256(t * pb) + 4096);
   if (rc) return rc;
   uint32_t* d_idx = arena_take<uint32_t>(ctx, t);
   uint8_t* d_p = arena_take<uint8_t>(ctx, t * pb);
@@ -173,7 +181,8 @@ static int recover_pubpoly(b2k_ctx* ctx, size_t t, const uint32_t* indices, cons
   S* cb = arena_take<S>(ctx, t + 1);
   S* rows = arena_take<S>(ctx, tt);
   uint8_t* scal = arena_take<uint8_t>(ctx, tt * 32);
-  auto* terms = arena_take<Jac<F>>(ctx, tt);
+  auto* terms = arena_take<Affine<F>>(ctx, tt);
+  auto* sums = arena_take<Jac<F>>(ctx, t);
   uint8_t* d_o = arena_take<uint8_t>(ctx, t * pb);
   if (!d_o) { ctx->err = "scratch arena too small"; return B2K_ERR_ARG; }
   cudaStream_t st = ctx->stream;
@@ -184,9 +193,10 @@ static int recover_pubpoly(b2k_ctx* ctx, size_t t, const uint32_t* indices, cons
   k_master_poly<FR><<<1, 1024, 0, st>>>((uint32_t)t, d_idx, ca, cb);
   k_lagrange_basis<FR><<<(unsigned)((t + 127) / 128), 128, 0, st>>>((uint32_t)t, d_idx, ca, rows, scal, ctx->d_flags);
   k_scale_points<CV><<<(unsigned)((tt + 127) / 128), 128, 0, st>>>(tt, (uint32_t)t, scal, d_pm, terms, ctx->d_flags, ctx->use_glv);
-  k_column_sum<CV><<<(unsigned)t, 64, 0, st>>>((uint32_t)t, terms, d_o);
+  k_column_sum<CV><<<(unsigned)t, 64, 0, st>>>((uint32_t)t, terms, sums);
+  k_sums_to_affine<CV><<<(unsigned)((t + 127) / 128), 128, 0, st>>>((uint32_t)t, sums, d_o);
   CK(cudaGetLastError());
-  ctx->launches += 5;
+  ctx->launches += 6;
   CK(cudaMemcpyAsync(commits_out, d_o, t * pb, cudaMemcpyDeviceToHost, st));
   rc = status_fetch_async(ctx);
   if (rc) return rc;

@@ -16,6 +16,7 @@
 // a ~ l0, b ~ l1, c ~ l3.  GT bytes equal those of a line-by-line restatement of the Go source (tests/).
 #pragma once
 #include "ec.cuh"
+#include "curves.cuh"
 
 namespace b2k {
 

@@ -31,34 +31,9 @@ template <class C> B2K_D void f_inv_bg(Fp2<C>& r, const Fp2<C>& a) {
   fp_mul_c(r.c0, a.c0, n); fp_mul_c(t, a.c1, n); fp_neg(r.c1, t);
 }
 
-// ---- software prefetch ----------------------------------------------------------------------------------------------------
-// ncu (profiles/r02d_accumulate_ncu_raw.csv): with ~3.4 warps per scheduler the gathers of round 1 are not hidden --
-// k_pt_forward<..., 1> spends 9.2 of its 15.6 cycles per issued instruction on `long_scoreboard`, k_pt_backward<..., 1> 3.4 of
-// 11.6.  The operands of the NEXT output of a thread are known one iteration ahead (same bucket: two entries further), so
-// their cache lines are requested while the current output's products run; no registers are tied up.
-B2K_D void prefetch_l1(const void* p) {
-#if defined(__CUDA_ARCH__)
-  asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
-#else
-  (void)p;
-#endif
-}
-// operands of the output whose inputs start at position a (a + 1 < end assumed by the caller); X_ONLY: only the x coordinates
-template <class CV, bool FIRST, bool X_ONLY>
-B2K_D void pt_prefetch(const Affine<typename CV::F>* in, const uint32_t* entries, uint32_t a) {
-  const char* p1;
-  const char* p2;
-  if (FIRST) {
-    p1 = reinterpret_cast<const char*>(in + (entries[a] & 0x7fffffffu));
-    p2 = reinterpret_cast<const char*>(in + (entries[a + 1] & 0x7fffffffu));
-  } else {
-    p1 = reinterpret_cast<const char*>(in + a);
-    p2 = reinterpret_cast<const char*>(in + a + 1);
-  }
-  constexpr int BYTES = X_ONLY ? (int)sizeof(typename CV::F) : (int)sizeof(Affine<typename CV::F>);
-#pragma unroll
-  for (int o = 0; o < BYTES; o += 32) { prefetch_l1(p1 + o); prefetch_l1(p2 + o); }
-}
+// (Round 2 tried software prefetch here -- `prefetch.global.L1` of the next output's operands and prefix product one iteration
+//  ahead, because ncu shows `long_scoreboard` stalls in the round-1 kernels: measured SLOWER, accumulate 5.48 -> 5.61 ms,
+//  profiles/r02_notes.md; the extra address arithmetic and the L1 traffic cost more than the latency they hide.  Removed.)
 
 constexpr int PT_MAXB = 64;     // outputs per thread (length of the prefix-product array in local memory)
 enum : int { PT_COPY1 = 0, PT_COPY2 = 1, PT_ADD = 2, PT_DBL = 3, PT_INF = 4 };
@@ -181,11 +156,9 @@ B2K_D void msm_pairtree_forward(uint32_t t, uint32_t B, uint32_t T, uint32_t tot
   for (uint32_t q = q0; q < q1; q++) {
     while (q >= oe) { g++; os = oe; oe = offs_out[g + 1]; is = ie; ie = offs_in[g + 1]; }
     F d;
-    const uint32_t a = is + 2 * (q - os);
-    if (q + 1 < oe && q + 1 < q1 && a + 3 < ie) pt_prefetch<CV, FIRST, true>(in, entries, a + 2);     // next output, same bucket
-    pt_denominator<CV, FIRST>(d, in, entries, a, ie);
+    pt_denominator<CV, FIRST>(d, in, entries, is + 2 * (q - os), ie);
     pre[(size_t)(q - q0) * T + t] = acc;
-    f_mul(acc, acc, d);
+    f_mul_i(acc, acc, d);
   }
   accs[t] = acc;
 }
@@ -217,22 +190,16 @@ B2K_D void msm_pairtree_backward(uint32_t t, uint32_t B, uint32_t T, uint32_t to
     while (q < os) { g--; os = offs_out[g]; ie = is; is = offs_in[g]; }
     Affine<F> p1, p2, r;
     F d, dinv, lam, tt;
-    const uint32_t a = is + 2 * (q - os);
-    if (q > q0 && q > os) {                                       // previous output of the same bucket: its operands and its prefix product
-      pt_prefetch<CV, FIRST, false>(in, entries, a - 2);
-      prefetch_l1(&pre[(size_t)(q - 1 - q0) * T + t]);
-      prefetch_l1(reinterpret_cast<const char*>(&pre[(size_t)(q - 1 - q0) * T + t]) + 32);
-    }
-    const bool pair = pt_fetch<CV, FIRST>(p1, p2, in, entries, a, ie);
+    const bool pair = pt_fetch<CV, FIRST>(p1, p2, in, entries, is + 2 * (q - os), ie);
     const int kind = pt_classify(d, p1, p2, pair);
     F pj = pre[(size_t)(q - q0) * T + t];
-    f_mul(dinv, inv, pj);
-    if (q > q0) f_mul(inv, inv, d);
-    if (kind == PT_DBL) { f_sqr(tt, p1.x); f_dbl(lam, tt); f_add(tt, lam, tt); }
+    f_mul_i(dinv, inv, pj);
+    if (q > q0) f_mul_i(inv, inv, d);
+    if (kind == PT_DBL) { f_sqr(tt, p1.x); f_dbl(lam, tt); f_add(tt, lam, tt); }   // (rare: stays a call in the compact layout)
     else f_sub(tt, p2.y, p1.y);
-    f_mul(lam, tt, dinv);
-    f_sqr(r.x, lam); f_sub(r.x, r.x, p1.x); f_sub(r.x, r.x, p2.x);
-    f_sub(tt, p1.x, r.x); f_mul(r.y, lam, tt); f_sub(r.y, r.y, p1.y);
+    f_mul_i(lam, tt, dinv);
+    f_sqr_i(r.x, lam); f_sub(r.x, r.x, p1.x); f_sub(r.x, r.x, p2.x);
+    f_sub(tt, p1.x, r.x); f_mul_i(r.y, lam, tt); f_sub(r.y, r.y, p1.y);
     if (kind == PT_COPY1) r = p1;
     else if (kind == PT_COPY2) r = p2;
     else if (kind == PT_INF) aff_set_inf(r);

@@ -442,6 +442,14 @@ int msm_enqueue(b2k_ctx* ctx, size_t n_in, const MsmPlan& pl, const uint8_t* d_s
   return B2K_OK;
 }
 
+// sorted-entry positions are 32-bit (offs[], cursor, entries, slice bounds): a problem whose pairs x windows reach 2^32 is refused
+template <class CV>
+inline bool msm_too_large(b2k_ctx* ctx, size_t n, const MsmPlan& pl) {
+  if ((unsigned long long)msm_virtual_n<CV>(ctx, n) * (unsigned long long)pl.W < (1ull << 32)) return false;
+  ctx->err = "MSM too large for one call: pairs x windows must stay below 2^32 (split the batch or use the sharded entry points)";
+  return true;
+}
+
 template <class CV>
 int msm_dev(b2k_ctx* ctx, size_t n, const void* d_scalars, const void* d_points, void* d_out, int affine_out = 0) {
   if (!ctx || !d_scalars || !d_points || !d_out || n == 0 || n >= (size_t(1) << 31)) {
@@ -450,6 +458,7 @@ int msm_dev(b2k_ctx* ctx, size_t n, const void* d_scalars, const void* d_points,
   }
   CK(cudaSetDevice(ctx->device));
   MsmPlan pl = msm_plan<CV>(ctx, n);
+  if (msm_too_large<CV>(ctx, n, pl)) return B2K_ERR_ARG;
   int rc = arena_reserve(ctx, msm_scratch_bytes<CV>(ctx, msm_virtual_n<CV>(ctx, n), pl));
   if (rc) return rc;
   return msm_enqueue<CV>(ctx, n, pl, (const uint8_t*)d_scalars, (const uint8_t*)d_points, (uint8_t*)d_out, affine_out);
@@ -472,6 +481,7 @@ int msm_buckets_dev(b2k_ctx* ctx, size_t n, const void* d_scalars, const void* d
   }
   CK(cudaSetDevice(ctx->device));
   MsmPlan pl = msm_plan<CV>(ctx, n);
+  if (msm_too_large<CV>(ctx, n, pl)) return B2K_ERR_ARG;
   if (plan_out) { plan_out[0] = pl.c; plan_out[1] = pl.W; plan_out[2] = pl.nb; plan_out[3] = (int)sizeof(X); }
   if (cap_bytes < (size_t)pl.W * pl.nb * sizeof(X) || (reinterpret_cast<uintptr_t>(d_buckets) & 15)) {
     ctx->err = "bucket buffer too small or not 16-byte aligned";
@@ -493,6 +503,7 @@ int msm_buckets_host(b2k_ctx* ctx, size_t n, const uint8_t* scalars, const uint8
   }
   CK(cudaSetDevice(ctx->device));
   MsmPlan pl = msm_plan<CV>(ctx, n);
+  if (msm_too_large<CV>(ctx, n, pl)) return B2K_ERR_ARG;
   if (plan_out) { plan_out[0] = pl.c; plan_out[1] = pl.W; plan_out[2] = pl.nb; plan_out[3] = (int)sizeof(X); }
   if (cap_bytes < (size_t)pl.W * pl.nb * sizeof(X) || (reinterpret_cast<uintptr_t>(d_buckets) & 15)) {
     ctx->err = "bucket buffer too small or not 16-byte aligned";
@@ -590,6 +601,7 @@ int msm_host(b2k_ctx* ctx, size_t n, const uint8_t* scalars, const uint8_t* poin
   }
   CK(cudaSetDevice(ctx->device));
   MsmPlan pl = msm_plan<CV>(ctx, n);
+  if (msm_too_large<CV>(ctx, n, pl)) return B2K_ERR_ARG;
   size_t in_bytes = pad256(n * 32) + pad256(n * (size_t)CV::IN_BYTES) + 256;
   int rc = arena_reserve(ctx, msm_scratch_bytes<CV>(ctx, msm_virtual_n<CV>(ctx, n), pl) + in_bytes);
   if (rc) return rc;

@@ -73,13 +73,13 @@ inline void launch_pairing_check_v(const b2k_ctx* ctx, int variant, size_t n, co
 
 }  // namespace b2k
 
-// The pairing kernels exist in two code layouts (fp.cuh: B2K_COMPACT_FIELD): b2k_pairing.cu holds the fully inlined one
-// (variants 0..2), b2k_pairing_compact.cu the one whose field products are out-of-line by-value calls (variants 3..5).
+// The pairing kernels exist in two code layouts (fp.cuh: B2K_COMPACT_FIELD): b2k_pairing.cu holds the compact one (field
+// products are out-of-line by-value calls; variants 0..2 = the default), b2k_pairing_inlined.cu the fully inlined one (variants 3..5).
 // Every caller (b2k_pairing.cu, the bls.Verify paths of b2k_h2c.cu) launches through these two functions.
 extern "C" void b2k_internal_launch_pair(const b2k_ctx* ctx, size_t n, const uint8_t* g1, const uint8_t* g2, uint8_t* gt);
 extern "C" void b2k_internal_launch_pairing_check(const b2k_ctx* ctx, size_t n, const uint8_t* a1, const uint8_t* a2, const uint8_t* b1,
                                                   const uint8_t* b2, uint8_t* ok, int b2_broadcast, const uint8_t* pre_ok);
-extern "C" void b2k_internal_launch_pair_compact(const b2k_ctx* ctx, int variant, size_t n, const uint8_t* g1, const uint8_t* g2, uint8_t* gt);
-extern "C" void b2k_internal_launch_pairing_check_compact(const b2k_ctx* ctx, int variant, size_t n, const uint8_t* a1, const uint8_t* a2,
+extern "C" void b2k_internal_launch_pair_inlined(const b2k_ctx* ctx, int variant, size_t n, const uint8_t* g1, const uint8_t* g2, uint8_t* gt);
+extern "C" void b2k_internal_launch_pairing_check_inlined(const b2k_ctx* ctx, int variant, size_t n, const uint8_t* a1, const uint8_t* a2,
                                                           const uint8_t* b1, const uint8_t* b2, uint8_t* ok, int b2_broadcast,
                                                           const uint8_t* pre_ok);

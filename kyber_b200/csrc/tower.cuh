@@ -171,6 +171,10 @@ template <class C> B2K_D bool f_eq(const Fp<C>& a, const Fp<C>& b) { return fp_e
 template <class C> B2K_D void f_set_zero(Fp<C>& r) { fp_set_zero(r); }
 template <class C> B2K_D void f_set_one(Fp<C>& r) { fp_set_one(r); }
 
+template <class C> B2K_D void f_mul_i(Fp<C>& r, const Fp<C>& a, const Fp<C>& b) { fp_mul_i(r, a, b); }
+template <class C> B2K_D void f_sqr_i(Fp<C>& r, const Fp<C>& a) { fp_sqr_i(r, a); }
+template <class C> B2K_D void f_mul_i(Fp2<C>& r, const Fp2<C>& a, const Fp2<C>& b) { fp2_mul(r, a, b); }
+template <class C> B2K_D void f_sqr_i(Fp2<C>& r, const Fp2<C>& a) { fp2_sqr(r, a); }
 template <class C> B2K_D void f_add(Fp2<C>& r, const Fp2<C>& a, const Fp2<C>& b) { fp2_add(r, a, b); }
 template <class C> B2K_D void f_sub(Fp2<C>& r, const Fp2<C>& a, const Fp2<C>& b) { fp2_sub(r, a, b); }
 template <class C> B2K_D void f_mul(Fp2<C>& r, const Fp2<C>& a, const Fp2<C>& b) { fp2_mul(r, a, b); }

@@ -45,7 +45,25 @@ for layout in (0, 1, 0, 1):
     tm = engs[0].last_timings()
     print(f"MSM 2^20 layout={layout}: {ms:.3f} ms per MSM pipelined ({n / ms * 1e3:.3e} muls/s); one MSM stages: accumulate {tm[4]:.3f} ms, rounds {tm[10]:.3f}, pipeline {tm[8]:.3f}", flush=True)
 
-# pairings: variants 0..2 inlined (64x4 / 64x8 / 64x6), 3..5 the same launch shapes in the compact layout
+# independent Point.Mul (k_mul_batch), both layouts
+outm = torch.empty(n * 48, dtype=torch.uint8, device=dev)
+for layout in (0, 1, 0, 1):
+    eng._check(eng.lib.b2k_set_msm_layout(eng.h, layout))
+    eng.call_dev("b2k_bls12381_g1_mul_batch_dev", n, d_s.data_ptr(), d_pts.data_ptr(), outm.data_ptr())
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(torch.cuda.current_stream())
+    eng.synchronize()
+    import time
+    t0 = time.perf_counter()
+    eng.call_dev("b2k_bls12381_g1_mul_batch_dev", n, d_s.data_ptr(), d_pts.data_ptr(), outm.data_ptr())
+    eng.synchronize()
+    ms = (time.perf_counter() - t0) * 1e3
+    assert bytes(outm[:48].cpu().tolist()) == o.g1_compress(o.g1_mul(s[0] * a[0] % o.R))
+    print(f"mul_batch 2^20 layout={layout}: {ms:.2f} ms ({n / ms * 1e3:.3e} muls/s)", flush=True)
+eng._check(eng.lib.b2k_set_msm_layout(eng.h, 0))
+
+# pairings: variants 0..2 compact layout (64x4 / 64x8 / 64x6), 3..5 the same launch shapes with inlined products
 m = 65536
 g1 = torch.frombuffer(bytearray(o.g1_to_affine_bytes(o.g1_mul(12345)) * m), dtype=torch.uint8).to(dev)
 g2 = torch.frombuffer(bytearray(o.g2_to_affine_bytes(o.g2_mul(6789)) * m), dtype=torch.uint8).to(dev)
@@ -62,6 +80,6 @@ for v in range(6):
         e0.record(); fn(); fn(); e1.record(); torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / 2
         per = 1 if name == "pair" else 2
-        print(f"pairing variant {v} ({'compact' if v >= 3 else 'inlined'}) {name}: n={m} {ms:.2f} ms -> {per * m / ms * 1e3:.3e} pairings/s", flush=True)
+        print(f"pairing variant {v} ({'inlined' if v >= 3 else 'compact'}) {name}: n={m} {ms:.2f} ms -> {per * m / ms * 1e3:.3e} pairings/s", flush=True)
     assert bool(ok.min().item() == 1) and bytes(gt[:576].cpu().tolist()) == wantgt
 print("all variants correct")

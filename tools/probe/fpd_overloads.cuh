@@ -26,6 +26,8 @@ B2K_D void f_add(FpD& r, const FpD& a, const FpD& b) { dfma::fp_add(r, a, b); }
 B2K_D void f_sub(FpD& r, const FpD& a, const FpD& b) { dfma::fp_sub(r, a, b); }
 B2K_D void f_mul(FpD& r, const FpD& a, const FpD& b) { dfma::mont_mul384(r, a, b); }
 B2K_D void f_sqr(FpD& r, const FpD& a) { dfma::mont_mul384(r, a, a); }
+B2K_D void f_mul_i(FpD& r, const FpD& a, const FpD& b) { dfma::mont_mul384(r, a, b); }   // the pair-tree rounds' inlined spelling
+B2K_D void f_sqr_i(FpD& r, const FpD& a) { dfma::mont_mul384(r, a, a); }
 B2K_D void f_set_zero(FpD& r) {
 #pragma unroll
   for (int i = 0; i < dfma::L; i++) r.v[i] = 0.0;
