@@ -230,43 +230,12 @@ B2K_NI void bn_frobenius(PFp12<PC>& r, const PFp12<PC>& f) {
 #undef B2K_BN_COEF_SEL
 }
 
-template <class PC>
-B2K_D void bn_fp4_sqr(PFp2<PC>& c0, PFp2<PC>& c1, const PFp2<PC>& a, const PFp2<PC>& b) {
-  PFp2<PC> t0, t1, t2;
-  fp2_sqr(t0, a);
-  fp2_sqr(t1, b);
-  PC::T::mul_xi(t2, t1);
-  fp2_add(c0, t2, t0);
-  fp2_add(t2, a, b);
-  fp2_sqr(t2, t2);
-  fp2_sub(t2, t2, t0);
-  fp2_sub(c1, t2, t1);
-}
-
-// Granger-Scott squaring in the cyclotomic subgroup (same slot assignment as pairing.cuh)
-template <class PC>
-B2K_NI void bn_cyclotomic_sqr(PFp12<PC>& r, const PFp12<PC>& f) {
-  PFp2<PC> z0 = f.c0.c0, z4 = f.c0.c1, z3 = f.c0.c2, z2 = f.c1.c0, z1 = f.c1.c1, z5 = f.c1.c2;
-  PFp2<PC> t0, t1, t2, t3;
-  bn_fp4_sqr<PC>(t0, t1, z0, z1);
-  fp2_sub(z0, t0, z0); fp2_dbl(z0, z0); fp2_add(z0, z0, t0);
-  fp2_add(z1, t1, z1); fp2_dbl(z1, z1); fp2_add(z1, z1, t1);
-  bn_fp4_sqr<PC>(t0, t1, z2, z3);
-  bn_fp4_sqr<PC>(t2, t3, z4, z5);
-  fp2_sub(z4, t0, z4); fp2_dbl(z4, z4); fp2_add(z4, z4, t0);
-  fp2_add(z5, t1, z5); fp2_dbl(z5, z5); fp2_add(z5, z5, t1);
-  PC::T::mul_xi(t0, t3);
-  fp2_add(z2, t0, z2); fp2_dbl(z2, z2); fp2_add(z2, z2, t0);
-  fp2_sub(z3, t2, z3); fp2_dbl(z3, z3); fp2_add(z3, z3, t2);
-  r.c0.c0 = z0; r.c0.c1 = z4; r.c0.c2 = z3;
-  r.c1.c0 = z2; r.c1.c1 = z1; r.c1.c2 = z5;
-}
-
+// Granger-Scott squaring in the cyclotomic subgroup: fp12_cyclotomic_sqr (tower.cuh)
 template <class PC>
 B2K_NI void bn_pow_u(PFp12<PC>& r, const PFp12<PC>& a) {
   PFp12<PC> acc = a;
   for (int b = 61; b >= 0; b--) {            // u has 63 bits (both curves), top bit consumed by acc = a
-    bn_cyclotomic_sqr<PC>(acc, acc);
+    fp12_cyclotomic_sqr(acc, acc);
     if ((PC::U >> b) & 1) fp12_mul(acc, acc, a);
   }
   r = acc;

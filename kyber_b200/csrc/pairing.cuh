@@ -161,37 +161,7 @@ B2K_NI void fp12_frobenius(BFp12& r, const BFp12& f) {
   }
 }
 
-// ---- squaring in the cyclotomic subgroup (Granger-Scott): 3 Fp4 squarings = 9 Fp2 squarings ------------
-// valid only for elements of order dividing p^4 - p^2 + 1, i.e. after the easy part of the final
-// exponentiation; checked against the generic fp12_sqr in the tests.
-B2K_D void fp4_sqr(BFp2& c0, BFp2& c1, const BFp2& a, const BFp2& b) {
-  BFp2 t0, t1, t2;
-  fp2_sqr(t0, a);
-  fp2_sqr(t1, b);
-  BT::mul_xi(t2, t1);
-  fp2_add(c0, t2, t0);
-  fp2_add(t2, a, b);
-  fp2_sqr(t2, t2);
-  fp2_sub(t2, t2, t0);
-  fp2_sub(c1, t2, t1);
-}
-
-B2K_NI void fp12_cyclotomic_sqr(BFp12& r, const BFp12& f) {
-  BFp2 z0 = f.c0.c0, z4 = f.c0.c1, z3 = f.c0.c2, z2 = f.c1.c0, z1 = f.c1.c1, z5 = f.c1.c2;
-  BFp2 t0, t1, t2, t3;
-  fp4_sqr(t0, t1, z0, z1);
-  fp2_sub(z0, t0, z0); fp2_dbl(z0, z0); fp2_add(z0, z0, t0);      // 3 t0 - 2 z0
-  fp2_add(z1, t1, z1); fp2_dbl(z1, z1); fp2_add(z1, z1, t1);      // 3 t1 + 2 z1
-  fp4_sqr(t0, t1, z2, z3);
-  fp4_sqr(t2, t3, z4, z5);
-  fp2_sub(z4, t0, z4); fp2_dbl(z4, z4); fp2_add(z4, z4, t0);
-  fp2_add(z5, t1, z5); fp2_dbl(z5, z5); fp2_add(z5, z5, t1);
-  BT::mul_xi(t0, t3);
-  fp2_add(z2, t0, z2); fp2_dbl(z2, z2); fp2_add(z2, z2, t0);
-  fp2_sub(z3, t2, z3); fp2_dbl(z3, z3); fp2_add(z3, z3, t2);
-  r.c0.c0 = z0; r.c0.c1 = z4; r.c0.c2 = z3;
-  r.c1.c0 = z2; r.c1.c1 = z1; r.c1.c2 = z5;
-}
+// (squaring in the cyclotomic subgroup: fp12_cyclotomic_sqr, tower.cuh)
 
 // ---- exponentiation by a 64-bit public exponent inside the cyclotomic subgroup ---------------------------
 B2K_NI void fp12_pow_u64(BFp12& r, const BFp12& a, uint64_t e) {

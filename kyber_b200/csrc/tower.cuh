@@ -363,4 +363,47 @@ B2K_NI void fp12_inv(Fp12<T>& r, const Fp12<T>& a) {
   fp6_neg(r.c1, t);
 }
 
+// ---- squaring in the cyclotomic subgroup (Granger-Scott): 3 Fp4 squarings = 9 Fp2 squarings ------------------------------------
+// Valid only for elements of order dividing p^4 - p^2 + 1, i.e. after the easy part of a final exponentiation; checked against
+// the generic fp12_sqr in the tests.  Slots: z0 = c0.c0, z4 = c0.c1, z3 = c0.c2, z2 = c1.c0, z1 = c1.c1, z5 = c1.c2; every
+// output slot depends on its own input slot and one Fp4 square, so r may alias f.
+// Everything here is out of line and BY REFERENCE on purpose: every live Fp2 of a caller is 2 N registers that the interprocedural
+// register allocation takes away from the field products underneath.  With the ten Fp2 values of the textbook formulation held by
+// value in one function, ptxas compiled EVERY fp_mul of the pairing kernels with ~120 extra moves and a callee-save spill
+// (500 instead of 385 instructions, in the function that is 72 % of the run time); tools/codegen_check.py keeps watch.
+template <class T>
+B2K_NI void fp4_sqr(Fp2<typename T::Base>& c0, Fp2<typename T::Base>& c1, const Fp2<typename T::Base>& a, const Fp2<typename T::Base>& b) {
+  Fp2<typename T::Base> t0, t1, t2;
+  fp2_sqr(t0, a);
+  fp2_sqr(t1, b);
+  T::mul_xi(t2, t1);
+  fp2_add(c0, t2, t0);
+  fp2_add(t2, a, b);
+  fp2_sqr(t2, t2);
+  fp2_sub(t2, t2, t0);
+  fp2_sub(c1, t2, t1);
+}
+// r = 3 t + 2 z (SIGN = +1) or 3 t - 2 z (SIGN = -1); r may alias z
+template <int SIGN, class C>
+B2K_NI void cyclotomic_fix(Fp2<C>& r, const Fp2<C>& t, const Fp2<C>& z) {
+  Fp2<C> u;
+  if (SIGN > 0) fp2_add(u, t, z); else fp2_sub(u, t, z);
+  fp2_dbl(u, u);
+  fp2_add(r, u, t);
+}
+template <class T>
+B2K_NI void fp12_cyclotomic_sqr(Fp12<T>& r, const Fp12<T>& f) {
+  Fp2<typename T::Base> t0, t1, t2, t3, t4, t5;
+  fp4_sqr<T>(t0, t1, f.c0.c0, f.c1.c1);          // (z0, z1)
+  fp4_sqr<T>(t2, t3, f.c1.c0, f.c0.c2);          // (z2, z3)
+  fp4_sqr<T>(t4, t5, f.c0.c1, f.c1.c2);          // (z4, z5)
+  T::mul_xi(t5, t5);
+  cyclotomic_fix<-1>(r.c0.c0, t0, f.c0.c0);      // z0 = 3 t0 - 2 z0
+  cyclotomic_fix<+1>(r.c1.c1, t1, f.c1.c1);      // z1 = 3 t1 + 2 z1
+  cyclotomic_fix<-1>(r.c0.c1, t2, f.c0.c1);      // z4 = 3 t2 - 2 z4
+  cyclotomic_fix<+1>(r.c1.c2, t3, f.c1.c2);      // z5 = 3 t3 + 2 z5
+  cyclotomic_fix<+1>(r.c1.c0, t5, f.c1.c0);      // z2 = 3 xi t5 + 2 z2
+  cyclotomic_fix<-1>(r.c0.c2, t4, f.c0.c2);      // z3 = 3 t4 - 2 z3
+}
+
 }  // namespace b2k
