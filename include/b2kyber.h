@@ -93,6 +93,9 @@ int b2k_set_msm_affine(b2k_ctx* ctx, int rounds, int batch);
 /* 1 (default) = every affine round runs as three kernels (forward prefix products, one inversion per thread, backward
  * additions; batch up to 1024), 0 = one fused kernel per round (batch up to 64, prefix products in local memory).  A/B aid. */
 int b2k_set_msm_affine_split(b2k_ctx* ctx, int split);
+/* Affine rounds with the operands of the next output staged global -> shared memory by cp.async: backward pass bit 0 = the first
+ * (gathering) round, bit 1 = the later rounds; forward pass bits 2 and 3 likewise.  Same bytes out; A/B aid. */
+int b2k_set_msm_staging(b2k_ctx* ctx, int mask);
 /* Register cap of the inversion kernel of the affine rounds: 4 [default] = uncapped; 5 = 96 registers, so that its single wave
  * leaves one block slot per SM for a product kernel of another MSM in flight (measured: no gain; kept for A/B).  (The 5/6-block variants of the XYZZ kernel
  * measured slower than 4 and were removed.) */
@@ -427,7 +430,8 @@ int b2k_bn254_g2_unmarshal_check(b2k_ctx* ctx, size_t n, const uint8_t* in /*[n]
 int b2k_bn256_g1_unmarshal_check(b2k_ctx* ctx, size_t n, const uint8_t* in /*[n][64]*/, uint8_t* ok /*[n]*/);
 int b2k_bn256_g2_unmarshal_check(b2k_ctx* ctx, size_t n, const uint8_t* in /*[n][128]*/, uint8_t* ok /*[n]*/);
 
-/* Launch-bound variant of the BLS12-381 pairing kernels (0 = default).  Tuning aid. */
+/* Launch shape / code layout of the BLS12-381 pairing kernels: variant = shape + 4 * layout, shape 0..2 = (64 threads, 4 / 8 / 6
+ * blocks per SM), layout 0 = out-of-line by-value field products (default), 1 = inlined.  Tuning aid. */
 int b2k_set_pairing_variant(b2k_ctx* ctx, int variant);
 
 /* ---- edwards25519 ---------------------------------------------------------------------------------------- */

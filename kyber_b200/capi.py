@@ -48,6 +48,7 @@ def load_library() -> C.CDLL:
         "b2k_set_msm_affine": (C.c_int, [vp, C.c_int, C.c_int]),
         "b2k_last_msm_plan": (C.c_int, [vp, C.POINTER(C.c_int), C.c_int]),
         "b2k_set_msm_affine_split": (C.c_int, [vp, C.c_int]),
+        "b2k_set_msm_staging": (C.c_int, [vp, C.c_int]),
         "b2k_set_mul_occupancy": (C.c_int, [vp, C.c_int]),
         "b2k_set_msm_layout": (C.c_int, [vp, C.c_int]),
     }

@@ -163,6 +163,12 @@ int b2k_set_msm_affine_split(b2k_ctx* ctx, int split) {
   return B2K_OK;
 }
 
+int b2k_set_msm_staging(b2k_ctx* ctx, int mask) {
+  if (!ctx || mask < 0 || mask > 15) return B2K_ERR_ARG;
+  ctx->pt_stage = mask;
+  return B2K_OK;
+}
+
 int b2k_set_msm_window(b2k_ctx* ctx, int c) {
   if (!ctx || (c != 0 && (c < 4 || c > 16))) return B2K_ERR_ARG;
   ctx->force_c = c;

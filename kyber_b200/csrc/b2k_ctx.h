@@ -34,6 +34,7 @@ struct b2k_ctx {
   int affine_split = 1;             // 1 = every round as three kernels (forward products / inversions / backward additions), 0 = one fused kernel
   int affine_batch = 0;             // outputs (batched affine additions) per thread of a round, 8..64; 0 = automatic
   int mul_minb = 0;                 // BLS12-381 G1 Point.Mul batches: resident blocks per SM (0 = compiler's choice, 3, 4), tuning aid
+  int pt_stage = 0;                 // affine rounds with cp.async-staged operands: backward pass bit 0 = round 0 (gather), bit 1 = later rounds; forward pass bits 2, 3
   int acc_minb = 4;                 // register cap of the inversion kernel of the affine rounds: 4 = uncapped (99 registers), 5 = 96 registers
                                     // (leaves a block slot per SM for another MSM's product kernel: measured no gain,
                                     // profiles/r01i_inversion_overlap_ab.txt); b2k_set_msm_occupancy, A/B aid

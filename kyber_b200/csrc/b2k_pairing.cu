@@ -13,13 +13,15 @@ using namespace b2k;
 extern "C" {
 
 void b2k_internal_launch_pair(const b2k_ctx* ctx, size_t n, const uint8_t* g1, const uint8_t* g2, uint8_t* gt) {
-  if (ctx->pair_variant >= 3) b2k_internal_launch_pair_inlined(ctx, ctx->pair_variant - 3, n, g1, g2, gt);
-  else launch_pair_v(ctx, ctx->pair_variant, n, g1, g2, gt);
+  const int layout = ctx->pair_variant / 4, shape = ctx->pair_variant % 4;
+  if (layout == 1) b2k_internal_launch_pair_inlined(ctx, shape, n, g1, g2, gt);
+  else launch_pair_v(ctx, shape, n, g1, g2, gt);
 }
 void b2k_internal_launch_pairing_check(const b2k_ctx* ctx, size_t n, const uint8_t* a1, const uint8_t* a2, const uint8_t* b1,
                                        const uint8_t* b2, uint8_t* ok, int b2_broadcast, const uint8_t* pre_ok) {
-  if (ctx->pair_variant >= 3) b2k_internal_launch_pairing_check_inlined(ctx, ctx->pair_variant - 3, n, a1, a2, b1, b2, ok, b2_broadcast, pre_ok);
-  else launch_pairing_check_v(ctx, ctx->pair_variant, n, a1, a2, b1, b2, ok, b2_broadcast, pre_ok);
+  const int layout = ctx->pair_variant / 4, shape = ctx->pair_variant % 4;
+  if (layout == 1) b2k_internal_launch_pairing_check_inlined(ctx, shape, n, a1, a2, b1, b2, ok, b2_broadcast, pre_ok);
+  else launch_pairing_check_v(ctx, shape, n, a1, a2, b1, b2, ok, b2_broadcast, pre_ok);
 }
 
 int b2k_bls12381_pair_dev(b2k_ctx* ctx, size_t n, const void* d_g1, const void* d_g2, void* d_gt) {
@@ -84,7 +86,7 @@ int b2k_bls12381_pairing_check(b2k_ctx* ctx, size_t n, const uint8_t* a1, const 
 }
 
 int b2k_set_pairing_variant(b2k_ctx* ctx, int v) {
-  if (!ctx || v < 0 || v > 5) return B2K_ERR_ARG;
+  if (!ctx || v < 0 || v > 7 || (v % 4) == 3) return B2K_ERR_ARG;
   ctx->pair_variant = v;
   return B2K_OK;
 }

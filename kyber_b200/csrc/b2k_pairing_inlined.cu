@@ -2,7 +2,7 @@
 // its point of use: 530 KB of code per kernel), kept for A/B runs.  ncu (profiles/r02d_pairing_check_ncu_details.txt) showed that
 // layout stalled 35 % of its issue cycles on instruction fetch; the library default is the compact layout (B2K_COMPACT_FIELD,
 // fp.cuh), measured 113.4 -> 83.5 ms per 65 536 checks (1.16e6 -> 1.57e6 pairings/s, profiles/r02g_layout_ab.txt).
-// b2k_set_pairing_variant(ctx, 3..5) selects the launch shapes 0..2 in this layout.
+// b2k_set_pairing_variant(ctx, 4..6) selects the launch shapes 0..2 in this layout.
 #undef B2K_COMPACT_FIELD
 #define b2k b2k_inlined
 #define b2k_host b2k_inlined_host

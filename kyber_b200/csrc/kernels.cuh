@@ -270,6 +270,28 @@ __global__ void __launch_bounds__(128, 4) k_pt_backward(uint32_t B, uint32_t tot
   msm_pairtree_backward<CV, FIRST>(t, B, gridDim.x * blockDim.x, total, in, entries, offs_in, offs_out, pre, accs, out);
 }
 
+// forward pass with the x coordinates of the next output staged by cp.async; dynamic shared memory: blockDim.x * 4 * sizeof(F)
+template <class CV, bool FIRST>
+__global__ void __launch_bounds__(128, 5) k_pt_forward_staged(uint32_t B, uint32_t total, const Affine<typename CV::F>* __restrict__ in,
+                                                              const uint32_t* __restrict__ entries, const uint32_t* __restrict__ offs_in,
+                                                              const uint32_t* __restrict__ offs_out, typename CV::F* __restrict__ pre,
+                                                              typename CV::F* __restrict__ accs) {
+  extern __shared__ __align__(16) unsigned char pt_smem[];
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  msm_pairtree_forward_staged<CV, FIRST>(t, B, gridDim.x * blockDim.x, total, in, entries, offs_in, offs_out, pre, accs, pt_smem, threadIdx.x);
+}
+// backward pass with the operands of the next output staged global -> shared by cp.async (msm_affine.cuh); dynamic shared memory:
+// blockDim.x * 4 * sizeof(Affine)
+template <class CV, bool FIRST>
+__global__ void __launch_bounds__(128, 4) k_pt_backward_staged(uint32_t B, uint32_t total, const Affine<typename CV::F>* __restrict__ in,
+                                                               const uint32_t* __restrict__ entries, const uint32_t* __restrict__ offs_in,
+                                                               const uint32_t* __restrict__ offs_out, const typename CV::F* __restrict__ pre,
+                                                               const typename CV::F* __restrict__ accs, Affine<typename CV::F>* __restrict__ out) {
+  extern __shared__ __align__(16) unsigned char pt_smem[];
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  msm_pairtree_backward_staged<CV, FIRST>(t, B, gridDim.x * blockDim.x, total, in, entries, offs_in, offs_out, pre, accs, out, pt_smem, threadIdx.x);
+}
+
 // buckets cut by slice boundaries: add their partials (<= 64 serially, larger ones go to a work list)
 template <class CV>
 __global__ void __launch_bounds__(128) k_msm_fixup(uint32_t total, uint32_t L, const uint32_t* __restrict__ offs,

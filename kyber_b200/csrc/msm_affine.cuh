@@ -20,6 +20,10 @@
 #pragma once
 #include "msm.cuh"
 #include "fp_inv.cuh"
+#ifdef B2K_HOST_EMUL
+#include <cstring>
+#include <vector>
+#endif
 
 namespace b2k {
 
@@ -205,6 +209,194 @@ B2K_D void msm_pairtree_backward(uint32_t t, uint32_t B, uint32_t T, uint32_t to
     else if (kind == PT_INF) aff_set_inf(r);
     out[q] = r;
   }
+}
+
+// ---- backward pass with asynchronously staged operands ---------------------------------------------------------------------
+// ncu on the split rounds (profiles/r02d_accumulate_ncu_details.txt): the backward kernels spend 2.0-3.4 of their 11.6 cycles per
+// issued instruction waiting for the two operand points of the output they are about to compute (`long_scoreboard`; round 0 gathers
+// them through the sorted entries, a DRAM round trip), with the multiply pipe at 70 %.  Prefetching them into registers costs the
+// 48 registers the kernel does not have (128 = 4 blocks per SM), and `prefetch.global.L1` measured slower.  Here the operands of
+// output q-1 travel global -> shared memory with cp.async (LDGSTS, 16 bytes each, no register staging) while output q is computed:
+// per thread two 2-point buffers (4 x 96 B; 48 KB per block of 128 threads, four blocks per SM as before).  Round 0 also loads
+// the two sorted entries of output q-2, so that the gather addresses of q-1 are in registers when its copies are issued.
+namespace stage {
+#ifndef B2K_HOST_EMUL
+using addr_t = uint32_t;                                     // shared-window address
+B2K_D addr_t addr(void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+B2K_D void cp16(addr_t dst, const void* src) { asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory"); }
+B2K_D void commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> B2K_D void wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+#else
+// host emulation (tests/host_emul): copies really are deferred -- they land when a wait retires their group, oldest first -- so a
+// schedule that reads a buffer too early or overwrites one too soon fails the emulation tests, not only the GPU run
+using addr_t = unsigned char*;
+struct Piece { unsigned char* dst; const unsigned char* src; };
+inline std::vector<std::vector<Piece>>& groups() { static thread_local std::vector<std::vector<Piece>> g(1); return g; }
+inline addr_t addr(void* p) { return reinterpret_cast<unsigned char*>(p); }
+inline void cp16(addr_t dst, const void* src) { groups().back().push_back({dst, reinterpret_cast<const unsigned char*>(src)}); }
+inline void commit() { groups().emplace_back(); }
+template <int N> inline void wait() {
+  auto& g = groups();                                        // g.back() is the open (uncommitted) group
+  while (g.size() > (size_t)N + 1) {
+    for (const Piece& c : g.front()) memcpy(c.dst, c.src, 16);
+    g.erase(g.begin());
+  }
+}
+#endif
+template <int BYTES> B2K_D void copy(addr_t dst, const void* src) {
+  static_assert(BYTES % 16 == 0, "16-byte pieces");
+#pragma unroll
+  for (int i = 0; i < BYTES / 16; i++) cp16(dst + 16 * i, reinterpret_cast<const unsigned char*>(src) + 16 * i);
+}
+}  // namespace stage
+
+// where the operands of one output live: input position a of a run ending at `end`; round 0: the two sorted entries at a, a + 1
+struct PtLook { uint32_t a, end, v0, v1; };
+
+template <class CV, bool FIRST>
+B2K_D void msm_pairtree_backward_staged(uint32_t t, uint32_t B, uint32_t T, uint32_t total, const Affine<typename CV::F>* in,
+                                        const uint32_t* entries, const uint32_t* offs_in, const uint32_t* offs_out,
+                                        const typename CV::F* pre, const typename CV::F* accs, Affine<typename CV::F>* out,
+                                        unsigned char* smem, uint32_t lane) {
+  using F = typename CV::F;
+  using A = Affine<F>;
+  static_assert(sizeof(A) % 16 == 0, "cp.async moves 16-byte pieces");
+  const uint32_t nout = offs_out[total];
+  const uint32_t q0 = t * B;
+  if (q0 >= nout) return;                                    // (no block-wide barrier below: every thread waits for its own copies only)
+  const uint32_t q1 = (nout - q0 < B) ? nout : q0 + B;
+  A* slot = reinterpret_cast<A*>(smem) + 4 * lane;           // lane = thread of the block; [buffer][operand]
+  const stage::addr_t sbase = stage::addr(slot);
+  uint32_t g = msm_find_bucket(offs_out, total, q1 - 1);
+  uint32_t os = offs_out[g], is = offs_in[g], ie = offs_in[g + 1];
+  // the bucket cursor only moves backwards; look(q) must be called with decreasing q
+  auto look = [&](uint32_t q) {
+    while (q < os) { g--; os = offs_out[g]; ie = is; is = offs_in[g]; }
+    PtLook L;
+    L.a = is + 2 * (q - os); L.end = ie; L.v0 = 0; L.v1 = 0;
+    if (FIRST) { L.v0 = entries[L.a]; L.v1 = (L.a + 1 < L.end) ? entries[L.a + 1] : L.v0; }
+    return L;
+  };
+  auto issue = [&](const PtLook& L, int buf) {
+    const stage::addr_t dst = sbase + (uint32_t)(2 * buf * sizeof(A));
+    if (FIRST) {
+      stage::copy<sizeof(A)>(dst, in + (L.v0 & 0x7fffffffu));
+      if (L.a + 1 < L.end) stage::copy<sizeof(A)>(dst + (uint32_t)sizeof(A), in + (L.v1 & 0x7fffffffu));
+    } else {
+      stage::copy<sizeof(A)>(dst, in + L.a);
+      if (L.a + 1 < L.end) stage::copy<sizeof(A)>(dst + (uint32_t)sizeof(A), in + L.a + 1);
+    }
+  };
+  PtLook cur = look(q1 - 1), nxt = cur;
+  issue(cur, 0);
+  stage::commit();
+  bool have_nxt = q1 - 1 > q0;
+  if (have_nxt) nxt = look(q1 - 2);
+  F inv = accs[t];
+  int k = 0;
+  for (uint32_t q = q1 - 1;; q--, k ^= 1) {
+    PtLook aft = nxt;
+    bool have_aft = false;
+    if (have_nxt) {
+      issue(nxt, k ^ 1);                                     // operands of output q-1 (round 0: its entries arrived during the last iteration)
+      if (q - 1 > q0) { aft = look(q - 2); have_aft = true; }
+    }
+    stage::commit();
+    stage::wait<1>();                                        // everything but the group just committed has landed: buffer k is complete
+    const bool pair = cur.a + 1 < cur.end;
+    Affine<F> p1 = slot[2 * k], p2, r;
+    if (pair) p2 = slot[2 * k + 1]; else p2 = p1;
+    if (FIRST) {
+      if (cur.v0 >> 31) f_neg(p1.y, p1.y);
+      if (pair) { if (cur.v1 >> 31) f_neg(p2.y, p2.y); } else p2.y = p1.y;
+    }
+    F d, dinv, lam, tt;
+    const int kind = pt_classify(d, p1, p2, pair);
+    F pj = pre[(size_t)(q - q0) * T + t];
+    f_mul_i(dinv, inv, pj);
+    if (q > q0) f_mul_i(inv, inv, d);
+    if (kind == PT_DBL) { f_sqr(tt, p1.x); f_dbl(lam, tt); f_add(tt, lam, tt); }
+    else f_sub(tt, p2.y, p1.y);
+    f_mul_i(lam, tt, dinv);
+    f_sqr_i(r.x, lam); f_sub(r.x, r.x, p1.x); f_sub(r.x, r.x, p2.x);
+    f_sub(tt, p1.x, r.x); f_mul_i(r.y, lam, tt); f_sub(r.y, r.y, p1.y);
+    if (kind == PT_COPY1) r = p1;
+    else if (kind == PT_COPY2) r = p2;
+    else if (kind == PT_INF) aff_set_inf(r);
+    out[q] = r;
+    if (q == q0) break;
+    cur = nxt; nxt = aft; have_nxt = have_aft;
+  }
+  stage::wait<0>();
+}
+
+// forward pass, staged the same way: only the two x coordinates of an output travel (48 bytes each; the rare x = 0 / equal-x
+// cases re-read the full points).  ncu: this pass waits 6-9 of its 15 cycles per issued instruction for them.
+template <class CV, bool FIRST>
+B2K_D void msm_pairtree_forward_staged(uint32_t t, uint32_t B, uint32_t T, uint32_t total, const Affine<typename CV::F>* in,
+                                       const uint32_t* entries, const uint32_t* offs_in, const uint32_t* offs_out,
+                                       typename CV::F* pre, typename CV::F* accs, unsigned char* smem, uint32_t lane) {
+  using F = typename CV::F;
+  static_assert(sizeof(F) % 16 == 0, "cp.async moves 16-byte pieces");
+  const uint32_t nout = offs_out[total];
+  const uint32_t q0 = t * B;
+  if (q0 >= nout) return;
+  const uint32_t q1 = (nout - q0 < B) ? nout : q0 + B;
+  F* slot = reinterpret_cast<F*>(smem) + 4 * lane;           // [buffer][x1, x2]
+  const stage::addr_t sbase = stage::addr(slot);
+  uint32_t g = msm_find_bucket(offs_out, total, q0);
+  uint32_t os = offs_out[g], oe = offs_out[g + 1], is = offs_in[g], ie = offs_in[g + 1];
+  auto look = [&](uint32_t q) {                              // increasing q only
+    while (q >= oe) { g++; os = oe; oe = offs_out[g + 1]; is = ie; ie = offs_in[g + 1]; }
+    PtLook L;
+    L.a = is + 2 * (q - os); L.end = ie; L.v0 = 0; L.v1 = 0;
+    if (FIRST && L.a + 1 < L.end) { L.v0 = entries[L.a]; L.v1 = entries[L.a + 1]; }
+    return L;
+  };
+  auto issue = [&](const PtLook& L, int buf) {
+    if (L.a + 1 >= L.end) return;                            // single operand: carried over, nothing to invert
+    const stage::addr_t dst = sbase + (uint32_t)(2 * buf * sizeof(F));
+    const Affine<F>* s1 = FIRST ? in + (L.v0 & 0x7fffffffu) : in + L.a;
+    const Affine<F>* s2 = FIRST ? in + (L.v1 & 0x7fffffffu) : in + L.a + 1;
+    stage::copy<sizeof(F)>(dst, &s1->x);
+    stage::copy<sizeof(F)>(dst + (uint32_t)sizeof(F), &s2->x);
+  };
+  PtLook cur = look(q0), nxt = cur;
+  issue(cur, 0);
+  stage::commit();
+  bool have_nxt = q0 + 1 < q1;
+  if (have_nxt) nxt = look(q0 + 1);
+  F acc;
+  f_set_one(acc);
+  int k = 0;
+  for (uint32_t q = q0;; q++, k ^= 1) {
+    PtLook aft = nxt;
+    bool have_aft = false;
+    if (have_nxt) {
+      issue(nxt, k ^ 1);
+      if (q + 2 < q1) { aft = look(q + 2); have_aft = true; }
+    }
+    stage::commit();
+    stage::wait<1>();
+    F d;
+    f_set_one(d);
+    if (cur.a + 1 < cur.end) {
+      F x1 = slot[2 * k], x2 = slot[2 * k + 1], dx;
+      f_sub(dx, x2, x1);
+      if (!f_is_zero(x1) && !f_is_zero(x2) && !f_is_zero(dx)) d = dx;
+      else {                                                 // rare: possible infinity / doubling / cancellation
+        Affine<F> p1, p2;
+        const bool pair = pt_fetch<CV, FIRST>(p1, p2, in, entries, cur.a, cur.end);
+        pt_classify(d, p1, p2, pair);
+      }
+    }
+    pre[(size_t)(q - q0) * T + t] = acc;
+    f_mul_i(acc, acc, d);
+    if (q + 1 == q1) break;
+    cur = nxt; nxt = aft; have_nxt = have_aft;
+  }
+  stage::wait<0>();
+  accs[t] = acc;
 }
 
 }  // namespace b2k

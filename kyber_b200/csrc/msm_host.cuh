@@ -374,12 +374,25 @@ int msm_enqueue(b2k_ctx* ctx, size_t n_in, const MsmPlan& pl, const uint8_t* d_s
           k_scan_finish<<<sblocks, 1024, 0, st>>>((uint32_t)total, bsum, offs_nxt, cursor);
           const unsigned grid = ap.T[r] / 128;
           if (ctx->affine_split) {
-            if (r == 0) k_pt_forward<CV, true><<<grid, 128, 0, st>>>(ap.B[r], (uint32_t)total, in_cur, entries, offs_cur, offs_nxt, pt_pre, pt_accs);
-            else k_pt_forward<CV, false><<<grid, 128, 0, st>>>(ap.B[r], (uint32_t)total, in_cur, nullptr, offs_cur, offs_nxt, pt_pre, pt_accs);
+            constexpr size_t fstage_bytes = 128 * 4 * sizeof(F);              // two 2-coordinate buffers per thread (24 KB for G1)
+            if (fstage_bytes <= 48 * 1024 && ((ctx->pt_stage >> (r == 0 ? 2 : 3)) & 1)) {
+              if (r == 0) k_pt_forward_staged<CV, true><<<grid, 128, fstage_bytes, st>>>(ap.B[r], (uint32_t)total, in_cur, entries, offs_cur, offs_nxt, pt_pre, pt_accs);
+              else k_pt_forward_staged<CV, false><<<grid, 128, fstage_bytes, st>>>(ap.B[r], (uint32_t)total, in_cur, nullptr, offs_cur, offs_nxt, pt_pre, pt_accs);
+            } else {
+              if (r == 0) k_pt_forward<CV, true><<<grid, 128, 0, st>>>(ap.B[r], (uint32_t)total, in_cur, entries, offs_cur, offs_nxt, pt_pre, pt_accs);
+              else k_pt_forward<CV, false><<<grid, 128, 0, st>>>(ap.B[r], (uint32_t)total, in_cur, nullptr, offs_cur, offs_nxt, pt_pre, pt_accs);
+            }
             if (ctx->acc_minb == 5) k_pt_invert<F, 5><<<grid, 128, 0, st>>>(ap.B[r], (uint32_t)total, offs_nxt, pt_accs);
             else k_pt_invert<F, 4><<<grid, 128, 0, st>>>(ap.B[r], (uint32_t)total, offs_nxt, pt_accs);
-            if (r == 0) k_pt_backward<CV, true><<<grid, 128, 0, st>>>(ap.B[r], (uint32_t)total, in_cur, entries, offs_cur, offs_nxt, pt_pre, pt_accs, out);
-            else k_pt_backward<CV, false><<<grid, 128, 0, st>>>(ap.B[r], (uint32_t)total, in_cur, nullptr, offs_cur, offs_nxt, pt_pre, pt_accs, out);
+            constexpr size_t stage_bytes = 128 * 4 * sizeof(Affine<F>);       // two 2-point buffers per thread (48 KB for G1)
+            const bool staged = stage_bytes <= 48 * 1024 && ((ctx->pt_stage >> (r == 0 ? 0 : 1)) & 1);
+            if (staged) {
+              if (r == 0) k_pt_backward_staged<CV, true><<<grid, 128, stage_bytes, st>>>(ap.B[r], (uint32_t)total, in_cur, entries, offs_cur, offs_nxt, pt_pre, pt_accs, out);
+              else k_pt_backward_staged<CV, false><<<grid, 128, stage_bytes, st>>>(ap.B[r], (uint32_t)total, in_cur, nullptr, offs_cur, offs_nxt, pt_pre, pt_accs, out);
+            } else {
+              if (r == 0) k_pt_backward<CV, true><<<grid, 128, 0, st>>>(ap.B[r], (uint32_t)total, in_cur, entries, offs_cur, offs_nxt, pt_pre, pt_accs, out);
+              else k_pt_backward<CV, false><<<grid, 128, 0, st>>>(ap.B[r], (uint32_t)total, in_cur, nullptr, offs_cur, offs_nxt, pt_pre, pt_accs, out);
+            }
             nl += 7;
           } else {
             if (r == 0) k_msm_pairtree_round<CV, true><<<grid, 128, 0, st>>>(ap.B[r], (uint32_t)total, in_cur, entries, offs_cur, offs_nxt, out);

@@ -52,7 +52,7 @@ static __global__ void __launch_bounds__(BLOCK, MINB) k_bls_pairing_check(size_t
 
 
 // launch-bound variants: (threads per block, min blocks per SM) -> register cap 65536 / (threads * blocks)
-#define B2K_PAIR_VARIANTS(X) X(0, 64, 4) X(1, 64, 8) X(2, 64, 6)     /* round 1 swept six shapes (profiles/r01*): (64, 4) won */
+#define B2K_PAIR_VARIANTS(X) X(0, 64, 4) X(1, 64, 8) X(2, 64, 6)   /* shapes (threads, min blocks per SM); (64, 4) = 255 registers wins every sweep (profiles/r01*, r02l) */
 inline void launch_pair_v(const b2k_ctx* ctx, int variant, size_t n, const uint8_t* g1, const uint8_t* g2, uint8_t* gt) {
   switch (variant) {
 #define X(ID, B, M) case ID: k_bls_pair<B, M><<<(unsigned)((n + B - 1) / B), B, 0, ctx->stream>>>(n, g1, g2, gt, ctx->d_flags); break;
@@ -73,8 +73,11 @@ inline void launch_pairing_check_v(const b2k_ctx* ctx, int variant, size_t n, co
 
 }  // namespace b2k
 
-// The pairing kernels exist in two code layouts (fp.cuh: B2K_COMPACT_FIELD): b2k_pairing.cu holds the compact one (field
-// products are out-of-line by-value calls; variants 0..2 = the default), b2k_pairing_inlined.cu the fully inlined one (variants 3..5).
+// The pairing kernels exist in two code layouts, variant = shape + 4 * layout (b2k_set_pairing_variant):
+//   layout 0 (variants 0..2, b2k_pairing.cu, the default): B2K_COMPACT_FIELD -- Fp and Fp2 products are out-of-line by-value calls
+//   layout 1 (variants 4..6, b2k_pairing_inlined.cu): every field product inlined at its point of use
+// (a third layout -- Fp product by value, Fp2 product out of line BY REFERENCE -- and a (64, 7) shape were measured and dropped:
+//  81.4 ms against 75.5 ms per 65 536 checks, and (64, 7) compiles to the 128 registers of (64, 8); profiles/r02l_pairing_variants.txt)
 // Every caller (b2k_pairing.cu, the bls.Verify paths of b2k_h2c.cu) launches through these two functions.
 extern "C" void b2k_internal_launch_pair(const b2k_ctx* ctx, size_t n, const uint8_t* g1, const uint8_t* g2, uint8_t* gt);
 extern "C" void b2k_internal_launch_pairing_check(const b2k_ctx* ctx, size_t n, const uint8_t* a1, const uint8_t* a2, const uint8_t* b1,

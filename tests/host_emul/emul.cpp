@@ -103,6 +103,7 @@ static MsmPlan emul_plan(int c, int m) {
   return pl;
 }
 
+static int g_pt_stage = 0;        // emul_set_pt_stage: run the backward pass of the split rounds through the cp.async-staged variant
 // digits, counting sort, (affine rounds,) accumulate, fix-up: the W x 2^(c-1) buckets of these pairs
 template <class CV>
 static int emul_msm_buckets(size_t n, const uint8_t* scalars, const uint8_t* pts, const MsmPlan& pl, std::vector<Xyzz<typename CV::F>>& B,
@@ -141,11 +142,25 @@ static int emul_msm_buckets(size_t n, const uint8_t* scalars, const uint8_t* pts
       if (split) {                                     // three kernels per round: forward / invert / backward
         std::vector<F> pre((size_t)T * PB), accs(T);
         for (uint32_t t = 0; t < T; t++) {
+          if (g_pt_stage) {
+            alignas(16) unsigned char slots[4 * sizeof(F)];
+            memset(slots, 0xEE, sizeof slots);
+            if (r == 0) msm_pairtree_forward_staged<CV, true>(t, (uint32_t)PB, T, (uint32_t)total, P.data(), entries.data(), offs.data(), no.data(), pre.data(), accs.data(), slots, 0);
+            else msm_pairtree_forward_staged<CV, false>(t, (uint32_t)PB, T, (uint32_t)total, cur.data(), nullptr, offs.data(), no.data(), pre.data(), accs.data(), slots, 0);
+            continue;
+          }
           if (r == 0) msm_pairtree_forward<CV, true>(t, (uint32_t)PB, T, (uint32_t)total, P.data(), entries.data(), offs.data(), no.data(), pre.data(), accs.data());
           else msm_pairtree_forward<CV, false>(t, (uint32_t)PB, T, (uint32_t)total, cur.data(), nullptr, offs.data(), no.data(), pre.data(), accs.data());
         }
         for (uint32_t t = 0; t < T; t++) msm_pairtree_invert<F>(t, (uint32_t)PB, (uint32_t)total, no.data(), accs.data());
         for (uint32_t t = 0; t < T; t++) {
+          if (g_pt_stage) {                            // operands staged by (emulated, deferred) cp.async: k_pt_backward_staged
+            alignas(16) unsigned char slots[4 * sizeof(Affine<F>)];
+            memset(slots, 0xEE, sizeof slots);
+            if (r == 0) msm_pairtree_backward_staged<CV, true>(t, (uint32_t)PB, T, (uint32_t)total, P.data(), entries.data(), offs.data(), no.data(), pre.data(), accs.data(), nxt.data(), slots, 0);
+            else msm_pairtree_backward_staged<CV, false>(t, (uint32_t)PB, T, (uint32_t)total, cur.data(), nullptr, offs.data(), no.data(), pre.data(), accs.data(), nxt.data(), slots, 0);
+            continue;
+          }
           if (r == 0) msm_pairtree_backward<CV, true>(t, (uint32_t)PB, T, (uint32_t)total, P.data(), entries.data(), offs.data(), no.data(), pre.data(), accs.data(), nxt.data());
           else msm_pairtree_backward<CV, false>(t, (uint32_t)PB, T, (uint32_t)total, cur.data(), nullptr, offs.data(), no.data(), pre.data(), accs.data(), nxt.data());
         }
@@ -358,3 +373,4 @@ void emul_bls12381_g2_mul_batch_w4(size_t n, const uint8_t* s, const uint8_t* p,
 void emul_bls12381_g2_mul_batch(size_t n, const uint8_t* s, const uint8_t* p, uint8_t* o) { emul_mul_batch<Bls381G2>(n, s, p, o); }
 int emul_bls12381_g2_msm(size_t n, const uint8_t* s, const uint8_t* p, int c, int m, int L, uint8_t* o) { return emul_msm<Bls381G2>(n, s, p, c, m, o, L); }
 }
+extern "C" void emul_set_pt_stage(int on) { g_pt_stage = on; }

@@ -176,6 +176,13 @@ def test_affine_pair_tree_round_bodies(emul):
             o48 = ctypes.create_string_buffer(48)        # the round as three kernels (forward x-only / invert / backward)
             rc = emul.emul_bls12381_g1_msm_affine_split(ctypes.c_size_t(n), sb, pb, c, m, L, rounds, 3 * pbatch, o48)
             assert rc == 0 and o48.raw == want, ("split", c, m, L, rounds, pbatch)
+            o48 = ctypes.create_string_buffer(48)        # ... with the backward pass's operands staged by (deferred) cp.async
+            emul.emul_set_pt_stage(1)
+            try:
+                rc = emul.emul_bls12381_g1_msm_affine_split(ctypes.c_size_t(n), sb, pb, c, m, L, rounds, 3 * pbatch, o48)
+            finally:
+                emul.emul_set_pt_stage(0)
+            assert rc == 0 and o48.raw == want, ("split + staged", c, m, L, rounds, pbatch)
     # bn254 (8-limb field) through the same template
     from oracle import bn254 as o4
     pts4 = [o4.g1_mul(rng.randrange(1, o4.ORDER)) for _ in range(12)]
