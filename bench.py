@@ -309,6 +309,14 @@ def section_bdn_aggregate(eng, torch, steps: int, threads: int):
     for _ in range(steps):
         once()
     ms = (time.perf_counter() - t0) * 1e3 / steps
+    parts = {}                                                            # where the time goes (one more pass, piece by piece)
+    for name, fn in (("coefficients_host_blake2xs", lambda: eng.bdn_coefficients(pks, 96, add_one=True)),
+                     ("g1_msm_signatures", lambda: eng.bls12381_g1_msm(cb, sig_aff)),
+                     ("g2_msm_keys", lambda: eng.bls12381_g2_msm(cb, pk_aff)),
+                     ("one_bls_verify", lambda: eng.bls12381_verify_g1sig(agg_key, [msg], h.DST_G1, agg_sig))):
+        t1 = time.perf_counter()
+        fn()
+        parts[name] = round((time.perf_counter() - t1) * 1e3, 3)
     # CPU: the reference's loop Mul(coef, sig) + Add over the signatures (bdn.go:128-154) with the same 128-bit coefficients, bounded sample
     from oracle import cpu_ref
     lib = cpu_ref.load()
@@ -317,7 +325,8 @@ def section_bdn_aggregate(eng, torch, steps: int, threads: int):
     out = cpu_ref.g1_msm_muladd(lib, cb[:32 * ns], sig_aff[:96 * ns], threads)
     dt = time.perf_counter() - t0
     assert out == eng.bls12381_g1_msm(cb[:32 * ns], sig_aff[:96 * ns])
-    return {"value": n / (ms * 1e-3), "unit": "signers/s", "ms_per_aggregate": ms, "signers": n,
+    return {"value": n / (ms * 1e-3), "unit": "signers/s", "ms_per_aggregate": ms, "signers": n, "parts_ms": parts,
+            "parts_note": "one_bls_verify is ONE pairing check: a single thread's latency (the kernels are one check per thread), not throughput",
             "workload": "BDN aggregate of 65 536 same-message signatures (BASELINE.json configs[2] mode B): coefficients, G1 MSM of the signatures, "
                         "G2 MSM of the keys (128-bit factors c_i + 1), one bls.Verify; host buffers every call",
             "cpu_baseline": {"value": ns / dt, "unit": "signers/s", "cores": threads, "kind": "port",

@@ -431,7 +431,8 @@ int b2k_bn256_g1_unmarshal_check(b2k_ctx* ctx, size_t n, const uint8_t* in /*[n]
 int b2k_bn256_g2_unmarshal_check(b2k_ctx* ctx, size_t n, const uint8_t* in /*[n][128]*/, uint8_t* ok /*[n]*/);
 
 /* Launch shape / code layout of the BLS12-381 pairing kernels: variant = shape + 4 * layout, shape 0..2 = (64 threads, 4 / 8 / 6
- * blocks per SM), layout 0 = out-of-line by-value field products (default), 1 = inlined.  Tuning aid. */
+ * blocks per SM), layout 0 = out-of-line by-value field products (default), 1 = inlined;
+ * 16 + 2 m + f = Miller loop and final exponentiation as two kernels (m, f: 0 = 128 registers, 1 = 255).  Tuning aid. */
 int b2k_set_pairing_variant(b2k_ctx* ctx, int variant);
 
 /* ---- edwards25519 ---------------------------------------------------------------------------------------- */

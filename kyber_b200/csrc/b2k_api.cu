@@ -103,6 +103,7 @@ void b2k_destroy(b2k_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   if (ctx->arena.base) cudaFree(ctx->arena.base);
   if (ctx->arena_in.base) cudaFree(ctx->arena_in.base);
+  if (ctx->pair_scratch) cudaFree(ctx->pair_scratch);
   if (ctx->d_flags) cudaFree(ctx->d_flags);
   if (ctx->h_flags) cudaFreeHost(ctx->h_flags);
   for (int i = 0; i < N_EV; i++) cudaEventDestroy(ctx->ev[i]);

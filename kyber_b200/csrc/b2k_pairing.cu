@@ -12,14 +12,39 @@ using namespace b2k;
 
 extern "C" {
 
+// Miller values of the split kernels: one grow-only buffer per context (nullptr when the allocation fails: the caller falls back to the fused kernel)
+static BFp12* pair_scratch(const b2k_ctx* cctx, size_t n) {
+  b2k_ctx* ctx = const_cast<b2k_ctx*>(cctx);
+  const size_t need = n * sizeof(BFp12);
+  if (need > ctx->pair_scratch_cap) {
+    cudaStreamSynchronize(ctx->stream);                       // nothing in flight may still read the old buffer
+    if (ctx->pair_scratch) cudaFree(ctx->pair_scratch);
+    ctx->pair_scratch = nullptr; ctx->pair_scratch_cap = 0;
+    void* p = nullptr;
+    if (cudaMalloc(&p, need) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    ctx->pair_scratch = p; ctx->pair_scratch_cap = need;
+  }
+  return reinterpret_cast<BFp12*>(ctx->pair_scratch);
+}
+
 void b2k_internal_launch_pair(const b2k_ctx* ctx, size_t n, const uint8_t* g1, const uint8_t* g2, uint8_t* gt) {
-  const int layout = ctx->pair_variant / 4, shape = ctx->pair_variant % 4;
+  int v = ctx->pair_variant;
+  if (v >= 16) {
+    if (BFp12* f = pair_scratch(ctx, n)) { launch_pair_split(ctx, v - 16, n, g1, g2, gt, f); return; }
+    v = 0;
+  }
+  const int layout = v / 4, shape = v % 4;
   if (layout == 1) b2k_internal_launch_pair_inlined(ctx, shape, n, g1, g2, gt);
   else launch_pair_v(ctx, shape, n, g1, g2, gt);
 }
 void b2k_internal_launch_pairing_check(const b2k_ctx* ctx, size_t n, const uint8_t* a1, const uint8_t* a2, const uint8_t* b1,
                                        const uint8_t* b2, uint8_t* ok, int b2_broadcast, const uint8_t* pre_ok) {
-  const int layout = ctx->pair_variant / 4, shape = ctx->pair_variant % 4;
+  int v = ctx->pair_variant;
+  if (v >= 16) {
+    if (BFp12* f = pair_scratch(ctx, n)) { launch_pairing_check_split(ctx, v - 16, n, a1, a2, b1, b2, ok, b2_broadcast, pre_ok, f); return; }
+    v = 0;
+  }
+  const int layout = v / 4, shape = v % 4;
   if (layout == 1) b2k_internal_launch_pairing_check_inlined(ctx, shape, n, a1, a2, b1, b2, ok, b2_broadcast, pre_ok);
   else launch_pairing_check_v(ctx, shape, n, a1, a2, b1, b2, ok, b2_broadcast, pre_ok);
 }
@@ -29,7 +54,7 @@ int b2k_bls12381_pair_dev(b2k_ctx* ctx, size_t n, const void* d_g1, const void* 
   CK(cudaSetDevice(ctx->device));
   b2k_internal_launch_pair(ctx, n, (const uint8_t*)d_g1, (const uint8_t*)d_g2, (uint8_t*)d_gt);
   CK(cudaGetLastError());
-  ctx->launches += 1;
+  ctx->launches += (ctx->pair_variant >= 16) ? 2 : 1;
   return B2K_OK;
 }
 
@@ -56,7 +81,7 @@ int b2k_bls12381_pairing_check_dev(b2k_ctx* ctx, size_t n, const void* a1, const
   CK(cudaSetDevice(ctx->device));
   b2k_internal_launch_pairing_check(ctx, n, (const uint8_t*)a1, (const uint8_t*)a2, (const uint8_t*)b1, (const uint8_t*)b2, (uint8_t*)d_ok, 0, nullptr);
   CK(cudaGetLastError());
-  ctx->launches += 1;
+  ctx->launches += (ctx->pair_variant >= 16) ? 2 : 1;
   return B2K_OK;
 }
 
@@ -86,7 +111,7 @@ int b2k_bls12381_pairing_check(b2k_ctx* ctx, size_t n, const uint8_t* a1, const 
 }
 
 int b2k_set_pairing_variant(b2k_ctx* ctx, int v) {
-  if (!ctx || v < 0 || v > 7 || (v % 4) == 3) return B2K_ERR_ARG;
+  if (!ctx || v < 0 || (v < 16 && (v > 7 || (v % 4) == 3)) || v >= 16 + 4) return B2K_ERR_ARG;
   ctx->pair_variant = v;
   return B2K_OK;
 }

@@ -11,7 +11,8 @@ gt = torch.empty(n * 576, dtype=torch.uint8, device='cuda')
 ok = torch.empty(n, dtype=torch.uint8, device='cuda')
 eng.set_stream(torch.cuda.current_stream().cuda_stream)
 want = o.gt_to_bytes(o.pairing_reference(o.g1_mul(12345), o.g2_mul(6789)))
-for v in (0, 1, 2, 4, 5, 6):
+variants = [0, 1, 2, 4, 16, 17, 18, 19, 0]      # fused compact shapes, fused inlined, the four split forms
+for v in variants:
     eng._check(eng.lib.b2k_set_pairing_variant(eng.h, v))
     for name, fn in (("pair", lambda: eng.call_dev("b2k_bls12381_pair_dev", n, g1.data_ptr(), g2.data_ptr(), gt.data_ptr())),
                      ("check", lambda: eng._check(eng.lib.b2k_bls12381_pairing_check_dev(eng.h, n, g1.data_ptr(), g2.data_ptr(), g1.data_ptr(), g2.data_ptr(), ok.data_ptr())))):
