@@ -1,5 +1,6 @@
 // b2k_g2.cu -- C ABI entry points for BLS12-381 G2 (Point.Mul batches, MSM) and for batched ZCash
 // decompression + subgroup checks of G1/G2 (UnmarshalBinary, kilic/g1.go:127-131, g2.go:126-130).
+#define B2K_FP2_BYREF 1   // Fp2 products out of line BY REFERENCE (tower.cuh): the G2 MSM / Point.Mul kernels of this unit hold whole Fp2 points by value
 #include "msm_host.cuh"
 #include "codec.cuh"
 using namespace b2k_host;

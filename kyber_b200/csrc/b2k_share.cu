@@ -6,6 +6,7 @@
 // (index, point) pairs; x_i = index_i + 1.
 // PubPoly.Eval / Shares (poly.go:340-357): v = sum_j x^j C_j by Horner, one thread per evaluation index; this is the
 // per-partial-signature cost of tbls.Recover (sign/tbls/tbls.go:118-151: public.Eval(idx) for every share).
+#define B2K_FP2_BYREF 1   // Fp2 products out of line BY REFERENCE (tower.cuh): instantiates the G2 MSM kernels (RecoverCommit on G2): same layout as b2k_g2.cu, or the weak host stubs of the two units would name different device code
 #include "msm_host.cuh"
 #include "codec.cuh"
 using namespace b2k_host;

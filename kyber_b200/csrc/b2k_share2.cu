@@ -5,6 +5,7 @@
 // steps, L_j = M / (x - x_j) / M'(x_j) by synthetic division (one thread per j, O(t) each instead of the reference's O(t^2)
 // polynomial products per j), then t^2 scalar multiplications and t column sums.
 // PriPoly.Commit (poly.go:143-149): commits[i] = coeffs[i] * B for one base point B -- a fixed-base batch.
+#define B2K_FP2_BYREF 1   // Fp2 products out of line BY REFERENCE (tower.cuh): G2 RecoverPubPoly / Commit batches: same layout as b2k_g2.cu
 #include "msm_host.cuh"
 #include "codec.cuh"
 using namespace b2k_host;

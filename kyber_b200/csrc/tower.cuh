@@ -31,7 +31,12 @@ template <class C> B2K_D void fp2_set_one(Fp2<C>& r) { fp_set_one(r.c0); fp_set_
 // Fp2 product instead of three round trips through local memory).
 // B2K_COMPACT_FIELD: one by-value body (operands and result in registers through the ABI) whose three products are calls
 // to the single out-of-line Fp product (fp.cuh) -- ~1 KB of code instead of 16 KB.
-#ifdef B2K_COMPACT_FIELD
+// B2K_FP2_BYREF (set by a translation unit in front of its includes) keeps the by-reference Fp2 product below with the
+// out-of-line Fp product underneath: kernels that hold whole Fp2 points by value (the G2 MSM: a 96-word XYZZ accumulator plus
+// temporaries) otherwise leave the register allocator so little room that the Fp product itself is compiled with 100-470 extra
+// instructions (tools/codegen_check.py: 470-853 instead of 385 in b2k_g2.o); the pairing kernels are the opposite case
+// (by value 75.5 ms, by reference 81.4 ms per 65 536 checks, profiles/r02l_pairing_variants.txt).
+#if defined(B2K_COMPACT_FIELD) && !defined(B2K_FP2_BYREF)
 template <class C>
 B2K_NI Fp2<C> fp2_mul_v(Fp2<C> a, Fp2<C> b) {
   Fp<C> t0, t1, s0, s1;
@@ -115,7 +120,7 @@ B2K_NI void fp2_mul_lazy(Fp2<C>& r, const Fp2<C>& a, const Fp2<C>& b) {
 }
 
 // complex squaring: 2 base multiplications (same register-resident structure)
-#ifdef B2K_COMPACT_FIELD
+#if defined(B2K_COMPACT_FIELD) && !defined(B2K_FP2_BYREF)
 template <class C>
 B2K_NI Fp2<C> fp2_sqr_v(Fp2<C> a) {
   Fp<C> s, d, m;

@@ -2,7 +2,7 @@
 # Run on the GPU box (under gpurun): launch list + one full ncu capture of the bucket-accumulate kernel.
 # Usage: tools/profile.sh <round-tag>
 set -u
-TAG=${1:-r02}
+TAG=${1:-r02z}
 mkdir -p gpurun_out
 export B2K_SKIP_CPU_BASELINE=1
 export B2K_SKIP_PAIRINGS=1

@@ -32,5 +32,5 @@ print("%-66s %6s %12s %10s %7s" % ("kernel", "count", "total_ms", "avg_us", "sha
 for k, (c, ns) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
     share = "-" if excluded(k) else "%.1f%%" % (100 * ns / total)
     print("%-66s %6d %12.3f %10.1f %7s" % (k, c, ns / 1e6, ns / c / 1e3, share))
-acc = sum(v[1] for k, v in agg.items() if "pairtree_round" in k or "accumulate_slices" in k or "k_pt_counts" in k)
+acc = sum(v[1] for k, v in agg.items() if "pairtree_round" in k or "accumulate_slices" in k or "k_pt_" in k)
 print("# bucket-accumulate pass (pair-tree rounds + XYZZ slices) share of one MSM under ncu: %.1f%%" % (100 * acc / total))
