@@ -109,6 +109,7 @@ void b2k_destroy(b2k_ctx* ctx) {
   for (int i = 0; i < N_EV; i++) cudaEventDestroy(ctx->ev[i]);
   for (int i = 0; i < 10; i++) cudaEventDestroy(ctx->gev[i]);
   if (ctx->stream2) { cudaStreamSynchronize(ctx->stream2); cudaStreamDestroy(ctx->stream2); }
+  if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }

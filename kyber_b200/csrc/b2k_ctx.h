@@ -27,7 +27,9 @@ struct b2k_ctx {
   int use_glv = 1;      // BLS12-381 G1 MSM: split scalars with the curve endomorphism (0 = plain 255-bit pipeline, for A/B)
   int use_v1 = 0;       // 1 = one-thread-per-bucket accumulate (kept for A/B measurements)
   cudaStream_t stream2 = nullptr;   // high-priority side stream: bucket reduction of one window group overlaps the next accumulate
-  cudaEvent_t gev[10];              // group hand-over events
+  cudaStream_t copy_stream = nullptr;   // H2D of the host-buffer MSM in chunks, next to the front-end kernels (msm_host)
+  int h2d_chunks = 0;               // > 1 while msm_host enqueues a chunked call: the front end waits for gev[1 + k] before chunk k
+  cudaEvent_t gev[10];              // group hand-over events (msm_groups > 1) / chunk hand-over events of the chunked input copy
   int msm_groups = 1;               // window groups of the overlapped MSM tail; measured SLOWER than the serial pipeline on
                                     // B200 (accumulate blocks fill the register file, nothing co-resides): kept as an experiment
   int affine_rounds = -1;           // affine pair-tree rounds before the XYZZ slices: -1 = automatic, 0 = off (A/B), 1..8 forced
@@ -35,6 +37,7 @@ struct b2k_ctx {
   int affine_batch = 0;             // outputs (batched affine additions) per thread of a round, 8..64; 0 = automatic
   int mul_minb = 0;                 // BLS12-381 G1 Point.Mul batches: resident blocks per SM (0 = compiler's choice, 3, 4), tuning aid
   int pt_stage = 0;                 // affine rounds with cp.async-staged operands: backward pass bit 0 = round 0 (gather), bit 1 = later rounds; forward pass bits 2, 3
+  bool pt_stage_opted = false;      // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) done for the staged backward kernels on this context's device
   int acc_minb = 4;                 // register cap of the inversion kernel of the affine rounds: 4 = uncapped (99 registers), 5 = 96 registers
                                     // (leaves a block slot per SM for another MSM's product kernel: measured no gain,
                                     // profiles/r01i_inversion_overlap_ab.txt); b2k_set_msm_occupancy, A/B aid

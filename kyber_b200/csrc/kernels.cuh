@@ -23,12 +23,14 @@ __global__ void __launch_bounds__(256) k_load_points(size_t n, const uint8_t* __
 // ---- GLV front end (BLS12-381 G1): operand conversion + scalar split in one pass ------------------------------
 // pts[i] = +-P_i, pts[n+i] = +-(-phi(P_i)) = (beta x, -+y); vscalars[i], vscalars[n+i] = the two 127-bit magnitudes as
 // 32-byte big-endian scalars, so that the digit/sort stages run unchanged over 2n (scalar, point) pairs.
-static __global__ void __launch_bounds__(256) k_glv_prepare_bls381(size_t n, const uint8_t* __restrict__ scalars,
+// The launch covers pairs [i0, i0 + cnt) of the n of the call: the host-buffer MSM launches it once per chunk of its input copy.
+static __global__ void __launch_bounds__(256) k_glv_prepare_bls381(size_t n, size_t i0, size_t cnt, const uint8_t* __restrict__ scalars,
                                                                    const uint8_t* __restrict__ wire,
                                                                    Affine<Fp<Bls381Fp>>* __restrict__ pts,
                                                                    uint8_t* __restrict__ vscalars, uint32_t* flags) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+  if (i >= cnt) return;
+  i += i0;
   using F = Fp<Bls381Fp>;
   Scalar256 k;
   scalar_load_be(k, scalars + 32 * i);
@@ -281,7 +283,7 @@ __global__ void __launch_bounds__(128, 5) k_pt_forward_staged(uint32_t B, uint32
   msm_pairtree_forward_staged<CV, FIRST>(t, B, gridDim.x * blockDim.x, total, in, entries, offs_in, offs_out, pre, accs, pt_smem, threadIdx.x);
 }
 // backward pass with the operands of the next output staged global -> shared by cp.async (msm_affine.cuh); dynamic shared memory:
-// blockDim.x * 4 * sizeof(Affine)
+// blockDim.x * (4 * sizeof(Affine) + sizeof(F))
 template <class CV, bool FIRST>
 __global__ void __launch_bounds__(128, 4) k_pt_backward_staged(uint32_t B, uint32_t total, const Affine<typename CV::F>* __restrict__ in,
                                                                const uint32_t* __restrict__ entries, const uint32_t* __restrict__ offs_in,

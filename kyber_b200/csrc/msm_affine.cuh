@@ -217,7 +217,7 @@ B2K_D void msm_pairtree_backward(uint32_t t, uint32_t B, uint32_t T, uint32_t to
 // them through the sorted entries, a DRAM round trip), with the multiply pipe at 70 %.  Prefetching them into registers costs the
 // 48 registers the kernel does not have (128 = 4 blocks per SM), and `prefetch.global.L1` measured slower.  Here the operands of
 // output q-1 travel global -> shared memory with cp.async (LDGSTS, 16 bytes each, no register staging) while output q is computed:
-// per thread two 2-point buffers (4 x 96 B; 48 KB per block of 128 threads, four blocks per SM as before).  Round 0 also loads
+// per thread two 2-point buffers and one slot for the prefix product (4 x 96 + 48 B; 54 KB per block of 128 threads, four blocks per SM as before).  Round 0 also loads
 // the two sorted entries of output q-2, so that the gather addresses of q-1 are in registers when its copies are issued.
 namespace stage {
 #ifndef B2K_HOST_EMUL
@@ -265,8 +265,11 @@ B2K_D void msm_pairtree_backward_staged(uint32_t t, uint32_t B, uint32_t T, uint
   const uint32_t q0 = t * B;
   if (q0 >= nout) return;                                    // (no block-wide barrier below: every thread waits for its own copies only)
   const uint32_t q1 = (nout - q0 < B) ? nout : q0 + B;
-  A* slot = reinterpret_cast<A*>(smem) + 4 * lane;           // lane = thread of the block; [buffer][operand]
-  const stage::addr_t sbase = stage::addr(slot);
+  // per thread: [2 buffers][2 operand points] + [1 prefix product]  (PT_STAGE_BYTES<F> below)
+  unsigned char* mine = smem + (size_t)lane * (4 * sizeof(A) + sizeof(F));
+  A* slot = reinterpret_cast<A*>(mine);
+  F* pslot = reinterpret_cast<F*>(mine + 4 * sizeof(A));
+  const stage::addr_t sbase = stage::addr(slot), spre = stage::addr(pslot);
   uint32_t g = msm_find_bucket(offs_out, total, q1 - 1);
   uint32_t os = offs_out[g], is = offs_in[g], ie = offs_in[g + 1];
   // the bucket cursor only moves backwards; look(q) must be called with decreasing q
@@ -277,7 +280,7 @@ B2K_D void msm_pairtree_backward_staged(uint32_t t, uint32_t B, uint32_t T, uint
     if (FIRST) { L.v0 = entries[L.a]; L.v1 = (L.a + 1 < L.end) ? entries[L.a + 1] : L.v0; }
     return L;
   };
-  auto issue = [&](const PtLook& L, int buf) {
+  auto issue = [&](const PtLook& L, int buf, uint32_t q) {   // the two operands of output q into buffer `buf`, its prefix product into the one slot
     const stage::addr_t dst = sbase + (uint32_t)(2 * buf * sizeof(A));
     if (FIRST) {
       stage::copy<sizeof(A)>(dst, in + (L.v0 & 0x7fffffffu));
@@ -286,34 +289,35 @@ B2K_D void msm_pairtree_backward_staged(uint32_t t, uint32_t B, uint32_t T, uint
       stage::copy<sizeof(A)>(dst, in + L.a);
       if (L.a + 1 < L.end) stage::copy<sizeof(A)>(dst + (uint32_t)sizeof(A), in + L.a + 1);
     }
+    stage::copy<sizeof(F)>(spre, pre + (size_t)(q - q0) * T + t);
   };
   PtLook cur = look(q1 - 1), nxt = cur;
-  issue(cur, 0);
+  issue(cur, 0, q1 - 1);
   stage::commit();
   bool have_nxt = q1 - 1 > q0;
   if (have_nxt) nxt = look(q1 - 2);
   F inv = accs[t];
   int k = 0;
   for (uint32_t q = q1 - 1;; q--, k ^= 1) {
-    PtLook aft = nxt;
-    bool have_aft = false;
-    if (have_nxt) {
-      issue(nxt, k ^ 1);                                     // operands of output q-1 (round 0: its entries arrived during the last iteration)
-      if (q - 1 > q0) { aft = look(q - 2); have_aft = true; }
-    }
-    stage::commit();
-    stage::wait<1>();                                        // everything but the group just committed has landed: buffer k is complete
+    stage::wait<0>();                                        // the one group in flight: operands + prefix product of output q
     const bool pair = cur.a + 1 < cur.end;
     Affine<F> p1 = slot[2 * k], p2, r;
     if (pair) p2 = slot[2 * k + 1]; else p2 = p1;
+    F pj = *pslot;
     if (FIRST) {
       if (cur.v0 >> 31) f_neg(p1.y, p1.y);
       if (pair) { if (cur.v1 >> 31) f_neg(p2.y, p2.y); } else p2.y = p1.y;
     }
     F d, dinv, lam, tt;
     const int kind = pt_classify(d, p1, p2, pair);
-    F pj = pre[(size_t)(q - q0) * T + t];
-    f_mul_i(dinv, inv, pj);
+    f_mul_i(dinv, inv, pj);                                  // consumes pj: its shared-memory read is complete, the slot may be refilled
+    PtLook aft = nxt;
+    bool have_aft = false;
+    if (have_nxt) {
+      issue(nxt, k ^ 1, q - 1);                              // output q-1 (round 0: its entries were loaded during the previous iteration)
+      if (q - 1 > q0) { aft = look(q - 2); have_aft = true; }
+    }
+    stage::commit();
     if (q > q0) f_mul_i(inv, inv, d);
     if (kind == PT_DBL) { f_sqr(tt, p1.x); f_dbl(lam, tt); f_add(tt, lam, tt); }
     else f_sub(tt, p2.y, p1.y);

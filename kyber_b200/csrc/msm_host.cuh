@@ -303,8 +303,20 @@ int msm_enqueue(b2k_ctx* ctx, size_t n_in, const MsmPlan& pl, const uint8_t* d_s
   int nl = 0;
   CK(cudaEventRecord(ctx->ev[0], st));
   CK(cudaMemsetAsync(counts, 0, (total + 1) * 4, st));
+  if (ctx->h2d_chunks > 1 && !glv) CK(cudaStreamWaitEvent(st, ctx->gev[ctx->h2d_chunks], 0));   // (not reached: msm_host chunks GLV calls only)
   if constexpr (GlvTraits<CV>::enabled) {
-    if (glv) k_glv_prepare_bls381<<<(unsigned)((n_in + 255) / 256), 256, 0, st>>>(n_in, d_scalars_in, d_points, pts, vsc, ctx->d_flags);
+    if (glv && ctx->h2d_chunks > 1) {
+      // host-buffer call: the inputs arrive in chunks on the copy stream (msm_host); every chunk is prepared as soon as it has landed,
+      // so that only the last chunk's front-end work is left when the copy ends
+      const size_t per = (n_in + ctx->h2d_chunks - 1) / ctx->h2d_chunks;
+      for (int k = 0; k < ctx->h2d_chunks; k++) {
+        const size_t i0 = (size_t)k * per;
+        if (i0 >= n_in) break;
+        const size_t cnt = (n_in - i0 < per) ? n_in - i0 : per;
+        CK(cudaStreamWaitEvent(st, ctx->gev[1 + k], 0));
+        k_glv_prepare_bls381<<<(unsigned)((cnt + 255) / 256), 256, 0, st>>>(n_in, i0, cnt, d_scalars_in, d_points, pts, vsc, ctx->d_flags);
+      }
+    } else if (glv) k_glv_prepare_bls381<<<(unsigned)((n_in + 255) / 256), 256, 0, st>>>(n_in, 0, n_in, d_scalars_in, d_points, pts, vsc, ctx->d_flags);
     else k_load_points<CV><<<gb_n, 256, 0, st>>>(n, d_points, pts, ctx->d_flags);
   } else {
     k_load_points<CV><<<gb_n, 256, 0, st>>>(n, d_points, pts, ctx->d_flags);
@@ -384,9 +396,14 @@ int msm_enqueue(b2k_ctx* ctx, size_t n_in, const MsmPlan& pl, const uint8_t* d_s
             }
             if (ctx->acc_minb == 5) k_pt_invert<F, 5><<<grid, 128, 0, st>>>(ap.B[r], (uint32_t)total, offs_nxt, pt_accs);
             else k_pt_invert<F, 4><<<grid, 128, 0, st>>>(ap.B[r], (uint32_t)total, offs_nxt, pt_accs);
-            constexpr size_t stage_bytes = 128 * 4 * sizeof(Affine<F>);       // two 2-point buffers per thread (48 KB for G1)
-            const bool staged = stage_bytes <= 48 * 1024 && ((ctx->pt_stage >> (r == 0 ? 0 : 1)) & 1);
+            constexpr size_t stage_bytes = 128 * (4 * sizeof(Affine<F>) + sizeof(F));   // per thread two 2-point buffers + one prefix product (54 KB for G1)
+            const bool staged = stage_bytes <= 56 * 1024 && ((ctx->pt_stage >> (r == 0 ? 0 : 1)) & 1);
             if (staged) {
+              if (!ctx->pt_stage_opted) {                     // more than 48 KB of dynamic shared memory needs the opt-in (per device: kept per context)
+                CK(cudaFuncSetAttribute(k_pt_backward_staged<CV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage_bytes));
+                CK(cudaFuncSetAttribute(k_pt_backward_staged<CV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage_bytes));
+                ctx->pt_stage_opted = true;
+              }
               if (r == 0) k_pt_backward_staged<CV, true><<<grid, 128, stage_bytes, st>>>(ap.B[r], (uint32_t)total, in_cur, entries, offs_cur, offs_nxt, pt_pre, pt_accs, out);
               else k_pt_backward_staged<CV, false><<<grid, 128, stage_bytes, st>>>(ap.B[r], (uint32_t)total, in_cur, nullptr, offs_cur, offs_nxt, pt_pre, pt_accs, out);
             } else {
@@ -603,6 +620,12 @@ int msm_finish_dev(b2k_ctx* ctx, int c, int W, const void* d_wsum, void* d_out, 
   return B2K_OK;
 }
 
+// the context's copy stream (created on first use; nullptr if that fails: the caller copies on the main stream instead)
+inline cudaStream_t copy_stream(b2k_ctx* ctx) {
+  if (!ctx->copy_stream && cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); ctx->copy_stream = nullptr; }
+  return ctx->copy_stream;
+}
+
 // Host-buffer MSM.  wait = false: everything (H2D copies, pipeline, D2H of the result and of the status word) is only
 // ENQUEUED on the context's stream; the caller collects the status with msm_wait() (b2k_wait).  With page-locked host
 // buffers the copies of one context overlap the kernels of another: two contexts alternate to keep PCIe and the SMs busy.
@@ -622,9 +645,31 @@ int msm_host(b2k_ctx* ctx, size_t n, const uint8_t* scalars, const uint8_t* poin
   auto* d_p = arena_take<uint8_t>(ctx, n * (size_t)CV::IN_BYTES);
   auto* d_o = arena_take<uint8_t>(ctx, 256);
   CK(cudaMemsetAsync(ctx->d_flags, 0, 4, ctx->stream));
-  CK(cudaMemcpyAsync(d_s, scalars, n * 32, cudaMemcpyHostToDevice, ctx->stream));
-  CK(cudaMemcpyAsync(d_p, points, n * (size_t)CV::IN_BYTES, cudaMemcpyHostToDevice, ctx->stream));
+  // Large G1 batches: the H2D copy goes in 8 chunks on its own stream and the front end (k_glv_prepare: range and curve checks, the
+  // endomorphism split, 8 field products per pair) runs chunk by chunk under it -- a blocking call no longer holds every kernel back until the
+  // last byte has arrived.  gev[0] orders the copies behind whatever still reads the arena, gev[1..8] hand the chunks over.
+  const bool chunked = msm_uses_glv<CV>(ctx, n) && ctx->msm_groups <= 1 && n >= (size_t(1) << 18) && copy_stream(ctx);
+  if (chunked) {
+    constexpr int K = 8;
+    const size_t per = (n + K - 1) / K;
+    CK(cudaEventRecord(ctx->gev[0], ctx->stream));
+    CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->gev[0], 0));
+    for (int k = 0; k < K; k++) {
+      const size_t i0 = (size_t)k * per;
+      const size_t cnt = i0 >= n ? 0 : ((n - i0 < per) ? n - i0 : per);
+      if (cnt) {
+        CK(cudaMemcpyAsync(d_s + 32 * i0, scalars + 32 * i0, cnt * 32, cudaMemcpyHostToDevice, ctx->copy_stream));
+        CK(cudaMemcpyAsync(d_p + (size_t)CV::IN_BYTES * i0, points + (size_t)CV::IN_BYTES * i0, cnt * (size_t)CV::IN_BYTES, cudaMemcpyHostToDevice, ctx->copy_stream));
+      }
+      CK(cudaEventRecord(ctx->gev[1 + k], ctx->copy_stream));
+    }
+    ctx->h2d_chunks = K;
+  } else {
+    CK(cudaMemcpyAsync(d_s, scalars, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_p, points, n * (size_t)CV::IN_BYTES, cudaMemcpyHostToDevice, ctx->stream));
+  }
   rc = msm_enqueue<CV>(ctx, n, pl, d_s, d_p, d_o, affine_out);
+  ctx->h2d_chunks = 0;
   if (rc) return rc;
   CK(cudaMemcpyAsync(out, d_o, affine_out ? CV::IN_BYTES : CV::OUT_BYTES, cudaMemcpyDeviceToHost, ctx->stream));
   if (!wait) { CK(cudaMemcpyAsync(ctx->h_flags, ctx->d_flags, 4, cudaMemcpyDeviceToHost, ctx->stream)); return B2K_OK; }   // b2k_wait fetches + clears

@@ -155,7 +155,7 @@ static int emul_msm_buckets(size_t n, const uint8_t* scalars, const uint8_t* pts
         for (uint32_t t = 0; t < T; t++) msm_pairtree_invert<F>(t, (uint32_t)PB, (uint32_t)total, no.data(), accs.data());
         for (uint32_t t = 0; t < T; t++) {
           if (g_pt_stage) {                            // operands staged by (emulated, deferred) cp.async: k_pt_backward_staged
-            alignas(16) unsigned char slots[4 * sizeof(Affine<F>)];
+            alignas(16) unsigned char slots[4 * sizeof(Affine<F>) + sizeof(F)];
             memset(slots, 0xEE, sizeof slots);
             if (r == 0) msm_pairtree_backward_staged<CV, true>(t, (uint32_t)PB, T, (uint32_t)total, P.data(), entries.data(), offs.data(), no.data(), pre.data(), accs.data(), nxt.data(), slots, 0);
             else msm_pairtree_backward_staged<CV, false>(t, (uint32_t)PB, T, (uint32_t)total, cur.data(), nullptr, offs.data(), no.data(), pre.data(), accs.data(), nxt.data(), slots, 0);
