@@ -189,9 +189,23 @@ def gpu_pairing_run(eng, torch, dev, n: int, steps: int):
     ms = e0.elapsed_time(e1) / steps
     res = ok.cpu()
     assert int(res.sum()) == n - 1 and int(res[7]) == 0, "pairing check results wrong"
+    # small batches (the one-at-a-time interface methods): the warp-cooperative kernel, one warp per check
+    small = {}
+    for m in (1, 1024):
+        ok.zero_()
+        def small_step():
+            eng._check(eng.lib.b2k_bls12381_pairing_check_dev(eng.h, m, a1.data_ptr(), a2.data_ptr(), b1.data_ptr(), b2.data_ptr(), ok.data_ptr()))
+        small_step(); torch.cuda.synchronize()
+        e0.record()
+        for _ in range(3):
+            small_step()
+        e1.record(); torch.cuda.synchronize()
+        assert int(ok[:m].sum()) == m - (1 if m > 7 else 0), "small-batch pairing check results wrong"
+        small[f"n{m}_ms"] = e0.elapsed_time(e1) / 3
     return {"value": 2 * n / (ms * 1e-3), "unit": "pairings/s", "ms_per_step": ms,
             "workload": f"{n} independent ValidatePairing checks (2-pair Miller loop + final exponentiation each)",
-            "checks_per_sec": n / (ms * 1e-3)}
+            "checks_per_sec": n / (ms * 1e-3), "small_batch_latency": small,
+            "small_batch_note": "device time of ONE call with 1 / 1024 checks (batches <= 8192 run one check per warp, coop_pairing.cuh)"}
 
 
 def gpu_mul_batch_run(eng, torch, dev, d_scal, d_pts, n: int, steps: int, scalars, a):

@@ -50,6 +50,11 @@ def _closure(src: str) -> list:
 def build(force: bool = False, verbose: bool = False) -> str:
     """Compile kyber_b200/libb2kyber.so.  Incremental per translation unit: a unit is recompiled when its own source or a
     header it includes (transitively) changed (stamp next to the object), the library is relinked when an object changed.  Returns the library path."""
+    # the program tables of the warp-cooperative pairing are generated (1 s, pure Python, the curve's public parameters only): tools/gen_coop_pairing.py
+    gen = os.path.join(HERE, "..", "tools", "gen_coop_pairing.py")
+    inc = os.path.join(CSRC, "coop_program.inc")
+    if not os.path.exists(inc) or os.path.getmtime(inc) < os.path.getmtime(gen):
+        subprocess.run([sys.executable, gen], check=True, stdout=subprocess.DEVNULL)
     objs, procs = [], []
     for u in UNITS:
         src = os.path.join(CSRC, u)

@@ -41,6 +41,7 @@ def load_library() -> C.CDLL:
         "b2k_set_msm_variant": (C.c_int, [vp, C.c_int]),
         "b2k_set_msm_glv": (C.c_int, [vp, C.c_int]),
         "b2k_set_pairing_variant": (C.c_int, [vp, C.c_int]),
+        "b2k_set_pairing_coop": (C.c_int, [vp, C.c_int]),
         "b2k_set_msm_groups": (C.c_int, [vp, C.c_int]),
         "b2k_set_msm_occupancy": (C.c_int, [vp, C.c_int]),
         "b2k_set_msm_chunk": (C.c_int, [vp, C.c_int]),

@@ -5,6 +5,7 @@
 #include "../../include/b2kyber.h"
 #include "b2k_ctx.h"
 #include "pairing_kernels.cuh"
+#include "coop_pairing.cuh"
 #include "msm_host.cuh"
 
 using namespace b2k;
@@ -28,6 +29,10 @@ static BFp12* pair_scratch(const b2k_ctx* cctx, size_t n) {
 }
 
 void b2k_internal_launch_pair(const b2k_ctx* ctx, size_t n, const uint8_t* g1, const uint8_t* g2, uint8_t* gt) {
+  if (ctx->coop_max_n > 0 && n <= (size_t)ctx->coop_max_n) {       // small batch: one WARP per pairing (coop_pairing.cuh)
+    coop::k_coop_pair<<<(unsigned)n, 32, coop::SMEM_BYTES, ctx->stream>>>(n, g1, g2, gt, ctx->d_flags);
+    return;
+  }
   int v = ctx->pair_variant;
   if (v >= 16) {
     if (BFp12* f = pair_scratch(ctx, n)) { launch_pair_split(ctx, v - 16, n, g1, g2, gt, f); return; }
@@ -39,6 +44,10 @@ void b2k_internal_launch_pair(const b2k_ctx* ctx, size_t n, const uint8_t* g1, c
 }
 void b2k_internal_launch_pairing_check(const b2k_ctx* ctx, size_t n, const uint8_t* a1, const uint8_t* a2, const uint8_t* b1,
                                        const uint8_t* b2, uint8_t* ok, int b2_broadcast, const uint8_t* pre_ok) {
+  if (ctx->coop_max_n > 0 && n <= (size_t)ctx->coop_max_n) {
+    coop::k_coop_pairing_check<<<(unsigned)n, 32, coop::SMEM_BYTES, ctx->stream>>>(n, a1, a2, b1, b2, ok, b2_broadcast, pre_ok, ctx->d_flags);
+    return;
+  }
   int v = ctx->pair_variant;
   if (v >= 16) {
     if (BFp12* f = pair_scratch(ctx, n)) { launch_pairing_check_split(ctx, v - 16, n, a1, a2, b1, b2, ok, b2_broadcast, pre_ok, f); return; }
@@ -54,7 +63,7 @@ int b2k_bls12381_pair_dev(b2k_ctx* ctx, size_t n, const void* d_g1, const void* 
   CK(cudaSetDevice(ctx->device));
   b2k_internal_launch_pair(ctx, n, (const uint8_t*)d_g1, (const uint8_t*)d_g2, (uint8_t*)d_gt);
   CK(cudaGetLastError());
-  ctx->launches += (ctx->pair_variant >= 16) ? 2 : 1;
+  ctx->launches += (ctx->pair_variant >= 16 && !(ctx->coop_max_n > 0 && n <= (size_t)ctx->coop_max_n)) ? 2 : 1;
   return B2K_OK;
 }
 
@@ -81,7 +90,7 @@ int b2k_bls12381_pairing_check_dev(b2k_ctx* ctx, size_t n, const void* a1, const
   CK(cudaSetDevice(ctx->device));
   b2k_internal_launch_pairing_check(ctx, n, (const uint8_t*)a1, (const uint8_t*)a2, (const uint8_t*)b1, (const uint8_t*)b2, (uint8_t*)d_ok, 0, nullptr);
   CK(cudaGetLastError());
-  ctx->launches += (ctx->pair_variant >= 16) ? 2 : 1;
+  ctx->launches += (ctx->pair_variant >= 16 && !(ctx->coop_max_n > 0 && n <= (size_t)ctx->coop_max_n)) ? 2 : 1;
   return B2K_OK;
 }
 
@@ -108,6 +117,12 @@ int b2k_bls12381_pairing_check(b2k_ctx* ctx, size_t n, const uint8_t* a1, const 
     int rc2 = b2k_host::status_finish(ctx);  // ValidatePairing, the call itself reports per-element booleans, not an error
     return rc2 == B2K_ERR_POINT ? B2K_OK : rc2;
   }
+}
+
+int b2k_set_pairing_coop(b2k_ctx* ctx, int max_n) {
+  if (!ctx || max_n < 0) return B2K_ERR_ARG;
+  ctx->coop_max_n = max_n;
+  return B2K_OK;
 }
 
 int b2k_set_pairing_variant(b2k_ctx* ctx, int v) {

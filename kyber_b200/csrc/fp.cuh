@@ -354,6 +354,27 @@ B2K_D bool fp_eq(const Fp<C>& a, const Fp<C>& b) {
   return o == 0;
 }
 
+// r = a + b or a - b mod p in ONE instruction stream (callers whose lanes mix additions and subtractions: coop_pairing.cuh):
+//   s = a + (b ^ m) + (m & 1), m = 0 / ~0 (a - b as a + ~b + 1; its carry-out is "no borrow");
+//   t = s - p for an addition, s + p for a subtraction; r = t where the addition reached p / the subtraction borrowed, else s.
+template <class C>
+B2K_D void fp_addsub(Fp<C>& r, const Fp<C>& a, const Fp<C>& b, bool minus) {
+  constexpr int N = C::N;
+  const uint32_t m = minus ? 0xffffffffu : 0u, nm = ~m;
+  uint32_t s[N], t[N];
+  ptx::add_cc(m, m & 1u);                                    // carry-in = 1 for the two's complement (~0 + 1 carries, 0 + 0 does not)
+#pragma unroll
+  for (int j = 0; j < N; j++) s[j] = ptx::addc_cc(a.v[j], b.v[j] ^ m);
+  const uint32_t carry = ptx::addc(0, 0);                    // subtraction: 1 = no borrow; addition: the sum's bit 32 N
+  ptx::add_cc(nm, nm & 1u);
+#pragma unroll
+  for (int j = 0; j < N; j++) t[j] = ptx::addc_cc(s[j], C::mod(j) ^ nm);
+  const uint32_t c2 = ptx::addc(0, 0);                       // addition: 1 = s - p did not borrow
+  const bool take = minus ? (carry == 0) : ((carry | c2) != 0);
+#pragma unroll
+  for (int j = 0; j < N; j++) r.v[j] = take ? t[j] : s[j];
+}
+
 template <class C>
 B2K_D void fp_neg(Fp<C>& r, const Fp<C>& a) {
   constexpr int N = C::N;

@@ -14,6 +14,9 @@ extern "C" {
   void emul_##name##_sub(const uint32_t* a, const uint32_t* b, uint32_t* r) {                      \
     Fp<C> x, y, z; for (int i = 0; i < C::N; i++) { x.v[i] = a[i]; y.v[i] = b[i]; }                \
     fp_sub(z, x, y); for (int i = 0; i < C::N; i++) r[i] = z.v[i]; }                               \
+  void emul_##name##_addsub(const uint32_t* a, const uint32_t* b, int minus, uint32_t* r) {        \
+    Fp<C> x, y, z; for (int i = 0; i < C::N; i++) { x.v[i] = a[i]; y.v[i] = b[i]; }                \
+    fp_addsub(z, x, y, minus != 0); for (int i = 0; i < C::N; i++) r[i] = z.v[i]; }                \
   void emul_##name##_sqr(const uint32_t* a, uint32_t* r) {                                         \
     Fp<C> x, z; for (int i = 0; i < C::N; i++) x.v[i] = a[i];                                      \
     fp_sqr(z, x); for (int i = 0; i < C::N; i++) r[i] = z.v[i]; }                                  \

@@ -95,6 +95,10 @@ def test_device_field_code_under_host_emulation(emul):
             assert val(out) == (a + b) % p
             getattr(emul, f"emul_{name}_sub")(lim(a), lim(b), out)
             assert val(out) == (a - b) % p
+            getattr(emul, f"emul_{name}_addsub")(lim(a), lim(b), 0, out)              # add / subtract as one instruction stream
+            assert val(out) == (a + b) % p
+            getattr(emul, f"emul_{name}_addsub")(lim(a), lim(b), 1, out)
+            assert val(out) == (a - b) % p
         for _ in range(200):                                                        # wide products are exact for ANY N-limb operands
             a, b = rng.choice((R - 1, rng.randrange(R), 2 * p - 2 if 2 * p - 2 < R else p - 1)), rng.randrange(R)
             wide = (ctypes.c_uint32 * (2 * n))()
