@@ -205,7 +205,7 @@ def gpu_pairing_run(eng, torch, dev, n: int, steps: int):
     return {"value": 2 * n / (ms * 1e-3), "unit": "pairings/s", "ms_per_step": ms,
             "workload": f"{n} independent ValidatePairing checks (2-pair Miller loop + final exponentiation each)",
             "checks_per_sec": n / (ms * 1e-3), "small_batch_latency": small,
-            "small_batch_note": "device time of ONE call with 1 / 1024 checks (batches <= 8192 run one check per warp, coop_pairing.cuh)"}
+            "small_batch_note": "device time of ONE call with 1 / 1024 checks (batches <= 10240 run one check per warp, coop_pairing.cuh)"}
 
 
 def gpu_mul_batch_run(eng, torch, dev, d_scal, d_pts, n: int, steps: int, scalars, a):

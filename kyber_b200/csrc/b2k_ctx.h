@@ -44,7 +44,7 @@ struct b2k_ctx {
   int reduce_levels = 0;            // bucket reduction: 0 = automatic (two levels for >= 4096 buckets per window), 1, 2
   int reduce_m1 = 0, reduce_m2 = 0; // chunk sizes of the two levels (0 = 8 and 4), tuning aid
   int pair_variant = 0; // launch-bound variant / code layout of the pairing kernels (tuning aid); >= 16: Miller and final exponentiation as two kernels
-  int coop_max_n = 8192;            // batches of at most this many BLS12-381 pairings / checks run one per WARP (coop_pairing.cuh; the measured
+  int coop_max_n = 10240;           // batches of at most this many BLS12-381 pairings / checks run one per WARP (coop_pairing.cuh; the measured
                                     // break-even with the one-per-thread kernels, profiles/r02t_coop.txt); 0 = never
   void* pair_scratch = nullptr;     // Miller values between the two kernels of the split pairing (576 B per element; grown on demand)
   size_t pair_scratch_cap = 0;

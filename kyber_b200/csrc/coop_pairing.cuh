@@ -34,36 +34,46 @@ B2K_D void slot_store(uint32_t* S, uint32_t s, const BFp& a) {
 }
 
 // one round: decode the lane's word, load operands, compute, store, __syncwarp().  Operations: 1 MUL, 3 ADD, 4 SUB, 7 MULC, 8 INV
-// (the generator encodes a^2, 2 a, -a as a * a, a + a, ZERO - a).  A round holds products only or additions / subtractions only.
+// (the generator encodes a^2, 2 a, -a as a * a, a + a, ZERO - a).  A round holds products only or additions / subtractions only, and
+// the two kinds take SEPARATE, warp-uniform code paths: the product path calls out-of-line functions, and sharing variables with it made
+// the compiler park the operands of every addition round on the stack.
 B2K_D void step(uint32_t* S, uint32_t w) {
   const uint32_t op = w >> 28, d = (w >> 18) & 511u, a = (w >> 9) & 511u, b = w & 511u;
-  if (op != 0) {
+  const bool additive = (op == 3 || op == 4);
+  if (__any_sync(0xffffffffu, additive)) {                   // an addition / subtraction round
+    if (additive) {
+      BFp x, y, z;
+      slot_load(x, S, a);
+      slot_load(y, S, b);
+      fp_addsub(z, x, y, op == 4);                           // one instruction stream for both (fp.cuh)
+      slot_store(S, d, z);
+    }
+  } else if (op != 0) {                                      // a product round (or the lone inversion)
     BFp x, y, z;
     slot_load(x, S, a);
-    if (op == 7) {
+    if (op == 8) {
+      fp_inv_bingcd(z, x);
+    } else {
+      if (op == 7) {
 #pragma unroll
-      for (int j = 0; j < 12; j++) y.v[j] = CONSTS[b][j];
-    } else slot_load(y, S, b);
-    if (op == 3 || op == 4) fp_addsub(z, x, y, op == 4);     // one instruction stream for both (fp.cuh)
-    else if (op == 8) {                                      // alone in its round; own copies: the out-of-line inversion takes addresses,
-      BFp xi = x, zi;                                        // which would push x and z of EVERY path into local memory
-      fp_inv_bingcd(zi, xi);
-      z = zi;
-    } else fp_mul(z, x, y);
+        for (int j = 0; j < 12; j++) y.v[j] = CONSTS[b][j];
+      } else slot_load(y, S, b);
+      fp_mul(z, x, y);
+    }
     slot_store(S, d, z);
   }
   __syncwarp();
 }
 
-// the interpreter proper: every lane of the warp calls it with the same program; the next round's word travels while this one runs
-// (fetching a group of 8 rounds ahead instead was measured slower: 3.68 against 3.56 ms per check, the unrolled body costs more than
-// the L2 latency it hides)
+// the interpreter proper: every lane of the warp calls it with the same program; the words of the next two rounds travel while this one
+// runs (an addition round is shorter than an L2 round trip; fetching a group of 8 rounds ahead was measured slower: the unrolled body costs
+// more than the latency it hides)
 B2K_D void run(uint32_t* S, const uint32_t* __restrict__ prog, int rounds, int lane) {
-  uint32_t w = prog[lane];
+  uint32_t w = prog[lane], w1 = rounds > 1 ? prog[32 + lane] : 0u;
   for (int r = 0; r < rounds; r++) {
-    const uint32_t wn = (r + 1 < rounds) ? prog[(size_t)(r + 1) * 32 + lane] : 0u;
+    const uint32_t w2 = (r + 2 < rounds) ? prog[(size_t)(r + 2) * 32 + lane] : 0u;
     step(S, w);
-    w = wn;
+    w = w1; w1 = w2;
   }
 }
 

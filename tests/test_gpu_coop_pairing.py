@@ -44,7 +44,7 @@ def test_coop_pair_and_check_match_the_oracle_and_the_batch_kernels(engine):
         got = list(engine.bls12381_pairing_check(bytes(bad), A2, B1, B2))
         assert got[3] == 0 and got[:3] == want[:3] and got[4:] == want[4:]
     finally:
-        engine._check(engine.lib.b2k_set_pairing_coop(engine.h, 8192))
+        engine._check(engine.lib.b2k_set_pairing_coop(engine.h, 10240))
 
 
 def test_bls_verify_goes_through_the_cooperative_kernel_for_small_batches(engine):
@@ -58,8 +58,8 @@ def test_bls_verify_goes_through_the_cooperative_kernel_for_small_batches(engine
         sigs = [o.g1_compress(o.g1_mul(sk, h.hash_to_g1(m, h.DST_G1))) for sk, m in zip(sks, msgs)]
         if n > 1:
             sigs[2] = o.g1_compress(o.g1_mul(sks[2] + 1, h.hash_to_g1(msgs[2], h.DST_G1)))      # a wrong signature
-        for coop in (8192, 0):
+        for coop in (10240, 0):
             engine._check(engine.lib.b2k_set_pairing_coop(engine.h, coop))
             ok = engine.bls12381_verify_g1sig(pks, msgs, h.DST_G1, b"".join(sigs))
             assert list(ok) == [0 if (n > 1 and i == 2) else 1 for i in range(n)], (n, coop)
-    engine._check(engine.lib.b2k_set_pairing_coop(engine.h, 8192))
+    engine._check(engine.lib.b2k_set_pairing_coop(engine.h, 10240))

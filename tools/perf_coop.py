@@ -42,4 +42,4 @@ for n in (1, 2, 8, 32, 148, 512, 1024, 2048, 4096, 8192, 16384, 65536):
     (c_ms, c_p), (t_ms, t_p) = row
     print(f"n={n:6d}  check: cooperative {c_ms:9.3f} ms ({2 * n / c_ms * 1e3:.3e} pairings/s) | per-thread {t_ms:9.3f} ms ({2 * n / t_ms * 1e3:.3e})"
           f"   pair: cooperative {c_p:9.3f} ms | per-thread {t_p:9.3f} ms", flush=True)
-eng._check(eng.lib.b2k_set_pairing_coop(eng.h, 8192))
+eng._check(eng.lib.b2k_set_pairing_coop(eng.h, 10240))
