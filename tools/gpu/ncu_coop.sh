@@ -1,3 +1,4 @@
+# Run under gpurun: ncu --set full of the cooperative pairing check, one warp per SM (profiles/r02u_coop_ncu_details.txt)
 cat > /tmp/coop_probe.py <<'PY'
 import sys
 sys.path.insert(0, '.')
