@@ -112,7 +112,7 @@ B2K_D void gather12(BFp12& e, const uint32_t* S, const uint16_t* out) {     // f
 }
 
 // gt[i] = e(g1[i], g2[i])
-static __global__ void __launch_bounds__(32) k_coop_pair(size_t n, const uint8_t* __restrict__ g1, const uint8_t* __restrict__ g2,
+static __global__ void __launch_bounds__(32, 16) k_coop_pair(size_t n, const uint8_t* __restrict__ g1, const uint8_t* __restrict__ g2,
                                                          uint8_t* __restrict__ gt, uint32_t* flags) {
   extern __shared__ __align__(16) uint32_t coop_sm[];
   const int lane = threadIdx.x;
@@ -134,7 +134,7 @@ static __global__ void __launch_bounds__(32) k_coop_pair(size_t n, const uint8_t
 }
 
 // ok[i] = ( e(a1[i], a2[i]) == e(b1[i], b2[i]) ); same arguments as k_bls_pairing_check
-static __global__ void __launch_bounds__(32) k_coop_pairing_check(size_t n, const uint8_t* __restrict__ a1, const uint8_t* __restrict__ a2,
+static __global__ void __launch_bounds__(32, 16) k_coop_pairing_check(size_t n, const uint8_t* __restrict__ a1, const uint8_t* __restrict__ a2,
                                                                   const uint8_t* __restrict__ b1, const uint8_t* __restrict__ b2,
                                                                   uint8_t* __restrict__ ok, int b2_broadcast,
                                                                   const uint8_t* __restrict__ pre_ok, uint32_t* flags) {

@@ -29,6 +29,7 @@ OUT = os.path.join(ROOT, "kyber_b200", "csrc", "coop_program.inc")
 NOP, MUL, SQR, ADD, SUB, NEG, DBL, MULC, INV = range(9)
 LONG = {MUL, SQR, MULC, INV}
 COST = {MUL: 400, SQR: 400, MULC: 400, INV: 40000, ADD: 60, SUB: 60, NEG: 40, DBL: 60}
+SLACK = 4000                                # scheduling window below the critical path, in COST units (compile_program)
 
 
 class _Zero:
@@ -400,15 +401,21 @@ def compile_program(npairs):
     ready_short = [i for i, t in enumerate(tasks) if ndeps[i] == 0 and t[0] not in LONG]
     rounds, done = [], 0
     while done < len(tasks):
-        # short operations first: they feed the products and free slots early (products first was tried: as many rounds, 2.5 x the slots)
-        pool = ready_short if ready_short else ready_long
+        # Only operations within SLACK of the longest remaining path are eligible: work that is ready early but needed late (the side
+        # branches of the final exponentiation) would otherwise sit in slots for thousands of rounds (482 slots without the rule, 288 with
+        # it, same number of rounds; the slot count decides how many warps share an SM).  Among the eligible ones short operations go
+        # first: they feed the products and free slots early (products first was tried: as many rounds, 2.5 x the slots).
+        pmax = max(prio[i] for i in ready_short + ready_long)
+        elig_s = [i for i in ready_short if prio[i] >= pmax - SLACK]
+        elig_l = [i for i in ready_long if prio[i] >= pmax - SLACK]
+        pool_src, pool = (ready_short, elig_s) if elig_s else (ready_long, elig_l)
         pool.sort(key=lambda i: -prio[i])
-        if pool is ready_long and tasks[pool[0]][0] == INV:          # an inversion runs alone (every other lane would idle anyway)
+        if pool_src is ready_long and tasks[pool[0]][0] == INV:      # an inversion runs alone (every other lane would idle anyway)
             take = [pool[0]]
         else:
             take = [i for i in pool if tasks[i][0] != INV][:32]
         for i in take:
-            pool.remove(i)
+            pool_src.remove(i)
         rounds.append(take)
         done += len(take)
         for i in take:
