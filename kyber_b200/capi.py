@@ -213,6 +213,10 @@ class Engine:
         """affine pair-tree rounds of the BLS12-381 G1 MSM: -1 automatic, 0 off, 1..8 forced; batch = additions per thread"""
         self._check(self.lib.b2k_set_msm_affine(self.h, int(rounds), int(batch)))
 
+    def set_pairing_coop(self, max_n: int):
+        """batches of at most max_n BLS12-381 pairings / checks run one per warp (coop_pairing.cuh); 0 = never"""
+        self._check(self.lib.b2k_set_pairing_coop(self.h, int(max_n)))
+
     def set_msm_affine_split(self, split: bool):
         """affine rounds as three kernels each (True, default) or one fused kernel (False)"""
         self._check(self.lib.b2k_set_msm_affine_split(self.h, int(split)))
