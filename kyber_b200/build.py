@@ -52,8 +52,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     header it includes (transitively) changed (stamp next to the object), the library is relinked when an object changed.  Returns the library path."""
     # the program tables of the warp-cooperative pairing are generated (1 s, pure Python, the curve's public parameters only): tools/gen_coop_pairing.py
     gen = os.path.join(HERE, "..", "tools", "gen_coop_pairing.py")
-    inc = os.path.join(CSRC, "coop_program.inc")
-    if not os.path.exists(inc) or os.path.getmtime(inc) < os.path.getmtime(gen):
+    incs = [os.path.join(CSRC, f"coop_program_{c}.inc") for c in ("bls", "bn254", "bn256")]
+    if any(not os.path.exists(i) or os.path.getmtime(i) < os.path.getmtime(gen) for i in incs):
         subprocess.run([sys.executable, gen], check=True, stdout=subprocess.DEVNULL)
     objs, procs = [], []
     for u in UNITS:

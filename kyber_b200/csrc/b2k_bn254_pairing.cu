@@ -1,6 +1,8 @@
 // b2k_bn254_pairing.cu -- C ABI entry points for bn254: batched pairings and G2 Point.Mul / MSM.
 #include "msm_host.cuh"
 #include "bn_pairing.cuh"
+#define B2K_COOP_BN254 1
+#include "coop_pairing.cuh"          // small batches: one warp per pairing
 using namespace b2k_host;
 
 namespace b2k {
@@ -42,6 +44,7 @@ __global__ void __launch_bounds__(64, 4) k_bn254_pairing_check(size_t n, const u
   ok[i] = fp12_is_one(e) ? 1 : 0;
 }
 
+using Coop254 = coop::Curve<Bn254G1, Bn254G2, Bn254Fp, NFp12, coop::BN254_P1, coop::BN254_P2>;
 }  // namespace b2k
 
 extern "C" {
@@ -58,7 +61,10 @@ int b2k_bn254_pair(b2k_ctx* ctx, size_t n, const uint8_t* g1, const uint8_t* g2,
   CK(cudaMemsetAsync(ctx->d_flags, 0, 4, st));
   CK(cudaMemcpyAsync(d1, g1, n * 64, cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(d2, g2, n * 128, cudaMemcpyHostToDevice, st));
-  k_bn254_pair<<<(unsigned)((n + 63) / 64), 64, 0, st>>>(n, d1, d2, dg, ctx->d_flags);
+  if (ctx->coop_max_n > 0 && n <= (size_t)(ctx->coop_max_n < 8192 ? ctx->coop_max_n : 8192))   // break-even measured near 8 192 on this curve
+    coop::k_coop_bn_pair<Coop254, Bn254Pair><<<(unsigned)n, 32, Coop254::L::BYTES, st>>>(n, d1, d2, dg, ctx->d_flags);
+  else
+    k_bn254_pair<<<(unsigned)((n + 63) / 64), 64, 0, st>>>(n, d1, d2, dg, ctx->d_flags);
   CK(cudaGetLastError());
   ctx->launches += 1;
   CK(cudaMemcpyAsync(gt, dg, n * 384, cudaMemcpyDeviceToHost, st));
@@ -82,7 +88,10 @@ int b2k_bn254_pairing_check(b2k_ctx* ctx, size_t n, const uint8_t* a1, const uin
   CK(cudaMemcpyAsync(da2, a2, n * 128, cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(db1, b1, n * 64, cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(db2, b2, n * 128, cudaMemcpyHostToDevice, st));
-  k_bn254_pairing_check<<<(unsigned)((n + 63) / 64), 64, 0, st>>>(n, da1, da2, db1, db2, dok, ctx->d_flags);
+  if (ctx->coop_max_n > 0 && n <= (size_t)(ctx->coop_max_n < 8192 ? ctx->coop_max_n : 8192))   // break-even measured near 8 192 on this curve
+    coop::k_coop_bn_pairing_check<Coop254><<<(unsigned)n, 32, Coop254::L::BYTES, st>>>(n, da1, da2, db1, db2, dok, ctx->d_flags);
+  else
+    k_bn254_pairing_check<<<(unsigned)((n + 63) / 64), 64, 0, st>>>(n, da1, da2, db1, db2, dok, ctx->d_flags);
   CK(cudaGetLastError());
   ctx->launches += 1;
   CK(cudaMemcpyAsync(ok, dok, n, cudaMemcpyDeviceToHost, st));

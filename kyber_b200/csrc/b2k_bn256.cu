@@ -2,10 +2,13 @@
 #include "msm_host.cuh"
 #include "bn256.cuh"
 #include "bn_pairing.cuh"
+#define B2K_COOP_BN256 1
+#include "coop_pairing.cuh"          // small batches: one warp per pairing
 using namespace b2k_host;
 
 namespace b2k {
 using PC6 = Bn256Pair;
+using Coop256 = coop::Curve<Bn256G1, Bn256G2, Bn256Fp, PFp12<Bn256Pair>, coop::BN256_P1, coop::BN256_P2>;
 
 // pairing/bn256/suite.go:99-105 Pair -> optimalAte (optate.go:266-274): identity when an operand is infinity
 __global__ void __launch_bounds__(64, 4) k_bn256_pair(size_t n, const uint8_t* __restrict__ g1, const uint8_t* __restrict__ g2,
@@ -63,7 +66,10 @@ int b2k_bn256_pair(b2k_ctx* ctx, size_t n, const uint8_t* g1, const uint8_t* g2,
   CK(cudaMemsetAsync(ctx->d_flags, 0, 4, st));
   CK(cudaMemcpyAsync(d1, g1, n * 64, cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(d2, g2, n * 128, cudaMemcpyHostToDevice, st));
-  k_bn256_pair<<<(unsigned)((n + 63) / 64), 64, 0, st>>>(n, d1, d2, dg, ctx->d_flags);
+  if (ctx->coop_max_n > 0 && n <= (size_t)(ctx->coop_max_n < 8192 ? ctx->coop_max_n : 8192))   // break-even measured near 8 192 on this curve
+    coop::k_coop_bn_pair<Coop256, PC6><<<(unsigned)n, 32, Coop256::L::BYTES, st>>>(n, d1, d2, dg, ctx->d_flags);
+  else
+    k_bn256_pair<<<(unsigned)((n + 63) / 64), 64, 0, st>>>(n, d1, d2, dg, ctx->d_flags);
   CK(cudaGetLastError());
   ctx->launches += 1;
   CK(cudaMemcpyAsync(gt, dg, n * 384, cudaMemcpyDeviceToHost, st));
@@ -87,7 +93,10 @@ int b2k_bn256_pairing_check(b2k_ctx* ctx, size_t n, const uint8_t* a1, const uin
   CK(cudaMemcpyAsync(da2, a2, n * 128, cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(db1, b1, n * 64, cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(db2, b2, n * 128, cudaMemcpyHostToDevice, st));
-  k_bn256_pairing_check<<<(unsigned)((n + 63) / 64), 64, 0, st>>>(n, da1, da2, db1, db2, dok, ctx->d_flags);
+  if (ctx->coop_max_n > 0 && n <= (size_t)(ctx->coop_max_n < 8192 ? ctx->coop_max_n : 8192))   // break-even measured near 8 192 on this curve
+    coop::k_coop_bn_pairing_check<Coop256><<<(unsigned)n, 32, Coop256::L::BYTES, st>>>(n, da1, da2, db1, db2, dok, ctx->d_flags);
+  else
+    k_bn256_pairing_check<<<(unsigned)((n + 63) / 64), 64, 0, st>>>(n, da1, da2, db1, db2, dok, ctx->d_flags);
   CK(cudaGetLastError());
   ctx->launches += 1;
   CK(cudaMemcpyAsync(ok, dok, n, cudaMemcpyDeviceToHost, st));

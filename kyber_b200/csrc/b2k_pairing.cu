@@ -5,6 +5,7 @@
 #include "../../include/b2kyber.h"
 #include "b2k_ctx.h"
 #include "pairing_kernels.cuh"
+#define B2K_COOP_BLS 1
 #include "coop_pairing.cuh"
 #include "msm_host.cuh"
 

@@ -63,3 +63,35 @@ def test_bls_verify_goes_through_the_cooperative_kernel_for_small_batches(engine
             ok = engine.bls12381_verify_g1sig(pks, msgs, h.DST_G1, b"".join(sigs))
             assert list(ok) == [0 if (n > 1 and i == 2) else 1 for i in range(n)], (n, coop)
     engine._check(engine.lib.b2k_set_pairing_coop(engine.h, 10240))
+
+
+@pytest.mark.parametrize("curve", ["bn254", "bn256"])
+def test_bn_pairings_on_both_kernels(engine, curve):
+    """bn254 / bn256 Pair and ValidatePairing (pairing/bn254/suite.go:133-144, pairing/bn256/suite.go:99-109) through the cooperative
+    kernel (small batches, the default) and through the one-per-thread kernel: same bytes as the restatement of the Go source."""
+    if curve == "bn254":
+        from oracle import bn254 as c, bn254_pairing as b
+        pair, check = engine.bn254_pair, engine.bn254_pairing_check
+    else:
+        from oracle import bn256 as c, bn256_pairing as b
+        pair, check = engine.bn256_pair, engine.bn256_pairing_check
+    rng = random.Random(63)
+    pairs = [(c.G1, b.G2), (None, b.G2), (c.G1, None)] + [(c.g1_mul(rng.randrange(1, c.ORDER)), b.g2_mul(rng.randrange(1, c.ORDER))) for _ in range(3)]
+    g1 = b"".join(c.g1_marshal(p) for p, _ in pairs)
+    g2 = b"".join(b.g2_marshal(q) for _, q in pairs)
+    want_gt = b"".join(b.gt_to_bytes(b.pairing(p, q)) for p, q in pairs)
+    x, y = rng.randrange(1, c.ORDER), rng.randrange(1, c.ORDER)
+    a1 = [c.g1_mul(x), c.g1_mul(x), None, None, c.g1_mul(x)]
+    a2 = [b.g2_mul(y)] * 5
+    b1 = [c.g1_mul(x * y % c.ORDER), c.g1_mul((x * y + 1) % c.ORDER), None, c.g1_mul(x), None]
+    b2 = [b.G2] * 5
+    want = [1, 0, 1, 0, 0]        # right, wrong, both sides 1, 1 against a non-trivial pairing (twice: the live pair alone)
+    A1, A2 = b"".join(c.g1_marshal(p) for p in a1), b"".join(b.g2_marshal(q) for q in a2)
+    B1, B2 = b"".join(c.g1_marshal(p) for p in b1), b"".join(b.g2_marshal(q) for q in b2)
+    try:
+        for coop in (1 << 20, 0):
+            engine.set_pairing_coop(coop)
+            assert pair(g1, g2) == want_gt, (curve, coop)
+            assert list(check(A1, A2, B1, B2)) == want, (curve, coop)
+    finally:
+        engine.set_pairing_coop(10240)

@@ -1,5 +1,5 @@
 #!/usr/bin/env python3
-"""Generate the program tables of the WARP-COOPERATIVE BLS12-381 pairing (kyber_b200/csrc/coop_program.inc).
+"""Generate the program tables of the WARP-COOPERATIVE pairings (kyber_b200/csrc/coop_program_{bls,bn254,bn256}.inc).
 
 Why: the batch kernels run one pairing per thread, so a single Suite.Pair / ValidatePairing (kilic/suite.go:57-75) costs one thread's
 latency (~37 ms).  A pairing is ~20 000 Fp products with a dependency depth of only ~1 000, so one WARP can run one pairing with its
@@ -11,7 +11,7 @@ allocator maps the values to slots of shared memory, and the device side (coop_p
 The SAME formulas run over plain integers and must reproduce the oracle's pairing; the ENCODED program is then interpreted numerically
 (reads of a round before its writes, exactly like the lanes) and must reproduce it again -- `--check`, run by tests/test_coop_program.py.
 
-Usage:  python tools/gen_coop_pairing.py            # rewrite kyber_b200/csrc/coop_program.inc
+Usage:  python tools/gen_coop_pairing.py            # rewrite kyber_b200/csrc/coop_program_*.inc
         python tools/gen_coop_pairing.py --check    # validate formulas + schedule + encoding against the oracle; exit 1 on mismatch
 """
 import hashlib
@@ -21,9 +21,45 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 # Generation needs nothing but the curve's public parameters (kyber_b200/build.py runs it: the product build must not touch oracle/);
 # only --check imports the oracle, as the checker.
-P = 0x1a0111ea397fe69a4b1ba7b6434bacd764774b84f38512bf6730d2a0f6b0f6241eabfffeb153ffffb9feffffffffaaab
-X_ABS = 0xd201000000010000                 # the curve parameter is x = -X_ABS
-OUT = os.path.join(ROOT, "kyber_b200", "csrc", "coop_program.inc")
+BLS_P = 0x1a0111ea397fe69a4b1ba7b6434bacd764774b84f38512bf6730d2a0f6b0f6241eabfffeb153ffffb9feffffffffaaab
+X_ABS = 0xd201000000010000                 # BLS12-381: the curve parameter is x = -X_ABS
+
+
+def _f2_pow_int(a, e):                                             # (a0 + a1 u)^e over the integers mod P, u^2 = -1
+    r = (1, 0)
+    while e:
+        if e & 1:
+            r = ((r[0] * a[0] - r[1] * a[1]) % P, (r[0] * a[1] + r[1] * a[0]) % P)
+        a = ((a[0] * a[0] - a[1] * a[1]) % P, 2 * a[0] * a[1] % P)
+        e >>= 1
+    return r
+
+
+def _bn_p(u): return 36 * u ** 4 + 36 * u ** 3 + 24 * u ** 2 + 6 * u + 1
+
+
+# public parameters of the three pairing curves: modulus, 32-bit limbs of the device field, xi (Fp6 = Fp2[v]/(v^3 - xi)) and, for the
+# Barreto-Naehrig curves, u and the signed digits of 6u + 2 (data of pairing/bn254/optate.go:117-120, pairing/bn256/optate.go:117-122)
+CURVES = {
+    "BLS": {"P": BLS_P, "limbs": 12, "XI": (1, 1)},
+    "BN254": {"P": _bn_p(4965661367192848881), "limbs": 8, "XI": (9, 1), "U": 4965661367192848881,
+              "NAF": [0, 0, 0, 1, 0, 1, 0, -1, 0, 0, 1, -1, 0, 0, 1, 0, 0, 1, 1, 0, -1, 0, 0, 1, 0, -1, 0, 0, 0, 0, 1, 1,
+                      1, 0, 0, -1, 0, 0, 1, 0, 0, 0, 0, 0, -1, 0, 0, 1, 1, 0, 0, -1, 0, 0, 0, 1, 1, 0, -1, 0, 0, 1, 0, 1, 1]},
+    "BN256": {"P": _bn_p(6518589491078791937), "limbs": 10, "XI": (3, 1), "U": 6518589491078791937,
+              "NAF": [0, 0, 0, 1, 0, 0, 0, 0, 0, 1, 0, 0, 1, 0, 0, 0, -1, 0, 1, 0, 1, 0, 0, 0, 0, 1, 0, 1, 0, 0, 0, -1, 0,
+                      1, 0, 0, 0, 1, 0, -1, 0, 0, 0, -1, 0, 1, 0, 0, 0, 0, 0, 1, 0, 0, -1, 0, -1, 0, 0, 0, 0, 1, 0, 0, 0, 1]},
+}
+P = BLS_P                                  # the modulus of the curve being compiled (set_curve)
+XI = (1, 1)
+_GAMMA = {}
+CUR = "BLS"
+
+
+def set_curve(name):
+    global P, XI, _GAMMA, CUR
+    c = CURVES[name]
+    CUR, P, XI = name, c["P"], c["XI"]
+    _GAMMA = {j: [_f2_pow_int(XI, k * (P ** j - 1) // 6) for k in range(6)] for j in (1, 2, 3)}   # xi^(k (p^j - 1)/6)
 
 # ---- operations -----------------------------------------------------------------------------------------------------------------
 NOP, MUL, SQR, ADD, SUB, NEG, DBL, MULC, INV = range(9)
@@ -140,7 +176,21 @@ def f2_sub(B, a, b): return (B.sub(a[0], b[0]), B.sub(a[1], b[1]))
 def f2_neg(B, a): return (B.neg(a[0]), B.neg(a[1]))
 def f2_dbl(B, a): return (B.dbl(a[0]), B.dbl(a[1]))
 def f2_conj(B, a): return (a[0], B.neg(a[1]))
-def f2_mul_xi(B, a): return (B.sub(a[0], a[1]), B.add(a[0], a[1]))
+def smul(B, a, k):                                                 # k a for a small positive integer k, by doublings and additions
+    r, t = ZERO, a
+    while k:
+        if k & 1: r = B.add(r, t)
+        k >>= 1
+        if k: t = B.dbl(t)
+    return r
+
+
+def f2_smul(B, a, k): return (smul(B, a[0], k), smul(B, a[1], k))
+
+
+def f2_mul_xi(B, a):                                               # (a0 + a1 u)(x0 + u): xi = x0 + u with x0 = 1 (BLS), 9 (bn254), 3 (bn256)
+    assert XI[1] == 1
+    return (B.sub(smul(B, a[0], XI[0]), a[1]), B.add(smul(B, a[1], XI[0]), a[0]))
 def f2_mul_fp(B, a, k): return (B.mul(a[0], k), B.mul(a[1], k))
 
 
@@ -232,19 +282,6 @@ def f12_inv(B, a):
 # w-power slots: w^0 c0.c0, w^1 c1.c0, w^2 c0.c1, w^3 c1.c1, w^4 c0.c2, w^5 c1.c2
 def _to_w(a): return [a[0][0], a[1][0], a[0][1], a[1][1], a[0][2], a[1][2]]
 def _from_w(c): return ((c[0], c[2], c[4]), (c[1], c[3], c[5]))
-
-
-def _f2_pow_int(a, e):                                             # (a0 + a1 u)^e over the integers mod P, u^2 = -1
-    r = (1, 0)
-    while e:
-        if e & 1:
-            r = ((r[0] * a[0] - r[1] * a[1]) % P, (r[0] * a[1] + r[1] * a[0]) % P)
-        a = ((a[0] * a[0] - a[1] * a[1]) % P, 2 * a[0] * a[1] % P)
-        e >>= 1
-    return r
-
-
-_GAMMA = {j: [_f2_pow_int((1, 1), k * (P ** j - 1) // 6) for k in range(6)] for j in (1, 2)}   # xi^(k (p^j - 1)/6), xi = 1 + u
 
 
 def f12_frobenius(B, a, j):
@@ -352,8 +389,123 @@ def miller_loop(B, pairs):                                         # pairs: [(P 
     return f12_conj(B, f)
 
 
+# ---- Barreto-Naehrig curves (bn254, bn256): the reference's own algorithm, pairing/bn254/optate.go (bn256 twin) -----------------------------
+# twist point r = (x, y, z, t = z^2) Jacobian; line = (a t + b) w + c with a, b in Fp2 and c in Fp2 (sparse product: mul_line_bn)
+def bn_line_add(B, r, p, q, r2):                                   # optate.go:5-54; p = affine twist point, q = affine G1 point
+    rx, ry, rz, rt = r
+    Bv = f2_mul(B, p[0], rt)
+    D = f2_add(B, p[1], rz)
+    D = f2_mul(B, f2_sub(B, f2_sub(B, f2_sqr(B, D), r2), rt), rt)
+    H = f2_sub(B, Bv, rx)
+    I = f2_sqr(B, H)
+    E = f2_smul(B, I, 4)
+    J = f2_mul(B, H, E)
+    L1 = f2_sub(B, f2_sub(B, D, ry), ry)
+    V = f2_mul(B, rx, E)
+    ox = f2_sub(B, f2_sub(B, f2_sub(B, f2_sqr(B, L1), J), V), V)
+    oz = f2_sub(B, f2_sub(B, f2_sqr(B, f2_add(B, rz, H)), rt), I)
+    t = f2_mul(B, f2_sub(B, V, ox), L1)
+    t2 = f2_dbl(B, f2_mul(B, ry, J))
+    oy = f2_sub(B, t, t2)
+    ot = f2_sqr(B, oz)
+    t = f2_sub(B, f2_sub(B, f2_sqr(B, f2_add(B, p[1], oz)), r2), ot)
+    t2 = f2_dbl(B, f2_mul(B, L1, p[0]))
+    a = f2_sub(B, t2, t)
+    c = f2_dbl(B, f2_mul_fp(B, oz, q[1]))
+    b = f2_dbl(B, f2_mul_fp(B, f2_neg(B, L1), q[0]))
+    return a, b, c, (ox, oy, oz, ot)
+
+
+def bn_line_double(B, r, q):                                       # optate.go:56-94
+    rx, ry, rz, rt = r
+    A, Bq = f2_sqr(B, rx), f2_sqr(B, ry)
+    C = f2_sqr(B, Bq)
+    D = f2_dbl(B, f2_sub(B, f2_sub(B, f2_sqr(B, f2_add(B, rx, Bq)), A), C))
+    E = f2_smul(B, A, 3)
+    G = f2_sqr(B, E)
+    ox = f2_sub(B, f2_sub(B, G, D), D)
+    oz = f2_sub(B, f2_sub(B, f2_sqr(B, f2_add(B, ry, rz)), Bq), rt)
+    oy = f2_sub(B, f2_mul(B, f2_sub(B, D, ox), E), f2_smul(B, C, 8))
+    ot = f2_sqr(B, oz)
+    t = f2_dbl(B, f2_mul(B, E, rt))
+    b = f2_mul_fp(B, f2_neg(B, t), q[0])
+    a = f2_sub(B, f2_sub(B, f2_sub(B, f2_sqr(B, f2_add(B, rx, E)), A), G), f2_smul(B, Bq, 4))
+    c = f2_mul_fp(B, f2_dbl(B, f2_mul(B, oz, rt)), q[1])
+    return a, b, c, (ox, oy, oz, ot)
+
+
+def bn_mul_line(B, f, a, b, c):                                    # f * ((a t + b) w + c), optate.go:96-114
+    return f12_mul(B, f, ((c, F2Z, F2Z), (b, a, F2Z)))
+
+
+def bn_miller(B, pairs):                                           # pairs: [(P = (x, y), Q = ((x0, x1), (y0, y1)))]; shared squarings
+    naf = CURVES[CUR]["NAF"]
+    n = len(naf)
+    R = [(Q[0], Q[1], (ONE, ZERO), (ONE, ZERO)) for _, Q in pairs]
+    R2 = [f2_sqr(B, Q[1]) for _, Q in pairs]
+    f = F12_ONE
+    for i in range(n - 1, 0, -1):
+        if i != n - 1:
+            f = f12_sqr(B, f)
+        for k, (Pt, Q) in enumerate(pairs):
+            a, b, c, R[k] = bn_line_double(B, R[k], Pt)
+            f = bn_mul_line(B, f, a, b, c)
+        d = naf[i - 1]
+        if d:
+            for k, (Pt, Q) in enumerate(pairs):
+                Qs = Q if d == 1 else (Q[0], f2_neg(B, Q[1]))
+                a, b, c, R[k] = bn_line_add(B, R[k], Qs, Pt, R2[k])
+                f = bn_mul_line(B, f, a, b, c)
+    xi_p1_3, xi_p1_2 = _f2_pow_int(XI, (P - 1) // 3), _f2_pow_int(XI, (P - 1) // 2)
+    xi_p2_3 = _f2_pow_int(XI, (P * P - 1) // 3)
+    assert xi_p2_3[1] == 0
+    for k, (Pt, Q) in enumerate(pairs):                            # the two Frobenius steps: Q1 = pi(Q), -Q2 = -pi^2(Q)
+        q1 = (f2_mul_const(B, f2_conj(B, Q[0]), xi_p1_3), f2_mul_const(B, f2_conj(B, Q[1]), xi_p1_2))
+        mq2 = (f2_mul_const(B, Q[0], xi_p2_3), Q[1])
+        a, b, c, R[k] = bn_line_add(B, R[k], q1, Pt, f2_sqr(B, q1[1]))
+        f = bn_mul_line(B, f, a, b, c)
+        a, b, c, _ = bn_line_add(B, R[k], mq2, Pt, f2_sqr(B, mq2[1]))
+        f = bn_mul_line(B, f, a, b, c)
+    return f
+
+
+def f12_pow_u(B, a, u):                                            # a^u inside the cyclotomic subgroup
+    acc = a
+    for bit in bin(u)[3:]:
+        acc = f12_cyclotomic_sqr(B, acc)
+        if bit == "1":
+            acc = f12_mul(B, acc, a)
+    return acc
+
+
+def bn_final_exponentiation(B, f):                                 # optate.go:212-261
+    U = CURVES[CUR]["U"]
+    t1 = f12_mul(B, f12_conj(B, f), f12_inv(B, f))
+    t1 = f12_mul(B, t1, f12_frobenius(B, t1, 2))
+    fp, fp2, fp3 = f12_frobenius(B, t1, 1), f12_frobenius(B, t1, 2), f12_frobenius(B, t1, 3)
+    fu = f12_pow_u(B, t1, U)
+    fu2 = f12_pow_u(B, fu, U)
+    fu3 = f12_pow_u(B, fu2, U)
+    y3 = f12_conj(B, f12_frobenius(B, fu, 1))
+    fu2p, fu3p = f12_frobenius(B, fu2, 1), f12_frobenius(B, fu3, 1)
+    y2 = f12_frobenius(B, fu2, 2)
+    y0 = f12_mul(B, f12_mul(B, fp, fp2), fp3)
+    y1, y5 = f12_conj(B, t1), f12_conj(B, fu2)
+    y4 = f12_conj(B, f12_mul(B, fu, fu2p))
+    y6 = f12_conj(B, f12_mul(B, fu3, fu3p))
+    t0 = f12_mul(B, f12_mul(B, f12_cyclotomic_sqr(B, y6), y4), y5)
+    t1b = f12_mul(B, f12_mul(B, y3, y5), t0)
+    t0 = f12_mul(B, t0, y2)
+    t1b = f12_cyclotomic_sqr(B, f12_mul(B, f12_cyclotomic_sqr(B, t1b), t0))
+    t0 = f12_mul(B, t1b, y1)
+    t1b = f12_mul(B, t1b, y0)
+    return f12_mul(B, f12_cyclotomic_sqr(B, t0), t1b)
+
+
 def pairing_product(B, pairs):
-    return final_exponentiation(B, miller_loop(B, pairs))
+    if CUR == "BLS":
+        return final_exponentiation(B, miller_loop(B, pairs))
+    return bn_final_exponentiation(B, bn_miller(B, pairs))
 
 
 def flat12(f):                                                     # 12 Fp values in the order of BFp12's memory layout
@@ -361,7 +513,8 @@ def flat12(f):                                                     # 12 Fp value
 
 
 # ---- compile: schedule into rounds, allocate slots, encode ---------------------------------------------------------------------------
-def compile_program(npairs):
+def compile_program(curve, npairs):
+    set_curve(curve)
     n_in = 6 * npairs                                              # per pair: P.x, P.y, Q.x.c0, Q.x.c1, Q.y.c0, Q.y.c1
     B = Sym(n_in)
     pairs = [((6 * i, 6 * i + 1), ((6 * i + 2, 6 * i + 3), (6 * i + 4, 6 * i + 5))) for i in range(npairs)]
@@ -464,7 +617,7 @@ def compile_program(npairs):
             assert s < 512 and ea < 512 and eb < 512
             words.append((eop << 28) | (s << 18) | (ea << 9) | eb)
         prog.append(words + [0] * (32 - len(words)))
-    return {"npairs": npairs, "n_in": n_in, "one": n_in, "zero": zero_id, "rounds": prog, "nslots": nslots, "out": [slot[v] for v in out],
+    return {"curve": curve, "npairs": npairs, "n_in": n_in, "one": n_in, "zero": zero_id, "rounds": prog, "nslots": nslots, "out": [slot[v] for v in out],
             "consts": B.consts, "ntasks": len(tasks),
             "nlong": sum(1 for take in rounds if tasks[take[0]][0] in LONG), "nmul": sum(1 for t in tasks if t[0] in LONG)}
 
@@ -498,15 +651,6 @@ def run_program(pg, inputs):
     return [S[s] for s in pg["out"]]
 
 
-def oracle_f12(pairs_pts):
-    sys.path.insert(0, ROOT)
-    from oracle import bls12381 as o
-    f = o.F12_ONE
-    for p1, q2 in pairs_pts:
-        f = o.f12_mul(f, o.miller_loop(p1, q2))
-    return o.final_exponentiation_cubed(f)
-
-
 def flat_oracle(f):
     return [f[h][k][c] for h in range(2) for k in range(3) for c in range(2)]
 
@@ -518,59 +662,89 @@ def inputs_of(pairs_pts):
     return v
 
 
+def _oracle(curve):
+    """(random pair, a true 2-pair identity, the reference value of a product of pairings, the GT one) from the test oracle"""
+    sys.path.insert(0, ROOT)
+    import types
+    if curve == "BLS":
+        from oracle import bls12381 as o
+        assert o.P == CURVES["BLS"]["P"] and o.X_ABS == X_ABS
+
+        def product(pts):
+            f = o.F12_ONE
+            for p1, q2 in pts:
+                f = o.f12_mul(f, o.miller_loop(p1, q2))
+            return o.final_exponentiation_cubed(f)
+        return types.SimpleNamespace(order=o.R, g1_mul=o.g1_mul, g2_mul=o.g2_mul, g1_neg=o.g1_neg, G2=o.G2, product=product, one=o.F12_ONE)
+    if curve == "BN254":
+        from oracle import bn254 as c, bn254_pairing as b
+    else:
+        from oracle import bn256 as c, bn256_pairing as b
+    assert c.P == CURVES[curve]["P"] and c.U == CURVES[curve]["U"]
+
+    def product(pts):
+        f = b.F12_ONE
+        for p1, q2 in pts:
+            f = b.f12_mul(f, b.miller(q2, p1))
+        return b.final_exponentiation(f)
+    return types.SimpleNamespace(order=c.ORDER, g1_mul=c.g1_mul, g2_mul=b.g2_mul, g1_neg=lambda pt: (pt[0], -pt[1] % c.P), G2=b.G2,
+                                 product=product, one=b.F12_ONE)
+
+
 def check(programs):
     import random
-    sys.path.insert(0, ROOT)
-    from oracle import bls12381 as o
-    assert o.P == P and o.X_ABS == X_ABS
     rng = random.Random(7)
     ok = True
-    for npairs, pg in programs.items():
+    for (curve, npairs), pg in programs.items():
+        set_curve(curve)
+        o = _oracle(curve)
         for trial in range(2):
-            pts = [(o.g1_mul(rng.randrange(1, o.R)), o.g2_mul(rng.randrange(1, o.R))) for _ in range(npairs)]
+            pts = [(o.g1_mul(rng.randrange(1, o.order)), o.g2_mul(rng.randrange(1, o.order))) for _ in range(npairs)]
             if trial == 1 and npairs == 2:                         # a true ValidatePairing instance: e(aG, bH) e(-abG, H) = 1
-                a, b = rng.randrange(1, o.R), rng.randrange(1, o.R)
-                pts = [(o.g1_mul(a), o.g2_mul(b)), (o.g1_neg(o.g1_mul(a * b % o.R)), o.G2)]
-            want = flat_oracle(oracle_f12(pts))
+                a, b = rng.randrange(1, o.order), rng.randrange(1, o.order)
+                pts = [(o.g1_mul(a), o.g2_mul(b)), (o.g1_neg(o.g1_mul(a * b % o.order)), o.G2)]
+            want = flat_oracle(o.product(pts))
             num = flat12(pairing_product(Num(), [((p[0], p[1]), (q[0], q[1])) for p, q in pts]))
             num = [1 if x is ONE else 0 if x is ZERO else x for x in num]
             got = run_program(pg, inputs_of(pts))
             good = num == want and got == want
             if trial == 1 and npairs == 2:
-                good = good and want == flat_oracle(o.F12_ONE)
-            print(f"  {npairs}-pair program, trial {trial}: formulas {'ok' if num == want else 'WRONG'}, encoded program {'ok' if got == want else 'WRONG'}")
+                good = good and want == flat_oracle(o.one)
+            print(f"  {curve} {npairs}-pair program, trial {trial}: formulas {'ok' if num == want else 'WRONG'}, encoded program {'ok' if got == want else 'WRONG'}")
             ok = ok and good
     return ok
 
 
-def mont_words(k):
-    v = k * (1 << 384) % P
-    return [(v >> (32 * i)) & 0xffffffff for i in range(12)]
+def mont_words(k, limbs):
+    v = k * (1 << (32 * limbs)) % P
+    return [(v >> (32 * i)) & 0xffffffff for i in range(limbs)]
 
 
-def emit(programs):
+def emit(programs, curve):
+    """the table file of one curve (kyber_b200/csrc/coop_program_<curve>.inc)"""
+    set_curve(curve)
+    limbs = CURVES[curve]["limbs"]
+    lines = [f"// GENERATED by tools/gen_coop_pairing.py -- do not edit.  Program tables of the warp-cooperative {curve} pairing (coop_pairing.cuh):",
+             "// word = op << 28 | dst << 18 | a << 9 | b; 32 words (one per lane) per round; op 0 = idle lane.",
+             "// ops: 1 MUL  3 ADD  4 SUB  7 MULC (b = constant index)  8 INV   (a^2, 2 a and -a are encoded as a * a, a + a and ZERO - a)",
+             "#pragma once", "#include <stdint.h>", "namespace b2k { namespace coop {"]
+    mine = {n: pg for (c, n), pg in programs.items() if c == curve}
     consts = []
-    for pg in programs.values():
+    for pg in mine.values():
         for k in pg["consts"]:
             if k not in consts:
                 consts.append(k)
-    lines = ["// GENERATED by tools/gen_coop_pairing.py -- do not edit.  Program tables of the warp-cooperative BLS12-381 pairing",
-             "// (coop_pairing.cuh): word = op << 28 | dst << 18 | a << 9 | b; 32 words (one per lane) per round; op 0 = idle lane.",
-             "// ops: 1 MUL  3 ADD  4 SUB  7 MULC (b = constant index)  8 INV   (a^2, 2 a and -a are encoded as a * a, a + a and ZERO - a)",
-             "#pragma once", "#include <stdint.h>", "namespace b2k { namespace coop {",
-             f"constexpr int N_CONST = {len(consts)};",
-             "__device__ const uint32_t CONSTS[N_CONST][12] = {   // Montgomery form, little-endian 32-bit limbs"]
+    lines.append(f"__device__ const uint32_t {curve}_CONSTS[{len(consts)}][{limbs}] = {{   // Montgomery form (R = 2^{32 * limbs}), little-endian 32-bit limbs")
     for k in consts:
-        lines.append("  {" + ", ".join("0x%08xu" % w for w in mont_words(k)) + "},")
+        lines.append("  {" + ", ".join("0x%08xu" % w for w in mont_words(k, limbs)) + "},")
     lines.append("};")
-    for npairs, pg in programs.items():
+    for npairs, pg in mine.items():
         remap = {i: consts.index(k) for i, k in enumerate(pg["consts"])}
-        tag = f"P{npairs}"
-        lines.append(f"// {npairs}-pair product + final exponentiation: {pg['ntasks']} operations ({pg['nmul']} products) in {len(pg['rounds'])} rounds "
+        tag = f"{curve}_P{npairs}"
+        lines.append(f"// {curve}, {npairs}-pair product + final exponentiation: {pg['ntasks']} operations ({pg['nmul']} products) in {len(pg['rounds'])} rounds "
                      f"({pg['nlong']} of them product rounds), {pg['nslots']} slots")
-        lines.append(f"constexpr int {tag}_ROUNDS = {len(pg['rounds'])}, {tag}_SLOTS = {pg['nslots']}, {tag}_INPUTS = {pg['n_in']}, {tag}_ONE = {pg['one']}, {tag}_ZERO = {pg['zero']};")
-        lines.append(f"__device__ const uint16_t {tag}_OUT[12] = {{" + ", ".join(str(s) for s in pg["out"]) + "};")
-        lines.append(f"__device__ const uint32_t {tag}_PROG[{tag}_ROUNDS * 32] = {{")
+        lines.append(f"__device__ const uint16_t {tag}_OUT[12] = {{" + ", ".join(str(x) for x in pg["out"]) + "};")
+        lines.append(f"__device__ const uint32_t {tag}_PROG[{len(pg['rounds'])} * 32] = {{")
         for words in pg["rounds"]:
             fixed = []
             for w in words:
@@ -579,23 +753,33 @@ def emit(programs):
                 fixed.append(w)
             lines.append("  " + ",".join("0x%xu" % w for w in fixed) + ",")
         lines.append("};")
+        lines.append(f"struct {tag} {{")
+        lines.append(f"  static constexpr int ROUNDS = {len(pg['rounds'])}, SLOTS = {pg['nslots']}, INPUTS = {pg['n_in']}, ONE = {pg['one']}, ZERO = {pg['zero']}, LIMBS = {limbs};")
+        lines.append(f"  static __device__ __forceinline__ const uint32_t* prog() {{ return {tag}_PROG; }}")
+        lines.append(f"  static __device__ __forceinline__ const uint16_t* out() {{ return {tag}_OUT; }}")
+        lines.append(f"  static __device__ __forceinline__ const uint32_t* consts() {{ return &{curve}_CONSTS[0][0]; }}")
+        lines.append("};")
     lines.append("} }  // namespace b2k::coop")
     return "\n".join(lines) + "\n"
 
 
+def out_path(curve): return os.path.join(ROOT, "kyber_b200", "csrc", f"coop_program_{curve.lower()}.inc")
+
+
 def main():
-    programs = {n: compile_program(n) for n in (1, 2)}
-    for n, pg in programs.items():
-        print(f"{n}-pair program: {pg['ntasks']} operations, {pg['nmul']} products, {len(pg['rounds'])} rounds ({pg['nlong']} product rounds), "
+    programs = {(c, n): compile_program(c, n) for c in CURVES for n in (1, 2)}
+    for (c, n), pg in programs.items():
+        print(f"{c} {n}-pair program: {pg['ntasks']} operations, {pg['nmul']} products, {len(pg['rounds'])} rounds ({pg['nlong']} product rounds), "
               f"{pg['nslots']} slots, {len(pg['consts'])} constants")
-    text = emit(programs)
+    texts = {c: emit(programs, c) for c in CURVES}
     if "--check" in sys.argv:
         good = check(programs)
-        same = os.path.exists(OUT) and open(OUT).read() == text
-        print("coop_program.inc is", "up to date" if same else "STALE (run tools/gen_coop_pairing.py)")
+        same = all(os.path.exists(out_path(c)) and open(out_path(c)).read() == texts[c] for c in CURVES)
+        print("coop_program_*.inc are", "up to date" if same else "STALE (run tools/gen_coop_pairing.py)")
         sys.exit(0 if good and same else 1)
-    open(OUT, "w").write(text)
-    print("wrote", OUT, len(text), "bytes, sha256", hashlib.sha256(text.encode()).hexdigest()[:16])
+    for c in CURVES:
+        open(out_path(c), "w").write(texts[c])
+        print("wrote", out_path(c), len(texts[c]), "bytes, sha256", hashlib.sha256(texts[c].encode()).hexdigest()[:16])
 
 
 if __name__ == "__main__":
