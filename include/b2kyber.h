@@ -436,7 +436,8 @@ int b2k_bn256_g2_unmarshal_check(b2k_ctx* ctx, size_t n, const uint8_t* in /*[n]
 int b2k_set_pairing_variant(b2k_ctx* ctx, int variant);
 /* Batches of at most max_n pairings / pairing checks (BLS12-381, bn254, bn256) run on the warp-cooperative kernels (one warp per
  * element: a single BLS12-381 Suite.Pair takes 2.0 ms instead of one thread's 20 ms, a single ValidatePairing 2.3 instead of 26 ms;
- * bn254 / bn256: 2.1 / 2.5 ms instead of 12-23 ms); larger batches use the one-per-thread kernels.  Default 10240 (the measured
+ * bn254 / bn256: 2.1 / 2.5 ms instead of 12-23 ms; GT.Mul on BLS12-381 and bn254, batches up to 4096: 2.5 instead of 22 ms); larger
+ * batches use the one-per-thread kernels.  Default 10240 (the measured
  * break-even on BLS12-381; the Barreto-Naehrig curves cap it at 8192), 0 = never.  Same bytes either way. */
 int b2k_set_pairing_coop(b2k_ctx* ctx, int max_n);
 

@@ -18,6 +18,8 @@
 #include "codec.cuh"
 #include "bn256.cuh"
 #include "bn_pairing.cuh"
+#define B2K_COOP_GT 1
+#include "coop_pairing.cuh"          // small batches of GT.Mul: one warp per element
 
 using namespace b2k;
 using namespace b2k_host;
@@ -43,6 +45,9 @@ B2K_D void bn_gt_load(PFp12<PC>& f, const uint8_t* in) {        // inverse of bn
 
 struct BlsPairing {
   using F12 = BFp12;
+  using FC = Bls381Fp;
+  using CoopSqr = coop::BLS_SQR;
+  using CoopMul = coop::BLS_MUL;
   using G1 = Bls381G1;
   using G2 = Bls381G2;
   using Fr = Bls381Fr;
@@ -56,6 +61,9 @@ struct BlsPairing {
 template <class PC, class G1T, class G2T, class FrT, bool RANGE>
 struct BnPairing {
   using F12 = PFp12<PC>;
+  using FC = typename PC::FC;
+  using CoopSqr = coop::BN254_SQR;                            // (only bn254 has GT.Mul in the ABI; bn256 never instantiates the exponentiation)
+  using CoopMul = coop::BN254_MUL;
   using G1 = G1T;
   using G2 = G2T;
   using Fr = FrT;
@@ -117,6 +125,80 @@ __global__ void __launch_bounds__(64, 4) k_gt_exp(size_t n, const uint8_t* __res
     }
   }
   P::store(out + (size_t)P::GT_BYTES * i, acc);
+}
+
+// The same exponentiation for SMALL batches, one WARP per element (coop_pairing.cuh): GT.Mul is called one element at a time by the
+// reference's IBE (encrypt/ibe: Gid^r), and one thread needs ~15 ms for its 255 Fp12 squarings and ~128 products.  The two steps are
+// programs of the cooperative interpreter (19 and 15 rounds on BLS12-381: the 36 / 54 Fp products of a step run in two rounds); the
+// accumulator lives in the programs' first 12 input slots, the base beside the slot array.
+template <class P, class C, class SQR, class MUL>
+__global__ void __launch_bounds__(32, 16) k_coop_gt_exp(size_t n, const uint8_t* __restrict__ scalars, const uint8_t* __restrict__ a,
+                                                        uint8_t* __restrict__ out, uint32_t* flags) {
+  constexpr int NS = (SQR::SLOTS > MUL::SLOTS ? SQR::SLOTS : MUL::SLOTS) | 1;
+  constexpr int N = C::N;
+  extern __shared__ __align__(16) uint32_t gt_sm[];
+  uint32_t* S = gt_sm;                                       // slots, limb-major
+  uint32_t* base = gt_sm + (size_t)N * NS;                   // the element a: 12 coefficients, limb-major with stride 12
+  const int lane = threadIdx.x;
+  const size_t i = blockIdx.x;
+  if (i >= n) return;
+  Scalar256 k;
+  scalar_load_be(k, scalars + 32 * i);                       // every lane: the loop below is warp-uniform
+  if (lane == 0) {
+    if (!scalar_in_range<typename P::Fr>(k)) atomicOr(flags, FLAG_SCALAR_RANGE);
+    if (!P::canonical(a + (size_t)P::GT_BYTES * i)) atomicOr(flags, FLAG_POINT);
+    typename P::F12 x;
+    P::load(x, a + (size_t)P::GT_BYTES * i);
+    const Fp<C>* c = reinterpret_cast<const Fp<C>*>(&x);
+    for (int q = 0; q < 12; q++)
+      for (int j = 0; j < N; j++) base[j * 12 + q] = c[q].v[j];
+  }
+  __syncwarp();
+  auto put = [&](int slot0, const uint32_t* src, int stride, const uint16_t* idx) {   // 12 values into slots slot0 .. slot0 + 11
+    uint32_t v[N];
+    if (lane < 12) {
+#pragma unroll
+      for (int j = 0; j < N; j++) v[j] = idx ? src[j * stride + idx[lane]] : src[j * stride + lane];
+    }
+    __syncwarp();
+    if (lane < 12) {
+#pragma unroll
+      for (int j = 0; j < N; j++) S[j * NS + slot0 + lane] = v[j];
+    }
+    __syncwarp();
+  };
+  auto consts = [&](int one, int zero) {
+    if (lane < N) { S[lane * NS + one] = C::r1(lane); S[lane * NS + zero] = 0u; }
+    __syncwarp();
+  };
+  bool started = false;
+  for (int b = 255; b >= 0; b--) {
+    if (started) {
+      consts(SQR::ONE, SQR::ZERO);
+      coop::run<SQR, NS, C>(S, lane);
+      put(0, S, NS, SQR::out());                             // acc = acc^2
+    }
+    if ((k.v[b >> 5] >> (b & 31)) & 1u) {
+      if (started) {
+        put(12, base, 12, nullptr);                          // second operand = a
+        consts(MUL::ONE, MUL::ZERO);
+        coop::run<MUL, NS, C>(S, lane);
+        put(0, S, NS, MUL::out());                           // acc = acc * a
+      } else {
+        put(0, base, 12, nullptr);                           // acc = a
+        started = true;
+      }
+    }
+  }
+  if (lane == 0) {
+    typename P::F12 r;
+    if (started) {
+      Fp<C>* c = reinterpret_cast<Fp<C>*>(&r);
+      for (int q = 0; q < 12; q++)
+        for (int j = 0; j < N; j++) c[q].v[j] = S[j * NS + q];
+    } else fp12_set_one(r);                                  // a^0
+    P::store(out + (size_t)P::GT_BYTES * i, r);
+  }
 }
 
 // ---- Miller / Finalize -----------------------------------------------------------------------------------------------------
@@ -244,7 +326,14 @@ int gt_binary(b2k_ctx* ctx, size_t n, const uint8_t* scalars, const uint8_t* a, 
     k_gt_inv<P><<<grid, 64, 0, st>>>(n, da, dout, ctx->d_flags);
   } else {
     CK(cudaMemcpyAsync(ds, scalars, n * 32, cudaMemcpyHostToDevice, st));
-    k_gt_exp<P><<<grid, 64, 0, st>>>(n, ds, da, dout, ctx->d_flags);
+    if (ctx->coop_max_n > 0 && n <= (size_t)(ctx->coop_max_n < 4096 ? ctx->coop_max_n : 4096)) {
+      using SQR = typename P::CoopSqr;
+      using MUL = typename P::CoopMul;
+      using C = typename P::FC;
+      constexpr int NS = (SQR::SLOTS > MUL::SLOTS ? SQR::SLOTS : MUL::SLOTS) | 1;
+      k_coop_gt_exp<P, C, SQR, MUL><<<(unsigned)n, 32, (size_t)C::N * (NS + 12) * 4, st>>>(n, ds, da, dout, ctx->d_flags);
+    } else
+      k_gt_exp<P><<<grid, 64, 0, st>>>(n, ds, da, dout, ctx->d_flags);
   }
   CK(cudaGetLastError());
   ctx->launches += 1;

@@ -28,6 +28,10 @@
 #ifdef B2K_COOP_BN256
 #include "coop_program_bn256.inc"
 #endif
+#ifdef B2K_COOP_GT                       // Fp12 square / product programs of the GT group (b2k_gt.cu)
+#include "coop_program_bls_gt.inc"
+#include "coop_program_bn254_gt.inc"
+#endif
 
 namespace b2k {
 namespace coop {

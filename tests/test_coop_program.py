@@ -16,4 +16,4 @@ def test_program_tables_reproduce_the_oracle_and_are_up_to_date():
         subprocess.run([sys.executable, os.path.join(ROOT, "tools", "gen_coop_pairing.py")], check=True, stdout=subprocess.DEVNULL)
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "gen_coop_pairing.py"), "--check"], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
-    assert r.stdout.count("encoded program ok") == 12 and "WRONG" not in r.stdout and "up to date" in r.stdout, r.stdout
+    assert r.stdout.count("encoded program ok") == 24 and "WRONG" not in r.stdout and "up to date" in r.stdout, r.stdout

@@ -95,3 +95,33 @@ def test_bn_pairings_on_both_kernels(engine, curve):
             assert list(check(A1, A2, B1, B2)) == want, (curve, coop)
     finally:
         engine.set_pairing_coop(10240)
+
+
+@pytest.mark.parametrize("curve", ["bls12381", "bn254"])
+def test_gt_exponentiation_on_both_kernels(engine, curve):
+    """GT.Mul (kilic/gt.go:62-71, pairing/bn254/point.go:606-623): a^s for scalars 0, 1, r - 1 and random ones, through the cooperative
+    kernel (small batches) and the one-per-thread kernel; a is a pairing value AND an arbitrary Fp12 element (the group law does not
+    care, the generic square-and-multiply must not either)."""
+    rng = random.Random(64)
+    if curve == "bls12381":
+        order, one = o.R, o.F12_ONE
+        e = o.pairing_reference(o.g1_mul(5), o.g2_mul(7))
+        rnd = tuple(tuple((rng.randrange(o.P), rng.randrange(o.P)) for _ in range(3)) for _ in range(2))
+        to_bytes, f12_pow = o.gt_to_bytes, o.f12_pow
+    else:
+        from oracle import bn254 as c4, bn254_pairing as b4
+        order = c4.ORDER
+        e = b4.pairing(c4.g1_mul(5), b4.g2_mul(7))
+        rnd = tuple(tuple((rng.randrange(c4.P), rng.randrange(c4.P)) for _ in range(3)) for _ in range(2))
+        to_bytes, f12_pow = b4.gt_to_bytes, b4.f12_pow
+    xs = [0, 1, order - 1, rng.randrange(order), rng.randrange(order), 2]
+    vals = [e, e, e, e, rnd, rnd]
+    sb = b"".join(x.to_bytes(32, "big") for x in xs)
+    ab = b"".join(to_bytes(v) for v in vals)
+    want = b"".join(to_bytes(f12_pow(v, x)) for v, x in zip(vals, xs))
+    try:
+        for coop in (1 << 20, 0):
+            engine.set_pairing_coop(coop)
+            assert engine.gt_exp(curve, sb, ab) == want, (curve, coop)
+    finally:
+        engine.set_pairing_coop(10240)

@@ -513,12 +513,25 @@ def flat12(f):                                                     # 12 Fp value
 
 
 # ---- compile: schedule into rounds, allocate slots, encode ---------------------------------------------------------------------------
-def compile_program(curve, npairs):
+def unflat12(v):                                                   # inverse of flat12 on a list of 12 values
+    return tuple(tuple((v[6 * h + 2 * k], v[6 * h + 2 * k + 1]) for k in range(3)) for h in range(2))
+
+
+def compile_program(curve, kind):
+    """kind 1 / 2: the product of that many pairings incl. the final exponentiation (inputs: 6 values per pair);
+    kind "SQR" / "MUL": the square of one / the product of two Fp12 elements (inputs: 12 / 24 values) -- the steps of GT.Mul"""
     set_curve(curve)
-    n_in = 6 * npairs                                              # per pair: P.x, P.y, Q.x.c0, Q.x.c1, Q.y.c0, Q.y.c1
-    B = Sym(n_in)
-    pairs = [((6 * i, 6 * i + 1), ((6 * i + 2, 6 * i + 3), (6 * i + 4, 6 * i + 5))) for i in range(npairs)]
-    out = flat12(pairing_product(B, pairs))
+    npairs = kind
+    if kind in ("SQR", "MUL"):
+        n_in = 12 if kind == "SQR" else 24
+        B = Sym(n_in)
+        a = unflat12(list(range(12)))
+        out = flat12(f12_sqr(B, a) if kind == "SQR" else f12_mul(B, a, unflat12(list(range(12, 24)))))
+    else:
+        n_in = 6 * npairs                                          # per pair: P.x, P.y, Q.x.c0, Q.x.c1, Q.y.c0, Q.y.c1
+        B = Sym(n_in)
+        pairs = [((6 * i, 6 * i + 1), ((6 * i + 2, 6 * i + 3), (6 * i + 4, 6 * i + 5))) for i in range(npairs)]
+        out = flat12(pairing_product(B, pairs))
     assert all(isinstance(x, int) for x in out), "an output coefficient is a constant"
     tasks = B.tasks
     producer = {t[3]: i for i, t in enumerate(tasks)}
@@ -675,7 +688,7 @@ def _oracle(curve):
             for p1, q2 in pts:
                 f = o.f12_mul(f, o.miller_loop(p1, q2))
             return o.final_exponentiation_cubed(f)
-        return types.SimpleNamespace(order=o.R, g1_mul=o.g1_mul, g2_mul=o.g2_mul, g1_neg=o.g1_neg, G2=o.G2, product=product, one=o.F12_ONE)
+        return types.SimpleNamespace(order=o.R, g1_mul=o.g1_mul, g2_mul=o.g2_mul, g1_neg=o.g1_neg, G2=o.G2, product=product, one=o.F12_ONE, f12_mul=o.f12_mul)
     if curve == "BN254":
         from oracle import bn254 as c, bn254_pairing as b
     else:
@@ -688,7 +701,7 @@ def _oracle(curve):
             f = b.f12_mul(f, b.miller(q2, p1))
         return b.final_exponentiation(f)
     return types.SimpleNamespace(order=c.ORDER, g1_mul=c.g1_mul, g2_mul=b.g2_mul, g1_neg=lambda pt: (pt[0], -pt[1] % c.P), G2=b.G2,
-                                 product=product, one=b.F12_ONE)
+                                 product=product, one=b.F12_ONE, f12_mul=b.f12_mul)
 
 
 def check(programs):
@@ -698,6 +711,16 @@ def check(programs):
     for (curve, npairs), pg in programs.items():
         set_curve(curve)
         o = _oracle(curve)
+        if npairs in ("SQR", "MUL"):                               # Fp12 square / product on random elements against plain-integer tower formulas
+            for trial in range(2):
+                vals = [rng.randrange(P) for _ in range(pg["n_in"])]
+                a = unflat12(vals[:12])
+                num = flat12(f12_sqr(Num(), a) if npairs == "SQR" else f12_mul(Num(), a, unflat12(vals[12:])))
+                want = flat_oracle(o.f12_mul(a, a if npairs == "SQR" else unflat12(vals[12:])))
+                got = run_program(pg, vals)
+                print(f"  {curve} Fp12 {npairs} program, trial {trial}: formulas {'ok' if num == want else 'WRONG'}, encoded program {'ok' if got == want else 'WRONG'}")
+                ok = ok and num == want and got == want
+            continue
         for trial in range(2):
             pts = [(o.g1_mul(rng.randrange(1, o.order)), o.g2_mul(rng.randrange(1, o.order))) for _ in range(npairs)]
             if trial == 1 and npairs == 2:                         # a true ValidatePairing instance: e(aG, bH) e(-abG, H) = 1
@@ -720,28 +743,32 @@ def mont_words(k, limbs):
     return [(v >> (32 * i)) & 0xffffffff for i in range(limbs)]
 
 
-def emit(programs, curve):
-    """the table file of one curve (kyber_b200/csrc/coop_program_<curve>.inc)"""
+def emit(programs, curve, gt=False):
+    """a table file of one curve: the pairing programs (kyber_b200/csrc/coop_program_<curve>.inc) or, gt=True, the Fp12 square / product
+    programs of the GT group (coop_program_<curve>_gt.inc; its own file: another translation unit uses them)"""
     set_curve(curve)
     limbs = CURVES[curve]["limbs"]
     lines = [f"// GENERATED by tools/gen_coop_pairing.py -- do not edit.  Program tables of the warp-cooperative {curve} pairing (coop_pairing.cuh):",
              "// word = op << 28 | dst << 18 | a << 9 | b; 32 words (one per lane) per round; op 0 = idle lane.",
              "// ops: 1 MUL  3 ADD  4 SUB  7 MULC (b = constant index)  8 INV   (a^2, 2 a and -a are encoded as a * a, a + a and ZERO - a)",
              "#pragma once", "#include <stdint.h>", "namespace b2k { namespace coop {"]
-    mine = {n: pg for (c, n), pg in programs.items() if c == curve}
+    mine = {n: pg for (c, n), pg in programs.items() if c == curve and (n in ("SQR", "MUL")) == gt}
+    cname = f"{curve}_GT_CONSTS" if gt else f"{curve}_CONSTS"
     consts = []
     for pg in mine.values():
         for k in pg["consts"]:
             if k not in consts:
                 consts.append(k)
-    lines.append(f"__device__ const uint32_t {curve}_CONSTS[{len(consts)}][{limbs}] = {{   // Montgomery form (R = 2^{32 * limbs}), little-endian 32-bit limbs")
+    lines.append(f"__device__ const uint32_t {cname}[{max(1, len(consts))}][{limbs}] = {{   // Montgomery form (R = 2^{32 * limbs}), little-endian 32-bit limbs")
+    if not consts:
+        lines.append("  {0},")
     for k in consts:
         lines.append("  {" + ", ".join("0x%08xu" % w for w in mont_words(k, limbs)) + "},")
     lines.append("};")
     for npairs, pg in mine.items():
         remap = {i: consts.index(k) for i, k in enumerate(pg["consts"])}
-        tag = f"{curve}_P{npairs}"
-        lines.append(f"// {curve}, {npairs}-pair product + final exponentiation: {pg['ntasks']} operations ({pg['nmul']} products) in {len(pg['rounds'])} rounds "
+        tag = f"{curve}_{npairs}" if gt else f"{curve}_P{npairs}"
+        lines.append(f"// {curve}, " + (f"Fp12 {npairs}" if gt else f"{npairs}-pair product + final exponentiation") + f": {pg['ntasks']} operations ({pg['nmul']} products) in {len(pg['rounds'])} rounds "
                      f"({pg['nlong']} of them product rounds), {pg['nslots']} slots")
         lines.append(f"__device__ const uint16_t {tag}_OUT[12] = {{" + ", ".join(str(x) for x in pg["out"]) + "};")
         lines.append(f"__device__ const uint32_t {tag}_PROG[{len(pg['rounds'])} * 32] = {{")
@@ -757,29 +784,30 @@ def emit(programs, curve):
         lines.append(f"  static constexpr int ROUNDS = {len(pg['rounds'])}, SLOTS = {pg['nslots']}, INPUTS = {pg['n_in']}, ONE = {pg['one']}, ZERO = {pg['zero']}, LIMBS = {limbs};")
         lines.append(f"  static __device__ __forceinline__ const uint32_t* prog() {{ return {tag}_PROG; }}")
         lines.append(f"  static __device__ __forceinline__ const uint16_t* out() {{ return {tag}_OUT; }}")
-        lines.append(f"  static __device__ __forceinline__ const uint32_t* consts() {{ return &{curve}_CONSTS[0][0]; }}")
+        lines.append(f"  static __device__ __forceinline__ const uint32_t* consts() {{ return &{cname}[0][0]; }}")
         lines.append("};")
     lines.append("} }  // namespace b2k::coop")
     return "\n".join(lines) + "\n"
 
 
-def out_path(curve): return os.path.join(ROOT, "kyber_b200", "csrc", f"coop_program_{curve.lower()}.inc")
+def out_path(curve, gt=False): return os.path.join(ROOT, "kyber_b200", "csrc", f"coop_program_{curve.lower()}{'_gt' if gt else ''}.inc")
 
 
 def main():
-    programs = {(c, n): compile_program(c, n) for c in CURVES for n in (1, 2)}
+    programs = {(c, n): compile_program(c, n) for c in CURVES for n in (1, 2, "SQR", "MUL")}
     for (c, n), pg in programs.items():
-        print(f"{c} {n}-pair program: {pg['ntasks']} operations, {pg['nmul']} products, {len(pg['rounds'])} rounds ({pg['nlong']} product rounds), "
+        what = f"Fp12 {n}" if n in ("SQR", "MUL") else f"{n}-pair"
+        print(f"{c} {what} program: {pg['ntasks']} operations, {pg['nmul']} products, {len(pg['rounds'])} rounds ({pg['nlong']} product rounds), "
               f"{pg['nslots']} slots, {len(pg['consts'])} constants")
-    texts = {c: emit(programs, c) for c in CURVES}
+    files = {out_path(c, gt): emit(programs, c, gt) for c in CURVES for gt in (False, True)}
     if "--check" in sys.argv:
         good = check(programs)
-        same = all(os.path.exists(out_path(c)) and open(out_path(c)).read() == texts[c] for c in CURVES)
+        same = all(os.path.exists(f) and open(f).read() == t for f, t in files.items())
         print("coop_program_*.inc are", "up to date" if same else "STALE (run tools/gen_coop_pairing.py)")
         sys.exit(0 if good and same else 1)
-    for c in CURVES:
-        open(out_path(c), "w").write(texts[c])
-        print("wrote", out_path(c), len(texts[c]), "bytes, sha256", hashlib.sha256(texts[c].encode()).hexdigest()[:16])
+    for f, t in files.items():
+        open(f, "w").write(t)
+        print("wrote", f, len(t), "bytes, sha256", hashlib.sha256(t.encode()).hexdigest()[:16])
 
 
 if __name__ == "__main__":
