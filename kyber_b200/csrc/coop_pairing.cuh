@@ -19,6 +19,7 @@
 #include "codec.cuh"
 #include "kernels.cuh"
 #include "fp_inv.cuh"
+#include "coop_core.cuh"
 #ifdef B2K_COOP_BLS
 #include "coop_program_bls.inc"
 #endif
@@ -36,53 +37,10 @@
 namespace b2k {
 namespace coop {
 
-// slots of one warp in shared memory, limb-major: word j of slot s at [j * NS + s] (NS odd: lanes on different slots hit different banks)
-template <class P1, class P2> struct Layout {
-  static constexpr int NS = (P1::SLOTS > P2::SLOTS ? P1::SLOTS : P2::SLOTS) | 1;
-  static constexpr size_t BYTES = (size_t)P1::LIMBS * NS * 4;
-};
-
-template <int NS, class C>
-B2K_D void slot_load(Fp<C>& r, const uint32_t* S, uint32_t s) {
-#pragma unroll
-  for (int j = 0; j < C::N; j++) r.v[j] = S[j * NS + s];
-}
-template <int NS, class C>
-B2K_D void slot_store(uint32_t* S, uint32_t s, const Fp<C>& a) {
-#pragma unroll
-  for (int j = 0; j < C::N; j++) S[j * NS + s] = a.v[j];
-}
-
-// one round: decode the lane's word, load operands, compute, store, __syncwarp().  Operations: 1 MUL, 3 ADD, 4 SUB, 7 MULC, 8 INV
-// (the generator encodes a^2, 2 a, -a as a * a, a + a, ZERO - a).  A round holds products only or additions / subtractions only, and
-// the two kinds take SEPARATE, warp-uniform code paths: the product path calls out-of-line functions, and sharing variables with it made
-// the compiler park the operands of every addition round on the stack.
 template <int NS, class C>
 B2K_D void step(uint32_t* S, uint32_t w, const uint32_t* consts) {
-  const uint32_t op = w >> 28, d = (w >> 18) & 511u, a = (w >> 9) & 511u, b = w & 511u;
-  const bool additive = (op == 3 || op == 4);
-  if (__any_sync(0xffffffffu, additive)) {                   // an addition / subtraction round
-    if (additive) {
-      Fp<C> x, y, z;
-      slot_load<NS>(x, S, a);
-      slot_load<NS>(y, S, b);
-      fp_addsub(z, x, y, op == 4);                           // one instruction stream for both (fp.cuh)
-      slot_store<NS>(S, d, z);
-    }
-  } else if (op != 0) {                                      // a product round (or the lone inversion)
-    Fp<C> x, y, z;
-    slot_load<NS>(x, S, a);
-    if (op == 8) {
-      fp_inv_bingcd(z, x);
-    } else {
-      if (op == 7) {
-#pragma unroll
-        for (int j = 0; j < C::N; j++) y.v[j] = consts[b * C::N + j];
-      } else slot_load<NS>(y, S, b);
-      fp_mul(z, x, y);
-    }
-    slot_store<NS>(S, d, z);
-  }
+  const uint32_t op = w >> 28;
+  step_lane<NS, C>(S, w, consts, __any_sync(0xffffffffu, op == 3 || op == 4));
   __syncwarp();
 }
 
