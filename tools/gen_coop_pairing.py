@@ -1,18 +1,24 @@
 #!/usr/bin/env python3
-"""Generate the program tables of the WARP-COOPERATIVE pairings (kyber_b200/csrc/coop_program_{bls,bn254,bn256}.inc).
+"""Generate the program tables of the WARP-COOPERATIVE pairings and GT exponentiation (kyber_b200/csrc/coop_program_*.inc).
 
-Why: the batch kernels run one pairing per thread, so a single Suite.Pair / ValidatePairing (kilic/suite.go:57-75) costs one thread's
-latency (~37 ms).  A pairing is ~20 000 Fp products with a dependency depth of only ~1 000, so one WARP can run one pairing with its
-32 lanes executing independent Fp operations in lock step.  The schedule is static (the loop bits of |x| are public), so it is compiled
-HERE, once: the tower / Miller / final-exponentiation formulas below run over a symbolic field that records every Fp operation, a list
-scheduler packs the operations into rounds of <= 32 (one per lane; long operations = products, short ones = add/sub), a linear-scan
-allocator maps the values to slots of shared memory, and the device side (coop_pairing.cuh) is a 60-line interpreter:
+Why: the batch kernels run one pairing per thread, so a single Suite.Pair / ValidatePairing (kilic/suite.go:57-75; pairing/bn254/suite.go:
+133-144; pairing/bn256/suite.go:99-109) costs one thread's latency (20-26 ms).  A pairing is ~20 000 Fp products with a dependency depth of
+only ~800, so one WARP can run one pairing with its 32 lanes executing independent Fp operations in lock step.  The schedule is static (the
+loop bits of |x| / the digits of 6u + 2 are public), so it is compiled HERE, once per curve (BLS12-381, bn254, bn256): the tower / Miller /
+final-exponentiation formulas below run over a symbolic field that records every Fp operation (exact zeros and ones propagate, so sparse
+operands cost nothing), a list scheduler packs the operations into rounds of <= 32 (one per lane; products and additions never share a
+round; only operations within SLACK of the critical path are eligible, which keeps the number of live values low), a linear-scan allocator
+maps the values to slots of shared memory, and the device side (coop_core.cuh, coop_pairing.cuh) is a 50-line interpreter:
     for every round: lane l decodes word [round][l] -> (op, dst, a, b), loads its operands from shared memory, computes, stores; __syncwarp().
-The SAME formulas run over plain integers and must reproduce the oracle's pairing; the ENCODED program is then interpreted numerically
-(reads of a round before its writes, exactly like the lanes) and must reproduce it again -- `--check`, run by tests/test_coop_program.py.
+Per curve: the 1-pair program (Pair), the 2-pair program (ValidatePairing: shared squarings, one final exponentiation) and the Fp12
+square / product programs that GT.Mul loops over (coop_program_<curve>_gt.inc).
+The SAME formulas run over plain integers and must reproduce the oracle's values; the ENCODED programs are then interpreted numerically
+(reads of a round before its writes, exactly like the lanes) and must reproduce them again -- `--check`, run by tests/test_coop_program.py,
+which also runs the device interpreter's per-lane core under host emulation over the tables.
+Generation needs only public curve parameters (kyber_b200/build.py runs it; the tables are git-ignored); only --check imports the oracle.
 
 Usage:  python tools/gen_coop_pairing.py            # rewrite kyber_b200/csrc/coop_program_*.inc
-        python tools/gen_coop_pairing.py --check    # validate formulas + schedule + encoding against the oracle; exit 1 on mismatch
+        python tools/gen_coop_pairing.py --check    # validate formulas + schedule + encoding against the oracle; exit 1 on mismatch or stale files
 """
 import hashlib
 import os
